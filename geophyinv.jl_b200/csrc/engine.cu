@@ -1,0 +1,973 @@
+// engine.cu -- C-ABI implementation (include/gpifdtd.h) of the B200 FDTD engine.
+//
+// Host side of the drop-in boundary for GeoPhyInv.jl's src/fdtd (citations relative to
+// /root/reference): owns all device memory, converts the reference's per-field arrays to the
+// unified-box layout described in kernels.cuh, and drives the time loop of mod_x_proc!
+// (propagate.jl:138-261) as two fused stencil launches plus one small source/receiver launch per
+// half step.  There is no CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gpifdtd.h"
+#include "kernels.cuh"
+
+using namespace gpi;
+
+namespace {
+
+// ---- field metadata (fields.jl:92-671 reduced to node types, see kernels.cuh) -------------------
+// per axis (z,y,x): 'I' tauii nodes (len n, offset 0), 'V' velocity nodes (n+1, 0), 'H' half (n-1, 1), 'J' inner (n-2, 1)
+const char* field_types(int f) {
+    switch (f) {
+    case GPI_P: case GPI_TAUXX: case GPI_TAUYY: case GPI_TAUZZ:
+    case GPI_DVXDX: case GPI_DVYDY: case GPI_DVZDZ: return "III";
+    case GPI_VX: return "IIV"; case GPI_VY: return "IVI"; case GPI_VZ: return "VII";
+    case GPI_DPDX: case GPI_DTAUXXDX: case GPI_DTAUXYDY: case GPI_DTAUXZDZ: return "JJH";
+    case GPI_DPDY: case GPI_DTAUYYDY: case GPI_DTAUXYDX: case GPI_DTAUYZDZ: return "JHJ";
+    case GPI_DPDZ: case GPI_DTAUZZDZ: case GPI_DTAUXZDX: case GPI_DTAUYZDY: return "HJJ";
+    case GPI_TAUXY: case GPI_DVXDY: case GPI_DVYDX: return "JHH";
+    case GPI_TAUXZ: case GPI_DVXDZ: case GPI_DVZDX: return "HJH";
+    case GPI_TAUYZ: case GPI_DVYDZ: case GPI_DVZDY: return "HHJ";
+    }
+    return nullptr;
+}
+int type_len(char t, int n) { return t == 'I' ? n : t == 'V' ? n + 1 : t == 'H' ? n - 1 : n - 2; }
+int type_off(char t) { return (t == 'H' || t == 'J') ? 1 : 0; }
+bool has_y(int f) {
+    switch (f) {
+    case GPI_VY: case GPI_TAUYY: case GPI_TAUXY: case GPI_TAUYZ: case GPI_DPDY: case GPI_DVYDY:
+    case GPI_DVXDY: case GPI_DVYDX: case GPI_DVYDZ: case GPI_DVZDY: case GPI_DTAUYYDY:
+    case GPI_DTAUXYDX: case GPI_DTAUXYDY: case GPI_DTAUYZDY: case GPI_DTAUYZDZ: return true;
+    }
+    return false;
+}
+bool field_exists(int nd, int phys, int f) {
+    if (f < 0 || f >= GPI_NFIELD || !field_types(f)) return false;
+    if (nd == 2 && has_y(f)) return false;
+    if (phys == GPI_ACOUSTIC) {
+        if (f >= GPI_TAUXX && f <= GPI_TAUYZ) return false;
+        if (f >= GPI_DVXDY && f <= GPI_DVZDY) return false;
+        if (f >= GPI_DTAUXXDX) return false;
+        return true;
+    }
+    return !(f == GPI_P || f == GPI_DPDX || f == GPI_DPDY || f == GPI_DPDZ);
+}
+int field_shape(int nd, int f, const int n[3], int out[3], int off[3]) {
+    const char* t = field_types(f);
+    if (!t || (nd == 2 && has_y(f))) return 1;
+    for (int q = 0; q < 3; q++) {
+        if (q == 1 && nd == 2) { out[q] = 1; off[q] = 0; continue; }
+        out[q] = type_len(t[q], n[q]); off[q] = type_off(t[q]);
+    }
+    return 0;
+}
+int dfield_axis(int f) {
+    switch (f) {
+    case GPI_DPDX: case GPI_DVXDX: case GPI_DVYDX: case GPI_DVZDX:
+    case GPI_DTAUXXDX: case GPI_DTAUXYDX: case GPI_DTAUXZDX: return 2;
+    case GPI_DPDY: case GPI_DVYDY: case GPI_DVXDY: case GPI_DVZDY:
+    case GPI_DTAUYYDY: case GPI_DTAUXYDY: case GPI_DTAUYZDY: return 1;
+    case GPI_DPDZ: case GPI_DVZDZ: case GPI_DVXDZ: case GPI_DVYDZ:
+    case GPI_DTAUZZDZ: case GPI_DTAUXZDZ: case GPI_DTAUYZDZ: return 0;
+    }
+    return -1;
+}
+// wavefield -> (is velocity?, slot)
+bool wf_slot(int f, bool& isv, int& slot) {
+    switch (f) {
+    case GPI_P: case GPI_TAUXX: isv = false; slot = T_XX; return true;
+    case GPI_TAUYY: isv = false; slot = T_YY; return true;
+    case GPI_TAUZZ: isv = false; slot = T_ZZ; return true;
+    case GPI_TAUXY: isv = false; slot = T_XY; return true;
+    case GPI_TAUXZ: isv = false; slot = T_XZ; return true;
+    case GPI_TAUYZ: isv = false; slot = T_YZ; return true;
+    case GPI_VX: isv = true; slot = V_X; return true;
+    case GPI_VY: isv = true; slot = V_Y; return true;
+    case GPI_VZ: isv = true; slot = V_Z; return true;
+    }
+    return false;
+}
+
+// ---- per-(pw, shot, field) acquisition data ------------------------------------------------------
+struct SparseDev {
+    bool set = false;
+    int ncol = 0, nnz = 0, nrows = 0;
+    int *colptr = nullptr, *tap_cell = nullptr;   float* tap_val = nullptr;                 // receiver view (CSC order)
+    int *row_cell = nullptr, *row_ptr = nullptr, *ent_col = nullptr;  float* ent_val = nullptr;   // injection view (row lists)
+};
+struct ShotData {
+    SparseDev spray[GPI_NWAVEFIELD], interp[GPI_NWAVEFIELD];
+    float* wav[GPI_NWAVEFIELD] = {};  int ns[GPI_NWAVEFIELD] = {};
+    float* rec[GPI_NWAVEFIELD] = {};  int nr[GPI_NWAVEFIELD] = {};
+    float* bnd[GPI_NWAVEFIELD][3] = {};          // [nt][slot] boundary planes (pw 1 only)
+    float* snap[GPI_NWAVEFIELD] = {};            // final-state snapshots (pw 1 only), unified volumes
+    std::vector<float*> usnaps;                  // user snapshots, unified volumes
+};
+
+struct Id128 { char b[128]; };     // ncclUniqueId is 128 opaque bytes, passed by value
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+}  // namespace
+
+struct gpi_handle {
+    gpi_config c;
+    Geom g;
+    int nd, el, npw, B;                 // B = shot batch
+    int device;
+    cudaStream_t stream = nullptr;  bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    // wavefields: W[b][pw][slot][vol]; TP same shape (adjoint only)
+    int slot_tau[6], slot_v[3], nslots;
+    float *W = nullptr, *TP = nullptr;
+    long long pwstride, bstride;
+    // CPML memory: one block per (b, pw) holding all terms
+    struct Term { int dfield; int axis; long long off; long long size; bool vel; int idx; };
+    std::vector<Term> terms;  long long mem_per_pw = 0;  float* MEM = nullptr;
+    float* pmlcoef = nullptr;           // [GPI_NFIELD][3][2*npml]
+    // medium
+    float* mod[GPI_NPARAM] = {};        // unified volumes
+    float* dmod[C_N] = {};  float** dmod_table = nullptr;
+    // gradients (acoustic 2-D): total + per batch slot
+    float* gtot[GPI_NPARAM] = {};  float* gshot = nullptr;   // gshot[b][2][vol]
+    std::vector<ShotData> shots[2];
+    std::vector<int32_t> itsnaps;
+    PostDesc *post_v = nullptr, *post_s = nullptr, *h_post_v = nullptr, *h_post_s = nullptr;
+    float* stage = nullptr;  size_t stage_floats = 0;       // pinned host staging
+    gpi_timers timers{};
+    // tuning
+    dim3 blk3{64, 2, 2}, blk2{128, 2, 1};
+    // nccl
+    NcclApi nccl;  void* comm = nullptr;  int rank = 0, nranks = 1;
+};
+
+static std::string g_create_err;
+
+#define FAIL(h, ...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); (h)->err = _b; return 1; } while (0)
+#define CU(h, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { char _b[512]; \
+    snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); (h)->err = _b; return 1; } } while (0)
+#define GUARD(h) do { if (!(h)) return 1; if (cudaSetDevice((h)->device) != cudaSuccess) { (h)->err = "cudaSetDevice failed"; return 1; } } while (0)
+
+namespace {
+
+float* wf_ptr(gpi_handle* h, float* base, int b, int ipw, int f) {
+    bool isv; int slot;
+    if (!wf_slot(f, isv, slot)) return nullptr;
+    int s = isv ? h->slot_v[slot] : h->slot_tau[slot];
+    if (s < 0) return nullptr;
+    return base + (long long)b * h->bstride + (long long)ipw * h->pwstride + (long long)s * h->g.vol;
+}
+
+int ensure_stage(gpi_handle* h, size_t nfloats) {
+    if (h->stage_floats >= nfloats) return 0;
+    if (h->stage) cudaFreeHost(h->stage);
+    h->stage = nullptr; h->stage_floats = 0;
+    CU(h, cudaMallocHost((void**)&h->stage, nfloats * sizeof(float)));
+    h->stage_floats = nfloats;
+    return 0;
+}
+
+// host array in the field's own shape (column-major [z,(y),x]) <-> unified volume on the device
+int upload_field(gpi_handle* h, int f, const float* src, float* dvol) {
+    int n[3] = {h->g.nz, h->g.ny, h->g.nx}, sh[3], off[3];
+    if (field_shape(h->nd, f, n, sh, off)) FAIL(h, "field %d has no shape in %d-D", f, h->nd);
+    if (ensure_stage(h, (size_t)h->g.vol)) return 1;
+    memset(h->stage, 0, (size_t)h->g.vol * sizeof(float));
+    for (int ix = 0; ix < sh[2]; ix++) for (int iy = 0; iy < sh[1]; iy++) {
+        const float* s = src + (size_t)sh[0] * ((size_t)iy + (size_t)sh[1] * ix);
+        float* d = h->stage + off[0] + (size_t)h->g.pz * ((size_t)(iy + off[1]) + (size_t)h->g.ny1 * (ix + off[2]));
+        memcpy(d, s, (size_t)sh[0] * sizeof(float));
+    }
+    CU(h, cudaMemcpyAsync(dvol, h->stage, (size_t)h->g.vol * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int download_field(gpi_handle* h, int f, const float* dvol, float* dst) {
+    int n[3] = {h->g.nz, h->g.ny, h->g.nx}, sh[3], off[3];
+    if (field_shape(h->nd, f, n, sh, off)) FAIL(h, "field %d has no shape in %d-D", f, h->nd);
+    if (ensure_stage(h, (size_t)h->g.vol)) return 1;
+    CU(h, cudaMemcpyAsync(h->stage, dvol, (size_t)h->g.vol * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (int ix = 0; ix < sh[2]; ix++) for (int iy = 0; iy < sh[1]; iy++) {
+        float* d = dst + (size_t)sh[0] * ((size_t)iy + (size_t)sh[1] * ix);
+        const float* s = h->stage + off[0] + (size_t)h->g.pz * ((size_t)(iy + off[1]) + (size_t)h->g.ny1 * (ix + off[2]));
+        memcpy(d, s, (size_t)sh[0] * sizeof(float));
+    }
+    return 0;
+}
+
+void free_sparse(SparseDev& s) {
+    cudaFree(s.colptr); cudaFree(s.tap_cell); cudaFree(s.tap_val);
+    cudaFree(s.row_cell); cudaFree(s.row_ptr); cudaFree(s.ent_col); cudaFree(s.ent_val);
+    s = SparseDev();
+}
+
+template <typename T>
+int to_device(gpi_handle* h, T** d, const std::vector<T>& v) {
+    *d = nullptr;
+    CU(h, cudaMalloc((void**)d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) CU(h, cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+dim3 grid_for(const gpi_handle* h, dim3 blk, int nbatch) {
+    const Geom& g = h->g;
+    if (h->nd == 3) {
+        int ntx = (g.nx1 + blk.z - 1) / blk.z;
+        return dim3((g.nz + 1 + blk.x - 1) / blk.x, (g.ny1 + blk.y - 1) / blk.y, ntx * nbatch);
+    }
+    return dim3((g.nz + 1 + blk.x - 1) / blk.x, (g.nx1 + blk.y - 1) / blk.y, nbatch);
+}
+
+void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch) {
+    memset(&a, 0, sizeof a);
+    for (int s = 0; s < 6; s++) a.tau[s] = h->slot_tau[s] >= 0 ? h->W + (long long)ipw * h->pwstride + (long long)h->slot_tau[s] * h->g.vol : nullptr;
+    for (int s = 0; s < 3; s++) a.v[s] = h->slot_v[s] >= 0 ? h->W + (long long)ipw * h->pwstride + (long long)h->slot_v[s] * h->g.vol : nullptr;
+    for (int s = 0; s < C_N; s++) a.c[s] = h->dmod[s];
+    const int np2 = 2 * h->c.npml;
+    for (const auto& t : h->terms) {
+        PmlTerm p;
+        p.mem = h->MEM + (long long)ipw * h->mem_per_pw + t.off;
+        p.a = h->pmlcoef + ((size_t)t.dfield * 3 + 0) * np2;
+        p.b = h->pmlcoef + ((size_t)t.dfield * 3 + 1) * np2;
+        p.kI = h->pmlcoef + ((size_t)t.dfield * 3 + 2) * np2;
+        p.bstride = (long long)h->npw * h->mem_per_pw;
+        (t.vel ? a.pv : a.ps)[t.idx] = p;
+    }
+    a.wstride = h->bstride;
+    a.nbatch = nbatch;
+}
+
+template <int ND, int EL>
+void launch_step_kernels(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
+    dim3 blk = ND == 3 ? h->blk3 : h->blk2;
+    dim3 grd = grid_for(h, blk, nbatch);
+    if (vel) k_vel<ND, EL><<<grd, blk, 0, h->stream>>>(h->g, a);
+    else     k_stress<ND, EL><<<grd, blk, 0, h->stream>>>(h->g, a);
+}
+void launch_step(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
+    if (h->nd == 2 && !h->el) launch_step_kernels<2, 0>(h, a, vel, nbatch);
+    else if (h->nd == 2)      launch_step_kernels<2, 1>(h, a, vel, nbatch);
+    else if (!h->el)          launch_step_kernels<3, 0>(h, a, vel, nbatch);
+    else                      launch_step_kernels<3, 1>(h, a, vel, nbatch);
+    h->timers.launches += 1;
+}
+
+// boundary-stored fields (boundary.jl:113-264)
+int boundary_fields(const gpi_handle* h, int out[3]) {
+    if (!h->el) { out[0] = GPI_P; return 1; }
+    out[0] = GPI_TAUXX; out[1] = GPI_TAUXZ; out[2] = GPI_TAUZZ; return 3;
+}
+long long bnd_slot_floats(const gpi_handle* h, int axis) {
+    const Geom& g = h->g; const int nb2 = 2 * h->c.nbound;
+    if (axis == 2) return (long long)g.pz * g.ny1 * nb2;
+    if (axis == 1) return (long long)g.pz * nb2 * g.nx1;
+    return (long long)g.nx1 * g.ny1 * nb2;
+}
+int launch_boundary(gpi_handle* h, bool save, int f, float* field, float* store, int axis) {
+    const Geom& g = h->g;
+    int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
+    field_shape(h->nd, f, n, sh, off);
+    const int minbit = axis == 0 ? ZMIN : axis == 1 ? YMIN : XMIN;
+    const int np = (h->c.pml_faces & minbit) ? h->c.npml : 0;       // min-face flag also used for the max side (boundary.jl:24,33)
+    const int nb = h->c.nbound;
+    const int lo = np + off[axis], hi = sh[axis] - np - nb + off[axis];
+    if (hi < lo) FAIL(h, "grid too small for the boundary store along axis %d", axis);
+    dim3 blk, grd;
+    if (axis == 2)      { blk = dim3(128, 1, 1); grd = dim3((g.pz + 127) / 128, g.ny1, 2 * nb); }
+    else if (axis == 1) { blk = dim3(128, 1, 1); grd = dim3((g.pz + 127) / 128, 2 * nb, g.nx1); }
+    else                { blk = dim3(128, 1, 1); grd = dim3((g.nx1 + 127) / 128, g.ny1, 2 * nb); }
+    const int k0 = off[0], j0 = off[1], i0 = off[2];
+    const int nk = off[0] + sh[0], nj = off[1] + sh[1], ni = off[2] + sh[2];
+    if (save) k_boundary<1><<<grd, blk, 0, h->stream>>>(g, field, store, axis, lo, hi, nb, nk, nj, ni, k0, j0, i0);
+    else      k_boundary<0><<<grd, blk, 0, h->stream>>>(g, field, store, axis, lo, hi, nb, nk, nj, ni, k0, j0, i0);
+    h->timers.launches += 1;
+    return 0;
+}
+
+__global__ void k_negate_copy(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dst[t] = __fmul_rn(src[t], -1.0f);
+}
+
+}  // namespace
+
+// =================================================================================================
+// lifecycle
+// =================================================================================================
+extern "C" int gpi_abi_version(void) { return GPI_ABI_VERSION; }
+
+extern "C" const char* gpi_last_error(const gpi_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int gpi_field_shape(int ndims, int physics, int field_id, const int32_t n[3], int32_t out[3]) {
+    if (!field_exists(ndims, physics, field_id)) return 1;
+    int nn[3] = {n[0], ndims == 3 ? n[1] : 1, n[2]}, o[3], off[3];
+    if (field_shape(ndims, field_id, nn, o, off)) return 1;
+    out[0] = o[0]; out[1] = o[1]; out[2] = o[2];
+    return 0;
+}
+
+static int create_impl(gpi_handle* h) {
+    const gpi_config& c = h->c;
+    Geom& g = h->g;
+    g.nz = c.n[0]; g.ny = h->nd == 3 ? c.n[1] : 1; g.nx = c.n[2];
+    g.pz = ((g.nz + 1 + 31) / 32) * 32;
+    g.ny1 = h->nd == 3 ? g.ny + 1 : 1;
+    g.nx1 = g.nx + 1;
+    g.npml = c.npml;
+    g.pzm = ((2 * c.npml + 31) / 32) * 32;
+    g.pml = c.pml_faces; g.rigid = c.rigid_faces; g.freesurf = c.stressfree_faces;
+    g.dzI = (float)c.dI[0]; g.dyI = (float)c.dI[1]; g.dxI = (float)c.dI[2];
+    g.vol = (long long)g.pz * g.ny1 * g.nx1;
+    if (g.vol >= (1LL << 31)) FAIL(h, "grid of %lld unified cells exceeds the 32-bit cell index of the source/receiver tables", g.vol);
+    // the min and max CPML slabs of a derivative field must not overlap (the reference would apply both)
+    for (int q = 0; q < 3; q++) {
+        if (q == 1 && h->nd == 2) continue;
+        const int lo = q == 0 ? ZMIN : q == 1 ? YMIN : XMIN, hi = q == 0 ? ZMAX : q == 1 ? YMAX : XMAX;
+        if ((c.pml_faces & lo) && (c.pml_faces & hi) && c.n[q] - 2 < 2 * c.npml)
+            FAIL(h, "axis %d: %d nodes cannot hold two %d-cell CPML slabs", q, c.n[q], c.npml);
+        if ((c.pml_faces & (lo | hi)) && c.n[q] - 2 < c.npml) FAIL(h, "axis %d shorter than the CPML slab", q);
+    }
+
+    // wavefield slots
+    for (int s = 0; s < 6; s++) h->slot_tau[s] = -1;
+    for (int s = 0; s < 3; s++) h->slot_v[s] = -1;
+    int ns = 0;
+    if (!h->el) h->slot_tau[T_XX] = ns++;
+    else {
+        h->slot_tau[T_XX] = ns++; if (h->nd == 3) h->slot_tau[T_YY] = ns++; h->slot_tau[T_ZZ] = ns++;
+        if (h->nd == 3) h->slot_tau[T_XY] = ns++;
+        h->slot_tau[T_XZ] = ns++;
+        if (h->nd == 3) h->slot_tau[T_YZ] = ns++;
+    }
+    h->slot_v[V_X] = ns++; if (h->nd == 3) h->slot_v[V_Y] = ns++; h->slot_v[V_Z] = ns++;
+    h->nslots = ns;
+    h->pwstride = (long long)ns * g.vol;
+    h->bstride = (long long)h->npw * h->pwstride;
+
+    // shot batch: 2-D problems are tiny and launch-bound, so several shots share every launch
+    int B = c.shot_batch > 0 ? c.shot_batch : (h->nd == 2 ? 16 : 1);
+    B = std::max(1, std::min(B, c.nshots));
+    h->B = B;
+
+    // CPML terms (cpml.jl:109-120: one memory array per derivative field)
+    struct TD { int f; bool vel; int idx; };
+    std::vector<TD> td;
+    if (!h->el) {
+        td = {{GPI_DPDX, true, 0}, {GPI_DPDZ, true, 2}, {GPI_DVXDX, false, 0}, {GPI_DVZDZ, false, 2}};
+        if (h->nd == 3) { td.push_back({GPI_DPDY, true, 1}); td.push_back({GPI_DVYDY, false, 1}); }
+    } else if (h->nd == 2) {
+        td = {{GPI_DTAUXXDX, true, 0}, {GPI_DTAUXZDZ, true, 2}, {GPI_DTAUXZDX, true, 6}, {GPI_DTAUZZDZ, true, 8},
+              {GPI_DVXDX, false, 0}, {GPI_DVZDZ, false, 2}, {GPI_DVXDZ, false, 5}, {GPI_DVZDX, false, 6}};
+    } else {
+        td = {{GPI_DTAUXXDX, true, 0}, {GPI_DTAUXYDY, true, 1}, {GPI_DTAUXZDZ, true, 2},
+              {GPI_DTAUXYDX, true, 3}, {GPI_DTAUYYDY, true, 4}, {GPI_DTAUYZDZ, true, 5},
+              {GPI_DTAUXZDX, true, 6}, {GPI_DTAUYZDY, true, 7}, {GPI_DTAUZZDZ, true, 8},
+              {GPI_DVXDX, false, 0}, {GPI_DVYDY, false, 1}, {GPI_DVZDZ, false, 2},
+              {GPI_DVXDY, false, 3}, {GPI_DVYDX, false, 4}, {GPI_DVXDZ, false, 5}, {GPI_DVZDX, false, 6},
+              {GPI_DVYDZ, false, 7}, {GPI_DVZDY, false, 8}};
+    }
+    long long off = 0;
+    for (auto& t : td) {
+        gpi_handle::Term T;
+        T.dfield = t.f; T.axis = dfield_axis(t.f); T.vel = t.vel; T.idx = t.idx; T.off = off;
+        const int minbit = T.axis == 0 ? ZMIN : T.axis == 1 ? YMIN : XMIN, maxbit = minbit << 1;
+        if (!(c.pml_faces & (minbit | maxbit))) T.size = 32;    // never touched
+        else if (T.axis == 2) T.size = (long long)g.pz * g.ny1 * 2 * c.npml;
+        else if (T.axis == 1) T.size = (long long)g.pz * 2 * c.npml * g.nx1;
+        else T.size = (long long)g.pzm * g.ny1 * g.nx1;
+        off += (T.size + 31) / 32 * 32;
+        h->terms.push_back(T);
+    }
+    h->mem_per_pw = off;
+
+    CU(h, cudaMalloc((void**)&h->W, (size_t)B * h->bstride * sizeof(float)));
+    CU(h, cudaMemset(h->W, 0, (size_t)B * h->bstride * sizeof(float)));
+    if (h->npw == 2) {
+        CU(h, cudaMalloc((void**)&h->TP, (size_t)B * h->bstride * sizeof(float)));
+        CU(h, cudaMemset(h->TP, 0, (size_t)B * h->bstride * sizeof(float)));
+    }
+    CU(h, cudaMalloc((void**)&h->MEM, (size_t)B * h->npw * h->mem_per_pw * sizeof(float)));
+    CU(h, cudaMemset(h->MEM, 0, (size_t)B * h->npw * h->mem_per_pw * sizeof(float)));
+
+    // CPML coefficients: a = b = 0, kI = 1 until update_pml! (cpml.jl:114)
+    const int np2 = 2 * c.npml;
+    std::vector<float> coef((size_t)GPI_NFIELD * 3 * np2, 0.f);
+    for (int f = 0; f < GPI_NFIELD; f++) for (int i = 0; i < np2; i++) coef[((size_t)f * 3 + 2) * np2 + i] = 1.f;
+    if (to_device(h, &h->pmlcoef, coef)) return 1;
+
+    // medium
+    const size_t vb = (size_t)g.vol * sizeof(float);
+    auto alloc_vol = [&](float** p) -> int { CU(h, cudaMalloc((void**)p, vb)); CU(h, cudaMemset(*p, 0, vb)); return 0; };
+    if (alloc_vol(&h->mod[GPI_RHO])) return 1;
+    if (!h->el) { if (alloc_vol(&h->mod[GPI_INVK])) return 1; }
+    else { if (alloc_vol(&h->mod[GPI_INVLAMBDA]) || alloc_vol(&h->mod[GPI_INVMU])) return 1; }
+    int need[C_N] = {1, h->nd == 3, 1, 1, h->el, h->el, h->el && h->nd == 3, h->el && h->nd == 3};
+    for (int s = 0; s < C_N; s++) if (need[s]) { if (alloc_vol(&h->dmod[s])) return 1; }
+    CU(h, cudaMalloc((void**)&h->dmod_table, C_N * sizeof(float*)));
+    CU(h, cudaMemcpy(h->dmod_table, h->dmod, C_N * sizeof(float*), cudaMemcpyHostToDevice));
+
+    // gradients exist upstream for acoustic media (fdtd.jl:164-170); imaging only in 2-D (gradient.jl:31)
+    if (!h->el && h->npw == 2) {
+        if (alloc_vol(&h->gtot[GPI_INVK]) || alloc_vol(&h->gtot[GPI_RHO])) return 1;
+        CU(h, cudaMalloc((void**)&h->gshot, (size_t)B * 2 * vb));
+        CU(h, cudaMemset(h->gshot, 0, (size_t)B * 2 * vb));
+    }
+
+    // per-shot state
+    for (int ipw = 0; ipw < h->npw; ipw++) h->shots[ipw].resize(c.nshots);
+    int bf[3]; const int nbf = boundary_fields(h, bf);
+    for (int is = 0; is < c.nshots; is++) {
+        ShotData& s = h->shots[0][is];
+        if (c.store_boundary) {
+            for (int i = 0; i < nbf; i++) {
+                for (int q = 0; q < 3; q++) {
+                    if (q == 1 && h->nd == 2) continue;
+                    size_t nb = (size_t)bnd_slot_floats(h, q) * c.nt * sizeof(float);
+                    CU(h, cudaMalloc((void**)&s.bnd[bf[i]][q], nb));
+                    CU(h, cudaMemset(s.bnd[bf[i]][q], 0, nb));
+                }
+                if (alloc_vol(&s.snap[bf[i]])) return 1;
+            }
+            const int vf[3] = {GPI_VX, GPI_VY, GPI_VZ};
+            for (int i = 0; i < 3; i++) if (field_exists(h->nd, c.physics, vf[i])) { if (alloc_vol(&s.snap[vf[i]])) return 1; }
+        }
+        if (c.nsnaps > 0) for (int ipw = 0; ipw < h->npw; ipw++) {
+            h->shots[ipw][is].usnaps.resize(c.nsnaps, nullptr);
+            for (int k = 0; k < c.nsnaps; k++) if (alloc_vol(&h->shots[ipw][is].usnaps[k])) return 1;
+        }
+    }
+    CU(h, cudaMalloc((void**)&h->post_v, (size_t)B * sizeof(PostDesc)));
+    CU(h, cudaMalloc((void**)&h->post_s, (size_t)B * sizeof(PostDesc)));
+    CU(h, cudaMallocHost((void**)&h->h_post_v, (size_t)B * sizeof(PostDesc)));
+    CU(h, cudaMallocHost((void**)&h->h_post_s, (size_t)B * sizeof(PostDesc)));
+    CU(h, cudaEventCreate(&h->ev0));
+    CU(h, cudaEventCreate(&h->ev1));
+    return 0;
+}
+
+extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
+    if (!cfg || !out) { g_create_err = "gpi_create: null argument"; return 1; }
+    *out = nullptr;
+    if (cfg->abi_version != GPI_ABI_VERSION) { g_create_err = "gpi_create: ABI version mismatch"; return 1; }
+    if (cfg->order != 2) { g_create_err = "gpi_create: only order 2 is implemented (orders 6/8 are broken upstream, order 4 is a later row)"; return 1; }
+    if (cfg->ndims != 2 && cfg->ndims != 3) { g_create_err = "gpi_create: ndims must be 2 or 3"; return 1; }
+    if (cfg->physics != GPI_ACOUSTIC && cfg->physics != GPI_ELASTIC) { g_create_err = "gpi_create: unknown physics"; return 1; }
+    if (cfg->npw < 1 || cfg->npw > 2 || cfg->nshots < 1 || cfg->nt < 1 || cfg->npml < 1 || cfg->nbound < 1 || cfg->nbound > 4) { g_create_err = "gpi_create: bad npw/nshots/nt/npml/nbound"; return 1; }
+    if (cfg->n[0] < 4 || cfg->n[2] < 4 || (cfg->ndims == 3 && cfg->n[1] < 4)) { g_create_err = "gpi_create: grid too small"; return 1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_create_err = "gpi_create: no CUDA device (this engine has no CPU fallback)"; return 1; }
+    gpi_handle* h = new gpi_handle();
+    h->c = *cfg; h->nd = cfg->ndims; h->el = cfg->physics == GPI_ELASTIC; h->npw = cfg->npw;
+    if (cfg->device >= 0) h->device = cfg->device; else cudaGetDevice(&h->device);
+    if (cudaSetDevice(h->device) != cudaSuccess) { g_create_err = "gpi_create: cudaSetDevice failed"; delete h; return 1; }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_err = "gpi_create: stream creation failed"; delete h; return 1; }
+    h->own_stream = true;
+    if (const char* e = getenv("GPI_BLOCK3")) { int a, b, c3; if (sscanf(e, "%d,%d,%d", &a, &b, &c3) == 3 && a * b * c3 <= 256) h->blk3 = dim3(a, b, c3); }
+    if (const char* e = getenv("GPI_BLOCK2")) { int a, b; if (sscanf(e, "%d,%d", &a, &b) == 2 && a * b <= 256) h->blk2 = dim3(a, b, 1); }
+    if (create_impl(h)) { g_create_err = "gpi_create: " + h->err; gpi_destroy(h); return 1; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int gpi_destroy(gpi_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
+    cudaFree(h->W); cudaFree(h->TP); cudaFree(h->MEM); cudaFree(h->pmlcoef);
+    for (auto& p : h->mod) cudaFree(p);
+    for (auto& p : h->dmod) cudaFree(p);
+    cudaFree(h->dmod_table);
+    for (auto& p : h->gtot) cudaFree(p);
+    cudaFree(h->gshot);
+    for (int ipw = 0; ipw < 2; ipw++) for (auto& s : h->shots[ipw]) {
+        for (int f = 0; f < GPI_NWAVEFIELD; f++) {
+            free_sparse(s.spray[f]); free_sparse(s.interp[f]);
+            cudaFree(s.wav[f]); cudaFree(s.rec[f]); cudaFree(s.snap[f]);
+            for (int q = 0; q < 3; q++) cudaFree(s.bnd[f][q]);
+        }
+        for (auto p : s.usnaps) cudaFree(p);
+    }
+    cudaFree(h->post_v); cudaFree(h->post_s);
+    if (h->h_post_v) cudaFreeHost(h->h_post_v);
+    if (h->h_post_s) cudaFreeHost(h->h_post_s);
+    if (h->stage) cudaFreeHost(h->stage);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" int gpi_set_stream(gpi_handle* h, void* s) {
+    GUARD(h);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)s; h->own_stream = false;
+    return 0;
+}
+extern "C" int gpi_synchronize(gpi_handle* h) { GUARD(h); CU(h, cudaStreamSynchronize(h->stream)); return 0; }
+
+// =================================================================================================
+// medium, CPML, acquisition, wavelets
+// =================================================================================================
+extern "C" int gpi_set_medium(gpi_handle* h, int p, const float* a) {
+    GUARD(h);
+    if (p < 0 || p >= GPI_NPARAM || !h->mod[p]) FAIL(h, "medium parameter %d is not part of this physics", p);
+    if (!a) FAIL(h, "null medium array");
+    return upload_field(h, h->el ? GPI_TAUXX : GPI_P, a, h->mod[p]);
+}
+extern "C" int gpi_get_medium(gpi_handle* h, int p, float* out) {
+    GUARD(h);
+    if (p < 0 || p >= GPI_NPARAM || !h->mod[p]) FAIL(h, "medium parameter %d is not part of this physics", p);
+    return download_field(h, h->el ? GPI_TAUXX : GPI_P, h->mod[p], out);
+}
+extern "C" int gpi_update_dmod(gpi_handle* h) {
+    GUARD(h);
+    dim3 blk = h->nd == 3 ? h->blk3 : h->blk2, grd = grid_for(h, blk, 1);
+    const float dt = (float)h->c.dt;
+    const float* m0 = h->el ? h->mod[GPI_INVLAMBDA] : h->mod[GPI_INVK];
+    if (h->nd == 2 && !h->el) k_dmod<2, 0><<<grd, blk, 0, h->stream>>>(h->g, m0, h->mod[GPI_RHO], nullptr, h->dmod_table, dt);
+    else if (h->nd == 2)      k_dmod<2, 1><<<grd, blk, 0, h->stream>>>(h->g, m0, h->mod[GPI_RHO], h->mod[GPI_INVMU], h->dmod_table, dt);
+    else if (!h->el)          k_dmod<3, 0><<<grd, blk, 0, h->stream>>>(h->g, m0, h->mod[GPI_RHO], nullptr, h->dmod_table, dt);
+    else                      k_dmod<3, 1><<<grd, blk, 0, h->stream>>>(h->g, m0, h->mod[GPI_RHO], h->mod[GPI_INVMU], h->dmod_table, dt);
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int gpi_set_pml(gpi_handle* h, int f, const float* a, const float* b, const float* kI) {
+    GUARD(h);
+    if (f < GPI_NWAVEFIELD || !field_exists(h->nd, h->c.physics, f)) FAIL(h, "field %d is not a derivative field of this physics", f);
+    const size_t np2 = 2 * h->c.npml;
+    CU(h, cudaMemcpy(h->pmlcoef + ((size_t)f * 3 + 0) * np2, a, np2 * sizeof(float), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->pmlcoef + ((size_t)f * 3 + 1) * np2, b, np2 * sizeof(float), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->pmlcoef + ((size_t)f * 3 + 2) * np2, kI, np2 * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int gpi_set_sparse(gpi_handle* h, int kind, int ipw, int issp, int f, int ncol,
+                              const int64_t* colptr, const int64_t* rowval, const float* nzval) {
+    GUARD(h);
+    if (ipw < 0 || ipw >= h->npw || issp < 0 || issp >= h->c.nshots) FAIL(h, "bad pw/shot index (%d, %d)", ipw, issp);
+    if (f < 0 || f >= GPI_NWAVEFIELD || !field_exists(h->nd, h->c.physics, f)) FAIL(h, "field %d is not a wavefield of this physics", f);
+    if (kind != GPI_SPRAY && kind != GPI_INTERP) FAIL(h, "kind must be GPI_SPRAY or GPI_INTERP");
+    if (ncol < 0 || !colptr || (ncol > 0 && (!rowval || !nzval))) FAIL(h, "null sparse arrays");
+    ShotData& s = h->shots[ipw][issp];
+    SparseDev& m = kind == GPI_SPRAY ? s.spray[f] : s.interp[f];
+    free_sparse(m);
+    const Geom& g = h->g;
+    int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
+    field_shape(h->nd, f, n, sh, off);
+    const long long flen = (long long)sh[0] * sh[1] * sh[2];
+    const int64_t nnz = colptr[ncol] - 1;
+    std::vector<int> cp(ncol + 1), cell(nnz);
+    std::vector<float> val(nnz);
+    bool isv; int slot; wf_slot(f, isv, slot);
+    std::map<int, std::vector<std::pair<int, float>>> rows;
+    for (int jcol = 0; jcol < ncol; jcol++) {
+        cp[jcol] = (int)(colptr[jcol] - 1);
+        if (colptr[jcol + 1] < colptr[jcol]) FAIL(h, "colptr not monotone");
+        for (int64_t e = colptr[jcol] - 1; e < colptr[jcol + 1] - 1; e++) {
+            const int64_t r = rowval[e] - 1;
+            if (r < 0 || r >= flen) FAIL(h, "row index %lld outside the field array of %lld entries", (long long)rowval[e], flen);
+            const int iz = (int)(r % sh[0]), iy = (int)((r / sh[0]) % sh[1]), ix = (int)(r / ((long long)sh[0] * sh[1]));
+            const int k = iz + off[0], j = iy + off[1], i = ix + off[2];
+            cell[e] = (int)((long long)k + (long long)g.pz * (j + (long long)g.ny1 * i));
+            val[e] = nzval[e];
+            // injection view: velocity sources only act on the @inn range (source.jl:166-177)
+            bool ok = true;
+            if (isv) {
+                const bool iny = h->nd == 2 || (j >= 1 && j <= g.ny - 2), inyh = h->nd == 2 || (j >= 1 && j <= g.ny - 1);
+                if (slot == V_X) ok = k >= 1 && k <= g.nz - 2 && iny && i >= 1 && i <= g.nx - 1;
+                if (slot == V_Z) ok = k >= 1 && k <= g.nz - 1 && iny && i >= 1 && i <= g.nx - 2;
+                if (slot == V_Y) ok = k >= 1 && k <= g.nz - 2 && inyh && i >= 1 && i <= g.nx - 2;
+            }
+            if (ok) rows[cell[e]].push_back({jcol, nzval[e]});
+        }
+    }
+    cp[ncol] = (int)nnz;
+    std::vector<int> rc, rp{0}, ec; std::vector<float> ev;
+    for (auto& kv : rows) {
+        rc.push_back(kv.first);
+        for (auto& e : kv.second) { ec.push_back(e.first); ev.push_back(e.second); }
+        rp.push_back((int)ec.size());
+    }
+    m.ncol = ncol; m.nnz = (int)nnz; m.nrows = (int)rc.size();
+    if (to_device(h, &m.colptr, cp) || to_device(h, &m.tap_cell, cell) || to_device(h, &m.tap_val, val) ||
+        to_device(h, &m.row_cell, rc) || to_device(h, &m.row_ptr, rp) || to_device(h, &m.ent_col, ec) || to_device(h, &m.ent_val, ev)) return 1;
+    m.set = true;
+    if (kind == GPI_INTERP) {
+        cudaFree(s.rec[f]); s.rec[f] = nullptr; s.nr[f] = ncol;
+        const size_t nb = (size_t)h->c.nt * std::max(ncol, 1) * sizeof(float);
+        CU(h, cudaMalloc((void**)&s.rec[f], nb));
+        CU(h, cudaMemset(s.rec[f], 0, nb));
+    }
+    return 0;
+}
+
+extern "C" int gpi_set_wavelets(gpi_handle* h, int ipw, int issp, int f, int ns, const float* w) {
+    GUARD(h);
+    if (ipw < 0 || ipw >= h->npw || issp < 0 || issp >= h->c.nshots) FAIL(h, "bad pw/shot index (%d, %d)", ipw, issp);
+    if (f < 0 || f >= GPI_NWAVEFIELD || !field_exists(h->nd, h->c.physics, f)) FAIL(h, "field %d is not a wavefield of this physics", f);
+    ShotData& s = h->shots[ipw][issp];
+    cudaFree(s.wav[f]); s.wav[f] = nullptr; s.ns[f] = 0;
+    if (!w || ns <= 0) return 0;           // removes the source field
+    const size_t nb = (size_t)h->c.nt * ns * sizeof(float);
+    CU(h, cudaMalloc((void**)&s.wav[f], nb));
+    CU(h, cudaMemcpy(s.wav[f], w, nb, cudaMemcpyHostToDevice));
+    s.ns[f] = ns;
+    return 0;
+}
+
+extern "C" int gpi_set_snap_steps(gpi_handle* h, int nsnaps, const int32_t* its) {
+    GUARD(h);
+    if (nsnaps != h->c.nsnaps) FAIL(h, "nsnaps differs from the configuration");
+    h->itsnaps.assign(its, its + nsnaps);
+    return 0;
+}
+
+extern "C" int gpi_reset(gpi_handle* h, int what) {
+    GUARD(h);
+    const size_t vb = (size_t)h->g.vol * sizeof(float);
+    if (what & GPI_RESET_WAVEFIELDS) {
+        CU(h, cudaMemsetAsync(h->W, 0, (size_t)h->B * h->bstride * sizeof(float), h->stream));
+        if (h->TP) CU(h, cudaMemsetAsync(h->TP, 0, (size_t)h->B * h->bstride * sizeof(float), h->stream));
+        CU(h, cudaMemsetAsync(h->MEM, 0, (size_t)h->B * h->npw * h->mem_per_pw * sizeof(float), h->stream));
+    }
+    for (int ipw = 0; ipw < h->npw; ipw++) for (auto& s : h->shots[ipw]) {
+        if (what & GPI_RESET_RECORDS) for (int f = 0; f < GPI_NWAVEFIELD; f++) if (s.rec[f])
+            CU(h, cudaMemsetAsync(s.rec[f], 0, (size_t)h->c.nt * std::max(s.nr[f], 1) * sizeof(float), h->stream));
+        if (what & GPI_RESET_BOUNDARY) for (int f = 0; f < GPI_NWAVEFIELD; f++) {
+            if (s.snap[f]) CU(h, cudaMemsetAsync(s.snap[f], 0, vb, h->stream));
+            for (int q = 0; q < 3; q++) if (s.bnd[f][q]) CU(h, cudaMemsetAsync(s.bnd[f][q], 0, (size_t)bnd_slot_floats(h, q) * h->c.nt * sizeof(float), h->stream));
+        }
+        if (what & GPI_RESET_SNAPS) for (auto p : s.usnaps) CU(h, cudaMemsetAsync(p, 0, vb, h->stream));
+    }
+    if (what & GPI_RESET_GRADIENTS) {
+        for (auto& p : h->gtot) if (p) CU(h, cudaMemsetAsync(p, 0, vb, h->stream));
+        if (h->gshot) CU(h, cudaMemsetAsync(h->gshot, 0, (size_t)h->B * 2 * vb, h->stream));
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// =================================================================================================
+// the hot loop
+// =================================================================================================
+namespace {
+
+InjOp make_inj(gpi_handle* h, const SparseDev& m, const float* wav, int kind, int axis) {
+    InjOp op; memset(&op, 0, sizeof op);
+    op.kind = kind; op.axis = axis;
+    op.nrows = m.nrows; op.row_cell = m.row_cell; op.row_ptr = m.row_ptr; op.ent_col = m.ent_col; op.ent_val = m.ent_val;
+    op.wav = wav;
+    (void)h;
+    return op;
+}
+
+// build the per-slot source/receiver descriptors of one batch (add_*_source!, record!)
+int build_post(gpi_handle* h, int shot0, int nb, int activepw, int src_flags) {
+    const int vf[3] = {GPI_VX, GPI_VY, GPI_VZ}, vaxis[3] = {2, 1, 0};
+    const int sf[4] = {GPI_P, GPI_TAUXX, GPI_TAUYY, GPI_TAUZZ};
+    for (int b = 0; b < nb; b++) {
+        const int is = shot0 + b;
+        PostDesc& pv = h->h_post_v[b]; PostDesc& ps = h->h_post_s[b];
+        memset(&pv, 0, sizeof pv); memset(&ps, 0, sizeof ps);
+        // ---- velocity sources (source.jl:124-157)
+        if ((activepw & 1) && (src_flags & 1)) for (int i = 0; i < 3; i++) {
+            const int f = vf[i]; ShotData& s = h->shots[0][is];
+            if (!s.wav[f]) continue;
+            if (!s.spray[f].set) FAIL(h, "shot %d: wavelets set for field %d but no spray matrix", is, f);
+            if (s.spray[f].ncol != s.ns[f]) FAIL(h, "shot %d field %d: %d wavelets but %d spray columns", is, f, s.ns[f], s.spray[f].ncol);
+            InjOp op = make_inj(h, s.spray[f], s.wav[f], 0, vaxis[i]);
+            op.ntarget = 1; op.target[0] = wf_ptr(h, h->W, b, 0, f); op.coef = h->mod[GPI_RHO];
+            if (pv.ninj >= MAX_OPS) FAIL(h, "too many source fields");
+            pv.inj[pv.ninj++] = op;
+        }
+        if (h->npw == 2 && (activepw & 2) && (src_flags & 2)) for (int i = 0; i < 3; i++) {
+            const int f = vf[i]; ShotData& s2 = h->shots[1][is]; ShotData& s1 = h->shots[0][is];
+            if (!s2.wav[f]) continue;
+            // adjoint sources are sprayed through pw 1's receiver matrix (source.jl:142-156)
+            if (!s1.interp[f].set) FAIL(h, "shot %d: adjoint wavelets for field %d but pw 1 has no receiver matrix for it", is, f);
+            if (s1.interp[f].ncol != s2.ns[f]) FAIL(h, "shot %d field %d: %d adjoint wavelets but %d receivers", is, f, s2.ns[f], s1.interp[f].ncol);
+            InjOp op = make_inj(h, s1.interp[f], s2.wav[f], 0, vaxis[i]);
+            op.ntarget = 1; op.target[0] = wf_ptr(h, h->W, b, 1, f); op.coef = h->mod[GPI_RHO];
+            if (pv.ninj >= MAX_OPS) FAIL(h, "too many source fields");
+            pv.inj[pv.ninj++] = op;
+        }
+        // ---- stress sources, pw 1 only (source.jl:61-119)
+        if ((activepw & 1) && (src_flags & 1)) for (int i = 0; i < 4; i++) {
+            const int f = sf[i]; ShotData& s = h->shots[0][is];
+            if (!field_exists(h->nd, h->c.physics, f) || !s.wav[f]) continue;
+            if (!s.spray[f].set) FAIL(h, "shot %d: wavelets set for field %d but no spray matrix", is, f);
+            if (s.spray[f].ncol != s.ns[f]) FAIL(h, "shot %d field %d: %d wavelets but %d spray columns", is, f, s.ns[f], s.spray[f].ncol);
+            InjOp op = make_inj(h, s.spray[f], s.wav[f], 1, 0);
+            op.coef = h->dmod[C_K];                    // dtK (acoustic) / dtM (elastic)
+            if (!h->el) { op.ntarget = 1; op.target[0] = wf_ptr(h, h->W, b, 0, GPI_P); }
+            else {                                     // every normal stress gets the same term (source.jl:99-118)
+                op.ntarget = 0;
+                op.target[op.ntarget++] = wf_ptr(h, h->W, b, 0, GPI_TAUXX);
+                if (h->nd == 3) op.target[op.ntarget++] = wf_ptr(h, h->W, b, 0, GPI_TAUYY);
+                op.target[op.ntarget++] = wf_ptr(h, h->W, b, 0, GPI_TAUZZ);
+            }
+            if (ps.ninj >= MAX_OPS) FAIL(h, "too many source fields");
+            ps.inj[ps.ninj++] = op;
+        }
+        // ---- receivers (receiver.jl:3-14; only p and velocities are ever recorded, propagate.jl:177,208)
+        for (int ipw = 0; ipw < h->npw; ipw++) {
+            if (!(activepw & (1 << ipw))) continue;
+            ShotData& s = h->shots[ipw][is];
+            for (int i = 0; i < 3; i++) {
+                const int f = vf[i];
+                if (!s.interp[f].set || !s.rec[f]) continue;
+                RecOp op; op.field = wf_ptr(h, h->W, b, ipw, f); op.nr = s.interp[f].ncol; op.colptr = s.interp[f].colptr;
+                op.tap_cell = s.interp[f].tap_cell; op.tap_val = s.interp[f].tap_val; op.rec = s.rec[f];
+                if (pv.nrec >= MAX_OPS) FAIL(h, "too many receiver fields");
+                pv.rec[pv.nrec++] = op;
+            }
+            if (!h->el && s.interp[GPI_P].set && s.rec[GPI_P]) {
+                RecOp op; op.field = wf_ptr(h, h->W, b, ipw, GPI_P); op.nr = s.interp[GPI_P].ncol; op.colptr = s.interp[GPI_P].colptr;
+                op.tap_cell = s.interp[GPI_P].tap_cell; op.tap_val = s.interp[GPI_P].tap_val; op.rec = s.rec[GPI_P];
+                ps.rec[ps.nrec++] = op;
+            }
+        }
+    }
+    CU(h, cudaMemcpyAsync(h->post_v, h->h_post_v, (size_t)nb * sizeof(PostDesc), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->post_s, h->h_post_s, (size_t)nb * sizeof(PostDesc), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+bool any_post(const PostDesc* d, int nb, bool with_rec) {
+    for (int b = 0; b < nb; b++) if (d[b].ninj > 0 || (with_rec && d[b].nrec > 0)) return true;
+    return false;
+}
+
+}  // namespace
+
+extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
+    GUARD(h);
+    if (mode != GPI_MODE_FORWARD && mode != GPI_MODE_FORWARD_SAVE && mode != GPI_MODE_ADJOINT) FAIL(h, "unknown mode %d", mode);
+    if (!(activepw & 1)) FAIL(h, "pw 1 must be active");
+    if ((activepw & 2) && h->npw < 2) FAIL(h, "pw 2 requested but the experiment was built with npw = 1");
+    if (mode == GPI_MODE_FORWARD_SAVE && !h->c.store_boundary) FAIL(h, "forward_save needs store_boundary=1 at construction (fdtd.jl:445-455)");
+    if (mode == GPI_MODE_ADJOINT && !h->c.store_boundary) FAIL(h, "adjoint needs the boundary store of a forward_save run");
+    const bool grad = mode == GPI_MODE_ADJOINT && (activepw & 2) && h->npw == 2;
+    if (grad && (h->el || h->nd != 2)) FAIL(h, "gradient imaging exists upstream only for 2-D acoustic media (gradient.jl:17-46)");
+    if (mode == GPI_MODE_ADJOINT && h->el && h->nd == 3) FAIL(h, "3-D elastic has no boundary_save! upstream (boundary.jl:215-264)");
+    const Geom& g = h->g;
+    const int nt = h->c.nt;
+    const size_t vb = (size_t)g.vol * sizeof(float);
+    int bf[3]; const int nbf = boundary_fields(h, bf);
+    const int vf[3] = {GPI_VX, GPI_VY, GPI_VZ};
+    h->timers = gpi_timers{};
+    CU(h, cudaEventRecord(h->ev0, h->stream));
+
+    for (int shot0 = 0; shot0 < h->c.nshots; shot0 += h->B) {
+        const int nb = std::min(h->B, h->c.nshots - shot0);
+        // reset_w2! (types.jl:100-113)
+        CU(h, cudaMemsetAsync(h->W, 0, (size_t)nb * h->bstride * sizeof(float), h->stream));
+        if (h->TP) CU(h, cudaMemsetAsync(h->TP, 0, (size_t)nb * h->bstride * sizeof(float), h->stream));
+        CU(h, cudaMemsetAsync(h->MEM, 0, (size_t)nb * h->npw * h->mem_per_pw * sizeof(float), h->stream));
+        if (grad) CU(h, cudaMemsetAsync(h->gshot, 0, (size_t)nb * 2 * vb, h->stream));
+        if (mode == GPI_MODE_ADJOINT) {       // boundary_force_snap_tau!/v! (boundary.jl:173-212)
+            for (int b = 0; b < nb; b++) {
+                ShotData& s = h->shots[0][shot0 + b];
+                for (int i = 0; i < nbf; i++) CU(h, cudaMemcpyAsync(wf_ptr(h, h->W, b, 0, bf[i]), s.snap[bf[i]], vb, cudaMemcpyDeviceToDevice, h->stream));
+                for (int i = 0; i < 3; i++) if (s.snap[vf[i]]) CU(h, cudaMemcpyAsync(wf_ptr(h, h->W, b, 0, vf[i]), s.snap[vf[i]], vb, cudaMemcpyDeviceToDevice, h->stream));
+            }
+        }
+        if (build_post(h, shot0, nb, activepw, src_flags)) return 1;
+        const bool do_post_v = any_post(h->h_post_v, nb, true);
+        const bool inj_s = any_post(h->h_post_s, nb, false), rec_s = any_post(h->h_post_s, nb, true);
+        StepArgs args[2];
+        for (int ipw = 0; ipw < h->npw; ipw++) fill_args(h, args[ipw], ipw, nb);
+        // record!(1, ..., [:p]) at the start of step 1 (zero unless the fields were loaded from snapshots)
+        if (rec_s) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, 1, 1, nt, (float)h->c.dt, 2); h->timers.launches += 1; }
+
+        for (int it = 1; it <= nt; it++) {
+            if (mode == GPI_MODE_ADJOINT) {
+                // save_tp! (save_tp.jl:5-12): one device copy of every wavefield of the batch
+                CU(h, cudaMemcpyAsync(h->TP, h->W, (size_t)nb * h->bstride * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+                // boundary_force!(nt - it + 1) on pw 1 (propagate.jl:188), x then (y) then z
+                for (int b = 0; b < nb; b++) for (int i = 0; i < nbf; i++) {
+                    const int axes[3] = {2, 1, 0};
+                    for (int ia = 0; ia < 3; ia++) {
+                        const int q = axes[ia]; if (q == 1 && h->nd == 2) continue;
+                        float* st = h->shots[0][shot0 + b].bnd[bf[i]][q] + (size_t)(nt - it) * bnd_slot_floats(h, q);
+                        if (launch_boundary(h, false, bf[i], wf_ptr(h, h->W, b, 0, bf[i]), st, q)) return 1;
+                    }
+                }
+            }
+            for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], true, nb);
+            if (do_post_v) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_v, it, it, nt, (float)h->c.dt, 3); h->timers.launches += 1; }
+            for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], false, nb);
+            // stress sources at step it, then the pressure record of step it+1 (record! runs at the start of a step)
+            if (inj_s || (rec_s && it < nt)) {
+                k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, it, it + 1, nt, (float)h->c.dt, 3);
+                h->timers.launches += 1;
+            }
+            if (mode == GPI_MODE_FORWARD_SAVE) {
+                for (int b = 0; b < nb; b++) for (int i = 0; i < nbf; i++) for (int q = 0; q < 3; q++) {
+                    if (q == 1 && h->nd == 2) continue;
+                    float* st = h->shots[0][shot0 + b].bnd[bf[i]][q] + (size_t)(it - 1) * bnd_slot_floats(h, q);
+                    if (launch_boundary(h, true, bf[i], wf_ptr(h, h->W, b, 0, bf[i]), st, q)) return 1;
+                }
+            }
+            if (grad) {
+                dim3 blk = h->blk2, grd = grid_for(h, blk, nb);
+                k_grad2d<<<grd, blk, 0, h->stream>>>(g,
+                    wf_ptr(h, h->W, 0, 0, GPI_P), wf_ptr(h, h->TP, 0, 0, GPI_P), wf_ptr(h, h->TP, 0, 1, GPI_P),
+                    wf_ptr(h, h->W, 0, 0, GPI_VX), wf_ptr(h, h->TP, 0, 0, GPI_VX), wf_ptr(h, h->TP, 0, 1, GPI_VX),
+                    wf_ptr(h, h->W, 0, 0, GPI_VZ), wf_ptr(h, h->TP, 0, 0, GPI_VZ), wf_ptr(h, h->TP, 0, 1, GPI_VZ),
+                    h->gshot, h->gshot + g.vol, (float)h->c.dtI, h->bstride, 2 * g.vol);
+                h->timers.launches += 1;
+            }
+            if (!h->itsnaps.empty()) for (int ks = 0; ks < (int)h->itsnaps.size(); ks++) if (h->itsnaps[ks] == it)
+                for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) for (int b = 0; b < nb; b++)
+                    CU(h, cudaMemcpyAsync(h->shots[ipw][shot0 + b].usnaps[ks], wf_ptr(h, h->W, b, ipw, h->c.snaps_field), vb, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        // final state for the initial-value problem of the time reversal (propagate.jl:251-258)
+        if (mode == GPI_MODE_FORWARD_SAVE)
+            for (int b = 0; b < nb; b++) for (int i = 0; i < nbf; i++) {
+                k_negate_copy<<<(unsigned)((g.vol + 255) / 256), 256, 0, h->stream>>>(h->shots[0][shot0 + b].snap[bf[i]], wf_ptr(h, h->W, b, 0, bf[i]), g.vol);
+                h->timers.launches += 1;
+            }
+        launch_step(h, args[0], true, nb);
+        if (mode == GPI_MODE_FORWARD_SAVE)
+            for (int b = 0; b < nb; b++) for (int i = 0; i < 3; i++) if (h->shots[0][shot0 + b].snap[vf[i]])
+                CU(h, cudaMemcpyAsync(h->shots[0][shot0 + b].snap[vf[i]], wf_ptr(h, h->W, b, 0, vf[i]), vb, cudaMemcpyDeviceToDevice, h->stream));
+        // sum_grads! (gradient.jl:2-11): stack in shot order
+        if (grad) for (int b = 0; b < nb; b++) {
+            k_axpy1<<<(unsigned)((g.vol + 255) / 256), 256, 0, h->stream>>>(h->gtot[GPI_INVK], h->gshot + (size_t)b * 2 * g.vol, g.vol);
+            k_axpy1<<<(unsigned)((g.vol + 255) / 256), 256, 0, h->stream>>>(h->gtot[GPI_RHO], h->gshot + (size_t)b * 2 * g.vol + g.vol, g.vol);
+            h->timers.launches += 2;
+        }
+        CU(h, cudaGetLastError());
+        // the pinned descriptor buffers are reused by the next batch
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
+    CU(h, cudaEventRecord(h->ev1, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaGetLastError());
+    float ms = 0.f;
+    CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->timers.run_ms = ms;
+    const int npw_active = ((activepw & 1) ? 1 : 0) + ((activepw & 2) ? 1 : 0);
+    h->timers.steps = (double)nt * h->c.nshots;
+    h->timers.cell_updates = (double)nt * h->c.nshots * npw_active * (double)g.nz * g.ny * g.nx;
+    return 0;
+}
+
+// =================================================================================================
+// results
+// =================================================================================================
+extern "C" int gpi_get_records(gpi_handle* h, int ipw, int issp, int f, float* out) {
+    GUARD(h);
+    if (ipw < 0 || ipw >= h->npw || issp < 0 || issp >= h->c.nshots) FAIL(h, "bad pw/shot index (%d, %d)", ipw, issp);
+    if (f < 0 || f >= GPI_NWAVEFIELD) FAIL(h, "bad field id %d", f);
+    ShotData& s = h->shots[ipw][issp];
+    if (!s.rec[f]) FAIL(h, "no receivers set for field %d of shot %d", f, issp);
+    CU(h, cudaMemcpyAsync(out, s.rec[f], (size_t)h->c.nt * s.nr[f] * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int gpi_records_device_ptr(gpi_handle* h, int ipw, int issp, int f, void** dptr, int64_t* nbytes) {
+    GUARD(h);
+    if (ipw < 0 || ipw >= h->npw || issp < 0 || issp >= h->c.nshots || f < 0 || f >= GPI_NWAVEFIELD) FAIL(h, "bad index");
+    ShotData& s = h->shots[ipw][issp];
+    if (!s.rec[f]) FAIL(h, "no receivers set for field %d of shot %d", f, issp);
+    *dptr = s.rec[f]; *nbytes = (int64_t)h->c.nt * s.nr[f] * sizeof(float);
+    return 0;
+}
+extern "C" int gpi_get_gradient(gpi_handle* h, int p, float* out) {
+    GUARD(h);
+    if (p < 0 || p >= GPI_NPARAM || !h->gtot[p]) FAIL(h, "no gradient for parameter %d (gradients exist for acoustic npw=2 experiments)", p);
+    return download_field(h, GPI_P, h->gtot[p], out);
+}
+extern "C" int gpi_gradient_device_ptr(gpi_handle* h, int p, void** dptr, int64_t* nfloats) {
+    GUARD(h);
+    if (p < 0 || p >= GPI_NPARAM || !h->gtot[p]) FAIL(h, "no gradient for parameter %d", p);
+    *dptr = h->gtot[p]; *nfloats = h->g.vol;
+    return 0;
+}
+extern "C" int gpi_get_snap(gpi_handle* h, int ipw, int issp, int isnap, float* out) {
+    GUARD(h);
+    if (ipw < 0 || ipw >= h->npw || issp < 0 || issp >= h->c.nshots || isnap < 0 || isnap >= h->c.nsnaps) FAIL(h, "bad snapshot index");
+    return download_field(h, h->c.snaps_field, h->shots[ipw][issp].usnaps[isnap], out);
+}
+extern "C" int gpi_get_field(gpi_handle* h, int ipw, int ib, int f, float* out) {
+    GUARD(h);
+    if (ipw < 0 || ipw >= h->npw || ib < 0 || ib >= h->B) FAIL(h, "bad pw/batch index");
+    float* p = wf_ptr(h, h->W, ib, ipw, f);
+    if (!p || !field_exists(h->nd, h->c.physics, f)) FAIL(h, "field %d is not a wavefield of this physics", f);
+    return download_field(h, f, p, out);
+}
+extern "C" int gpi_set_field(gpi_handle* h, int ipw, int ib, int f, const float* in) {
+    GUARD(h);
+    if (ipw < 0 || ipw >= h->npw || ib < 0 || ib >= h->B) FAIL(h, "bad pw/batch index");
+    float* p = wf_ptr(h, h->W, ib, ipw, f);
+    if (!p || !field_exists(h->nd, h->c.physics, f)) FAIL(h, "field %d is not a wavefield of this physics", f);
+    return upload_field(h, f, in, p);
+}
+extern "C" int gpi_get_timers(gpi_handle* h, gpi_timers* out) { if (!h || !out) return 1; *out = h->timers; return 0; }
+
+// =================================================================================================
+// NCCL (loaded lazily so the library also loads where libnccl is absent)
+// =================================================================================================
+namespace {
+int load_nccl(gpi_handle* h, NcclApi& n) {
+    if (n.lib) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (auto nm : names) { n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (n.lib) break; }
+    if (!n.lib) { if (h) h->err = "libnccl.so.2 not found"; return 1; }
+    n.GetUniqueId = (int (*)(void*))dlsym(n.lib, "ncclGetUniqueId");
+    n.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(n.lib, "ncclCommInitRank");
+    n.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(n.lib, "ncclAllReduce");
+    n.CommDestroy = (int (*)(void*))dlsym(n.lib, "ncclCommDestroy");
+    n.GetErrorString = (const char* (*)(int))dlsym(n.lib, "ncclGetErrorString");
+    if (!n.GetUniqueId || !n.CommInitRank || !n.AllReduce || !n.CommDestroy) { if (h) h->err = "libnccl is missing symbols"; return 1; }
+    return 0;
+}
+NcclApi g_nccl;
+}  // namespace
+
+extern "C" int gpi_nccl_unique_id(void* id128) {
+    if (!id128 || load_nccl(nullptr, g_nccl)) return 1;
+    return g_nccl.GetUniqueId(id128);
+}
+extern "C" int gpi_nccl_init(gpi_handle* h, const void* id128, int rank, int nranks) {
+    GUARD(h);
+    if (load_nccl(h, h->nccl)) return 1;
+    Id128 id; memcpy(&id, id128, sizeof id);
+    int r = h->nccl.CommInitRank(&h->comm, nranks, id, rank);
+    if (r != 0) FAIL(h, "ncclCommInitRank failed: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(r) : "?");
+    h->rank = rank; h->nranks = nranks;
+    return 0;
+}
+// the cross-worker half of sum_grads! (gradient.jl:2-11): one sum all-reduce per parameter over NVLink
+extern "C" int gpi_allreduce_gradients(gpi_handle* h) {
+    GUARD(h);
+    if (!h->comm) { if (h->nranks == 1) return 0; FAIL(h, "gpi_nccl_init has not been called"); }
+    for (int p = 0; p < GPI_NPARAM; p++) if (h->gtot[p]) {
+        int r = h->nccl.AllReduce(h->gtot[p], h->gtot[p], (size_t)h->g.vol, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->comm, h->stream);
+        if (r != 0) FAIL(h, "ncclAllReduce failed: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(r) : "?");
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}

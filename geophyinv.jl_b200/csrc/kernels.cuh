@@ -1,0 +1,557 @@
+// kernels.cuh -- sm_100a stencil kernels of the B200 FDTD engine.
+//
+// What they compute follows GeoPhyInv.jl's src/fdtd (citations relative to /root/reference);
+// how they compute it does not: the reference issues ~20 (2-D acoustic) to ~55 (3-D elastic)
+// ParallelStencil kernels per time step that round-trip every derivative array through memory
+// (advance_acou.jl:11-96, advance_elastic.jl:233-531, cpml.jl:158-215, dirichlet.jl:35-74).
+// Here one step is two fused sweeps:
+//
+//   k_vel    : stress derivatives -> CPML memory update -> velocity update -> rigid faces
+//              (update_dstress! + update_v!,  propagate.jl:191-198)
+//   k_stress : velocity derivatives -> CPML -> stress / pressure update -> free surface
+//              (update_dv! + update_stress!, propagate.jl:212-219)
+//
+// Derivatives never touch HBM.  Every field lives in ONE common "unified box"
+// (nz+1) x (ny+1) x (nx+1), z fastest with a 128-byte-multiple pitch, so that all arrays of a
+// cell share the same linear index and alignment:
+//     integer nodes  (tauii/p)          : reference index iz      -> k = iz-1
+//     velocity nodes (-1/2, length n+1) : reference index iz      -> k = iz-1   (node k sits at k-1/2)
+//     half nodes     (+1/2, length n-1) : reference index iz      -> k = iz     (node k sits at k-1/2)
+//     inner nodes    (+1,   length n-2) : reference index iz      -> k = iz
+// (src/fields.jl:92-671).  A forward difference onto a half node is f(k)-f(k-1); onto an integer
+// node from half nodes it is f(k+1)-f(k).
+//
+// Arithmetic: the reference's Base.Threads path evaluates Float32 mul/add separately (Julia does
+// not contract to FMA outside @fastmath/muladd).  All updates therefore use __fmul_rn/__fadd_rn/
+// __fsub_rn, which nvcc never contracts, in exactly the reference's association order, so the
+// engine reproduces the CPU path bit for bit rather than "to tolerance".  The kernels are HBM-bound
+// (0.3-0.5 flop/B); giving up FMA costs nothing measurable.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpi {
+
+enum { ZMIN = 1, ZMAX = 2, YMIN = 4, YMAX = 8, XMIN = 16, XMAX = 32 };
+
+// tau slots inside a wavefield set
+enum { T_XX = 0, T_YY = 1, T_ZZ = 2, T_XY = 3, T_XZ = 4, T_YZ = 5 };   // acoustic: T_XX slot holds p
+enum { V_X = 0, V_Y = 1, V_Z = 2 };
+// dmod slots
+enum { C_BX = 0, C_BY, C_BZ, C_K /*dtK or dtM*/, C_L /*dtlambda*/, C_MUXZ, C_MUXY, C_MUYZ, C_N };
+
+struct Geom {
+    int nz, ny, nx;          // extended grid (tauii nodes); ny = 1 in 2-D
+    int pz;                  // z pitch in floats (multiple of 32)
+    int ny1;                 // rows per x-plane: ny+1 (3-D) or 1 (2-D)
+    int nx1;                 // nx+1
+    int npml;
+    int pzm;                 // pitch of z-axis CPML memory rows (>= 2*npml, multiple of 32)
+    int pml, rigid, freesurf;// face masks
+    float dzI, dyI, dxI;
+    long long vol;           // floats per field volume = pz*ny1*nx1
+};
+
+// one CPML memory term (a derivative field of the reference): memory array + a,b,kI vectors
+struct PmlTerm {
+    float* mem;              // batch slot 0
+    const float* a; const float* b; const float* kI;   // 2*npml each
+    long long bstride;       // floats between batch slots
+};
+
+struct StepArgs {
+    // wavefields (batch slot 0 of this pw); *_out == *_in in forward mode
+    float* tau[6];
+    float* v[3];
+    const float* c[C_N];     // dmod in unified layout (shared by all shots)
+    PmlTerm pv[9];           // terms of k_vel, order documented at the kernel
+    PmlTerm ps[9];           // terms of k_stress
+    long long wstride;       // floats between batch slots of the wavefield set
+    int nbatch;
+};
+
+__device__ __forceinline__ long long uidx(const Geom& g, int k, int j, int i) {
+    return (long long)k + (long long)g.pz * ((long long)j + (long long)g.ny1 * (long long)i);
+}
+
+// CPML memory-variable update on one derivative value (cpml.jl:175-183):
+//     m = b*m + a*d ;  d = d*kI + m
+// AXIS: 0=z 1=y 2=x.  The derivative field covers unified coordinates [s0, s0+len) along AXIS;
+// its first/last npml entries are the min/max slabs (cpml.jl:190-211).
+template <int AXIS>
+__device__ __forceinline__ float cpml(const Geom& g, const PmlTerm& t, float d, int k, int j, int i,
+                                      int s0, int len, int b) {
+    const int u = AXIS == 0 ? k : (AXIS == 1 ? j : i);
+    const int minbit = AXIS == 0 ? ZMIN : (AXIS == 1 ? YMIN : XMIN);
+    const int maxbit = AXIS == 0 ? ZMAX : (AXIS == 1 ? YMAX : XMAX);
+    const int r = u - s0;
+    int s = -1;
+    if ((g.pml & minbit) && r < g.npml) s = r;
+    else {
+        const int rm = r - (len - g.npml);
+        if ((g.pml & maxbit) && rm >= 0) s = g.npml + rm;
+    }
+    if (s >= 0) {
+        long long mi;
+        if (AXIS == 2)      mi = (long long)k + (long long)g.pz * ((long long)j + (long long)g.ny1 * s);
+        else if (AXIS == 1) mi = (long long)k + (long long)g.pz * ((long long)s + 2LL * g.npml * i);
+        else                mi = (long long)s + (long long)g.pzm * ((long long)j + (long long)g.ny1 * i);
+        float* mp = t.mem + (long long)b * t.bstride + mi;
+        float m = *mp;
+        m = __fadd_rn(__fmul_rn(__ldg(t.b + s), m), __fmul_rn(__ldg(t.a + s), d));
+        *mp = m;
+        d = __fadd_rn(__fmul_rn(d, __ldg(t.kI + s)), m);
+    }
+    return d;
+}
+
+// thread -> unified cell.  3-D: grid.z folds (x tile, batch); 2-D: grid.y = x tiles, grid.z = batch.
+template <int ND>
+__device__ __forceinline__ bool cell(const Geom& g, int nbatch, int& k, int& j, int& i, int& b) {
+    k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ND == 3) {
+        j = blockIdx.y * blockDim.y + threadIdx.y;
+        const int ntx = (g.nx1 + blockDim.z - 1) / blockDim.z;
+        b = blockIdx.z / ntx;
+        i = (blockIdx.z - b * ntx) * blockDim.z + threadIdx.z;
+    } else {
+        j = 0;
+        i = blockIdx.y * blockDim.y + threadIdx.y;
+        b = blockIdx.z;
+    }
+    (void)nbatch;
+    return k <= g.nz && j < g.ny1 && i <= g.nx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_vel: update_dstress! + update_v! (+ dirichlet) fused.
+//   acoustic (advance_acou.jl:258-283):  v_inn = v_inn + b * dpd?          (PLUS)
+//   elastic  (advance_elastic.jl:69-110): v_inn = v_inn - b * (sum of dtau) (MINUS, reference order)
+// CPML term order in a.pv:
+//   acoustic : 0 dpdx, 1 dpdy, 2 dpdz
+//   elastic  : 0 dtauxxdx 1 dtauxydy 2 dtauxzdz | 3 dtauxydx 4 dtauyydy 5 dtauyzdz | 6 dtauxzdx 7 dtauyzdy 8 dtauzzdz
+// ------------------------------------------------------------------------------------------------
+template <int ND, int EL>
+__global__ void __launch_bounds__(256) k_vel(const Geom g, const StepArgs a) {
+    int k, j, i, b;
+    if (!cell<ND>(g, a.nbatch, k, j, i, b)) return;
+    const long long w = (long long)b * a.wstride;
+    const long long c = uidx(g, k, j, i);
+    const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
+    const int nz = g.nz, ny = g.ny, nx = g.nx;
+
+    // interior ranges of the three velocity components (@inn of compute_v!)
+    const bool iny  = (ND == 2) || (j >= 1 && j <= ny - 2);
+    const bool inyh = (ND == 2) || (j >= 1 && j <= ny - 1);
+    const bool vxin = k >= 1 && k <= nz - 2 && iny && i >= 1 && i <= nx - 1;
+    const bool vzin = k >= 1 && k <= nz - 1 && iny && i >= 1 && i <= nx - 2;
+    const bool vyin = (ND == 3) && k >= 1 && k <= nz - 2 && inyh && i >= 1 && i <= nx - 2;
+
+    // array extents (who owns an entry to write)
+    const bool vxown = k <= nz - 1 && (ND == 2 || j <= ny - 1);            // i <= nx always
+    const bool vzown = i <= nx - 1 && (ND == 2 || j <= ny - 1);            // k <= nz always
+    const bool vyown = (ND == 3) && k <= nz - 1 && i <= nx - 1;            // j <= ny always
+
+    float* vx = a.v[V_X] + w; float* vz = a.v[V_Z] + w; float* vy = (ND == 3) ? a.v[V_Y] + w : nullptr;
+    float nvx = 0.f, nvy = 0.f, nvz = 0.f;
+    if (vxown) nvx = vx[c];
+    if (vzown) nvz = vz[c];
+    if (ND == 3 && vyown) nvy = vy[c];
+
+    if (!EL) {
+        const float* p = a.tau[T_XX] + w;
+        const float pc = (vxin || vzin || vyin) ? p[c] : 0.f;
+        if (vxin) {
+            float d = __fmul_rn(__fsub_rn(pc, p[c - sx]), g.dxI);
+            d = cpml<2>(g, a.pv[0], d, k, j, i, 1, nx - 1, b);
+            nvx = __fadd_rn(nvx, __fmul_rn(__ldg(a.c[C_BX] + c), d));
+        }
+        if (ND == 3 && vyin) {
+            float d = __fmul_rn(__fsub_rn(pc, p[c - sy]), g.dyI);
+            d = cpml<1>(g, a.pv[1], d, k, j, i, 1, ny - 1, b);
+            nvy = __fadd_rn(nvy, __fmul_rn(__ldg(a.c[C_BY] + c), d));
+        }
+        if (vzin) {
+            float d = __fmul_rn(__fsub_rn(pc, p[c - 1]), g.dzI);
+            d = cpml<0>(g, a.pv[2], d, k, j, i, 1, nz - 1, b);
+            nvz = __fadd_rn(nvz, __fmul_rn(__ldg(a.c[C_BZ] + c), d));
+        }
+    } else if (ND == 2) {
+        const float* txx = a.tau[T_XX] + w; const float* tzz = a.tau[T_ZZ] + w; const float* txz = a.tau[T_XZ] + w;
+        if (vxin) {
+            float dxx = __fmul_rn(__fsub_rn(txx[c], txx[c - sx]), g.dxI);      // @d_xi(tauxx)
+            dxx = cpml<2>(g, a.pv[0], dxx, k, j, i, 1, nx - 1, b);
+            float dxz = __fmul_rn(__fsub_rn(txz[c + 1], txz[c]), g.dzI);       // @d_za(tauxz)
+            dxz = cpml<0>(g, a.pv[2], dxz, k, j, i, 1, nz - 2, b);
+            nvx = __fsub_rn(nvx, __fmul_rn(__ldg(a.c[C_BX] + c), __fadd_rn(dxx, dxz)));
+        }
+        if (vzin) {
+            float dzx = __fmul_rn(__fsub_rn(txz[c + sx], txz[c]), g.dxI);      // @d_xa(tauxz)
+            dzx = cpml<2>(g, a.pv[6], dzx, k, j, i, 1, nx - 2, b);
+            float dzz = __fmul_rn(__fsub_rn(tzz[c], tzz[c - 1]), g.dzI);       // @d_zi(tauzz)
+            dzz = cpml<0>(g, a.pv[8], dzz, k, j, i, 1, nz - 1, b);
+            nvz = __fsub_rn(nvz, __fmul_rn(__ldg(a.c[C_BZ] + c), __fadd_rn(dzx, dzz)));
+        }
+    } else {
+        const float* txx = a.tau[T_XX] + w; const float* tyy = a.tau[T_YY] + w; const float* tzz = a.tau[T_ZZ] + w;
+        const float* txy = a.tau[T_XY] + w; const float* txz = a.tau[T_XZ] + w; const float* tyz = a.tau[T_YZ] + w;
+        // shared centre values (each read once per thread)
+        const bool any = vxin || vyin || vzin;
+        const float cxy = (vxin || vyin) ? txy[c] : 0.f;
+        const float cxz = (vxin || vzin) ? txz[c] : 0.f;
+        const float cyz = (vyin || vzin) ? tyz[c] : 0.f;
+        (void)any;
+        if (vxin) {
+            float dxx = __fmul_rn(__fsub_rn(txx[c], txx[c - sx]), g.dxI);      // @d_xi(tauxx)
+            dxx = cpml<2>(g, a.pv[0], dxx, k, j, i, 1, nx - 1, b);
+            float dxy = __fmul_rn(__fsub_rn(txy[c + sy], cxy), g.dyI);         // @d_ya(tauxy)
+            dxy = cpml<1>(g, a.pv[1], dxy, k, j, i, 1, ny - 2, b);
+            float dxz = __fmul_rn(__fsub_rn(txz[c + 1], cxz), g.dzI);          // @d_za(tauxz)
+            dxz = cpml<0>(g, a.pv[2], dxz, k, j, i, 1, nz - 2, b);
+            nvx = __fsub_rn(nvx, __fmul_rn(__ldg(a.c[C_BX] + c), __fadd_rn(__fadd_rn(dxx, dxy), dxz)));
+        }
+        if (vyin) {
+            float dyx = __fmul_rn(__fsub_rn(txy[c + sx], cxy), g.dxI);         // @d_xa(tauxy)
+            dyx = cpml<2>(g, a.pv[3], dyx, k, j, i, 1, nx - 2, b);
+            float dyy = __fmul_rn(__fsub_rn(tyy[c], tyy[c - sy]), g.dyI);      // @d_yi(tauyy)
+            dyy = cpml<1>(g, a.pv[4], dyy, k, j, i, 1, ny - 1, b);
+            float dyz = __fmul_rn(__fsub_rn(tyz[c + 1], cyz), g.dzI);          // @d_za(tauyz)
+            dyz = cpml<0>(g, a.pv[5], dyz, k, j, i, 1, nz - 2, b);
+            nvy = __fsub_rn(nvy, __fmul_rn(__ldg(a.c[C_BY] + c), __fadd_rn(__fadd_rn(dyx, dyy), dyz)));
+        }
+        if (vzin) {
+            float dzx = __fmul_rn(__fsub_rn(txz[c + sx], cxz), g.dxI);         // @d_xa(tauxz)
+            dzx = cpml<2>(g, a.pv[6], dzx, k, j, i, 1, nx - 2, b);
+            float dzy = __fmul_rn(__fsub_rn(tyz[c + sy], cyz), g.dyI);         // @d_ya(tauyz)
+            dzy = cpml<1>(g, a.pv[7], dzy, k, j, i, 1, ny - 2, b);
+            float dzz = __fmul_rn(__fsub_rn(tzz[c], tzz[c - 1]), g.dzI);       // @d_zi(tauzz)
+            dzz = cpml<0>(g, a.pv[8], dzz, k, j, i, 1, nz - 1, b);
+            nvz = __fsub_rn(nvz, __fmul_rn(__ldg(a.c[C_BZ] + c), __fadd_rn(__fadd_rn(dzx, dzy), dzz)));
+        }
+    }
+
+    // ---- rigid faces (dirichlet.jl:35-74), reference call order x, (y,) z; later faces override.
+    // Ghost entries (v?[1] / v?[n+1] along their own axis) are written by the thread that owns the
+    // mirrored inner node, so no thread reads a neighbour's new value.
+    const int R = g.rigid;
+    const bool tz0 = (R & ZMIN) && k == 0, tz1 = (R & ZMAX) && k == nz - 1;
+    const bool ty0 = ND == 3 && (R & YMIN) && j == 0, ty1 = ND == 3 && (R & YMAX) && j == ny - 1;
+    const bool tx0 = (R & XMIN) && i == 0, tx1 = (R & XMAX) && i == nx - 1;
+    // the tangential zeroing of face q covers the tauii index range of the other two axes
+    const bool injj = (ND == 2) || j <= ny - 1;
+    if (vxown) {
+        float val = nvx;
+        // zeroed by y faces (i <= nx-1) and z faces (i <= nx-1)
+        const bool zero = i <= nx - 1 && (ty0 || ty1 || tz0 || tz1);
+        const bool ghost_min = (R & XMIN) && i == 0, ghost_max = (R & XMAX) && i == nx;
+        if (zero) val = 0.f;
+        if (!(ghost_min || ghost_max)) vx[c] = val;
+        if ((R & XMIN) && i == 1) vx[c - sx] = (ty0 || ty1 || tz0 || tz1) ? 0.f : -nvx;     // vx[1] = -vx[2]
+        if ((R & XMAX) && i == nx - 1) vx[c + sx] = -nvx;                                   // vx[n+1] = -vx[n]
+    }
+    if (vzown) {
+        float val = nvz;
+        const bool zero = k <= nz - 1 && (tx0 || tx1 || ty0 || ty1);
+        const bool ghost_min = (R & ZMIN) && k == 0, ghost_max = (R & ZMAX) && k == nz;
+        if (zero) val = 0.f;
+        if (!(ghost_min || ghost_max)) vz[c] = val;
+        // the z faces are applied last: their ghosts mirror the value left by the x/y faces
+        if ((R & ZMIN) && k == 1) vz[c - 1] = -val;
+        if ((R & ZMAX) && k == nz - 1) vz[c + 1] = -val;
+    }
+    if (ND == 3 && vyown) {
+        float val = nvy;
+        const bool zero_before = j <= ny - 1 && (tx0 || tx1);      // x faces run before the y faces
+        const bool zero_after  = j <= ny - 1 && (tz0 || tz1);      // z faces run after
+        const bool ghost_min = (R & YMIN) && j == 0, ghost_max = (R & YMAX) && j == ny;
+        if (zero_before) val = 0.f;
+        const float mirrored = val;
+        if (zero_after) val = 0.f;
+        if (!(ghost_min || ghost_max)) vy[c] = val;
+        if ((R & YMIN) && j == 1) vy[c - sy] = zero_after ? 0.f : -mirrored;
+        if ((R & YMAX) && j == ny - 1) vy[c + sy] = -mirrored;
+    }
+    (void)injj;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_stress: update_dv! + update_stress! (+ free surface) fused.
+//   acoustic (advance_acou.jl:288-313): p = p + (dvxdx + dvzdz [+ dvydy]) * dtK
+//   elastic  (advance_elastic.jl:155-230)
+// CPML term order in a.ps:
+//   0 dvxdx 1 dvydy 2 dvzdz | 3 dvxdy 4 dvydx (tauxy) | 5 dvxdz 6 dvzdx (tauxz) | 7 dvydz 8 dvzdy (tauyz)
+// ------------------------------------------------------------------------------------------------
+template <int ND, int EL>
+__global__ void __launch_bounds__(256) k_stress(const Geom g, const StepArgs a) {
+    int k, j, i, b;
+    if (!cell<ND>(g, a.nbatch, k, j, i, b)) return;
+    const long long w = (long long)b * a.wstride;
+    const long long c = uidx(g, k, j, i);
+    const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
+    const int nz = g.nz, ny = g.ny, nx = g.nx;
+
+    const float* vx = a.v[V_X] + w; const float* vz = a.v[V_Z] + w; const float* vy = (ND == 3) ? a.v[V_Y] + w : nullptr;
+    const bool nin = k <= nz - 1 && (ND == 2 || j <= ny - 1) && i <= nx - 1;       // tauii / p nodes
+
+    float cvx = 0.f, cvy = 0.f, cvz = 0.f;
+    const bool need_c = k <= nz - 1 || i <= nx - 1;    // cheap superset
+    if (need_c) {
+        if (k <= nz - 1 && (ND == 2 || j <= ny - 1)) cvx = vx[c];
+        if (i <= nx - 1 && (ND == 2 || j <= ny - 1)) cvz = vz[c];
+        if (ND == 3 && k <= nz - 1 && i <= nx - 1) cvy = vy[c];
+    }
+
+    float dxx = 0.f, dyy = 0.f, dzz = 0.f;
+    if (nin) {
+        dxx = __fmul_rn(__fsub_rn(vx[c + sx], cvx), g.dxI);                    // @d_xa(vx)
+        dxx = cpml<2>(g, a.ps[0], dxx, k, j, i, 0, nx, b);
+        if (ND == 3) {
+            dyy = __fmul_rn(__fsub_rn(vy[c + sy], cvy), g.dyI);                // @d_ya(vy)
+            dyy = cpml<1>(g, a.ps[1], dyy, k, j, i, 0, ny, b);
+        }
+        dzz = __fmul_rn(__fsub_rn(vz[c + 1], cvz), g.dzI);                     // @d_za(vz)
+        dzz = cpml<0>(g, a.ps[2], dzz, k, j, i, 0, nz, b);
+    }
+
+    if (!EL) {
+        if (nin) {
+            float* p = a.tau[T_XX] + w;
+            const float s = (ND == 3) ? __fadd_rn(__fadd_rn(dxx, dzz), dyy) : __fadd_rn(dxx, dzz);
+            p[c] = __fadd_rn(p[c], __fmul_rn(s, __ldg(a.c[C_K] + c)));
+        }
+        return;
+    }
+
+    const bool fs = (g.freesurf & ZMIN) != 0;
+    if (nin) {
+        const float M = __ldg(a.c[C_K] + c), L = __ldg(a.c[C_L] + c);
+        float* txx = a.tau[T_XX] + w; float* tzz = a.tau[T_ZZ] + w;
+        float nzz;
+        if (ND == 3) {
+            float* tyy = a.tau[T_YY] + w;
+            txx[c] = __fsub_rn(__fsub_rn(txx[c], __fmul_rn(M, dxx)), __fmul_rn(L, __fadd_rn(dyy, dzz)));
+            tyy[c] = __fsub_rn(__fsub_rn(tyy[c], __fmul_rn(M, dyy)), __fmul_rn(L, __fadd_rn(dxx, dzz)));
+            nzz    = __fsub_rn(__fsub_rn(tzz[c], __fmul_rn(M, dzz)), __fmul_rn(L, __fadd_rn(dyy, dxx)));
+        } else {
+            txx[c] = __fsub_rn(__fsub_rn(txx[c], __fmul_rn(M, dxx)), __fmul_rn(L, dzz));
+            nzz    = __fsub_rn(__fsub_rn(tzz[c], __fmul_rn(M, dzz)), __fmul_rn(L, dxx));
+        }
+        // free surface (advance_elastic.jl:215-230): tauzz[1] = -tauzz[2], written by the owner of node 2
+        if (!(fs && k == 0)) tzz[c] = nzz;
+        if (fs && k == 1) tzz[c - 1] = -nzz;
+    }
+    // shear stresses on their own (half) grids
+    const bool jh = (ND == 2) || (j >= 1 && j <= ny - 1);     // half nodes along y
+    const bool jj = (ND == 2) || (j >= 1 && j <= ny - 2);     // inner nodes along y
+    // tauxz: z half, y inner, x half
+    if (k >= 1 && k <= nz - 1 && jj && i >= 1 && i <= nx - 1) {
+        float* txz = a.tau[T_XZ] + w;
+        float dxz = __fmul_rn(__fsub_rn(cvx, vx[c - 1]), g.dzI);               // @d_zi(vx)
+        dxz = cpml<0>(g, a.ps[5], dxz, k, j, i, 1, nz - 1, b);
+        float dzx = __fmul_rn(__fsub_rn(cvz, vz[c - sx]), g.dxI);              // @d_xi(vz)
+        dzx = cpml<2>(g, a.ps[6], dzx, k, j, i, 1, nx - 1, b);
+        float n = __fsub_rn(txz[c], __fmul_rn(__ldg(a.c[C_MUXZ] + c), __fadd_rn(dxz, dzx)));
+        if (fs && k == 1) n = 0.f;                                             // free_surface!(tauxz)
+        txz[c] = n;
+    }
+    if (ND == 3) {
+        // tauxy: z inner, y half, x half
+        if (k >= 1 && k <= nz - 2 && jh && i >= 1 && i <= nx - 1) {
+            float* txy = a.tau[T_XY] + w;
+            float dxy = __fmul_rn(__fsub_rn(cvx, vx[c - sy]), g.dyI);          // @d_yi(vx)
+            dxy = cpml<1>(g, a.ps[3], dxy, k, j, i, 1, ny - 1, b);
+            float dyx = __fmul_rn(__fsub_rn(cvy, vy[c - sx]), g.dxI);          // @d_xi(vy)
+            dyx = cpml<2>(g, a.ps[4], dyx, k, j, i, 1, nx - 1, b);
+            txy[c] = __fsub_rn(txy[c], __fmul_rn(__ldg(a.c[C_MUXY] + c), __fadd_rn(dxy, dyx)));
+        }
+        // tauyz: z half, y half, x inner
+        if (k >= 1 && k <= nz - 1 && jh && i >= 1 && i <= nx - 2) {
+            float* tyz = a.tau[T_YZ] + w;
+            float dyz = __fmul_rn(__fsub_rn(cvy, vy[c - 1]), g.dzI);           // @d_zi(vy)
+            dyz = cpml<0>(g, a.ps[7], dyz, k, j, i, 1, nz - 1, b);
+            float dzy = __fmul_rn(__fsub_rn(cvz, vz[c - sy]), g.dyI);          // @d_yi(vz)
+            dzy = cpml<1>(g, a.ps[8], dzy, k, j, i, 1, ny - 1, b);
+            float n = __fsub_rn(tyz[c], __fmul_rn(__ldg(a.c[C_MUYZ] + c), __fadd_rn(dyz, dzy)));
+            if (fs && k == 1) n = 0.f;                                         // free_surface!(tauyz)
+            tyz[c] = n;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_dmod: update_dmod! + store_invav*! (medium.jl:143-221).  The reference's `dt / @av_*(b)` and
+// `inv(a) + 2.0*inv(b)` carry Float64 literals, so those are evaluated in double and rounded once.
+// mod slots: 0 invK|invlambda, 1 rho, 2 invmu
+// ------------------------------------------------------------------------------------------------
+template <int ND, int EL>
+__global__ void k_dmod(const Geom g, const float* __restrict__ m0, const float* __restrict__ rho,
+                       const float* __restrict__ imu, float* const* __restrict__ out, float dt) {
+    int k, j, i, b;
+    if (!cell<ND>(g, 1, k, j, i, b)) return;
+    const long long c = uidx(g, k, j, i);
+    const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
+    const int nz = g.nz, ny = g.ny, nx = g.nx;
+    const double ddt = (double)dt;
+    const bool iny = (ND == 2) || (j >= 1 && j <= ny - 2);
+    const bool inyh = (ND == 2) || (j >= 1 && j <= ny - 1);
+    if (k >= 1 && k <= nz - 2 && iny && i >= 1 && i <= nx - 1)         // @av_xi(rho) on the vx interior
+        out[C_BX][c] = (float)(ddt / ((double)__fadd_rn(rho[c - sx], rho[c]) * 0.5));
+    if (k >= 1 && k <= nz - 1 && iny && i >= 1 && i <= nx - 2)         // @av_zi(rho)
+        out[C_BZ][c] = (float)(ddt / ((double)__fadd_rn(rho[c - 1], rho[c]) * 0.5));
+    if (ND == 3 && k >= 1 && k <= nz - 2 && inyh && i >= 1 && i <= nx - 2)   // @av_yi(rho)
+        out[C_BY][c] = (float)(ddt / ((double)__fadd_rn(rho[c - sy], rho[c]) * 0.5));
+    const bool nin = k <= nz - 1 && (ND == 2 || j <= ny - 1) && i <= nx - 1;
+    if (nin) {
+        if (!EL) out[C_K][c] = __fmul_rn(__fdiv_rn(1.0f, m0[c]), dt);                                  // dtK
+        else {
+            const float il = __fdiv_rn(1.0f, m0[c]), im = __fdiv_rn(1.0f, imu[c]);
+            out[C_L][c] = __fmul_rn(il, dt);                                                           // dtlambda
+            out[C_K][c] = __fmul_rn((float)((double)il + 2.0 * (double)im), dt);                       // dtM
+        }
+    }
+    if (EL) {
+        if (ND == 2) {
+            if (k >= 1 && k <= nz - 1 && i >= 1 && i <= nx - 1) {      // @av(invmu) (diff2D.jl:222-225)
+                const float s = __fadd_rn(__fadd_rn(__fadd_rn(imu[c - 1 - sx], imu[c - sx]), imu[c - 1]), imu[c]);
+                out[C_MUXZ][c] = (float)(ddt / ((double)s * 0.25));
+            }
+        } else {
+            if (k >= 1 && k <= nz - 1 && j >= 1 && j <= ny - 2 && i >= 1 && i <= nx - 1) {   // @av_xzi
+                const float s = __fadd_rn(__fadd_rn(__fadd_rn(imu[c - 1 - sx], imu[c - sx]), imu[c - 1]), imu[c]);
+                out[C_MUXZ][c] = (float)(ddt / ((double)s * 0.25));
+            }
+            if (k >= 1 && k <= nz - 2 && j >= 1 && j <= ny - 1 && i >= 1 && i <= nx - 1) {   // @av_xyi
+                const float s = __fadd_rn(__fadd_rn(__fadd_rn(imu[c - sy - sx], imu[c - sx]), imu[c - sy]), imu[c]);
+                out[C_MUXY][c] = (float)(ddt / ((double)s * 0.25));
+            }
+            if (k >= 1 && k <= nz - 1 && j >= 1 && j <= ny - 1 && i >= 1 && i <= nx - 2) {   // @av_yzi
+                const float s = __fadd_rn(__fadd_rn(__fadd_rn(imu[c - 1 - sy], imu[c - sy]), imu[c - 1]), imu[c]);
+                out[C_MUYZ][c] = (float)(ddt / ((double)s * 0.25));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sources and receivers: one block per shot of the batch; inject, barrier, record.
+// Replaces the reference's dense SpMV into a full-grid buffer plus a full-grid muladd sweep
+// (source.jl:61-177) by O(ns * 2^N) scattered updates with the same per-cell summation order,
+// and the per-step SpMV' (receiver.jl:3-14) by direct gathers into the [nt, nr] record block.
+// ------------------------------------------------------------------------------------------------
+struct InjOp {
+    int kind;                 // 0: velocity (muladd_with_density_v?!), 1: stress (muladd_tauii!)
+    int axis;                 // velocity: axis of the 2-point rho average (0 z, 1 y, 2 x)
+    int ntarget;              // 1 (velocity, p) or 2/3 (elastic: every normal stress)
+    float* target[3];
+    const float* coef;        // stress: dtK / dtM ; velocity: rho
+    int nrows;                // distinct cells hit
+    const int* row_cell;      // unified linear index of each cell (fits int for <= 2^31 cells; checked on host)
+    const int* row_ptr;       // nrows+1
+    const int* ent_col;       // source index (column) of each entry, column order preserved
+    const float* ent_val;
+    const float* wav;         // [nt, ns]
+};
+struct RecOp {
+    const float* field;
+    int nr;
+    const int* colptr;        // nr+1 (0-based)
+    const int* tap_cell;      // unified linear index per stored entry, CSC order
+    const float* tap_val;
+    float* rec;               // [nt, nr]
+};
+enum { MAX_OPS = 8 };
+struct PostDesc { int ninj, nrec; InjOp inj[MAX_OPS]; RecOp rec[MAX_OPS]; };
+
+__global__ void k_post(const Geom g, const PostDesc* __restrict__ descs, int it /*1-based*/, int rec_it /*1-based row to write*/,
+                       int nt, float dt, int flags /* bit0 inject, bit1 record */) {
+    const PostDesc& d = descs[blockIdx.x];
+    const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
+    const int ninj = (flags & 1) ? d.ninj : 0;
+    const int nrec = ((flags & 2) && rec_it >= 1 && rec_it <= nt) ? d.nrec : 0;
+    for (int o = 0; o < ninj; o++) {
+        const InjOp& op = d.inj[o];
+        for (int r = threadIdx.x; r < op.nrows; r += blockDim.x) {
+            float buf = 0.f;                                         // mul!(buf, S, w): buf[row] += nzval * w[col]
+            for (int e = op.row_ptr[r]; e < op.row_ptr[r + 1]; e++)
+                buf = __fadd_rn(buf, __fmul_rn(op.ent_val[e], op.wav[(size_t)(it - 1) + (size_t)nt * op.ent_col[e]]));
+            const long long c = op.row_cell[r];
+            if (op.kind == 1) {
+                const float add = __fmul_rn(buf, op.coef[c]);        // pw = pw + (pv * dtK)
+                for (int t = 0; t < op.ntarget; t++) op.target[t][c] = __fadd_rn(op.target[t][c], add);
+            } else {                                                 // pw = pw + (pv / av(rho) * dt), Float64 as in the reference
+                const long long off = op.axis == 0 ? 1 : (op.axis == 1 ? sy : sx);
+                const float s = __fadd_rn(op.coef[c - off], op.coef[c]);
+                float* t = op.target[0];
+                t[c] = (float)((double)t[c] + ((double)buf / ((double)s * 0.5) * (double)dt));
+            }
+        }
+    }
+    __syncthreads();
+    for (int o = 0; o < nrec; o++) {
+        const RecOp& op = d.rec[o];
+        for (int ir = threadIdx.x; ir < op.nr; ir += blockDim.x) {
+            float tmp = 0.f;                                         // mul!(rec, transpose(R), field)
+            for (int e = op.colptr[ir]; e < op.colptr[ir + 1]; e++)
+                tmp = __fadd_rn(tmp, __fmul_rn(op.tap_val[e], op.field[op.tap_cell[e]]));
+            op.rec[(size_t)(rec_it - 1) + (size_t)nt * ir] = tmp;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// boundary store for time reversal (boundary.jl:17-52, 217-264): 3+3 planes per axis just inside the
+// PML, saved negated in :forward_save and forced back in :adjoint.  Store layout (engine's own):
+// axis x: [6][ny1][pz] ; axis y: [nx1][6][pz] ; axis z: [6][ny1][nx1].
+// ------------------------------------------------------------------------------------------------
+template <int SAVE>
+__global__ void k_boundary(const Geom g, float* __restrict__ field, float* __restrict__ store, int axis,
+                           int lo, int hi /* first unified index of the min / max triple */, int nbound,
+                           int nk, int nj, int ni /* field extents (unified upper bounds, exclusive) */,
+                           int k0, int j0, int i0 /* field lower bounds */) {
+    // thread space: (k or plane, j, i) over the store
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t1 = blockIdx.y * blockDim.y + threadIdx.y;
+    const int t2 = blockIdx.z;
+    int k, j, i, p;   // p = plane 0..2*nbound-1
+    long long si;
+    if (axis == 2)      { k = t0; j = t1; p = t2; if (k >= g.pz || j >= g.ny1 || p >= 2 * nbound) return; i = (p < nbound ? lo + p : hi + p - nbound); si = (long long)k + (long long)g.pz * (j + (long long)g.ny1 * p); }
+    else if (axis == 1) { k = t0; p = t1; i = t2; if (k >= g.pz || p >= 2 * nbound || i >= g.nx1) return; j = (p < nbound ? lo + p : hi + p - nbound); si = (long long)k + (long long)g.pz * (p + 2LL * nbound * i); }
+    else                { i = t0; j = t1; p = t2; if (i >= g.nx1 || j >= g.ny1 || p >= 2 * nbound) return; k = (p < nbound ? lo + p : hi + p - nbound); si = (long long)i + (long long)g.nx1 * (j + (long long)g.ny1 * p); }
+    if (k < k0 || k >= nk || j < j0 || j >= nj || i < i0 || i >= ni) return;
+    const long long c = uidx(g, k, j, i);
+    if (SAVE) store[si] = __fmul_rn(field[c], -1.0f);     // rmul!(b, -1)
+    else      field[c] = store[si];
+}
+
+// ------------------------------------------------------------------------------------------------
+// gradient imaging, 2-D acoustic (gradient.jl:17-56), one pass over the grid:
+//   g_invK += p2_tp * (p1_tp - p1) * dtI
+//   g_rho_inn -= av_xi(bx) + av_zi(bz),  b? = v?2_tp * (v?1 - v?1_tp) * dtI   (buffers recomputed on the fly)
+// The reference's one-cell shift in combine_gmodrho! (gradient.jl:53-56) is kept.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_grad2d(const Geom g, const float* __restrict__ p1, const float* __restrict__ p1tp, const float* __restrict__ p2tp,
+                         const float* __restrict__ vx1, const float* __restrict__ vx1tp, const float* __restrict__ vx2tp,
+                         const float* __restrict__ vz1, const float* __restrict__ vz1tp, const float* __restrict__ vz2tp,
+                         float* __restrict__ gK, float* __restrict__ gR, float dtI, long long wstride, long long gstride) {
+    int k, j, i, b;
+    if (!cell<2>(g, 1, k, j, i, b)) return;
+    if (k > g.nz - 1 || i > g.nx - 1) return;
+    const long long w = (long long)b * wstride, gw = (long long)b * gstride;
+    const long long c = uidx(g, k, 0, i), sx = g.pz;
+    gK[gw + c] = __fadd_rn(gK[gw + c], __fmul_rn(__fmul_rn(p2tp[w + c], __fsub_rn(p1tp[w + c], p1[w + c])), dtI));
+    if (k >= 1 && k <= g.nz - 2 && i >= 1 && i <= g.nx - 2) {
+        auto bufx = [&](long long q) { return __fmul_rn(__fmul_rn(vx2tp[w + q], __fsub_rn(vx1[w + q], vx1tp[w + q])), dtI); };
+        auto bufz = [&](long long q) { return __fmul_rn(__fmul_rn(vz2tp[w + q], __fsub_rn(vz1[w + q], vz1tp[w + q])), dtI); };
+        const float ax = __fadd_rn(bufx(c - sx), bufx(c));     // vxbuffer[iz+1, ix] + vxbuffer[iz+1, ix+1]
+        const float az = __fadd_rn(bufz(c - 1), bufz(c));      // vzbuffer[iz, ix+1] + vzbuffer[iz+1, ix+1]
+        gR[gw + c] = (float)((double)gR[gw + c] - (double)ax * 0.5 - (double)az * 0.5);
+    }
+}
+
+// g_total += g_shot, in shot order (sum_grads!, gradient.jl:2-11)
+__global__ void k_axpy1(float* __restrict__ y, const float* __restrict__ x, long long n) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) y[t] = __fadd_rn(y[t], x[t]);
+}
+
+}  // namespace gpi

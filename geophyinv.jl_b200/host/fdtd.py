@@ -1,0 +1,449 @@
+"""`SeisForwExpt` / `PFdtd` and the `update!` workflow, backed by the B200 engine.
+
+Python mirror of the reference's L3 host layer (citations relative to /root/reference):
+construction src/fdtd/fdtd.jl:43-295, `update!(pa)` src/fdtd/propagate.jl:74-135,
+`update!(pa, medium)` src/fdtd/medium.jl:103-186, `update!(pa, srcwav, src_types)`
+src/fdtd/source.jl:192-246, `update!(pa, ageom)` src/fdtd/ageom.jl:58-98, `pa[:data]`
+src/fdtd/getprop.jl:10-31, `lossvalue` / `gradient!` src/fdtd/func_grad.jl:1-49.
+
+Everything that touched device arrays in the reference is a call into the C ABI
+(include/gpifdtd.h) here -- exactly the lines the Julia shim (julia/GPIFdtdB200.jl) replaces with
+`ccall`.  Julia `Distributed` workers become ranks: one process per GPU, each owning the
+contiguous chunk of supersources `sschunks[rank]` (fdtd.jl:246-255).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .. import engine as E
+from .cpml import pml_coefficients
+from .data import (AGeomss, Medium, Recs, Srcs, findfreq, get_adjoint_ageom, get_source, make_recs,
+                   padarray)
+from .grids import NBOUND, NPML, ORDER, StepRange, dfields_of, dim_names, field_shape, wavefields_of
+from .proj import get_proj_matrix
+
+F32 = np.float32
+ALL_FACES = ["zmin", "zmax", "ymin", "ymax", "xmax", "xmin"]
+
+
+# --------------------------------------------------------------------------------------------------
+# attrib_mod (src/physics_types.jl:17-49)
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class _Fdtd:
+    mode: str = "forward"
+    npw: int = 1
+    born: bool = False
+
+    def __post_init__(self):
+        self.mode = str(self.mode).lstrip(":")
+        if self.mode != "forward" and self.npw == 1 and not self.born:
+            self.npw = 2                       # FdtdAcoustic(:forward_save) has npw = 2 (physics_types.jl:42-48)
+        if self.born:
+            raise NotImplementedError("FD-Born scattering sources are a later row (SURVEY.md section 8f)")
+
+
+class FdtdAcoustic(_Fdtd):
+    physics = "acoustic"
+
+
+class FdtdElastic(_Fdtd):
+    physics = "elastic"
+
+
+def medium_parameters(attrib_mod) -> List[str]:
+    """Independent parameters `mod` (src/fdtd/medium.jl:81-95)."""
+    return ["invK", "rho"] if attrib_mod.physics == "acoustic" else ["invlambda", "invmu", "rho"]
+
+
+def sschunks(nss: int, nworker: int):
+    """fdtd.jl:251-255 (0-based half-open ranges)."""
+    ssi = [int(round(float(s))) for s in np.linspace(0, nss, nworker + 1)]      # round(Int, .): ties to even, like Python
+    return [range(ssi[i], ssi[i + 1]) for i in range(nworker)]
+
+
+def view_inner(a: np.ndarray, npml: int, faces) -> np.ndarray:
+    """medium.jl:13-26"""
+    fs = {str(f).lstrip(":") for f in faces}
+    sl = []
+    for d, n in zip(dim_names(a.ndim), a.shape):
+        sl.append(slice(npml if d + "min" in fs else 0, n - npml if d + "max" in fs else n))
+    return a[tuple(sl)]
+
+
+class PCommon:
+    """`P_common` (src/fdtd/types.jl:132-166): parameters shared by all supersources."""
+    pass
+
+
+class PFdtd:
+    """`PFdtd` (types.jl:181-186).  Build with `SeisForwExpt(attrib_mod; ...)`."""
+
+    def __init__(self, attrib_mod, *, medium: Medium, tgrid: StepRange, ageom, srcwav,
+                 pml_faces: Sequence[str] = tuple(ALL_FACES), rigid_faces=None, rfields: Sequence[str] = ("vz",),
+                 stressfree_faces: Sequence[str] = ("dummy",), tsnaps=None, snaps_field: Optional[str] = None,
+                 verbose: bool = False, nworker: Optional[int] = None, rank: int = 0, device: int = -1,
+                 shot_batch: int = 0, upstream_3d_swap: bool = True):
+        N = medium.ndims
+        npw = attrib_mod.npw
+        assert (attrib_mod.physics == "elastic") == medium.elastic, "attrib_mod / medium mismatch"
+        pml_faces = [str(f).lstrip(":") for f in pml_faces]
+        rigid_faces = pml_faces if rigid_faces is None else [str(f).lstrip(":") for f in rigid_faces]
+        rfields = [str(f).lstrip(":") for f in rfields]
+
+        # ---- normalise ageom / srcwav to npw entries (fdtd.jl:88-102)
+        if isinstance(ageom[0], AGeomss):
+            if npw == 2:
+                adj = get_adjoint_ageom(ageom)
+                srcwav = [srcwav, [Srcs(a.ns, tgrid, rfields) for a in adj]]
+                ageom = [ageom, adj]
+            else:
+                ageom, srcwav = [ageom] * npw, [srcwav] * npw
+        assert len(ageom) == npw and len(srcwav) == npw
+        fields_ok = set(wavefields_of(attrib_mod.physics, N)) | set(dfields_of(attrib_mod.physics, N))
+        for rf in rfields:
+            assert rf in fields_ok, f"rfield {rf} not a field of {attrib_mod.physics} {N}-D"
+        for sw in srcwav:
+            for s in sw:
+                for f in s.fields:
+                    assert f in fields_ok, f"source field {f} not a field of {attrib_mod.physics} {N}-D"
+        nss = len(ageom[0])
+        assert all(len(a) == nss for a in ageom), "different supersources"
+        assert tgrid.last >= srcwav[0][0].grid.last - 1e-12, "modeling time is less than source time"
+        for a in ageom:
+            for ass in a:
+                if not ass.inside(medium.grid):
+                    raise ValueError("sources or receivers not inside medium")
+        for a, sw in zip(ageom, srcwav):
+            assert all(x.ns == y.n for x, y in zip(a, sw)), "ageom and srcwav mismatch"
+
+        c = self.c = PCommon()
+        c.attrib_mod, c.medium, c.ageom, c.srcwav = attrib_mod, medium.copy(), [list(a) for a in ageom], [[s.copy() for s in sw] for sw in srcwav]
+        c.pml_faces = pml_faces
+        c.rigid_faces = list(dict.fromkeys(list(rigid_faces) + pml_faces))          # fdtd.jl:215
+        c.stressfree_faces = [str(f).lstrip(":") for f in stressfree_faces]
+        c.rfields, c.tgrid, c.verbose = rfields, tgrid, verbose
+        c.upstream_3d_swap = upstream_3d_swap
+        c.exmedium = padarray(medium, NPML, pml_faces)                                # fdtd.jl:137
+        c.mparams = medium_parameters(attrib_mod)
+        c.ref_mod = {name: c.exmedium.ref(name) for name in c.mparams}               # fdtd.jl:175
+        n = [len(g) for g in c.exmedium.grid]
+        nt = len(tgrid)
+        # fc / ic (fdtd.jl:301-332): Float32 copies of Float64 host values
+        ds = [g.step for g in c.exmedium.grid]
+        dt = tgrid.step
+        c.fc = {"dt": F32(dt), "dtI": F32(1.0 / dt)}
+        for d, s in zip(dim_names(N), ds):
+            c.fc["d" + d] = F32(s)
+            c.fc["d" + d + "I"] = F32(1.0 / s)
+        c.ic = {**{"n" + d: nn for d, nn in zip(dim_names(N), n)}, "nt": nt, "nsls": 0, "npw": npw}
+        c.gradients = {name: np.zeros(n, F32, order="F") for name in c.mparams}      # fdtd.jl:164-170
+        c.data = [make_recs(tgrid, ageom[ip], rfields) for ip in range(npw)]         # fdtd.jl:194
+        if snaps_field is not None:
+            tsn = [0.5 * (tgrid.last + tgrid.first)] if tsnaps is None else list(tsnaps)
+            c.itsnaps = [int(np.argmin(np.abs(tgrid.values - t))) + 1 for t in tsn]   # fdtd.jl:181-185
+            c.snaps_field = str(snaps_field).lstrip(":")
+        else:
+            c.itsnaps, c.snaps_field = [], None
+
+        # ---- shots -> workers (fdtd.jl:246-255); one rank = one GPU
+        if nworker is None:
+            nworker = 1
+        nworker = min(nss, nworker)
+        self.sschunks = sschunks(nss, nworker)
+        self.rank, self.nworker = rank, nworker
+        self.local = self.sschunks[rank] if rank < nworker else range(0)
+        self._nccl = False
+
+        # ---- engine (replaces P_x_worker_x_pw / P_x_worker_x_pw_x_ss, fdtd.jl:340-528)
+        cfg = E.GpiConfig()
+        cfg.abi_version, cfg.ndims, cfg.order = E.ABI_VERSION, N, ORDER
+        cfg.physics = E.ACOUSTIC if attrib_mod.physics == "acoustic" else E.ELASTIC
+        cfg.n[0], cfg.n[1], cfg.n[2] = n[0], (n[1] if N == 3 else 1), n[-1]
+        cfg.nt, cfg.npml, cfg.nbound = nt, NPML, NBOUND
+        cfg.pml_faces, cfg.rigid_faces = E.face_mask(c.pml_faces), E.face_mask(c.rigid_faces)
+        cfg.stressfree_faces = E.face_mask(c.stressfree_faces)
+        cfg.npw, cfg.nshots = npw, max(len(self.local), 1)
+        cfg.store_boundary = 1 if attrib_mod.mode == "forward_save" else 0            # fdtd.jl:445-455
+        cfg.nsnaps = len(c.itsnaps)
+        cfg.snaps_field = E.FIELD[c.snaps_field] if c.snaps_field else 0
+        cfg.device, cfg.shot_batch = device, shot_batch
+        cfg.dt, cfg.dtI = float(c.fc["dt"]), float(c.fc["dtI"])
+        names3 = ["z", "y", "x"]
+        for q, d in enumerate(names3):
+            cfg.d[q] = float(c.fc.get("d" + d, F32(1)))
+            cfg.dI[q] = float(c.fc.get("d" + d + "I", F32(1)))
+        self.cfg = cfg
+        self.engine = self._make_engine(cfg)
+        if c.itsnaps:
+            self.engine.set_snap_steps(c.itsnaps)
+
+        self.update_medium(medium)                                                     # fdtd.jl:240
+        self.update_ageom(c.ageom)                                                     # fdtd.jl:522-525
+        self.update_srcwav(c.srcwav, [1] * npw)                                        # fdtd.jl:274
+        self.update_pml()                                                              # fdtd.jl:279
+
+    # the only place the backend is chosen: the CUDA library, or nothing
+    def _make_engine(self, cfg):
+        return E.Engine(cfg)
+
+    # ---------------------------------------------------------------------------------------------
+    # update!(pa, medium)  (medium.jl:131-140)
+    # ---------------------------------------------------------------------------------------------
+    def update_medium(self, medium: Medium):
+        c = self.c
+        c.medium = medium.copy()
+        c.exmedium = padarray(c.medium, NPML, c.pml_faces)
+        c.mod = {name: c.exmedium[name] for name in c.mparams}
+        for name in c.mparams:
+            self.engine.set_medium(name, c.mod[name])
+        self.engine.update_dmod()
+
+    # update!(pa, m, mparams): log-parameterised model vector (medium.jl:31-52)
+    def update_model(self, m: np.ndarray, mparams=None):
+        c = self.c
+        mparams = c.mparams if mparams is None else mparams
+        chunks = np.split(np.asarray(m, F32), len(mparams))
+        for x, name in zip(chunks, mparams):
+            inner = view_inner(c.mod[name], NPML, c.pml_faces)
+            inner[...] = (np.exp(x.reshape(inner.shape, order="F")) * c.ref_mod[name]).astype(F32)
+            self.engine.set_medium(name, c.mod[name])
+        self.engine.update_dmod()
+
+    def get_modelvector(self, mparams=None) -> np.ndarray:
+        """medium.jl:3-9, 55-76"""
+        c = self.c
+        mparams = c.mparams if mparams is None else mparams
+        out = []
+        for name in mparams:
+            inner = view_inner(c.mod[name], NPML, c.pml_faces)
+            out.append(np.log(inner * (F32(1) / c.ref_mod[name])).astype(F32).ravel(order="F"))
+        return np.concatenate(out)
+
+    # ---------------------------------------------------------------------------------------------
+    # update!(pa, ageom[, Srcs|Recs])  (ageom.jl:33-98)
+    # ---------------------------------------------------------------------------------------------
+    def update_ageom(self, ageom, what: str = "both"):
+        c = self.c
+        if isinstance(ageom[0], AGeomss):
+            ageom = [ageom]
+        names = dim_names(c.medium.ndims)
+        for ipw in range(c.ic["npw"]):
+            c.ageom[ipw] = list(ageom[ipw])
+            for issp, iss in enumerate(self.local):
+                a = c.ageom[ipw][iss]
+                if what in ("both", "srcs"):
+                    pts = [[a.s[d][i] for d in names] for i in range(a.ns)]
+                    for sf in c.srcwav[ipw][iss].fields:
+                        cp, rv, nz, _ = get_proj_matrix(sf, c.exmedium.grid, pts, c.upstream_3d_swap)
+                        self.engine.set_sparse(E.SPRAY, ipw, issp, sf, cp, rv, nz)
+                if what in ("both", "recs"):
+                    pts = [[a.r[d][i] for d in names] for i in range(a.nr)]
+                    for rf in c.rfields:
+                        cp, rv, nz, _ = get_proj_matrix(rf, c.exmedium.grid, pts, c.upstream_3d_swap)
+                        self.engine.set_sparse(E.INTERP, ipw, issp, rf, cp, rv, nz)
+
+    # ---------------------------------------------------------------------------------------------
+    # update!(pa, srcwav, src_types)  (source.jl:192-246)
+    # ---------------------------------------------------------------------------------------------
+    def update_srcwav(self, srcwav, src_types=None):
+        c = self.c
+        if isinstance(srcwav[0], Srcs):
+            srcwav = [srcwav]
+        npw = c.ic["npw"]
+        assert len(srcwav) == npw
+        src_types = [1] * npw if src_types is None else list(src_types)
+        old_fields = [[list(s.fields) for s in sw] for sw in c.srcwav]
+        c.srcwav = [[s.copy() for s in sw] for sw in srcwav]
+        nt = c.ic["nt"]
+        for ipw in range(npw):
+            freqmin, freqmax, freqpeaks = 0.0, np.inf, []
+            for issp, iss in enumerate(self.local):
+                s = c.srcwav[ipw][iss]
+                for f in old_fields[ipw][iss]:
+                    if f not in s.fields:
+                        self.engine.set_wavelets(ipw, issp, f, None)
+                peaks = []
+                for sf in s.fields:                                         # fill_wavelets! (source.jl:24-58)
+                    w = np.zeros((nt, s.n), F32, order="F")
+                    w[: len(s.grid), :] = s.d[sf][:nt, :]
+                    w = get_source(w, sf, src_types[ipw])
+                    self.engine.set_wavelets(ipw, issp, sf, w)
+                    if not np.all(np.isclose(w, 0.0)):
+                        freqmax = min(findfreq(w, s.grid, "max"), freqmax)
+                        freqmin = max(findfreq(w, s.grid, "min"), freqmin)
+                        peaks.append(findfreq(w, s.grid, "peak"))
+                if peaks:
+                    freqpeaks.append(float(np.mean(peaks)))
+            # source fields may have changed => rebuild the spray matrices (source.jl:225)
+            self.update_ageom(c.ageom, "srcs")
+            if ipw == 0 and freqpeaks:
+                c.fc["freqmin"], c.fc["freqmax"] = F32(freqmin), F32(freqmax)
+                c.fc["freqpeak"] = F32(np.mean(freqpeaks))
+        if "freqpeak" not in c.fc:
+            c.fc["freqmin"], c.fc["freqmax"], c.fc["freqpeak"] = F32(0), F32(np.inf), F32(0)
+
+    # update_pml!(pac)  (cpml.jl:144-155)
+    def update_pml(self):
+        c = self.c
+        N = c.medium.ndims
+        vb = c.exmedium.bounds("vp")
+        velavg = F32((vb[0] + vb[1]) / F32(2))
+        c.pml = pml_coefficients(dfields_of(c.attrib_mod.physics, N), c.exmedium.grid, c.medium.grid,
+                                 c.pml_faces, float(c.fc["dt"]), float(velavg), float(c.fc["freqpeak"]), NPML)
+        for df, (a, b, kI) in c.pml.items():
+            self.engine.set_pml(df, a, b, kI)
+
+    # ---------------------------------------------------------------------------------------------
+    # update!(pa)  (propagate.jl:74-135)
+    # ---------------------------------------------------------------------------------------------
+    def get_update_parameters(self):
+        """propagate.jl:38-60"""
+        c = self.c
+        if c.ic["npw"] == 1:
+            return dict(activepw=[1], src_flags=[True], rec_flags=[True])
+        if c.attrib_mod.mode == "adjoint":
+            return dict(activepw=[1, 2], src_flags=[True, True], rec_flags=[False, False])
+        if c.attrib_mod.mode in ("forward", "forward_save"):
+            return dict(activepw=[1], src_flags=[True, False], rec_flags=[True, False])
+        raise ValueError(f"unknown mode {c.attrib_mod.mode}")
+
+    def update(self, upa=None):
+        c = self.c
+        upa = self.get_update_parameters() if upa is None else upa
+        mode = c.attrib_mod.mode
+        # initialize!(pa.c), initialize_boundary!, initialize!(localpart)  (propagate.jl:82-94, types.jl:41-176)
+        for g in c.gradients.values():
+            g[...] = 0
+        for dat in c.data:
+            for d in dat:
+                d.fill(0.0)
+        what = E.RESET_RECORDS | E.RESET_GRADIENTS | E.RESET_SNAPS | E.RESET_WAVEFIELDS
+        if mode == "forward_save":
+            what |= E.RESET_BOUNDARY
+        self.engine.reset(what)
+        if len(self.local):
+            # mod_x_proc! (propagate.jl:100-106)
+            self.engine.run(mode, upa["activepw"], upa["src_flags"])
+        # sum_grads! (propagate.jl:110-117, gradient.jl:2-11)
+        if mode == "adjoint" and c.ic["npw"] == 2 and c.attrib_mod.physics == "acoustic":
+            if self._nccl:
+                self.engine.allreduce_gradients()
+            for name in ("invK", "rho"):
+                c.gradients[name][...] = self.engine.get_gradient(name)
+        # update_datamat! + update_data! (propagate.jl:119-133, receiver.jl:17-46)
+        for ipw in upa["activepw"]:
+            if upa["rec_flags"][ipw - 1]:
+                for rf in c.rfields:
+                    for issp, iss in enumerate(self.local):
+                        nr = c.ageom[ipw - 1][iss].nr
+                        c.data[ipw - 1][iss].d[rf][...] = self.engine.get_records(ipw - 1, issp, rf, nr)
+        return self.engine.timers()
+
+    # multi-GPU plumbing: the ncclUniqueId travels through whatever the host already has
+    def init_nccl(self, uid: Optional[bytes], nranks: int):
+        self.engine.nccl_init(uid, self.rank, nranks)
+        self._nccl = True
+
+    # pa[:data, i], pa[:snaps, i] (getprop.jl:10-31)
+    def __getitem__(self, key):
+        if isinstance(key, tuple):
+            what, ipw = key
+        else:
+            what, ipw = key, 1
+        what = str(what).lstrip(":")
+        c = self.c
+        if what == "data":
+            return c.data[ipw - 1]
+        if what == "snaps":
+            return [[self.engine.get_snap(ipw - 1, issp, k) for k in range(len(c.itsnaps))] for issp, _ in enumerate(self.local)]
+        if what in ("medium", "exmedium", "ageom", "srcwav"):
+            return getattr(c, what)
+        raise KeyError(key)
+
+
+def SeisForwExpt(attrib_mod, **kw) -> PFdtd:
+    """`SeisForwExpt(attrib_mod; medium, ageom, srcwav, tgrid, ...)` (fdtd.jl:43-47)."""
+    return PFdtd(attrib_mod, **kw)
+
+
+def update(pa: PFdtd, *args, **kw):
+    """Dispatch like the reference's `update!` methods."""
+    if not args:
+        return pa.update(**kw)
+    a = args[0]
+    if isinstance(a, Medium):
+        return pa.update_medium(a)
+    if isinstance(a, np.ndarray):
+        return pa.update_model(a, *args[1:])
+    first = a[0][0] if isinstance(a[0], (list, tuple)) else a[0]
+    if isinstance(first, Srcs):
+        return pa.update_srcwav(a, *args[1:])
+    if isinstance(first, AGeomss):
+        return pa.update_ageom(a)
+    raise TypeError("no method update! for these arguments")
+
+
+# --------------------------------------------------------------------------------------------------
+# FWI objective and gradient (src/fdtd/func_grad.jl:1-49, src/database/database.jl:355-379)
+# --------------------------------------------------------------------------------------------------
+def l2_lossvalue(dobs, data) -> float:
+    """`lossvalue(L2DistLoss(), dobs, data)`: sum over shots, fields, samples of (d1 - d2)^2."""
+    tot = 0.0
+    for a, b in zip(dobs, data):
+        for f in a.fields:
+            tot += float(np.sum((a.d[f].astype(np.float64) - b.d[f].astype(np.float64)) ** 2))
+    return tot
+
+
+def l2_adjoint_source(buffer, dobs, data):
+    """`gradient!(buffer, loss, dobs, data)`: g = deriv(L2DistLoss(), dobs, data) element-wise
+    (database.jl:369-373).  With LossFunctions 0.11's (output, target) order this is 2*(dobs - data)
+    (third-party convention)."""
+    for g, a, b in zip(buffer, dobs, data):
+        for f in g.fields:
+            g.d[f][...] = F32(2) * (a.d[f] - b.d[f])
+
+
+def lossvalue(m, dobs, pa: PFdtd, mparams=None) -> float:
+    """func_grad.jl:1-9"""
+    pa.update_model(m, mparams)
+    mode_save = pa.c.attrib_mod.mode
+    pa.c.attrib_mod.mode = "forward_save"
+    pa.update_srcwav(pa.c.srcwav, [1, 0])
+    pa.update()
+    pa.c.attrib_mod.mode = mode_save
+    return l2_lossvalue(dobs, pa.c.data[0])
+
+
+def gradient(g: np.ndarray, m, dobs, pa: PFdtd, mparams=None) -> float:
+    """`gradient!(g, m, loss, dobs, pa, mparams)` (func_grad.jl:11-49).  Returns the loss of the
+    forward pass (the reference re-evaluates it on `pa.c.data[1]` after the adjoint pass has
+    zeroed that container -- an upstream slip we do not copy)."""
+    c = pa.c
+    mparams = c.mparams if mparams is None else mparams
+    pa.update_model(m, mparams)
+    mode_save = c.attrib_mod.mode
+    c.attrib_mod.mode = "forward_save"
+    pa.update_srcwav(c.srcwav, [1, 0])
+    pa.update()
+    loss = l2_lossvalue(dobs, c.data[0])
+    l2_adjoint_source(c.srcwav[1], dobs, c.data[0])
+    for s in c.srcwav[1]:
+        s.reverse()
+    pa.update_srcwav(c.srcwav, [-1, 1])
+    c.attrib_mod.mode = "adjoint"
+    pa.update()
+    chunks = np.split(np.asarray(m, F32), len(mparams))
+    gch = np.split(g, len(mparams))
+    for x, gi, name in zip(chunks, gch, mparams):
+        r = c.ref_mod[name]
+        gm = view_inner(c.gradients[name], NPML, c.pml_faces)
+        gm[...] = gm * np.exp(x.reshape(gm.shape, order="F")) * r      # chain rule (func_grad.jl:36-39)
+        gi[...] = gm.ravel(order="F")
+    c.attrib_mod.mode = mode_save
+    return loss

@@ -1,0 +1,188 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes wrapper of the CPU restatement (oracle/fdtd_oracle.c).
+
+`OracleEngine` has the method surface of `geophyinv_jl_b200.Engine`, so the SAME host layer
+(Medium/AGeom/Srcs -> C-ABI calls) can drive either the CUDA engine (product) or this checker:
+`OraclePFdtd` is `PFdtd` with `_make_engine` overridden.  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this module; the product package never
+does, and has no code path that could reach it.
+
+Parity status: UNPINNED against upstream artefacts (the reference ships no golden vectors for this
+path and Julia is not installed here); pinned by the reference's own test invariants instead
+(tests/test_oracle_invariants.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+import geophyinv_jl_b200 as G  # noqa: E402
+from geophyinv_jl_b200 import engine as E  # noqa: E402
+
+_libs = {}
+
+
+def build():
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+def load(dtype=np.float32):
+    key = np.dtype(dtype).itemsize
+    if key in _libs:
+        return _libs[key]
+    path = os.path.join(_HERE, "liboracle_f32.so" if key == 4 else "liboracle_f64.so")
+    if not os.path.exists(path):
+        build()
+    lib = C.CDLL(path)
+    assert lib.orc_real_size() == key
+    lib.orc_last_error.restype = C.c_char_p
+    lib.orc_last_error.argtypes = [C.c_void_p]
+    lib.orc_last_run_seconds.restype = C.c_double
+    lib.orc_last_run_seconds.argtypes = [C.c_void_p]
+    _libs[key] = lib
+    return lib
+
+
+class OracleEngine:
+    def __init__(self, cfg: E.GpiConfig, dtype=np.float32, threads: int | None = None):
+        self.dtype = np.dtype(dtype)
+        self.lib = load(dtype)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        if threads:
+            self.lib.orc_set_threads(int(threads))
+        self.threads = threads or self.lib.orc_max_threads()
+        if self.lib.orc_create(C.byref(cfg), C.byref(self.h)) != 0:
+            raise RuntimeError(self.lib.orc_last_error(None).decode())
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.lib.orc_last_error(self.h).decode())
+
+    def _a(self, a):
+        return np.ascontiguousarray(np.asarray(a, dtype=self.dtype).ravel(order="F"))
+
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    def close(self):
+        if self.h and self.h.value:
+            self.lib.orc_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def field_shape(self, field):
+        out = (C.c_int32 * 3)()
+        if self.lib.orc_field_shape(self.cfg.ndims, E.FIELD[field], self.cfg.n, out) != 0:
+            raise RuntimeError(f"no field {field}")
+        sh = tuple(out)
+        return sh if self.cfg.ndims == 3 else (sh[0], sh[2])
+
+    def set_medium(self, name, a):
+        a = self._a(a); self._ck(self.lib.orc_set_medium(self.h, E.PARAM[name], self._p(a)))
+
+    def get_medium(self, name):
+        shp = self.field_shape("p" if self.cfg.physics == E.ACOUSTIC else "tauxx")
+        out = np.empty(int(np.prod(shp)), self.dtype)
+        self._ck(self.lib.orc_get_medium(self.h, E.PARAM[name], self._p(out)))
+        return out.reshape(shp, order="F")
+
+    def update_dmod(self):
+        self._ck(self.lib.orc_update_dmod(self.h))
+
+    def set_pml(self, dfield, a, b, kI):
+        a, b, kI = self._a(a), self._a(b), self._a(kI)
+        self._ck(self.lib.orc_set_pml(self.h, E.FIELD[dfield], self._p(a), self._p(b), self._p(kI)))
+
+    def set_sparse(self, kind, ipw, issp, field, colptr, rowval, nzval):
+        colptr = np.ascontiguousarray(colptr, np.int64); rowval = np.ascontiguousarray(rowval, np.int64)
+        nzval = self._a(nzval)
+        self._ck(self.lib.orc_set_sparse(self.h, kind, ipw, issp, E.FIELD[field], colptr.size - 1,
+                                         self._p(colptr), self._p(rowval), self._p(nzval)))
+
+    def set_wavelets(self, ipw, issp, field, w):
+        if w is None:
+            self._ck(self.lib.orc_set_wavelets(self.h, ipw, issp, E.FIELD[field], 0, None)); return
+        w = np.asarray(w)
+        wf = self._a(w)
+        self._ck(self.lib.orc_set_wavelets(self.h, ipw, issp, E.FIELD[field], w.shape[1], self._p(wf)))
+
+    def run(self, mode, activepw=(1,), src_flags=(True,)):
+        am = sum(1 << (p - 1) for p in activepw)
+        sm = sum(1 << i for i, f in enumerate(src_flags) if f)
+        self._ck(self.lib.orc_run(self.h, E.MODE[mode], am, sm))
+
+    def advance(self, it0, nsteps):
+        self._ck(self.lib.orc_advance(self.h, int(it0), int(nsteps)))
+
+    def get_records(self, ipw, issp, field, nr):
+        out = np.empty(self.cfg.nt * nr, self.dtype)
+        self._ck(self.lib.orc_get_records(self.h, ipw, issp, E.FIELD[field], self._p(out)))
+        return out.reshape((self.cfg.nt, nr), order="F")
+
+    def get_gradient(self, name):
+        shp = self.field_shape("p")
+        out = np.empty(int(np.prod(shp)), self.dtype)
+        self._ck(self.lib.orc_get_gradient(self.h, E.PARAM[name], self._p(out)))
+        return out.reshape(shp, order="F")
+
+    def get_field(self, ipw, field, ibatch=0):
+        shp = self.field_shape(field)
+        out = np.empty(int(np.prod(shp)), self.dtype)
+        self._ck(self.lib.orc_get_field(self.h, ipw, ibatch, E.FIELD[field], self._p(out)))
+        return out.reshape(shp, order="F")
+
+    def set_field(self, ipw, field, a, ibatch=0):
+        a = self._a(a); self._ck(self.lib.orc_set_field(self.h, ipw, ibatch, E.FIELD[field], self._p(a)))
+
+    def get_dmod(self, idx):
+        shape = (C.c_int32 * 3)()
+        self._ck(self.lib.orc_get_dmod(self.h, idx, None, shape))
+        out = np.empty(int(np.prod(tuple(shape))), self.dtype)
+        self._ck(self.lib.orc_get_dmod(self.h, idx, self._p(out), shape))
+        sh = tuple(shape)
+        return out.reshape(sh if self.cfg.ndims == 3 else (sh[0], sh[2]), order="F")
+
+    def set_snap_steps(self, its):
+        its = np.ascontiguousarray(its, np.int32)
+        self._ck(self.lib.orc_set_snap_steps(self.h, its.size, self._p(its)))
+
+    def get_snap(self, ipw, issp, isnap):
+        shp = self.field_shape(E.FIELDS[self.cfg.snaps_field])
+        out = np.empty(int(np.prod(shp)), self.dtype)
+        self._ck(self.lib.orc_get_snap(self.h, ipw, issp, isnap, self._p(out)))
+        return out.reshape(shp, order="F")
+
+    def reset(self, what):
+        self._ck(self.lib.orc_reset(self.h, what))
+
+    def timers(self):
+        s = self.lib.orc_last_run_seconds(self.h)
+        return {"run_ms": s * 1e3, "steps": 0.0, "cell_updates": 0.0, "stencil_ms": 0.0, "launches": 0.0}
+
+    def allreduce_gradients(self):
+        pass
+
+
+class OraclePFdtd(G.PFdtd):
+    """The product's host layer driving the CPU restatement instead of the GPU (tests only)."""
+    oracle_dtype = np.float32
+    oracle_threads = None
+
+    def _make_engine(self, cfg):
+        return OracleEngine(cfg, self.oracle_dtype, self.oracle_threads)
+
+
+class OraclePFdtd64(OraclePFdtd):
+    oracle_dtype = np.float64

@@ -1,0 +1,150 @@
+"""Parity of the CUDA engine against the CPU restatement (oracle/) through the C ABI.
+
+Gates (BASELINE.json north_star): receiver records rel-L2 <= 1e-5, FWI gradients <= 1e-4 in Float32.
+Because the kernels reproduce the reference's Float32 operation order without FMA contraction, the
+expected result is bit-identical records; the tests assert the gate and report exactness.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+REC_TOL = 1e-5      # north_star: relative L2 misfit on receiver records
+GRAD_TOL = 1e-4     # north_star: relative L2 misfit on FWI gradients
+
+
+def both(G, O, attrib_factory, kw, **extra):
+    pg = G.SeisForwExpt(attrib_factory(), **kw, **extra)
+    po = O.OraclePFdtd(attrib_factory(), **kw)
+    return pg, po
+
+
+def compare_records(pg, po, ipw=0):
+    worst = 0.0
+    exact = True
+    for iss in range(len(pg.c.data[ipw])):
+        for f in pg.c.rfields:
+            a, b = pg.c.data[ipw][iss].d[f], po.c.data[ipw][iss].d[f]
+            assert np.isfinite(a).all()
+            assert np.abs(b).max() > 0, "oracle record is empty; the case does not test anything"
+            worst = max(worst, rel_l2(a, b))
+            exact &= bool(np.array_equal(a, b))
+    return worst, exact
+
+
+def compare_fields(pg, po, fields, ipw=0):
+    worst = 0.0
+    for f in fields:
+        a, b = pg.engine.get_field(ipw, f), po.engine.get_field(ipw, f)
+        if np.abs(b).max() == 0:
+            assert np.abs(a).max() == 0
+            continue
+        worst = max(worst, rel_l2(a, b))
+    return worst
+
+
+@pytest.mark.parametrize("sfield,rfields", [("p", ("p",)), ("vz", ("vz", "vx", "p")), ("vx", ("vx",))])
+def test_c1_acoustic2d_records(G, O, sfield, rfields):
+    """BASELINE config 1: 2-D acoustic 201x201, Ricker, 64 receivers, 1000 steps, CPML."""
+    from geophyinv_jl_b200.host import gallery
+    kw = gallery.c1_acou2d_homo(sfield=sfield, rfields=rfields)
+    pg, po = both(G, O, G.FdtdAcoustic, kw)
+    pg.update(); po.update()
+    err, exact = compare_records(pg, po)
+    print(f"C1 {sfield}->{rfields}: rel-L2 {err:.3e}, bit-exact {exact}")
+    assert err <= REC_TOL
+    assert compare_fields(pg, po, ["p", "vx", "vz"]) <= REC_TOL
+
+
+def test_acoustic2d_multishot_batches(G, O):
+    """Several supersources: batched on the GPU (shot_batch=3 -> ragged last batch), serial in the oracle."""
+    from geophyinv_jl_b200.host import gallery
+    kw = gallery.c2_acou2d_layered(nz=90, nx=140, nt=300, nss=5, nr=20, fq=15.0)
+    pg, po = both(G, O, G.FdtdAcoustic, kw, shot_batch=3)
+    pg.update(); po.update()
+    err, exact = compare_records(pg, po)
+    print(f"2-D acoustic 5 shots: rel-L2 {err:.3e}, bit-exact {exact}")
+    assert err <= REC_TOL
+
+
+@pytest.mark.parametrize("stressfree", [False, True])
+def test_elastic2d_records(G, O, stressfree):
+    from geophyinv_jl_b200.host import gallery
+    kw = gallery.elastic2d(stressfree=stressfree)
+    pg, po = both(G, O, G.FdtdElastic, kw)
+    pg.update(); po.update()
+    err, exact = compare_records(pg, po)
+    print(f"2-D elastic stressfree={stressfree}: rel-L2 {err:.3e}, bit-exact {exact}")
+    assert err <= REC_TOL
+    assert compare_fields(pg, po, ["tauxx", "tauzz", "tauxz", "vx", "vz"]) <= REC_TOL
+
+
+def test_elastic2d_stress_source(G, O):
+    from geophyinv_jl_b200.host import gallery
+    kw = gallery.elastic2d(sfield="tauxx", rfields=("vz", "vx"))
+    pg, po = both(G, O, G.FdtdElastic, kw)
+    pg.update(); po.update()
+    err, exact = compare_records(pg, po)
+    print(f"2-D elastic explosive source: rel-L2 {err:.3e}, bit-exact {exact}")
+    assert err <= REC_TOL
+
+
+def test_acoustic3d_records(G, O):
+    from geophyinv_jl_b200.host import gallery
+    kw = gallery.acou3d()
+    pg, po = both(G, O, G.FdtdAcoustic, kw)
+    pg.update(); po.update()
+    err, exact = compare_records(pg, po)
+    print(f"3-D acoustic: rel-L2 {err:.3e}, bit-exact {exact}")
+    assert err <= REC_TOL
+    assert compare_fields(pg, po, ["p", "vx", "vy", "vz"]) <= REC_TOL
+
+
+@pytest.mark.parametrize("stressfree", [False, True])
+def test_c3_elastic3d_reduced(G, O, stressfree):
+    """BASELINE config 3 down-sized (40^3 + CPML = 122^3, 150 steps): the roofline kernel's parity case."""
+    from geophyinv_jl_b200.host import gallery
+    kw = gallery.c3_elastic3d(n=40, nt=150, nr=12, fq=25.0, rfields=("vz", "vx", "vy"), stressfree=stressfree)
+    pg, po = both(G, O, G.FdtdElastic, kw)
+    pg.update(); po.update()
+    err, exact = compare_records(pg, po)
+    print(f"3-D elastic stressfree={stressfree}: rel-L2 {err:.3e}, bit-exact {exact}")
+    assert err <= REC_TOL
+    assert compare_fields(pg, po, ["tauxx", "tauyy", "tauzz", "tauxy", "tauxz", "tauyz", "vx", "vy", "vz"]) <= REC_TOL
+
+
+def test_dmod_matches_oracle(G, O):
+    """update_dmod! (medium.jl:143-221): coefficient arrays agree bit for bit (checked through the
+    wavefield after one step with unit fields is overkill; compare the medium round trip instead)."""
+    from geophyinv_jl_b200.host import gallery
+    kw = gallery.elastic2d(nt=5)
+    pg, po = both(G, O, G.FdtdElastic, kw)
+    for name in ("invlambda", "invmu", "rho"):
+        assert np.array_equal(pg.engine.get_medium(name), po.engine.get_medium(name))
+
+
+def test_fwi_gradient_acoustic2d(G, O):
+    """BASELINE config 4 down-sized: forward_save + adjoint + imaging; gradients w.r.t. invK and rho."""
+    from geophyinv_jl_b200.host import gallery
+    kw, true = gallery.c4_fwi2d(nz=70, nx=110, nt=500, nss=3, nr=24, fq=10.0)
+    mk = lambda cls: cls(G.FdtdAcoustic("forward_save"), **kw)
+    pg, po = G.PFdtd(G.FdtdAcoustic("forward_save"), **kw, shot_batch=2), O.OraclePFdtd(G.FdtdAcoustic("forward_save"), **kw)
+    # observed data from the true medium (oracle), then gradient at the model medium with both
+    pt = O.OraclePFdtd(G.FdtdAcoustic(), **{**kw, "medium": true})
+    pt.update()
+    dobs = [d.copy() for d in pt.c.data[0]]
+    m = pg.get_modelvector()
+    gg, go = np.zeros_like(m), np.zeros_like(m)
+    lg = G.gradient(gg, m, dobs, pg)
+    lo = G.gradient(go, m, dobs, po)
+    assert abs(lg - lo) <= 1e-5 * abs(lo)
+    half = m.size // 2
+    eK, eR = rel_l2(gg[:half], go[:half]), rel_l2(gg[half:], go[half:])
+    print(f"FWI gradient: invK rel-L2 {eK:.3e}, rho rel-L2 {eR:.3e}, loss {lg:.6e} vs {lo:.6e}")
+    assert np.abs(go[:half]).max() > 0 and np.abs(go[half:]).max() > 0
+    assert eK <= GRAD_TOL and eR <= GRAD_TOL
+    # stacked raw gradients on the extended grid too
+    for name in ("invK", "rho"):
+        assert rel_l2(pg.engine.get_gradient(name), po.engine.get_gradient(name)) <= GRAD_TOL
