@@ -151,6 +151,9 @@ struct gpi_handle {
     PostDesc *post_v = nullptr, *post_s = nullptr, *h_post_v = nullptr, *h_post_s = nullptr;
     float* stage = nullptr;  size_t stage_floats = 0;       // pinned host staging
     gpi_timers timers{};
+    std::vector<cudaEvent_t> evpool;  size_t evused = 0;   // sampled per-kernel timing (pairs)
+    std::vector<int> evkind;                                // 0 = velocity kernel, 1 = stress kernel
+    int sample_every = 16;
     // tuning
     dim3 blk3{64, 2, 2}, blk2{128, 2, 1};
     // nccl
@@ -261,7 +264,21 @@ void launch_step_kernels(gpi_handle* h, const StepArgs& a, bool vel, int nbatch)
     if (vel) k_vel<ND, EL><<<grd, blk, 0, h->stream>>>(h->g, a);
     else     k_stress<ND, EL><<<grd, blk, 0, h->stream>>>(h->g, a);
 }
-void launch_step(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
+// one CUDA-event pair around a sampled launch; the pair's elapsed time is the kernel's duration because
+// the stream is in-order (the first event completes when the preceding work has drained)
+cudaEvent_t sample_event(gpi_handle* h) {
+    if (h->evused == h->evpool.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        h->evpool.push_back(e);
+    }
+    return h->evpool[h->evused++];
+}
+void launch_step(gpi_handle* h, const StepArgs& a, bool vel, int nbatch, bool sample = false) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (sample) { e0 = sample_event(h); e1 = sample_event(h); }
+    if (e0 && e1) { cudaEventRecord(e0, h->stream); h->evkind.push_back(vel ? 0 : 1); }
+    struct Closer { gpi_handle* h; cudaEvent_t e; ~Closer() { if (e) cudaEventRecord(e, h->stream); } } closer{h, (e0 && e1) ? e1 : nullptr};
     if (h->nd == 2 && !h->el) launch_step_kernels<2, 0>(h, a, vel, nbatch);
     else if (h->nd == 2)      launch_step_kernels<2, 1>(h, a, vel, nbatch);
     else if (!h->el)          launch_step_kernels<3, 0>(h, a, vel, nbatch);
@@ -479,6 +496,7 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (cudaSetDevice(h->device) != cudaSuccess) { g_create_err = "gpi_create: cudaSetDevice failed"; delete h; return 1; }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_err = "gpi_create: stream creation failed"; delete h; return 1; }
     h->own_stream = true;
+    if (const char* e = getenv("GPI_SAMPLE_EVERY")) h->sample_every = atoi(e);
     if (const char* e = getenv("GPI_BLOCK3")) { int a, b, c3; if (sscanf(e, "%d,%d,%d", &a, &b, &c3) == 3 && a * b * c3 <= 256) h->blk3 = dim3(a, b, c3); }
     if (const char* e = getenv("GPI_BLOCK2")) { int a, b; if (sscanf(e, "%d,%d", &a, &b) == 2 && a * b <= 256) h->blk2 = dim3(a, b, 1); }
     if (create_impl(h)) { g_create_err = "gpi_create: " + h->err; gpi_destroy(h); return 1; }
@@ -511,6 +529,7 @@ extern "C" int gpi_destroy(gpi_handle* h) {
     if (h->stage) cudaFreeHost(h->stage);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (auto e : h->evpool) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -776,6 +795,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     int bf[3]; const int nbf = boundary_fields(h, bf);
     const int vf[3] = {GPI_VX, GPI_VY, GPI_VZ};
     h->timers = gpi_timers{};
+    h->evused = 0; h->evkind.clear();
     CU(h, cudaEventRecord(h->ev0, h->stream));
 
     for (int shot0 = 0; shot0 < h->c.nshots; shot0 += h->B) {
@@ -814,9 +834,10 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                     }
                 }
             }
-            for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], true, nb);
+            const bool sample = h->sample_every > 0 && (it % h->sample_every) == 0;
+            for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], true, nb, sample && ipw == 0);
             if (do_post_v) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_v, it, it, nt, (float)h->c.dt, 3); h->timers.launches += 1; }
-            for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], false, nb);
+            for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], false, nb, sample && ipw == 0);
             // stress sources at step it, then the pressure record of step it+1 (record! runs at the start of a step)
             if (inj_s || (rec_s && it < nt)) {
                 k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, it, it + 1, nt, (float)h->c.dt, 3);
@@ -868,6 +889,13 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     float ms = 0.f;
     CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->timers.run_ms = ms;
+    for (size_t q = 0; q < h->evkind.size(); q++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, h->evpool[2 * q], h->evpool[2 * q + 1]) != cudaSuccess) continue;
+        if (h->evkind[q] == 0) { h->timers.vel_ms += t; h->timers.vel_n += 1; }
+        else                   { h->timers.stress_ms += t; h->timers.stress_n += 1; }
+    }
+    h->timers.stencil_ms = h->timers.vel_ms + h->timers.stress_ms;
     const int npw_active = ((activepw & 1) ? 1 : 0) + ((activepw & 2) ? 1 : 0);
     h->timers.steps = (double)nt * h->c.nshots;
     h->timers.cell_updates = (double)nt * h->c.nshots * npw_active * (double)g.nz * g.ny * g.nx;

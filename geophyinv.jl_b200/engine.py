@@ -45,7 +45,8 @@ class GpiConfig(C.Structure):
 
 class GpiTimers(C.Structure):
     _fields_ = [("run_ms", C.c_double), ("steps", C.c_double), ("cell_updates", C.c_double),
-                ("stencil_ms", C.c_double), ("launches", C.c_double)]
+                ("stencil_ms", C.c_double), ("launches", C.c_double),
+                ("vel_ms", C.c_double), ("vel_n", C.c_double), ("stress_ms", C.c_double), ("stress_n", C.c_double)]
 
 
 def face_mask(faces) -> int:

@@ -16,6 +16,15 @@ from .grids import StepRange
 F32 = np.float32
 
 
+def _ricker(fq, tgrid, tpeak):
+    """Ricker on `tgrid`; when `tgrid` is shorter than the wavelet (bounded CPU samples of a big case),
+    the wavelet is generated on a long enough grid of the same step and truncated."""
+    need = int(np.ceil((tpeak + 1.5 / fq) / tgrid.step)) + 2
+    if len(tgrid) >= need:
+        return ricker(fq, tgrid, tpeak=tpeak)
+    return ricker(fq, StepRange(tgrid.first, tgrid.step, need), tpeak=tpeak)[: len(tgrid)]
+
+
 def c1_acou2d_homo(nz=201, nx=201, nt=1000, nr=64, sfield="p", rfields=("p",), nss=1, dt=2e-3, fq=10.0):
     """C1: 2-D acoustic homogeneous 201x201 (10 m), vp = rho = 2500, Ricker 10 Hz, :xwell geometry,
     PML on four faces, 1000 steps of 2 ms (media/gallery.jl:14-21, fdtd/gallery.jl:8-13)."""
@@ -23,7 +32,7 @@ def c1_acou2d_homo(nz=201, nx=201, nt=1000, nr=64, sfield="p", rfields=("p",), n
     medium = Medium.homogeneous(grid, 2500.0, 2500.0)
     tgrid = StepRange(0.0, dt, nt)
     ageom = ageom_xwell(grid, nss=nss, nr=nr)
-    wav = ricker(fq, tgrid, tpeak=0.15)
+    wav = ricker(fq, tgrid, tpeak=max(0.15, 1.5 / fq))
     if sfield != "p":
         wav = wav * 1e6                                   # fdtd/gallery.jl:12
     srcwav = make_srcwav(tgrid, ageom, [sfield], wav)
@@ -52,7 +61,7 @@ def c2_acou2d_layered(nz=350, nx=1700, nt=4000, nss=64, nr=256, dt=1e-3, fq=8.0,
     xr = np.linspace(grid[1].first + 0.02 * (grid[1].last - grid[1].first), grid[1].last - 0.02 * (grid[1].last - grid[1].first), nr)
     zs = 2.0 * d
     ageom = [AGeomss({"z": [zs], "x": [x]}, {"z": np.full(nr, zs), "x": xr}) for x in xs]
-    wav = ricker(fq, tgrid, tpeak=min(1.5 / fq + 0.02, tgrid.last - 1.5 / fq))
+    wav = _ricker(fq, tgrid, 1.5 / fq + 0.02)
     if sfield != "p":
         wav = wav * 1e6
     srcwav = make_srcwav(tgrid, ageom, [sfield], wav)
@@ -76,8 +85,8 @@ def c3_elastic3d(n=256, nt=2000, nr=64, dt=1e-3, fq=10.0, d=10.0, seed=1234, sfi
     src = {"z": [0.5 * L + 0.3 * d], "y": [0.5 * L + 0.2 * d], "x": [0.5 * L + 0.1 * d]}
     rec = {"z": np.full(nr, 0.25 * L + 0.4 * d), "y": np.full(nr, 0.5 * L + 0.2 * d), "x": np.linspace(0.1 * L, 0.9 * L, nr)}
     ageom = [AGeomss(src, rec)]
-    tpeak = min(1.5 / fq + 0.01, tgrid.last - 1.5 / fq)
-    wav = ricker(fq, tgrid, tpeak=tpeak) * (1e6 if sfield.startswith("v") else 1.0)
+    tpeak = 1.5 / fq + 0.01
+    wav = _ricker(fq, tgrid, tpeak) * (1e6 if sfield.startswith("v") else 1.0)
     srcwav = make_srcwav(tgrid, ageom, [sfield], wav)
     kw = dict(medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=list(rfields))
     if stressfree:

@@ -111,6 +111,10 @@ typedef struct gpi_timers {
     double cell_updates;      /* extended-grid cell updates executed        */
     double stencil_ms;        /* device time inside the two stencil kernels */
     double launches;          /* kernels launched by the last gpi_run       */
+    /* per-kernel CUDA-event samples taken inside the last gpi_run (every GPI_SAMPLE_EVERY-th step,
+     * default 16; pw 1 launches only): summed duration and number of sampled launches */
+    double vel_ms, vel_n;     /* fused velocity kernel  (update_dstress! + update_v!)  */
+    double stress_ms, stress_n; /* fused stress kernel  (update_dv! + update_stress!)  */
 } gpi_timers;
 
 typedef struct gpi_handle gpi_handle;

@@ -1,0 +1,64 @@
+"""Worker of tests/test_multirank_gloo.py (launched by torch.distributed.run, world_size 2, gloo, CPU).
+Exercises the N>1 host path -- shot chunks per rank, record gather, gradient sum, unique-id broadcast --
+with the CPU oracle standing in for the GPU engine (test infrastructure only)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+
+import geophyinv_jl_b200 as G  # noqa: E402
+from geophyinv_jl_b200.host import dist as D, gallery  # noqa: E402
+import oracle as O  # noqa: E402
+
+
+def main():
+    dist = D.init_process_group("gloo")
+    rank, _, world = D.env_ranks()
+    assert world == 2 and dist is not None
+    O.OraclePFdtd.oracle_threads = 2
+
+    # --- forward modelling, 5 supersources over 2 ranks (chunks 0:2 and 2:5, fdtd.jl:251-255)
+    kw = gallery.c2_acou2d_layered(nz=60, nx=90, nt=220, nss=5, nr=12, fq=15.0)
+    pa = O.OraclePFdtd(G.FdtdAcoustic(), **kw, nworker=world, rank=rank)
+    assert [list(c) for c in pa.sschunks] == [[0, 1], [2, 3, 4]]
+    assert list(pa.local) == [[0, 1], [2, 3, 4]][rank]
+    pa.update()
+    D.gather_records(pa, dist, dst=0)
+
+    # --- the 128-byte id travels from rank 0 to everyone
+    uid = D.share_unique_id(lambda: bytes(range(128)), dist)
+    assert uid == bytes(range(128))
+
+    # --- FWI gradient: local shots per rank, then one sum over ranks
+    kwg, true = gallery.c4_fwi2d(nz=50, nx=70, nt=300, nss=3, nr=10, fq=12.0)
+    pt = O.OraclePFdtd(G.FdtdAcoustic(), **{**kwg, "medium": true})
+    pt.update()
+    dobs = [d.copy() for d in pt.c.data[0]]
+    pg = O.OraclePFdtd(G.FdtdAcoustic("forward_save"), **kwg, nworker=world, rank=rank)
+    m = pg.get_modelvector()
+    g = np.zeros_like(m)
+    G.gradient(g, m, dobs, pg)
+    gsum = D.allreduce_host([g], dist)[0]
+
+    if rank == 0:
+        ref = O.OraclePFdtd(G.FdtdAcoustic(), **kw)
+        ref.update()
+        for iss in range(5):
+            a, b = pa.c.data[0][iss].d["p"], ref.c.data[0][iss].d["p"]
+            assert np.abs(b).max() > 0 and np.array_equal(a, b), f"records of supersource {iss} differ"
+        pr = O.OraclePFdtd(G.FdtdAcoustic("forward_save"), **kwg)
+        gr = np.zeros_like(m)
+        G.gradient(gr, m, dobs, pr)
+        err = np.linalg.norm(gsum - gr) / np.linalg.norm(gr)
+        assert err < 1e-5, err
+        print(f"MULTIRANK_OK gradient rel-L2 {err:.2e}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

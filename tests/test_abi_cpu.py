@@ -1,0 +1,104 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/gpifdtd.h declares, agrees with the Python binding's struct layouts, and refuses to run
+without a GPU instead of falling back to anything."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "gpifdtd.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gpi_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib(G):
+    if not os.path.exists(G.engine.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return G.load_library()
+
+
+def test_every_declared_symbol_is_exported(G, lib):
+    syms = header_symbols()
+    assert len(syms) >= 27
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/gpifdtd.h but not exported by libgpifdtd.so"
+    assert sorted(G.engine.EXPORTS) == syms, "Python binding and header disagree on the export list"
+
+
+def test_struct_layouts_match_header(G):
+    # gpi_config: 18 int32 (n[3] counted thrice) + 8 doubles; gpi_timers: 9 doubles
+    assert C.sizeof(G.engine.GpiConfig) == 4 * 20 + 8 * 8
+    assert C.sizeof(G.engine.GpiTimers) == 8 * 9
+    assert G.engine.GpiConfig.dt.offset == 80
+
+
+def test_field_shapes_follow_fields_jl(G, lib):
+    """fields.jl:92-671 via SURVEY App. A: staggered array shapes."""
+    n = (C.c_int32 * 3)(20, 30, 40)
+    out = (C.c_int32 * 3)()
+    want3 = {"p": (20, 30, 40), "vx": (20, 30, 41), "vy": (20, 31, 40), "vz": (21, 30, 40),
+             "tauxy": (18, 29, 39), "tauxz": (19, 28, 39), "tauyz": (19, 29, 38),
+             "dtauxxdx": (18, 28, 39), "dtauyydy": (18, 29, 38), "dtauzzdz": (19, 28, 38)}
+    for f, shp in want3.items():
+        phys = G.engine.ACOUSTIC if f == "p" else G.engine.ELASTIC
+        assert lib.gpi_field_shape(3, phys, G.engine.FIELD[f], n, out) == 0
+        assert tuple(out) == shp, f
+    n2 = (C.c_int32 * 3)(20, 1, 40)
+    want2 = {"p": (20, 1, 40), "vx": (20, 1, 41), "vz": (21, 1, 40), "dpdx": (18, 1, 39), "dpdz": (19, 1, 38)}
+    for f, shp in want2.items():
+        assert lib.gpi_field_shape(2, G.engine.ACOUSTIC, G.engine.FIELD[f], n2, out) == 0
+        assert tuple(out) == shp, f
+    # fields that do not exist for the physics / dimensionality are an error, not a guess
+    assert lib.gpi_field_shape(2, G.engine.ACOUSTIC, G.engine.FIELD["vy"], n2, out) != 0
+    assert lib.gpi_field_shape(3, G.engine.ACOUSTIC, G.engine.FIELD["tauxy"], n, out) != 0
+    assert lib.gpi_field_shape(3, G.engine.ELASTIC, G.engine.FIELD["p"], n, out) != 0
+    # host-side shape table agrees with the library
+    for f, shp in want3.items():
+        assert G.field_shape(f, (20, 30, 40)) == shp
+
+
+def test_no_gpu_means_error_not_fallback(G, lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    cfg = G.engine.GpiConfig()
+    cfg.abi_version, cfg.ndims, cfg.physics, cfg.order = 1, 2, 0, 2
+    cfg.n[0], cfg.n[1], cfg.n[2] = 100, 1, 100
+    cfg.nt, cfg.npml, cfg.nbound, cfg.npw, cfg.nshots = 10, 41, 3, 1, 1
+    h = C.c_void_p()
+    assert lib.gpi_create(C.byref(cfg), C.byref(h)) != 0
+    assert not h.value
+    msg = lib.gpi_last_error(None).decode()
+    assert "no CUDA device" in msg and "no CPU fallback" in msg
+    with pytest.raises(G.EngineError):
+        G.Engine(cfg)
+
+
+def test_bad_config_rejected(G, lib):
+    h = C.c_void_p()
+    cfg = G.engine.GpiConfig()
+    cfg.abi_version = 99
+    assert lib.gpi_create(C.byref(cfg), C.byref(h)) != 0
+    assert "ABI" in lib.gpi_last_error(None).decode()
+    cfg.abi_version, cfg.order, cfg.ndims = 1, 8, 2
+    assert lib.gpi_create(C.byref(cfg), C.byref(h)) != 0
+    assert "order" in lib.gpi_last_error(None).decode()
+    assert lib.gpi_create(None, C.byref(h)) != 0
+
+
+def test_product_never_imports_oracle():
+    """The product package must have no path to the CPU oracle (it is test infrastructure)."""
+    pkg = os.path.join(ROOT, "geophyinv.jl_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "liboracle" not in txt and "from oracle" not in txt, f
