@@ -140,7 +140,8 @@ struct gpi_handle {
     // CPML memory: one block per (b, pw) holding all terms
     struct Term { int dfield; int axis; long long off; long long size; bool vel; int idx; };
     std::vector<Term> terms;  long long mem_per_pw = 0;  float* MEM = nullptr;
-    float* pmlcoef = nullptr;           // [GPI_NFIELD][3][2*npml]
+    float* pmlcoef = nullptr;           // [GPI_NFIELD][3][2*npml]  (x / y terms: indexed by slab position)
+    float* pmlztab = nullptr;           // [GPI_NFIELD][3][pz]      (z terms: indexed by the unified z coordinate)
     // medium
     float* mod[GPI_NPARAM] = {};        // unified volumes
     float* dmod[C_N] = {};  float** dmod_table = nullptr;
@@ -156,6 +157,7 @@ struct gpi_handle {
     int sample_every = 16;
     // tuning
     dim3 blk3{64, 2, 2}, blk2{128, 2, 1};
+    int blkv = GPI_VEC_THREADS;  bool vec3 = true;      // 3-D: float4-per-thread kernels (kernels3d.cuh); GPI_SCALAR3D=1 selects the scalar ones
     // nccl
     NcclApi nccl;  void* comm = nullptr;  int rank = 0, nranks = 1;
 };
@@ -247,9 +249,15 @@ void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch) {
     for (const auto& t : h->terms) {
         PmlTerm p;
         p.mem = h->MEM + (long long)ipw * h->mem_per_pw + t.off;
-        p.a = h->pmlcoef + ((size_t)t.dfield * 3 + 0) * np2;
-        p.b = h->pmlcoef + ((size_t)t.dfield * 3 + 1) * np2;
-        p.kI = h->pmlcoef + ((size_t)t.dfield * 3 + 2) * np2;
+        if (t.axis == 0) {
+            p.a = h->pmlztab + ((size_t)t.dfield * 3 + 0) * h->g.pz;
+            p.b = h->pmlztab + ((size_t)t.dfield * 3 + 1) * h->g.pz;
+            p.kI = h->pmlztab + ((size_t)t.dfield * 3 + 2) * h->g.pz;
+        } else {
+            p.a = h->pmlcoef + ((size_t)t.dfield * 3 + 0) * np2;
+            p.b = h->pmlcoef + ((size_t)t.dfield * 3 + 1) * np2;
+            p.kI = h->pmlcoef + ((size_t)t.dfield * 3 + 2) * np2;
+        }
         p.bstride = (long long)h->npw * h->mem_per_pw;
         (t.vel ? a.pv : a.ps)[t.idx] = p;
     }
@@ -257,8 +265,17 @@ void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch) {
     a.nbatch = nbatch;
 }
 
+template <int EL>
+void launch_step_kernels3v(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
+    const Geom& g = h->g;
+    const int ngroups = (g.pz / 4) * g.ny1;
+    dim3 blk(h->blkv), grd((ngroups + h->blkv - 1) / h->blkv, g.nx1, nbatch);
+    if (vel) k_vel3v<EL><<<grd, blk, 0, h->stream>>>(g, a);
+    else     k_stress3v<EL><<<grd, blk, 0, h->stream>>>(g, a);
+}
 template <int ND, int EL>
 void launch_step_kernels(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
+    if (ND == 3 && h->vec3) { launch_step_kernels3v<EL>(h, a, vel, nbatch); return; }
     dim3 blk = ND == 3 ? h->blk3 : h->blk2;
     dim3 grd = grid_for(h, blk, nbatch);
     if (vel) k_vel<ND, EL><<<grd, blk, 0, h->stream>>>(h->g, a);
@@ -348,7 +365,7 @@ static int create_impl(gpi_handle* h) {
     g.ny1 = h->nd == 3 ? g.ny + 1 : 1;
     g.nx1 = g.nx + 1;
     g.npml = c.npml;
-    g.pzm = ((2 * c.npml + 31) / 32) * 32;
+    g.pzm = ((2 * ((c.npml + 3 + 3) / 4 * 4) + 31) / 32) * 32;     // two float4-aligned halves (kernels.cuh, cpml<>)
     g.pml = c.pml_faces; g.rigid = c.rigid_faces; g.freesurf = c.stressfree_faces;
     g.dzI = (float)c.dI[0]; g.dyI = (float)c.dI[1]; g.dxI = (float)c.dI[2];
     g.vol = (long long)g.pz * g.ny1 * g.nx1;
@@ -428,6 +445,9 @@ static int create_impl(gpi_handle* h) {
     std::vector<float> coef((size_t)GPI_NFIELD * 3 * np2, 0.f);
     for (int f = 0; f < GPI_NFIELD; f++) for (int i = 0; i < np2; i++) coef[((size_t)f * 3 + 2) * np2 + i] = 1.f;
     if (to_device(h, &h->pmlcoef, coef)) return 1;
+    std::vector<float> ztab((size_t)GPI_NFIELD * 3 * g.pz, 0.f);
+    for (int f = 0; f < GPI_NFIELD; f++) for (int i = 0; i < g.pz; i++) ztab[((size_t)f * 3 + 2) * g.pz + i] = 1.f;
+    if (to_device(h, &h->pmlztab, ztab)) return 1;
 
     // medium
     const size_t vb = (size_t)g.vol * sizeof(float);
@@ -498,6 +518,8 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     h->own_stream = true;
     if (const char* e = getenv("GPI_SAMPLE_EVERY")) h->sample_every = atoi(e);
     if (const char* e = getenv("GPI_BLOCK3")) { int a, b, c3; if (sscanf(e, "%d,%d,%d", &a, &b, &c3) == 3 && a * b * c3 <= 256) h->blk3 = dim3(a, b, c3); }
+    if (const char* e = getenv("GPI_SCALAR3D")) h->vec3 = atoi(e) == 0;
+    if (const char* e = getenv("GPI_BLOCKV")) { int a = atoi(e); if (a >= 32 && a <= GPI_VEC_THREADS && a % 32 == 0) h->blkv = a; }
     if (const char* e = getenv("GPI_BLOCK2")) { int a, b; if (sscanf(e, "%d,%d", &a, &b) == 2 && a * b <= 256) h->blk2 = dim3(a, b, 1); }
     if (create_impl(h)) { g_create_err = "gpi_create: " + h->err; gpi_destroy(h); return 1; }
     *out = h;
@@ -509,7 +531,7 @@ extern "C" int gpi_destroy(gpi_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
-    cudaFree(h->W); cudaFree(h->TP); cudaFree(h->MEM); cudaFree(h->pmlcoef);
+    cudaFree(h->W); cudaFree(h->TP); cudaFree(h->MEM); cudaFree(h->pmlcoef); cudaFree(h->pmlztab);
     for (auto& p : h->mod) cudaFree(p);
     for (auto& p : h->dmod) cudaFree(p);
     cudaFree(h->dmod_table);
@@ -577,6 +599,24 @@ extern "C" int gpi_set_pml(gpi_handle* h, int f, const float* a, const float* b,
     CU(h, cudaMemcpy(h->pmlcoef + ((size_t)f * 3 + 0) * np2, a, np2 * sizeof(float), cudaMemcpyHostToDevice));
     CU(h, cudaMemcpy(h->pmlcoef + ((size_t)f * 3 + 1) * np2, b, np2 * sizeof(float), cudaMemcpyHostToDevice));
     CU(h, cudaMemcpy(h->pmlcoef + ((size_t)f * 3 + 2) * np2, kI, np2 * sizeof(float), cudaMemcpyHostToDevice));
+    if (dfield_axis(f) == 0) {
+        // z terms: expand onto the unified z coordinate; identity (a = b = 0, kI = 1) outside the slabs
+        const Geom& g = h->g;
+        int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
+        field_shape(h->nd, f, n, sh, off);
+        const int s0 = off[0], len = sh[0], npml = h->c.npml;
+        std::vector<float> ta(g.pz, 0.f), tb(g.pz, 0.f), tk(g.pz, 1.f);
+        for (int k = 0; k < g.pz; k++) {
+            const int r = k - s0;
+            int s = -1;
+            if ((h->c.pml_faces & ZMIN) && r >= 0 && r < npml) s = r;
+            else if ((h->c.pml_faces & ZMAX) && r - (len - npml) >= 0 && r < len) s = npml + r - (len - npml);
+            if (s >= 0) { ta[k] = a[s]; tb[k] = b[s]; tk[k] = kI[s]; }
+        }
+        CU(h, cudaMemcpy(h->pmlztab + ((size_t)f * 3 + 0) * g.pz, ta.data(), g.pz * sizeof(float), cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->pmlztab + ((size_t)f * 3 + 1) * g.pz, tb.data(), g.pz * sizeof(float), cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->pmlztab + ((size_t)f * 3 + 2) * g.pz, tk.data(), g.pz * sizeof(float), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 

@@ -78,29 +78,42 @@ __device__ __forceinline__ long long uidx(const Geom& g, int k, int j, int i) {
 //     m = b*m + a*d ;  d = d*kI + m
 // AXIS: 0=z 1=y 2=x.  The derivative field covers unified coordinates [s0, s0+len) along AXIS;
 // its first/last npml entries are the min/max slabs (cpml.jl:190-211).
+// Storage (engine's own): x terms [k, j, s], y terms [k, s, i] with s the reference's slab index
+// 0..2*npml-1.  z terms [zi, j, i] with a row of pzm = 2*zhalf floats: the min slab keeps the unified
+// coordinate (zi = k), the max slab sits at zi = zhalf + (k - kb), kb = the 4-aligned start of the slab,
+// so that the vector kernels can move z memory with aligned float4 accesses.  For z terms the
+// coefficient vectors are pre-expanded to k-indexed tables (identity a=b=0, kI=1 outside the slabs).
+__device__ __forceinline__ int slab_index(int u, int s0, int len, int npml, bool hmin, bool hmax) {
+    const int r = u - s0;
+    if (hmin && r >= 0 && r < npml) return r;
+    const int rm = r - (len - npml);
+    if (hmax && rm >= 0 && rm < npml) return npml + rm;
+    return -1;
+}
+__device__ __forceinline__ int zslab_base(int s0, int len, int npml) { return ((s0 + len - npml) >> 2) << 2; }
+
 template <int AXIS>
 __device__ __forceinline__ float cpml(const Geom& g, const PmlTerm& t, float d, int k, int j, int i,
                                       int s0, int len, int b) {
     const int u = AXIS == 0 ? k : (AXIS == 1 ? j : i);
     const int minbit = AXIS == 0 ? ZMIN : (AXIS == 1 ? YMIN : XMIN);
     const int maxbit = AXIS == 0 ? ZMAX : (AXIS == 1 ? YMAX : XMAX);
-    const int r = u - s0;
-    int s = -1;
-    if ((g.pml & minbit) && r < g.npml) s = r;
-    else {
-        const int rm = r - (len - g.npml);
-        if ((g.pml & maxbit) && rm >= 0) s = g.npml + rm;
-    }
+    const int s = slab_index(u, s0, len, g.npml, (g.pml & minbit) != 0, (g.pml & maxbit) != 0);
     if (s >= 0) {
         long long mi;
+        int ci = s;
         if (AXIS == 2)      mi = (long long)k + (long long)g.pz * ((long long)j + (long long)g.ny1 * s);
         else if (AXIS == 1) mi = (long long)k + (long long)g.pz * ((long long)s + 2LL * g.npml * i);
-        else                mi = (long long)s + (long long)g.pzm * ((long long)j + (long long)g.ny1 * i);
+        else {
+            const int zi = s < g.npml ? k : (g.pzm >> 1) + (k - zslab_base(s0, len, g.npml));
+            mi = (long long)zi + (long long)g.pzm * ((long long)j + (long long)g.ny1 * i);
+            ci = k;
+        }
         float* mp = t.mem + (long long)b * t.bstride + mi;
         float m = *mp;
-        m = __fadd_rn(__fmul_rn(__ldg(t.b + s), m), __fmul_rn(__ldg(t.a + s), d));
+        m = __fadd_rn(__fmul_rn(__ldg(t.b + ci), m), __fmul_rn(__ldg(t.a + ci), d));
         *mp = m;
-        d = __fadd_rn(__fmul_rn(d, __ldg(t.kI + s)), m);
+        d = __fadd_rn(__fmul_rn(d, __ldg(t.kI + ci)), m);
     }
     return d;
 }
@@ -132,9 +145,7 @@ __device__ __forceinline__ bool cell(const Geom& g, int nbatch, int& k, int& j, 
 //   elastic  : 0 dtauxxdx 1 dtauxydy 2 dtauxzdz | 3 dtauxydx 4 dtauyydy 5 dtauyzdz | 6 dtauxzdx 7 dtauyzdy 8 dtauzzdz
 // ------------------------------------------------------------------------------------------------
 template <int ND, int EL>
-__global__ void __launch_bounds__(256) k_vel(const Geom g, const StepArgs a) {
-    int k, j, i, b;
-    if (!cell<ND>(g, a.nbatch, k, j, i, b)) return;
+__device__ __forceinline__ void vel_cell(const Geom& g, const StepArgs& a, int k, int j, int i, int b) {
     const long long w = (long long)b * a.wstride;
     const long long c = uidx(g, k, j, i);
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
@@ -274,6 +285,13 @@ __global__ void __launch_bounds__(256) k_vel(const Geom g, const StepArgs a) {
     (void)injj;
 }
 
+template <int ND, int EL>
+__global__ void __launch_bounds__(256) k_vel(const Geom g, const StepArgs a) {
+    int k, j, i, b;
+    if (!cell<ND>(g, a.nbatch, k, j, i, b)) return;
+    vel_cell<ND, EL>(g, a, k, j, i, b);
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_stress: update_dv! + update_stress! (+ free surface) fused.
 //   acoustic (advance_acou.jl:288-313): p = p + (dvxdx + dvzdz [+ dvydy]) * dtK
@@ -282,9 +300,7 @@ __global__ void __launch_bounds__(256) k_vel(const Geom g, const StepArgs a) {
 //   0 dvxdx 1 dvydy 2 dvzdz | 3 dvxdy 4 dvydx (tauxy) | 5 dvxdz 6 dvzdx (tauxz) | 7 dvydz 8 dvzdy (tauyz)
 // ------------------------------------------------------------------------------------------------
 template <int ND, int EL>
-__global__ void __launch_bounds__(256) k_stress(const Geom g, const StepArgs a) {
-    int k, j, i, b;
-    if (!cell<ND>(g, a.nbatch, k, j, i, b)) return;
+__device__ __forceinline__ void stress_cell(const Geom& g, const StepArgs& a, int k, int j, int i, int b) {
     const long long w = (long long)b * a.wstride;
     const long long c = uidx(g, k, j, i);
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
@@ -377,6 +393,15 @@ __global__ void __launch_bounds__(256) k_stress(const Geom g, const StepArgs a) 
         }
     }
 }
+
+template <int ND, int EL>
+__global__ void __launch_bounds__(256) k_stress(const Geom g, const StepArgs a) {
+    int k, j, i, b;
+    if (!cell<ND>(g, a.nbatch, k, j, i, b)) return;
+    stress_cell<ND, EL>(g, a, k, j, i, b);
+}
+
+#include "kernels3d.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // k_dmod: update_dmod! + store_invav*! (medium.jl:143-221).  The reference's `dt / @av_*(b)` and

@@ -1,0 +1,365 @@
+// kernels3d.cuh -- the 3-D stencil kernels of the roofline case (included inside namespace gpi).
+//
+// Same arithmetic as vel_cell / stress_cell (kernels.cuh), organised for HBM throughput on sm_100a:
+//
+//   * one thread owns FOUR consecutive z cells (z is the fast axis, pitch a multiple of 128 B), so every
+//     field, coefficient and CPML-memory access is an aligned 128-bit load/store; the z-1 / z+1
+//     neighbours come from the thread's own vector or from the neighbouring lane by warp shuffle (one
+//     scalar load only on the first / last lane of a warp);
+//   * all loads of a thread are issued up front, unconditionally (18-20 independent 16-byte requests in
+//     flight per thread), which is what a latency x bandwidth product of ~35 KB per SM needs -- the scalar
+//     kernels issue 4-byte loads behind range predicates and reach only 20-35 % of HBM;
+//   * the (z, y) plane is linearised into float4 groups so no lanes are wasted on a ragged z extent;
+//     x comes from blockIdx.y (consecutive planes are scheduled back to back, so the +-1-plane
+//     neighbours are L2 hits: measured DRAM traffic equals the algorithmic bytes);
+//   * range predicates in z are per element and applied only at the store; rows on the outer shell
+//     of the box (rigid faces, ghost cells, ragged x / y ranges; 2.4 % of the rows) run the scalar
+//     reference-order code of kernels.cuh;
+//   * CPML: x / y slab membership is uniform per thread (coefficients are broadcast loads, memory is
+//     moved as float4); z slabs use k-indexed coefficient tables (identity outside the slab) and the
+//     float4-aligned z-memory layout described at cpml<> in kernels.cuh.
+//
+// Arithmetic stays __fmul_rn / __fadd_rn / __fsub_rn in the reference's association order: results are
+// bit-identical to the scalar kernels and to the CPU restatement.
+
+#ifndef GPI_VEC_THREADS
+#define GPI_VEC_THREADS 128
+#endif
+#ifndef GPI_VEC_MINBLOCKS
+#define GPI_VEC_MINBLOCKS 3
+#endif
+
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 ld4(const float* p) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    F4 r; r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w; return r;
+}
+__device__ __forceinline__ F4 ldg4(const float* p) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    F4 r; r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w; return r;
+}
+__device__ __forceinline__ void st4(float* p, const F4& r) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+}
+
+// value at z-1 of element 0: lane-1's element 3, or a scalar load on the first lane of the warp
+__device__ __forceinline__ float z_prev(const F4& c, const float* p, unsigned mask, int lane, int k0) {
+    float r = __shfl_up_sync(mask, c.v[3], 1);
+    if (lane == 0 && k0 > 0) r = p[-1];
+    return r;
+}
+// value at z+1 of element 3: lane+1's element 0, or a scalar load on the last lane of the warp
+__device__ __forceinline__ float z_next(const F4& c, const float* p, unsigned mask, int lane, bool more) {
+    float r = __shfl_down_sync(mask, c.v[0], 1);
+    if (lane == 31 && more) r = p[4];
+    return r;
+}
+
+// d[e] * scale after a forward difference
+__device__ __forceinline__ F4 diff4(const F4& hi, const F4& lo, float sI) {
+    F4 r;
+#pragma unroll
+    for (int e = 0; e < 4; e++) r.v[e] = __fmul_rn(__fsub_rn(hi.v[e], lo.v[e]), sI);
+    return r;
+}
+// forward difference along z onto half nodes: f(k) - f(k-1)
+__device__ __forceinline__ F4 diff4_zm(const F4& c, float prev, float sI) {
+    F4 r;
+    r.v[0] = __fmul_rn(__fsub_rn(c.v[0], prev), sI);
+#pragma unroll
+    for (int e = 1; e < 4; e++) r.v[e] = __fmul_rn(__fsub_rn(c.v[e], c.v[e - 1]), sI);
+    return r;
+}
+// forward difference along z from half nodes onto integer nodes: f(k+1) - f(k)
+__device__ __forceinline__ F4 diff4_zp(const F4& c, float next, float sI) {
+    F4 r;
+#pragma unroll
+    for (int e = 0; e < 3; e++) r.v[e] = __fmul_rn(__fsub_rn(c.v[e + 1], c.v[e]), sI);
+    r.v[3] = __fmul_rn(__fsub_rn(next, c.v[3]), sI);
+    return r;
+}
+
+// CPML on four z-consecutive values, split in three phases so that every DRAM-latency load of a thread
+// (fields, coefficients AND memory variables) is in flight before the first dependent instruction and
+// before any store (stores would otherwise fence later loads: the compiler must assume aliasing):
+//   pml_open_*  : slab test, address, issue the 16-byte load of the memory variables
+//   pml_apply_* : m = b*m + a*d ; d = d*kI + m   (coefficients are L1-resident broadcast / table loads)
+//   pml_close   : store the memory variables
+struct Pml4 { float* mp; int s; F4 m; };
+
+template <int AXIS>   // 1 = y, 2 = x: slab index s uniform over the four cells (-1: not in a slab)
+__device__ __forceinline__ void pml_open(Pml4& q, const Geom& g, const PmlTerm& t, int s, int k0, int j, int i, int b) {
+    q.s = s; q.mp = nullptr;
+    if (s < 0) return;
+    long long mi;
+    if (AXIS == 2) mi = (long long)k0 + (long long)g.pz * ((long long)j + (long long)g.ny1 * s);
+    else           mi = (long long)k0 + (long long)g.pz * ((long long)s + 2LL * g.npml * i);
+    q.mp = t.mem + (long long)b * t.bstride + mi;
+    q.m = ld4(q.mp);
+}
+// z terms: float4-aligned memory rows (cpml<> in kernels.cuh); s holds k0 for the table look-up
+__device__ __forceinline__ void pml_open_z(Pml4& q, const Geom& g, const PmlTerm& t, int s0, int len, int k0, int j, int i, int b) {
+    const int npml = g.npml;
+    int zi = -1;
+    if ((g.pml & ZMIN) && k0 < s0 + npml) zi = k0;
+    else if (g.pml & ZMAX) {
+        const int kb = zslab_base(s0, len, npml);
+        if (k0 >= kb && k0 < s0 + len) zi = (g.pzm >> 1) + (k0 - kb);
+    }
+    q.s = k0; q.mp = nullptr;
+    if (zi < 0) return;
+    q.mp = t.mem + (long long)b * t.bstride + (long long)zi + (long long)g.pzm * ((long long)j + (long long)g.ny1 * i);
+    q.m = ld4(q.mp);
+}
+__device__ __forceinline__ void pml_apply(Pml4& q, const PmlTerm& t, F4& d) {
+    if (!q.mp) return;
+    const float a = __ldg(t.a + q.s), bb = __ldg(t.b + q.s), kI = __ldg(t.kI + q.s);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        q.m.v[e] = __fadd_rn(__fmul_rn(bb, q.m.v[e]), __fmul_rn(a, d.v[e]));
+        d.v[e] = __fadd_rn(__fmul_rn(d.v[e], kI), q.m.v[e]);
+    }
+}
+__device__ __forceinline__ void pml_apply_z(Pml4& q, const PmlTerm& t, F4& d) {
+    if (!q.mp) return;
+    const F4 a = ldg4(t.a + q.s), bb = ldg4(t.b + q.s), kI = ldg4(t.kI + q.s);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        q.m.v[e] = __fadd_rn(__fmul_rn(bb.v[e], q.m.v[e]), __fmul_rn(a.v[e], d.v[e]));
+        d.v[e] = __fadd_rn(__fmul_rn(d.v[e], kI.v[e]), q.m.v[e]);
+    }
+}
+__device__ __forceinline__ void pml_close(const Pml4& q) { if (q.mp) st4(q.mp, q.m); }
+
+// thread -> (group of four z cells, row j); plane i = blockIdx.y, batch slot = blockIdx.z
+struct Vec3Idx { int k0, j, i, b, lane; bool valid; };
+__device__ __forceinline__ Vec3Idx vec3_index(const Geom& g) {
+    Vec3Idx q;
+    const int nq = g.pz >> 2;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    q.valid = gid < nq * g.ny1;
+    q.j = gid / nq;
+    q.k0 = (gid - q.j * nq) << 2;
+    q.i = blockIdx.y; q.b = blockIdx.z;
+    q.lane = threadIdx.x & 31;
+    return q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// velocity kernel, 3-D (see vel_cell for the reference citations and the CPML term order)
+// ------------------------------------------------------------------------------------------------
+template <int EL>
+__global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(const Geom g, const StepArgs a) {
+    const Vec3Idx q = vec3_index(g);
+    const int k0 = q.k0, j = q.j, i = q.i, b = q.b;
+    const int nz = g.nz, ny = g.ny, nx = g.nx;
+    const bool fast = q.valid && i >= 2 && i <= nx - 2 && j >= 2 && j <= ny - 2;
+    const unsigned mask = __ballot_sync(0xffffffffu, fast);
+    if (!q.valid) return;
+    if (!fast) {
+#pragma unroll 1
+        for (int e = 0; e < 4; e++) if (k0 + e <= nz) vel_cell<3, EL>(g, a, k0 + e, j, i, b);
+        return;
+    }
+    const long long w = (long long)b * a.wstride;
+    const long long c = uidx(g, k0, j, i) + w;
+    const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
+    const bool more = k0 + 4 < g.pz;
+    const bool hxmin = g.pml & XMIN, hxmax = g.pml & XMAX, hymin = g.pml & YMIN, hymax = g.pml & YMAX;
+
+    float* vx = a.v[V_X] + c; float* vy = a.v[V_Y] + c; float* vz = a.v[V_Z] + c;
+    F4 nvx = ld4(vx), nvy = ld4(vy), nvz = ld4(vz);
+
+    if (!EL) {
+        const float* p = a.tau[T_XX] + c;
+        const F4 pc = ld4(p), pmx = ld4(p - sx), pmy = ld4(p - sy);
+        const F4 bx = ldg4(a.c[C_BX] + c - w), by = ldg4(a.c[C_BY] + c - w), bz = ldg4(a.c[C_BZ] + c - w);
+        Pml4 m0, m1, m2;
+        pml_open<2>(m0, g, a.pv[0], slab_index(i, 1, nx - 1, g.npml, hxmin, hxmax), k0, j, i, b);
+        pml_open<1>(m1, g, a.pv[1], slab_index(j, 1, ny - 1, g.npml, hymin, hymax), k0, j, i, b);
+        pml_open_z(m2, g, a.pv[2], 1, nz - 1, k0, j, i, b);
+        const float pprev = z_prev(pc, p, mask, q.lane, k0);
+        F4 dx = diff4(pc, pmx, g.dxI);        pml_apply(m0, a.pv[0], dx);
+        F4 dy = diff4(pc, pmy, g.dyI);        pml_apply(m1, a.pv[1], dy);
+        F4 dz = diff4_zm(pc, pprev, g.dzI);   pml_apply_z(m2, a.pv[2], dz);
+        pml_close(m0); pml_close(m1); pml_close(m2);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int k = k0 + e;
+            if (k >= 1 && k <= nz - 2) {
+                nvx.v[e] = __fadd_rn(nvx.v[e], __fmul_rn(bx.v[e], dx.v[e]));
+                nvy.v[e] = __fadd_rn(nvy.v[e], __fmul_rn(by.v[e], dy.v[e]));
+            }
+            if (k >= 1 && k <= nz - 1) nvz.v[e] = __fadd_rn(nvz.v[e], __fmul_rn(bz.v[e], dz.v[e]));
+        }
+    } else {
+        const float* txx = a.tau[T_XX] + c; const float* tyy = a.tau[T_YY] + c; const float* tzz = a.tau[T_ZZ] + c;
+        const float* txy = a.tau[T_XY] + c; const float* txz = a.tau[T_XZ] + c; const float* tyz = a.tau[T_YZ] + c;
+        const F4 xx = ld4(txx), xxm = ld4(txx - sx);
+        const F4 yy = ld4(tyy), yym = ld4(tyy - sy);
+        const F4 zz = ld4(tzz);
+        const F4 xy = ld4(txy), xypy = ld4(txy + sy), xypx = ld4(txy + sx);
+        const F4 xz = ld4(txz), xzpx = ld4(txz + sx);
+        const F4 yz = ld4(tyz), yzpy = ld4(tyz + sy);
+        const F4 bx = ldg4(a.c[C_BX] + c - w), by = ldg4(a.c[C_BY] + c - w), bz = ldg4(a.c[C_BZ] + c - w);
+        const int sx0 = slab_index(i, 1, nx - 1, g.npml, hxmin, hxmax);      // dtauxxdx
+        const int sx1 = slab_index(i, 1, nx - 2, g.npml, hxmin, hxmax);      // dtauxydx, dtauxzdx
+        const int sy0 = slab_index(j, 1, ny - 2, g.npml, hymin, hymax);      // dtauxydy, dtauyzdy
+        const int sy1 = slab_index(j, 1, ny - 1, g.npml, hymin, hymax);      // dtauyydy
+        Pml4 m0, m1, m2, m3, m4, m5, m6, m7, m8;
+        pml_open<2>(m0, g, a.pv[0], sx0, k0, j, i, b);   pml_open<1>(m1, g, a.pv[1], sy0, k0, j, i, b);   pml_open_z(m2, g, a.pv[2], 1, nz - 2, k0, j, i, b);
+        pml_open<2>(m3, g, a.pv[3], sx1, k0, j, i, b);   pml_open<1>(m4, g, a.pv[4], sy1, k0, j, i, b);   pml_open_z(m5, g, a.pv[5], 1, nz - 2, k0, j, i, b);
+        pml_open<2>(m6, g, a.pv[6], sx1, k0, j, i, b);   pml_open<1>(m7, g, a.pv[7], sy0, k0, j, i, b);   pml_open_z(m8, g, a.pv[8], 1, nz - 1, k0, j, i, b);
+        const float zzprev = z_prev(zz, tzz, mask, q.lane, k0);
+        const float xznext = z_next(xz, txz, mask, q.lane, more);
+        const float yznext = z_next(yz, tyz, mask, q.lane, more);
+
+        // vx: dtauxxdx + dtauxydy + dtauxzdz
+        F4 dxx = diff4(xx, xxm, g.dxI);            pml_apply(m0, a.pv[0], dxx);
+        F4 dxy = diff4(xypy, xy, g.dyI);           pml_apply(m1, a.pv[1], dxy);
+        F4 dxz = diff4_zp(xz, xznext, g.dzI);      pml_apply_z(m2, a.pv[2], dxz);
+        // vy: dtauxydx + dtauyydy + dtauyzdz
+        F4 dyx = diff4(xypx, xy, g.dxI);           pml_apply(m3, a.pv[3], dyx);
+        F4 dyy = diff4(yy, yym, g.dyI);            pml_apply(m4, a.pv[4], dyy);
+        F4 dyz = diff4_zp(yz, yznext, g.dzI);      pml_apply_z(m5, a.pv[5], dyz);
+        // vz: dtauxzdx + dtauyzdy + dtauzzdz
+        F4 dzx = diff4(xzpx, xz, g.dxI);           pml_apply(m6, a.pv[6], dzx);
+        F4 dzy = diff4(yzpy, yz, g.dyI);           pml_apply(m7, a.pv[7], dzy);
+        F4 dzz = diff4_zm(zz, zzprev, g.dzI);      pml_apply_z(m8, a.pv[8], dzz);
+        pml_close(m0); pml_close(m1); pml_close(m2); pml_close(m3); pml_close(m4); pml_close(m5); pml_close(m6); pml_close(m7); pml_close(m8);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int k = k0 + e;
+            if (k >= 1 && k <= nz - 2) {
+                nvx.v[e] = __fsub_rn(nvx.v[e], __fmul_rn(bx.v[e], __fadd_rn(__fadd_rn(dxx.v[e], dxy.v[e]), dxz.v[e])));
+                nvy.v[e] = __fsub_rn(nvy.v[e], __fmul_rn(by.v[e], __fadd_rn(__fadd_rn(dyx.v[e], dyy.v[e]), dyz.v[e])));
+            }
+            if (k >= 1 && k <= nz - 1)
+                nvz.v[e] = __fsub_rn(nvz.v[e], __fmul_rn(bz.v[e], __fadd_rn(__fadd_rn(dzx.v[e], dzy.v[e]), dzz.v[e])));
+        }
+    }
+
+    // rigid z faces (dirichlet.jl:35-74); the x / y faces only touch shell rows (scalar path)
+    const int R = g.rigid;
+    const bool head = k0 == 0, tail = k0 + 3 >= nz - 1;
+    if (head && (R & ZMIN)) { nvx.v[0] = 0.f; nvy.v[0] = 0.f; nvz.v[0] = -nvz.v[1]; }
+    if (!tail) {
+        st4(vx, nvx); st4(vy, nvy); st4(vz, nvz);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int k = k0 + e;
+            if (k <= nz - 1) {
+                const bool zero = (R & ZMAX) && k == nz - 1;
+                vx[e] = zero ? 0.f : nvx.v[e];
+                vy[e] = zero ? 0.f : nvy.v[e];
+                vz[e] = nvz.v[e];
+                if ((R & ZMAX) && k == nz - 1) vz[e + 1] = -nvz.v[e];       // vz[nz+1] = -vz[nz]
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stress kernel, 3-D (see stress_cell for the reference citations and the CPML term order)
+// ------------------------------------------------------------------------------------------------
+template <int EL>
+__global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v(const Geom g, const StepArgs a) {
+    const Vec3Idx q = vec3_index(g);
+    const int k0 = q.k0, j = q.j, i = q.i, b = q.b;
+    const int nz = g.nz, ny = g.ny, nx = g.nx;
+    const bool fast = q.valid && i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2;
+    const unsigned mask = __ballot_sync(0xffffffffu, fast);
+    if (!q.valid) return;
+    if (!fast) {
+#pragma unroll 1
+        for (int e = 0; e < 4; e++) if (k0 + e <= nz) stress_cell<3, EL>(g, a, k0 + e, j, i, b);
+        return;
+    }
+    const long long w = (long long)b * a.wstride;
+    const long long c = uidx(g, k0, j, i) + w;
+    const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
+    const bool more = k0 + 4 < g.pz;
+    const bool hxmin = g.pml & XMIN, hxmax = g.pml & XMAX, hymin = g.pml & YMIN, hymax = g.pml & YMAX;
+
+    // ---- phase 1: every load of the thread ---------------------------------------------------------
+    const float* vx = a.v[V_X] + c; const float* vy = a.v[V_Y] + c; const float* vz = a.v[V_Z] + c;
+    const F4 cvx = ld4(vx), cvy = ld4(vy), cvz = ld4(vz);
+    const F4 vxpx = ld4(vx + sx), vypy = ld4(vy + sy);
+    Pml4 m0, m1, m2;
+    pml_open<2>(m0, g, a.ps[0], slab_index(i, 0, nx, g.npml, hxmin, hxmax), k0, j, i, b);
+    pml_open<1>(m1, g, a.ps[1], slab_index(j, 0, ny, g.npml, hymin, hymax), k0, j, i, b);
+    pml_open_z(m2, g, a.ps[2], 0, nz, k0, j, i, b);
+
+    if (!EL) {
+        float* p = a.tau[T_XX] + c;
+        F4 pc = ld4(p);
+        const F4 K = ldg4(a.c[C_K] + c - w);
+        const float vznext = z_next(cvz, vz, mask, q.lane, more);
+        F4 dxx = diff4(vxpx, cvx, g.dxI);           pml_apply(m0, a.ps[0], dxx);       // @d_xa(vx)
+        F4 dyy = diff4(vypy, cvy, g.dyI);           pml_apply(m1, a.ps[1], dyy);       // @d_ya(vy)
+        F4 dzz = diff4_zp(cvz, vznext, g.dzI);      pml_apply_z(m2, a.ps[2], dzz);     // @d_za(vz)
+#pragma unroll
+        for (int e = 0; e < 4; e++) if (k0 + e <= nz - 1)
+            pc.v[e] = __fadd_rn(pc.v[e], __fmul_rn(__fadd_rn(__fadd_rn(dxx.v[e], dzz.v[e]), dyy.v[e]), K.v[e]));
+        st4(p, pc);
+        pml_close(m0); pml_close(m1); pml_close(m2);
+        return;
+    }
+
+    const bool fs = (g.freesurf & ZMIN) != 0;
+    float* txx = a.tau[T_XX] + c; float* tyy = a.tau[T_YY] + c; float* tzz = a.tau[T_ZZ] + c;
+    float* txy = a.tau[T_XY] + c; float* txz = a.tau[T_XZ] + c; float* tyz = a.tau[T_YZ] + c;
+    F4 xx = ld4(txx), yy = ld4(tyy), zz = ld4(tzz), xy = ld4(txy), xz = ld4(txz), yz = ld4(tyz);
+    const F4 M = ldg4(a.c[C_K] + c - w), L = ldg4(a.c[C_L] + c - w);
+    const F4 muxz = ldg4(a.c[C_MUXZ] + c - w), muxy = ldg4(a.c[C_MUXY] + c - w), muyz = ldg4(a.c[C_MUYZ] + c - w);
+    const F4 vxmy = ld4(vx - sy), vymx = ld4(vy - sx), vzmx = ld4(vz - sx), vzmy = ld4(vz - sy);
+    const int sxh = slab_index(i, 1, nx - 1, g.npml, hxmin, hxmax);      // dvzdx, dvydx
+    const int syh = slab_index(j, 1, ny - 1, g.npml, hymin, hymax);      // dvxdy, dvzdy
+    Pml4 m3, m4, m5, m6, m7, m8;
+    pml_open<1>(m3, g, a.ps[3], syh, k0, j, i, b);   pml_open<2>(m4, g, a.ps[4], sxh, k0, j, i, b);
+    pml_open_z(m5, g, a.ps[5], 1, nz - 1, k0, j, i, b);   pml_open<2>(m6, g, a.ps[6], sxh, k0, j, i, b);
+    pml_open_z(m7, g, a.ps[7], 1, nz - 1, k0, j, i, b);   pml_open<1>(m8, g, a.ps[8], syh, k0, j, i, b);
+    const float vznext = z_next(cvz, vz, mask, q.lane, more);
+    const float vxprev = z_prev(cvx, vx, mask, q.lane, k0);
+    const float vyprev = z_prev(cvy, vy, mask, q.lane, k0);
+
+    // ---- phase 2: arithmetic in the reference's order ------------------------------------------------
+    F4 dxx = diff4(vxpx, cvx, g.dxI);           pml_apply(m0, a.ps[0], dxx);       // @d_xa(vx)
+    F4 dyy = diff4(vypy, cvy, g.dyI);           pml_apply(m1, a.ps[1], dyy);       // @d_ya(vy)
+    F4 dzz = diff4_zp(cvz, vznext, g.dzI);      pml_apply_z(m2, a.ps[2], dzz);     // @d_za(vz)
+#pragma unroll
+    for (int e = 0; e < 4; e++) if (k0 + e <= nz - 1) {
+        xx.v[e] = __fsub_rn(__fsub_rn(xx.v[e], __fmul_rn(M.v[e], dxx.v[e])), __fmul_rn(L.v[e], __fadd_rn(dyy.v[e], dzz.v[e])));
+        yy.v[e] = __fsub_rn(__fsub_rn(yy.v[e], __fmul_rn(M.v[e], dyy.v[e])), __fmul_rn(L.v[e], __fadd_rn(dxx.v[e], dzz.v[e])));
+        zz.v[e] = __fsub_rn(__fsub_rn(zz.v[e], __fmul_rn(M.v[e], dzz.v[e])), __fmul_rn(L.v[e], __fadd_rn(dyy.v[e], dxx.v[e])));
+    }
+    if (fs && k0 == 0) zz.v[0] = -zz.v[1];                     // free_surface_mirror!: tauzz[1] = -tauzz[2]
+
+    // tauxz: z half, y inner, x half
+    F4 dxz = diff4_zm(cvx, vxprev, g.dzI);      pml_apply_z(m5, a.ps[5], dxz);     // @d_zi(vx)
+    F4 dzx = diff4(cvz, vzmx, g.dxI);           pml_apply(m6, a.ps[6], dzx);       // @d_xi(vz)
+    // tauxy: z inner, y half, x half
+    F4 dxy = diff4(cvx, vxmy, g.dyI);           pml_apply(m3, a.ps[3], dxy);       // @d_yi(vx)
+    F4 dyx = diff4(cvy, vymx, g.dxI);           pml_apply(m4, a.ps[4], dyx);       // @d_xi(vy)
+    // tauyz: z half, y half, x inner
+    F4 dyz = diff4_zm(cvy, vyprev, g.dzI);      pml_apply_z(m7, a.ps[7], dyz);     // @d_zi(vy)
+    F4 dzy = diff4(cvz, vzmy, g.dyI);           pml_apply(m8, a.ps[8], dzy);       // @d_yi(vz)
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int k = k0 + e;
+        if (k >= 1 && k <= nz - 1) {
+            float n = __fsub_rn(xz.v[e], __fmul_rn(muxz.v[e], __fadd_rn(dxz.v[e], dzx.v[e])));
+            if (fs && k == 1) n = 0.f;                             // free_surface!(tauxz)
+            xz.v[e] = n;
+            n = __fsub_rn(yz.v[e], __fmul_rn(muyz.v[e], __fadd_rn(dyz.v[e], dzy.v[e])));
+            if (fs && k == 1) n = 0.f;                             // free_surface!(tauyz)
+            yz.v[e] = n;
+        }
+        if (k >= 1 && k <= nz - 2) xy.v[e] = __fsub_rn(xy.v[e], __fmul_rn(muxy.v[e], __fadd_rn(dxy.v[e], dyx.v[e])));
+    }
+
+    // ---- phase 3: stores -----------------------------------------------------------------------------
+    st4(txx, xx); st4(tyy, yy); st4(tzz, zz); st4(txz, xz); st4(txy, xy); st4(tyz, yz);
+    pml_close(m0); pml_close(m1); pml_close(m2); pml_close(m3); pml_close(m4); pml_close(m5); pml_close(m6); pml_close(m7); pml_close(m8);
+}
