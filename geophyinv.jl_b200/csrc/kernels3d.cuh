@@ -4,8 +4,7 @@
 //
 //   * one thread owns FOUR consecutive z cells (z is the fast axis, pitch a multiple of 128 B), so every
 //     field, coefficient and CPML-memory access is an aligned 128-bit load/store; the z-1 / z+1
-//     neighbours come from the thread's own vector or from the neighbouring lane by warp shuffle (one
-//     scalar load only on the first / last lane of a warp);
+//     neighbours come from the thread's own vector plus one scalar load per differentiated field;
 //   * all loads of a thread are issued up front, unconditionally (18-20 independent 16-byte requests in
 //     flight per thread), which is what a latency x bandwidth product of ~35 KB per SM needs -- the scalar
 //     kernels issue 4-byte loads behind range predicates and reach only 20-35 % of HBM;
@@ -30,30 +29,46 @@
 #endif
 
 struct F4 { float v[4]; };
+// Loads and stores of the fast path are volatile asm: the compiler keeps volatile asm statements in
+// program order, so every load of a thread is issued before its first store and -- the point -- before
+// the arithmetic that consumes the first loaded value.  With plain C++ loads nvcc sinks the loads whose
+// values are needed last (the velocities and buoyancies of k_vel3v) below the CPML arithmetic to save
+// registers, which costs a second, serialised DRAM round trip per thread.
 __device__ __forceinline__ F4 ld4(const float* p) {
-    const float4 q = *reinterpret_cast<const float4*>(p);
-    F4 r; r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w; return r;
+    F4 r;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+    return r;
 }
 __device__ __forceinline__ F4 ldg4(const float* p) {
-    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
-    F4 r; r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w; return r;
+    F4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+    return r;
+}
+// ptxas still sinks the loads whose values are consumed last below the CPML arithmetic; a prefetch of
+// those lines, issued with the first loads, turns that second round trip into a cache hit.
+#if defined(GPI_PF_NONE)
+#define GPI_PF "// no prefetch %0"
+#elif defined(GPI_PF_L2)
+#define GPI_PF "prefetch.global.L2 [%0];"
+#else
+#define GPI_PF "prefetch.global.L1 [%0];"
+#endif
+__device__ __forceinline__ void pf(const float* p) { asm volatile(GPI_PF :: "l"(p)); }
+__device__ __forceinline__ float ld1(const float* p) {
+    float r;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
 }
 __device__ __forceinline__ void st4(float* p, const F4& r) {
-    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]) : "memory");
 }
 
-// value at z-1 of element 0: lane-1's element 3, or a scalar load on the first lane of the warp
-__device__ __forceinline__ float z_prev(const F4& c, const float* p, unsigned mask, int lane, int k0) {
-    float r = __shfl_up_sync(mask, c.v[3], 1);
-    if (lane == 0 && k0 > 0) r = p[-1];
-    return r;
-}
-// value at z+1 of element 3: lane+1's element 0, or a scalar load on the last lane of the warp
-__device__ __forceinline__ float z_next(const F4& c, const float* p, unsigned mask, int lane, bool more) {
-    float r = __shfl_down_sync(mask, c.v[0], 1);
-    if (lane == 31 && more) r = p[4];
-    return r;
-}
+// value at z-1 of element 0 / at z+1 of element 3: one scalar load each, issued with all the other loads
+// of the thread.  They hit the 128-byte lines the neighbouring lanes fetch anyway (no extra DRAM or L2
+// traffic); warp shuffles would save the L1 request but make the first use of a loaded register precede
+// the issue of the remaining loads (ptxas schedules SHFL early), which serialises two DRAM round trips.
+__device__ __forceinline__ float z_prev(const float* p, int k0) { return k0 > 0 ? ld1(p - 1) : 0.f; }
+__device__ __forceinline__ float z_next(const float* p, bool more) { return more ? ld1(p + 4) : 0.f; }
 
 // d[e] * scale after a forward difference
 __device__ __forceinline__ F4 diff4(const F4& hi, const F4& lo, float sI) {
@@ -132,7 +147,7 @@ __device__ __forceinline__ void pml_apply_z(Pml4& q, const PmlTerm& t, F4& d) {
 __device__ __forceinline__ void pml_close(const Pml4& q) { if (q.mp) st4(q.mp, q.m); }
 
 // thread -> (group of four z cells, row j); plane i = blockIdx.y, batch slot = blockIdx.z
-struct Vec3Idx { int k0, j, i, b, lane; bool valid; };
+struct Vec3Idx { int k0, j, i, b; bool valid; };
 __device__ __forceinline__ Vec3Idx vec3_index(const Geom& g) {
     Vec3Idx q;
     const int nq = g.pz >> 2;
@@ -141,7 +156,6 @@ __device__ __forceinline__ Vec3Idx vec3_index(const Geom& g) {
     q.j = gid / nq;
     q.k0 = (gid - q.j * nq) << 2;
     q.i = blockIdx.y; q.b = blockIdx.z;
-    q.lane = threadIdx.x & 31;
     return q;
 }
 
@@ -154,7 +168,6 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
     const int k0 = q.k0, j = q.j, i = q.i, b = q.b;
     const int nz = g.nz, ny = g.ny, nx = g.nx;
     const bool fast = q.valid && i >= 2 && i <= nx - 2 && j >= 2 && j <= ny - 2;
-    const unsigned mask = __ballot_sync(0xffffffffu, fast);
     if (!q.valid) return;
     if (!fast) {
 #pragma unroll 1
@@ -168,6 +181,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
     const bool hxmin = g.pml & XMIN, hxmax = g.pml & XMAX, hymin = g.pml & YMIN, hymax = g.pml & YMAX;
 
     float* vx = a.v[V_X] + c; float* vy = a.v[V_Y] + c; float* vz = a.v[V_Z] + c;
+    pf(vx); pf(vy); pf(vz); pf(a.c[C_BX] + c - w); pf(a.c[C_BY] + c - w); pf(a.c[C_BZ] + c - w);
     F4 nvx = ld4(vx), nvy = ld4(vy), nvz = ld4(vz);
 
     if (!EL) {
@@ -178,7 +192,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
         pml_open<2>(m0, g, a.pv[0], slab_index(i, 1, nx - 1, g.npml, hxmin, hxmax), k0, j, i, b);
         pml_open<1>(m1, g, a.pv[1], slab_index(j, 1, ny - 1, g.npml, hymin, hymax), k0, j, i, b);
         pml_open_z(m2, g, a.pv[2], 1, nz - 1, k0, j, i, b);
-        const float pprev = z_prev(pc, p, mask, q.lane, k0);
+        const float pprev = z_prev(p, k0);
         F4 dx = diff4(pc, pmx, g.dxI);        pml_apply(m0, a.pv[0], dx);
         F4 dy = diff4(pc, pmy, g.dyI);        pml_apply(m1, a.pv[1], dy);
         F4 dz = diff4_zm(pc, pprev, g.dzI);   pml_apply_z(m2, a.pv[2], dz);
@@ -210,9 +224,9 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
         pml_open<2>(m0, g, a.pv[0], sx0, k0, j, i, b);   pml_open<1>(m1, g, a.pv[1], sy0, k0, j, i, b);   pml_open_z(m2, g, a.pv[2], 1, nz - 2, k0, j, i, b);
         pml_open<2>(m3, g, a.pv[3], sx1, k0, j, i, b);   pml_open<1>(m4, g, a.pv[4], sy1, k0, j, i, b);   pml_open_z(m5, g, a.pv[5], 1, nz - 2, k0, j, i, b);
         pml_open<2>(m6, g, a.pv[6], sx1, k0, j, i, b);   pml_open<1>(m7, g, a.pv[7], sy0, k0, j, i, b);   pml_open_z(m8, g, a.pv[8], 1, nz - 1, k0, j, i, b);
-        const float zzprev = z_prev(zz, tzz, mask, q.lane, k0);
-        const float xznext = z_next(xz, txz, mask, q.lane, more);
-        const float yznext = z_next(yz, tyz, mask, q.lane, more);
+        const float zzprev = z_prev(tzz, k0);
+        const float xznext = z_next(txz, more);
+        const float yznext = z_next(tyz, more);
 
         // vx: dtauxxdx + dtauxydy + dtauxzdz
         F4 dxx = diff4(xx, xxm, g.dxI);            pml_apply(m0, a.pv[0], dxx);
@@ -269,7 +283,6 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
     const int k0 = q.k0, j = q.j, i = q.i, b = q.b;
     const int nz = g.nz, ny = g.ny, nx = g.nx;
     const bool fast = q.valid && i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2;
-    const unsigned mask = __ballot_sync(0xffffffffu, fast);
     if (!q.valid) return;
     if (!fast) {
 #pragma unroll 1
@@ -295,7 +308,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
         float* p = a.tau[T_XX] + c;
         F4 pc = ld4(p);
         const F4 K = ldg4(a.c[C_K] + c - w);
-        const float vznext = z_next(cvz, vz, mask, q.lane, more);
+        const float vznext = z_next(vz, more);
         F4 dxx = diff4(vxpx, cvx, g.dxI);           pml_apply(m0, a.ps[0], dxx);       // @d_xa(vx)
         F4 dyy = diff4(vypy, cvy, g.dyI);           pml_apply(m1, a.ps[1], dyy);       // @d_ya(vy)
         F4 dzz = diff4_zp(cvz, vznext, g.dzI);      pml_apply_z(m2, a.ps[2], dzz);     // @d_za(vz)
@@ -310,6 +323,8 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
     const bool fs = (g.freesurf & ZMIN) != 0;
     float* txx = a.tau[T_XX] + c; float* tyy = a.tau[T_YY] + c; float* tzz = a.tau[T_ZZ] + c;
     float* txy = a.tau[T_XY] + c; float* txz = a.tau[T_XZ] + c; float* tyz = a.tau[T_YZ] + c;
+    pf(txx); pf(tyy); pf(tzz); pf(txy); pf(txz); pf(tyz);
+    pf(a.c[C_K] + c - w); pf(a.c[C_L] + c - w); pf(a.c[C_MUXZ] + c - w); pf(a.c[C_MUXY] + c - w); pf(a.c[C_MUYZ] + c - w);
     F4 xx = ld4(txx), yy = ld4(tyy), zz = ld4(tzz), xy = ld4(txy), xz = ld4(txz), yz = ld4(tyz);
     const F4 M = ldg4(a.c[C_K] + c - w), L = ldg4(a.c[C_L] + c - w);
     const F4 muxz = ldg4(a.c[C_MUXZ] + c - w), muxy = ldg4(a.c[C_MUXY] + c - w), muyz = ldg4(a.c[C_MUYZ] + c - w);
@@ -320,9 +335,9 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
     pml_open<1>(m3, g, a.ps[3], syh, k0, j, i, b);   pml_open<2>(m4, g, a.ps[4], sxh, k0, j, i, b);
     pml_open_z(m5, g, a.ps[5], 1, nz - 1, k0, j, i, b);   pml_open<2>(m6, g, a.ps[6], sxh, k0, j, i, b);
     pml_open_z(m7, g, a.ps[7], 1, nz - 1, k0, j, i, b);   pml_open<1>(m8, g, a.ps[8], syh, k0, j, i, b);
-    const float vznext = z_next(cvz, vz, mask, q.lane, more);
-    const float vxprev = z_prev(cvx, vx, mask, q.lane, k0);
-    const float vyprev = z_prev(cvy, vy, mask, q.lane, k0);
+    const float vznext = z_next(vz, more);
+    const float vxprev = z_prev(vx, k0);
+    const float vyprev = z_prev(vy, k0);
 
     // ---- phase 2: arithmetic in the reference's order ------------------------------------------------
     F4 dxx = diff4(vxpx, cvx, g.dxI);           pml_apply(m0, a.ps[0], dxx);       // @d_xa(vx)

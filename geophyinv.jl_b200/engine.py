@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgpifdtd.so")
+LIB_PATH = os.environ.get("GPI_LIB") or os.path.join(_HERE, "libgpifdtd.so")   # GPI_LIB: a tuning variant of the same library
 
 ABI_VERSION = 1
 ACOUSTIC, ELASTIC = 0, 1
