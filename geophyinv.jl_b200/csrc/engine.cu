@@ -268,7 +268,7 @@ void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch) {
 template <int EL>
 void launch_step_kernels3v(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
     const Geom& g = h->g;
-    const int ngroups = (g.pz / 4) * g.ny1;
+    const int ngroups = (g.pz / VW) * g.ny1;
     dim3 blk(h->blkv), grd((ngroups + h->blkv - 1) / h->blkv, g.nx1, nbatch);
     if (vel) k_vel3v<EL><<<grd, blk, 0, h->stream>>>(g, a);
     else     k_stress3v<EL><<<grd, blk, 0, h->stream>>>(g, a);

@@ -21,19 +21,27 @@
 // Arithmetic stays __fmul_rn / __fadd_rn / __fsub_rn in the reference's association order: results are
 // bit-identical to the scalar kernels and to the CPU restatement.
 
+// Launch shape, tuned on B200 (profiles/r01/tuning.md): one warp per block, 12 blocks per SM (168
+// registers per thread).  Small blocks retire and refill independently, which keeps more loads in flight
+// than 3 x 128 threads at the same register budget (27.6 vs 26.3 Gcell-updates/s on 338^3).
 #ifndef GPI_VEC_THREADS
-#define GPI_VEC_THREADS 128
+#define GPI_VEC_THREADS 32
 #endif
 #ifndef GPI_VEC_MINBLOCKS
-#define GPI_VEC_MINBLOCKS 3
+#define GPI_VEC_MINBLOCKS 12
 #endif
 
-struct F4 { float v[4]; };
+#ifndef GPI_VEC_W
+#define GPI_VEC_W 4          // z cells per thread: 4 (128-bit accesses) or 2 (64-bit accesses, half the registers)
+#endif
+constexpr int VW = GPI_VEC_W;
+struct F4 { float v[VW]; };
 // Loads and stores of the fast path are volatile asm: the compiler keeps volatile asm statements in
 // program order, so every load of a thread is issued before its first store and -- the point -- before
 // the arithmetic that consumes the first loaded value.  With plain C++ loads nvcc sinks the loads whose
 // values are needed last (the velocities and buoyancies of k_vel3v) below the CPML arithmetic to save
 // registers, which costs a second, serialised DRAM round trip per thread.
+#if GPI_VEC_W == 4
 __device__ __forceinline__ F4 ld4(const float* p) {
     F4 r;
     asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
@@ -44,6 +52,24 @@ __device__ __forceinline__ F4 ldg4(const float* p) {
     asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
     return r;
 }
+__device__ __forceinline__ void st4(float* p, const F4& r) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]) : "memory");
+}
+#else
+__device__ __forceinline__ F4 ld4(const float* p) {
+    F4 r;
+    asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ F4 ldg4(const float* p) {
+    F4 r;
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st4(float* p, const F4& r) {
+    asm volatile("st.global.v2.f32 [%0], {%1,%2};" :: "l"(p), "f"(r.v[0]), "f"(r.v[1]) : "memory");
+}
+#endif
 // ptxas still sinks the loads whose values are consumed last below the CPML arithmetic; a prefetch of
 // those lines, issued with the first loads, turns that second round trip into a cache hit.
 #if defined(GPI_PF_NONE)
@@ -59,22 +85,18 @@ __device__ __forceinline__ float ld1(const float* p) {
     asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
-__device__ __forceinline__ void st4(float* p, const F4& r) {
-    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]) : "memory");
-}
-
 // value at z-1 of element 0 / at z+1 of element 3: one scalar load each, issued with all the other loads
 // of the thread.  They hit the 128-byte lines the neighbouring lanes fetch anyway (no extra DRAM or L2
 // traffic); warp shuffles would save the L1 request but make the first use of a loaded register precede
 // the issue of the remaining loads (ptxas schedules SHFL early), which serialises two DRAM round trips.
 __device__ __forceinline__ float z_prev(const float* p, int k0) { return k0 > 0 ? ld1(p - 1) : 0.f; }
-__device__ __forceinline__ float z_next(const float* p, bool more) { return more ? ld1(p + 4) : 0.f; }
+__device__ __forceinline__ float z_next(const float* p, bool more) { return more ? ld1(p + VW) : 0.f; }
 
 // d[e] * scale after a forward difference
 __device__ __forceinline__ F4 diff4(const F4& hi, const F4& lo, float sI) {
     F4 r;
 #pragma unroll
-    for (int e = 0; e < 4; e++) r.v[e] = __fmul_rn(__fsub_rn(hi.v[e], lo.v[e]), sI);
+    for (int e = 0; e < VW; e++) r.v[e] = __fmul_rn(__fsub_rn(hi.v[e], lo.v[e]), sI);
     return r;
 }
 // forward difference along z onto half nodes: f(k) - f(k-1)
@@ -82,15 +104,15 @@ __device__ __forceinline__ F4 diff4_zm(const F4& c, float prev, float sI) {
     F4 r;
     r.v[0] = __fmul_rn(__fsub_rn(c.v[0], prev), sI);
 #pragma unroll
-    for (int e = 1; e < 4; e++) r.v[e] = __fmul_rn(__fsub_rn(c.v[e], c.v[e - 1]), sI);
+    for (int e = 1; e < VW; e++) r.v[e] = __fmul_rn(__fsub_rn(c.v[e], c.v[e - 1]), sI);
     return r;
 }
 // forward difference along z from half nodes onto integer nodes: f(k+1) - f(k)
 __device__ __forceinline__ F4 diff4_zp(const F4& c, float next, float sI) {
     F4 r;
 #pragma unroll
-    for (int e = 0; e < 3; e++) r.v[e] = __fmul_rn(__fsub_rn(c.v[e + 1], c.v[e]), sI);
-    r.v[3] = __fmul_rn(__fsub_rn(next, c.v[3]), sI);
+    for (int e = 0; e < VW - 1; e++) r.v[e] = __fmul_rn(__fsub_rn(c.v[e + 1], c.v[e]), sI);
+    r.v[VW - 1] = __fmul_rn(__fsub_rn(next, c.v[VW - 1]), sI);
     return r;
 }
 
@@ -130,7 +152,7 @@ __device__ __forceinline__ void pml_apply(Pml4& q, const PmlTerm& t, F4& d) {
     if (!q.mp) return;
     const float a = __ldg(t.a + q.s), bb = __ldg(t.b + q.s), kI = __ldg(t.kI + q.s);
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
+    for (int e = 0; e < VW; e++) {
         q.m.v[e] = __fadd_rn(__fmul_rn(bb, q.m.v[e]), __fmul_rn(a, d.v[e]));
         d.v[e] = __fadd_rn(__fmul_rn(d.v[e], kI), q.m.v[e]);
     }
@@ -139,7 +161,7 @@ __device__ __forceinline__ void pml_apply_z(Pml4& q, const PmlTerm& t, F4& d) {
     if (!q.mp) return;
     const F4 a = ldg4(t.a + q.s), bb = ldg4(t.b + q.s), kI = ldg4(t.kI + q.s);
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
+    for (int e = 0; e < VW; e++) {
         q.m.v[e] = __fadd_rn(__fmul_rn(bb.v[e], q.m.v[e]), __fmul_rn(a.v[e], d.v[e]));
         d.v[e] = __fadd_rn(__fmul_rn(d.v[e], kI.v[e]), q.m.v[e]);
     }
@@ -150,11 +172,11 @@ __device__ __forceinline__ void pml_close(const Pml4& q) { if (q.mp) st4(q.mp, q
 struct Vec3Idx { int k0, j, i, b; bool valid; };
 __device__ __forceinline__ Vec3Idx vec3_index(const Geom& g) {
     Vec3Idx q;
-    const int nq = g.pz >> 2;
+    const int nq = g.pz / VW;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     q.valid = gid < nq * g.ny1;
     q.j = gid / nq;
-    q.k0 = (gid - q.j * nq) << 2;
+    q.k0 = (gid - q.j * nq) * VW;
     q.i = blockIdx.y; q.b = blockIdx.z;
     return q;
 }
@@ -171,13 +193,13 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
     if (!q.valid) return;
     if (!fast) {
 #pragma unroll 1
-        for (int e = 0; e < 4; e++) if (k0 + e <= nz) vel_cell<3, EL>(g, a, k0 + e, j, i, b);
+        for (int e = 0; e < VW; e++) if (k0 + e <= nz) vel_cell<3, EL>(g, a, k0 + e, j, i, b);
         return;
     }
     const long long w = (long long)b * a.wstride;
     const long long c = uidx(g, k0, j, i) + w;
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
-    const bool more = k0 + 4 < g.pz;
+    const bool more = k0 + VW < g.pz;
     const bool hxmin = g.pml & XMIN, hxmax = g.pml & XMAX, hymin = g.pml & YMIN, hymax = g.pml & YMAX;
 
     float* vx = a.v[V_X] + c; float* vy = a.v[V_Y] + c; float* vz = a.v[V_Z] + c;
@@ -198,7 +220,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
         F4 dz = diff4_zm(pc, pprev, g.dzI);   pml_apply_z(m2, a.pv[2], dz);
         pml_close(m0); pml_close(m1); pml_close(m2);
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
+        for (int e = 0; e < VW; e++) {
             const int k = k0 + e;
             if (k >= 1 && k <= nz - 2) {
                 nvx.v[e] = __fadd_rn(nvx.v[e], __fmul_rn(bx.v[e], dx.v[e]));
@@ -242,7 +264,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
         F4 dzz = diff4_zm(zz, zzprev, g.dzI);      pml_apply_z(m8, a.pv[8], dzz);
         pml_close(m0); pml_close(m1); pml_close(m2); pml_close(m3); pml_close(m4); pml_close(m5); pml_close(m6); pml_close(m7); pml_close(m8);
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
+        for (int e = 0; e < VW; e++) {
             const int k = k0 + e;
             if (k >= 1 && k <= nz - 2) {
                 nvx.v[e] = __fsub_rn(nvx.v[e], __fmul_rn(bx.v[e], __fadd_rn(__fadd_rn(dxx.v[e], dxy.v[e]), dxz.v[e])));
@@ -255,13 +277,13 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
 
     // rigid z faces (dirichlet.jl:35-74); the x / y faces only touch shell rows (scalar path)
     const int R = g.rigid;
-    const bool head = k0 == 0, tail = k0 + 3 >= nz - 1;
+    const bool head = k0 == 0, tail = k0 + VW - 1 >= nz - 1;
     if (head && (R & ZMIN)) { nvx.v[0] = 0.f; nvy.v[0] = 0.f; nvz.v[0] = -nvz.v[1]; }
     if (!tail) {
         st4(vx, nvx); st4(vy, nvy); st4(vz, nvz);
     } else {
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
+        for (int e = 0; e < VW; e++) {
             const int k = k0 + e;
             if (k <= nz - 1) {
                 const bool zero = (R & ZMAX) && k == nz - 1;
@@ -286,13 +308,13 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
     if (!q.valid) return;
     if (!fast) {
 #pragma unroll 1
-        for (int e = 0; e < 4; e++) if (k0 + e <= nz) stress_cell<3, EL>(g, a, k0 + e, j, i, b);
+        for (int e = 0; e < VW; e++) if (k0 + e <= nz) stress_cell<3, EL>(g, a, k0 + e, j, i, b);
         return;
     }
     const long long w = (long long)b * a.wstride;
     const long long c = uidx(g, k0, j, i) + w;
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
-    const bool more = k0 + 4 < g.pz;
+    const bool more = k0 + VW < g.pz;
     const bool hxmin = g.pml & XMIN, hxmax = g.pml & XMAX, hymin = g.pml & YMIN, hymax = g.pml & YMAX;
 
     // ---- phase 1: every load of the thread ---------------------------------------------------------
@@ -313,7 +335,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
         F4 dyy = diff4(vypy, cvy, g.dyI);           pml_apply(m1, a.ps[1], dyy);       // @d_ya(vy)
         F4 dzz = diff4_zp(cvz, vznext, g.dzI);      pml_apply_z(m2, a.ps[2], dzz);     // @d_za(vz)
 #pragma unroll
-        for (int e = 0; e < 4; e++) if (k0 + e <= nz - 1)
+        for (int e = 0; e < VW; e++) if (k0 + e <= nz - 1)
             pc.v[e] = __fadd_rn(pc.v[e], __fmul_rn(__fadd_rn(__fadd_rn(dxx.v[e], dzz.v[e]), dyy.v[e]), K.v[e]));
         st4(p, pc);
         pml_close(m0); pml_close(m1); pml_close(m2);
@@ -344,7 +366,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
     F4 dyy = diff4(vypy, cvy, g.dyI);           pml_apply(m1, a.ps[1], dyy);       // @d_ya(vy)
     F4 dzz = diff4_zp(cvz, vznext, g.dzI);      pml_apply_z(m2, a.ps[2], dzz);     // @d_za(vz)
 #pragma unroll
-    for (int e = 0; e < 4; e++) if (k0 + e <= nz - 1) {
+    for (int e = 0; e < VW; e++) if (k0 + e <= nz - 1) {
         xx.v[e] = __fsub_rn(__fsub_rn(xx.v[e], __fmul_rn(M.v[e], dxx.v[e])), __fmul_rn(L.v[e], __fadd_rn(dyy.v[e], dzz.v[e])));
         yy.v[e] = __fsub_rn(__fsub_rn(yy.v[e], __fmul_rn(M.v[e], dyy.v[e])), __fmul_rn(L.v[e], __fadd_rn(dxx.v[e], dzz.v[e])));
         zz.v[e] = __fsub_rn(__fsub_rn(zz.v[e], __fmul_rn(M.v[e], dzz.v[e])), __fmul_rn(L.v[e], __fadd_rn(dyy.v[e], dxx.v[e])));
@@ -361,7 +383,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
     F4 dyz = diff4_zm(cvy, vyprev, g.dzI);      pml_apply_z(m7, a.ps[7], dyz);     // @d_zi(vy)
     F4 dzy = diff4(cvz, vzmy, g.dyI);           pml_apply(m8, a.ps[8], dzy);       // @d_yi(vz)
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
+    for (int e = 0; e < VW; e++) {
         const int k = k0 + e;
         if (k >= 1 && k <= nz - 1) {
             float n = __fsub_rn(xz.v[e], __fmul_rn(muxz.v[e], __fadd_rn(dxz.v[e], dzx.v[e])));
