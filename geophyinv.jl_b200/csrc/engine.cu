@@ -118,6 +118,10 @@ struct NcclApi {
     int (*GetUniqueId)(void*) = nullptr;
     int (*CommInitRank)(void**, int, Id128, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -160,6 +164,10 @@ struct gpi_handle {
     int blkv = GPI_VEC_THREADS;  bool vec3 = true;      // 3-D: float4-per-thread kernels (kernels3d.cuh); GPI_SCALAR3D=1 selects the scalar ones
     // nccl
     NcclApi nccl;  void* comm = nullptr;  int rank = 0, nranks = 1;
+    // z-slab domain decomposition
+    bool slab = false;  int srank = 0, snranks = 1;  int ka = 0, kb = 0;      // owned global unified z range [ka, kb)
+    int pzt = 0;                                                                // length of the k-indexed z coefficient tables
+    float* halo_send[2] = {nullptr, nullptr};  float* halo_recv[2] = {nullptr, nullptr};   // [0] towards rank-1, [1] towards rank+1
 };
 
 static std::string g_create_err;
@@ -188,31 +196,47 @@ int ensure_stage(gpi_handle* h, size_t nfloats) {
     return 0;
 }
 
-// host array in the field's own shape (column-major [z,(y),x]) <-> unified volume on the device
-int upload_field(gpi_handle* h, int f, const float* src, float* dvol) {
-    int n[3] = {h->g.nz, h->g.ny, h->g.nx}, sh[3], off[3];
+// host array in the field's own GLOBAL shape (column-major [z,(y),x]) <-> unified volume on the device.
+// A slab handle keeps local z indices kl = k - koff for k in [koff, koff + pz): uploads copy every row it can
+// hold (owned rows and the halo rows next to them), downloads return the owned rows and zero elsewhere.
+// `k_first`/`nk` describe a z-window of the source: src holds global field rows k_first .. k_first+nk-1.
+int upload_field(gpi_handle* h, int f, const float* src, float* dvol, int k_first = 0, int nk = -1) {
+    const Geom& g = h->g;
+    int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
     if (field_shape(h->nd, f, n, sh, off)) FAIL(h, "field %d has no shape in %d-D", f, h->nd);
-    if (ensure_stage(h, (size_t)h->g.vol)) return 1;
-    memset(h->stage, 0, (size_t)h->g.vol * sizeof(float));
-    for (int ix = 0; ix < sh[2]; ix++) for (int iy = 0; iy < sh[1]; iy++) {
-        const float* s = src + (size_t)sh[0] * ((size_t)iy + (size_t)sh[1] * ix);
-        float* d = h->stage + off[0] + (size_t)h->g.pz * ((size_t)(iy + off[1]) + (size_t)h->g.ny1 * (ix + off[2]));
-        memcpy(d, s, (size_t)sh[0] * sizeof(float));
+    if (nk < 0) nk = sh[0];
+    if (ensure_stage(h, (size_t)g.vol)) return 1;
+    // the staging buffer starts from the device copy so that rows outside the window keep their values
+    if (k_first != 0 || nk != sh[0]) {
+        CU(h, cudaMemcpyAsync(h->stage, dvol, (size_t)g.vol * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    } else memset(h->stage, 0, (size_t)g.vol * sizeof(float));
+    // field row iz (0-based in the global field array) sits at global unified k = iz + off[0]
+    const int iz_lo = std::max(std::max(0, k_first), g.koff - off[0]);
+    const int iz_hi = std::min(std::min(sh[0], k_first + nk), g.koff + g.pz - off[0]);      // exclusive
+    if (iz_hi > iz_lo) for (int ix = 0; ix < sh[2]; ix++) for (int iy = 0; iy < sh[1]; iy++) {
+        const float* sp = src + (size_t)nk * ((size_t)iy + (size_t)sh[1] * ix) + (iz_lo - k_first);
+        float* d = h->stage + (iz_lo + off[0] - g.koff) + (size_t)g.pz * ((size_t)(iy + off[1]) + (size_t)g.ny1 * (ix + off[2]));
+        memcpy(d, sp, (size_t)(iz_hi - iz_lo) * sizeof(float));
     }
-    CU(h, cudaMemcpyAsync(dvol, h->stage, (size_t)h->g.vol * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(dvol, h->stage, (size_t)g.vol * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 int download_field(gpi_handle* h, int f, const float* dvol, float* dst) {
-    int n[3] = {h->g.nz, h->g.ny, h->g.nx}, sh[3], off[3];
+    const Geom& g = h->g;
+    int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
     if (field_shape(h->nd, f, n, sh, off)) FAIL(h, "field %d has no shape in %d-D", f, h->nd);
-    if (ensure_stage(h, (size_t)h->g.vol)) return 1;
-    CU(h, cudaMemcpyAsync(h->stage, dvol, (size_t)h->g.vol * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (ensure_stage(h, (size_t)g.vol)) return 1;
+    CU(h, cudaMemcpyAsync(h->stage, dvol, (size_t)g.vol * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    for (int ix = 0; ix < sh[2]; ix++) for (int iy = 0; iy < sh[1]; iy++) {
-        float* d = dst + (size_t)sh[0] * ((size_t)iy + (size_t)sh[1] * ix);
-        const float* s = h->stage + off[0] + (size_t)h->g.pz * ((size_t)(iy + off[1]) + (size_t)h->g.ny1 * (ix + off[2]));
-        memcpy(d, s, (size_t)sh[0] * sizeof(float));
+    const int iz_lo = std::max(0, g.koff + g.klo - off[0]);
+    const int iz_hi = std::min(sh[0], g.koff + g.khi + 1 - off[0]);                          // exclusive
+    if (h->slab) memset(dst, 0, (size_t)sh[0] * sh[1] * sh[2] * sizeof(float));
+    if (iz_hi > iz_lo) for (int ix = 0; ix < sh[2]; ix++) for (int iy = 0; iy < sh[1]; iy++) {
+        float* d = dst + (size_t)sh[0] * ((size_t)iy + (size_t)sh[1] * ix) + iz_lo;
+        const float* sp = h->stage + (iz_lo + off[0] - g.koff) + (size_t)g.pz * ((size_t)(iy + off[1]) + (size_t)g.ny1 * (ix + off[2]));
+        memcpy(d, sp, (size_t)(iz_hi - iz_lo) * sizeof(float));
     }
     return 0;
 }
@@ -235,9 +259,9 @@ dim3 grid_for(const gpi_handle* h, dim3 blk, int nbatch) {
     const Geom& g = h->g;
     if (h->nd == 3) {
         int ntx = (g.nx1 + blk.z - 1) / blk.z;
-        return dim3((g.nz + 1 + blk.x - 1) / blk.x, (g.ny1 + blk.y - 1) / blk.y, ntx * nbatch);
+        return dim3((g.khi + 1 + blk.x - 1) / blk.x, (g.ny1 + blk.y - 1) / blk.y, ntx * nbatch);
     }
-    return dim3((g.nz + 1 + blk.x - 1) / blk.x, (g.nx1 + blk.y - 1) / blk.y, nbatch);
+    return dim3((g.khi + 1 + blk.x - 1) / blk.x, (g.nx1 + blk.y - 1) / blk.y, nbatch);
 }
 
 void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch) {
@@ -250,9 +274,9 @@ void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch) {
         PmlTerm p;
         p.mem = h->MEM + (long long)ipw * h->mem_per_pw + t.off;
         if (t.axis == 0) {
-            p.a = h->pmlztab + ((size_t)t.dfield * 3 + 0) * h->g.pz;
-            p.b = h->pmlztab + ((size_t)t.dfield * 3 + 1) * h->g.pz;
-            p.kI = h->pmlztab + ((size_t)t.dfield * 3 + 2) * h->g.pz;
+            p.a = h->pmlztab + ((size_t)t.dfield * 3 + 0) * h->pzt;
+            p.b = h->pmlztab + ((size_t)t.dfield * 3 + 1) * h->pzt;
+            p.kI = h->pmlztab + ((size_t)t.dfield * 3 + 2) * h->pzt;
         } else {
             p.a = h->pmlcoef + ((size_t)t.dfield * 3 + 0) * np2;
             p.b = h->pmlcoef + ((size_t)t.dfield * 3 + 1) * np2;
@@ -361,7 +385,21 @@ static int create_impl(gpi_handle* h) {
     const gpi_config& c = h->c;
     Geom& g = h->g;
     g.nz = c.n[0]; g.ny = h->nd == 3 ? c.n[1] : 1; g.nx = c.n[2];
-    g.pz = ((g.nz + 1 + 31) / 32) * 32;
+    // z-slab window: global unified nodes k in [0, nz] split evenly; koff is a multiple of four so that
+    // the vector kernels' global table / z-memory indices keep their 16-byte alignment
+    g.koff = 0; g.klo = 0; g.khi = g.nz;
+    h->ka = 0; h->kb = g.nz + 1;
+    if (h->slab) {
+        const long long nodes = g.nz + 1;
+        h->ka = (int)(nodes * h->srank / h->snranks);
+        h->kb = (int)(nodes * (h->srank + 1) / h->snranks);
+        if (h->kb - h->ka < 4) FAIL(h, "z-slab of rank %d has only %d planes", h->srank, h->kb - h->ka);
+        g.koff = h->srank == 0 ? 0 : ((h->ka - 1) / 4) * 4;
+        g.klo = h->ka - g.koff;
+        g.khi = h->kb - 1 - g.koff;
+    }
+    g.pz = ((g.khi + 2 + 31) / 32) * 32;
+    h->pzt = ((g.nz + 64 + 31) / 32) * 32;
     g.ny1 = h->nd == 3 ? g.ny + 1 : 1;
     g.nx1 = g.nx + 1;
     g.npml = c.npml;
@@ -445,8 +483,8 @@ static int create_impl(gpi_handle* h) {
     std::vector<float> coef((size_t)GPI_NFIELD * 3 * np2, 0.f);
     for (int f = 0; f < GPI_NFIELD; f++) for (int i = 0; i < np2; i++) coef[((size_t)f * 3 + 2) * np2 + i] = 1.f;
     if (to_device(h, &h->pmlcoef, coef)) return 1;
-    std::vector<float> ztab((size_t)GPI_NFIELD * 3 * g.pz, 0.f);
-    for (int f = 0; f < GPI_NFIELD; f++) for (int i = 0; i < g.pz; i++) ztab[((size_t)f * 3 + 2) * g.pz + i] = 1.f;
+    std::vector<float> ztab((size_t)GPI_NFIELD * 3 * h->pzt, 0.f);
+    for (int f = 0; f < GPI_NFIELD; f++) for (int i = 0; i < h->pzt; i++) ztab[((size_t)f * 3 + 2) * h->pzt + i] = 1.f;
     if (to_device(h, &h->pmlztab, ztab)) return 1;
 
     // medium
@@ -496,6 +534,11 @@ static int create_impl(gpi_handle* h) {
     CU(h, cudaMallocHost((void**)&h->h_post_s, (size_t)B * sizeof(PostDesc)));
     CU(h, cudaEventCreate(&h->ev0));
     CU(h, cudaEventCreate(&h->ev1));
+    if (h->slab) for (int d = 0; d < 2; d++) {
+        const size_t nb = (size_t)3 * g.ny1 * g.nx1 * sizeof(float);
+        CU(h, cudaMalloc((void**)&h->halo_send[d], nb));
+        CU(h, cudaMalloc((void**)&h->halo_recv[d], nb));
+    }
     return 0;
 }
 
@@ -512,6 +555,12 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_create_err = "gpi_create: no CUDA device (this engine has no CPU fallback)"; return 1; }
     gpi_handle* h = new gpi_handle();
     h->c = *cfg; h->nd = cfg->ndims; h->el = cfg->physics == GPI_ELASTIC; h->npw = cfg->npw;
+    if (cfg->slab_nranks > 1) {
+        if (cfg->ndims != 3 || cfg->npw != 1 || cfg->store_boundary || cfg->slab_rank < 0 || cfg->slab_rank >= cfg->slab_nranks) {
+            g_create_err = "gpi_create: z-slabs need ndims = 3, npw = 1, no boundary store and 0 <= slab_rank < slab_nranks"; delete h; return 1;
+        }
+        h->slab = true; h->srank = cfg->slab_rank; h->snranks = cfg->slab_nranks;
+    }
     if (cfg->device >= 0) h->device = cfg->device; else cudaGetDevice(&h->device);
     if (cudaSetDevice(h->device) != cudaSuccess) { g_create_err = "gpi_create: cudaSetDevice failed"; delete h; return 1; }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_err = "gpi_create: stream creation failed"; delete h; return 1; }
@@ -552,6 +601,7 @@ extern "C" int gpi_destroy(gpi_handle* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (auto e : h->evpool) cudaEventDestroy(e);
+    for (int d = 0; d < 2; d++) { cudaFree(h->halo_send[d]); cudaFree(h->halo_recv[d]); }
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -573,6 +623,17 @@ extern "C" int gpi_set_medium(gpi_handle* h, int p, const float* a) {
     if (p < 0 || p >= GPI_NPARAM || !h->mod[p]) FAIL(h, "medium parameter %d is not part of this physics", p);
     if (!a) FAIL(h, "null medium array");
     return upload_field(h, h->el ? GPI_TAUXX : GPI_P, a, h->mod[p]);
+}
+extern "C" int gpi_set_medium_rows(gpi_handle* h, int p, const float* rows, int k_first, int nk) {
+    GUARD(h);
+    if (p < 0 || p >= GPI_NPARAM || !h->mod[p]) FAIL(h, "medium parameter %d is not part of this physics", p);
+    if (!rows || k_first < 0 || nk < 1 || k_first + nk > h->g.nz) FAIL(h, "bad medium row window [%d, %d)", k_first, k_first + nk);
+    return upload_field(h, h->el ? GPI_TAUXX : GPI_P, rows, h->mod[p], k_first, nk);
+}
+extern "C" int gpi_slab_range(gpi_handle* h, int32_t* k_begin, int32_t* k_end) {
+    if (!h || !k_begin || !k_end) return 1;
+    *k_begin = h->ka; *k_end = h->kb;
+    return 0;
 }
 extern "C" int gpi_get_medium(gpi_handle* h, int p, float* out) {
     GUARD(h);
@@ -605,17 +666,18 @@ extern "C" int gpi_set_pml(gpi_handle* h, int f, const float* a, const float* b,
         int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
         field_shape(h->nd, f, n, sh, off);
         const int s0 = off[0], len = sh[0], npml = h->c.npml;
-        std::vector<float> ta(g.pz, 0.f), tb(g.pz, 0.f), tk(g.pz, 1.f);
-        for (int k = 0; k < g.pz; k++) {
+        const int pzt = h->pzt;
+        std::vector<float> ta(pzt, 0.f), tb(pzt, 0.f), tk(pzt, 1.f);
+        for (int k = 0; k < pzt; k++) {
             const int r = k - s0;
             int s = -1;
             if ((h->c.pml_faces & ZMIN) && r >= 0 && r < npml) s = r;
             else if ((h->c.pml_faces & ZMAX) && r - (len - npml) >= 0 && r < len) s = npml + r - (len - npml);
             if (s >= 0) { ta[k] = a[s]; tb[k] = b[s]; tk[k] = kI[s]; }
         }
-        CU(h, cudaMemcpy(h->pmlztab + ((size_t)f * 3 + 0) * g.pz, ta.data(), g.pz * sizeof(float), cudaMemcpyHostToDevice));
-        CU(h, cudaMemcpy(h->pmlztab + ((size_t)f * 3 + 1) * g.pz, tb.data(), g.pz * sizeof(float), cudaMemcpyHostToDevice));
-        CU(h, cudaMemcpy(h->pmlztab + ((size_t)f * 3 + 2) * g.pz, tk.data(), g.pz * sizeof(float), cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->pmlztab + ((size_t)f * 3 + 0) * pzt, ta.data(), pzt * sizeof(float), cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->pmlztab + ((size_t)f * 3 + 1) * pzt, tb.data(), pzt * sizeof(float), cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->pmlztab + ((size_t)f * 3 + 2) * pzt, tk.data(), pzt * sizeof(float), cudaMemcpyHostToDevice));
     }
     return 0;
 }
@@ -646,9 +708,13 @@ extern "C" int gpi_set_sparse(gpi_handle* h, int kind, int ipw, int issp, int f,
             const int64_t r = rowval[e] - 1;
             if (r < 0 || r >= flen) FAIL(h, "row index %lld outside the field array of %lld entries", (long long)rowval[e], flen);
             const int iz = (int)(r % sh[0]), iy = (int)((r / sh[0]) % sh[1]), ix = (int)(r / ((long long)sh[0] * sh[1]));
-            const int k = iz + off[0], j = iy + off[1], i = ix + off[2];
-            cell[e] = (int)((long long)k + (long long)g.pz * (j + (long long)g.ny1 * i));
-            val[e] = nzval[e];
+            const int k = iz + off[0], j = iy + off[1], i = ix + off[2];       // k: global unified z index
+            const int kl = k - g.koff;
+            const bool owned = kl >= g.klo && kl <= g.khi;
+            // a tap outside this handle's slab contributes nothing here (its owner adds it; records are summed over ranks)
+            cell[e] = owned ? (int)((long long)kl + (long long)g.pz * (j + (long long)g.ny1 * i)) : (int)g.klo;
+            val[e] = owned ? nzval[e] : 0.f;
+            if (!owned) continue;
             // injection view: velocity sources only act on the @inn range (source.jl:166-177)
             bool ok = true;
             if (isv) {
@@ -812,6 +878,46 @@ int build_post(gpi_handle* h, int shot0, int nb, int activepw, int src_flags) {
     return 0;
 }
 
+// z-slab halo exchange with the two z neighbours.  phase 0 (before the velocity kernel):
+// tauzz | p travels up (plane khi -> neighbour's klo-1), tauxz and tauyz travel down (plane klo ->
+// neighbour's khi+1).  phase 1 (before the stress kernel): vx, vy travel up, vz travels down.
+// One pack kernel per direction, one grouped NCCL send/recv over NVLink, one unpack kernel per direction,
+// all on the engine's stream.
+int exchange_halos(gpi_handle* h, int phase) {
+    if (!h->slab) return 0;
+    if (!h->comm) FAIL(h, "z-slab handles need gpi_nccl_init before gpi_run");
+    const Geom& g = h->g;
+    const size_t plane = (size_t)g.ny1 * g.nx1;
+    int up[3], dn[3], nup = 0, ndn = 0;
+    if (phase == 0) {
+        up[nup++] = h->el ? GPI_TAUZZ : GPI_P;
+        if (h->el) { dn[ndn++] = GPI_TAUXZ; dn[ndn++] = GPI_TAUYZ; }
+    } else {
+        if (h->el) { up[nup++] = GPI_VX; up[nup++] = GPI_VY; }
+            dn[ndn++] = GPI_VZ;
+    }
+    const bool has_up = h->srank < h->snranks - 1, has_dn = h->srank > 0;
+    dim3 blk(128), grd((g.ny1 + 127) / 128, g.nx1);
+    auto args = [&](const int* f, int n, int k) { HaloArgs a; a.n = n; for (int q = 0; q < 3; q++) { a.field[q] = q < n ? wf_ptr(h, h->W, 0, 0, f[q]) : nullptr; a.k[q] = k; } return a; };
+    if (has_up && nup) { k_halo<1><<<grd, blk, 0, h->stream>>>(g, args(up, nup, g.khi), h->halo_send[1]); h->timers.launches += 1; }
+    if (has_dn && ndn) { k_halo<1><<<grd, blk, 0, h->stream>>>(g, args(dn, ndn, g.klo), h->halo_send[0]); h->timers.launches += 1; }
+    const int F32 = 7;   // ncclFloat32
+    int rc = h->nccl.GroupStart();
+    if (has_up) {
+        if (nup && !rc) rc = h->nccl.Send(h->halo_send[1], nup * plane, F32, h->srank + 1, h->comm, h->stream);
+        if (ndn && !rc) rc = h->nccl.Recv(h->halo_recv[1], ndn * plane, F32, h->srank + 1, h->comm, h->stream);
+    }
+    if (has_dn) {
+        if (ndn && !rc) rc = h->nccl.Send(h->halo_send[0], ndn * plane, F32, h->srank - 1, h->comm, h->stream);
+        if (nup && !rc) rc = h->nccl.Recv(h->halo_recv[0], nup * plane, F32, h->srank - 1, h->comm, h->stream);
+    }
+    const int rc2 = h->nccl.GroupEnd();
+    if (rc || rc2) FAIL(h, "NCCL halo exchange failed: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(rc ? rc : rc2) : "?");
+    if (has_up && ndn) { k_halo<0><<<grd, blk, 0, h->stream>>>(g, args(dn, ndn, g.khi + 1), h->halo_recv[1]); h->timers.launches += 1; }
+    if (has_dn && nup) { k_halo<0><<<grd, blk, 0, h->stream>>>(g, args(up, nup, g.klo - 1), h->halo_recv[0]); h->timers.launches += 1; }
+    return 0;
+}
+
 bool any_post(const PostDesc* d, int nb, bool with_rec) {
     for (int b = 0; b < nb; b++) if (d[b].ninj > 0 || (with_rec && d[b].nrec > 0)) return true;
     return false;
@@ -824,6 +930,8 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     if (mode != GPI_MODE_FORWARD && mode != GPI_MODE_FORWARD_SAVE && mode != GPI_MODE_ADJOINT) FAIL(h, "unknown mode %d", mode);
     if (!(activepw & 1)) FAIL(h, "pw 1 must be active");
     if ((activepw & 2) && h->npw < 2) FAIL(h, "pw 2 requested but the experiment was built with npw = 1");
+    if (h->slab && mode != GPI_MODE_FORWARD) FAIL(h, "z-slab handles run forward modelling only");
+    if (h->slab && (!h->comm || h->nranks != h->snranks || h->rank != h->srank)) FAIL(h, "z-slab handles need gpi_nccl_init(rank = slab_rank, nranks = slab_nranks) before gpi_run");
     if (mode == GPI_MODE_FORWARD_SAVE && !h->c.store_boundary) FAIL(h, "forward_save needs store_boundary=1 at construction (fdtd.jl:445-455)");
     if (mode == GPI_MODE_ADJOINT && !h->c.store_boundary) FAIL(h, "adjoint needs the boundary store of a forward_save run");
     const bool grad = mode == GPI_MODE_ADJOINT && (activepw & 2) && h->npw == 2;
@@ -877,12 +985,14 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             const bool sample = h->sample_every > 0 && (it % h->sample_every) == 0;
             for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], true, nb, sample && ipw == 0);
             if (do_post_v) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_v, it, it, nt, (float)h->c.dt, 3); h->timers.launches += 1; }
+            if (exchange_halos(h, 1)) return 1;
             for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], false, nb, sample && ipw == 0);
             // stress sources at step it, then the pressure record of step it+1 (record! runs at the start of a step)
             if (inj_s || (rec_s && it < nt)) {
                 k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, it, it + 1, nt, (float)h->c.dt, 3);
                 h->timers.launches += 1;
             }
+            if (exchange_halos(h, 0)) return 1;
             if (mode == GPI_MODE_FORWARD_SAVE) {
                 for (int b = 0; b < nb; b++) for (int i = 0; i < nbf; i++) for (int q = 0; q < 3; q++) {
                     if (q == 1 && h->nd == 2) continue;
@@ -919,6 +1029,13 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             k_axpy1<<<(unsigned)((g.vol + 255) / 256), 256, 0, h->stream>>>(h->gtot[GPI_RHO], h->gshot + (size_t)b * 2 * g.vol + g.vol, g.vol);
             h->timers.launches += 2;
         }
+        // z-slabs: every rank holds the partial sums of the taps it owns; one sum all-reduce per record block
+        if (h->slab) for (int b = 0; b < nb; b++) for (int f = 0; f < GPI_NWAVEFIELD; f++) {
+            ShotData& sd = h->shots[0][shot0 + b];
+            if (!sd.rec[f] || sd.nr[f] == 0) continue;
+            int r = h->nccl.AllReduce(sd.rec[f], sd.rec[f], (size_t)nt * sd.nr[f], /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->comm, h->stream);
+            if (r != 0) FAIL(h, "ncclAllReduce of the records failed: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(r) : "?");
+        }
         CU(h, cudaGetLastError());
         // the pinned descriptor buffers are reused by the next batch
         CU(h, cudaStreamSynchronize(h->stream));
@@ -938,7 +1055,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     h->timers.stencil_ms = h->timers.vel_ms + h->timers.stress_ms;
     const int npw_active = ((activepw & 1) ? 1 : 0) + ((activepw & 2) ? 1 : 0);
     h->timers.steps = (double)nt * h->c.nshots;
-    h->timers.cell_updates = (double)nt * h->c.nshots * npw_active * (double)g.nz * g.ny * g.nx;
+    h->timers.cell_updates = (double)nt * h->c.nshots * npw_active * (double)(h->slab ? std::min(h->kb, g.nz) - h->ka : g.nz) * g.ny * g.nx;
     return 0;
 }
 
@@ -1007,6 +1124,10 @@ int load_nccl(gpi_handle* h, NcclApi& n) {
     n.GetUniqueId = (int (*)(void*))dlsym(n.lib, "ncclGetUniqueId");
     n.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(n.lib, "ncclCommInitRank");
     n.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(n.lib, "ncclAllReduce");
+    n.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(n.lib, "ncclSend");
+    n.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(n.lib, "ncclRecv");
+    n.GroupStart = (int (*)())dlsym(n.lib, "ncclGroupStart");
+    n.GroupEnd = (int (*)())dlsym(n.lib, "ncclGroupEnd");
     n.CommDestroy = (int (*)(void*))dlsym(n.lib, "ncclCommDestroy");
     n.GetErrorString = (const char* (*)(int))dlsym(n.lib, "ncclGetErrorString");
     if (!n.GetUniqueId || !n.CommInitRank || !n.AllReduce || !n.CommDestroy) { if (h) h->err = "libnccl is missing symbols"; return 1; }

@@ -41,7 +41,11 @@ enum { V_X = 0, V_Y = 1, V_Z = 2 };
 enum { C_BX = 0, C_BY, C_BZ, C_K /*dtK or dtM*/, C_L /*dtlambda*/, C_MUXZ, C_MUXY, C_MUYZ, C_N };
 
 struct Geom {
-    int nz, ny, nx;          // extended grid (tauii nodes); ny = 1 in 2-D
+    int nz, ny, nx;          // extended GLOBAL grid (tauii nodes); ny = 1 in 2-D
+    // z-slab window of this handle (multi-GPU domain decomposition; the full domain has koff = 0,
+    // klo = 0, khi = nz): local z index kl <-> global k = kl + koff (koff % 4 == 0); this handle
+    // updates the nodes kl in [klo, khi]; kl = klo-1 and khi+1 are halo planes filled by the exchange.
+    int koff, klo, khi;
     int pz;                  // z pitch in floats (multiple of 32)
     int ny1;                 // rows per x-plane: ny+1 (3-D) or 1 (2-D)
     int nx1;                 // nx+1
@@ -92,7 +96,7 @@ __device__ __forceinline__ int slab_index(int u, int s0, int len, int npml, bool
 }
 __device__ __forceinline__ int zslab_base(int s0, int len, int npml) { return ((s0 + len - npml) >> 2) << 2; }
 
-template <int AXIS>
+template <int AXIS>    // k is the GLOBAL z index
 __device__ __forceinline__ float cpml(const Geom& g, const PmlTerm& t, float d, int k, int j, int i,
                                       int s0, int len, int b) {
     const int u = AXIS == 0 ? k : (AXIS == 1 ? j : i);
@@ -102,8 +106,8 @@ __device__ __forceinline__ float cpml(const Geom& g, const PmlTerm& t, float d, 
     if (s >= 0) {
         long long mi;
         int ci = s;
-        if (AXIS == 2)      mi = (long long)k + (long long)g.pz * ((long long)j + (long long)g.ny1 * s);
-        else if (AXIS == 1) mi = (long long)k + (long long)g.pz * ((long long)s + 2LL * g.npml * i);
+        if (AXIS == 2)      mi = (long long)(k - g.koff) + (long long)g.pz * ((long long)j + (long long)g.ny1 * s);
+        else if (AXIS == 1) mi = (long long)(k - g.koff) + (long long)g.pz * ((long long)s + 2LL * g.npml * i);
         else {
             const int zi = s < g.npml ? k : (g.pzm >> 1) + (k - zslab_base(s0, len, g.npml));
             mi = (long long)zi + (long long)g.pzm * ((long long)j + (long long)g.ny1 * i);
@@ -133,7 +137,7 @@ __device__ __forceinline__ bool cell(const Geom& g, int nbatch, int& k, int& j, 
         b = blockIdx.z;
     }
     (void)nbatch;
-    return k <= g.nz && j < g.ny1 && i <= g.nx;
+    return k >= g.klo && k <= g.khi && j < g.ny1 && i <= g.nx;      // k: local z index of an owned node
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -145,9 +149,10 @@ __device__ __forceinline__ bool cell(const Geom& g, int nbatch, int& k, int& j, 
 //   elastic  : 0 dtauxxdx 1 dtauxydy 2 dtauxzdz | 3 dtauxydx 4 dtauyydy 5 dtauyzdz | 6 dtauxzdx 7 dtauyzdy 8 dtauzzdz
 // ------------------------------------------------------------------------------------------------
 template <int ND, int EL>
-__device__ __forceinline__ void vel_cell(const Geom& g, const StepArgs& a, int k, int j, int i, int b) {
+__device__ __forceinline__ void vel_cell(const Geom& g, const StepArgs& a, int kl, int j, int i, int b) {
     const long long w = (long long)b * a.wstride;
-    const long long c = uidx(g, k, j, i);
+    const long long c = uidx(g, kl, j, i);
+    const int k = kl + g.koff;                  // global z index: every range predicate below is global
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
     const int nz = g.nz, ny = g.ny, nx = g.nx;
 
@@ -300,9 +305,10 @@ __global__ void __launch_bounds__(256) k_vel(const Geom g, const StepArgs a) {
 //   0 dvxdx 1 dvydy 2 dvzdz | 3 dvxdy 4 dvydx (tauxy) | 5 dvxdz 6 dvzdx (tauxz) | 7 dvydz 8 dvzdy (tauyz)
 // ------------------------------------------------------------------------------------------------
 template <int ND, int EL>
-__device__ __forceinline__ void stress_cell(const Geom& g, const StepArgs& a, int k, int j, int i, int b) {
+__device__ __forceinline__ void stress_cell(const Geom& g, const StepArgs& a, int kl, int j, int i, int b) {
     const long long w = (long long)b * a.wstride;
-    const long long c = uidx(g, k, j, i);
+    const long long c = uidx(g, kl, j, i);
+    const int k = kl + g.koff;                  // global z index
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
     const int nz = g.nz, ny = g.ny, nx = g.nx;
 
@@ -414,6 +420,7 @@ __global__ void k_dmod(const Geom g, const float* __restrict__ m0, const float* 
     int k, j, i, b;
     if (!cell<ND>(g, 1, k, j, i, b)) return;
     const long long c = uidx(g, k, j, i);
+    k += g.koff;                                // global z index for the range predicates
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
     const int nz = g.nz, ny = g.ny, nx = g.nx;
     const double ddt = (double)dt;
@@ -570,6 +577,26 @@ __global__ void k_grad2d(const Geom g, const float* __restrict__ p1, const float
         const float ax = __fadd_rn(bufx(c - sx), bufx(c));     // vxbuffer[iz+1, ix] + vxbuffer[iz+1, ix+1]
         const float az = __fadd_rn(bufz(c - 1), bufz(c));      // vzbuffer[iz, ix+1] + vzbuffer[iz+1, ix+1]
         gR[gw + c] = (float)((double)gR[gw + c] - (double)ax * 0.5 - (double)az * 0.5);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// z-slab halo planes (multi-GPU domain decomposition, no counterpart in the reference).  z is the
+// fast axis, so a z = const plane is strided in memory: pack gathers up to three planes into one
+// contiguous buffer [field][i][j] that travels over NVLink; unpack scatters it into the halo plane.
+// ------------------------------------------------------------------------------------------------
+struct HaloArgs { int n; float* field[3]; int k[3]; };
+template <int PACK>
+__global__ void k_halo(const Geom g, const HaloArgs a, float* __restrict__ buf) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= g.ny1) return;
+    const long long plane = (long long)g.ny1 * g.nx1;
+    const long long q = (long long)j + (long long)g.ny1 * i;
+    for (int f = 0; f < a.n; f++) {
+        float* p = a.field[f] + uidx(g, a.k[f], j, i);
+        if (PACK) buf[f * plane + q] = *p;
+        else      *p = buf[f * plane + q];
     }
 }
 

@@ -135,8 +135,9 @@ __device__ __forceinline__ void pml_open(Pml4& q, const Geom& g, const PmlTerm& 
     q.m = ld4(q.mp);
 }
 // z terms: float4-aligned memory rows (cpml<> in kernels.cuh); s holds k0 for the table look-up
-__device__ __forceinline__ void pml_open_z(Pml4& q, const Geom& g, const PmlTerm& t, int s0, int len, int k0, int j, int i, int b) {
+__device__ __forceinline__ void pml_open_z(Pml4& q, const Geom& g, const PmlTerm& t, int s0, int len, int k0l, int j, int i, int b) {
     const int npml = g.npml;
+    const int k0 = k0l + g.koff;                 // global index of the first cell (koff % 4 == 0 keeps the alignment)
     int zi = -1;
     if ((g.pml & ZMIN) && k0 < s0 + npml) zi = k0;
     else if (g.pml & ZMAX) {
@@ -193,9 +194,10 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
     if (!q.valid) return;
     if (!fast) {
 #pragma unroll 1
-        for (int e = 0; e < VW; e++) if (k0 + e <= nz) vel_cell<3, EL>(g, a, k0 + e, j, i, b);
+        for (int e = 0; e < VW; e++) if (k0 + e >= g.klo && k0 + e <= g.khi) vel_cell<3, EL>(g, a, k0 + e, j, i, b);
         return;
     }
+    const int kg0 = k0 + g.koff;                 // global z index of element 0
     const long long w = (long long)b * a.wstride;
     const long long c = uidx(g, k0, j, i) + w;
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
@@ -221,12 +223,12 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
         pml_close(m0); pml_close(m1); pml_close(m2);
 #pragma unroll
         for (int e = 0; e < VW; e++) {
-            const int k = k0 + e;
-            if (k >= 1 && k <= nz - 2) {
+            const int k = kg0 + e; const bool own = (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo);
+            if (own && k >= 1 && k <= nz - 2) {
                 nvx.v[e] = __fadd_rn(nvx.v[e], __fmul_rn(bx.v[e], dx.v[e]));
                 nvy.v[e] = __fadd_rn(nvy.v[e], __fmul_rn(by.v[e], dy.v[e]));
             }
-            if (k >= 1 && k <= nz - 1) nvz.v[e] = __fadd_rn(nvz.v[e], __fmul_rn(bz.v[e], dz.v[e]));
+            if (own && k >= 1 && k <= nz - 1) nvz.v[e] = __fadd_rn(nvz.v[e], __fmul_rn(bz.v[e], dz.v[e]));
         }
     } else {
         const float* txx = a.tau[T_XX] + c; const float* tyy = a.tau[T_YY] + c; const float* tzz = a.tau[T_ZZ] + c;
@@ -265,27 +267,27 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
         pml_close(m0); pml_close(m1); pml_close(m2); pml_close(m3); pml_close(m4); pml_close(m5); pml_close(m6); pml_close(m7); pml_close(m8);
 #pragma unroll
         for (int e = 0; e < VW; e++) {
-            const int k = k0 + e;
-            if (k >= 1 && k <= nz - 2) {
+            const int k = kg0 + e; const bool own = (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo);
+            if (own && k >= 1 && k <= nz - 2) {
                 nvx.v[e] = __fsub_rn(nvx.v[e], __fmul_rn(bx.v[e], __fadd_rn(__fadd_rn(dxx.v[e], dxy.v[e]), dxz.v[e])));
                 nvy.v[e] = __fsub_rn(nvy.v[e], __fmul_rn(by.v[e], __fadd_rn(__fadd_rn(dyx.v[e], dyy.v[e]), dyz.v[e])));
             }
-            if (k >= 1 && k <= nz - 1)
+            if (own && k >= 1 && k <= nz - 1)
                 nvz.v[e] = __fsub_rn(nvz.v[e], __fmul_rn(bz.v[e], __fadd_rn(__fadd_rn(dzx.v[e], dzy.v[e]), dzz.v[e])));
         }
     }
 
     // rigid z faces (dirichlet.jl:35-74); the x / y faces only touch shell rows (scalar path)
     const int R = g.rigid;
-    const bool head = k0 == 0, tail = k0 + VW - 1 >= nz - 1;
+    const bool head = kg0 == 0, tail = kg0 + VW - 1 >= nz - 1;
     if (head && (R & ZMIN)) { nvx.v[0] = 0.f; nvy.v[0] = 0.f; nvz.v[0] = -nvz.v[1]; }
     if (!tail) {
         st4(vx, nvx); st4(vy, nvy); st4(vz, nvz);
     } else {
 #pragma unroll
         for (int e = 0; e < VW; e++) {
-            const int k = k0 + e;
-            if (k <= nz - 1) {
+            const int k = kg0 + e; const bool own = (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo);
+            if (own && k <= nz - 1) {
                 const bool zero = (R & ZMAX) && k == nz - 1;
                 vx[e] = zero ? 0.f : nvx.v[e];
                 vy[e] = zero ? 0.f : nvy.v[e];
@@ -308,9 +310,10 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
     if (!q.valid) return;
     if (!fast) {
 #pragma unroll 1
-        for (int e = 0; e < VW; e++) if (k0 + e <= nz) stress_cell<3, EL>(g, a, k0 + e, j, i, b);
+        for (int e = 0; e < VW; e++) if (k0 + e >= g.klo && k0 + e <= g.khi) stress_cell<3, EL>(g, a, k0 + e, j, i, b);
         return;
     }
+    const int kg0 = k0 + g.koff;                 // global z index of element 0
     const long long w = (long long)b * a.wstride;
     const long long c = uidx(g, k0, j, i) + w;
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
@@ -335,7 +338,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
         F4 dyy = diff4(vypy, cvy, g.dyI);           pml_apply(m1, a.ps[1], dyy);       // @d_ya(vy)
         F4 dzz = diff4_zp(cvz, vznext, g.dzI);      pml_apply_z(m2, a.ps[2], dzz);     // @d_za(vz)
 #pragma unroll
-        for (int e = 0; e < VW; e++) if (k0 + e <= nz - 1)
+        for (int e = 0; e < VW; e++) if (kg0 + e <= nz - 1 && (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo))
             pc.v[e] = __fadd_rn(pc.v[e], __fmul_rn(__fadd_rn(__fadd_rn(dxx.v[e], dzz.v[e]), dyy.v[e]), K.v[e]));
         st4(p, pc);
         pml_close(m0); pml_close(m1); pml_close(m2);
@@ -366,12 +369,12 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
     F4 dyy = diff4(vypy, cvy, g.dyI);           pml_apply(m1, a.ps[1], dyy);       // @d_ya(vy)
     F4 dzz = diff4_zp(cvz, vznext, g.dzI);      pml_apply_z(m2, a.ps[2], dzz);     // @d_za(vz)
 #pragma unroll
-    for (int e = 0; e < VW; e++) if (k0 + e <= nz - 1) {
+    for (int e = 0; e < VW; e++) if (kg0 + e <= nz - 1 && (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo)) {
         xx.v[e] = __fsub_rn(__fsub_rn(xx.v[e], __fmul_rn(M.v[e], dxx.v[e])), __fmul_rn(L.v[e], __fadd_rn(dyy.v[e], dzz.v[e])));
         yy.v[e] = __fsub_rn(__fsub_rn(yy.v[e], __fmul_rn(M.v[e], dyy.v[e])), __fmul_rn(L.v[e], __fadd_rn(dxx.v[e], dzz.v[e])));
         zz.v[e] = __fsub_rn(__fsub_rn(zz.v[e], __fmul_rn(M.v[e], dzz.v[e])), __fmul_rn(L.v[e], __fadd_rn(dyy.v[e], dxx.v[e])));
     }
-    if (fs && k0 == 0) zz.v[0] = -zz.v[1];                     // free_surface_mirror!: tauzz[1] = -tauzz[2]
+    if (fs && kg0 == 0) zz.v[0] = -zz.v[1];                     // free_surface_mirror!: tauzz[1] = -tauzz[2]
 
     // tauxz: z half, y inner, x half
     F4 dxz = diff4_zm(cvx, vxprev, g.dzI);      pml_apply_z(m5, a.ps[5], dxz);     // @d_zi(vx)
@@ -384,8 +387,8 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
     F4 dzy = diff4(cvz, vzmy, g.dyI);           pml_apply(m8, a.ps[8], dzy);       // @d_yi(vz)
 #pragma unroll
     for (int e = 0; e < VW; e++) {
-        const int k = k0 + e;
-        if (k >= 1 && k <= nz - 1) {
+        const int k = kg0 + e; const bool own = (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo);
+        if (own && k >= 1 && k <= nz - 1) {
             float n = __fsub_rn(xz.v[e], __fmul_rn(muxz.v[e], __fadd_rn(dxz.v[e], dzx.v[e])));
             if (fs && k == 1) n = 0.f;                             // free_surface!(tauxz)
             xz.v[e] = n;
@@ -393,7 +396,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
             if (fs && k == 1) n = 0.f;                             // free_surface!(tauyz)
             yz.v[e] = n;
         }
-        if (k >= 1 && k <= nz - 2) xy.v[e] = __fsub_rn(xy.v[e], __fmul_rn(muxy.v[e], __fadd_rn(dxy.v[e], dyx.v[e])));
+        if (own && k >= 1 && k <= nz - 2) xy.v[e] = __fsub_rn(xy.v[e], __fmul_rn(muxy.v[e], __fadd_rn(dxy.v[e], dyx.v[e])));
     }
 
     // ---- phase 3: stores -----------------------------------------------------------------------------

@@ -39,6 +39,7 @@ class GpiConfig(C.Structure):
         ("pml_faces", C.c_int32), ("rigid_faces", C.c_int32), ("stressfree_faces", C.c_int32),
         ("npw", C.c_int32), ("nshots", C.c_int32), ("store_boundary", C.c_int32),
         ("nsnaps", C.c_int32), ("snaps_field", C.c_int32), ("device", C.c_int32), ("shot_batch", C.c_int32),
+        ("slab_rank", C.c_int32), ("slab_nranks", C.c_int32),
         ("dt", C.c_double), ("dtI", C.c_double), ("d", C.c_double * 3), ("dI", C.c_double * 3),
     ]
 
@@ -59,7 +60,7 @@ def face_mask(faces) -> int:
 
 
 EXPORTS = [
-    "gpi_create", "gpi_destroy", "gpi_last_error", "gpi_abi_version", "gpi_set_medium", "gpi_get_medium",
+    "gpi_create", "gpi_destroy", "gpi_last_error", "gpi_abi_version", "gpi_set_medium", "gpi_set_medium_rows", "gpi_get_medium", "gpi_slab_range",
     "gpi_update_dmod", "gpi_set_pml", "gpi_set_sparse", "gpi_set_wavelets", "gpi_run", "gpi_get_records",
     "gpi_get_gradient", "gpi_get_snap", "gpi_set_snap_steps", "gpi_get_field", "gpi_set_field", "gpi_reset",
     "gpi_nccl_unique_id", "gpi_nccl_init", "gpi_allreduce_gradients", "gpi_records_device_ptr",
@@ -88,6 +89,8 @@ def load_library(path: str = LIB_PATH):
         "gpi_abi_version": ([], C.c_int),
         "gpi_set_medium": ([vp, C.c_int, fp], C.c_int),
         "gpi_get_medium": ([vp, C.c_int, fp], C.c_int),
+        "gpi_set_medium_rows": ([vp, C.c_int, fp, C.c_int, C.c_int], C.c_int),
+        "gpi_slab_range": ([vp, ip, ip], C.c_int),
         "gpi_update_dmod": ([vp], C.c_int),
         "gpi_set_pml": ([vp, C.c_int, fp, fp, fp], C.c_int),
         "gpi_set_sparse": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i64p, i64p, fp], C.c_int),
@@ -173,6 +176,17 @@ class Engine:
     def set_medium(self, name: str, a):
         a = _f32(a)
         self._ck(self.lib.gpi_set_medium(self.h, PARAM[name], _fp(a)))
+
+    def set_medium_rows(self, name: str, rows, k_first: int):
+        """rows: [nk, (ny,) nx] = global rows k_first .. k_first+nk-1 of the extended medium array."""
+        rows = np.asarray(rows, np.float32)
+        a = _f32(rows)
+        self._ck(self.lib.gpi_set_medium_rows(self.h, PARAM[name], _fp(a), int(k_first), int(rows.shape[0])))
+
+    def slab_range(self):
+        a, b = C.c_int32(), C.c_int32()
+        self._ck(self.lib.gpi_slab_range(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def get_medium(self, name: str):
         shp = self.field_shape("p" if self.cfg.physics == ACOUSTIC else "tauxx")

@@ -87,7 +87,10 @@ class PFdtd:
                  pml_faces: Sequence[str] = tuple(ALL_FACES), rigid_faces=None, rfields: Sequence[str] = ("vz",),
                  stressfree_faces: Sequence[str] = ("dummy",), tsnaps=None, snaps_field: Optional[str] = None,
                  verbose: bool = False, nworker: Optional[int] = None, rank: int = 0, device: int = -1,
-                 shot_batch: int = 0, upstream_3d_swap: bool = True):
+                 shot_batch: int = 0, upstream_3d_swap: bool = True, zslab=None):
+        """`zslab=(rank, nranks)`: z-slab domain decomposition of ONE experiment over `nranks` GPUs (new
+        capability): every rank builds the same experiment, owns one slab of the extended grid and
+        exchanges halo planes over NVLink inside `update!`; call `init_nccl` (or `dist.attach_nccl`) first."""
         N = medium.ndims
         npw = attrib_mod.npw
         assert (attrib_mod.physics == "elastic") == medium.elastic, "attrib_mod / medium mismatch"
@@ -158,6 +161,11 @@ class PFdtd:
         self.rank, self.nworker = rank, nworker
         self.local = self.sschunks[rank] if rank < nworker else range(0)
         self._nccl = False
+        self.zslab = None
+        if zslab is not None and zslab[1] > 1:
+            assert nworker == 1 and N == 3 and npw == 1, "z-slabs: one 3-D forward experiment shared by all ranks"
+            self.zslab = (int(zslab[0]), int(zslab[1]))
+            self.rank, self.local = self.zslab[0], self.sschunks[0]
 
         # ---- engine (replaces P_x_worker_x_pw / P_x_worker_x_pw_x_ss, fdtd.jl:340-528)
         cfg = E.GpiConfig()
@@ -172,6 +180,8 @@ class PFdtd:
         cfg.nsnaps = len(c.itsnaps)
         cfg.snaps_field = E.FIELD[c.snaps_field] if c.snaps_field else 0
         cfg.device, cfg.shot_batch = device, shot_batch
+        if self.zslab:
+            cfg.slab_rank, cfg.slab_nranks = self.zslab
         cfg.dt, cfg.dtI = float(c.fc["dt"]), float(c.fc["dtI"])
         names3 = ["z", "y", "x"]
         for q, d in enumerate(names3):

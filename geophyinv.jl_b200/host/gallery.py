@@ -108,7 +108,7 @@ def acou3d(n=48, nt=200, nr=16, dt=1e-3, fq=20.0, d=10.0, seed=7, sfield="p", rf
     src = {"z": [0.5 * L + 0.3 * d], "y": [0.45 * L + 0.2 * d], "x": [0.4 * L + 0.1 * d]}
     rec = {"z": np.full(nr, 0.3 * L + 0.4 * d), "y": np.linspace(0.2 * L, 0.8 * L, nr), "x": np.linspace(0.1 * L, 0.9 * L, nr)}
     ageom = [AGeomss(src, rec)]
-    wav = ricker(fq, tgrid, tpeak=min(1.5 / fq + 0.005, tgrid.last - 1.5 / fq)) * (1e6 if sfield.startswith("v") else 1.0)
+    wav = _ricker(fq, tgrid, 1.5 / fq + 0.005) * (1e6 if sfield.startswith("v") else 1.0)
     srcwav = make_srcwav(tgrid, ageom, [sfield], wav)
     return dict(medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=list(rfields))
 
@@ -127,7 +127,7 @@ def elastic2d(nz=120, nx=150, nt=400, nr=24, nss=2, dt=1e-3, fq=12.0, d=10.0, se
     for iss in range(nss):
         sx = (0.3 + 0.4 * iss / max(nss - 1, 1)) * Lx + 0.37 * d
         ageom.append(AGeomss({"z": [0.15 * Lz + 0.21 * d], "x": [sx]}, {"z": np.full(nr, 0.1 * Lz + 0.6 * d), "x": np.linspace(0.05 * Lx, 0.95 * Lx, nr)}))
-    wav = ricker(fq, tgrid, tpeak=min(1.5 / fq + 0.005, tgrid.last - 1.5 / fq)) * (1e6 if sfield.startswith("v") else 1.0)
+    wav = _ricker(fq, tgrid, 1.5 / fq + 0.005) * (1e6 if sfield.startswith("v") else 1.0)
     srcwav = make_srcwav(tgrid, ageom, [sfield], wav)
     kw = dict(medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=list(rfields),
               pml_faces=["zmin", "zmax", "xmin", "xmax"])

@@ -98,6 +98,8 @@ typedef struct gpi_config {
     int32_t snaps_field;      /* field id to snapshot                                  */
     int32_t device;           /* CUDA device ordinal; -1 = current device              */
     int32_t shot_batch;       /* shots propagated concurrently (0 = engine decides)    */
+    int32_t slab_rank;        /* z-slab domain decomposition (3-D, forward mode): this handle owns slab   */
+    int32_t slab_nranks;      /* slab_rank of slab_nranks (0 or 1 = whole grid on this GPU); n[] stays GLOBAL */
     double  dt, dtI;          /* fc[:dt], fc[:dtI]                                      */
     double  d[3];             /* fc[:dz], fc[:dy], fc[:dx]                              */
     double  dI[3];            /* fc[:dzI], fc[:dyI], fc[:dxI]                           */
@@ -127,6 +129,9 @@ int  gpi_abi_version(void);
 
 /* ---- medium: replaces copyto!(mod[name], exmedium, name) + update_dmod! (medium.jl:131-221) -- */
 int  gpi_set_medium(gpi_handle* h, int param_id, const float* ex_array /* [nz,(ny),nx] */);
+/* same, from a z-window of the global array: rows[nk, (ny), nx] holds global rows k_first .. k_first+nk-1
+ * (a slab handle only needs its own rows plus one halo row on each side; see gpi_slab_range) */
+int  gpi_set_medium_rows(gpi_handle* h, int param_id, const float* rows, int k_first, int nk);
 int  gpi_get_medium(gpi_handle* h, int param_id, float* out);
 int  gpi_update_dmod(gpi_handle* h);
 
@@ -162,6 +167,13 @@ int  gpi_reset(gpi_handle* h, int what);
 int  gpi_nccl_unique_id(void* id128 /* 128 bytes out */);
 int  gpi_nccl_init(gpi_handle* h, const void* id128, int rank, int nranks);
 int  gpi_allreduce_gradients(gpi_handle* h);
+/* z-slab domain decomposition (new capability, no reference counterpart: one 3-D shot spread over the GPUs of a
+ * box).  Create every handle with the same GLOBAL n[] and slab_rank / slab_nranks, call gpi_nccl_init with the
+ * slab rank, then use the ordinary calls: host arrays stay global-shaped (uploads take the rows the slab needs,
+ * downloads fill the rows it owns and zero the rest), gpi_run exchanges one halo plane of tauzz|p, tauxz, tauyz /
+ * vx, vy, vz per half step with the z neighbours and all-reduces the records at the end.
+ * gpi_slab_range: global unified z range [k_begin, k_end) owned by the handle (whole grid: 0 .. n[0]+1). */
+int  gpi_slab_range(gpi_handle* h, int32_t* k_begin, int32_t* k_end);
 
 /* ---- raw device access for zero-copy callers (CUDA.jl CuArray / torch tensors) ---------------- */
 int  gpi_records_device_ptr(gpi_handle* h, int ipw, int issp, int field_id, void** dptr, int64_t* nbytes);

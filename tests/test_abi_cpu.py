@@ -27,17 +27,17 @@ def lib(G):
 
 def test_every_declared_symbol_is_exported(G, lib):
     syms = header_symbols()
-    assert len(syms) >= 27
+    assert len(syms) >= 29
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/gpifdtd.h but not exported by libgpifdtd.so"
     assert sorted(G.engine.EXPORTS) == syms, "Python binding and header disagree on the export list"
 
 
 def test_struct_layouts_match_header(G):
-    # gpi_config: 18 int32 (n[3] counted thrice) + 8 doubles; gpi_timers: 9 doubles
-    assert C.sizeof(G.engine.GpiConfig) == 4 * 20 + 8 * 8
+    # gpi_config: 22 int32 (n[3] counted thrice) + 8 doubles; gpi_timers: 9 doubles
+    assert C.sizeof(G.engine.GpiConfig) == 4 * 22 + 8 * 8
     assert C.sizeof(G.engine.GpiTimers) == 8 * 9
-    assert G.engine.GpiConfig.dt.offset == 80
+    assert G.engine.GpiConfig.dt.offset == 88
 
 
 def test_field_shapes_follow_fields_jl(G, lib):
