@@ -269,19 +269,20 @@ def run_ours(args):
     B = max(1, min(nss, pa.engine.cfg.shot_batch or (16 if wl["ndims"] == 2 else 1)))
     peak, peak_kind = measured_peak()
     kern = {}
+    KV, KS = ("k_vel3v", "k_stress3v") if wl["ndims"] == 3 else ("k_vel", "k_stress")      # kernel names as ncu lists them
     if vel_n > 0 and str_n > 0:
-        kern["k_vel"] = {"ms": vel_ms / vel_n, "bytes": bv * B}
-        kern["k_stress"] = {"ms": str_ms / str_n, "bytes": bs * B}
+        kern[KV] = {"ms": vel_ms / vel_n, "bytes": bv * B}
+        kern[KS] = {"ms": str_ms / str_n, "bytes": bs * B}
     roof = None
     if kern:
         dom = max(kern, key=lambda k: kern[k]["ms"])
         ach = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9
-        step_share = (kern["k_vel"]["ms"] + kern["k_stress"]["ms"]) * nt * (nss / B) * args.steps / max(dev_ms, 1e-9) if world == 1 else None
+        step_share = (kern[KV]["ms"] + kern[KS]["ms"]) * nt * (nss / B) * args.steps / max(dev_ms, 1e-9) if world == 1 else None
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "peak_source": peak_kind, "traffic": None, "avg_launch_ms": kern[dom]["ms"],
                 "algorithmic_bytes_per_launch": kern[dom]["bytes"],
                 "other": {k: {"avg_launch_ms": v["ms"], "achieved": v["bytes"] / (v["ms"] * 1e-3) / 1e9, "frac": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak} for k, v in kern.items() if k != dom},
-                "both_kernels_frac": (bv + bs) * B / ((kern["k_vel"]["ms"] + kern["k_stress"]["ms"]) * 1e-3) / 1e9 / peak,
+                "both_kernels_frac": (bv + bs) * B / ((kern[KV]["ms"] + kern[KS]["ms"]) * 1e-3) / 1e9 / peak,
                 "stencil_share_of_step": step_share}
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):

@@ -1,0 +1,140 @@
+# GPIFdtdB200.jl -- the reference-side binding of libgpifdtd.so (include/gpifdtd.h).
+#
+# What a GeoPhyInv maintainer adds to `src/fdtd/` to swap the ParallelStencil kernels for the B200 engine.
+# Every function below REPLACES THE BODY of the reference function named in its comment with `ccall`s;
+# construction (`SeisForwExpt`), `Medium`, `AGeom`, `Srcs/Recs`, `update!` call order and the records layout
+# are untouched.  Julia is not installed in the build image, so this file is exercised only through its
+# line-by-line Python twin (geophyinv.jl_b200/engine.py + host/fdtd.py), which the test-suite runs.
+#
+# Conventions: Julia arrays are column-major [z,(y),x] Float32 -- exactly what the ABI takes; sparse matrices
+# are `SparseMatrixCSC{Float32,Int64}` whose `colptr/rowval/nzval` are passed as they are (1-based).
+module GPIFdtdB200
+
+using SparseArrays
+
+const LIB = get(ENV, "GPI_LIB", joinpath(@__DIR__, "..", "geophyinv.jl_b200", "libgpifdtd.so"))
+
+const ABI_VERSION = Int32(1)
+const FIELDS = [:p, :vx, :vy, :vz, :tauxx, :tauyy, :tauzz, :tauxy, :tauxz, :tauyz,
+    :dpdx, :dpdy, :dpdz, :dvxdx, :dvydy, :dvzdz, :dvxdy, :dvxdz, :dvydx, :dvydz, :dvzdx, :dvzdy,
+    :dtauxxdx, :dtauyydy, :dtauzzdz, :dtauxydx, :dtauxydy, :dtauxzdx, :dtauxzdz, :dtauyzdy, :dtauyzdz]
+field_id(f::Symbol) = Int32(findfirst(==(f), FIELDS) - 1)
+const PARAMS = Dict(:invK => 0, :rho => 1, :invlambda => 2, :invmu => 3)
+const FACES = Dict(:zmin => 1, :zmax => 2, :ymin => 4, :ymax => 8, :xmin => 16, :xmax => 32)
+face_mask(faces) = Int32(mapreduce(f -> get(FACES, f, 0), |, faces; init = 0))
+const MODES = Dict(:forward => 0, :forward_save => 1, :adjoint => 2)
+
+# mirrors `gpi_config` (include/gpifdtd.h); isbits, passed by reference
+struct GpiConfig
+    abi_version::Int32; ndims::Int32; physics::Int32; order::Int32
+    n::NTuple{3,Int32}; nt::Int32; npml::Int32; nbound::Int32
+    pml_faces::Int32; rigid_faces::Int32; stressfree_faces::Int32
+    npw::Int32; nshots::Int32; store_boundary::Int32
+    nsnaps::Int32; snaps_field::Int32; device::Int32; shot_batch::Int32
+    slab_rank::Int32; slab_nranks::Int32
+    dt::Float64; dtI::Float64; d::NTuple{3,Float64}; dI::NTuple{3,Float64}
+end
+
+mutable struct Engine
+    h::Ptr{Cvoid}
+    nt::Int
+end
+
+lasterror(h) = unsafe_string(ccall((:gpi_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
+check(e::Engine, rc) = rc == 0 || error("gpifdtd: ", lasterror(e.h))
+
+# ---- P_x_worker_x_pw(...) / P_x_worker_x_pw_x_ss(...)  (src/fdtd/fdtd.jl:340-528) --------------------
+# called once per worker from the `ddata` init closure (fdtd.jl:261-266) instead of allocating Data.Arrays
+function Engine(pac, sschunk; device = -1, shot_batch = 0, slab = (0, 1))
+    N = ndims(pac.medium)
+    n = length.(pac.exmedium.grid)
+    cfg = GpiConfig(ABI_VERSION, N, pac.attrib_mod isa FdtdElastic ? 1 : 0, _fd_order,
+        (n[1], N == 3 ? n[2] : 1, n[end]), pac.ic[:nt], _fd_npml, _fd_nbound,
+        face_mask(pac.pml_faces), face_mask(pac.rigid_faces), face_mask(pac.stressfree_faces),
+        pac.ic[:npw], length(sschunk), pac.attrib_mod.mode == :forward_save ? 1 : 0,   # fdtd.jl:445-455
+        length(pac.itsnaps), field_id(pac.snaps_field), device, shot_batch, slab[1], slab[2],
+        pac.fc[:dt], pac.fc[:dtI],
+        (pac.fc[:dz], N == 3 ? pac.fc[:dy] : 1.0, pac.fc[:dx]), (pac.fc[:dzI], N == 3 ? pac.fc[:dyI] : 1.0, pac.fc[:dxI]))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:gpi_create, LIB), Cint, (Ref{GpiConfig}, Ref{Ptr{Cvoid}}), cfg, out)
+    rc == 0 || error("gpifdtd: ", lasterror(C_NULL))
+    e = Engine(out[], pac.ic[:nt])
+    finalizer(x -> ccall((:gpi_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), e)
+    return e
+end
+
+# ---- update!(pac::P_common, medium)  (src/fdtd/medium.jl:131-140): copyto!(mod[name], ...) + update_dmod! ------
+function update_medium!(e::Engine, pac)
+    for name in names(pac.mod)[1]
+        a = Array{Float32}(pac.exmedium[name])                       # [nz,(ny),nx] on the extended grid
+        check(e, ccall((:gpi_set_medium, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}), e.h, PARAMS[name], a))
+    end
+    check(e, ccall((:gpi_update_dmod, LIB), Cint, (Ptr{Cvoid},), e.h))   # update_dmod! + store_invav*! (medium.jl:143-221)
+end
+
+# ---- update_pml!(pac)  (src/fdtd/cpml.jl:144-155): the host loop stays, the three copyto! become one call -------
+function set_pml!(e::Engine, dfield::Symbol, a::Vector{Float32}, b::Vector{Float32}, kI::Vector{Float32})
+    check(e, ccall((:gpi_set_pml, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
+        e.h, field_id(dfield), a, b, kI))
+end
+
+# ---- update!(pass, ipw, iss, ageomss, pac, ::Srcs / ::Recs)  (src/fdtd/ageom.jl:33-58) ---------------------------
+# `S` is the SparseMatrixCSC the reference builds with get_proj_matrix; kind 0 = spray, 1 = interpolation
+function set_sparse!(e::Engine, kind, ipw, issp, field::Symbol, S::SparseMatrixCSC{Float32,Int64})
+    check(e, ccall((:gpi_set_sparse, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{Float32}),
+        e.h, kind, ipw - 1, issp - 1, field_id(field), size(S, 2), S.colptr, S.rowval, S.nzval))
+end
+
+# ---- fill_wavelets!(ipw, iss, wavelets, srcwav, src_types)  (src/fdtd/source.jl:24-58) ---------------------------
+# w[nt, ns] already transformed by get_source (source.jl:3-19)
+function set_wavelets!(e::Engine, ipw, issp, field::Symbol, w::Matrix{Float32})
+    check(e, ccall((:gpi_set_wavelets, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ptr{Float32}),
+        e.h, ipw - 1, issp - 1, field_id(field), size(w, 2), w))
+end
+
+# ---- initialize!(pap), initialize_boundary!, reset_w2!  (src/fdtd/types.jl:41-113) -------------------------------
+reset!(e::Engine, what) = check(e, ccall((:gpi_reset, LIB), Cint, (Ptr{Cvoid}, Cint), e.h, what))
+
+# ---- mod_x_proc!(pac, pap, activepw, src_flags)  (src/fdtd/propagate.jl:138-261) ---------------------------------
+# the whole shot loop x time loop of this worker; blocking like the reference's remotecall_wait
+function mod_x_proc!(e::Engine, pac, activepw, src_flags)
+    am = mapreduce(p -> 1 << (p - 1), |, activepw; init = 0)
+    sm = mapreduce(i -> src_flags[i] ? 1 << (i - 1) : 0, |, eachindex(src_flags); init = 0)
+    check(e, ccall((:gpi_run, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint), e.h, MODES[pac.attrib_mod.mode], am, sm))
+end
+
+# ---- update_datamat!(rfield, ipw, pac, pap)  (src/fdtd/receiver.jl:17-34): ONE copy per (shot, field) -------------
+function update_datamat!(e::Engine, datamat, rfield::Symbol, ipw, issp, iss, nr)
+    buf = Matrix{Float32}(undef, e.nt, nr)
+    check(e, ccall((:gpi_get_records, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}), e.h, ipw - 1, issp - 1, field_id(rfield), buf))
+    datamat[:, 1:nr, iss] .= buf
+end
+
+# ---- sum_grads!(pac, pap)  (src/fdtd/gradient.jl:2-11): device stack + one NCCL all-reduce, then one copy ----------
+function sum_grads!(e::Engine, pac; allreduce = false)
+    allreduce && check(e, ccall((:gpi_allreduce_gradients, LIB), Cint, (Ptr{Cvoid},), e.h))
+    for name in names(pac.gradients)[1]
+        g = Array{Float32}(undef, size(pac.gradients[name]))
+        check(e, ccall((:gpi_get_gradient, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}), e.h, PARAMS[name], g))
+        pac.gradients[name] .= g
+    end
+end
+
+# ---- pa[:snaps, i]  (src/fdtd/getprop.jl:10-25) -------------------------------------------------------------------
+function get_snap(e::Engine, shape, ipw, issp, isnap)
+    out = Array{Float32}(undef, shape)
+    check(e, ccall((:gpi_get_snap, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}), e.h, ipw - 1, issp - 1, isnap - 1, out))
+    return out
+end
+
+# ---- one process per GPU: the ncclUniqueId travels over Julia Distributed (remotecall_fetch) -----------------------
+function nccl_unique_id()
+    id = zeros(UInt8, 128)
+    ccall((:gpi_nccl_unique_id, LIB), Cint, (Ptr{UInt8},), id) == 0 || error("ncclGetUniqueId failed")
+    return id
+end
+nccl_init!(e::Engine, id::Vector{UInt8}, rank, nranks) =
+    check(e, ccall((:gpi_nccl_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), e.h, id, rank, nranks))
+
+end # module
