@@ -148,7 +148,7 @@ def run_reference(args):
     nt_s = args.cpu_steps
     wl = workload(args.workload, nt_override=nt_s)
     po = O.OraclePFdtd(wl["attrib"](), **wl["kw"])
-    n_ex = [len(g) for g in po.c.exmedium.grid]
+    n_ex = [len(g) for g in po.c.exgrid]
     nss = len(po.local)
     cells = float(np.prod(n_ex)) * nt_s * nss
     for _ in range(args.warmup):
@@ -179,7 +179,7 @@ def cpu_baseline_sample(wl_name, nt_s=8):
     O.build()
     wl = workload(wl_name, nt_override=nt_s)
     po = O.OraclePFdtd(wl["attrib"](), **wl["kw"])
-    n_ex = [len(g) for g in po.c.exmedium.grid]
+    n_ex = [len(g) for g in po.c.exgrid]
     po.update()                                        # warm-up (page faults, thread pool)
     reps, sec = 0, 0.0
     while sec < 10.0 and reps < 6:
@@ -209,7 +209,7 @@ def run_ours(args):
     pa = G.SeisForwExpt(wl["attrib"](), **kw, device=local_rank)
     t_build = time.time() - t0
     c = pa.c
-    n_ex = [len(g) for g in c.exmedium.grid]
+    n_ex = [len(g) for g in c.exgrid]
     nt, nss = c.ic["nt"], len(pa.local)
     cells_per_step = float(np.prod(n_ex)) * nt * nss
 

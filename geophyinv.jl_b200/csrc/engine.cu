@@ -155,6 +155,7 @@ struct gpi_handle {
     std::vector<int32_t> itsnaps;
     PostDesc *post_v = nullptr, *post_s = nullptr, *h_post_v = nullptr, *h_post_s = nullptr;
     float* stage = nullptr;  size_t stage_floats = 0;       // pinned host staging
+    float* dscratch = nullptr;  size_t dscratch_floats = 0; // device scratch (raw interior medium before padding)
     gpi_timers timers{};
     std::vector<cudaEvent_t> evpool;  size_t evused = 0;   // sampled per-kernel timing (pairs)
     std::vector<int> evkind;                                // 0 = velocity kernel, 1 = stress kernel
@@ -357,6 +358,17 @@ int launch_boundary(gpi_handle* h, bool save, int f, float* field, float* store,
     else      k_boundary<0><<<grd, blk, 0, h->stream>>>(g, field, store, axis, lo, hi, nb, nk, nj, ni, k0, j0, i0);
     h->timers.launches += 1;
     return 0;
+}
+
+// Replicate-pad an un-extended medium array into the unified volume (media.jl:260-275: Pad(:replicate) on
+// the PML faces): node (k, j, i) of the extended grid reads the interior node clamped to the array.
+__global__ void k_pad_replicate(const Geom g, const float* __restrict__ src, float* __restrict__ dst,
+                                int mz, int my, int mx, int lz, int ly, int lx) {
+    const int kl = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, i = blockIdx.z;
+    const int k = kl + g.koff;
+    if (kl >= g.pz || k >= g.nz) return;
+    const int sz = min(max(k - lz, 0), mz - 1), sy = min(max(j - ly, 0), my - 1), sx = min(max(i - lx, 0), mx - 1);
+    dst[uidx(g, kl, j, i)] = src[(long long)sz + (long long)mz * ((long long)sy + (long long)my * sx)];
 }
 
 __global__ void k_negate_copy(float* __restrict__ dst, const float* __restrict__ src, long long n) {
@@ -598,6 +610,7 @@ extern "C" int gpi_destroy(gpi_handle* h) {
     if (h->h_post_v) cudaFreeHost(h->h_post_v);
     if (h->h_post_s) cudaFreeHost(h->h_post_s);
     if (h->stage) cudaFreeHost(h->stage);
+    cudaFree(h->dscratch);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (auto e : h->evpool) cudaEventDestroy(e);
@@ -629,6 +642,30 @@ extern "C" int gpi_set_medium_rows(gpi_handle* h, int p, const float* rows, int 
     if (p < 0 || p >= GPI_NPARAM || !h->mod[p]) FAIL(h, "medium parameter %d is not part of this physics", p);
     if (!rows || k_first < 0 || nk < 1 || k_first + nk > h->g.nz) FAIL(h, "bad medium row window [%d, %d)", k_first, k_first + nk);
     return upload_field(h, h->el ? GPI_TAUXX : GPI_P, rows, h->mod[p], k_first, nk);
+}
+// update!(pa, medium) without the host-side padarray: the interior array goes to the device as it is (one
+// contiguous H2D copy, 1/2.3 of the extended bytes at C3) and the replicate padding happens there.
+extern "C" int gpi_set_medium_interior(gpi_handle* h, int p, const float* a, const int32_t n_in[3], const int32_t lo[3]) {
+    GUARD(h);
+    if (p < 0 || p >= GPI_NPARAM || !h->mod[p]) FAIL(h, "medium parameter %d is not part of this physics", p);
+    if (!a || !n_in || !lo) FAIL(h, "null medium array");
+    const Geom& g = h->g;
+    const int mz = n_in[0], my = h->nd == 3 ? n_in[1] : 1, mx = n_in[2];
+    const int lz = lo[0], ly = h->nd == 3 ? lo[1] : 0, lx = lo[2];
+    if (mz < 1 || my < 1 || mx < 1 || lz < 0 || ly < 0 || lx < 0 || mz + lz > g.nz || my + ly > g.ny || mx + lx > g.nx)
+        FAIL(h, "interior medium [%d,%d,%d] + padding [%d,%d,%d] does not fit the extended grid [%d,%d,%d]", mz, my, mx, lz, ly, lx, g.nz, g.ny, g.nx);
+    const size_t nf = (size_t)mz * my * mx;
+    if (h->dscratch_floats < nf) {
+        cudaFree(h->dscratch); h->dscratch = nullptr; h->dscratch_floats = 0;
+        CU(h, cudaMalloc((void**)&h->dscratch, nf * sizeof(float)));
+        h->dscratch_floats = nf;
+    }
+    CU(h, cudaMemcpyAsync(h->dscratch, a, nf * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    dim3 blk(128), grd((g.pz + 127) / 128, g.ny, g.nx);
+    k_pad_replicate<<<grd, blk, 0, h->stream>>>(g, h->dscratch, h->mod[p], mz, my, mx, lz, ly, lx);
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));     // `a` is borrowed for the duration of the call only
+    return 0;
 }
 extern "C" int gpi_slab_range(gpi_handle* h, int32_t* k_begin, int32_t* k_end) {
     if (!h || !k_begin || !k_end) return 1;

@@ -80,6 +80,18 @@ __device__ __forceinline__ void st4(float* p, const F4& r) {
 #define GPI_PF "prefetch.global.L1 [%0];"
 #endif
 __device__ __forceinline__ void pf(const float* p) { asm volatile(GPI_PF :: "l"(p)); }
+// Plane-ahead L2 prefetch: blocks are scheduled plane by plane (blockIdx.y = x plane), so the lines this
+// thread's (k, j) group will need GPI_PF_AHEAD planes later can be requested from DRAM now, with no register
+// and no scoreboard cost; when the later block loads them they are L2 hits (~250 cycles instead of ~700).
+#ifndef GPI_PF_AHEAD
+#define GPI_PF_AHEAD 0
+#endif
+__device__ __forceinline__ void pf2(const float* p) {
+#ifdef GPI_PF_SPARSE
+    if ((threadIdx.x & 7) == 0)              // one request per 128-byte line (8 lanes x 16 B)
+#endif
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
 __device__ __forceinline__ float ld1(const float* p) {
     float r;
     asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p));
@@ -124,9 +136,20 @@ __device__ __forceinline__ F4 diff4_zp(const F4& c, float next, float sI) {
 //   pml_close   : store the memory variables
 struct Pml4 { float* mp; int s; F4 m; };
 
+// Diagnostic builds (tuning only, results are WRONG on purpose): GPI_EXP_NOPML skips every CPML term,
+// GPI_EXP_NONBR replaces the x / y neighbour loads by the centre line (L1 hits) -- they bound what the CPML
+// traffic and the neighbour requests cost.  build.sh never defines them.
+#ifdef GPI_EXP_NONBR
+#define GPI_NBR(x) 0
+#else
+#define GPI_NBR(x) (x)
+#endif
 template <int AXIS>   // 1 = y, 2 = x: slab index s uniform over the four cells (-1: not in a slab)
 __device__ __forceinline__ void pml_open(Pml4& q, const Geom& g, const PmlTerm& t, int s, int k0, int j, int i, int b) {
     q.s = s; q.mp = nullptr;
+#ifdef GPI_EXP_NOPML
+    return;
+#endif
     if (s < 0) return;
     long long mi;
     if (AXIS == 2) mi = (long long)k0 + (long long)g.pz * ((long long)j + (long long)g.ny1 * s);
@@ -139,6 +162,9 @@ __device__ __forceinline__ void pml_open_z(Pml4& q, const Geom& g, const PmlTerm
     const int npml = g.npml;
     const int k0 = k0l + g.koff;                 // global index of the first cell (koff % 4 == 0 keeps the alignment)
     int zi = -1;
+#ifdef GPI_EXP_NOPML
+    q.s = k0; q.mp = nullptr; return;
+#endif
     if ((g.pml & ZMIN) && k0 < s0 + npml) zi = k0;
     else if (g.pml & ZMAX) {
         const int kb = zslab_base(s0, len, npml);
@@ -200,12 +226,19 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
     const int kg0 = k0 + g.koff;                 // global z index of element 0
     const long long w = (long long)b * a.wstride;
     const long long c = uidx(g, k0, j, i) + w;
-    const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
+    const long long sy = GPI_NBR(g.pz), sx = GPI_NBR((long long)g.pz * g.ny1);
     const bool more = k0 + VW < g.pz;
     const bool hxmin = g.pml & XMIN, hxmax = g.pml & XMAX, hymin = g.pml & YMIN, hymax = g.pml & YMAX;
 
     float* vx = a.v[V_X] + c; float* vy = a.v[V_Y] + c; float* vz = a.v[V_Z] + c;
     pf(vx); pf(vy); pf(vz); pf(a.c[C_BX] + c - w); pf(a.c[C_BY] + c - w); pf(a.c[C_BZ] + c - w);
+    if (GPI_PF_AHEAD > 0 && i + GPI_PF_AHEAD <= nx - 2) {
+        const long long o = GPI_PF_AHEAD * sx;
+        pf2(vx + o); pf2(vy + o); pf2(vz + o);
+        pf2(a.c[C_BX] + c - w + o); pf2(a.c[C_BY] + c - w + o); pf2(a.c[C_BZ] + c - w + o);
+        pf2(a.tau[T_XX] + c + o);
+        if (EL) { pf2(a.tau[T_YY] + c + o); pf2(a.tau[T_ZZ] + c + o); pf2(a.tau[T_XY] + c + o + sx); pf2(a.tau[T_XZ] + c + o + sx); pf2(a.tau[T_YZ] + c + o); }
+    }
     F4 nvx = ld4(vx), nvy = ld4(vy), nvz = ld4(vz);
 
     if (!EL) {
@@ -316,12 +349,21 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
     const int kg0 = k0 + g.koff;                 // global z index of element 0
     const long long w = (long long)b * a.wstride;
     const long long c = uidx(g, k0, j, i) + w;
-    const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
+    const long long sy = GPI_NBR(g.pz), sx = GPI_NBR((long long)g.pz * g.ny1);
     const bool more = k0 + VW < g.pz;
     const bool hxmin = g.pml & XMIN, hxmax = g.pml & XMAX, hymin = g.pml & YMIN, hymax = g.pml & YMAX;
 
     // ---- phase 1: every load of the thread ---------------------------------------------------------
     const float* vx = a.v[V_X] + c; const float* vy = a.v[V_Y] + c; const float* vz = a.v[V_Z] + c;
+    if (GPI_PF_AHEAD > 0 && i + GPI_PF_AHEAD <= nx - 2) {
+        const long long o = GPI_PF_AHEAD * sx;
+        pf2(vx + o + sx); pf2(vy + o); pf2(vz + o);
+        pf2(a.tau[T_XX] + c + o); pf2(a.c[C_K] + c - w + o);
+        if (EL) {
+            pf2(a.tau[T_YY] + c + o); pf2(a.tau[T_ZZ] + c + o); pf2(a.tau[T_XY] + c + o); pf2(a.tau[T_XZ] + c + o); pf2(a.tau[T_YZ] + c + o);
+            pf2(a.c[C_L] + c - w + o); pf2(a.c[C_MUXZ] + c - w + o); pf2(a.c[C_MUXY] + c - w + o); pf2(a.c[C_MUYZ] + c - w + o);
+        }
+    }
     const F4 cvx = ld4(vx), cvy = ld4(vy), cvz = ld4(vz);
     const F4 vxpx = ld4(vx + sx), vypy = ld4(vy + sy);
     Pml4 m0, m1, m2;

@@ -60,7 +60,7 @@ def face_mask(faces) -> int:
 
 
 EXPORTS = [
-    "gpi_create", "gpi_destroy", "gpi_last_error", "gpi_abi_version", "gpi_set_medium", "gpi_set_medium_rows", "gpi_get_medium", "gpi_slab_range",
+    "gpi_create", "gpi_destroy", "gpi_last_error", "gpi_abi_version", "gpi_set_medium", "gpi_set_medium_rows", "gpi_set_medium_interior", "gpi_get_medium", "gpi_slab_range",
     "gpi_update_dmod", "gpi_set_pml", "gpi_set_sparse", "gpi_set_wavelets", "gpi_run", "gpi_get_records",
     "gpi_get_gradient", "gpi_get_snap", "gpi_set_snap_steps", "gpi_get_field", "gpi_set_field", "gpi_reset",
     "gpi_nccl_unique_id", "gpi_nccl_init", "gpi_allreduce_gradients", "gpi_records_device_ptr",
@@ -90,6 +90,7 @@ def load_library(path: str = LIB_PATH):
         "gpi_set_medium": ([vp, C.c_int, fp], C.c_int),
         "gpi_get_medium": ([vp, C.c_int, fp], C.c_int),
         "gpi_set_medium_rows": ([vp, C.c_int, fp, C.c_int, C.c_int], C.c_int),
+        "gpi_set_medium_interior": ([vp, C.c_int, fp, ip, ip], C.c_int),
         "gpi_slab_range": ([vp, ip, ip], C.c_int),
         "gpi_update_dmod": ([vp], C.c_int),
         "gpi_set_pml": ([vp, C.c_int, fp, fp, fp], C.c_int),
@@ -176,6 +177,15 @@ class Engine:
     def set_medium(self, name: str, a):
         a = _f32(a)
         self._ck(self.lib.gpi_set_medium(self.h, PARAM[name], _fp(a)))
+
+    def set_medium_interior(self, name: str, a, lo):
+        """`a`: un-extended array [mz,(my),mx]; `lo`: padding cells on the min face of each axis.  The
+        replicate padding (media.jl:260-275) runs on the device."""
+        a = np.asarray(a)
+        shp = a.shape if a.ndim == 3 else (a.shape[0], 1, a.shape[1])
+        lo3 = tuple(lo) if len(lo) == 3 else (lo[0], 0, lo[1])
+        flat = a.reshape(-1, order="F") if (a.dtype == np.float32 and a.flags.f_contiguous) else _f32(a)
+        self._ck(self.lib.gpi_set_medium_interior(self.h, PARAM[name], _fp(flat), (C.c_int32 * 3)(*shp), (C.c_int32 * 3)(*lo3)))
 
     def set_medium_rows(self, name: str, rows, k_first: int):
         """rows: [nk, (ny,) nx] = global rows k_first .. k_first+nk-1 of the extended medium array."""

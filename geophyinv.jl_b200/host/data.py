@@ -27,14 +27,15 @@ def _farr(a, dtype=F32):
 class Medium:
     """AcousticMedium (vp, rho) or ElasticMedium (vp, vs, rho) on `grid = [mz, (my,) mx]`."""
 
-    def __init__(self, grid: Sequence[StepRange], vp, rho, vs=None):
+    def __init__(self, grid: Sequence[StepRange], vp, rho, vs=None, validate: bool = True):
         self.grid = list(grid)
         shp = tuple(len(g) for g in self.grid)
         self.vp, self.rho = _farr(vp), _farr(rho)
         self.vs = None if vs is None else _farr(vs)
         for a in (self.vp, self.rho) + (() if self.vs is None else (self.vs,)):
             assert a.shape == shp, f"medium array shape {a.shape} != grid {shp}"
-            assert np.all(a >= 0), "negative medium parameters"
+            if validate:
+                assert np.all(a >= 0), "negative medium parameters"
 
     @property
     def elastic(self) -> bool:
@@ -77,7 +78,35 @@ class Medium:
         return [max(F32(0), F32(m.min() - F32(frac) * r)), F32(m.max() + F32(frac) * r)]
 
     def copy(self) -> "Medium":
-        return Medium(self.grid, self.vp.copy(), self.rho.copy(), None if self.vs is None else self.vs.copy())
+        return Medium(self.grid, self.vp.copy(order="F"), self.rho.copy(order="F"),
+                      None if self.vs is None else self.vs.copy(order="F"), validate=False)
+
+    def copy_from(self, other: "Medium") -> "Medium":
+        """`copyto!(pac.medium, medium)` (medium.jl:133): in place, no allocation."""
+        assert self.elastic == other.elastic and self.vp.shape == other.vp.shape, "medium shape / physics mismatch"
+        self.grid = list(other.grid)
+        np.copyto(self.vp, other.vp); np.copyto(self.rho, other.rho)
+        if self.elastic:
+            np.copyto(self.vs, other.vs)
+        return self
+
+    def derived_into(self, name: str, out: np.ndarray, tmp: np.ndarray) -> np.ndarray:
+        """`self[name]` for the engine's independent parameters, evaluated into preallocated Float32 buffers
+        with exactly the operations (and order) of `__getitem__`, so the values are bit-identical."""
+        vp, rho, vs = self.vp, self.rho, self.vs
+        if name == "rho":
+            return rho
+        if name == "invK" and not self.elastic or name == "invlambda" and not self.elastic:
+            np.multiply(vp, vp, out=out); np.multiply(out, rho, out=out)                       # K = vp*vp*rho
+        elif name == "invmu":
+            np.multiply(vs, vs, out=out); np.multiply(out, rho, out=out)                       # mu = vs*vs*rho
+        elif name == "invlambda":
+            np.multiply(vp, vp, out=out); np.multiply(vs, vs, out=tmp); np.multiply(tmp, F32(2), out=tmp)
+            np.subtract(out, tmp, out=out); np.multiply(out, rho, out=out)                     # (vp*vp - 2*(vs*vs))*rho
+        else:
+            raise KeyError(name)
+        np.divide(F32(1), out, out=out)
+        return out
 
 
 def _face_flags(faces, ndims):
@@ -108,7 +137,13 @@ def padarray(medium: Medium, npml: int = NPML, faces=("zmin", "zmax", "ymin", "y
             idx.append(np.clip(np.arange(-lo, n + hi), 0, n - 1))
         return _farr(a[np.ix_(*idx)])
 
-    return Medium(padmgrid(medium.grid, npml, faces), pad(medium.vp), pad(medium.rho), None if medium.vs is None else pad(medium.vs))
+    return Medium(padmgrid(medium.grid, npml, faces), pad(medium.vp), pad(medium.rho), None if medium.vs is None else pad(medium.vs), validate=False)
+
+
+def pad_widths(ndims: int, npml: int, faces):
+    """cells of replicate padding on the (min, max) face of each axis"""
+    fmin, fmax = _face_flags(faces, ndims)
+    return [npml if a else 0 for a in fmin], [npml if b else 0 for b in fmax]
 
 
 # --------------------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ import numpy as np
 from .. import engine as E
 from .cpml import pml_coefficients
 from .data import (AGeomss, Medium, Recs, Srcs, findfreq, get_adjoint_ageom, get_source, make_recs,
-                   padarray)
+                   pad_widths, padarray, padmgrid)
 from .grids import NBOUND, NPML, ORDER, StepRange, dfields_of, dim_names, field_shape, wavefields_of
 from .proj import get_proj_matrix
 
@@ -76,8 +76,26 @@ def view_inner(a: np.ndarray, npml: int, faces) -> np.ndarray:
 
 
 class PCommon:
-    """`P_common` (src/fdtd/types.jl:132-166): parameters shared by all supersources."""
-    pass
+    """`P_common` (src/fdtd/types.jl:132-166): parameters shared by all supersources.
+
+    `exmedium` (fdtd.jl:137) and `mod` (fdtd.jl:139-146) are materialised on the host only when something
+    reads them (reference values, CPML bounds, the model-vector path): `update!(pa, medium)` itself sends the
+    un-extended arrays to the engine, which pads on the device."""
+
+    _exmedium = None
+    _mod = None
+
+    @property
+    def exmedium(self) -> Medium:
+        if self._exmedium is None:
+            self._exmedium = padarray(self.medium, NPML, self.pml_faces)
+        return self._exmedium
+
+    @property
+    def mod(self):
+        if self._mod is None:
+            self._mod = {name: self.exmedium[name] for name in self.mparams}
+        return self._mod
 
 
 class PFdtd:
@@ -131,13 +149,13 @@ class PFdtd:
         c.stressfree_faces = [str(f).lstrip(":") for f in stressfree_faces]
         c.rfields, c.tgrid, c.verbose = rfields, tgrid, verbose
         c.upstream_3d_swap = upstream_3d_swap
-        c.exmedium = padarray(medium, NPML, pml_faces)                                # fdtd.jl:137
+        c.exgrid = padmgrid(medium.grid, NPML, pml_faces)                             # grid of exmedium (fdtd.jl:137)
         c.mparams = medium_parameters(attrib_mod)
         c.ref_mod = {name: c.exmedium.ref(name) for name in c.mparams}               # fdtd.jl:175
-        n = [len(g) for g in c.exmedium.grid]
+        n = [len(g) for g in c.exgrid]
         nt = len(tgrid)
         # fc / ic (fdtd.jl:301-332): Float32 copies of Float64 host values
-        ds = [g.step for g in c.exmedium.grid]
+        ds = [g.step for g in c.exgrid]
         dt = tgrid.step
         c.fc = {"dt": F32(dt), "dtI": F32(1.0 / dt)}
         for d, s in zip(dim_names(N), ds):
@@ -206,11 +224,14 @@ class PFdtd:
     # ---------------------------------------------------------------------------------------------
     def update_medium(self, medium: Medium):
         c = self.c
-        c.medium = medium.copy()
-        c.exmedium = padarray(c.medium, NPML, c.pml_faces)
-        c.mod = {name: c.exmedium[name] for name in c.mparams}
-        for name in c.mparams:
-            self.engine.set_medium(name, c.mod[name])
+        if medium is not c.medium:
+            c.medium.copy_from(medium)                                                 # copyto!(pac.medium, medium)
+        c._exmedium = c._mod = None                                                    # padarray! happens on the device
+        lo, _ = pad_widths(c.medium.ndims, NPML, c.pml_faces)
+        if getattr(self, "_dbuf", None) is None or self._dbuf[0].shape != c.medium.vp.shape:
+            self._dbuf = [np.empty(c.medium.vp.shape, F32, order="F") for _ in range(2)]
+        for name in c.mparams:                                                         # copyto!(mod[name], exmedium, name)
+            self.engine.set_medium_interior(name, c.medium.derived_into(name, self._dbuf[0], self._dbuf[1]), lo)
         self.engine.update_dmod()
 
     # update!(pa, m, mparams): log-parameterised model vector (medium.jl:31-52)
@@ -221,7 +242,7 @@ class PFdtd:
         for x, name in zip(chunks, mparams):
             inner = view_inner(c.mod[name], NPML, c.pml_faces)
             inner[...] = (np.exp(x.reshape(inner.shape, order="F")) * c.ref_mod[name]).astype(F32)
-            self.engine.set_medium(name, c.mod[name])
+            self.engine.set_medium(name, c.mod[name])        # the padding keeps its old values, as in the reference
         self.engine.update_dmod()
 
     def get_modelvector(self, mparams=None) -> np.ndarray:
@@ -249,12 +270,12 @@ class PFdtd:
                 if what in ("both", "srcs"):
                     pts = [[a.s[d][i] for d in names] for i in range(a.ns)]
                     for sf in c.srcwav[ipw][iss].fields:
-                        cp, rv, nz, _ = get_proj_matrix(sf, c.exmedium.grid, pts, c.upstream_3d_swap)
+                        cp, rv, nz, _ = get_proj_matrix(sf, c.exgrid, pts, c.upstream_3d_swap)
                         self.engine.set_sparse(E.SPRAY, ipw, issp, sf, cp, rv, nz)
                 if what in ("both", "recs"):
                     pts = [[a.r[d][i] for d in names] for i in range(a.nr)]
                     for rf in c.rfields:
-                        cp, rv, nz, _ = get_proj_matrix(rf, c.exmedium.grid, pts, c.upstream_3d_swap)
+                        cp, rv, nz, _ = get_proj_matrix(rf, c.exgrid, pts, c.upstream_3d_swap)
                         self.engine.set_sparse(E.INTERP, ipw, issp, rf, cp, rv, nz)
 
     # ---------------------------------------------------------------------------------------------
@@ -303,7 +324,7 @@ class PFdtd:
         N = c.medium.ndims
         vb = c.exmedium.bounds("vp")
         velavg = F32((vb[0] + vb[1]) / F32(2))
-        c.pml = pml_coefficients(dfields_of(c.attrib_mod.physics, N), c.exmedium.grid, c.medium.grid,
+        c.pml = pml_coefficients(dfields_of(c.attrib_mod.physics, N), c.exgrid, c.medium.grid,
                                  c.pml_faces, float(c.fc["dt"]), float(velavg), float(c.fc["freqpeak"]), NPML)
         for df, (a, b, kI) in c.pml.items():
             self.engine.set_pml(df, a, b, kI)
@@ -327,8 +348,10 @@ class PFdtd:
         upa = self.get_update_parameters() if upa is None else upa
         mode = c.attrib_mod.mode
         # initialize!(pa.c), initialize_boundary!, initialize!(localpart)  (propagate.jl:82-94, types.jl:41-176)
-        for g in c.gradients.values():
-            g[...] = 0
+        if getattr(self, "_grad_dirty", True):
+            for g in c.gradients.values():
+                g[...] = 0
+            self._grad_dirty = False
         for dat in c.data:
             for d in dat:
                 d.fill(0.0)
@@ -343,6 +366,7 @@ class PFdtd:
         if mode == "adjoint" and c.ic["npw"] == 2 and c.attrib_mod.physics == "acoustic":
             if self._nccl:
                 self.engine.allreduce_gradients()
+            self._grad_dirty = True
             for name in ("invK", "rho"):
                 c.gradients[name][...] = self.engine.get_gradient(name)
         # update_datamat! + update_data! (propagate.jl:119-133, receiver.jl:17-46)

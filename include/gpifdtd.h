@@ -132,6 +132,10 @@ int  gpi_set_medium(gpi_handle* h, int param_id, const float* ex_array /* [nz,(n
 /* same, from a z-window of the global array: rows[nk, (ny), nx] holds global rows k_first .. k_first+nk-1
  * (a slab handle only needs its own rows plus one halo row on each side; see gpi_slab_range) */
 int  gpi_set_medium_rows(gpi_handle* h, int param_id, const float* rows, int k_first, int nk);
+/* same, from the UN-extended array a[mz,(my),mx] (column-major): one contiguous H2D copy, then the
+ * replicate padding of padarray! (media.jl:260-275) runs on the device; lo[q] = cells of padding on the
+ * min face of axis q (npml on PML faces, else 0), n_in = (mz, my, mx) (my ignored in 2-D) */
+int  gpi_set_medium_interior(gpi_handle* h, int param_id, const float* a, const int32_t n_in[3], const int32_t lo[3]);
 int  gpi_get_medium(gpi_handle* h, int param_id, float* out);
 int  gpi_update_dmod(gpi_handle* h);
 

@@ -92,6 +92,13 @@ class OracleEngine:
     def set_medium(self, name, a):
         a = self._a(a); self._ck(self.lib.orc_set_medium(self.h, E.PARAM[name], self._p(a)))
 
+    def set_medium_interior(self, name, a, lo):
+        """Host-side replicate padding (media.jl:260-275) -- the independent check of the engine's device-side pad."""
+        a = np.asarray(a)
+        n = [self.cfg.n[0], self.cfg.n[2]] if a.ndim == 2 else list(self.cfg.n)
+        idx = [np.clip(np.arange(-l, nn - l), 0, m - 1) for l, nn, m in zip(lo, n, a.shape)]
+        self.set_medium(name, a[np.ix_(*idx)])
+
     def get_medium(self, name):
         shp = self.field_shape("p" if self.cfg.physics == E.ACOUSTIC else "tauxx")
         out = np.empty(int(np.prod(shp)), self.dtype)

@@ -178,6 +178,28 @@ def test_dmod_matches_oracle(G, O):
         assert np.array_equal(pg.engine.get_medium(name), po.engine.get_medium(name))
 
 
+def test_medium_padded_on_device(G, O):
+    """update!(pa, medium) sends the un-extended arrays; the replicate padding of padarray! (media.jl:260-275)
+    runs on the device.  Compare with the host-side padarray for full and partial PML faces, 2-D and 3-D."""
+    from geophyinv_jl_b200.host import gallery
+    cases = [(G.FdtdElastic, gallery.c3_elastic3d(n=22, nt=4, nr=4, fq=60.0, stressfree=True)),
+             (G.FdtdElastic, gallery.c3_elastic3d(n=21, nt=4, nr=4, fq=60.0)),
+             (G.FdtdAcoustic, gallery.c1_acou2d_homo(nz=37, nx=52, nt=4, nr=4)),
+             (G.FdtdElastic, gallery.elastic2d(nz=33, nx=47, nt=4, stressfree=True))]
+    for cls, kw in cases:
+        pg = G.SeisForwExpt(cls(), **kw)
+        ex = G.padarray(kw["medium"], G.NPML, pg.c.pml_faces)
+        for name in pg.c.mparams:
+            assert np.array_equal(pg.engine.get_medium(name), ex[name]), name
+        # a second update with a different medium overwrites every padded cell
+        m2 = kw["medium"].copy(); m2.vp *= np.float32(1.01); m2.rho *= np.float32(0.99)
+        pg.update_medium(m2)
+        ex2 = G.padarray(m2, G.NPML, pg.c.pml_faces)
+        for name in pg.c.mparams:
+            assert np.array_equal(pg.engine.get_medium(name), ex2[name]), name
+        assert np.array_equal(pg.c.mod[pg.c.mparams[0]], ex2[pg.c.mparams[0]])
+
+
 def test_fwi_gradient_acoustic2d(G, O):
     """BASELINE config 4 down-sized: forward_save + adjoint + imaging; gradients w.r.t. invK and rho."""
     from geophyinv_jl_b200.host import gallery
