@@ -269,7 +269,11 @@ def run_ours(args):
     B = max(1, min(nss, pa.engine.cfg.shot_batch or (16 if wl["ndims"] == 2 else 1)))
     peak, peak_kind = measured_peak()
     kern = {}
-    KV, KS = ("k_vel3v", "k_stress3v") if wl["ndims"] == 3 else ("k_vel", "k_stress")      # kernel names as ncu lists them
+    # kernel names as ncu lists them: 3-D elastic runs the TMA-pipelined k_step3t<0|1> unless GPI_TMA3=0
+    if wl["ndims"] == 3 and wl["elastic"] and os.environ.get("GPI_TMA3", "1") != "0":
+        KV, KS = "k_step3t<0> (velocity)", "k_step3t<1> (stress)"
+    else:
+        KV, KS = ("k_vel3v", "k_stress3v") if wl["ndims"] == 3 else ("k_vel", "k_stress")
     if vel_n > 0 and str_n > 0:
         kern[KV] = {"ms": vel_ms / vel_n, "bytes": bv * B}
         kern[KS] = {"ms": str_ms / str_n, "bytes": bs * B}

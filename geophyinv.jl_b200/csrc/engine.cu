@@ -5,6 +5,7 @@
 // unified-box layout described in kernels.cuh, and drives the time loop of mod_x_proc!
 // (propagate.jl:138-261) as two fused stencil launches plus one small source/receiver launch per
 // half step.  There is no CPU fallback: every entry point needs a CUDA device.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <algorithm>
@@ -162,6 +163,9 @@ struct gpi_handle {
     int sample_every = 16;
     // tuning
     dim3 blk3{64, 2, 2}, blk2{128, 2, 1};
+    bool tma3 = false; int num_sms = 148;  int tma3_ctas = 0;
+    struct TmaSet { const float* key = nullptr; t3::Maps m[2]; } tmaps[2];   // TMA descriptors per pw: [0] velocity, [1] stress kernel
+    void* encode_tiled = nullptr;                                            // cuTensorMapEncodeTiled (driver entry point)   // 3-D elastic: TMA-pipelined persistent kernels (kernels3t.cuh); GPI_TMA3=0 selects k_*3v
     int blkv = GPI_VEC_THREADS;  bool vec3 = true;      // 3-D: float4-per-thread kernels (kernels3d.cuh); GPI_SCALAR3D=1 selects the scalar ones
     // nccl
     NcclApi nccl;  void* comm = nullptr;  int rank = 0, nranks = 1;
@@ -290,10 +294,67 @@ void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch) {
     a.nbatch = nbatch;
 }
 
+// TMA descriptors of the operand boxes of kernels3t.cuh: every array is a rank-3 tensor (z, y, x) = (pz, ny1, nx1)
+// with the unified-box strides; a box is (ZC + 8) x rows x 1; out-of-range coordinates read zeros.
+int build_tmaps(gpi_handle* h, const StepArgs& a, int kind, t3::Maps& out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    const Geom& g = h->g;
+    const int nbox = kind == 0 ? (int)t3::V_NBOX : (int)t3::S_NBOX;
+    memset(&out, 0, sizeof out);
+    for (int b = 0; b < nbox; b++) {
+        const t3::BoxSpec bs = t3::box_spec(kind, b);
+        const float* base = bs.arr < 6 ? a.tau[bs.arr] : bs.arr < 9 ? a.v[bs.arr - 6] : a.c[bs.arr - 9];
+        if (!base) FAIL(h, "TMA descriptor: operand %d of kernel %d is not allocated", bs.arr, kind);
+        cuuint64_t dims[3] = {(cuuint64_t)g.pz, (cuuint64_t)g.ny1, (cuuint64_t)g.nx1};
+        cuuint64_t strides[2] = {(cuuint64_t)g.pz * 4, (cuuint64_t)g.pz * g.ny1 * 4};
+        cuuint32_t box[3] = {(cuuint32_t)t3::PITCH, (cuuint32_t)bs.rows, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult rc = ((EncodeFn)h->encode_tiled)(reinterpret_cast<CUtensorMap*>(out.m[b]), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base,
+                                                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) FAIL(h, "cuTensorMapEncodeTiled failed (%d) for box %d of kernel %d", (int)rc, b, kind);
+    }
+    return 0;
+}
+template <int KIND>
+int launch_step3t(gpi_handle* h, const StepArgs& a) {
+    const Geom& g = h->g;
+    // descriptors are cached per wavefield set (the pointers of a pw never change after gpi_create)
+    gpi_handle::TmaSet* set = nullptr;
+    for (auto& ts : h->tmaps) if (ts.key == a.v[0]) set = &ts;
+    if (!set) {
+        set = h->tmaps[0].key ? &h->tmaps[1] : &h->tmaps[0];
+        if (build_tmaps(h, a, 0, set->m[0]) || build_tmaps(h, a, 1, set->m[1])) return 1;
+        set->key = a.v[0];
+    }
+    t3::Sched sc{};
+    if (KIND == 0) {
+        sc.ilo = 2; sc.ihi = g.nx - 2; sc.jlo = 2; sc.jhi = g.ny - 2;
+        sc.nsp = 4; sc.sp[0] = 0; sc.sp[1] = 1; sc.sp[2] = g.nx - 1; sc.sp[3] = g.nx;
+        sc.nsr = 4; sc.sr[0] = 0; sc.sr[1] = 1; sc.sr[2] = g.ny - 1; sc.sr[3] = g.ny;
+    } else {
+        sc.ilo = 1; sc.ihi = g.nx - 2; sc.jlo = 1; sc.jhi = g.ny - 2;
+        sc.nsp = 3; sc.sp[0] = 0; sc.sp[1] = g.nx - 1; sc.sp[2] = g.nx;
+        sc.nsr = 3; sc.sr[0] = 0; sc.sr[1] = g.ny - 1; sc.sr[2] = g.ny;
+    }
+    sc.njb = (sc.jhi - sc.jlo + 1 + t3::R - 1) / t3::R;
+    sc.nzc = (g.pz + t3::ZC - 1) / t3::ZC;
+    sc.ntiles = (sc.ihi - sc.ilo + 1) * sc.njb * sc.nzc;
+    const int nctas = std::max(1, std::min(sc.ntiles, h->tma3_ctas > 0 ? h->tma3_ctas : T3_MINB * h->num_sms));
+    const size_t smem = t3::smem_bytes(KIND == 0 ? (int)t3::V_FLOATS : (int)t3::S_FLOATS);
+    t3::k_step3t<KIND><<<nctas, t3::NTHREADS, smem, h->stream>>>(g, a, sc, set->m[KIND]);
+    return 0;
+}
 template <int EL>
 void launch_step_kernels3v(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
     const Geom& g = h->g;
-    const int ngroups = (g.pz / VW) * g.ny1;
+    if (EL && h->tma3 && nbatch == 1 && g.nx >= 8 && g.ny >= 8) {
+        if ((vel ? launch_step3t<0>(h, a) : launch_step3t<1>(h, a)) == 0) return;
+        h->tma3 = false;                        // descriptor creation failed: fall back to the register-staged kernels
+    }
+    const int ngroups = vec3_threads(g.pz, g.ny1);
     dim3 blk(h->blkv), grd((ngroups + h->blkv - 1) / h->blkv, g.nx1, nbatch);
     if (vel) k_vel3v<EL><<<grd, blk, 0, h->stream>>>(g, a);
     else     k_stress3v<EL><<<grd, blk, 0, h->stream>>>(g, a);
@@ -580,6 +641,18 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (const char* e = getenv("GPI_SAMPLE_EVERY")) h->sample_every = atoi(e);
     if (const char* e = getenv("GPI_BLOCK3")) { int a, b, c3; if (sscanf(e, "%d,%d,%d", &a, &b, &c3) == 3 && a * b * c3 <= 256) h->blk3 = dim3(a, b, c3); }
     if (const char* e = getenv("GPI_SCALAR3D")) h->vec3 = atoi(e) == 0;
+    if (const char* e = getenv("GPI_TMA3")) h->tma3 = atoi(e) != 0;
+    if (const char* e = getenv("GPI_TMA3_CTAS")) h->tma3_ctas = atoi(e);
+    if (h->nd == 3 && h->el) {
+        cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
+        cudaError_t e0 = cudaFuncSetAttribute(t3::k_step3t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::smem_bytes(t3::V_FLOATS));
+        cudaError_t e1 = cudaFuncSetAttribute(t3::k_step3t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::smem_bytes(t3::S_FLOATS));
+        cudaFuncSetAttribute(t3::k_step3t<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(t3::k_step3t<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e2 = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &h->encode_tiled, cudaEnableDefault, &qres);
+        if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess || !h->encode_tiled) { h->tma3 = false; cudaGetLastError(); }
+    }
     if (const char* e = getenv("GPI_BLOCKV")) { int a = atoi(e); if (a >= 32 && a <= GPI_VEC_THREADS && a % 32 == 0) h->blkv = a; }
     if (const char* e = getenv("GPI_BLOCK2")) { int a, b; if (sscanf(e, "%d,%d", &a, &b) == 2 && a * b <= 256) h->blk2 = dim3(a, b, 1); }
     if (create_impl(h)) { g_create_err = "gpi_create: " + h->err; gpi_destroy(h); return 1; }

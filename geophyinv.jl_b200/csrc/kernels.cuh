@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(256) k_stress(const Geom g, const StepArgs a) 
 }
 
 #include "kernels3d.cuh"
+#include "kernels3t.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // k_dmod: update_dmod! + store_invav*! (medium.jl:143-221).  The reference's `dt / @av_*(b)` and

@@ -144,18 +144,26 @@ struct Pml4 { float* mp; int s; F4 m; };
 #else
 #define GPI_NBR(x) (x)
 #endif
+#ifndef GPI_EXP_NOPML_AXES
+#define GPI_EXP_NOPML_AXES 0          // diagnostic: bit q set = skip the CPML terms of axis q (0 z, 1 y, 2 x)
+#endif
 template <int AXIS>   // 1 = y, 2 = x: slab index s uniform over the four cells (-1: not in a slab)
 __device__ __forceinline__ void pml_open(Pml4& q, const Geom& g, const PmlTerm& t, int s, int k0, int j, int i, int b) {
     q.s = s; q.mp = nullptr;
 #ifdef GPI_EXP_NOPML
     return;
 #endif
+    if ((GPI_EXP_NOPML_AXES >> AXIS) & 1) return;
     if (s < 0) return;
     long long mi;
     if (AXIS == 2) mi = (long long)k0 + (long long)g.pz * ((long long)j + (long long)g.ny1 * s);
     else           mi = (long long)k0 + (long long)g.pz * ((long long)s + 2LL * g.npml * i);
     q.mp = t.mem + (long long)b * t.bstride + mi;
+#ifdef GPI_EXP_PMLNOMEM
+    q.m = F4{};
+#else
     q.m = ld4(q.mp);
+#endif
 }
 // z terms: float4-aligned memory rows (cpml<> in kernels.cuh); s holds k0 for the table look-up
 __device__ __forceinline__ void pml_open_z(Pml4& q, const Geom& g, const PmlTerm& t, int s0, int len, int k0l, int j, int i, int b) {
@@ -165,6 +173,7 @@ __device__ __forceinline__ void pml_open_z(Pml4& q, const Geom& g, const PmlTerm
 #ifdef GPI_EXP_NOPML
     q.s = k0; q.mp = nullptr; return;
 #endif
+    if (GPI_EXP_NOPML_AXES & 1) { q.s = k0; q.mp = nullptr; return; }
     if ((g.pml & ZMIN) && k0 < s0 + npml) zi = k0;
     else if (g.pml & ZMAX) {
         const int kb = zslab_base(s0, len, npml);
@@ -173,9 +182,16 @@ __device__ __forceinline__ void pml_open_z(Pml4& q, const Geom& g, const PmlTerm
     q.s = k0; q.mp = nullptr;
     if (zi < 0) return;
     q.mp = t.mem + (long long)b * t.bstride + (long long)zi + (long long)g.pzm * ((long long)j + (long long)g.ny1 * i);
+#ifdef GPI_EXP_PMLNOMEM
+    q.m = F4{};
+#else
     q.m = ld4(q.mp);
+#endif
 }
 __device__ __forceinline__ void pml_apply(Pml4& q, const PmlTerm& t, F4& d) {
+#ifdef GPI_EXP_PMLNOARITH
+    return;
+#endif
     if (!q.mp) return;
     const float a = __ldg(t.a + q.s), bb = __ldg(t.b + q.s), kI = __ldg(t.kI + q.s);
 #pragma unroll
@@ -185,6 +201,9 @@ __device__ __forceinline__ void pml_apply(Pml4& q, const PmlTerm& t, F4& d) {
     }
 }
 __device__ __forceinline__ void pml_apply_z(Pml4& q, const PmlTerm& t, F4& d) {
+#ifdef GPI_EXP_PMLNOARITH
+    return;
+#endif
     if (!q.mp) return;
     const F4 a = ldg4(t.a + q.s), bb = ldg4(t.b + q.s), kI = ldg4(t.kI + q.s);
 #pragma unroll
@@ -193,17 +212,45 @@ __device__ __forceinline__ void pml_apply_z(Pml4& q, const PmlTerm& t, F4& d) {
         d.v[e] = __fadd_rn(__fmul_rn(d.v[e], kI.v[e]), q.m.v[e]);
     }
 }
-__device__ __forceinline__ void pml_close(const Pml4& q) { if (q.mp) st4(q.mp, q.m); }
+__device__ __forceinline__ void pml_close(const Pml4& q) {
+#ifndef GPI_EXP_PMLNOMEM
+    if (q.mp) st4(q.mp, q.m);
+#endif
+}
 
-// thread -> (group of four z cells, row j); plane i = blockIdx.y, batch slot = blockIdx.z
+// thread -> (group of four z cells, row j); plane i = blockIdx.y, batch slot = blockIdx.z.
+// GPI_VEC_ROWS = 1: the (z, y) plane is linearised group by group (a warp = 128 consecutive z cells of a row,
+// straddling rows).  GPI_VEC_ROWS = R (4 or 8): a warp = R rows x (32/R) groups, i.e. one whole 128-byte (R = 4)
+// or 64-byte (R = 8) segment per row.  Every access is still a full-line request, but a warp now sits in ONE z
+// chunk: only the warps of the first / last chunks of a row contain z-slab cells, so the divergent z-CPML code is
+// executed by ~4/11 of the warps instead of ~3/4 (and without divergence in the chunks that lie inside the slab).
+#ifndef GPI_VEC_ROWS
+#define GPI_VEC_ROWS 1
+#endif
 struct Vec3Idx { int k0, j, i, b; bool valid; };
+__host__ __device__ inline int vec3_threads(int pz, int ny1) {
+    const int nq = pz / VW;
+    if (GPI_VEC_ROWS == 1) return nq * ny1;
+    const int lpr = 32 / GPI_VEC_ROWS;                       // lanes (groups) per row inside a warp
+    return (nq / lpr) * ((ny1 + GPI_VEC_ROWS - 1) / GPI_VEC_ROWS) * 32;
+}
 __device__ __forceinline__ Vec3Idx vec3_index(const Geom& g) {
     Vec3Idx q;
     const int nq = g.pz / VW;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    q.valid = gid < nq * g.ny1;
-    q.j = gid / nq;
-    q.k0 = (gid - q.j * nq) * VW;
+    if (GPI_VEC_ROWS == 1) {
+        q.valid = gid < nq * g.ny1;
+        q.j = gid / nq;
+        q.k0 = (gid - q.j * nq) * VW;
+    } else {
+        constexpr int R = GPI_VEC_ROWS, LPR = 32 / R;
+        const int nzc = nq / LPR;                            // z chunks per row (pz is a multiple of 32 floats)
+        const int w = gid >> 5, l = gid & 31;
+        const int jb = w / nzc, zc = w - jb * nzc;
+        q.j = jb * R + l / LPR;
+        q.k0 = (zc * LPR + (l % LPR)) * VW;
+        q.valid = q.j < g.ny1;
+    }
     q.i = blockIdx.y; q.b = blockIdx.z;
     return q;
 }

@@ -32,7 +32,7 @@ def c1_acou2d_homo(nz=201, nx=201, nt=1000, nr=64, sfield="p", rfields=("p",), n
     medium = Medium.homogeneous(grid, 2500.0, 2500.0)
     tgrid = StepRange(0.0, dt, nt)
     ageom = ageom_xwell(grid, nss=nss, nr=nr)
-    wav = ricker(fq, tgrid, tpeak=max(0.15, 1.5 / fq))
+    wav = _ricker(fq, tgrid, max(0.15, 1.5 / fq))
     if sfield != "p":
         wav = wav * 1e6                                   # fdtd/gallery.jl:12
     srcwav = make_srcwav(tgrid, ageom, [sfield], wav)

@@ -64,12 +64,33 @@ function Engine(pac, sschunk; device = -1, shot_batch = 0, slab = (0, 1))
 end
 
 # ---- update!(pac::P_common, medium)  (src/fdtd/medium.jl:131-140): copyto!(mod[name], ...) + update_dmod! ------
+# `padarray!(pac.exmedium, ...)` (medium.jl:134, media.jl:260-275) is not needed for the upload: the un-extended
+# array goes to the device and the engine replicates it into the PML there (gpi_set_medium_interior).
 function update_medium!(e::Engine, pac)
+    N = ndims(pac.medium)
+    dims = N == 3 ? (:z, :y, :x) : (:z, :x)
+    lo3 = Int32[0, 0, 0]; n3 = Int32[1, 1, 1]
+    for (q, d) in enumerate(dims)
+        slot = N == 3 ? q : (q == 1 ? 1 : 3)
+        lo3[slot] = Symbol(d, :min) in pac.pml_faces ? _fd_npextend : 0
+        n3[slot] = length(pac.medium.grid[q])
+    end
     for name in names(pac.mod)[1]
-        a = Array{Float32}(pac.exmedium[name])                       # [nz,(ny),nx] on the extended grid
-        check(e, ccall((:gpi_set_medium, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}), e.h, PARAMS[name], a))
+        a = Array{Float32}(pac.medium[name])                         # [mz,(my),mx], no padding
+        check(e, ccall((:gpi_set_medium_interior, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Ptr{Int32}, Ptr{Int32}),
+            e.h, PARAMS[name], a, n3, lo3))
     end
     check(e, ccall((:gpi_update_dmod, LIB), Cint, (Ptr{Cvoid},), e.h))   # update_dmod! + store_invav*! (medium.jl:143-221)
+end
+
+# model-vector path (medium.jl:31-52): only the interior view of `mod` changes and the padding keeps its old
+# values, so the extended array is uploaded as it is
+function update_mod!(e::Engine, pac)
+    for name in names(pac.mod)[1]
+        a = Array{Float32}(pac.mod[name])                            # [nz,(ny),nx] on the extended grid
+        check(e, ccall((:gpi_set_medium, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}), e.h, PARAMS[name], a))
+    end
+    check(e, ccall((:gpi_update_dmod, LIB), Cint, (Ptr{Cvoid},), e.h))
 end
 
 # ---- update_pml!(pac)  (src/fdtd/cpml.jl:144-155): the host loop stays, the three copyto! become one call -------
