@@ -136,6 +136,7 @@ struct gpi_handle {
     int device;
     cudaStream_t stream = nullptr;  bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t side = nullptr;  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // the shell kernels of kernels3t.cuh run beside the tile kernels
     std::string err;
 
     // wavefields: W[b][pw][slot][vol]; TP same shape (adjoint only)
@@ -163,9 +164,10 @@ struct gpi_handle {
     int sample_every = 16;
     // tuning
     dim3 blk3{64, 2, 2}, blk2{128, 2, 1};
-    bool tma3 = false; int num_sms = 148;  int tma3_ctas = 0;
-    struct TmaSet { const float* key = nullptr; t3::Maps m[2]; } tmaps[2];   // TMA descriptors per pw: [0] velocity, [1] stress kernel
+    bool tma3 = true;  int num_sms = 148;  int tma3_ctas = 0;
+    struct TmaSet { const float* key = nullptr; t3::Maps* d[2] = {nullptr, nullptr}; } tmaps[2];   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
     void* encode_tiled = nullptr;                                            // cuTensorMapEncodeTiled (driver entry point)   // 3-D elastic: TMA-pipelined persistent kernels (kernels3t.cuh); GPI_TMA3=0 selects k_*3v
+    bool vec2 = true;                                   // 2-D: float4-per-thread kernels (kernels2v.cuh); GPI_SCALAR2D=1 selects the scalar ones
     int blkv = GPI_VEC_THREADS;  bool vec3 = true;      // 3-D: float4-per-thread kernels (kernels3d.cuh); GPI_SCALAR3D=1 selects the scalar ones
     // nccl
     NcclApi nccl;  void* comm = nullptr;  int rank = 0, nranks = 1;
@@ -294,28 +296,51 @@ void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch) {
     a.nbatch = nbatch;
 }
 
-// TMA descriptors of the operand boxes of kernels3t.cuh: every array is a rank-3 tensor (z, y, x) = (pz, ny1, nx1)
-// with the unified-box strides; a box is (ZC + 8) x rows x 1; out-of-range coordinates read zeros.
-int build_tmaps(gpi_handle* h, const StepArgs& a, int kind, t3::Maps& out) {
+// TMA descriptors of the operand boxes of kernels3t.cuh.  Every field / coefficient array is a rank-3 tensor
+// (z, y, x) = (pz, ny1, nx1) with the unified-box strides, box = (128 or 136) x rows x 1; CPML memory arrays are
+// (pz, ny1, 2 npml) for x terms, (pz, 2 npml, nx1) for y terms, (pzm, ny1, nx1) for z terms.  Out-of-range
+// coordinates read zeros.
+int encode_map(gpi_handle* h, void* out, const float* base, const cuuint64_t dims[3], cuuint32_t b0, cuuint32_t b1) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    cuuint64_t strides[2] = {dims[0] * 4, dims[0] * dims[1] * 4};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = ((EncodeFn)h->encode_tiled)(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base,
+                                              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) FAIL(h, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+    return 0;
+}
+int build_tmaps(gpi_handle* h, const StepArgs& a, int kind, t3::Maps** dout) {
     const Geom& g = h->g;
     const int nbox = kind == 0 ? (int)t3::V_NBOX : (int)t3::S_NBOX;
-    memset(&out, 0, sizeof out);
+    t3::Maps hm;
+    memset(&hm, 0, sizeof hm);
+    const cuuint64_t fdims[3] = {(cuuint64_t)g.pz, (cuuint64_t)g.ny1, (cuuint64_t)g.nx1};
     for (int b = 0; b < nbox; b++) {
         const t3::BoxSpec bs = t3::box_spec(kind, b);
         const float* base = bs.arr < 6 ? a.tau[bs.arr] : bs.arr < 9 ? a.v[bs.arr - 6] : a.c[bs.arr - 9];
         if (!base) FAIL(h, "TMA descriptor: operand %d of kernel %d is not allocated", bs.arr, kind);
-        cuuint64_t dims[3] = {(cuuint64_t)g.pz, (cuuint64_t)g.ny1, (cuuint64_t)g.nx1};
-        cuuint64_t strides[2] = {(cuuint64_t)g.pz * 4, (cuuint64_t)g.pz * g.ny1 * 4};
-        cuuint32_t box[3] = {(cuuint32_t)t3::PITCH, (cuuint32_t)bs.rows, 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        CUresult rc = ((EncodeFn)h->encode_tiled)(reinterpret_cast<CUtensorMap*>(out.m[b]), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base,
-                                                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (rc != CUDA_SUCCESS) FAIL(h, "cuTensorMapEncodeTiled failed (%d) for box %d of kernel %d", (int)rc, b, kind);
+        if (encode_map(h, hm.m[b], base, fdims, bs.halo ? t3::PH : t3::ZC, bs.rows)) return 1;
     }
+    const cuuint64_t np2 = 2 * (cuuint64_t)g.npml;
+    const cuuint64_t xdims[3] = {(cuuint64_t)g.pz, (cuuint64_t)g.ny1, np2};
+    const cuuint64_t ydims[3] = {(cuuint64_t)g.pz, np2, (cuuint64_t)g.nx1};
+    const cuuint64_t zdims[3] = {(cuuint64_t)g.pzm, (cuuint64_t)g.ny1, (cuuint64_t)g.nx1};
+    for (int q = 0; q < 3; q++) {
+        const PmlTerm* terms = kind == 0 ? a.pv : a.ps;
+        const float* mx = terms[t3::term_index(kind, 2, q)].mem;
+        const float* my = terms[t3::term_index(kind, 1, q)].mem;
+        const float* mz = terms[t3::term_index(kind, 0, q)].mem;
+        if (mx && (g.pml & (XMIN | XMAX)) && encode_map(h, hm.m[nbox + q], mx, xdims, t3::ZC, t3::R)) return 1;
+        if (my && (g.pml & (YMIN | YMAX)) && encode_map(h, hm.m[nbox + 3 + q], my, ydims, t3::ZC, t3::R)) return 1;
+        if (mz && (g.pml & (ZMIN | ZMAX)) && encode_map(h, hm.m[nbox + 6 + q], mz, zdims, t3::PZM, t3::R)) return 1;
+    }
+    if (!*dout) CU(h, cudaMalloc((void**)dout, sizeof(t3::Maps)));
+    CU(h, cudaMemcpyAsync(*dout, &hm, sizeof hm, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 template <int KIND>
@@ -326,7 +351,7 @@ int launch_step3t(gpi_handle* h, const StepArgs& a) {
     for (auto& ts : h->tmaps) if (ts.key == a.v[0]) set = &ts;
     if (!set) {
         set = h->tmaps[0].key ? &h->tmaps[1] : &h->tmaps[0];
-        if (build_tmaps(h, a, 0, set->m[0]) || build_tmaps(h, a, 1, set->m[1])) return 1;
+        if (build_tmaps(h, a, 0, &set->d[0]) || build_tmaps(h, a, 1, &set->d[1])) return 1;
         set->key = a.v[0];
     }
     t3::Sched sc{};
@@ -343,14 +368,23 @@ int launch_step3t(gpi_handle* h, const StepArgs& a) {
     sc.nzc = (g.pz + t3::ZC - 1) / t3::ZC;
     sc.ntiles = (sc.ihi - sc.ilo + 1) * sc.njb * sc.nzc;
     const int nctas = std::max(1, std::min(sc.ntiles, h->tma3_ctas > 0 ? h->tma3_ctas : T3_MINB * h->num_sms));
-    const size_t smem = t3::smem_bytes(KIND == 0 ? (int)t3::V_FLOATS : (int)t3::S_FLOATS);
-    t3::k_step3t<KIND><<<nctas, t3::NTHREADS, smem, h->stream>>>(g, a, sc, set->m[KIND]);
+    // The shell touches cells no tile touches and reads only fields this half step does not write, so it runs
+    // beside the persistent tile kernel on a side stream (it needs no shared memory and fits next to the two
+    // resident tile CTAs of an SM): fork, shell, join.
+    const int nlines = sc.nsp * g.ny1 + (sc.ihi - sc.ilo + 1) * sc.nsr;
+    CU(h, cudaEventRecord(h->ev_fork, h->stream));
+    CU(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    t3::k_shell3<KIND><<<nlines, 128, 0, h->side>>>(g, a, sc);
+    CU(h, cudaEventRecord(h->ev_join, h->side));
+    t3::k_step3t<KIND><<<nctas, t3::NTHREADS, t3::smem_bytes(KIND), h->stream>>>(g, a, sc, set->d[KIND]);
+    CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    h->timers.launches += 1;
     return 0;
 }
 template <int EL>
 void launch_step_kernels3v(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
     const Geom& g = h->g;
-    if (EL && h->tma3 && nbatch == 1 && g.nx >= 8 && g.ny >= 8) {
+    if (EL && h->tma3 && nbatch == 1 && g.pzm == t3::PZM && g.nx >= 2 * g.npml + 8 && g.ny >= 2 * g.npml + 8) {
         if ((vel ? launch_step3t<0>(h, a) : launch_step3t<1>(h, a)) == 0) return;
         h->tma3 = false;                        // descriptor creation failed: fall back to the register-staged kernels
     }
@@ -362,6 +396,13 @@ void launch_step_kernels3v(gpi_handle* h, const StepArgs& a, bool vel, int nbatc
 template <int ND, int EL>
 void launch_step_kernels(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
     if (ND == 3 && h->vec3) { launch_step_kernels3v<EL>(h, a, vel, nbatch); return; }
+    if (ND == 2 && h->vec2) {
+        const int nthreads = (h->g.pz / VW) * h->g.nx1;
+        dim3 blk(128), grd((nthreads + 127) / 128, nbatch);
+        if (vel) k_vel2v<EL><<<grd, blk, 0, h->stream>>>(h->g, a);
+        else     k_stress2v<EL><<<grd, blk, 0, h->stream>>>(h->g, a);
+        return;
+    }
     dim3 blk = ND == 3 ? h->blk3 : h->blk2;
     dim3 grd = grid_for(h, blk, nbatch);
     if (vel) k_vel<ND, EL><<<grd, blk, 0, h->stream>>>(h->g, a);
@@ -607,6 +648,9 @@ static int create_impl(gpi_handle* h) {
     CU(h, cudaMallocHost((void**)&h->h_post_s, (size_t)B * sizeof(PostDesc)));
     CU(h, cudaEventCreate(&h->ev0));
     CU(h, cudaEventCreate(&h->ev1));
+    CU(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CU(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CU(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     if (h->slab) for (int d = 0; d < 2; d++) {
         const size_t nb = (size_t)3 * g.ny1 * g.nx1 * sizeof(float);
         CU(h, cudaMalloc((void**)&h->halo_send[d], nb));
@@ -641,12 +685,13 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (const char* e = getenv("GPI_SAMPLE_EVERY")) h->sample_every = atoi(e);
     if (const char* e = getenv("GPI_BLOCK3")) { int a, b, c3; if (sscanf(e, "%d,%d,%d", &a, &b, &c3) == 3 && a * b * c3 <= 256) h->blk3 = dim3(a, b, c3); }
     if (const char* e = getenv("GPI_SCALAR3D")) h->vec3 = atoi(e) == 0;
+    if (const char* e = getenv("GPI_SCALAR2D")) h->vec2 = atoi(e) == 0;
     if (const char* e = getenv("GPI_TMA3")) h->tma3 = atoi(e) != 0;
     if (const char* e = getenv("GPI_TMA3_CTAS")) h->tma3_ctas = atoi(e);
     if (h->nd == 3 && h->el) {
         cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
-        cudaError_t e0 = cudaFuncSetAttribute(t3::k_step3t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::smem_bytes(t3::V_FLOATS));
-        cudaError_t e1 = cudaFuncSetAttribute(t3::k_step3t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::smem_bytes(t3::S_FLOATS));
+        cudaError_t e0 = cudaFuncSetAttribute(t3::k_step3t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::smem_bytes(0));
+        cudaError_t e1 = cudaFuncSetAttribute(t3::k_step3t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::smem_bytes(1));
         cudaFuncSetAttribute(t3::k_step3t<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(t3::k_step3t<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaDriverEntryPointQueryResult qres;
@@ -684,8 +729,12 @@ extern "C" int gpi_destroy(gpi_handle* h) {
     if (h->h_post_s) cudaFreeHost(h->h_post_s);
     if (h->stage) cudaFreeHost(h->stage);
     cudaFree(h->dscratch);
+    for (auto& ts : h->tmaps) { cudaFree(ts.d[0]); cudaFree(ts.d[1]); }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side) cudaStreamDestroy(h->side);
     for (auto e : h->evpool) cudaEventDestroy(e);
     for (int d = 0; d < 2; d++) { cudaFree(h->halo_send[d]); cudaFree(h->halo_recv[d]); }
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -729,7 +778,8 @@ extern "C" int gpi_set_medium_interior(gpi_handle* h, int p, const float* a, con
         FAIL(h, "interior medium [%d,%d,%d] + padding [%d,%d,%d] does not fit the extended grid [%d,%d,%d]", mz, my, mx, lz, ly, lx, g.nz, g.ny, g.nx);
     const size_t nf = (size_t)mz * my * mx;
     if (h->dscratch_floats < nf) {
-        cudaFree(h->dscratch); h->dscratch = nullptr; h->dscratch_floats = 0;
+        cudaFree(h->dscratch);
+    for (auto& ts : h->tmaps) { cudaFree(ts.d[0]); cudaFree(ts.d[1]); } h->dscratch = nullptr; h->dscratch_floats = 0;
         CU(h, cudaMalloc((void**)&h->dscratch, nf * sizeof(float)));
         h->dscratch_floats = nf;
     }

@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(256) k_stress(const Geom g, const StepArgs a) 
 }
 
 #include "kernels3d.cuh"
+#include "kernels2v.cuh"
 #include "kernels3t.cuh"
 
 // ------------------------------------------------------------------------------------------------
