@@ -151,6 +151,8 @@ struct gpi_handle {
     // medium
     float* mod[GPI_NPARAM] = {};        // unified volumes
     float* dmod[C_N] = {};  float** dmod_table = nullptr;
+    // FD-Born (2-D acoustic): medium perturbation, scattering coefficients (d dtK, d bx, d bz), derivative scratch [B][2][vol]
+    float* modp[GPI_NPARAM] = {};  float* born_c[3] = {};  float* born_d = nullptr;  bool born_ready = false;
     // gradients (acoustic 2-D): total + per batch slot
     float* gtot[GPI_NPARAM] = {};  float* gshot = nullptr;   // gshot[b][2][vol]
     std::vector<ShotData> shots[2];
@@ -396,7 +398,7 @@ void launch_step_kernels3v(gpi_handle* h, const StepArgs& a, bool vel, int nbatc
 template <int ND, int EL>
 void launch_step_kernels(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
     if (ND == 3 && h->vec3) { launch_step_kernels3v<EL>(h, a, vel, nbatch); return; }
-    if (ND == 2 && h->vec2) {
+    if (ND == 2 && h->vec2 && !a.dout[0]) {        // the derivative write-out of FD-Born lives in the scalar kernels
         const int nthreads = (h->g.pz / VW) * h->g.nx1;
         dim3 blk(128), grd((nthreads + 127) / 128, nbatch);
         if (vel) k_vel2v<EL><<<grd, blk, 0, h->stream>>>(h->g, a);
@@ -729,6 +731,9 @@ extern "C" int gpi_destroy(gpi_handle* h) {
     if (h->h_post_s) cudaFreeHost(h->h_post_s);
     if (h->stage) cudaFreeHost(h->stage);
     cudaFree(h->dscratch);
+    for (auto& p : h->modp) cudaFree(p);
+    for (auto& p : h->born_c) cudaFree(p);
+    cudaFree(h->born_d);
     for (auto& ts : h->tmaps) { cudaFree(ts.d[0]); cudaFree(ts.d[1]); }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -811,6 +816,30 @@ extern "C" int gpi_update_dmod(gpi_handle* h) {
     else                      k_dmod<3, 1><<<grd, blk, 0, h->stream>>>(h->g, m0, h->mod[GPI_RHO], h->mod[GPI_INVMU], h->dmod_table, dt);
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int gpi_set_medium_pert(gpi_handle* h, int p, const float* a) {
+    GUARD(h);
+    if (h->nd != 2 || h->el) FAIL(h, "FD-Born exists for 2-D acoustic media only (born.jl:1-12)");
+    if (p != GPI_INVK && p != GPI_RHO) FAIL(h, "medium perturbation %d is not a parameter of this physics", p);
+    if (!a) FAIL(h, "null medium perturbation");
+    if (!h->modp[p]) { CU(h, cudaMalloc((void**)&h->modp[p], (size_t)h->g.vol * sizeof(float))); CU(h, cudaMemset(h->modp[p], 0, (size_t)h->g.vol * sizeof(float))); }
+    h->born_ready = false;
+    return upload_field(h, GPI_P, a, h->modp[p]);
+}
+extern "C" int gpi_update_born(gpi_handle* h) {
+    GUARD(h);
+    if (h->nd != 2 || h->el || h->npw != 2) FAIL(h, "FD-Born needs a 2-D acoustic experiment with npw = 2");
+    if (!h->modp[GPI_INVK] || !h->modp[GPI_RHO]) FAIL(h, "gpi_update_born: set the perturbations of invK and rho first");
+    const size_t vb = (size_t)h->g.vol * sizeof(float);
+    for (auto& p : h->born_c) if (!p) { CU(h, cudaMalloc((void**)&p, vb)); CU(h, cudaMemset(p, 0, vb)); }
+    if (!h->born_d) CU(h, cudaMalloc((void**)&h->born_d, (size_t)h->B * 2 * vb));
+    dim3 blk = h->blk2, grd = grid_for(h, blk, 1);
+    k_born_coef<<<grd, blk, 0, h->stream>>>(h->g, h->mod[GPI_INVK], h->mod[GPI_RHO], h->modp[GPI_INVK], h->modp[GPI_RHO],
+                                            h->born_c[0], h->born_c[1], h->born_c[2], (float)h->c.dt);
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->born_ready = true;
     return 0;
 }
 extern "C" int gpi_set_pml(gpi_handle* h, int f, const float* a, const float* b, const float* kI) {
@@ -1087,6 +1116,12 @@ bool any_post(const PostDesc* d, int nb, bool with_rec) {
 
 extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     GUARD(h);
+    const bool born = (mode & GPI_RUN_BORN) != 0;
+    const int unshifted = (mode & GPI_RUN_UNSHIFTED_RHO) ? 1 : 0;
+    mode &= ~(GPI_RUN_BORN | GPI_RUN_UNSHIFTED_RHO);
+    if (born && (h->nd != 2 || h->el || h->npw != 2 || (activepw & 3) != 3)) FAIL(h, "FD-Born needs a 2-D acoustic experiment with both wavefields active");
+    if (born && mode == GPI_MODE_ADJOINT) FAIL(h, "FD-Born scattering sources exist in the forward modes only (born.jl:27-30)");
+    if (born && !h->born_ready) FAIL(h, "FD-Born: call gpi_set_medium_pert and gpi_update_born first");
     if (mode != GPI_MODE_FORWARD && mode != GPI_MODE_FORWARD_SAVE && mode != GPI_MODE_ADJOINT) FAIL(h, "unknown mode %d", mode);
     if (!(activepw & 1)) FAIL(h, "pw 1 must be active");
     if ((activepw & 2) && h->npw < 2) FAIL(h, "pw 2 requested but the experiment was built with npw = 1");
@@ -1125,6 +1160,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
         const bool inj_s = any_post(h->h_post_s, nb, false), rec_s = any_post(h->h_post_s, nb, true);
         StepArgs args[2];
         for (int ipw = 0; ipw < h->npw; ipw++) fill_args(h, args[ipw], ipw, nb);
+        if (born) { args[0].dout[0] = h->born_d; args[0].dout[1] = h->born_d + g.vol; args[0].dstride = 2 * g.vol; }
         // record!(1, ..., [:p]) at the start of step 1 (zero unless the fields were loaded from snapshots)
         if (rec_s) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, 1, 1, nt, (float)h->c.dt, 2); h->timers.launches += 1; }
 
@@ -1144,9 +1180,19 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             }
             const bool sample = h->sample_every > 0 && (it % h->sample_every) == 0;
             for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], true, nb, sample && ipw == 0);
+            if (born) {        // add_born_sources_velocity! (propagate.jl:205)
+                dim3 blk = h->blk2, grd = grid_for(h, blk, nb);
+                k_born_add<0><<<grd, blk, 0, h->stream>>>(g, args[1].v[V_X], args[1].v[V_Z], h->born_d, h->born_d + g.vol, h->born_c[1], h->born_c[2], h->bstride, 2 * g.vol);
+                h->timers.launches += 1;
+            }
             if (do_post_v) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_v, it, it, nt, (float)h->c.dt, 3); h->timers.launches += 1; }
             if (exchange_halos(h, 1)) return 1;
             for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], false, nb, sample && ipw == 0);
+            if (born) {        // add_born_sources_stress! (propagate.jl:226)
+                dim3 blk = h->blk2, grd = grid_for(h, blk, nb);
+                k_born_add<1><<<grd, blk, 0, h->stream>>>(g, args[1].tau[T_XX], nullptr, h->born_d, h->born_d + g.vol, h->born_c[0], nullptr, h->bstride, 2 * g.vol);
+                h->timers.launches += 1;
+            }
             // stress sources at step it, then the pressure record of step it+1 (record! runs at the start of a step)
             if (inj_s || (rec_s && it < nt)) {
                 k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, it, it + 1, nt, (float)h->c.dt, 3);
@@ -1166,7 +1212,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                     wf_ptr(h, h->W, 0, 0, GPI_P), wf_ptr(h, h->TP, 0, 0, GPI_P), wf_ptr(h, h->TP, 0, 1, GPI_P),
                     wf_ptr(h, h->W, 0, 0, GPI_VX), wf_ptr(h, h->TP, 0, 0, GPI_VX), wf_ptr(h, h->TP, 0, 1, GPI_VX),
                     wf_ptr(h, h->W, 0, 0, GPI_VZ), wf_ptr(h, h->TP, 0, 0, GPI_VZ), wf_ptr(h, h->TP, 0, 1, GPI_VZ),
-                    h->gshot, h->gshot + g.vol, (float)h->c.dtI, h->bstride, 2 * g.vol);
+                    h->gshot, h->gshot + g.vol, (float)h->c.dtI, h->bstride, 2 * g.vol, unshifted);
                 h->timers.launches += 1;
             }
             if (!h->itsnaps.empty()) for (int ks = 0; ks < (int)h->itsnaps.size(); ks++) if (h->itsnaps[ks] == it)

@@ -72,6 +72,10 @@ struct StepArgs {
     PmlTerm ps[9];           // terms of k_stress
     long long wstride;       // floats between batch slots of the wavefield set
     int nbatch;
+    // FD-Born (2-D acoustic): when set, the scalar kernels also store the CPML-corrected derivatives of this
+    // wavefield (dpdx, dpdz in the velocity kernel; dvxdx, dvzdz in the stress kernel), the scattering sources
+    float* dout[2];
+    long long dstride;       // floats between batch slots of dout
 };
 
 __device__ __forceinline__ long long uidx(const Geom& g, int k, int j, int i) {
@@ -180,6 +184,7 @@ __device__ __forceinline__ void vel_cell(const Geom& g, const StepArgs& a, int k
         if (vxin) {
             float d = __fmul_rn(__fsub_rn(pc, p[c - sx]), g.dxI);
             d = cpml<2>(g, a.pv[0], d, k, j, i, 1, nx - 1, b);
+            if (ND == 2 && a.dout[0]) a.dout[0][c + (long long)b * a.dstride] = d;
             nvx = __fadd_rn(nvx, __fmul_rn(__ldg(a.c[C_BX] + c), d));
         }
         if (ND == 3 && vyin) {
@@ -190,6 +195,7 @@ __device__ __forceinline__ void vel_cell(const Geom& g, const StepArgs& a, int k
         if (vzin) {
             float d = __fmul_rn(__fsub_rn(pc, p[c - 1]), g.dzI);
             d = cpml<0>(g, a.pv[2], d, k, j, i, 1, nz - 1, b);
+            if (ND == 2 && a.dout[1]) a.dout[1][c + (long long)b * a.dstride] = d;
             nvz = __fadd_rn(nvz, __fmul_rn(__ldg(a.c[C_BZ] + c), d));
         }
     } else if (ND == 2) {
@@ -336,6 +342,7 @@ __device__ __forceinline__ void stress_cell(const Geom& g, const StepArgs& a, in
     }
 
     if (!EL) {
+        if (ND == 2 && nin && a.dout[0]) { a.dout[0][c + (long long)b * a.dstride] = dxx; a.dout[1][c + (long long)b * a.dstride] = dzz; }
         if (nin) {
             float* p = a.tau[T_XX] + w;
             const float s = (ND == 3) ? __fadd_rn(__fadd_rn(dxx, dzz), dyy) : __fadd_rn(dxx, dzz);
@@ -566,19 +573,78 @@ __global__ void k_boundary(const Geom g, float* __restrict__ field, float* __res
 __global__ void k_grad2d(const Geom g, const float* __restrict__ p1, const float* __restrict__ p1tp, const float* __restrict__ p2tp,
                          const float* __restrict__ vx1, const float* __restrict__ vx1tp, const float* __restrict__ vx2tp,
                          const float* __restrict__ vz1, const float* __restrict__ vz1tp, const float* __restrict__ vz2tp,
-                         float* __restrict__ gK, float* __restrict__ gR, float dtI, long long wstride, long long gstride) {
+                         float* __restrict__ gK, float* __restrict__ gR, float dtI, long long wstride, long long gstride, int unshifted) {
     int k, j, i, b;
     if (!cell<2>(g, 1, k, j, i, b)) return;
     if (k > g.nz - 1 || i > g.nx - 1) return;
     const long long w = (long long)b * wstride, gw = (long long)b * gstride;
     const long long c = uidx(g, k, 0, i), sx = g.pz;
     gK[gw + c] = __fadd_rn(gK[gw + c], __fmul_rn(__fmul_rn(p2tp[w + c], __fsub_rn(p1tp[w + c], p1[w + c])), dtI));
+    if (unshifted) {
+        // GPI_RUN_UNSHIFTED_RHO: cell (k, i) takes the velocity nodes that bound it -- vx nodes i and i+1, vz nodes k and
+        // k+1, interior nodes only -- which makes the imaging the exact transpose of the FD-Born map
+        auto bufx = [&](int kk, int ii) { const long long q = w + uidx(g, kk, 0, ii);
+            return (kk >= 1 && kk <= g.nz - 2 && ii >= 1 && ii <= g.nx - 1) ? __fmul_rn(__fmul_rn(vx2tp[q], __fsub_rn(vx1[q], vx1tp[q])), dtI) : 0.f; };
+        auto bufz = [&](int kk, int ii) { const long long q = w + uidx(g, kk, 0, ii);
+            return (kk >= 1 && kk <= g.nz - 1 && ii >= 1 && ii <= g.nx - 2) ? __fmul_rn(__fmul_rn(vz2tp[q], __fsub_rn(vz1[q], vz1tp[q])), dtI) : 0.f; };
+        const float ax = __fadd_rn(bufx(k, i), bufx(k, i + 1)), az = __fadd_rn(bufz(k, i), bufz(k + 1, i));
+        gR[gw + c] = (float)((double)gR[gw + c] - (double)ax * 0.5 - (double)az * 0.5);
+        return;
+    }
     if (k >= 1 && k <= g.nz - 2 && i >= 1 && i <= g.nx - 2) {
         auto bufx = [&](long long q) { return __fmul_rn(__fmul_rn(vx2tp[w + q], __fsub_rn(vx1[w + q], vx1tp[w + q])), dtI); };
         auto bufz = [&](long long q) { return __fmul_rn(__fmul_rn(vz2tp[w + q], __fsub_rn(vz1[w + q], vz1tp[w + q])), dtI); };
         const float ax = __fadd_rn(bufx(c - sx), bufx(c));     // vxbuffer[iz+1, ix] + vxbuffer[iz+1, ix+1]
         const float az = __fadd_rn(bufz(c - 1), bufz(c));      // vzbuffer[iz, ix+1] + vzbuffer[iz+1, ix+1]
         gR[gw + c] = (float)((double)gR[gw + c] - (double)ax * 0.5 - (double)az * 0.5);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FD-Born scattering sources, 2-D acoustic (born.jl:1-12; upstream passes argument lists that match no kernel,
+// the intent is the commented legacy code born.jl:32-99): the second wavefield is driven by the first one's
+// derivatives times the perturbation of the update coefficients,
+//     v?2_inn = v?2_inn + d(dt / av(rho)) * dpd?1          (after update_v!, propagate.jl:205)
+//     p2      = p2 + (dvxdx1 + dvzdz1) * d(dt K)           (after update_stress!, propagate.jl:226)
+// k_born_coef linearises the coefficient perturbations in (d invK, d rho), so that the map from the medium
+// perturbation to the scattered data is exactly linear:
+//     d(dt K) = -((K K) d invK) dt,  K = 1 / invK;     d(dt / av rho) = -(dt av(d rho)) / (av rho)^2   (Float64, rounded once)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_born_coef(const Geom g, const float* __restrict__ invK, const float* __restrict__ rho,
+                            const float* __restrict__ dinvK, const float* __restrict__ drho,
+                            float* __restrict__ ddtK, float* __restrict__ dbx, float* __restrict__ dbz, float dt) {
+    int k, j, i, b;
+    if (!cell<2>(g, 1, k, j, i, b)) return;
+    const long long c = uidx(g, k, 0, i), sx = g.pz;
+    const int nz = g.nz, nx = g.nx;
+    const double ddt = (double)dt;
+    if (k <= nz - 1 && i <= nx - 1) {
+        const float K = __fdiv_rn(1.0f, invK[c]);
+        ddtK[c] = -__fmul_rn(__fmul_rn(__fmul_rn(K, K), dinvK[c]), dt);
+    }
+    if (k >= 1 && k <= nz - 2 && i >= 1 && i <= nx - 1) {
+        const double av = (double)__fadd_rn(rho[c - sx], rho[c]) * 0.5, dav = (double)__fadd_rn(drho[c - sx], drho[c]) * 0.5;
+        dbx[c] = (float)(-(ddt * dav) / (av * av));
+    }
+    if (k >= 1 && k <= nz - 1 && i >= 1 && i <= nx - 2) {
+        const double av = (double)__fadd_rn(rho[c - 1], rho[c]) * 0.5, dav = (double)__fadd_rn(drho[c - 1], drho[c]) * 0.5;
+        dbz[c] = (float)(-(ddt * dav) / (av * av));
+    }
+}
+// KIND 0: velocities of pw 2 (d0 = dpdx1, d1 = dpdz1, c0 = dbx, c1 = dbz); KIND 1: pressure of pw 2 (d0 = dvxdx1, d1 = dvzdz1, c0 = d(dtK))
+template <int KIND>
+__global__ void k_born_add(const Geom g, float* __restrict__ f0, float* __restrict__ f1, const float* __restrict__ d0,
+                           const float* __restrict__ d1, const float* __restrict__ c0, const float* __restrict__ c1,
+                           long long wstride, long long dstride) {
+    int k, j, i, b;
+    if (!cell<2>(g, 1, k, j, i, b)) return;
+    const long long c = uidx(g, k, 0, i), w = (long long)b * wstride, dw = (long long)b * dstride;
+    const int nz = g.nz, nx = g.nx;
+    if (KIND == 0) {
+        if (k >= 1 && k <= nz - 2 && i >= 1 && i <= nx - 1) f0[c + w] = __fadd_rn(f0[c + w], __fmul_rn(c0[c], d0[c + dw]));
+        if (k >= 1 && k <= nz - 1 && i >= 1 && i <= nx - 2) f1[c + w] = __fadd_rn(f1[c + w], __fmul_rn(c1[c], d1[c + dw]));
+    } else {
+        if (k <= nz - 1 && i <= nx - 1) f0[c + w] = __fadd_rn(f0[c + w], __fmul_rn(__fadd_rn(d0[c + dw], d1[c + dw]), c0[c]));
     }
 }
 

@@ -18,6 +18,8 @@ LIB_PATH = os.environ.get("GPI_LIB") or os.path.join(_HERE, "libgpifdtd.so")   #
 ABI_VERSION = 1
 ACOUSTIC, ELASTIC = 0, 1
 MODE = {"forward": 0, "forward_save": 1, "adjoint": 2}
+RUN_BORN = 0x100                     # OR into the mode: FD-Born scattering sources from pw 1 into pw 2
+RUN_UNSHIFTED_RHO = 0x200            # OR into an adjoint run: g_rho without upstream's one-cell shift (exact transpose of the Born map)
 FACE = {"zmin": 1, "zmax": 2, "ymin": 4, "ymax": 8, "xmin": 16, "xmax": 32}
 PARAM = {"invK": 0, "rho": 1, "invlambda": 2, "invmu": 3}
 FIELDS = [
@@ -61,7 +63,7 @@ def face_mask(faces) -> int:
 
 EXPORTS = [
     "gpi_create", "gpi_destroy", "gpi_last_error", "gpi_abi_version", "gpi_set_medium", "gpi_set_medium_rows", "gpi_set_medium_interior", "gpi_get_medium", "gpi_slab_range",
-    "gpi_update_dmod", "gpi_set_pml", "gpi_set_sparse", "gpi_set_wavelets", "gpi_run", "gpi_get_records",
+    "gpi_update_dmod", "gpi_set_medium_pert", "gpi_update_born", "gpi_set_pml", "gpi_set_sparse", "gpi_set_wavelets", "gpi_run", "gpi_get_records",
     "gpi_get_gradient", "gpi_get_snap", "gpi_set_snap_steps", "gpi_get_field", "gpi_set_field", "gpi_reset",
     "gpi_nccl_unique_id", "gpi_nccl_init", "gpi_allreduce_gradients", "gpi_records_device_ptr",
     "gpi_gradient_device_ptr", "gpi_set_stream", "gpi_synchronize", "gpi_get_timers", "gpi_field_shape",
@@ -93,6 +95,8 @@ def load_library(path: str = LIB_PATH):
         "gpi_set_medium_interior": ([vp, C.c_int, fp, ip, ip], C.c_int),
         "gpi_slab_range": ([vp, ip, ip], C.c_int),
         "gpi_update_dmod": ([vp], C.c_int),
+        "gpi_set_medium_pert": ([vp, C.c_int, fp], C.c_int),
+        "gpi_update_born": ([vp], C.c_int),
         "gpi_set_pml": ([vp, C.c_int, fp, fp, fp], C.c_int),
         "gpi_set_sparse": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i64p, i64p, fp], C.c_int),
         "gpi_set_wavelets": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, fp], C.c_int),
@@ -207,6 +211,14 @@ class Engine:
     def update_dmod(self):
         self._ck(self.lib.gpi_update_dmod(self.h))
 
+    def set_medium_pert(self, name: str, a):
+        """FD-Born: perturbation of `invK` | `rho` on the extended grid (medium.jl:103-127)."""
+        a = _f32(a)
+        self._ck(self.lib.gpi_set_medium_pert(self.h, PARAM[name], _fp(a)))
+
+    def update_born(self):
+        self._ck(self.lib.gpi_update_born(self.h))
+
     def set_pml(self, dfield: str, a, b, kI):
         a, b, kI = _f32(a), _f32(b), _f32(kI)
         assert a.size == b.size == kI.size == 2 * self.cfg.npml
@@ -229,10 +241,10 @@ class Engine:
         wf = _f32(w)
         self._ck(self.lib.gpi_set_wavelets(self.h, ipw, issp, FIELD[field], w.shape[1], _fp(wf)))
 
-    def run(self, mode: str, activepw=(1,), src_flags=(True,)):
+    def run(self, mode: str, activepw=(1,), src_flags=(True,), born: bool = False, unshifted_rho: bool = False):
         am = sum(1 << (p - 1) for p in activepw)
         sm = sum(1 << i for i, f in enumerate(src_flags) if f)
-        self._ck(self.lib.gpi_run(self.h, MODE[mode], am, sm))
+        self._ck(self.lib.gpi_run(self.h, MODE[mode] | (RUN_BORN if born else 0) | (RUN_UNSHIFTED_RHO if unshifted_rho else 0), am, sm))
 
     def get_records(self, ipw: int, issp: int, field: str, nr: int):
         out = np.empty(self.cfg.nt * nr, np.float32)

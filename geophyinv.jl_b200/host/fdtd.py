@@ -41,10 +41,8 @@ class _Fdtd:
 
     def __post_init__(self):
         self.mode = str(self.mode).lstrip(":")
-        if self.mode != "forward" and self.npw == 1 and not self.born:
-            self.npw = 2                       # FdtdAcoustic(:forward_save) has npw = 2 (physics_types.jl:42-48)
-        if self.born:
-            raise NotImplementedError("FD-Born scattering sources are a later row (SURVEY.md section 8f)")
+        if (self.mode != "forward" or self.born) and self.npw == 1:
+            self.npw = 2                       # FdtdAcoustic(:forward_save) / FdtdAcoustic{Born}() have npw = 2 (physics_types.jl:37-48)
 
 
 class FdtdAcoustic(_Fdtd):
@@ -112,6 +110,8 @@ class PFdtd:
         N = medium.ndims
         npw = attrib_mod.npw
         assert (attrib_mod.physics == "elastic") == medium.elastic, "attrib_mod / medium mismatch"
+        if attrib_mod.born and not (attrib_mod.physics == "acoustic" and N == 2):
+            raise NotImplementedError("FD-Born exists upstream for 2-D acoustic media only (src/fdtd/born.jl:1-12)")
         pml_faces = [str(f).lstrip(":") for f in pml_faces]
         rigid_faces = pml_faces if rigid_faces is None else [str(f).lstrip(":") for f in rigid_faces]
         rfields = [str(f).lstrip(":") for f in rfields]
@@ -211,6 +211,9 @@ class PFdtd:
             self.engine.set_snap_steps(c.itsnaps)
 
         self.update_medium(medium)                                                     # fdtd.jl:240
+        if attrib_mod.born:                                                            # fdtd.jl:242-244: no perturbation yet
+            c.dmod_pert = {name: np.zeros(n, F32, order="F") for name in c.mparams}
+            self._upload_born()
         self.update_ageom(c.ageom)                                                     # fdtd.jl:522-525
         self.update_srcwav(c.srcwav, [1] * npw)                                        # fdtd.jl:274
         self.update_pml()                                                              # fdtd.jl:279
@@ -233,6 +236,22 @@ class PFdtd:
         for name in c.mparams:                                                         # copyto!(mod[name], exmedium, name)
             self.engine.set_medium_interior(name, c.medium.derived_into(name, self._dbuf[0], self._dbuf[1]), lo)
         self.engine.update_dmod()
+
+    # ---------------------------------------------------------------------------------------------
+    # update!(pa, medium, medium_pert)  (medium.jl:103-127): FD-Born, waves propagate in `medium`
+    # ---------------------------------------------------------------------------------------------
+    def update_medium_pert(self, medium: Medium, medium_pert: Medium):
+        c = self.c
+        assert c.attrib_mod.born, "update!(pa, medium, medium_pert) needs FdtdAcoustic{Born}"
+        self.update_medium(medium)
+        expert = padarray(medium_pert, NPML, c.pml_faces)
+        c.dmod_pert = {name: np.asfortranarray(expert[name] - c.mod[name]) for name in c.mparams}      # δmod .= exmedium_pert .- mod
+        self._upload_born()
+
+    def _upload_born(self):
+        for name in self.c.mparams:
+            self.engine.set_medium_pert(name, self.c.dmod_pert[name])
+        self.engine.update_born()
 
     # update!(pa, m, mparams): log-parameterised model vector (medium.jl:31-52)
     def update_model(self, m: np.ndarray, mparams=None):
@@ -335,6 +354,10 @@ class PFdtd:
     def get_update_parameters(self):
         """propagate.jl:38-60"""
         c = self.c
+        if c.attrib_mod.born:                                                          # propagate.jl:53-60
+            if c.attrib_mod.mode == "adjoint":
+                return dict(activepw=[1, 2], src_flags=[True, True], rec_flags=[False, False])
+            return dict(activepw=[1, 2], src_flags=[True, False], rec_flags=[False, True])
         if c.ic["npw"] == 1:
             return dict(activepw=[1], src_flags=[True], rec_flags=[True])
         if c.attrib_mod.mode == "adjoint":
@@ -361,7 +384,12 @@ class PFdtd:
         self.engine.reset(what)
         if len(self.local):
             # mod_x_proc! (propagate.jl:100-106)
-            self.engine.run(mode, upa["activepw"], upa["src_flags"])
+            if c.attrib_mod.born and mode != "adjoint":
+                self.engine.run(mode, upa["activepw"], upa["src_flags"], born=True)
+            elif getattr(self, "unshifted_rho", False) and mode == "adjoint":
+                self.engine.run(mode, upa["activepw"], upa["src_flags"], unshifted_rho=True)
+            else:
+                self.engine.run(mode, upa["activepw"], upa["src_flags"])
         # sum_grads! (propagate.jl:110-117, gradient.jl:2-11)
         if mode == "adjoint" and c.ic["npw"] == 2 and c.attrib_mod.physics == "acoustic":
             if self._nccl:
@@ -411,6 +439,8 @@ def update(pa: PFdtd, *args, **kw):
         return pa.update(**kw)
     a = args[0]
     if isinstance(a, Medium):
+        if len(args) > 1 and isinstance(args[1], Medium):
+            return pa.update_medium_pert(a, args[1])
         return pa.update_medium(a)
     if isinstance(a, np.ndarray):
         return pa.update_model(a, *args[1:])
@@ -481,3 +511,91 @@ def gradient(g: np.ndarray, m, dobs, pa: PFdtd, mparams=None) -> float:
         gi[...] = gm.ravel(order="F")
     c.attrib_mod.mode = mode_save
     return loss
+
+
+# --------------------------------------------------------------------------------------------------
+# FD-Born linearised map (src/fdtd/func_grad.jl:51-120, commented upstream; test/fwi/born_map.jl)
+# --------------------------------------------------------------------------------------------------
+def forward_map(d: np.ndarray, m: np.ndarray, pa: PFdtd) -> np.ndarray:
+    """`forward_map!(d, m, pa)` (func_grad.jl:53-68): `m` = [δinvK; δrho] on the extended grid (column-major),
+    `d` = the scattered data of the first supersource, fields in `rfields` order."""
+    c = pa.c
+    n = c.gradients[c.mparams[0]].shape
+    for x, name in zip(np.split(np.asarray(m, F32), len(c.mparams)), c.mparams):
+        c.dmod_pert[name] = np.asfortranarray(x.reshape(n, order="F"))
+    pa._upload_born()
+    pa.update_srcwav(c.srcwav, [1, 1])
+    mode_save = c.attrib_mod.mode
+    c.attrib_mod.mode = "forward"
+    pa.update()
+    c.attrib_mod.mode = mode_save
+    d[...] = np.concatenate([c.data[1][0].d[f].ravel(order="F") for f in c.rfields])
+    return d
+
+
+def adjoint_map(gm: np.ndarray, d: np.ndarray, pa: PFdtd, exact: bool = True) -> np.ndarray:
+    """`adjoint_map!(gm, d, pa)` (func_grad.jl:70-92): `d` becomes the adjoint source at the receivers of the first
+    supersource; the imaging condition of `compute_gradient!` gives `gm` = [g_invK; g_rho].  The forward_save pass
+    that fills the boundary store of pw 1 runs here (upstream assumes an earlier call did it).
+    `exact=True`: g_rho without upstream's one-cell shift (gradient.jl:53-56) and the sign of a transpose (the
+    imaging accumulates MINUS the transpose, the convention of the FWI gradient), so that
+    <y, F x> == <x, F' y> (test/fwi/born_map.jl); `exact=False` returns `pa.c.gradients` as the reference would."""
+    c = pa.c
+    assert c.attrib_mod.physics == "acoustic" and all(f in ("vx", "vz") for f in c.rfields), \
+        "adjoint sources exist for velocity receivers only (source.jl:142-156)"
+    mode_save = c.attrib_mod.mode
+    c.attrib_mod.mode = "forward_save"
+    pa.update_srcwav(c.srcwav, [1, 0])
+    pa.update()
+    s2 = c.srcwav[1][0]
+    for x, f in zip(np.split(np.asarray(d, F32), len(c.rfields)), c.rfields):
+        s2.d[f][...] = x.reshape(s2.d[f].shape, order="F")
+    for s in c.srcwav[1]:
+        s.reverse()
+    pa.update_srcwav(c.srcwav, [-1, 1])
+    c.attrib_mod.mode = "adjoint"
+    pa.unshifted_rho = bool(exact)
+    try:
+        pa.update()
+    finally:
+        pa.unshifted_rho = False
+        c.attrib_mod.mode = mode_save
+    gm[...] = np.concatenate([c.gradients[name].ravel(order="F") for name in c.mparams])
+    if exact:
+        gm *= F32(-1)
+    return gm
+
+
+class LinearMap:
+    """`LinearMap(pa)` for `FdtdAcoustic{Born}` (func_grad.jl:106-120): `F @ x` = forward_map, `F.T @ y` = adjoint_map.
+
+    `F` is exactly linear in x = [δinvK; δrho].  `F.T` is its transpose to rounding (dot test 1e-8 in Float64,
+    tests/test_oracle_invariants.py) for perturbations supported away from the source and receiver cells: there the
+    imaging condition of gradient.jl:17-56 sees the injected wavelets inside `v1 - v1_tp` and the adjoint source
+    inside `v2_tp`, which the scattering sources of born.jl do not contain (upstream behaviour, kept)."""
+
+    def __init__(self, pa: PFdtd):
+        self.pa = pa
+        c = pa.c
+        nd = sum(c.data[0][0].d[f].size for f in c.rfields)
+        nm = sum(g.size for g in c.gradients.values())
+        self.shape = (nd, nm)
+
+    def matvec(self, x):
+        return forward_map(np.zeros(self.shape[0], F32), x, self.pa)
+
+    def rmatvec(self, y):
+        return adjoint_map(np.zeros(self.shape[1], F32), y, self.pa)
+
+    __matmul__ = matvec
+
+    @property
+    def T(self):
+        outer = self
+
+        class _T:
+            shape = (outer.shape[1], outer.shape[0])
+
+            def __matmul__(self, y):
+                return outer.rmatvec(y)
+        return _T()

@@ -39,6 +39,11 @@ enum { GPI_ACOUSTIC = 0, GPI_ELASTIC = 1 };
 
 /* attrib_mod.mode, reference src/physics_types.jl:17-49, src/fdtd/propagate.jl:38-60 */
 enum { GPI_MODE_FORWARD = 0, GPI_MODE_FORWARD_SAVE = 1, GPI_MODE_ADJOINT = 2 };
+/* OR into the mode of gpi_run: FD-Born scattering sources from pw 1 into pw 2 (FdtdAcoustic{Born}, born.jl:1-12) */
+#define GPI_RUN_BORN 0x100
+/* OR into the mode of an adjoint run: g_rho takes the velocity nodes that bound a cell instead of upstream's one-cell-shifted
+ * pair (combine_gmodrho!, gradient.jl:53-56), which makes the imaging the exact transpose of the FD-Born map (LinearMap) */
+#define GPI_RUN_UNSHIFTED_RHO 0x200
 
 /* face bit masks (pml_faces / rigid_faces / stressfree_faces), reference src/fdtd/fdtd.jl:65-68 */
 enum {
@@ -138,6 +143,10 @@ int  gpi_set_medium_rows(gpi_handle* h, int param_id, const float* rows, int k_f
 int  gpi_set_medium_interior(gpi_handle* h, int param_id, const float* a, const int32_t n_in[3], const int32_t lo[3]);
 int  gpi_get_medium(gpi_handle* h, int param_id, float* out);
 int  gpi_update_dmod(gpi_handle* h);
+/* FD-Born (2-D acoustic): replaces copyto!(pac.δmod[name], exmedium_pert) followed by δmod .-= mod of update!(pac, medium, medium_pert)
+ * (medium.jl:103-127): the perturbation of invK | rho on the extended grid, then the scattering coefficients */
+int  gpi_set_medium_pert(gpi_handle* h, int param_id, const float* ex_array /* [nz, nx] */);
+int  gpi_update_born(gpi_handle* h);
 
 /* ---- CPML: replaces copyto!(pml[df][:a|:b|:kI], ...) in update_pml! (cpml.jl:100-102) -------- */
 int  gpi_set_pml(gpi_handle* h, int dfield_id, const float* a, const float* b, const float* kI /* 2*npml each */);

@@ -149,6 +149,8 @@ typedef struct orc_handle {
     int nz, ny, nx, nd;
     REAL dt, dtI, dzI, dyI, dxI;
     arr mod[GPI_NPARAM], dmod[DM_N];
+    arr modp[GPI_NPARAM], bornc[3];   /* FD-Born: medium perturbation; d(dtK), d(bx), d(bz) */
+    int born_ready;
     REAL *pa[GPI_NFIELD], *pb[GPI_NFIELD], *pk[GPI_NFIELD];   /* CPML a, b, kI (2*npml each) */
     arr gradients[GPI_NPARAM];
     pw_t pw[2];
@@ -715,7 +717,7 @@ static void boundary_force(orc_handle* h, int it, int issp) {   /* boundary.jl:1
 /* ------------------------------------------------------------------------------------------------
  * gradient imaging: src/fdtd/gradient.jl:17-61 (2-D acoustic; gradlame! + gradrho!)
  * ---------------------------------------------------------------------------------------------- */
-static void compute_gradient(orc_handle* h, int issp) {
+static void compute_gradient(orc_handle* h, int issp, int unshifted) {
     pw_t *p1 = &h->pw[0], *p2 = &h->pw[1]; shot_t* s = &p1->ss[issp];
     arr g = s->grad[GPI_INVK], pf = p1->w[GPI_P], pfp = p1->wtp[GPI_P], pap = p2->wtp[GPI_P];
     REAL dtI = h->dtI;
@@ -728,6 +730,16 @@ static void compute_gradient(orc_handle* h, int issp) {
         for (size_t i = 0; i < b.len; i++) b.d[i] = va.d[i] * (v.d[i] - vp.d[i]) * dtI;
     }
     arr gr = s->grad[GPI_RHO], bx = p1->vbuf[GPI_VX], bz = p1->vbuf[GPI_VZ];
+    if (unshifted) {     /* GPI_RUN_UNSHIFTED_RHO: cell (iz, ix) <- vx nodes ix, ix+1 and vz nodes iz, iz+1 (interior nodes only) */
+        OMP_FOR
+        for (int ix = 1; ix <= gr.n[2]; ix++) for (int iz = 1; iz <= gr.n[0]; iz++) {
+            #define BXI(z, x) (((z) >= 2 && (z) <= bx.n[0] - 1 && (x) >= 2 && (x) <= bx.n[2] - 1) ? A2(bx, z, x) : (REAL)0)
+            #define BZI(z, x) (((z) >= 2 && (z) <= bz.n[0] - 1 && (x) >= 2 && (x) <= bz.n[2] - 1) ? A2(bz, z, x) : (REAL)0)
+            A2(gr, iz, ix) = (REAL)((double)A2(gr, iz, ix) - (double)(REAL)(BXI(iz, ix) + BXI(iz, ix + 1)) * 0.5
+                                                             - (double)(REAL)(BZI(iz, ix) + BZI(iz + 1, ix)) * 0.5);
+        }
+        return;
+    }
     OMP_FOR
     for (int ix = 1; ix <= gr.n[2] - 2; ix++) for (int iz = 1; iz <= gr.n[0] - 2; iz++)                     /* combine_gmodrho!: Float64 via 0.5 literals */
         A2(gr, iz + 1, ix + 1) = (REAL)((double)A2(gr, iz + 1, ix + 1)
@@ -756,8 +768,52 @@ static double now_s(void) {
 #endif
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * FD-Born scattering sources, 2-D acoustic (born.jl:1-12 names the intent -- compute_v!(v2, d invrho, dp1, dt),
+ * compute_p!(p2, dv1, d K, dt) -- with argument lists that match no kernel upstream; commented legacy code
+ * born.jl:32-99).  The coefficient perturbations are linearised in (d invK, d rho):
+ *     d(dt K) = -((K K) d invK) dt;   d(dt / av rho) = -(dt av(d rho)) / (av rho)^2  (Float64, rounded once)
+ * ---------------------------------------------------------------------------------------------- */
+static void update_born(orc_handle* h) {
+    double dt = (double)h->dt;
+    arr rho = h->mod[GPI_RHO], drho = h->modp[GPI_RHO], iK = h->mod[GPI_INVK], diK = h->modp[GPI_INVK];
+    arr dK = h->bornc[0], dbx = h->bornc[1], dbz = h->bornc[2];
+    for (size_t i = 0; i < dK.len; i++) { REAL K = (REAL)1 / iK.d[i]; dK.d[i] = -((REAL)((REAL)(K * K) * diK.d[i]) * h->dt); }
+    for (int ix = 1; ix <= dbx.n[2]; ix++) for (int iz = 1; iz <= dbx.n[0]; iz++) {
+        double av = (double)(REAL)(A2(rho, iz + 1, ix) + A2(rho, iz + 1, ix + 1)) * 0.5, dav = (double)(REAL)(A2(drho, iz + 1, ix) + A2(drho, iz + 1, ix + 1)) * 0.5;
+        A2(dbx, iz, ix) = (REAL)(-(dt * dav) / (av * av));
+    }
+    for (int ix = 1; ix <= dbz.n[2]; ix++) for (int iz = 1; iz <= dbz.n[0]; iz++) {
+        double av = (double)(REAL)(A2(rho, iz, ix + 1) + A2(rho, iz + 1, ix + 1)) * 0.5, dav = (double)(REAL)(A2(drho, iz, ix + 1) + A2(drho, iz + 1, ix + 1)) * 0.5;
+        A2(dbz, iz, ix) = (REAL)(-(dt * dav) / (av * av));
+    }
+}
+/* add_born_sources_velocity! (propagate.jl:205): @inn(v?2) = @inn(v?2) + @all(d b?) * @all(dpd?1) */
+static void born_velocity(orc_handle* h) {
+    arr vx = h->pw[1].w[GPI_VX], vz = h->pw[1].w[GPI_VZ], dpdx = h->pw[0].w[GPI_DPDX], dpdz = h->pw[0].w[GPI_DPDZ];
+    arr dbx = h->bornc[1], dbz = h->bornc[2];
+    OMP_FOR
+    for (int ix = 1; ix <= dpdx.n[2]; ix++) for (int iz = 1; iz <= dpdx.n[0]; iz++)
+        A2(vx, iz + 1, ix + 1) = A2(vx, iz + 1, ix + 1) + A2(dbx, iz, ix) * A2(dpdx, iz, ix);
+    OMP_FOR
+    for (int ix = 1; ix <= dpdz.n[2]; ix++) for (int iz = 1; iz <= dpdz.n[0]; iz++)
+        A2(vz, iz + 1, ix + 1) = A2(vz, iz + 1, ix + 1) + A2(dbz, iz, ix) * A2(dpdz, iz, ix);
+}
+/* add_born_sources_stress! (propagate.jl:226): @all(p2) = @all(p2) + (@all(dvxdx1) + @all(dvzdz1)) * @all(d dtK) */
+static void born_stress(orc_handle* h) {
+    arr p = h->pw[1].w[GPI_P], dvxdx = h->pw[0].w[GPI_DVXDX], dvzdz = h->pw[0].w[GPI_DVZDZ], dK = h->bornc[0];
+    OMP_FOR
+    for (int ix = 1; ix <= p.n[2]; ix++) for (int iz = 1; iz <= p.n[0]; iz++)
+        A2(p, iz, ix) = A2(p, iz, ix) + (A2(dvxdx, iz, ix) + A2(dvzdz, iz, ix)) * A2(dK, iz, ix);
+}
+
 int orc_run(orc_handle* h, int mode, int activepw, int src_flags) {
     double t0 = now_s();
+    const int born = (mode & GPI_RUN_BORN) != 0, unshifted = (mode & GPI_RUN_UNSHIFTED_RHO) != 0;
+    mode &= ~(GPI_RUN_BORN | GPI_RUN_UNSHIFTED_RHO);
+    if (born && (h->nd != 2 || h->c.physics != GPI_ACOUSTIC || h->c.npw != 2 || (activepw & 3) != 3 || mode == GPI_MODE_ADJOINT || !h->born_ready)) {
+        snprintf(h->err, sizeof h->err, "FD-Born needs a 2-D acoustic experiment, both wavefields active, a forward mode and orc_update_born"); return 1;
+    }
     int nt = h->c.nt;
     const int recp[1] = {GPI_P}, recv[3] = {GPI_VX, GPI_VY, GPI_VZ};
     if (mode == GPI_MODE_FORWARD_SAVE && !h->c.store_boundary) {
@@ -785,12 +841,14 @@ int orc_run(orc_handle* h, int mode, int activepw, int src_flags) {
             for (int ipw = 0; ipw < h->c.npw; ipw++) if (activepw & (1 << ipw)) update_dstress(h, &h->pw[ipw]);
             for (int ipw = 0; ipw < h->c.npw; ipw++) if (activepw & (1 << ipw)) update_v(h, &h->pw[ipw]);
             add_velocity_source(h, it, issp, activepw, src_flags);
+            if (born) born_velocity(h);
             record(h, it, issp, activepw, recv, 3);
             for (int ipw = 0; ipw < h->c.npw; ipw++) if (activepw & (1 << ipw)) update_dv(h, &h->pw[ipw]);
             for (int ipw = 0; ipw < h->c.npw; ipw++) if (activepw & (1 << ipw)) update_stress(h, &h->pw[ipw]);
             add_stress_source(h, it, issp, activepw, src_flags);
+            if (born) born_stress(h);
             if (mode == GPI_MODE_FORWARD_SAVE) boundary_save(h, it, issp);
-            if (mode == GPI_MODE_ADJOINT && h->c.npw == 2) compute_gradient(h, issp);
+            if (mode == GPI_MODE_ADJOINT && h->c.npw == 2) compute_gradient(h, issp, unshifted);
             if (h->c.nsnaps > 0 && h->itsnaps)
                 for (int k = 0; k < h->c.nsnaps; k++) if (h->itsnaps[k] == it)
                     for (int ipw = 0; ipw < h->c.npw; ipw++) if ((activepw & (1 << ipw)) && h->pw[ipw].ss[issp].usnaps)
@@ -922,6 +980,8 @@ int orc_destroy(orc_handle* h) {
     if (!h) return 0;
     for (int p = 0; p < GPI_NPARAM; p++) { arr_free(&h->mod[p]); arr_free(&h->gradients[p]); }
     for (int d = 0; d < DM_N; d++) arr_free(&h->dmod[d]);
+    for (int p = 0; p < GPI_NPARAM; p++) arr_free(&h->modp[p]);
+    for (int q = 0; q < 3; q++) arr_free(&h->bornc[q]);
     for (int f = 0; f < GPI_NFIELD; f++) { free(h->pa[f]); free(h->pb[f]); free(h->pk[f]); }
     for (int ipw = 0; ipw < h->c.npw; ipw++) {
         pw_t* pw = &h->pw[ipw];
@@ -955,6 +1015,17 @@ int orc_get_medium(orc_handle* h, int p, REAL* out) {
     memcpy(out, h->mod[p].d, h->mod[p].len * sizeof(REAL)); return 0;
 }
 int orc_update_dmod(orc_handle* h) { update_dmod(h); return 0; }
+int orc_set_medium_pert(orc_handle* h, int p, const REAL* a) {
+    CHECK(h->nd == 2 && h->c.physics == GPI_ACOUSTIC && (p == GPI_INVK || p == GPI_RHO), "FD-Born: 2-D acoustic invK | rho only");
+    if (!h->modp[p].d) { int n[3] = {h->nz, 1, h->nx}; CHECK(!arr_alloc(&h->modp[p], n), "out of memory"); }
+    memcpy(h->modp[p].d, a, h->modp[p].len * sizeof(REAL)); h->born_ready = 0; return 0;
+}
+int orc_update_born(orc_handle* h) {
+    CHECK(h->nd == 2 && h->c.physics == GPI_ACOUSTIC && h->c.npw == 2 && h->modp[GPI_INVK].d && h->modp[GPI_RHO].d, "FD-Born: set both perturbations first");
+    const int dm[3] = {DM_DTK, DM_BX, DM_BZ};
+    for (int q = 0; q < 3; q++) if (!h->bornc[q].d) { CHECK(!arr_alloc(&h->bornc[q], h->dmod[dm[q]].n), "out of memory"); }
+    update_born(h); h->born_ready = 1; return 0;
+}
 int orc_set_pml(orc_handle* h, int f, const REAL* a, const REAL* b, const REAL* kI) {
     CHECK(f >= GPI_NWAVEFIELD && f < GPI_NFIELD && h->pa[f], "not a derivative field of this physics");
     size_t nb = 2 * h->c.npml * sizeof(REAL);

@@ -108,6 +108,12 @@ class OracleEngine:
     def update_dmod(self):
         self._ck(self.lib.orc_update_dmod(self.h))
 
+    def set_medium_pert(self, name, a):
+        a = self._a(a); self._ck(self.lib.orc_set_medium_pert(self.h, E.PARAM[name], self._p(a)))
+
+    def update_born(self):
+        self._ck(self.lib.orc_update_born(self.h))
+
     def set_pml(self, dfield, a, b, kI):
         a, b, kI = self._a(a), self._a(b), self._a(kI)
         self._ck(self.lib.orc_set_pml(self.h, E.FIELD[dfield], self._p(a), self._p(b), self._p(kI)))
@@ -125,10 +131,10 @@ class OracleEngine:
         wf = self._a(w)
         self._ck(self.lib.orc_set_wavelets(self.h, ipw, issp, E.FIELD[field], w.shape[1], self._p(wf)))
 
-    def run(self, mode, activepw=(1,), src_flags=(True,)):
+    def run(self, mode, activepw=(1,), src_flags=(True,), born=False, unshifted_rho=False):
         am = sum(1 << (p - 1) for p in activepw)
         sm = sum(1 << i for i, f in enumerate(src_flags) if f)
-        self._ck(self.lib.orc_run(self.h, E.MODE[mode], am, sm))
+        self._ck(self.lib.orc_run(self.h, E.MODE[mode] | (E.RUN_BORN if born else 0) | (E.RUN_UNSHIFTED_RHO if unshifted_rho else 0), am, sm))
 
     def advance(self, it0, nsteps):
         self._ck(self.lib.orc_advance(self.h, int(it0), int(nsteps)))

@@ -166,3 +166,67 @@ def test_gradient_vs_finite_differences(G, O):
         print(f"d loss / d {name}: adjoint {ad:.6e}  finite-difference {fd:.6e}  ratio {ad / fd:.4f}")
         assert np.sign(ad) == np.sign(fd)
         assert abs(ad / fd - 1) < 0.1
+
+
+# --------------------------------------------------------------------------------------------------
+# FD-Born (src/fdtd/born.jl, test/fwi/born_map.jl): first-order accuracy, linearity, dot test
+# --------------------------------------------------------------------------------------------------
+def _born_kw(G, sfield="p", rfields=("p", "vz"), nt=700):
+    from geophyinv_jl_b200.host import gallery
+    return gallery.c1_acou2d_homo(nz=51, nx=57, nt=nt, nr=10, sfield=sfield, rfields=rfields, fq=8.0, dt=1.8e-3)
+
+
+def test_born_is_first_order_in_the_perturbation(G, O):
+    """The scattered data of `update!(pa, medium, medium_pert)` equal full modelling in the perturbed medium minus the
+    background up to O(eps^2): the relative error halves with eps (pins sign and scaling of the scattering sources)."""
+    errs = []
+    for eps in (0.01, 0.005):
+        kw = _born_kw(G)
+        m0 = kw["medium"]
+        mp = m0.copy()
+        mp.vp[20:30, 24:34] *= np.float32(1 + eps)
+        mp.rho[20:30, 24:34] *= np.float32(1 + eps)
+        pb = O.OraclePFdtd64(G.FdtdAcoustic(born=True), **kw)
+        G.update(pb, m0, mp)
+        pb.update()
+        p0 = O.OraclePFdtd64(G.FdtdAcoustic(), **kw); p0.update()
+        p1 = O.OraclePFdtd64(G.FdtdAcoustic(), **{**kw, "medium": mp}); p1.update()
+        for f in ("p", "vz"):
+            dd = p1.c.data[0][0].d[f].astype(np.float64) - p0.c.data[0][0].d[f].astype(np.float64)
+            db = pb.c.data[1][0].d[f].astype(np.float64)
+            assert np.linalg.norm(dd) > 0
+            errs.append(np.linalg.norm(db - dd) / np.linalg.norm(dd))
+    assert max(errs[:2]) < 0.1 and max(errs[2:]) < 0.05
+    assert errs[2] < 0.6 * errs[0] and errs[3] < 0.6 * errs[1]
+
+
+def test_born_linear_map_linearity_and_dot_test(G, O):
+    """test/fwi/born_map.jl: F(x1 + x2) == F x1 + F x2 and <y, F x> == <x, F' y> (rtol 1e-5 upstream)."""
+    kw = _born_kw(G, sfield="vz", rfields=("vz",), nt=500)
+    rng = np.random.default_rng(5)
+    m = kw["medium"]
+    m.vp *= (1 + 0.03 * rng.standard_normal(m.vp.shape)).astype(np.float32)
+    m.rho *= (1 + 0.03 * rng.standard_normal(m.rho.shape)).astype(np.float32)
+    pa = O.OraclePFdtd64(G.FdtdAcoustic("forward_save", born=True), **kw)
+    F = G.LinearMap(pa)
+    n = pa.c.gradients["invK"].shape
+
+    def randm():
+        a = np.zeros(n, np.float32, order="F"); b = np.zeros(n, np.float32, order="F")
+        inner = (slice(G.NPML + 9, n[0] - G.NPML - 9), slice(G.NPML + 9, n[1] - G.NPML - 9))     # away from sources / receivers, see LinearMap
+        a[inner] = rng.standard_normal(a[inner].shape) * 1e-12          # invK ~ 6e-11
+        b[inner] = rng.standard_normal(b[inner].shape) * 25.0           # rho ~ 2500
+        return np.concatenate([a.ravel(order="F"), b.ravel(order="F")])
+
+    x1, x2 = randm(), randm()
+    d1, d2, d12 = (F @ x1).astype(np.float64), (F @ x2).astype(np.float64), (F @ (x1 + x2)).astype(np.float64)
+    assert np.sum(d12 ** 2) > 0
+    assert np.sum((d12 - (d1 + d2)) ** 2) / np.sum(d12 ** 2) < 1e-12      # records are stored in Float32
+    y = rng.standard_normal(F.shape[0]).astype(np.float32)
+    a = float(np.dot(y.astype(np.float64), d1))
+    b = float(np.dot(x1.astype(np.float64), (F.T @ y).astype(np.float64)))
+    assert abs(a - b) <= 1e-5 * abs(a), (a, b)
+    # the reference's own imaging (one-cell shift in combine_gmodrho!, opposite sign) is not the transpose
+    g_ref = G.adjoint_map(np.zeros(F.shape[1], np.float32), y, pa, exact=False)
+    b_ref = -float(np.dot(x1.astype(np.float64), g_ref.astype(np.float64)))
+    assert abs(a - b_ref) > 1e-3 * abs(a)

@@ -223,3 +223,54 @@ def test_fwi_gradient_acoustic2d(G, O):
     # stacked raw gradients on the extended grid too
     for name in ("invK", "rho"):
         assert rel_l2(pg.engine.get_gradient(name), po.engine.get_gradient(name)) <= GRAD_TOL
+
+
+# --------------------------------------------------------------------------------------------------
+# FD-Born: scattering sources pw 1 -> pw 2, LinearMap
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sfield,rfields", [("p", ["p", "vx"]), ("vz", ["vz"])])
+def test_born_records_match_oracle(G, O, sfield, rfields):
+    from geophyinv_jl_b200.host import gallery
+    kw = gallery.c1_acou2d_homo(nz=61, nx=73, nt=400, nr=12, sfield=sfield, rfields=rfields, fq=10.0, dt=1.8e-3, nss=3)
+    m0 = kw["medium"]
+    rng = np.random.default_rng(2)
+    m0.vp *= (1 + 0.02 * rng.standard_normal(m0.vp.shape)).astype(np.float32)
+    mp = m0.copy()
+    mp.vp[24:36, 30:44] *= np.float32(1.02)
+    mp.rho[20:30, 28:40] *= np.float32(0.97)
+    pg = G.SeisForwExpt(G.FdtdAcoustic(born=True), **kw, shot_batch=2)
+    po = O.OraclePFdtd(G.FdtdAcoustic(born=True), **kw)
+    for p in (pg, po):
+        G.update(p, m0, mp)
+        p.update()
+    worst, exact = compare_records(pg, po, ipw=1)
+    print(f"FD-Born {sfield}->{rfields}: rel-L2 {worst:.3e}, bit-exact {exact}")
+    assert worst <= REC_TOL
+    assert max(np.abs(pg.c.data[1][0].d[f]).max() for f in rfields) > 0
+
+
+def test_born_linear_map_dot_test(G, O):
+    """<y, F x> == <x, F' y> on the GPU (Float32 arithmetic; upstream's gate is rtol 1e-5 in Float64) and the
+    unshifted imaging matches the oracle."""
+    from geophyinv_jl_b200.host import gallery
+    kw = gallery.c1_acou2d_homo(nz=51, nx=57, nt=500, nr=10, sfield="vz", rfields=("vz",), fq=8.0, dt=1.8e-3)
+    pg = G.SeisForwExpt(G.FdtdAcoustic("forward_save", born=True), **kw)
+    po = O.OraclePFdtd(G.FdtdAcoustic("forward_save", born=True), **kw)
+    Fg, Fo = G.LinearMap(pg), G.LinearMap(po)
+    n = pg.c.gradients["invK"].shape
+    rng = np.random.default_rng(9)
+    a0 = np.zeros(n, np.float32, order="F"); b0 = np.zeros(n, np.float32, order="F")
+    inner = (slice(G.NPML + 9, n[0] - G.NPML - 9), slice(G.NPML + 9, n[1] - G.NPML - 9))     # away from sources / receivers, see LinearMap
+    a0[inner] = rng.standard_normal(a0[inner].shape) * 1e-12
+    b0[inner] = rng.standard_normal(b0[inner].shape) * 25.0
+    x = np.concatenate([a0.ravel(order="F"), b0.ravel(order="F")])
+    y = rng.standard_normal(Fg.shape[0]).astype(np.float32)
+    dg, do = Fg @ x, Fo @ x
+    assert rel_l2(dg, do) <= REC_TOL
+    gg, go = Fg.T @ y, Fo.T @ y
+    assert rel_l2(gg, go) <= GRAD_TOL
+    a = float(np.dot(y.astype(np.float64), dg.astype(np.float64)))
+    b = float(np.dot(x.astype(np.float64), gg.astype(np.float64)))
+    print(f"Born dot test (GPU, Float32): <y,Fx> = {a:.8e}, <x,F'y> = {b:.8e}, rel {abs(a - b) / abs(a):.2e}; "
+          f"F rel-L2 vs oracle {rel_l2(dg, do):.1e}, F' {rel_l2(gg, go):.1e}")
+    assert abs(a - b) <= 1e-4 * abs(a)
