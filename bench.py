@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline measurement of the B200 FDTD engine (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4|c3small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4|c5|c3small|c5small]
 
 Workload at N=1 (default, `c3`): BASELINE config 3 -- 3-D isotropic elastic 256^3 (+41-cell CPML on six
 faces = 338^3 extended cells), one :vz source, 64 receivers, 2000 time steps.  One bench "step" is one
@@ -412,6 +412,83 @@ def run_c5(args):
         dist.destroy_process_group()
 
 
+def run_c4(args):
+    """BASELINE config 4: 2-D acoustic FWI gradient (forward_save + adjoint + imaging) over the supersources of
+    every rank (32 in total at N = 1; `--nss` per GPU otherwise), one NCCL sum all-reduce of the gradient over NVLink.
+    A bench step = one `gradient!` call (func_grad.jl:11-49) through the host API: model vector in, gradient out."""
+    import torch
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    import geophyinv_jl_b200 as G
+    from geophyinv_jl_b200.host import dist as D, gallery
+    dist = D.init_process_group("nccl")
+    nss_per = args.nss or 32
+    nt = args.nt or 3000
+    kw, true = gallery.c4_fwi2d(nt=nt, nss=nss_per * world)
+    t0 = time.time()
+    pa = G.SeisForwExpt(G.FdtdAcoustic("forward_save"), **kw, nworker=world, rank=rank, device=local_rank)
+    D.attach_nccl(pa, dist)
+    t_build = time.time() - t0
+    n_ex = [len(g) for g in pa.c.exgrid]
+    # "observed" data: the +5 % box, modelled once (not timed)
+    pt = G.SeisForwExpt(G.FdtdAcoustic(), **{**kw, "medium": true}, nworker=world, rank=rank, device=local_rank)
+    pt.update()
+    dobs = [d.copy() for d in pt.c.data[0]]
+    del pt
+    m = pa.get_modelvector()
+    g = np.zeros_like(m)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        G.gradient(g, m, dobs, pa)
+    sampler = ClockSampler(local_rank)
+    barrier(); sampler.start()
+    e0 = time.perf_counter()
+    dev_ms = launches = 0.0
+    for _ in range(args.steps):
+        G.gradient(g, m, dobs, pa)
+        # device time of the two passes of this call (forward_save, adjoint), from the engine's CUDA events
+        dev_ms += pa.last_run_ms
+        launches += pa.last_launches
+    barrier()
+    e2e_s = allmax(time.perf_counter() - e0)
+    clocks = sampler.stop()
+    dev_ms = allmax(dev_ms)
+    cells = float(np.prod(n_ex)) * nt * nss_per * world * 3          # forward_save: 1 wavefield; adjoint: 2
+    if rank == 0:
+        peak, peak_kind = measured_peak()
+        gb = cells / 3 * (48 + 112) / 1e9                             # SURVEY 8d: 48 B forward, 112 B adjoint step per cell
+        print(json.dumps({
+            "metric": "Gcell-updates/s", "value": cells * args.steps / (dev_ms * 1e-3) / 1e9, "unit": "Gcell-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C4: 2-D acoustic FWI gradient, {n_ex} extended cells, {nt} steps, {nss_per} supersources per GPU, NCCL gradient all-reduce",
+                       "extended_grid": n_ex, "time_steps_per_step": nt, "supersources_per_gpu": nss_per, "parallelism": f"shots sharded x{world}",
+                       "l2": "16 resident shots x 3 wavefields exceed the 126 MB L2"},
+            "e2e": {"value": cells * args.steps / e2e_s / 1e9, "unit": "Gcell-updates/s", "h2d_bytes_per_step": int(m.nbytes), "d2h_bytes_per_step": int(g.nbytes),
+                    "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "forward_save + adjoint passes (k_vel2v, k_stress2v, k_grad2d, boundary, tp copy)",
+                         "achieved": gb * args.steps / (dev_ms * 1e-3), "peak": peak, "unit": "GB/s", "frac": gb * args.steps / (dev_ms * 1e-3) / peak / world,
+                         "peak_source": peak_kind, "traffic": None, "note": "whole-pass figure: algorithmic bytes of SURVEY 8d (48 + 112 B per cell-step) / device time, per GPU"},
+            "cpu_baseline": None, "clocks": clocks, "build_s": t_build,
+            "gradients_per_hour": 3600.0 * args.steps / e2e_s, "shots_per_hour": 3600.0 * nss_per * world * args.steps / e2e_s}), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -422,11 +499,14 @@ def main():
     ap.add_argument("--nt", type=int, default=None, help="override the number of time steps per bench step (debug)")
     ap.add_argument("--cpu-steps", type=int, default=8, help="time steps per CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nss", type=int, default=None, help="supersources per GPU (c4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload in ("c5", "c5small"):
         run_c5(args)
+    elif args.workload == "c4":
+        run_c4(args)
     else:
         run_ours(args)
 

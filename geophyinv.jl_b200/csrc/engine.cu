@@ -372,13 +372,15 @@ int launch_step3t(gpi_handle* h, const StepArgs& a) {
     const int nctas = std::max(1, std::min(sc.ntiles, h->tma3_ctas > 0 ? h->tma3_ctas : T3_MINB * h->num_sms));
     // The shell touches cells no tile touches and reads only fields this half step does not write, so it runs
     // beside the persistent tile kernel on a side stream (it needs no shared memory and fits next to the two
-    // resident tile CTAs of an SM): fork, shell, join.
+    // resident tile CTAs of an SM).  The tile kernel is launched FIRST: its tiles are assigned statically, so
+    // every CTA must become resident at once -- shell blocks that got to the SMs earlier would delay some of
+    // them by the shell's whole duration.
     const int nlines = sc.nsp * g.ny1 + (sc.ihi - sc.ilo + 1) * sc.nsr;
     CU(h, cudaEventRecord(h->ev_fork, h->stream));
+    t3::k_step3t<KIND><<<nctas, t3::NTHREADS, t3::smem_bytes(KIND), h->stream>>>(g, a, sc, set->d[KIND]);
     CU(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     t3::k_shell3<KIND><<<nlines, 128, 0, h->side>>>(g, a, sc);
     CU(h, cudaEventRecord(h->ev_join, h->side));
-    t3::k_step3t<KIND><<<nctas, t3::NTHREADS, t3::smem_bytes(KIND), h->stream>>>(g, a, sc, set->d[KIND]);
     CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->timers.launches += 1;
     return 0;

@@ -404,7 +404,11 @@ class PFdtd:
                     for issp, iss in enumerate(self.local):
                         nr = c.ageom[ipw - 1][iss].nr
                         c.data[ipw - 1][iss].d[rf][...] = self.engine.get_records(ipw - 1, issp, rf, nr)
-        return self.engine.timers()
+        t = self.engine.timers()
+        # accumulated over the passes of one lossvalue / gradient! call (they reset it)
+        self.last_run_ms = getattr(self, "last_run_ms", 0.0) + t.get("run_ms", 0.0)
+        self.last_launches = getattr(self, "last_launches", 0.0) + t.get("launches", 0.0)
+        return t
 
     # multi-GPU plumbing: the ncclUniqueId travels through whatever the host already has
     def init_nccl(self, uid: Optional[bytes], nranks: int):
@@ -490,6 +494,7 @@ def gradient(g: np.ndarray, m, dobs, pa: PFdtd, mparams=None) -> float:
     zeroed that container -- an upstream slip we do not copy)."""
     c = pa.c
     mparams = c.mparams if mparams is None else mparams
+    pa.last_run_ms = pa.last_launches = 0.0
     pa.update_model(m, mparams)
     mode_save = c.attrib_mod.mode
     c.attrib_mod.mode = "forward_save"
