@@ -158,6 +158,7 @@ struct gpi_handle {
     std::vector<ShotData> shots[2];
     std::vector<int32_t> itsnaps;
     PostDesc *post_v = nullptr, *post_s = nullptr, *h_post_v = nullptr, *h_post_s = nullptr;
+    float** bnd_table = nullptr;        // boundary stores of the resident batch, [b][field][axis]
     float* stage = nullptr;  size_t stage_floats = 0;       // pinned host staging
     float* dscratch = nullptr;  size_t dscratch_floats = 0; // device scratch (raw interior medium before padding)
     gpi_timers timers{};
@@ -445,24 +446,53 @@ long long bnd_slot_floats(const gpi_handle* h, int axis) {
     if (axis == 1) return (long long)g.pz * nb2 * g.nx1;
     return (long long)g.nx1 * g.ny1 * nb2;
 }
-int launch_boundary(gpi_handle* h, bool save, int f, float* field, float* store, int axis) {
+// one launch for the whole batch: every stored field, axis and plane (k_boundary)
+int launch_boundary(gpi_handle* h, bool save, int nb, int slot /* 0-based time slot */) {
     const Geom& g = h->g;
-    int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
-    field_shape(h->nd, f, n, sh, off);
-    const int minbit = axis == 0 ? ZMIN : axis == 1 ? YMIN : XMIN;
-    const int np = (h->c.pml_faces & minbit) ? h->c.npml : 0;       // min-face flag also used for the max side (boundary.jl:24,33)
-    const int nb = h->c.nbound;
-    const int lo = np + off[axis], hi = sh[axis] - np - nb + off[axis];
-    if (hi < lo) FAIL(h, "grid too small for the boundary store along axis %d", axis);
-    dim3 blk, grd;
-    if (axis == 2)      { blk = dim3(128, 1, 1); grd = dim3((g.pz + 127) / 128, g.ny1, 2 * nb); }
-    else if (axis == 1) { blk = dim3(128, 1, 1); grd = dim3((g.pz + 127) / 128, 2 * nb, g.nx1); }
-    else                { blk = dim3(128, 1, 1); grd = dim3((g.nx1 + 127) / 128, g.ny1, 2 * nb); }
-    const int k0 = off[0], j0 = off[1], i0 = off[2];
-    const int nk = off[0] + sh[0], nj = off[1] + sh[1], ni = off[2] + sh[2];
-    if (save) k_boundary<1><<<grd, blk, 0, h->stream>>>(g, field, store, axis, lo, hi, nb, nk, nj, ni, k0, j0, i0);
-    else      k_boundary<0><<<grd, blk, 0, h->stream>>>(g, field, store, axis, lo, hi, nb, nk, nj, ni, k0, j0, i0);
+    BndArgs a; memset(&a, 0, sizeof a);
+    int bf[3]; a.nf = boundary_fields(h, bf);
+    a.nbound = h->c.nbound;
+    a.naxes = 0;
+    for (int q = 2; q >= 0; q--) if (!(q == 1 && h->nd == 2)) a.axes[a.naxes++] = q;
+    int umax = 0, vmax = 0;
+    for (int i = 0; i < a.nf; i++) {
+        int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
+        field_shape(h->nd, bf[i], n, sh, off);
+        BndField& F = a.f[i];
+        F.f0 = wf_ptr(h, h->W, 0, 0, bf[i]);
+        for (int ia = 0; ia < a.naxes; ia++) {
+            const int axis = a.axes[ia];
+            const int minbit = axis == 0 ? ZMIN : axis == 1 ? YMIN : XMIN;
+            const int np = (h->c.pml_faces & minbit) ? h->c.npml : 0;   // min-face flag also used for the max side (boundary.jl:24,33)
+            F.lo[axis] = np + off[axis]; F.hi[axis] = sh[axis] - np - a.nbound + off[axis];
+            if (F.hi[axis] < F.lo[axis]) FAIL(h, "grid too small for the boundary store along axis %d", axis);
+        }
+        F.k0 = off[0]; F.j0 = off[1]; F.i0 = off[2];
+        F.nk = off[0] + sh[0]; F.nj = off[1] + sh[1]; F.ni = off[2] + sh[2];
+    }
+    for (int ia = 0; ia < a.naxes; ia++) {
+        const int axis = a.axes[ia];
+        umax = std::max(umax, axis == 0 ? g.nx1 : g.pz);
+        vmax = std::max(vmax, axis == 1 ? g.nx1 : g.ny1);
+        a.slot_off[axis] = (long long)slot * bnd_slot_floats(h, axis);
+    }
+    a.stores = h->bnd_table;
+    a.wstride = h->bstride;
+    dim3 blk(128), grd((umax + 127) / 128, vmax, 2 * a.nbound * a.naxes * a.nf * nb);
+    if (save) k_boundary<1><<<grd, blk, 0, h->stream>>>(g, a);
+    else      k_boundary<0><<<grd, blk, 0, h->stream>>>(g, a);
     h->timers.launches += 1;
+    return 0;
+}
+// device table of the boundary stores of the batch's shots: [b][field][axis]
+int build_bnd_table(gpi_handle* h, int shot0, int nb) {
+    int bf[3]; const int nbf = boundary_fields(h, bf);
+    std::vector<float*> t((size_t)nb * nbf * 3, nullptr);
+    for (int b = 0; b < nb; b++) for (int i = 0; i < nbf; i++) for (int q = 0; q < 3; q++)
+        t[((size_t)b * nbf + i) * 3 + q] = h->shots[0][shot0 + b].bnd[bf[i]][q];
+    if (!h->bnd_table) CU(h, cudaMalloc((void**)&h->bnd_table, (size_t)h->B * 9 * sizeof(float*)));
+    CU(h, cudaMemcpyAsync(h->bnd_table, t.data(), t.size() * sizeof(float*), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));      // `t` is a pageable temporary
     return 0;
 }
 
@@ -728,7 +758,7 @@ extern "C" int gpi_destroy(gpi_handle* h) {
         }
         for (auto p : s.usnaps) cudaFree(p);
     }
-    cudaFree(h->post_v); cudaFree(h->post_s);
+    cudaFree(h->post_v); cudaFree(h->post_s); cudaFree(h->bnd_table);
     if (h->h_post_v) cudaFreeHost(h->h_post_v);
     if (h->h_post_s) cudaFreeHost(h->h_post_s);
     if (h->stage) cudaFreeHost(h->stage);
@@ -1158,6 +1188,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             }
         }
         if (build_post(h, shot0, nb, activepw, src_flags)) return 1;
+        if (mode != GPI_MODE_FORWARD && build_bnd_table(h, shot0, nb)) return 1;
         const bool do_post_v = any_post(h->h_post_v, nb, true);
         const bool inj_s = any_post(h->h_post_s, nb, false), rec_s = any_post(h->h_post_s, nb, true);
         StepArgs args[2];
@@ -1171,14 +1202,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                 // save_tp! (save_tp.jl:5-12): one device copy of every wavefield of the batch
                 CU(h, cudaMemcpyAsync(h->TP, h->W, (size_t)nb * h->bstride * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
                 // boundary_force!(nt - it + 1) on pw 1 (propagate.jl:188), x then (y) then z
-                for (int b = 0; b < nb; b++) for (int i = 0; i < nbf; i++) {
-                    const int axes[3] = {2, 1, 0};
-                    for (int ia = 0; ia < 3; ia++) {
-                        const int q = axes[ia]; if (q == 1 && h->nd == 2) continue;
-                        float* st = h->shots[0][shot0 + b].bnd[bf[i]][q] + (size_t)(nt - it) * bnd_slot_floats(h, q);
-                        if (launch_boundary(h, false, bf[i], wf_ptr(h, h->W, b, 0, bf[i]), st, q)) return 1;
-                    }
-                }
+                if (launch_boundary(h, false, nb, nt - it)) return 1;
             }
             const bool sample = h->sample_every > 0 && (it % h->sample_every) == 0;
             for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], true, nb, sample && ipw == 0);
@@ -1201,13 +1225,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                 h->timers.launches += 1;
             }
             if (exchange_halos(h, 0)) return 1;
-            if (mode == GPI_MODE_FORWARD_SAVE) {
-                for (int b = 0; b < nb; b++) for (int i = 0; i < nbf; i++) for (int q = 0; q < 3; q++) {
-                    if (q == 1 && h->nd == 2) continue;
-                    float* st = h->shots[0][shot0 + b].bnd[bf[i]][q] + (size_t)(it - 1) * bnd_slot_floats(h, q);
-                    if (launch_boundary(h, true, bf[i], wf_ptr(h, h->W, b, 0, bf[i]), st, q)) return 1;
-                }
-            }
+            if (mode == GPI_MODE_FORWARD_SAVE && launch_boundary(h, true, nb, it - 1)) return 1;
             if (grad) {
                 dim3 blk = h->blk2, grd = grid_for(h, blk, nb);
                 k_grad2d<<<grd, blk, 0, h->stream>>>(g,

@@ -544,24 +544,43 @@ __global__ void k_post(const Geom g, const PostDesc* __restrict__ descs, int it 
 // PML, saved negated in :forward_save and forced back in :adjoint.  Store layout (engine's own):
 // axis x: [6][ny1][pz] ; axis y: [nx1][6][pz] ; axis z: [6][ny1][nx1].
 // ------------------------------------------------------------------------------------------------
+// One launch covers every (shot of the batch, stored field, axis, plane): blockIdx.z folds them, so a time step
+// of :forward_save / :adjoint costs one boundary launch instead of (shots x fields x axes).  The planes of
+// different axes overlap at the corners of the box; a save reads the same field there and a force writes the same
+// saved value, so the reference's x, (y,) z call order does not matter.
+struct BndField {
+    float* f0;                // batch slot 0 of the field
+    int lo[3], hi[3];         // first unified index of the min / max triple along each axis
+    int k0, j0, i0, nk, nj, ni;   // field extents in unified coordinates [lower, upper)
+};
+struct BndArgs {
+    int nf, naxes, nbound;
+    int axes[3];              // axes that exist (2-D: z, x)
+    BndField f[3];
+    float* const* stores;     // [b][field][axis 0..2]: the shot's store of nt slots
+    long long slot_off[3];    // (slot index) x (floats per slot) per axis for this time step
+    long long wstride;        // floats between batch slots of the wavefield set
+};
 template <int SAVE>
-__global__ void k_boundary(const Geom g, float* __restrict__ field, float* __restrict__ store, int axis,
-                           int lo, int hi /* first unified index of the min / max triple */, int nbound,
-                           int nk, int nj, int ni /* field extents (unified upper bounds, exclusive) */,
-                           int k0, int j0, int i0 /* field lower bounds */) {
-    // thread space: (k or plane, j, i) over the store
-    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t1 = blockIdx.y * blockDim.y + threadIdx.y;
-    const int t2 = blockIdx.z;
-    int k, j, i, p;   // p = plane 0..2*nbound-1
+__global__ void k_boundary(const Geom g, const BndArgs a) {
+    int z = blockIdx.z;
+    const int p = z % (2 * a.nbound); z /= 2 * a.nbound;      // plane 0..2*nbound-1
+    const int ia = z % a.naxes; z /= a.naxes;
+    const int fi = z % a.nf; const int b = z / a.nf;
+    const int axis = a.axes[ia];
+    const BndField& F = a.f[fi];
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = blockIdx.y;
+    const int q = p < a.nbound ? F.lo[axis] + p : F.hi[axis] + p - a.nbound;
+    int k, j, i;
     long long si;
-    if (axis == 2)      { k = t0; j = t1; p = t2; if (k >= g.pz || j >= g.ny1 || p >= 2 * nbound) return; i = (p < nbound ? lo + p : hi + p - nbound); si = (long long)k + (long long)g.pz * (j + (long long)g.ny1 * p); }
-    else if (axis == 1) { k = t0; p = t1; i = t2; if (k >= g.pz || p >= 2 * nbound || i >= g.nx1) return; j = (p < nbound ? lo + p : hi + p - nbound); si = (long long)k + (long long)g.pz * (p + 2LL * nbound * i); }
-    else                { i = t0; j = t1; p = t2; if (i >= g.nx1 || j >= g.ny1 || p >= 2 * nbound) return; k = (p < nbound ? lo + p : hi + p - nbound); si = (long long)i + (long long)g.nx1 * (j + (long long)g.ny1 * p); }
-    if (k < k0 || k >= nk || j < j0 || j >= nj || i < i0 || i >= ni) return;
-    const long long c = uidx(g, k, j, i);
-    if (SAVE) store[si] = __fmul_rn(field[c], -1.0f);     // rmul!(b, -1)
-    else      field[c] = store[si];
+    if (axis == 2)      { k = t0; j = t1; i = q; if (k >= g.pz || j >= g.ny1) return; si = (long long)k + (long long)g.pz * (j + (long long)g.ny1 * p); }
+    else if (axis == 1) { k = t0; i = t1; j = q; if (k >= g.pz || i >= g.nx1) return; si = (long long)k + (long long)g.pz * (p + 2LL * a.nbound * i); }
+    else                { i = t0; j = t1; k = q; if (i >= g.nx1 || j >= g.ny1) return; si = (long long)i + (long long)g.nx1 * (j + (long long)g.ny1 * p); }
+    if (k < F.k0 || k >= F.nk || j < F.j0 || j >= F.nj || i < F.i0 || i >= F.ni) return;
+    float* field = F.f0 + (long long)b * a.wstride + uidx(g, k, j, i);
+    float* store = a.stores[(b * a.nf + fi) * 3 + axis] + a.slot_off[axis] + si;
+    if (SAVE) *store = __fmul_rn(*field, -1.0f);     // rmul!(b, -1)
+    else      *field = *store;
 }
 
 // ------------------------------------------------------------------------------------------------

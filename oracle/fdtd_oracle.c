@@ -819,7 +819,7 @@ int orc_run(orc_handle* h, int mode, int activepw, int src_flags) {
     if (mode == GPI_MODE_FORWARD_SAVE && !h->c.store_boundary) {
         snprintf(h->err, sizeof h->err, "forward_save needs store_boundary=1 at construction (fdtd.jl:445-455)"); return 1;
     }
-    if (mode == GPI_MODE_ADJOINT && !(h->c.physics == GPI_ACOUSTIC && h->nd == 2) && h->c.npw == 2) {
+    if (mode == GPI_MODE_ADJOINT && !(h->c.physics == GPI_ACOUSTIC && h->nd == 2) && h->c.npw == 2 && (activepw & 2)) {
         snprintf(h->err, sizeof h->err, "adjoint gradient exists upstream only for 2-D acoustic (gradient.jl:31)"); return 1;
     }
     for (int issp = 0; issp < h->c.nshots; issp++) {
