@@ -25,7 +25,8 @@ using namespace gpi;
 namespace {
 
 // ---- field metadata (fields.jl:92-671 reduced to node types, see kernels.cuh) -------------------
-// per axis (z,y,x): 'I' tauii nodes (len n, offset 0), 'V' velocity nodes (n+1, 0), 'H' half (n-1, 1), 'J' inner (n-2, 1)
+// per axis (z,y,x), O = order - 1, h = (order - 2) / 2; (length, storage offset of the array's first entry):
+// 'I' tauii nodes (n, h), 'V' velocity nodes (n+O, 0), 'H' half (n-O, 1+2h), 'J' inner (n-2O, O+h)
 const char* field_types(int f) {
     switch (f) {
     case GPI_P: case GPI_TAUXX: case GPI_TAUYY: case GPI_TAUZZ:
@@ -40,8 +41,8 @@ const char* field_types(int f) {
     }
     return nullptr;
 }
-int type_len(char t, int n) { return t == 'I' ? n : t == 'V' ? n + 1 : t == 'H' ? n - 1 : n - 2; }
-int type_off(char t) { return (t == 'H' || t == 'J') ? 1 : 0; }
+int type_len(char t, int n, int order) { const int O = order - 1; return t == 'I' ? n : t == 'V' ? n + O : t == 'H' ? n - O : n - 2 * O; }
+int type_off(char t, int order) { const int h = (order - 2) / 2; return t == 'I' ? h : t == 'V' ? 0 : t == 'H' ? 1 + 2 * h : 1 + 3 * h; }
 bool has_y(int f) {
     switch (f) {
     case GPI_VY: case GPI_TAUYY: case GPI_TAUXY: case GPI_TAUYZ: case GPI_DPDY: case GPI_DVYDY:
@@ -61,12 +62,12 @@ bool field_exists(int nd, int phys, int f) {
     }
     return !(f == GPI_P || f == GPI_DPDX || f == GPI_DPDY || f == GPI_DPDZ);
 }
-int field_shape(int nd, int f, const int n[3], int out[3], int off[3]) {
+int field_shape(int nd, int f, const int n[3], int out[3], int off[3], int order = 2) {
     const char* t = field_types(f);
     if (!t || (nd == 2 && has_y(f))) return 1;
     for (int q = 0; q < 3; q++) {
         if (q == 1 && nd == 2) { out[q] = 1; off[q] = 0; continue; }
-        out[q] = type_len(t[q], n[q]); off[q] = type_off(t[q]);
+        out[q] = type_len(t[q], n[q], order); off[q] = type_off(t[q], order);
     }
     return 0;
 }
@@ -213,7 +214,7 @@ int ensure_stage(gpi_handle* h, size_t nfloats) {
 int upload_field(gpi_handle* h, int f, const float* src, float* dvol, int k_first = 0, int nk = -1) {
     const Geom& g = h->g;
     int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
-    if (field_shape(h->nd, f, n, sh, off)) FAIL(h, "field %d has no shape in %d-D", f, h->nd);
+    if (field_shape(h->nd, f, n, sh, off, h->c.order)) FAIL(h, "field %d has no shape in %d-D", f, h->nd);
     if (nk < 0) nk = sh[0];
     if (ensure_stage(h, (size_t)g.vol)) return 1;
     // the staging buffer starts from the device copy so that rows outside the window keep their values
@@ -236,7 +237,7 @@ int upload_field(gpi_handle* h, int f, const float* src, float* dvol, int k_firs
 int download_field(gpi_handle* h, int f, const float* dvol, float* dst) {
     const Geom& g = h->g;
     int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
-    if (field_shape(h->nd, f, n, sh, off)) FAIL(h, "field %d has no shape in %d-D", f, h->nd);
+    if (field_shape(h->nd, f, n, sh, off, h->c.order)) FAIL(h, "field %d has no shape in %d-D", f, h->nd);
     if (ensure_stage(h, (size_t)g.vol)) return 1;
     CU(h, cudaMemcpyAsync(h->stage, dvol, (size_t)g.vol * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -283,7 +284,7 @@ void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch) {
     for (const auto& t : h->terms) {
         PmlTerm p;
         p.mem = h->MEM + (long long)ipw * h->mem_per_pw + t.off;
-        if (t.axis == 0) {
+        if (t.axis == 0 && h->c.order == 2) {
             p.a = h->pmlztab + ((size_t)t.dfield * 3 + 0) * h->pzt;
             p.b = h->pmlztab + ((size_t)t.dfield * 3 + 1) * h->pzt;
             p.kI = h->pmlztab + ((size_t)t.dfield * 3 + 2) * h->pzt;
@@ -423,11 +424,40 @@ cudaEvent_t sample_event(gpi_handle* h) {
     }
     return h->evpool[h->evused++];
 }
+// order 4 (kernels4.cuh): the fused velocity kernel, then one face-sized launch per axis for the rigid faces in the
+// reference's x, (y,) z order (dirichlet.jl:3-78; update_v!, advance_acou.jl:36-58); the fused stress kernel
+template <int ND, int EL>
+void launch_step_kernels4(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
+    const Geom& g = h->g;
+    dim3 blk = ND == 3 ? h->blk3 : h->blk2;
+    dim3 grd = grid_for(h, blk, nbatch);
+    if (!vel) { k_stress4<ND, EL><<<grd, blk, 0, h->stream>>>(g, a); return; }
+    k_vel4<ND, EL><<<grd, blk, 0, h->stream>>>(g, a);
+    const int nn[3] = {g.nz, g.ny, g.nx};
+    for (int axis = 2; axis >= 0; axis--) {
+        if (axis == 1 && ND == 2) continue;
+        const int minbit = axis == 0 ? ZMIN : axis == 1 ? YMIN : XMIN;
+        if (!(g.rigid & (minbit | (minbit << 1)))) continue;
+        const int o1 = axis == 0 ? (ND == 3 ? 1 : 2) : 0;
+        const int o2 = axis == 0 ? (ND == 3 ? 2 : -1) : (axis == 1 ? 2 : (ND == 3 ? 1 : -1));
+        dim3 fb(128), fg((nn[o1] + 127) / 128, o2 >= 0 ? nn[o2] : 1, nbatch);
+        k_dirichlet4<ND><<<fg, fb, 0, h->stream>>>(g, a, axis);
+        h->timers.launches += 1;
+    }
+}
 void launch_step(gpi_handle* h, const StepArgs& a, bool vel, int nbatch, bool sample = false) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (sample) { e0 = sample_event(h); e1 = sample_event(h); }
     if (e0 && e1) { cudaEventRecord(e0, h->stream); h->evkind.push_back(vel ? 0 : 1); }
     struct Closer { gpi_handle* h; cudaEvent_t e; ~Closer() { if (e) cudaEventRecord(e, h->stream); } } closer{h, (e0 && e1) ? e1 : nullptr};
+    if (h->c.order == 4) {
+        if (h->nd == 2 && !h->el) launch_step_kernels4<2, 0>(h, a, vel, nbatch);
+        else if (h->nd == 2)      launch_step_kernels4<2, 1>(h, a, vel, nbatch);
+        else if (!h->el)          launch_step_kernels4<3, 0>(h, a, vel, nbatch);
+        else                      launch_step_kernels4<3, 1>(h, a, vel, nbatch);
+        h->timers.launches += 1;
+        return;
+    }
     if (h->nd == 2 && !h->el) launch_step_kernels<2, 0>(h, a, vel, nbatch);
     else if (h->nd == 2)      launch_step_kernels<2, 1>(h, a, vel, nbatch);
     else if (!h->el)          launch_step_kernels<3, 0>(h, a, vel, nbatch);
@@ -457,7 +487,7 @@ int launch_boundary(gpi_handle* h, bool save, int nb, int slot /* 0-based time s
     int umax = 0, vmax = 0;
     for (int i = 0; i < a.nf; i++) {
         int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
-        field_shape(h->nd, bf[i], n, sh, off);
+        field_shape(h->nd, bf[i], n, sh, off, h->c.order);
         BndField& F = a.f[i];
         F.f0 = wf_ptr(h, h->W, 0, 0, bf[i]);
         for (int ia = 0; ia < a.naxes; ia++) {
@@ -504,7 +534,7 @@ __global__ void k_pad_replicate(const Geom g, const float* __restrict__ src, flo
     const int k = kl + g.koff;
     if (kl >= g.pz || k >= g.nz) return;
     const int sz = min(max(k - lz, 0), mz - 1), sy = min(max(j - ly, 0), my - 1), sx = min(max(i - lx, 0), mx - 1);
-    dst[uidx(g, kl, j, i)] = src[(long long)sz + (long long)mz * ((long long)sy + (long long)my * sx)];
+    dst[uidx(g, kl + g.h, g.ny1 > 1 ? j + g.h : j, i + g.h)] = src[(long long)sz + (long long)mz * ((long long)sy + (long long)my * sx)];
 }
 
 __global__ void k_negate_copy(float* __restrict__ dst, const float* __restrict__ src, long long n) {
@@ -521,12 +551,15 @@ extern "C" int gpi_abi_version(void) { return GPI_ABI_VERSION; }
 
 extern "C" const char* gpi_last_error(const gpi_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
-extern "C" int gpi_field_shape(int ndims, int physics, int field_id, const int32_t n[3], int32_t out[3]) {
-    if (!field_exists(ndims, physics, field_id)) return 1;
+extern "C" int gpi_field_shape_order(int ndims, int physics, int order, int field_id, const int32_t n[3], int32_t out[3]) {
+    if ((order != 2 && order != 4) || !field_exists(ndims, physics, field_id)) return 1;
     int nn[3] = {n[0], ndims == 3 ? n[1] : 1, n[2]}, o[3], off[3];
-    if (field_shape(ndims, field_id, nn, o, off)) return 1;
+    if (field_shape(ndims, field_id, nn, o, off, order)) return 1;
     out[0] = o[0]; out[1] = o[1]; out[2] = o[2];
     return 0;
+}
+extern "C" int gpi_field_shape(int ndims, int physics, int field_id, const int32_t n[3], int32_t out[3]) {
+    return gpi_field_shape_order(ndims, physics, 2, field_id, n, out);
 }
 
 static int create_impl(gpi_handle* h) {
@@ -535,7 +568,8 @@ static int create_impl(gpi_handle* h) {
     g.nz = c.n[0]; g.ny = h->nd == 3 ? c.n[1] : 1; g.nx = c.n[2];
     // z-slab window: global unified nodes k in [0, nz] split evenly; koff is a multiple of four so that
     // the vector kernels' global table / z-memory indices keep their 16-byte alignment
-    g.koff = 0; g.klo = 0; g.khi = g.nz;
+    g.h = (c.order - 2) / 2;                       // order 4: one extra node on the min side of every axis
+    g.koff = 0; g.klo = 0; g.khi = g.nz + 2 * g.h;
     h->ka = 0; h->kb = g.nz + 1;
     if (h->slab) {
         const long long nodes = g.nz + 1;
@@ -548,8 +582,8 @@ static int create_impl(gpi_handle* h) {
     }
     g.pz = ((g.khi + 2 + 31) / 32) * 32;
     h->pzt = ((g.nz + 64 + 31) / 32) * 32;
-    g.ny1 = h->nd == 3 ? g.ny + 1 : 1;
-    g.nx1 = g.nx + 1;
+    g.ny1 = h->nd == 3 ? g.ny + 1 + 2 * g.h : 1;
+    g.nx1 = g.nx + 1 + 2 * g.h;
     g.npml = c.npml;
     g.pzm = ((2 * ((c.npml + 3 + 3) / 4 * 4) + 31) / 32) * 32;     // two float4-aligned halves (kernels.cuh, cpml<>)
     g.pml = c.pml_faces; g.rigid = c.rigid_faces; g.freesurf = c.stressfree_faces;
@@ -560,9 +594,10 @@ static int create_impl(gpi_handle* h) {
     for (int q = 0; q < 3; q++) {
         if (q == 1 && h->nd == 2) continue;
         const int lo = q == 0 ? ZMIN : q == 1 ? YMIN : XMIN, hi = q == 0 ? ZMAX : q == 1 ? YMAX : XMAX;
-        if ((c.pml_faces & lo) && (c.pml_faces & hi) && c.n[q] - 2 < 2 * c.npml)
+        const int inner = c.n[q] - 2 * (c.order - 1);      // shortest derivative field along the axis
+        if ((c.pml_faces & lo) && (c.pml_faces & hi) && inner < 2 * c.npml)
             FAIL(h, "axis %d: %d nodes cannot hold two %d-cell CPML slabs", q, c.n[q], c.npml);
-        if ((c.pml_faces & (lo | hi)) && c.n[q] - 2 < c.npml) FAIL(h, "axis %d shorter than the CPML slab", q);
+        if ((c.pml_faces & (lo | hi)) && inner < c.npml) FAIL(h, "axis %d shorter than the CPML slab", q);
     }
 
     // wavefield slots
@@ -697,7 +732,9 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (!cfg || !out) { g_create_err = "gpi_create: null argument"; return 1; }
     *out = nullptr;
     if (cfg->abi_version != GPI_ABI_VERSION) { g_create_err = "gpi_create: ABI version mismatch"; return 1; }
-    if (cfg->order != 2) { g_create_err = "gpi_create: only order 2 is implemented (orders 6/8 are broken upstream, order 4 is a later row)"; return 1; }
+    if (cfg->order != 2 && cfg->order != 4) { g_create_err = "gpi_create: orders 2 and 4 are implemented (orders 6/8 are broken upstream)"; return 1; }
+    if (cfg->npml != 40 + (cfg->order - 1)) { g_create_err = "gpi_create: npml must be 40 + (order - 1) (GeoPhyInv.jl:90)"; return 1; }
+    if (cfg->order == 4 && cfg->slab_nranks > 1) { g_create_err = "gpi_create: z-slabs are implemented for order 2 (an order-4 cut needs two halo planes)"; return 1; }
     if (cfg->ndims != 2 && cfg->ndims != 3) { g_create_err = "gpi_create: ndims must be 2 or 3"; return 1; }
     if (cfg->physics != GPI_ACOUSTIC && cfg->physics != GPI_ELASTIC) { g_create_err = "gpi_create: unknown physics"; return 1; }
     if (cfg->npw < 1 || cfg->npw > 2 || cfg->nshots < 1 || cfg->nt < 1 || cfg->npml < 1 || cfg->nbound < 1 || cfg->nbound > 4) { g_create_err = "gpi_create: bad npw/nshots/nt/npml/nbound"; return 1; }
@@ -842,6 +879,15 @@ extern "C" int gpi_update_dmod(gpi_handle* h) {
     dim3 blk = h->nd == 3 ? h->blk3 : h->blk2, grd = grid_for(h, blk, 1);
     const float dt = (float)h->c.dt;
     const float* m0 = h->el ? h->mod[GPI_INVLAMBDA] : h->mod[GPI_INVK];
+    if (h->c.order == 4) {
+        if (h->nd == 2 && !h->el) k_dmod4<2, 0><<<grd, blk, 0, h->stream>>>(h->g, m0, h->mod[GPI_RHO], nullptr, h->dmod_table, dt);
+        else if (h->nd == 2)      k_dmod4<2, 1><<<grd, blk, 0, h->stream>>>(h->g, m0, h->mod[GPI_RHO], h->mod[GPI_INVMU], h->dmod_table, dt);
+        else if (!h->el)          k_dmod4<3, 0><<<grd, blk, 0, h->stream>>>(h->g, m0, h->mod[GPI_RHO], nullptr, h->dmod_table, dt);
+        else                      k_dmod4<3, 1><<<grd, blk, 0, h->stream>>>(h->g, m0, h->mod[GPI_RHO], h->mod[GPI_INVMU], h->dmod_table, dt);
+        CU(h, cudaGetLastError());
+        CU(h, cudaStreamSynchronize(h->stream));
+        return 0;
+    }
     if (h->nd == 2 && !h->el) k_dmod<2, 0><<<grd, blk, 0, h->stream>>>(h->g, m0, h->mod[GPI_RHO], nullptr, h->dmod_table, dt);
     else if (h->nd == 2)      k_dmod<2, 1><<<grd, blk, 0, h->stream>>>(h->g, m0, h->mod[GPI_RHO], h->mod[GPI_INVMU], h->dmod_table, dt);
     else if (!h->el)          k_dmod<3, 0><<<grd, blk, 0, h->stream>>>(h->g, m0, h->mod[GPI_RHO], nullptr, h->dmod_table, dt);
@@ -853,6 +899,7 @@ extern "C" int gpi_update_dmod(gpi_handle* h) {
 extern "C" int gpi_set_medium_pert(gpi_handle* h, int p, const float* a) {
     GUARD(h);
     if (h->nd != 2 || h->el) FAIL(h, "FD-Born exists for 2-D acoustic media only (born.jl:1-12)");
+    if (h->c.order != 2) FAIL(h, "FD-Born is defined for order 2 only");
     if (p != GPI_INVK && p != GPI_RHO) FAIL(h, "medium perturbation %d is not a parameter of this physics", p);
     if (!a) FAIL(h, "null medium perturbation");
     if (!h->modp[p]) { CU(h, cudaMalloc((void**)&h->modp[p], (size_t)h->g.vol * sizeof(float))); CU(h, cudaMemset(h->modp[p], 0, (size_t)h->g.vol * sizeof(float))); }
@@ -885,7 +932,7 @@ extern "C" int gpi_set_pml(gpi_handle* h, int f, const float* a, const float* b,
         // z terms: expand onto the unified z coordinate; identity (a = b = 0, kI = 1) outside the slabs
         const Geom& g = h->g;
         int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
-        field_shape(h->nd, f, n, sh, off);
+        field_shape(h->nd, f, n, sh, off, h->c.order);
         const int s0 = off[0], len = sh[0], npml = h->c.npml;
         const int pzt = h->pzt;
         std::vector<float> ta(pzt, 0.f), tb(pzt, 0.f), tk(pzt, 1.f);
@@ -915,7 +962,7 @@ extern "C" int gpi_set_sparse(gpi_handle* h, int kind, int ipw, int issp, int f,
     free_sparse(m);
     const Geom& g = h->g;
     int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
-    field_shape(h->nd, f, n, sh, off);
+    field_shape(h->nd, f, n, sh, off, h->c.order);
     const long long flen = (long long)sh[0] * sh[1] * sh[2];
     const int64_t nnz = colptr[ncol] - 1;
     std::vector<int> cp(ncol + 1), cell(nnz);
@@ -939,10 +986,15 @@ extern "C" int gpi_set_sparse(gpi_handle* h, int kind, int ipw, int issp, int f,
             // injection view: velocity sources only act on the @inn range (source.jl:166-177)
             bool ok = true;
             if (isv) {
-                const bool iny = h->nd == 2 || (j >= 1 && j <= g.ny - 2), inyh = h->nd == 2 || (j >= 1 && j <= g.ny - 1);
-                if (slot == V_X) ok = k >= 1 && k <= g.nz - 2 && iny && i >= 1 && i <= g.nx - 1;
-                if (slot == V_Z) ok = k >= 1 && k <= g.nz - 1 && iny && i >= 1 && i <= g.nx - 2;
-                if (slot == V_Y) ok = k >= 1 && k <= g.nz - 2 && inyh && i >= 1 && i <= g.nx - 2;
+                // unified coordinates (storage - h); J = inner nodes [O, n-1-O], H = half nodes [1+h, n-1-h]
+                const int hh = g.h, O = h->c.order - 1;
+                const int ku = k - hh, ju = h->nd == 3 ? j - hh : 0, iu = i - hh;
+                auto inJ = [&](int u, int n) { return u >= O && u <= n - 1 - O; };
+                auto inH = [&](int u, int n) { return u >= 1 + hh && u <= n - 1 - hh; };
+                const bool jJ = h->nd == 2 || inJ(ju, g.ny), jH = h->nd == 2 || inH(ju, g.ny);
+                if (slot == V_X) ok = inJ(ku, g.nz) && jJ && inH(iu, g.nx);
+                if (slot == V_Z) ok = inH(ku, g.nz) && jJ && inJ(iu, g.nx);
+                if (slot == V_Y) ok = inJ(ku, g.nz) && jH && inJ(iu, g.nx);
             }
             if (ok) rows[cell[e]].push_back({jcol, nzval[e]});
         }
@@ -1152,6 +1204,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     const int unshifted = (mode & GPI_RUN_UNSHIFTED_RHO) ? 1 : 0;
     mode &= ~(GPI_RUN_BORN | GPI_RUN_UNSHIFTED_RHO);
     if (born && (h->nd != 2 || h->el || h->npw != 2 || (activepw & 3) != 3)) FAIL(h, "FD-Born needs a 2-D acoustic experiment with both wavefields active");
+    if ((born || unshifted) && h->c.order != 2) FAIL(h, "FD-Born and its exact-transpose imaging are defined for order 2 only");
     if (born && mode == GPI_MODE_ADJOINT) FAIL(h, "FD-Born scattering sources exist in the forward modes only (born.jl:27-30)");
     if (born && !h->born_ready) FAIL(h, "FD-Born: call gpi_set_medium_pert and gpi_update_born first");
     if (mode != GPI_MODE_FORWARD && mode != GPI_MODE_FORWARD_SAVE && mode != GPI_MODE_ADJOINT) FAIL(h, "unknown mode %d", mode);

@@ -46,6 +46,7 @@ struct Geom {
     // klo = 0, khi = nz): local z index kl <-> global k = kl + koff (koff % 4 == 0); this handle
     // updates the nodes kl in [klo, khi]; kl = klo-1 and khi+1 are halo planes filled by the exchange.
     int koff, klo, khi;
+    int h;                   // order 4: storage index = unified coordinate + h on every axis (kernels4.cuh); 0 at order 2
     int pz;                  // z pitch in floats (multiple of 32)
     int ny1;                 // rows per x-plane: ny+1 (3-D) or 1 (2-D)
     int nx1;                 // nx+1
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(256) k_stress(const Geom g, const StepArgs a) 
 #include "kernels3d.cuh"
 #include "kernels2v.cuh"
 #include "kernels3t.cuh"
+#include "kernels4.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // k_dmod: update_dmod! + store_invav*! (medium.jl:143-221).  The reference's `dt / @av_*(b)` and
@@ -521,7 +523,7 @@ __global__ void k_post(const Geom g, const PostDesc* __restrict__ descs, int it 
                 for (int t = 0; t < op.ntarget; t++) op.target[t][c] = __fadd_rn(op.target[t][c], add);
             } else {                                                 // pw = pw + (pv / av(rho) * dt), Float64 as in the reference
                 const long long off = op.axis == 0 ? 1 : (op.axis == 1 ? sy : sx);
-                const float s = __fadd_rn(op.coef[c - off], op.coef[c]);
+                const float s = __fadd_rn(op.coef[c - (g.h + 1) * off], op.coef[c - g.h * off]);     // @av_?i: integer nodes u-1-h, u-h
                 float* t = op.target[0];
                 t[c] = (float)((double)t[c] + ((double)buf / ((double)s * 0.5) * (double)dt));
             }
@@ -595,9 +597,9 @@ __global__ void k_grad2d(const Geom g, const float* __restrict__ p1, const float
                          float* __restrict__ gK, float* __restrict__ gR, float dtI, long long wstride, long long gstride, int unshifted) {
     int k, j, i, b;
     if (!cell<2>(g, 1, k, j, i, b)) return;
-    if (k > g.nz - 1 || i > g.nx - 1) return;
+    if (k > g.nz - 1 || i > g.nx - 1) return;            // (k, i): tauii node; its storage index is shifted by g.h at order 4
     const long long w = (long long)b * wstride, gw = (long long)b * gstride;
-    const long long c = uidx(g, k, 0, i), sx = g.pz;
+    const long long c = uidx(g, k + g.h, 0, i + g.h), sx = g.pz;
     gK[gw + c] = __fadd_rn(gK[gw + c], __fmul_rn(__fmul_rn(p2tp[w + c], __fsub_rn(p1tp[w + c], p1[w + c])), dtI));
     if (unshifted) {
         // GPI_RUN_UNSHIFTED_RHO: cell (k, i) takes the velocity nodes that bound it -- vx nodes i and i+1, vz nodes k and
@@ -610,11 +612,14 @@ __global__ void k_grad2d(const Geom g, const float* __restrict__ p1, const float
         gR[gw + c] = (float)((double)gR[gw + c] - (double)ax * 0.5 - (double)az * 0.5);
         return;
     }
-    if (k >= 1 && k <= g.nz - 2 && i >= 1 && i <= g.nx - 2) {
+    const int o = 1 + 2 * g.h;                           // @inn(g): tauii nodes [O, n-1-O]
+    if (k >= o && k <= g.nz - 1 - o && i >= o && i <= g.nx - 1 - o) {
         auto bufx = [&](long long q) { return __fmul_rn(__fmul_rn(vx2tp[w + q], __fsub_rn(vx1[w + q], vx1tp[w + q])), dtI); };
         auto bufz = [&](long long q) { return __fmul_rn(__fmul_rn(vz2tp[w + q], __fsub_rn(vz1[w + q], vz1tp[w + q])), dtI); };
-        const float ax = __fadd_rn(bufx(c - sx), bufx(c));     // vxbuffer[iz+1, ix] + vxbuffer[iz+1, ix+1]
-        const float az = __fadd_rn(bufz(c - 1), bufz(c));      // vzbuffer[iz, ix+1] + vzbuffer[iz+1, ix+1]
+        // @av_xi(vxbuffer) = vxbuffer[izi, ix] + vxbuffer[izi, ix+1]: velocity nodes 3h+1 and 3h below the cell's own index
+        const long long q1 = 3 * g.h + 1, q0 = 3 * g.h;
+        const float ax = __fadd_rn(bufx(c - q1 * sx), bufx(c - q0 * sx));
+        const float az = __fadd_rn(bufz(c - q1), bufz(c - q0));      // @av_zi(vzbuffer)
         gR[gw + c] = (float)((double)gR[gw + c] - (double)ax * 0.5 - (double)az * 0.5);
     }
 }

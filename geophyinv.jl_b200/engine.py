@@ -66,7 +66,7 @@ EXPORTS = [
     "gpi_update_dmod", "gpi_set_medium_pert", "gpi_update_born", "gpi_set_pml", "gpi_set_sparse", "gpi_set_wavelets", "gpi_run", "gpi_get_records",
     "gpi_get_gradient", "gpi_get_snap", "gpi_set_snap_steps", "gpi_get_field", "gpi_set_field", "gpi_reset",
     "gpi_nccl_unique_id", "gpi_nccl_init", "gpi_allreduce_gradients", "gpi_records_device_ptr",
-    "gpi_gradient_device_ptr", "gpi_set_stream", "gpi_synchronize", "gpi_get_timers", "gpi_field_shape",
+    "gpi_gradient_device_ptr", "gpi_set_stream", "gpi_synchronize", "gpi_get_timers", "gpi_field_shape", "gpi_field_shape_order",
 ]
 
 _lib = None
@@ -117,6 +117,7 @@ def load_library(path: str = LIB_PATH):
         "gpi_synchronize": ([vp], C.c_int),
         "gpi_get_timers": ([vp, C.POINTER(GpiTimers)], C.c_int),
         "gpi_field_shape": ([C.c_int, C.c_int, C.c_int, ip, ip], C.c_int),
+        "gpi_field_shape_order": ([C.c_int, C.c_int, C.c_int, C.c_int, ip, ip], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)
@@ -171,7 +172,7 @@ class Engine:
 
     def field_shape(self, field: str):
         out = (C.c_int32 * 3)()
-        rc = self.lib.gpi_field_shape(self.cfg.ndims, self.cfg.physics, FIELD[field], self.cfg.n, out)
+        rc = self.lib.gpi_field_shape_order(self.cfg.ndims, self.cfg.physics, self.cfg.order, FIELD[field], self.cfg.n, out)
         if rc != 0:
             raise EngineError(f"field {field} does not exist for this physics / ndims")
         sh = tuple(out)

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .grids import NPML, StepRange, dfield_axis, dim_names, get_mgrid
+from .grids import NPML, ORDER, StepRange, dfield_axis, dim_names, get_mgrid
 
 
 def pml_profile(exmgrid: StepRange, mgrid: StepRange, flags, dt: float, velavg: float, freqpeak: float, npml: int = NPML):
@@ -53,7 +53,7 @@ def pml_profile(exmgrid: StepRange, mgrid: StepRange, flags, dt: float, velavg: 
     return pa.astype(np.float32), pb.astype(np.float32), pkI.astype(np.float32)
 
 
-def pml_coefficients(dfields, exgrid, mgrid, pml_faces, dt: float, velavg: float, freqpeak: float, npml: int = NPML):
+def pml_coefficients(dfields, exgrid, mgrid, pml_faces, dt: float, velavg: float, freqpeak: float, npml: int = NPML, order: int = ORDER):
     """Loop over the derivative fields (cpml.jl:125-142): each uses ITS OWN staggered 1-D grid along
     its last letter.  Returns {dfield: (a, b, kI)}."""
     nd = len(exgrid)
@@ -62,7 +62,7 @@ def pml_coefficients(dfields, exgrid, mgrid, pml_faces, dt: float, velavg: float
     for df in dfields:
         i = dfield_axis(df, nd)
         dim = dim_names(nd)[i]
-        exg = get_mgrid(df, exgrid)[i]
+        exg = get_mgrid(df, exgrid, order)[i]
         flags = [dim + "min" in faces, dim + "max" in faces]
         out[df] = pml_profile(exg, mgrid[i], flags, dt, velavg, freqpeak, npml)
     return out

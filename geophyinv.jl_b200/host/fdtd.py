@@ -23,7 +23,7 @@ from .. import engine as E
 from .cpml import pml_coefficients
 from .data import (AGeomss, Medium, Recs, Srcs, findfreq, get_adjoint_ageom, get_source, make_recs,
                    pad_widths, padarray, padmgrid)
-from .grids import NBOUND, NPML, ORDER, StepRange, dfields_of, dim_names, field_shape, wavefields_of
+from .grids import NBOUND, NPML, ORDER, StepRange, dfields_of, dim_names, field_shape, npml_of, wavefields_of
 from .proj import get_proj_matrix
 
 F32 = np.float32
@@ -82,11 +82,13 @@ class PCommon:
 
     _exmedium = None
     _mod = None
+    order = ORDER
+    npml = NPML
 
     @property
     def exmedium(self) -> Medium:
         if self._exmedium is None:
-            self._exmedium = padarray(self.medium, NPML, self.pml_faces)
+            self._exmedium = padarray(self.medium, self.npml, self.pml_faces)
         return self._exmedium
 
     @property
@@ -103,11 +105,15 @@ class PFdtd:
                  pml_faces: Sequence[str] = tuple(ALL_FACES), rigid_faces=None, rfields: Sequence[str] = ("vz",),
                  stressfree_faces: Sequence[str] = ("dummy",), tsnaps=None, snaps_field: Optional[str] = None,
                  verbose: bool = False, nworker: Optional[int] = None, rank: int = 0, device: int = -1,
-                 shot_batch: int = 0, upstream_3d_swap: bool = True, zslab=None):
+                 shot_batch: int = 0, upstream_3d_swap: bool = True, zslab=None, order: int = ORDER):
         """`zslab=(rank, nranks)`: z-slab domain decomposition of ONE experiment over `nranks` GPUs (new
         capability): every rank builds the same experiment, owns one slab of the extended grid and
-        exchanges halo planes over NVLink inside `update!`; call `init_nccl` (or `dist.attach_nccl`) first."""
+        exchanges halo planes over NVLink inside `update!`; call `init_nccl` (or `dist.attach_nccl`) first.
+        `order` = `_fd_order` (2 or 4), a compile-time preference upstream (src/GeoPhyInv.jl:85-92)."""
         N = medium.ndims
+        npml = npml_of(order)
+        if order != 2 and (attrib_mod.born or zslab is not None):
+            raise NotImplementedError("FD-Born and z-slabs are implemented for order 2")
         npw = attrib_mod.npw
         assert (attrib_mod.physics == "elastic") == medium.elastic, "attrib_mod / medium mismatch"
         if attrib_mod.born and not (attrib_mod.physics == "acoustic" and N == 2):
@@ -143,13 +149,14 @@ class PFdtd:
             assert all(x.ns == y.n for x, y in zip(a, sw)), "ageom and srcwav mismatch"
 
         c = self.c = PCommon()
+        c.order, c.npml = order, npml
         c.attrib_mod, c.medium, c.ageom, c.srcwav = attrib_mod, medium.copy(), [list(a) for a in ageom], [[s.copy() for s in sw] for sw in srcwav]
         c.pml_faces = pml_faces
         c.rigid_faces = list(dict.fromkeys(list(rigid_faces) + pml_faces))          # fdtd.jl:215
         c.stressfree_faces = [str(f).lstrip(":") for f in stressfree_faces]
         c.rfields, c.tgrid, c.verbose = rfields, tgrid, verbose
         c.upstream_3d_swap = upstream_3d_swap
-        c.exgrid = padmgrid(medium.grid, NPML, pml_faces)                             # grid of exmedium (fdtd.jl:137)
+        c.exgrid = padmgrid(medium.grid, npml, pml_faces)                             # grid of exmedium (fdtd.jl:137)
         c.mparams = medium_parameters(attrib_mod)
         c.ref_mod = {name: c.exmedium.ref(name) for name in c.mparams}               # fdtd.jl:175
         n = [len(g) for g in c.exgrid]
@@ -160,7 +167,7 @@ class PFdtd:
         c.fc = {"dt": F32(dt), "dtI": F32(1.0 / dt)}
         for d, s in zip(dim_names(N), ds):
             c.fc["d" + d] = F32(s)
-            c.fc["d" + d + "I"] = F32(1.0 / s)
+            c.fc["d" + d + "I"] = F32(1.0 / s) if order == 2 else F32(1.0 / (s * 24.0))     # fdtd.jl:316-319
         c.ic = {**{"n" + d: nn for d, nn in zip(dim_names(N), n)}, "nt": nt, "nsls": 0, "npw": npw}
         c.gradients = {name: np.zeros(n, F32, order="F") for name in c.mparams}      # fdtd.jl:164-170
         c.data = [make_recs(tgrid, ageom[ip], rfields) for ip in range(npw)]         # fdtd.jl:194
@@ -187,10 +194,10 @@ class PFdtd:
 
         # ---- engine (replaces P_x_worker_x_pw / P_x_worker_x_pw_x_ss, fdtd.jl:340-528)
         cfg = E.GpiConfig()
-        cfg.abi_version, cfg.ndims, cfg.order = E.ABI_VERSION, N, ORDER
+        cfg.abi_version, cfg.ndims, cfg.order = E.ABI_VERSION, N, order
         cfg.physics = E.ACOUSTIC if attrib_mod.physics == "acoustic" else E.ELASTIC
         cfg.n[0], cfg.n[1], cfg.n[2] = n[0], (n[1] if N == 3 else 1), n[-1]
-        cfg.nt, cfg.npml, cfg.nbound = nt, NPML, NBOUND
+        cfg.nt, cfg.npml, cfg.nbound = nt, npml, NBOUND
         cfg.pml_faces, cfg.rigid_faces = E.face_mask(c.pml_faces), E.face_mask(c.rigid_faces)
         cfg.stressfree_faces = E.face_mask(c.stressfree_faces)
         cfg.npw, cfg.nshots = npw, max(len(self.local), 1)
@@ -230,7 +237,7 @@ class PFdtd:
         if medium is not c.medium:
             c.medium.copy_from(medium)                                                 # copyto!(pac.medium, medium)
         c._exmedium = c._mod = None                                                    # padarray! happens on the device
-        lo, _ = pad_widths(c.medium.ndims, NPML, c.pml_faces)
+        lo, _ = pad_widths(c.medium.ndims, c.npml, c.pml_faces)
         if getattr(self, "_dbuf", None) is None or self._dbuf[0].shape != c.medium.vp.shape:
             self._dbuf = [np.empty(c.medium.vp.shape, F32, order="F") for _ in range(2)]
         for name in c.mparams:                                                         # copyto!(mod[name], exmedium, name)
@@ -244,7 +251,7 @@ class PFdtd:
         c = self.c
         assert c.attrib_mod.born, "update!(pa, medium, medium_pert) needs FdtdAcoustic{Born}"
         self.update_medium(medium)
-        expert = padarray(medium_pert, NPML, c.pml_faces)
+        expert = padarray(medium_pert, c.npml, c.pml_faces)
         c.dmod_pert = {name: np.asfortranarray(expert[name] - c.mod[name]) for name in c.mparams}      # δmod .= exmedium_pert .- mod
         self._upload_born()
 
@@ -259,7 +266,7 @@ class PFdtd:
         mparams = c.mparams if mparams is None else mparams
         chunks = np.split(np.asarray(m, F32), len(mparams))
         for x, name in zip(chunks, mparams):
-            inner = view_inner(c.mod[name], NPML, c.pml_faces)
+            inner = view_inner(c.mod[name], c.npml, c.pml_faces)
             inner[...] = (np.exp(x.reshape(inner.shape, order="F")) * c.ref_mod[name]).astype(F32)
             self.engine.set_medium(name, c.mod[name])        # the padding keeps its old values, as in the reference
         self.engine.update_dmod()
@@ -270,7 +277,7 @@ class PFdtd:
         mparams = c.mparams if mparams is None else mparams
         out = []
         for name in mparams:
-            inner = view_inner(c.mod[name], NPML, c.pml_faces)
+            inner = view_inner(c.mod[name], c.npml, c.pml_faces)
             out.append(np.log(inner * (F32(1) / c.ref_mod[name])).astype(F32).ravel(order="F"))
         return np.concatenate(out)
 
@@ -289,12 +296,12 @@ class PFdtd:
                 if what in ("both", "srcs"):
                     pts = [[a.s[d][i] for d in names] for i in range(a.ns)]
                     for sf in c.srcwav[ipw][iss].fields:
-                        cp, rv, nz, _ = get_proj_matrix(sf, c.exgrid, pts, c.upstream_3d_swap)
+                        cp, rv, nz, _ = get_proj_matrix(sf, c.exgrid, pts, c.upstream_3d_swap, c.order)
                         self.engine.set_sparse(E.SPRAY, ipw, issp, sf, cp, rv, nz)
                 if what in ("both", "recs"):
                     pts = [[a.r[d][i] for d in names] for i in range(a.nr)]
                     for rf in c.rfields:
-                        cp, rv, nz, _ = get_proj_matrix(rf, c.exgrid, pts, c.upstream_3d_swap)
+                        cp, rv, nz, _ = get_proj_matrix(rf, c.exgrid, pts, c.upstream_3d_swap, c.order)
                         self.engine.set_sparse(E.INTERP, ipw, issp, rf, cp, rv, nz)
 
     # ---------------------------------------------------------------------------------------------
@@ -344,7 +351,7 @@ class PFdtd:
         vb = c.exmedium.bounds("vp")
         velavg = F32((vb[0] + vb[1]) / F32(2))
         c.pml = pml_coefficients(dfields_of(c.attrib_mod.physics, N), c.exgrid, c.medium.grid,
-                                 c.pml_faces, float(c.fc["dt"]), float(velavg), float(c.fc["freqpeak"]), NPML)
+                                 c.pml_faces, float(c.fc["dt"]), float(velavg), float(c.fc["freqpeak"]), c.npml, c.order)
         for df, (a, b, kI) in c.pml.items():
             self.engine.set_pml(df, a, b, kI)
 
@@ -511,7 +518,7 @@ def gradient(g: np.ndarray, m, dobs, pa: PFdtd, mparams=None) -> float:
     gch = np.split(g, len(mparams))
     for x, gi, name in zip(chunks, gch, mparams):
         r = c.ref_mod[name]
-        gm = view_inner(c.gradients[name], NPML, c.pml_faces)
+        gm = view_inner(c.gradients[name], c.npml, c.pml_faces)
         gm[...] = gm * np.exp(x.reshape(gm.shape, order="F")) * r      # chain rule (func_grad.jl:36-39)
         gi[...] = gm.ravel(order="F")
     c.attrib_mod.mode = mode_save

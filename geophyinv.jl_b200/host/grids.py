@@ -1,12 +1,15 @@
 """Ranges and staggered-grid geometry (host side).
 
 Mirrors Julia's `StepRangeLen` as used for `medium.grid` / `tgrid`, and `get_mgrid`
-(reference src/fields.jl:92-671) reduced to per-axis node types for order 2:
+(reference src/fields.jl:92-671) reduced to per-axis node types, O = order - 1 (orders 2 and 4):
 
-    'I'  tauii / p nodes      offset  0    length n
-    'V'  velocity nodes       offset -1/2  length n+1
-    'H'  half nodes           offset +1/2  length n-1
-    'J'  inner integer nodes  offset +1    length n-2
+    'I'  tauii / p nodes      offset  0     length n
+    'V'  velocity nodes       offset -O/2   length n+O
+    'H'  half nodes           offset +O/2   length n-O
+    'J'  inner integer nodes  offset +O     length n-2O
+
+The reference fixes the order at compile time (`_fd_order`, a Preferences.jl constant, src/GeoPhyInv.jl:85-92); here
+it is a per-experiment keyword (`SeisForwExpt(...; order=4)`), `ORDER` below being the default.
 """
 from __future__ import annotations
 
@@ -17,6 +20,13 @@ import numpy as np
 ORDER = 2                      # _fd_order     (src/GeoPhyInv.jl:85)
 NPML = 40 + (ORDER - 1)        # _fd_npml = _fd_npextend (src/GeoPhyInv.jl:90-91)
 NBOUND = 3                     # _fd_nbound    (src/GeoPhyInv.jl:92)
+
+
+def npml_of(order: int) -> int:
+    """`_fd_npml = _fd_npextend = 40 + (_fd_order - 1)` (src/GeoPhyInv.jl:90-91)."""
+    if order not in (2, 4):
+        raise NotImplementedError("orders 2 and 4 are implemented (6 and 8 are broken upstream)")
+    return 40 + (order - 1)
 
 
 @dataclass(frozen=True)
@@ -100,7 +110,7 @@ def dfields_of(physics: str, ndims: int):
     return [f for f in fields_of(physics, ndims) if f.startswith("d")]
 
 
-def get_mgrid(field: str, grids):
+def get_mgrid(field: str, grids, order: int = ORDER):
     """Grid of `field` given the tauii grids `[mz, (my,) mx]` (src/fields.jl:92-671)."""
     ndims = len(grids)
     t = FIELD_TYPES[field]
@@ -108,16 +118,16 @@ def get_mgrid(field: str, grids):
         t = t[0] + t[2]
     out = []
     for ty, m in zip(t, grids):
-        out.append(StepRange(m.start + _OFFSET[ty] * m.step * (ORDER - 1), m.step, m.length + _DLEN[ty] * (ORDER - 1)))
+        out.append(StepRange(m.start + _OFFSET[ty] * m.step * (order - 1), m.step, m.length + _DLEN[ty] * (order - 1)))
     return out
 
 
-def field_shape(field: str, n):
+def field_shape(field: str, n, order: int = ORDER):
     ndims = len(n)
     t = FIELD_TYPES[field]
     if ndims == 2:
         t = t[0] + t[2]
-    return tuple(int(nn + _DLEN[ty]) for ty, nn in zip(t, n))
+    return tuple(int(nn + _DLEN[ty] * (order - 1)) for ty, nn in zip(t, n))
 
 
 def dfield_axis(field: str, ndims: int) -> int:

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .grids import get_mgrid
+from .grids import ORDER, get_mgrid
 
 
 def get_neighbour_indices(arr: np.ndarray, val: float):
@@ -64,10 +64,10 @@ def bilinear_interp(grids, point, upstream_3d_swap: bool = True):
     return idx[order], w[order]
 
 
-def get_proj_matrix(field: str, exgrid, points, upstream_3d_swap: bool = True):
+def get_proj_matrix(field: str, exgrid, points, upstream_3d_swap: bool = True, order: int = ORDER):
     """`get_proj_matrix(field, attrib_mod, exmedium.grid..., Ps)` (fdtd/ageom.jl:16-22,
     proj_mat.jl:229-247): one column per point.  Returns (colptr, rowval, nzval, nrows)."""
-    grids = get_mgrid(field, exgrid)
+    grids = get_mgrid(field, exgrid, order)
     colptr, rowval, nzval = [1], [], []
     for P in points:
         idx, w = bilinear_interp(grids, P, upstream_3d_swap)

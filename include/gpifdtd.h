@@ -88,10 +88,10 @@ typedef struct gpi_config {
     int32_t abi_version;      /* GPI_ABI_VERSION */
     int32_t ndims;            /* 2 or 3                                   (_fd_ndims)  */
     int32_t physics;          /* GPI_ACOUSTIC | GPI_ELASTIC                            */
-    int32_t order;            /* 2 (only order implemented this round)    (_fd_order)  */
+    int32_t order;            /* 2 or 4 (6/8 are broken upstream)         (_fd_order)  */
     int32_t n[3];             /* extended nz, ny, nx; ny = 1 when ndims == 2           */
     int32_t nt;               /* time steps                                            */
-    int32_t npml;             /* 40 + (order-1) = 41                      (_fd_npml)   */
+    int32_t npml;             /* 40 + (order-1) = 41 | 43                 (_fd_npml)   */
     int32_t nbound;           /* 3                                        (_fd_nbound) */
     int32_t pml_faces;        /* bit mask of GPI_ZMIN..GPI_XMAX                        */
     int32_t rigid_faces;      /* bit mask; the host passes unique(rigid U pml), fdtd.jl:215 */
@@ -196,7 +196,10 @@ int  gpi_synchronize(gpi_handle* h);
 
 /* ---- instrumentation ------------------------------------------------------------------------- */
 int  gpi_get_timers(gpi_handle* h, gpi_timers* out);
-int  gpi_field_shape(int ndims, int physics, int field_id, const int32_t n[3], int32_t out[3]);
+int  gpi_field_shape(int ndims, int physics, int field_id, const int32_t n[3], int32_t out[3]);      /* order 2 */
+/* shape of a field's own staggered array (fields.jl:92-671) for _fd_order = 2 | 4: velocity axes n + (order-1),
+ * half-node axes n - (order-1), inner axes n - 2 (order-1) */
+int  gpi_field_shape_order(int ndims, int physics, int order, int field_id, const int32_t n[3], int32_t out[3]);
 
 #ifdef __cplusplus
 }

@@ -53,9 +53,9 @@ static void arr_free(arr* a) { free(a->d); a->d = NULL; a->len = 0; }
 static void arr_zero(arr* a) { if (a->d) memset(a->d, 0, a->len * sizeof(REAL)); }
 
 /* ------------------------------------------------------------------------------------------------
- * field shapes: src/fields.jl:92-671 (get_mgrid) reduced to per-axis node types for order 2
- *   I: tauii nodes, length n        V: velocity nodes (-1/2), length n+1
- *   H: half nodes (+1/2), length n-1   J: inner integer nodes (+1), length n-2
+ * field shapes: src/fields.jl:92-671 (get_mgrid) reduced to per-axis node types, O = order - 1
+ *   I: tauii nodes, length n              V: velocity nodes (-O/2), length n+O
+ *   H: half nodes (+O/2), length n-O      J: inner integer nodes (+O), length n-2O
  * ---------------------------------------------------------------------------------------------- */
 static const char* field_types3(int f) {           /* (z,y,x) */
     switch (f) {
@@ -71,7 +71,10 @@ static const char* field_types3(int f) {           /* (z,y,x) */
     }
     return NULL;
 }
-static int type_len(char t, int n) { return t == 'I' ? n : t == 'V' ? n + 1 : t == 'H' ? n - 1 : n - 2; }
+/* O = _fd_order - 1 (1 or 3): V nodes n+O, H nodes n-O, J nodes n-2O (fields.jl:92-671).  File-scope: the entry
+ * points set it from the handle's order before any shape or sweep is evaluated. */
+static int g_O = 1;
+static int type_len(char t, int n) { return t == 'I' ? n : t == 'V' ? n + g_O : t == 'H' ? n - g_O : n - 2 * g_O; }
 
 /* also exported (orc_field_shape) so the tests can check the engine's gpi_field_shape against it */
 static int field_shape(int ndims, int f, const int n[3], int out[3]) {
@@ -169,22 +172,40 @@ static int imax3(int a, int b, int c) { return imax2(a, imax2(b, c)); }
 
 #define OMP_FOR _Pragma("omp parallel for schedule(static)")
 
+/* ---- finite-difference macros (diff2D.jl:15-97, diff3D.jl:15-134) -------------------------------------------
+ * O = _fd_order - 1 is the shift of `@inn` and of the `_i` macros (izi = iz + O, diff2D.jl:5-13).
+ * order 2: A[i+1] - A[i] in the array's own precision.
+ * order 4: A[i+2]*27.0 - A[i+1]*27.0 + A[i] - A[i+3]: the Float64 literals promote the whole expression, the
+ *          product with d?I (which carries the 1/24, fdtd.jl:318-319) stays Float64 and the store rounds once.
+ * The order is per handle; the entry points copy it into the file-scope g_O before any sweep runs. */
+static inline REAL fd(const REAL* p, size_t s, REAL sI) {
+    if (g_O == 1) return (p[s] - p[0]) * sI;
+    return (REAL)(((double)p[2 * s] * 27.0 - (double)p[s] * 27.0 + (double)p[0] - (double)p[3 * s]) * (double)sI);
+}
+#define DZ2(a, iz, ix, sI)     fd(&A2(a, iz, ix), 1, sI)
+#define DX2(a, iz, ix, sI)     fd(&A2(a, iz, ix), (size_t)(a).n[0], sI)
+#define DZ3(a, iz, iy, ix, sI) fd(&A3(a, iz, iy, ix), 1, sI)
+#define DY3(a, iz, iy, ix, sI) fd(&A3(a, iz, iy, ix), (size_t)(a).n[0], sI)
+#define DX3(a, iz, iy, ix, sI) fd(&A3(a, iz, iy, ix), (size_t)(a).n[0] * (size_t)(a).n[1], sI)
+
 /* compute_dp! (advance_acou.jl:258-262) */
 static void compute_dp_2d(arr p, arr dpdx, arr dpdz, REAL dzI, REAL dxI) {
+    const int O = g_O;
     int nz = imax3(p.n[0], dpdx.n[0], dpdz.n[0]), nx = imax3(p.n[2], dpdx.n[2], dpdz.n[2]);
     OMP_FOR
     for (int ix = 1; ix <= nx; ix++) for (int iz = 1; iz <= nz; iz++) {
-        if (iz <= dpdx.n[0] && ix <= dpdx.n[2]) A2(dpdx, iz, ix) = (A2(p, iz + 1, ix + 1) - A2(p, iz + 1, ix)) * dxI;   /* @d_xi */
-        if (iz <= dpdz.n[0] && ix <= dpdz.n[2]) A2(dpdz, iz, ix) = (A2(p, iz + 1, ix + 1) - A2(p, iz, ix + 1)) * dzI;   /* @d_zi */
+        if (iz <= dpdx.n[0] && ix <= dpdx.n[2]) A2(dpdx, iz, ix) = DX2(p, iz + O, ix, dxI);   /* @d_xi */
+        if (iz <= dpdz.n[0] && ix <= dpdz.n[2]) A2(dpdz, iz, ix) = DZ2(p, iz, ix + O, dzI);   /* @d_zi */
     }
 }
 /* compute_v! (advance_acou.jl:273-277) */
 static void compute_v_acou_2d(arr vx, arr vz, arr bx, arr bz, arr dpdx, arr dpdz) {
+    const int O = g_O;
     int nz = imax2(vx.n[0], vz.n[0]), nx = imax2(vx.n[2], vz.n[2]);
     OMP_FOR
     for (int ix = 1; ix <= nx; ix++) for (int iz = 1; iz <= nz; iz++) {
-        if (iz <= vx.n[0] - 2 && ix <= vx.n[2] - 2) A2(vx, iz + 1, ix + 1) = A2(vx, iz + 1, ix + 1) + A2(bx, iz, ix) * A2(dpdx, iz, ix);
-        if (iz <= vz.n[0] - 2 && ix <= vz.n[2] - 2) A2(vz, iz + 1, ix + 1) = A2(vz, iz + 1, ix + 1) + A2(bz, iz, ix) * A2(dpdz, iz, ix);
+        if (iz <= vx.n[0] - 2 * O && ix <= vx.n[2] - 2 * O) A2(vx, iz + O, ix + O) = A2(vx, iz + O, ix + O) + A2(bx, iz, ix) * A2(dpdx, iz, ix);
+        if (iz <= vz.n[0] - 2 * O && ix <= vz.n[2] - 2 * O) A2(vz, iz + O, ix + O) = A2(vz, iz + O, ix + O) + A2(bz, iz, ix) * A2(dpdz, iz, ix);
     }
 }
 /* compute_dv! (advance_acou.jl:288-292) */
@@ -192,8 +213,8 @@ static void compute_dv_acou_2d(arr vx, arr vz, arr dvxdx, arr dvzdz, REAL dxI, R
     int nz = imax2(vz.n[0], dvxdx.n[0]), nx = imax2(vx.n[2], dvxdx.n[2]);
     OMP_FOR
     for (int ix = 1; ix <= nx; ix++) for (int iz = 1; iz <= nz; iz++) {
-        if (iz <= dvxdx.n[0] && ix <= dvxdx.n[2]) A2(dvxdx, iz, ix) = (A2(vx, iz, ix + 1) - A2(vx, iz, ix)) * dxI;   /* @d_xa */
-        if (iz <= dvzdz.n[0] && ix <= dvzdz.n[2]) A2(dvzdz, iz, ix) = (A2(vz, iz + 1, ix) - A2(vz, iz, ix)) * dzI;   /* @d_za */
+        if (iz <= dvxdx.n[0] && ix <= dvxdx.n[2]) A2(dvxdx, iz, ix) = DX2(vx, iz, ix, dxI);   /* @d_xa */
+        if (iz <= dvzdz.n[0] && ix <= dvzdz.n[2]) A2(dvzdz, iz, ix) = DZ2(vz, iz, ix, dzI);   /* @d_za */
     }
 }
 /* compute_p! (advance_acou.jl:303-306) */
@@ -207,24 +228,25 @@ static void compute_p_2d(arr p, arr dvxdx, arr dvzdz, arr dtK) {
  * kernels, 3-D acoustic: src/fdtd/advance_acou.jl:265-313
  * ---------------------------------------------------------------------------------------------- */
 static void compute_dp_3d(arr p, arr dpdx, arr dpdy, arr dpdz, REAL dzI, REAL dyI, REAL dxI) {
+    const int O = g_O;
     int nz = p.n[0], ny = p.n[1], nx = p.n[2];
     OMP_FOR
     for (int ix = 1; ix <= nx; ix++) for (int iy = 1; iy <= ny; iy++) for (int iz = 1; iz <= nz; iz++) {
-        if (iz <= dpdx.n[0] && iy <= dpdx.n[1] && ix <= dpdx.n[2]) A3(dpdx, iz, iy, ix) = (A3(p, iz + 1, iy + 1, ix + 1) - A3(p, iz + 1, iy + 1, ix)) * dxI;
-        if (iz <= dpdy.n[0] && iy <= dpdy.n[1] && ix <= dpdy.n[2]) A3(dpdy, iz, iy, ix) = (A3(p, iz + 1, iy + 1, ix + 1) - A3(p, iz + 1, iy, ix + 1)) * dyI;
-        if (iz <= dpdz.n[0] && iy <= dpdz.n[1] && ix <= dpdz.n[2]) A3(dpdz, iz, iy, ix) = (A3(p, iz + 1, iy + 1, ix + 1) - A3(p, iz, iy + 1, ix + 1)) * dzI;
+        if (iz <= dpdx.n[0] && iy <= dpdx.n[1] && ix <= dpdx.n[2]) A3(dpdx, iz, iy, ix) = DX3(p, iz + O, iy + O, ix, dxI);
+        if (iz <= dpdy.n[0] && iy <= dpdy.n[1] && ix <= dpdy.n[2]) A3(dpdy, iz, iy, ix) = DY3(p, iz + O, iy, ix + O, dyI);
+        if (iz <= dpdz.n[0] && iy <= dpdz.n[1] && ix <= dpdz.n[2]) A3(dpdz, iz, iy, ix) = DZ3(p, iz, iy + O, ix + O, dzI);
     }
 }
+#define INN3(a) (iz <= (a).n[0] - 2 * O && iy <= (a).n[1] - 2 * O && ix <= (a).n[2] - 2 * O)
+#define I3(a)   A3(a, iz + O, iy + O, ix + O)
 static void compute_v_acou_3d(arr vx, arr vy, arr vz, arr bx, arr by, arr bz, arr dpdx, arr dpdy, arr dpdz) {
+    const int O = g_O;
     int nz = vz.n[0], ny = vy.n[1], nx = vx.n[2];
     OMP_FOR
     for (int ix = 1; ix <= nx; ix++) for (int iy = 1; iy <= ny; iy++) for (int iz = 1; iz <= nz; iz++) {
-        if (iz <= vx.n[0] - 2 && iy <= vx.n[1] - 2 && ix <= vx.n[2] - 2)
-            A3(vx, iz + 1, iy + 1, ix + 1) = A3(vx, iz + 1, iy + 1, ix + 1) + A3(bx, iz, iy, ix) * A3(dpdx, iz, iy, ix);
-        if (iz <= vy.n[0] - 2 && iy <= vy.n[1] - 2 && ix <= vy.n[2] - 2)
-            A3(vy, iz + 1, iy + 1, ix + 1) = A3(vy, iz + 1, iy + 1, ix + 1) + A3(by, iz, iy, ix) * A3(dpdy, iz, iy, ix);
-        if (iz <= vz.n[0] - 2 && iy <= vz.n[1] - 2 && ix <= vz.n[2] - 2)
-            A3(vz, iz + 1, iy + 1, ix + 1) = A3(vz, iz + 1, iy + 1, ix + 1) + A3(bz, iz, iy, ix) * A3(dpdz, iz, iy, ix);
+        if (INN3(vx)) I3(vx) = I3(vx) + A3(bx, iz, iy, ix) * A3(dpdx, iz, iy, ix);
+        if (INN3(vy)) I3(vy) = I3(vy) + A3(by, iz, iy, ix) * A3(dpdy, iz, iy, ix);
+        if (INN3(vz)) I3(vz) = I3(vz) + A3(bz, iz, iy, ix) * A3(dpdz, iz, iy, ix);
     }
 }
 static void compute_dv_acou_3d(arr vx, arr vy, arr vz, arr dvxdx, arr dvydy, arr dvzdz, REAL dxI, REAL dyI, REAL dzI) {
@@ -232,9 +254,9 @@ static void compute_dv_acou_3d(arr vx, arr vy, arr vz, arr dvxdx, arr dvydy, arr
     OMP_FOR
     for (int ix = 1; ix <= nx; ix++) for (int iy = 1; iy <= ny; iy++) for (int iz = 1; iz <= nz; iz++) {
         if (iz <= dvxdx.n[0] && iy <= dvxdx.n[1] && ix <= dvxdx.n[2]) {
-            A3(dvxdx, iz, iy, ix) = (A3(vx, iz, iy, ix + 1) - A3(vx, iz, iy, ix)) * dxI;
-            A3(dvydy, iz, iy, ix) = (A3(vy, iz, iy + 1, ix) - A3(vy, iz, iy, ix)) * dyI;
-            A3(dvzdz, iz, iy, ix) = (A3(vz, iz + 1, iy, ix) - A3(vz, iz, iy, ix)) * dzI;
+            A3(dvxdx, iz, iy, ix) = DX3(vx, iz, iy, ix, dxI);
+            A3(dvydy, iz, iy, ix) = DY3(vy, iz, iy, ix, dyI);
+            A3(dvzdz, iz, iy, ix) = DZ3(vz, iz, iy, ix, dzI);
         }
     }
 }
@@ -249,36 +271,39 @@ static void compute_p_3d(arr p, arr dvxdx, arr dvydy, arr dvzdz, arr dtK) {
  * kernels, 2-D elastic: src/fdtd/advance_elastic.jl:48-67,96-110,145-153,179-210
  * ---------------------------------------------------------------------------------------------- */
 static void compute_dstress_2d(arr tauxx, arr tauzz, arr tauxz, arr dtauxxdx, arr dtauxzdx, arr dtauzzdz, arr dtauxzdz, REAL dxI, REAL dzI) {
+    const int O = g_O;
     int nz = tauxx.n[0], nx = tauxx.n[2];
     OMP_FOR
     for (int ix = 1; ix <= nx; ix++) for (int iz = 1; iz <= nz; iz++) {
-        if (iz <= dtauxxdx.n[0] && ix <= dtauxxdx.n[2]) A2(dtauxxdx, iz, ix) = (A2(tauxx, iz + 1, ix + 1) - A2(tauxx, iz + 1, ix)) * dxI;  /* @d_xi */
-        if (iz <= dtauxzdx.n[0] && ix <= dtauxzdx.n[2]) A2(dtauxzdx, iz, ix) = (A2(tauxz, iz, ix + 1) - A2(tauxz, iz, ix)) * dxI;          /* @d_xa */
-        if (iz <= dtauzzdz.n[0] && ix <= dtauzzdz.n[2]) A2(dtauzzdz, iz, ix) = (A2(tauzz, iz + 1, ix + 1) - A2(tauzz, iz, ix + 1)) * dzI;  /* @d_zi */
-        if (iz <= dtauxzdz.n[0] && ix <= dtauxzdz.n[2]) A2(dtauxzdz, iz, ix) = (A2(tauxz, iz + 1, ix) - A2(tauxz, iz, ix)) * dzI;          /* @d_za */
+        if (iz <= dtauxxdx.n[0] && ix <= dtauxxdx.n[2]) A2(dtauxxdx, iz, ix) = DX2(tauxx, iz + O, ix, dxI);  /* @d_xi */
+        if (iz <= dtauxzdx.n[0] && ix <= dtauxzdx.n[2]) A2(dtauxzdx, iz, ix) = DX2(tauxz, iz, ix, dxI);      /* @d_xa */
+        if (iz <= dtauzzdz.n[0] && ix <= dtauzzdz.n[2]) A2(dtauzzdz, iz, ix) = DZ2(tauzz, iz, ix + O, dzI);  /* @d_zi */
+        if (iz <= dtauxzdz.n[0] && ix <= dtauxzdz.n[2]) A2(dtauxzdz, iz, ix) = DZ2(tauxz, iz, ix, dzI);      /* @d_za */
     }
 }
 static void compute_v_el_2d(arr vx, arr vz, arr dtauxxdx, arr dtauxzdx, arr dtauzzdz, arr dtauxzdz, arr bx, arr bz) {
+    const int O = g_O;
     int nz = vz.n[0], nx = vx.n[2];
     OMP_FOR
     for (int ix = 1; ix <= nx; ix++) for (int iz = 1; iz <= nz; iz++) {
-        if (iz <= vx.n[0] - 2 && ix <= vx.n[2] - 2)
-            A2(vx, iz + 1, ix + 1) = A2(vx, iz + 1, ix + 1) - A2(bx, iz, ix) * (A2(dtauxxdx, iz, ix) + A2(dtauxzdz, iz, ix));
-        if (iz <= vz.n[0] - 2 && ix <= vz.n[2] - 2)
-            A2(vz, iz + 1, ix + 1) = A2(vz, iz + 1, ix + 1) - A2(bz, iz, ix) * (A2(dtauxzdx, iz, ix) + A2(dtauzzdz, iz, ix));
+        if (iz <= vx.n[0] - 2 * O && ix <= vx.n[2] - 2 * O)
+            A2(vx, iz + O, ix + O) = A2(vx, iz + O, ix + O) - A2(bx, iz, ix) * (A2(dtauxxdx, iz, ix) + A2(dtauxzdz, iz, ix));
+        if (iz <= vz.n[0] - 2 * O && ix <= vz.n[2] - 2 * O)
+            A2(vz, iz + O, ix + O) = A2(vz, iz + O, ix + O) - A2(bz, iz, ix) * (A2(dtauxzdx, iz, ix) + A2(dtauzzdz, iz, ix));
     }
 }
 static void compute_dv_el_2d(arr vx, arr vz, arr dvxdx, arr dvzdz, arr dvxdz, arr dvzdx, REAL dxI, REAL dzI) {
+    const int O = g_O;
     int nz = vz.n[0], nx = vx.n[2];
     OMP_FOR
     for (int ix = 1; ix <= nx; ix++) for (int iz = 1; iz <= nz; iz++) {
         if (iz <= dvxdx.n[0] && ix <= dvxdx.n[2]) {
-            A2(dvxdx, iz, ix) = (A2(vx, iz, ix + 1) - A2(vx, iz, ix)) * dxI;          /* @d_xa */
-            A2(dvzdz, iz, ix) = (A2(vz, iz + 1, ix) - A2(vz, iz, ix)) * dzI;          /* @d_za */
+            A2(dvxdx, iz, ix) = DX2(vx, iz, ix, dxI);          /* @d_xa */
+            A2(dvzdz, iz, ix) = DZ2(vz, iz, ix, dzI);          /* @d_za */
         }
         if (iz <= dvxdz.n[0] && ix <= dvxdz.n[2]) {
-            A2(dvxdz, iz, ix) = (A2(vx, iz + 1, ix + 1) - A2(vx, iz, ix + 1)) * dzI;  /* @d_zi */
-            A2(dvzdx, iz, ix) = (A2(vz, iz + 1, ix + 1) - A2(vz, iz + 1, ix)) * dxI;  /* @d_xi */
+            A2(dvxdz, iz, ix) = DZ2(vx, iz, ix + O, dzI);      /* @d_zi */
+            A2(dvzdx, iz, ix) = DX2(vz, iz + O, ix, dxI);      /* @d_xi */
         }
     }
 }
@@ -299,9 +324,9 @@ static void compute_stressij_2d(arr tauxz, arr dvxdz, arr dvzdx, arr dtavmu) {
  * kernels, 3-D elastic: src/fdtd/advance_elastic.jl:10-46,69-94,112-143,155-206
  * ---------------------------------------------------------------------------------------------- */
 #define IN3(a) (iz <= (a).n[0] && iy <= (a).n[1] && ix <= (a).n[2])
-#define INN3(a) (iz <= (a).n[0] - 2 && iy <= (a).n[1] - 2 && ix <= (a).n[2] - 2)
 
 static void compute_dstress_3d(arr* w, REAL dxI, REAL dyI, REAL dzI) {
+    const int O = g_O;
     arr tauxx = w[GPI_TAUXX], tauyy = w[GPI_TAUYY], tauzz = w[GPI_TAUZZ], tauxy = w[GPI_TAUXY], tauxz = w[GPI_TAUXZ], tauyz = w[GPI_TAUYZ];
     arr dtauxxdx = w[GPI_DTAUXXDX], dtauxydx = w[GPI_DTAUXYDX], dtauxzdx = w[GPI_DTAUXZDX];
     arr dtauyydy = w[GPI_DTAUYYDY], dtauxydy = w[GPI_DTAUXYDY], dtauyzdy = w[GPI_DTAUYZDY];
@@ -309,18 +334,19 @@ static void compute_dstress_3d(arr* w, REAL dxI, REAL dyI, REAL dzI) {
     int nz = tauxx.n[0], ny = tauxx.n[1], nx = tauxx.n[2];
     OMP_FOR
     for (int ix = 1; ix <= nx; ix++) for (int iy = 1; iy <= ny; iy++) for (int iz = 1; iz <= nz; iz++) {
-        if (IN3(dtauxxdx)) A3(dtauxxdx, iz, iy, ix) = (A3(tauxx, iz + 1, iy + 1, ix + 1) - A3(tauxx, iz + 1, iy + 1, ix)) * dxI;  /* @d_xi */
-        if (IN3(dtauxydx)) A3(dtauxydx, iz, iy, ix) = (A3(tauxy, iz, iy, ix + 1) - A3(tauxy, iz, iy, ix)) * dxI;                  /* @d_xa */
-        if (IN3(dtauxzdx)) A3(dtauxzdx, iz, iy, ix) = (A3(tauxz, iz, iy, ix + 1) - A3(tauxz, iz, iy, ix)) * dxI;                  /* @d_xa */
-        if (IN3(dtauyydy)) A3(dtauyydy, iz, iy, ix) = (A3(tauyy, iz + 1, iy + 1, ix + 1) - A3(tauyy, iz + 1, iy, ix + 1)) * dyI;  /* @d_yi */
-        if (IN3(dtauxydy)) A3(dtauxydy, iz, iy, ix) = (A3(tauxy, iz, iy + 1, ix) - A3(tauxy, iz, iy, ix)) * dyI;                  /* @d_ya */
-        if (IN3(dtauyzdy)) A3(dtauyzdy, iz, iy, ix) = (A3(tauyz, iz, iy + 1, ix) - A3(tauyz, iz, iy, ix)) * dyI;                  /* @d_ya */
-        if (IN3(dtauzzdz)) A3(dtauzzdz, iz, iy, ix) = (A3(tauzz, iz + 1, iy + 1, ix + 1) - A3(tauzz, iz, iy + 1, ix + 1)) * dzI;  /* @d_zi */
-        if (IN3(dtauxzdz)) A3(dtauxzdz, iz, iy, ix) = (A3(tauxz, iz + 1, iy, ix) - A3(tauxz, iz, iy, ix)) * dzI;                  /* @d_za */
-        if (IN3(dtauyzdz)) A3(dtauyzdz, iz, iy, ix) = (A3(tauyz, iz + 1, iy, ix) - A3(tauyz, iz, iy, ix)) * dzI;                  /* @d_za */
+        if (IN3(dtauxxdx)) A3(dtauxxdx, iz, iy, ix) = DX3(tauxx, iz + O, iy + O, ix, dxI);  /* @d_xi */
+        if (IN3(dtauxydx)) A3(dtauxydx, iz, iy, ix) = DX3(tauxy, iz, iy, ix, dxI);          /* @d_xa */
+        if (IN3(dtauxzdx)) A3(dtauxzdx, iz, iy, ix) = DX3(tauxz, iz, iy, ix, dxI);          /* @d_xa */
+        if (IN3(dtauyydy)) A3(dtauyydy, iz, iy, ix) = DY3(tauyy, iz + O, iy, ix + O, dyI);  /* @d_yi */
+        if (IN3(dtauxydy)) A3(dtauxydy, iz, iy, ix) = DY3(tauxy, iz, iy, ix, dyI);          /* @d_ya */
+        if (IN3(dtauyzdy)) A3(dtauyzdy, iz, iy, ix) = DY3(tauyz, iz, iy, ix, dyI);          /* @d_ya */
+        if (IN3(dtauzzdz)) A3(dtauzzdz, iz, iy, ix) = DZ3(tauzz, iz, iy + O, ix + O, dzI);  /* @d_zi */
+        if (IN3(dtauxzdz)) A3(dtauxzdz, iz, iy, ix) = DZ3(tauxz, iz, iy, ix, dzI);          /* @d_za */
+        if (IN3(dtauyzdz)) A3(dtauyzdz, iz, iy, ix) = DZ3(tauyz, iz, iy, ix, dzI);          /* @d_za */
     }
 }
 static void compute_v_el_3d(arr* w, arr bx, arr by, arr bz) {
+    const int O = g_O;
     arr vx = w[GPI_VX], vy = w[GPI_VY], vz = w[GPI_VZ];
     arr dtauxxdx = w[GPI_DTAUXXDX], dtauxydx = w[GPI_DTAUXYDX], dtauxzdx = w[GPI_DTAUXZDX];
     arr dtauyydy = w[GPI_DTAUYYDY], dtauxydy = w[GPI_DTAUXYDY], dtauyzdy = w[GPI_DTAUYZDY];
@@ -328,27 +354,28 @@ static void compute_v_el_3d(arr* w, arr bx, arr by, arr bz) {
     int nz = vz.n[0], ny = vy.n[1], nx = vx.n[2];
     OMP_FOR
     for (int ix = 1; ix <= nx; ix++) for (int iy = 1; iy <= ny; iy++) for (int iz = 1; iz <= nz; iz++) {
-        if (INN3(vx)) A3(vx, iz + 1, iy + 1, ix + 1) = A3(vx, iz + 1, iy + 1, ix + 1) - A3(bx, iz, iy, ix) * (A3(dtauxxdx, iz, iy, ix) + A3(dtauxydy, iz, iy, ix) + A3(dtauxzdz, iz, iy, ix));
-        if (INN3(vy)) A3(vy, iz + 1, iy + 1, ix + 1) = A3(vy, iz + 1, iy + 1, ix + 1) - A3(by, iz, iy, ix) * (A3(dtauxydx, iz, iy, ix) + A3(dtauyydy, iz, iy, ix) + A3(dtauyzdz, iz, iy, ix));
-        if (INN3(vz)) A3(vz, iz + 1, iy + 1, ix + 1) = A3(vz, iz + 1, iy + 1, ix + 1) - A3(bz, iz, iy, ix) * (A3(dtauxzdx, iz, iy, ix) + A3(dtauyzdy, iz, iy, ix) + A3(dtauzzdz, iz, iy, ix));
+        if (INN3(vx)) I3(vx) = I3(vx) - A3(bx, iz, iy, ix) * (A3(dtauxxdx, iz, iy, ix) + A3(dtauxydy, iz, iy, ix) + A3(dtauxzdz, iz, iy, ix));
+        if (INN3(vy)) I3(vy) = I3(vy) - A3(by, iz, iy, ix) * (A3(dtauxydx, iz, iy, ix) + A3(dtauyydy, iz, iy, ix) + A3(dtauyzdz, iz, iy, ix));
+        if (INN3(vz)) I3(vz) = I3(vz) - A3(bz, iz, iy, ix) * (A3(dtauxzdx, iz, iy, ix) + A3(dtauyzdy, iz, iy, ix) + A3(dtauzzdz, iz, iy, ix));
     }
 }
 static void compute_dv_el_3d(arr* w, REAL dxI, REAL dyI, REAL dzI) {
+    const int O = g_O;
     arr vx = w[GPI_VX], vy = w[GPI_VY], vz = w[GPI_VZ];
     arr dvxdx = w[GPI_DVXDX], dvydy = w[GPI_DVYDY], dvzdz = w[GPI_DVZDZ];
     arr dvxdy = w[GPI_DVXDY], dvxdz = w[GPI_DVXDZ], dvydx = w[GPI_DVYDX], dvydz = w[GPI_DVYDZ], dvzdx = w[GPI_DVZDX], dvzdy = w[GPI_DVZDY];
     int nz = vz.n[0], ny = vy.n[1], nx = vx.n[2];
     OMP_FOR
     for (int ix = 1; ix <= nx; ix++) for (int iy = 1; iy <= ny; iy++) for (int iz = 1; iz <= nz; iz++) {
-        if (IN3(dvxdx)) A3(dvxdx, iz, iy, ix) = (A3(vx, iz, iy, ix + 1) - A3(vx, iz, iy, ix)) * dxI;                 /* @d_xa */
-        if (IN3(dvydy)) A3(dvydy, iz, iy, ix) = (A3(vy, iz, iy + 1, ix) - A3(vy, iz, iy, ix)) * dyI;                 /* @d_ya */
-        if (IN3(dvzdz)) A3(dvzdz, iz, iy, ix) = (A3(vz, iz + 1, iy, ix) - A3(vz, iz, iy, ix)) * dzI;                 /* @d_za */
-        if (IN3(dvxdy)) A3(dvxdy, iz, iy, ix) = (A3(vx, iz + 1, iy + 1, ix + 1) - A3(vx, iz + 1, iy, ix + 1)) * dyI; /* @d_yi */
-        if (IN3(dvxdz)) A3(dvxdz, iz, iy, ix) = (A3(vx, iz + 1, iy + 1, ix + 1) - A3(vx, iz, iy + 1, ix + 1)) * dzI; /* @d_zi */
-        if (IN3(dvydz)) A3(dvydz, iz, iy, ix) = (A3(vy, iz + 1, iy + 1, ix + 1) - A3(vy, iz, iy + 1, ix + 1)) * dzI; /* @d_zi */
-        if (IN3(dvydx)) A3(dvydx, iz, iy, ix) = (A3(vy, iz + 1, iy + 1, ix + 1) - A3(vy, iz + 1, iy + 1, ix)) * dxI; /* @d_xi */
-        if (IN3(dvzdx)) A3(dvzdx, iz, iy, ix) = (A3(vz, iz + 1, iy + 1, ix + 1) - A3(vz, iz + 1, iy + 1, ix)) * dxI; /* @d_xi */
-        if (IN3(dvzdy)) A3(dvzdy, iz, iy, ix) = (A3(vz, iz + 1, iy + 1, ix + 1) - A3(vz, iz + 1, iy, ix + 1)) * dyI; /* @d_yi */
+        if (IN3(dvxdx)) A3(dvxdx, iz, iy, ix) = DX3(vx, iz, iy, ix, dxI);                 /* @d_xa */
+        if (IN3(dvydy)) A3(dvydy, iz, iy, ix) = DY3(vy, iz, iy, ix, dyI);                 /* @d_ya */
+        if (IN3(dvzdz)) A3(dvzdz, iz, iy, ix) = DZ3(vz, iz, iy, ix, dzI);                 /* @d_za */
+        if (IN3(dvxdy)) A3(dvxdy, iz, iy, ix) = DY3(vx, iz + O, iy, ix + O, dyI);         /* @d_yi */
+        if (IN3(dvxdz)) A3(dvxdz, iz, iy, ix) = DZ3(vx, iz, iy + O, ix + O, dzI);         /* @d_zi */
+        if (IN3(dvydz)) A3(dvydz, iz, iy, ix) = DZ3(vy, iz, iy + O, ix + O, dzI);         /* @d_zi */
+        if (IN3(dvydx)) A3(dvydx, iz, iy, ix) = DX3(vy, iz + O, iy + O, ix, dxI);         /* @d_xi */
+        if (IN3(dvzdx)) A3(dvzdx, iz, iy, ix) = DX3(vz, iz + O, iy + O, ix, dxI);         /* @d_xi */
+        if (IN3(dvzdy)) A3(dvzdy, iz, iy, ix) = DY3(vz, iz + O, iy, ix + O, dyI);         /* @d_yi */
     }
 }
 static void compute_stressii_3d(arr* w, arr dtM, arr dtlambda) {
@@ -401,7 +428,7 @@ static void memory_pml(orc_handle* h, pw_t* pw, int df) {
 }
 
 /* ------------------------------------------------------------------------------------------------
- * rigid faces: src/fdtd/dirichlet.jl:35-74 (order 2: one ghost pair)
+ * rigid faces: src/fdtd/dirichlet.jl:3-78 (order/2 ghost pairs)
  *   dirichlet{q}min!(vq, vrest..., n): vrest[.., 1, ..] = 0; vq[.., 1, ..] = -vq[.., 2, ..]
  *   dirichlet{q}max!(vq, vrest..., n): vrest[.., n, ..] = 0; vq[.., n+1, ..] = -vq[.., n, ..]
  *   launched over (1:n_other...) of the tauii grid (advance_acou.jl:51-58,161-193)
@@ -427,9 +454,12 @@ static void dirichlet(orc_handle* h, pw_t* pw) {
                     id[q] = side ? n : 1;
                     A3(pw->w[vq[r]], id[0], id[1], id[2]) = 0;
                 }
-                int ig = side ? n + 1 : 1, is = side ? n : 2;   /* ghost <- -mirror */
-                id[q] = is; REAL v = A3(pw->w[vq[q]], id[0], id[1], id[2]);
-                id[q] = ig; A3(pw->w[vq[q]], id[0], id[1], id[2]) = -v;
+                const int order = g_O + 1, fdh = order / 2;       /* dirichlet.jl:12-24: ghost <- -mirror, ifd = 1..fdh */
+                for (int ifd = 1; ifd <= fdh; ifd++) {
+                    int ig = side ? n + order - ifd : ifd, is = side ? n + ifd - 1 : order + 1 - ifd;
+                    id[q] = is; REAL v = A3(pw->w[vq[q]], id[0], id[1], id[2]);
+                    id[q] = ig; A3(pw->w[vq[q]], id[0], id[1], id[2]) = -v;
+                }
             }
         }
     }
@@ -529,21 +559,22 @@ static void update_stress(orc_handle* h, pw_t* pw) {
  * ---------------------------------------------------------------------------------------------- */
 static void update_dmod(orc_handle* h) {
     double dt = (double)h->dt;
+    const int O = g_O;                      /* izi = iz + O (diff2D.jl:5-13); the `+ 1` neighbours of the @av macros do not scale with the order */
     arr rho = h->mod[GPI_RHO];
     if (h->nd == 2) {
         arr bx = h->dmod[DM_BX], bz = h->dmod[DM_BZ];
         for (int ix = 1; ix <= bx.n[2]; ix++) for (int iz = 1; iz <= bx.n[0]; iz++)     /* store_invavxi!: @av_xi */
-            A2(bx, iz, ix) = (REAL)(dt / ((double)(REAL)(A2(rho, iz + 1, ix) + A2(rho, iz + 1, ix + 1)) * 0.5));
+            A2(bx, iz, ix) = (REAL)(dt / ((double)(REAL)(A2(rho, iz + O, ix) + A2(rho, iz + O, ix + 1)) * 0.5));
         for (int ix = 1; ix <= bz.n[2]; ix++) for (int iz = 1; iz <= bz.n[0]; iz++)     /* store_invavzi!: @av_zi */
-            A2(bz, iz, ix) = (REAL)(dt / ((double)(REAL)(A2(rho, iz, ix + 1) + A2(rho, iz + 1, ix + 1)) * 0.5));
+            A2(bz, iz, ix) = (REAL)(dt / ((double)(REAL)(A2(rho, iz, ix + O) + A2(rho, iz + 1, ix + O)) * 0.5));
     } else {
         arr bx = h->dmod[DM_BX], by = h->dmod[DM_BY], bz = h->dmod[DM_BZ];
         for (int ix = 1; ix <= bx.n[2]; ix++) for (int iy = 1; iy <= bx.n[1]; iy++) for (int iz = 1; iz <= bx.n[0]; iz++)
-            A3(bx, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(rho, iz + 1, iy + 1, ix) + A3(rho, iz + 1, iy + 1, ix + 1)) * 0.5));
+            A3(bx, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(rho, iz + O, iy + O, ix) + A3(rho, iz + O, iy + O, ix + 1)) * 0.5));
         for (int ix = 1; ix <= by.n[2]; ix++) for (int iy = 1; iy <= by.n[1]; iy++) for (int iz = 1; iz <= by.n[0]; iz++)
-            A3(by, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(rho, iz + 1, iy, ix + 1) + A3(rho, iz + 1, iy + 1, ix + 1)) * 0.5));
+            A3(by, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(rho, iz + O, iy, ix + O) + A3(rho, iz + O, iy + 1, ix + O)) * 0.5));
         for (int ix = 1; ix <= bz.n[2]; ix++) for (int iy = 1; iy <= bz.n[1]; iy++) for (int iz = 1; iz <= bz.n[0]; iz++)
-            A3(bz, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(rho, iz, iy + 1, ix + 1) + A3(rho, iz + 1, iy + 1, ix + 1)) * 0.5));
+            A3(bz, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(rho, iz, iy + O, ix + O) + A3(rho, iz + 1, iy + O, ix + O)) * 0.5));
     }
     if (h->c.physics == GPI_ACOUSTIC) {
         arr K = h->dmod[DM_DTK], iK = h->mod[GPI_INVK];    /* broadcast!(inv, dtK, invK); rmul!(dtK, dt) */
@@ -561,11 +592,11 @@ static void update_dmod(orc_handle* h) {
     } else {                   /* @av_xzi / @av_xyi / @av_yzi (diff3D.jl:339-378) */
         arr m1 = h->dmod[DM_MUXZ], m2 = h->dmod[DM_MUXY], m3 = h->dmod[DM_MUYZ];
         for (int ix = 1; ix <= m1.n[2]; ix++) for (int iy = 1; iy <= m1.n[1]; iy++) for (int iz = 1; iz <= m1.n[0]; iz++)
-            A3(m1, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(im, iz, iy + 1, ix) + A3(im, iz + 1, iy + 1, ix) + A3(im, iz, iy + 1, ix + 1) + A3(im, iz + 1, iy + 1, ix + 1)) * 0.25));
+            A3(m1, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(im, iz, iy + O, ix) + A3(im, iz + 1, iy + O, ix) + A3(im, iz, iy + O, ix + 1) + A3(im, iz + 1, iy + O, ix + 1)) * 0.25));
         for (int ix = 1; ix <= m2.n[2]; ix++) for (int iy = 1; iy <= m2.n[1]; iy++) for (int iz = 1; iz <= m2.n[0]; iz++)
-            A3(m2, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(im, iz + 1, iy, ix) + A3(im, iz + 1, iy + 1, ix) + A3(im, iz + 1, iy, ix + 1) + A3(im, iz + 1, iy + 1, ix + 1)) * 0.25));
+            A3(m2, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(im, iz + O, iy, ix) + A3(im, iz + O, iy + 1, ix) + A3(im, iz + O, iy, ix + 1) + A3(im, iz + O, iy + 1, ix + 1)) * 0.25));
         for (int ix = 1; ix <= m3.n[2]; ix++) for (int iy = 1; iy <= m3.n[1]; iy++) for (int iz = 1; iz <= m3.n[0]; iz++)
-            A3(m3, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(im, iz, iy, ix + 1) + A3(im, iz + 1, iy, ix + 1) + A3(im, iz, iy + 1, ix + 1) + A3(im, iz + 1, iy + 1, ix + 1)) * 0.25));
+            A3(m3, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(im, iz, iy, ix + O) + A3(im, iz + 1, iy, ix + O) + A3(im, iz, iy + 1, ix + O) + A3(im, iz + 1, iy + 1, ix + O)) * 0.25));
     }
 }
 
@@ -585,19 +616,20 @@ static void spmv(arr buf, const csc* S, const REAL* w, int nt, int it) {
  * evaluated in Float64 because @av_?i carries a Float64 literal. */
 static void muladd_with_density(orc_handle* h, arr pw, arr pv, int vfield) {
     arr rho = h->mod[GPI_RHO]; double dt = (double)h->dt;
+    const int O = g_O;
     if (h->nd == 2) {
         OMP_FOR
-        for (int ix = 1; ix <= pw.n[2] - 2; ix++) for (int iz = 1; iz <= pw.n[0] - 2; iz++) {
-            REAL s = vfield == GPI_VX ? (REAL)(A2(rho, iz + 1, ix) + A2(rho, iz + 1, ix + 1)) : (REAL)(A2(rho, iz, ix + 1) + A2(rho, iz + 1, ix + 1));
-            A2(pw, iz + 1, ix + 1) = (REAL)((double)A2(pw, iz + 1, ix + 1) + ((double)A2(pv, iz + 1, ix + 1) / ((double)s * 0.5) * dt));
+        for (int ix = 1; ix <= pw.n[2] - 2 * O; ix++) for (int iz = 1; iz <= pw.n[0] - 2 * O; iz++) {
+            REAL s = vfield == GPI_VX ? (REAL)(A2(rho, iz + O, ix) + A2(rho, iz + O, ix + 1)) : (REAL)(A2(rho, iz, ix + O) + A2(rho, iz + 1, ix + O));
+            A2(pw, iz + O, ix + O) = (REAL)((double)A2(pw, iz + O, ix + O) + ((double)A2(pv, iz + O, ix + O) / ((double)s * 0.5) * dt));
         }
     } else {
         OMP_FOR
-        for (int ix = 1; ix <= pw.n[2] - 2; ix++) for (int iy = 1; iy <= pw.n[1] - 2; iy++) for (int iz = 1; iz <= pw.n[0] - 2; iz++) {
-            REAL s = vfield == GPI_VX ? (REAL)(A3(rho, iz + 1, iy + 1, ix) + A3(rho, iz + 1, iy + 1, ix + 1))
-                   : vfield == GPI_VY ? (REAL)(A3(rho, iz + 1, iy, ix + 1) + A3(rho, iz + 1, iy + 1, ix + 1))
-                                      : (REAL)(A3(rho, iz, iy + 1, ix + 1) + A3(rho, iz + 1, iy + 1, ix + 1));
-            A3(pw, iz + 1, iy + 1, ix + 1) = (REAL)((double)A3(pw, iz + 1, iy + 1, ix + 1) + ((double)A3(pv, iz + 1, iy + 1, ix + 1) / ((double)s * 0.5) * dt));
+        for (int ix = 1; ix <= pw.n[2] - 2 * O; ix++) for (int iy = 1; iy <= pw.n[1] - 2 * O; iy++) for (int iz = 1; iz <= pw.n[0] - 2 * O; iz++) {
+            REAL s = vfield == GPI_VX ? (REAL)(A3(rho, iz + O, iy + O, ix) + A3(rho, iz + O, iy + O, ix + 1))
+                   : vfield == GPI_VY ? (REAL)(A3(rho, iz + O, iy, ix + O) + A3(rho, iz + O, iy + 1, ix + O))
+                                      : (REAL)(A3(rho, iz, iy + O, ix + O) + A3(rho, iz + 1, iy + O, ix + O));
+            I3(pw) = (REAL)((double)I3(pw) + ((double)I3(pv) / ((double)s * 0.5) * dt));
         }
     }
 }
@@ -740,11 +772,12 @@ static void compute_gradient(orc_handle* h, int issp, int unshifted) {
         }
         return;
     }
+    const int O = g_O;
     OMP_FOR
-    for (int ix = 1; ix <= gr.n[2] - 2; ix++) for (int iz = 1; iz <= gr.n[0] - 2; iz++)                     /* combine_gmodrho!: Float64 via 0.5 literals */
-        A2(gr, iz + 1, ix + 1) = (REAL)((double)A2(gr, iz + 1, ix + 1)
-            - (double)(REAL)(A2(bx, iz + 1, ix) + A2(bx, iz + 1, ix + 1)) * 0.5
-            - (double)(REAL)(A2(bz, iz, ix + 1) + A2(bz, iz + 1, ix + 1)) * 0.5);
+    for (int ix = 1; ix <= gr.n[2] - 2 * O; ix++) for (int iz = 1; iz <= gr.n[0] - 2 * O; iz++)             /* combine_gmodrho!: Float64 via 0.5 literals */
+        A2(gr, iz + O, ix + O) = (REAL)((double)A2(gr, iz + O, ix + O)
+            - (double)(REAL)(A2(bx, iz + O, ix) + A2(bx, iz + O, ix + 1)) * 0.5
+            - (double)(REAL)(A2(bz, iz, ix + O) + A2(bz, iz + 1, ix + O)) * 0.5);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -811,6 +844,8 @@ int orc_run(orc_handle* h, int mode, int activepw, int src_flags) {
     double t0 = now_s();
     const int born = (mode & GPI_RUN_BORN) != 0, unshifted = (mode & GPI_RUN_UNSHIFTED_RHO) != 0;
     mode &= ~(GPI_RUN_BORN | GPI_RUN_UNSHIFTED_RHO);
+    g_O = h->c.order - 1;
+    if ((born || unshifted) && h->c.order != 2) { snprintf(h->err, sizeof h->err, "FD-Born and its exact-transpose imaging are defined for order 2 only"); return 1; }
     if (born && (h->nd != 2 || h->c.physics != GPI_ACOUSTIC || h->c.npw != 2 || (activepw & 3) != 3 || mode == GPI_MODE_ADJOINT || !h->born_ready)) {
         snprintf(h->err, sizeof h->err, "FD-Born needs a 2-D acoustic experiment, both wavefields active, a forward mode and orc_update_born"); return 1;
     }
@@ -877,6 +912,7 @@ int orc_run(orc_handle* h, int mode, int activepw, int src_flags) {
 
 /* steps-only entry for the CPU baseline: advance nsteps of shot 0 in forward mode, no reset */
 int orc_advance(orc_handle* h, int it0, int nsteps) {
+    g_O = h->c.order - 1;
     const int recp[1] = {GPI_P}, recv[3] = {GPI_VX, GPI_VY, GPI_VZ};
     for (int it = it0; it < it0 + nsteps && it <= h->c.nt; it++) {
         record(h, it, 0, 1, recp, 1);
@@ -894,7 +930,13 @@ int orc_advance(orc_handle* h, int it0, int nsteps) {
  * ---------------------------------------------------------------------------------------------- */
 const char* orc_last_error(const orc_handle* h) { return h ? h->err : g_err; }
 int orc_real_size(void) { return (int)sizeof(REAL); }
-int orc_field_shape(int ndims, int f, const int32_t n[3], int32_t out[3]) { int nn[3] = {n[0], n[1], n[2]}, o[3]; int r = field_shape(ndims, f, nn, o); if (!r) { out[0] = o[0]; out[1] = o[1]; out[2] = o[2]; } return r; }
+int orc_field_shape_order(int ndims, int order, int f, const int32_t n[3], int32_t out[3]) {
+    const int keep = g_O; g_O = order - 1;
+    int nn[3] = {n[0], n[1], n[2]}, o[3]; int r = field_shape(ndims, f, nn, o); if (!r) { out[0] = o[0]; out[1] = o[1]; out[2] = o[2]; }
+    g_O = keep;
+    return r;
+}
+int orc_field_shape(int ndims, int f, const int32_t n[3], int32_t out[3]) { return orc_field_shape_order(ndims, 2, f, n, out); }
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
@@ -914,7 +956,9 @@ static int is_velocity(int f) { return f == GPI_VX || f == GPI_VY || f == GPI_VZ
 
 int orc_create(const gpi_config* cfg, orc_handle** out) {
     if (!cfg || !out) { snprintf(g_err, sizeof g_err, "null argument"); return 1; }
-    if (cfg->order != 2) { snprintf(g_err, sizeof g_err, "only order 2 is restated"); return 1; }
+    if (cfg->order != 2 && cfg->order != 4) { snprintf(g_err, sizeof g_err, "orders 2 and 4 are restated (6 and 8 are broken upstream)"); return 1; }
+    if (cfg->npml != 40 + (cfg->order - 1)) { snprintf(g_err, sizeof g_err, "npml must be 40 + (order - 1) (GeoPhyInv.jl:90)"); return 1; }
+    g_O = cfg->order - 1;
     if (cfg->ndims != 2 && cfg->ndims != 3) { snprintf(g_err, sizeof g_err, "ndims must be 2 or 3"); return 1; }
     orc_handle* h = (orc_handle*)calloc(1, sizeof *h);
     h->c = *cfg; h->nd = cfg->ndims;
@@ -1014,13 +1058,14 @@ int orc_get_medium(orc_handle* h, int p, REAL* out) {
     CHECK(p >= 0 && p < GPI_NPARAM && h->mod[p].d, "medium parameter not part of this physics");
     memcpy(out, h->mod[p].d, h->mod[p].len * sizeof(REAL)); return 0;
 }
-int orc_update_dmod(orc_handle* h) { update_dmod(h); return 0; }
+int orc_update_dmod(orc_handle* h) { g_O = h->c.order - 1; update_dmod(h); return 0; }
 int orc_set_medium_pert(orc_handle* h, int p, const REAL* a) {
     CHECK(h->nd == 2 && h->c.physics == GPI_ACOUSTIC && (p == GPI_INVK || p == GPI_RHO), "FD-Born: 2-D acoustic invK | rho only");
     if (!h->modp[p].d) { int n[3] = {h->nz, 1, h->nx}; CHECK(!arr_alloc(&h->modp[p], n), "out of memory"); }
     memcpy(h->modp[p].d, a, h->modp[p].len * sizeof(REAL)); h->born_ready = 0; return 0;
 }
 int orc_update_born(orc_handle* h) {
+    CHECK(h->c.order == 2, "FD-Born is defined for order 2 only");
     CHECK(h->nd == 2 && h->c.physics == GPI_ACOUSTIC && h->c.npw == 2 && h->modp[GPI_INVK].d && h->modp[GPI_RHO].d, "FD-Born: set both perturbations first");
     const int dm[3] = {DM_DTK, DM_BX, DM_BZ};
     for (int q = 0; q < 3; q++) if (!h->bornc[q].d) { CHECK(!arr_alloc(&h->bornc[q], h->dmod[dm[q]].n), "out of memory"); }

@@ -84,7 +84,7 @@ class OracleEngine:
 
     def field_shape(self, field):
         out = (C.c_int32 * 3)()
-        if self.lib.orc_field_shape(self.cfg.ndims, E.FIELD[field], self.cfg.n, out) != 0:
+        if self.lib.orc_field_shape_order(self.cfg.ndims, self.cfg.order, E.FIELD[field], self.cfg.n, out) != 0:
             raise RuntimeError(f"no field {field}")
         sh = tuple(out)
         return sh if self.cfg.ndims == 3 else (sh[0], sh[2])

@@ -36,6 +36,10 @@ CASES = {
     "elastic2d_freesurface": (G.FdtdElastic, lambda: gallery.elastic2d(stressfree=True), ("vz", "vx")),
     "acou3d": (G.FdtdAcoustic, lambda: gallery.acou3d(), ("p", "vx")),
     "c3_elastic3d_n40": (G.FdtdElastic, lambda: gallery.c3_elastic3d(n=40, nt=150, nr=12, fq=25.0, rfields=("vz", "vx", "vy")), ("vz", "vx", "vy")),
+    # _fd_order = 4 (SeisForwExpt(...; order=4)): heterogeneous 2-D acoustic, 2-D elastic with the free surface, 3-D elastic
+    "o4_acou2d": (G.FdtdAcoustic, lambda: dict(gallery.c2_acou2d_layered(nz=90, nx=140, nt=400, nss=2, nr=20, fq=15.0, rfields=("p", "vx")), order=4), ("p", "vx")),
+    "o4_elastic2d_freesurface": (G.FdtdElastic, lambda: dict(gallery.elastic2d(nt=350, stressfree=True), order=4), ("vz", "vx")),
+    "o4_elastic3d_n30": (G.FdtdElastic, lambda: dict(gallery.c3_elastic3d(n=30, nt=110, nr=10, fq=25.0, rfields=("vz", "vx", "vy")), order=4), ("vz", "vx", "vy")),
 }
 
 
@@ -67,8 +71,12 @@ def gradient_case():
 
 if __name__ == "__main__":
     O.build()
+    only = sys.argv[1:]                      # optional: names of the fixtures to (re)write
     for name in CASES:
+        if only and name not in only:
+            continue
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **records_case(name))
         print("wrote", name)
-    np.savez_compressed(os.path.join(HERE, "c4_fwi2d_gradient.npz"), **gradient_case())
-    print("wrote c4_fwi2d_gradient")
+    if not only or "c4_fwi2d_gradient" in only:
+        np.savez_compressed(os.path.join(HERE, "c4_fwi2d_gradient.npz"), **gradient_case())
+        print("wrote c4_fwi2d_gradient")

@@ -23,7 +23,7 @@ def load(name):
     return dict(np.load(os.path.join(HERE, "golden", name + ".npz")))
 
 
-@pytest.mark.parametrize("name", ["c1_acou2d_p", "elastic2d_freesurface", "acou3d"])
+@pytest.mark.parametrize("name", ["c1_acou2d_p", "elastic2d_freesurface", "acou3d", "o4_acou2d", "o4_elastic2d_freesurface"])
 def test_oracle_reproduces_golden(O, name):
     got, want = MG.records_case(name), load(name)
     assert set(got) == set(want)
