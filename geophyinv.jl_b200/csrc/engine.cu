@@ -1024,9 +1024,13 @@ extern "C" int gpi_set_wavelets(gpi_handle* h, int ipw, int issp, int f, int ns,
     if (ipw < 0 || ipw >= h->npw || issp < 0 || issp >= h->c.nshots) FAIL(h, "bad pw/shot index (%d, %d)", ipw, issp);
     if (f < 0 || f >= GPI_NWAVEFIELD || !field_exists(h->nd, h->c.physics, f)) FAIL(h, "field %d is not a wavefield of this physics", f);
     ShotData& s = h->shots[ipw][issp];
+    const size_t nb = (size_t)h->c.nt * (ns > 0 ? ns : 0) * sizeof(float);
+    if (w && ns > 0 && s.wav[f] && s.ns[f] == ns) {      // same shape as before (every FWI iteration): no free / malloc
+        CU(h, cudaMemcpy(s.wav[f], w, nb, cudaMemcpyHostToDevice));
+        return 0;
+    }
     cudaFree(s.wav[f]); s.wav[f] = nullptr; s.ns[f] = 0;
     if (!w || ns <= 0) return 0;           // removes the source field
-    const size_t nb = (size_t)h->c.nt * ns * sizeof(float);
     CU(h, cudaMalloc((void**)&s.wav[f], nb));
     CU(h, cudaMemcpy(s.wav[f], w, nb, cudaMemcpyHostToDevice));
     s.ns[f] = ns;

@@ -293,16 +293,27 @@ class PFdtd:
             c.ageom[ipw] = list(ageom[ipw])
             for issp, iss in enumerate(self.local):
                 a = c.ageom[ipw][iss]
+                # The reference rebuilds every spray matrix on each update!(pa, srcwav) (source.jl:225); here a matrix
+                # whose points have not moved since it was uploaded is left alone (the engine keeps it).
+                cache = self.__dict__.setdefault("_sparse_cache", {})
                 if what in ("both", "srcs"):
-                    pts = [[a.s[d][i] for d in names] for i in range(a.ns)]
+                    pts = np.array([[a.s[d][i] for d in names] for i in range(a.ns)], np.float64).reshape(a.ns, len(names))
                     for sf in c.srcwav[ipw][iss].fields:
+                        key = (E.SPRAY, ipw, issp, sf)
+                        if key in cache and np.array_equal(cache[key], pts):
+                            continue
                         cp, rv, nz, _ = get_proj_matrix(sf, c.exgrid, pts, c.upstream_3d_swap, c.order)
                         self.engine.set_sparse(E.SPRAY, ipw, issp, sf, cp, rv, nz)
+                        cache[key] = pts
                 if what in ("both", "recs"):
-                    pts = [[a.r[d][i] for d in names] for i in range(a.nr)]
+                    pts = np.array([[a.r[d][i] for d in names] for i in range(a.nr)], np.float64).reshape(a.nr, len(names))
                     for rf in c.rfields:
+                        key = (E.INTERP, ipw, issp, rf)
+                        if key in cache and np.array_equal(cache[key], pts):
+                            continue
                         cp, rv, nz, _ = get_proj_matrix(rf, c.exgrid, pts, c.upstream_3d_swap, c.order)
                         self.engine.set_sparse(E.INTERP, ipw, issp, rf, cp, rv, nz)
+                        cache[key] = pts
 
     # ---------------------------------------------------------------------------------------------
     # update!(pa, srcwav, src_types)  (source.jl:192-246)

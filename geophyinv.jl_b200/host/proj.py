@@ -64,9 +64,60 @@ def bilinear_interp(grids, point, upstream_3d_swap: bool = True):
     return idx[order], w[order]
 
 
+def _neighbours_vec(arr: np.ndarray, vals: np.ndarray):
+    """`get_neighbour_indices` and the clamped fraction of `bilinear_interp` for all points of one axis."""
+    n = arr.size
+    idx = np.searchsorted(arr, vals, side="left") + 1
+    i1 = np.where(idx == 1, 1, np.where(idx >= n, n - 1, idx - 1))
+    i2 = i1 + 1
+    d = (vals - arr[i1 - 1]) / (arr[i2 - 1] - arr[i1 - 1])
+    d = np.where(vals < arr.min(), 0.0, np.where(vals > arr.max(), 1.0, d))
+    return i1.astype(np.int64), i2.astype(np.int64), d
+
+
 def get_proj_matrix(field: str, exgrid, points, upstream_3d_swap: bool = True, order: int = ORDER):
     """`get_proj_matrix(field, attrib_mod, exmedium.grid..., Ps)` (fdtd/ageom.jl:16-22,
-    proj_mat.jl:229-247): one column per point.  Returns (colptr, rowval, nzval, nrows)."""
+    proj_mat.jl:229-247): one column per point.  Returns (colptr, rowval, nzval, nrows).
+
+    All points are processed at once (the reference builds one sparse column per point and `sparse_hcat`s them;
+    SURVEY 8f rank 4 names this the host-side bottleneck once the engine is fast): same operations per element as
+    `bilinear_interp`, hence the same bits (tests/test_oracle_invariants.py::test_weights_sum_to_one)."""
+    grids = get_mgrid(field, exgrid, order)
+    g = [gr.values for gr in grids]
+    nd = len(g)
+    nrows = int(np.prod([len(x) for x in g]))
+    P = np.asarray(points, np.float64).reshape(-1, nd)
+    npt = P.shape[0]
+    if npt == 0:
+        return np.ones(1, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float32), nrows
+    if nd == 2:
+        a1, a2, da = _neighbours_vec(g[0], P[:, 0])
+        b1, b2, db = _neighbours_vec(g[1], P[:, 1])
+        n = g[0].size
+        lin = lambda ia, ib: ia + (ib - 1) * n
+        idx = np.stack([lin(a1, b1), lin(a1, b2), lin(a2, b1), lin(a2, b2)], axis=1)
+        w = np.stack([(1 - da) * (1 - db), (1 - da) * db, da * (1 - db), da * db], axis=1)
+    else:
+        cz, cx = (P[:, 2], P[:, 0]) if upstream_3d_swap else (P[:, 0], P[:, 2])     # SURVEY App. C.1
+        a1, a2, da = _neighbours_vec(g[0], cz)
+        b1, b2, db = _neighbours_vec(g[1], P[:, 1])
+        c1, c2, dc = _neighbours_vec(g[2], cx)
+        n, m = g[0].size, g[1].size
+        lin = lambda ia, ib, ic: ia + (ib - 1) * n + (ic - 1) * n * m
+        idx = np.stack([lin(a1, b1, c1), lin(a1, b1, c2), lin(a1, b2, c1), lin(a1, b2, c2),
+                        lin(a2, b1, c1), lin(a2, b1, c2), lin(a2, b2, c1), lin(a2, b2, c2)], axis=1)
+        w = np.stack([(1 - da) * (1 - db) * (1 - dc), (1 - da) * (1 - db) * dc, (1 - da) * db * (1 - dc), (1 - da) * db * dc,
+                      da * (1 - db) * (1 - dc), da * (1 - db) * dc, da * db * (1 - dc), da * db * dc], axis=1)
+    o = np.argsort(idx, axis=1, kind="stable")                 # sparsevec sorts by index
+    idx = np.take_along_axis(idx, o, axis=1)
+    w = np.take_along_axis(w, o, axis=1).astype(np.float32)    # weights buffer is zeros(number, npt)
+    k = idx.shape[1]
+    colptr = 1 + k * np.arange(npt + 1, dtype=np.int64)
+    return colptr, np.ascontiguousarray(idx.ravel()), np.ascontiguousarray(w.ravel()), nrows
+
+
+def get_proj_matrix_pointwise(field: str, exgrid, points, upstream_3d_swap: bool = True, order: int = ORDER):
+    """The same matrix built one point at a time, as the reference does (kept as the check of the batched build)."""
     grids = get_mgrid(field, exgrid, order)
     colptr, rowval, nzval = [1], [], []
     for P in points:

@@ -41,6 +41,27 @@ def test_weights_sum_to_one(G):
             assert rv[cp[j] - 1:cp[j + 1] - 1].max() <= np.prod(shp)
 
 
+def test_batched_proj_matrix_equals_pointwise():
+    """`get_proj_matrix` builds all columns at once; the reference (and `get_proj_matrix_pointwise`) one point at a time
+    (proj_mat.jl:229-247).  Same bits, including points outside the grid (clamped fractions) and on nodes."""
+    import geophyinv_jl_b200 as G
+    from geophyinv_jl_b200.host.proj import get_proj_matrix, get_proj_matrix_pointwise
+    rng = np.random.default_rng(0)
+    g2 = [G.StepRange(0.0, 10.0, 50), G.StepRange(-100.0, 7.5, 60)]
+    pts = [list(p) for p in np.column_stack([rng.uniform(-30, 520, 300), rng.uniform(-130, 380, 300)])]
+    pts += [[0.0, -100.0], [490.0, 342.5], [10.0, -92.5], [5.0, -96.25]]
+    for f in ("p", "vx", "vz", "dpdx"):
+        for order in (2, 4):
+            A, B = get_proj_matrix(f, g2, pts, True, order), get_proj_matrix_pointwise(f, g2, pts, True, order)
+            assert all(np.array_equal(a, b) for a, b in zip(A[:3], B[:3])) and A[3] == B[3], (f, order)
+    g3 = [G.StepRange(0.0, 10.0, 20), G.StepRange(5.0, 10.0, 22), G.StepRange(-10.0, 10.0, 24)]
+    pts = [list(p) for p in np.column_stack([rng.uniform(-20, 220, 200), rng.uniform(-20, 240, 200), rng.uniform(-30, 250, 200)])]
+    for f in ("tauxx", "vx", "vy", "vz", "tauxy"):
+        for swap in (True, False):
+            A, B = get_proj_matrix(f, g3, pts, swap, 2), get_proj_matrix_pointwise(f, g3, pts, swap, 2)
+            assert all(np.array_equal(a, b) for a, b in zip(A[:3], B[:3])), (f, swap)
+
+
 def analytic_p_record(kw, medium_vp, medium_rho):
     """Frequency-domain homogeneous solution of  p_tt/c^2 - lap p = rho q'(t) delta(x):
     P(w) = rho (i w) Q(w) (-i/4) H0^(2)(k r), with point-source strength Q = wavelet * dz * dx because the
