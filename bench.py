@@ -116,7 +116,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload(name, nt_override=None):
+def workload(name, nt_override=None, nss=None):
     from geophyinv_jl_b200.host import gallery
     import geophyinv_jl_b200 as G
     if name == "c3":
@@ -126,8 +126,8 @@ def workload(name, nt_override=None):
         kw = gallery.c3_elastic3d(n=64, nt=nt_override or 200, fq=20.0)
         return dict(kw=kw, attrib=G.FdtdElastic, label="3-D elastic 64^3 + CPML(41) = 146^3 (debug size)", ndims=3, elastic=True)
     if name == "c2":
-        kw = gallery.c2_acou2d_layered(nt=nt_override or 4000, nss=8)
-        return dict(kw=kw, attrib=G.FdtdAcoustic, label="C2: 2-D acoustic layered 350x1700 + CPML, 8 supersources per GPU", ndims=2, elastic=False)
+        kw = gallery.c2_acou2d_layered(nt=nt_override or 4000, nss=nss or 8)
+        return dict(kw=kw, attrib=G.FdtdAcoustic, label=f"C2: 2-D acoustic layered 350x1700 + CPML, {nss or 8} supersources per GPU", ndims=2, elastic=False)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -203,10 +203,10 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import geophyinv_jl_b200 as G
-    wl = workload(args.workload, nt_override=args.nt)
+    wl = workload(args.workload, nt_override=args.nt, nss=args.nss)
     kw = wl["kw"]
     t0 = time.time()
-    pa = G.SeisForwExpt(wl["attrib"](), **kw, device=local_rank)
+    pa = G.SeisForwExpt(wl["attrib"](), **kw, device=local_rank, shot_batch=args.shot_batch, order=args.order)
     t_build = time.time() - t0
     c = pa.c
     n_ex = [len(g) for g in c.exgrid]
@@ -307,7 +307,7 @@ def run_ours(args):
             "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["label"], "extended_grid": n_ex, "time_steps_per_step": nt, "supersources_per_gpu": nss,
+            "config": {"workload": wl["label"], "fd_order": args.order, "shot_batch": int(B), "extended_grid": n_ex, "time_steps_per_step": nt, "supersources_per_gpu": nss,
                        "parallelism": f"one supersource stream per GPU x{world}", "l2": "working set (3.3 GB at C3) far exceeds the 126 MB L2; no flush needed",
                        "interior_equivalent_value": value * float(np.prod([len(g) for g in c.medium.grid])) / float(np.prod(n_ex))},
             "e2e": {"value": e2e_val, "unit": "Gcell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -499,7 +499,9 @@ def main():
     ap.add_argument("--nt", type=int, default=None, help="override the number of time steps per bench step (debug)")
     ap.add_argument("--cpu-steps", type=int, default=8, help="time steps per CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--nss", type=int, default=None, help="supersources per GPU (c4)")
+    ap.add_argument("--nss", type=int, default=None, help="supersources per GPU (c2, c4)")
+    ap.add_argument("--shot-batch", type=int, default=0, help="supersources resident per launch (0 = engine default: 16 in 2-D, 1 in 3-D)")
+    ap.add_argument("--order", type=int, default=2, help="_fd_order: 2 (default, the reference's default) or 4")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
