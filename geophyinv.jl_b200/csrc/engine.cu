@@ -1219,7 +1219,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     if (mode == GPI_MODE_FORWARD_SAVE && !h->c.store_boundary) FAIL(h, "forward_save needs store_boundary=1 at construction (fdtd.jl:445-455)");
     if (mode == GPI_MODE_ADJOINT && !h->c.store_boundary) FAIL(h, "adjoint needs the boundary store of a forward_save run");
     const bool grad = mode == GPI_MODE_ADJOINT && (activepw & 2) && h->npw == 2;
-    if (grad && (h->el || h->nd != 2)) FAIL(h, "gradient imaging exists upstream only for 2-D acoustic media (gradient.jl:17-46)");
+    if (grad && h->el) FAIL(h, "gradient imaging exists for acoustic media only (gradient.jl:17-46; 3-D: kernels.cuh k_grad3d)");
     if (mode == GPI_MODE_ADJOINT && h->el && h->nd == 3) FAIL(h, "3-D elastic has no boundary_save! upstream (boundary.jl:215-264)");
     const Geom& g = h->g;
     const int nt = h->c.nt;
@@ -1283,7 +1283,19 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             }
             if (exchange_halos(h, 0)) return 1;
             if (mode == GPI_MODE_FORWARD_SAVE && launch_boundary(h, true, nb, it - 1)) return 1;
-            if (grad) {
+            if (grad && h->nd == 3) {
+                for (int b = 0; b < nb; b++) {
+                    Grad3Args ga;
+                    ga.p1 = wf_ptr(h, h->W, b, 0, GPI_P); ga.p1tp = wf_ptr(h, h->TP, b, 0, GPI_P); ga.p2tp = wf_ptr(h, h->TP, b, 1, GPI_P);
+                    for (int q = 0; q < 3; q++) {
+                        ga.v1[q] = wf_ptr(h, h->W, b, 0, vf[q]); ga.v1tp[q] = wf_ptr(h, h->TP, b, 0, vf[q]); ga.v2tp[q] = wf_ptr(h, h->TP, b, 1, vf[q]);
+                    }
+                    ga.gK = h->gshot + (size_t)b * 2 * g.vol; ga.gR = ga.gK + g.vol;
+                    dim3 blk = h->blk3, grd = grid_for(h, blk, 1);
+                    k_grad3d<<<grd, blk, 0, h->stream>>>(g, ga, (float)h->c.dtI, unshifted);
+                    h->timers.launches += 1;
+                }
+            } else if (grad) {
                 dim3 blk = h->blk2, grd = grid_for(h, blk, nb);
                 k_grad2d<<<grd, blk, 0, h->stream>>>(g,
                     wf_ptr(h, h->W, 0, 0, GPI_P), wf_ptr(h, h->TP, 0, 0, GPI_P), wf_ptr(h, h->TP, 0, 1, GPI_P),

@@ -625,6 +625,44 @@ __global__ void k_grad2d(const Geom g, const float* __restrict__ p1, const float
 }
 
 // ------------------------------------------------------------------------------------------------
+// gradient imaging, 3-D acoustic.  gradlame! (gradient.jl:17-29) is dimension-free; gradrho! exists
+// upstream for 2-D only (gradient.jl:31,58-61).  Same construction with the y term between x and z:
+//   g_rho_inn -= av_xi(bx) + av_yi(by) + av_zi(bz),   b? = v?2_tp * (v?1 - v?1_tp) * dtI
+// `unshifted` (GPI_RUN_UNSHIFTED_RHO, order 2): the cell takes the interior velocity nodes that bound it instead of
+// upstream's one-cell-shifted pairs, which is what finite differences of the loss confirm (tests/test_adjoint3d.py).
+// ------------------------------------------------------------------------------------------------
+struct Grad3Args {
+    const float *p1, *p1tp, *p2tp;
+    const float *v1[3], *v1tp[3], *v2tp[3];      // V_X, V_Y, V_Z
+    float *gK, *gR;
+};
+__global__ void k_grad3d(const Geom g, const Grad3Args a, float dtI, int unshifted) {
+    int k, j, i, b;
+    if (!cell<3>(g, 1, k, j, i, b)) return;
+    if (k > g.nz - 1 || j > g.ny - 1 || i > g.nx - 1) return;        // (k, j, i): tauii node
+    const long long c = uidx(g, k + g.h, j + g.h, i + g.h), sy = g.pz, sx = (long long)g.pz * g.ny1;
+    a.gK[c] = __fadd_rn(a.gK[c], __fmul_rn(__fmul_rn(a.p2tp[c], __fsub_rn(a.p1tp[c], a.p1[c])), dtI));
+    auto buf = [&](int q, long long x) { return __fmul_rn(__fmul_rn(a.v2tp[q][x], __fsub_rn(a.v1[q][x], a.v1tp[q][x])), dtI); };
+    if (unshifted) {
+        // interior nodes of each component (@inn of compute_v!): vx (J, J, H), vy (J, H, J), vz (H, J, J)
+        auto bx = [&](int ii) { return (k >= 1 && k <= g.nz - 2 && j >= 1 && j <= g.ny - 2 && ii >= 1 && ii <= g.nx - 1) ? buf(V_X, uidx(g, k, j, ii)) : 0.f; };
+        auto by = [&](int jj) { return (k >= 1 && k <= g.nz - 2 && jj >= 1 && jj <= g.ny - 1 && i >= 1 && i <= g.nx - 2) ? buf(V_Y, uidx(g, k, jj, i)) : 0.f; };
+        auto bz = [&](int kk) { return (kk >= 1 && kk <= g.nz - 1 && j >= 1 && j <= g.ny - 2 && i >= 1 && i <= g.nx - 2) ? buf(V_Z, uidx(g, kk, j, i)) : 0.f; };
+        const float ax = __fadd_rn(bx(i), bx(i + 1)), ay = __fadd_rn(by(j), by(j + 1)), az = __fadd_rn(bz(k), bz(k + 1));
+        a.gR[c] = (float)((double)a.gR[c] - (double)ax * 0.5 - (double)ay * 0.5 - (double)az * 0.5);
+        return;
+    }
+    const int o = 1 + 2 * g.h;
+    if (k >= o && k <= g.nz - 1 - o && j >= o && j <= g.ny - 1 - o && i >= o && i <= g.nx - 1 - o) {
+        const long long q1 = 3 * g.h + 1, q0 = 3 * g.h;             // see k_grad2d
+        const float ax = __fadd_rn(buf(V_X, c - q1 * sx), buf(V_X, c - q0 * sx));
+        const float ay = __fadd_rn(buf(V_Y, c - q1 * sy), buf(V_Y, c - q0 * sy));
+        const float az = __fadd_rn(buf(V_Z, c - q1), buf(V_Z, c - q0));
+        a.gR[c] = (float)((double)a.gR[c] - (double)ax * 0.5 - (double)ay * 0.5 - (double)az * 0.5);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // FD-Born scattering sources, 2-D acoustic (born.jl:1-12; upstream passes argument lists that match no kernel,
 // the intent is the commented legacy code born.jl:32-99): the second wavefield is driven by the first one's
 // derivatives times the perturbation of the update coefficients,

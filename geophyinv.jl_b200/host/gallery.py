@@ -147,3 +147,30 @@ def c4_fwi2d(nz=350, nx=1700, nt=3000, nss=32, nr=128, dt=1e-3, fq=8.0, d=10.0, 
     z0, z1, x0, x1 = int(0.4 * nz), int(0.6 * nz), int(0.4 * nx), int(0.6 * nx)
     true.vp[z0:z1, x0:x1] *= F32(1 + box)
     return kw, true
+
+
+def fwi3d(n=24, nt=220, nr=12, nss=2, dt=1e-3, fq=18.0, d=10.0, box=0.05, seed=11):
+    """3-D acoustic FWI gradient case: smooth random model, 'observed' data from the same medium
+    with a +5 % vp and rho box.  Source and records are :vz / :vx (adjoint injection exists only for velocity fields)."""
+    from scipy.ndimage import gaussian_filter
+    grid = [StepRange(0.0, d, n)] * 3
+    rng = np.random.default_rng(seed)
+    vp = (2500.0 * (1 + 0.04 * gaussian_filter(rng.standard_normal((n, n, n)), 2.0) / 0.1)).astype(F32)
+    rho = (2200.0 * (1 + 0.04 * gaussian_filter(rng.standard_normal((n, n, n)), 2.0) / 0.1)).astype(F32)
+    medium = Medium(grid, vp, rho)
+    tgrid = StepRange(0.0, dt, nt)
+    L = grid[0].last
+    ageom = []
+    for iss in range(nss):
+        sx = (0.25 + 0.5 * iss / max(nss - 1, 1)) * L + 0.13 * d
+        src = {"z": [0.2 * L + 0.3 * d], "y": [0.45 * L + 0.2 * d], "x": [sx]}
+        rec = {"z": np.full(nr, 0.8 * L + 0.4 * d), "y": np.linspace(0.2 * L, 0.8 * L, nr), "x": np.linspace(0.1 * L, 0.9 * L, nr)}
+        ageom.append(AGeomss(src, rec))
+    wav = _ricker(fq, tgrid, 1.5 / fq + 0.005) * 1e6
+    srcwav = make_srcwav(tgrid, ageom, ["vz"], wav)
+    kw = dict(medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=["vz", "vx"])
+    true = medium.copy()
+    a, b = int(0.35 * n), int(0.65 * n)
+    true.vp[a:b, a:b, a:b] *= F32(1 + box)
+    true.rho[a:b, a:b, a:b] *= F32(1 + box)
+    return kw, true

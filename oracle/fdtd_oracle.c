@@ -749,7 +749,43 @@ static void boundary_force(orc_handle* h, int it, int issp) {   /* boundary.jl:1
 /* ------------------------------------------------------------------------------------------------
  * gradient imaging: src/fdtd/gradient.jl:17-61 (2-D acoustic; gradlame! + gradrho!)
  * ---------------------------------------------------------------------------------------------- */
+/* 3-D acoustic imaging.  gradlame! (gradient.jl:17-29) is dimension-free; gradrho! exists upstream for 2-D only
+ * (gradient.jl:31, compute_gradient!(::Val{:adjoint}, ::Val{2}, ...) :58-61).  The 3-D method here is the same construction with the
+ * y term added between x and z:  @inn(g) = @inn(g) - @av_xi(vxbuffer) - @av_yi(vybuffer) - @av_zi(vzbuffer)
+ * (new math upstream lacks; checked against finite differences in tests/test_adjoint3d.py). */
+static void compute_gradient_3d(orc_handle* h, int issp, int unshifted) {
+    pw_t *p1 = &h->pw[0], *p2 = &h->pw[1]; shot_t* s = &p1->ss[issp];
+    arr g = s->grad[GPI_INVK], pf = p1->w[GPI_P], pfp = p1->wtp[GPI_P], pap = p2->wtp[GPI_P];
+    REAL dtI = h->dtI;
+    OMP_FOR
+    for (size_t i = 0; i < g.len; i++) g.d[i] = g.d[i] + pap.d[i] * (pfp.d[i] - pf.d[i]) * dtI;
+    const int vf[3] = {GPI_VX, GPI_VY, GPI_VZ};
+    for (int k = 0; k < 3; k++) {
+        arr b = p1->vbuf[vf[k]], v = p1->w[vf[k]], vp = p1->wtp[vf[k]], va = p2->wtp[vf[k]];
+        OMP_FOR
+        for (size_t i = 0; i < b.len; i++) b.d[i] = va.d[i] * (v.d[i] - vp.d[i]) * dtI;
+    }
+    arr gr = s->grad[GPI_RHO], bx = p1->vbuf[GPI_VX], by = p1->vbuf[GPI_VY], bz = p1->vbuf[GPI_VZ];
+    const int O = g_O;
+    if (unshifted) {     /* GPI_RUN_UNSHIFTED_RHO: cell (iz, iy, ix) <- the interior velocity nodes that bound it (vx ix, ix+1; vy iy, iy+1; vz iz, iz+1) */
+        #define INT3(b, z, y, x) (((z) >= 2 && (z) <= (b).n[0] - 1 && (y) >= 2 && (y) <= (b).n[1] - 1 && (x) >= 2 && (x) <= (b).n[2] - 1) ? A3(b, z, y, x) : (REAL)0)
+        OMP_FOR
+        for (int ix = 1; ix <= gr.n[2]; ix++) for (int iy = 1; iy <= gr.n[1]; iy++) for (int iz = 1; iz <= gr.n[0]; iz++)
+            A3(gr, iz, iy, ix) = (REAL)((double)A3(gr, iz, iy, ix)
+                - (double)(REAL)(INT3(bx, iz, iy, ix) + INT3(bx, iz, iy, ix + 1)) * 0.5
+                - (double)(REAL)(INT3(by, iz, iy, ix) + INT3(by, iz, iy + 1, ix)) * 0.5
+                - (double)(REAL)(INT3(bz, iz, iy, ix) + INT3(bz, iz + 1, iy, ix)) * 0.5);
+        return;
+    }
+    OMP_FOR
+    for (int ix = 1; ix <= gr.n[2] - 2 * O; ix++) for (int iy = 1; iy <= gr.n[1] - 2 * O; iy++) for (int iz = 1; iz <= gr.n[0] - 2 * O; iz++)
+        I3(gr) = (REAL)((double)I3(gr)
+            - (double)(REAL)(A3(bx, iz + O, iy + O, ix) + A3(bx, iz + O, iy + O, ix + 1)) * 0.5
+            - (double)(REAL)(A3(by, iz + O, iy, ix + O) + A3(by, iz + O, iy + 1, ix + O)) * 0.5
+            - (double)(REAL)(A3(bz, iz, iy + O, ix + O) + A3(bz, iz + 1, iy + O, ix + O)) * 0.5);
+}
 static void compute_gradient(orc_handle* h, int issp, int unshifted) {
+    if (h->nd == 3) { compute_gradient_3d(h, issp, unshifted); return; }
     pw_t *p1 = &h->pw[0], *p2 = &h->pw[1]; shot_t* s = &p1->ss[issp];
     arr g = s->grad[GPI_INVK], pf = p1->w[GPI_P], pfp = p1->wtp[GPI_P], pap = p2->wtp[GPI_P];
     REAL dtI = h->dtI;
@@ -854,8 +890,8 @@ int orc_run(orc_handle* h, int mode, int activepw, int src_flags) {
     if (mode == GPI_MODE_FORWARD_SAVE && !h->c.store_boundary) {
         snprintf(h->err, sizeof h->err, "forward_save needs store_boundary=1 at construction (fdtd.jl:445-455)"); return 1;
     }
-    if (mode == GPI_MODE_ADJOINT && !(h->c.physics == GPI_ACOUSTIC && h->nd == 2) && h->c.npw == 2 && (activepw & 2)) {
-        snprintf(h->err, sizeof h->err, "adjoint gradient exists upstream only for 2-D acoustic (gradient.jl:31)"); return 1;
+    if (mode == GPI_MODE_ADJOINT && h->c.physics != GPI_ACOUSTIC && h->c.npw == 2 && (activepw & 2)) {
+        snprintf(h->err, sizeof h->err, "gradient imaging exists for acoustic media only (gradient.jl:17-46)"); return 1;
     }
     for (int issp = 0; issp < h->c.nshots; issp++) {
         reset_w2(h);
@@ -883,7 +919,7 @@ int orc_run(orc_handle* h, int mode, int activepw, int src_flags) {
             add_stress_source(h, it, issp, activepw, src_flags);
             if (born) born_stress(h);
             if (mode == GPI_MODE_FORWARD_SAVE) boundary_save(h, it, issp);
-            if (mode == GPI_MODE_ADJOINT && h->c.npw == 2) compute_gradient(h, issp, unshifted);
+            if (mode == GPI_MODE_ADJOINT && h->c.npw == 2 && (activepw & 2)) compute_gradient(h, issp, unshifted);
             if (h->c.nsnaps > 0 && h->itsnaps)
                 for (int k = 0; k < h->c.nsnaps; k++) if (h->itsnaps[k] == it)
                     for (int ipw = 0; ipw < h->c.npw; ipw++) if ((activepw & (1 << ipw)) && h->pw[ipw].ss[issp].usnaps)

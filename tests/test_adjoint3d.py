@@ -1,0 +1,78 @@
+"""3-D acoustic adjoint + gradient imaging.  Upstream has `gradlame!` for any dimension but `gradrho!` and
+`compute_gradient!` for 2-D only (src/fdtd/gradient.jl:17-61); the 3-D method is the same construction with a y term.
+No upstream counterpart exists to compare with, so the check is the one upstream's own gradient test uses
+(test/fwi/gradient_accuracy.jl:57-109): the adjoint-state gradient against finite differences of the loss."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+GRAD_TOL = 1e-4
+
+
+def test_gradient3d_vs_finite_differences(G, O):
+    from geophyinv_jl_b200.host import gallery
+    from scipy.ndimage import gaussian_filter
+    n = 20
+    kw, true = gallery.fwi3d(n=n, nt=170, nr=10)
+    pt = O.OraclePFdtd64(G.FdtdAcoustic(), **{**kw, "medium": true})
+    pt.update()
+    dobs = [d.copy() for d in pt.c.data[0]]
+    pa = O.OraclePFdtd64(G.FdtdAcoustic("forward_save"), **kw)
+    m = pa.get_modelvector().astype(np.float64)
+    rng = np.random.default_rng(5)
+    dK = gaussian_filter(rng.standard_normal((n, n, n)), 3.0).ravel(order="F")
+    dR = gaussian_filter(rng.standard_normal((n, n, n)), 3.0).ravel(order="F")
+    fds = {}
+    for name, dm in (("invK", np.concatenate([dK, 0 * dR])), ("rho", np.concatenate([0 * dK, dR]))):
+        dm = dm / np.abs(dm).max()
+        eps = 2e-3
+        fds[name] = ((G.lossvalue(m + eps * dm, dobs, pa) - G.lossvalue(m - eps * dm, dobs, pa)) / (2 * eps), dm)
+    for unshifted, tol_rho in ((False, 0.12), (True, 0.02)):
+        pa.unshifted_rho = unshifted
+        g = np.zeros_like(m)
+        G.gradient(g, m, dobs, pa)
+        for name, (fd, dm) in fds.items():
+            ratio = float(np.dot(g, dm)) / fd
+            print(f"3-D acoustic, unshifted={unshifted}: d loss / d {name} adjoint / finite-difference = {ratio:.4f}")
+            assert abs(ratio - 1) < (0.02 if name == "invK" else tol_rho)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("unshifted", [False, True])
+def test_gradient3d_engine_matches_oracle(G, O, unshifted):
+    from geophyinv_jl_b200.host import gallery
+    kw, true = gallery.fwi3d(n=26, nt=200, nr=12)
+    pt = O.OraclePFdtd(G.FdtdAcoustic(), **{**kw, "medium": true})
+    pt.update()
+    dobs = [d.copy() for d in pt.c.data[0]]
+    pg = G.PFdtd(G.FdtdAcoustic("forward_save"), **kw)
+    po = O.OraclePFdtd(G.FdtdAcoustic("forward_save"), **kw)
+    pg.unshifted_rho = po.unshifted_rho = unshifted
+    m = pg.get_modelvector()
+    gg, go = np.zeros_like(m), np.zeros_like(m)
+    lg, lo = G.gradient(gg, m, dobs, pg), G.gradient(go, m, dobs, po)
+    half = m.size // 2
+    eK, eR = rel_l2(gg[:half], go[:half]), rel_l2(gg[half:], go[half:])
+    print(f"3-D FWI gradient unshifted={unshifted}: invK rel-L2 {eK:.3e}, rho rel-L2 {eR:.3e}, loss {lg:.6e} vs {lo:.6e}")
+    assert abs(lg - lo) <= 1e-5 * abs(lo)
+    assert np.abs(go[:half]).max() > 0 and np.abs(go[half:]).max() > 0
+    assert eK <= GRAD_TOL and eR <= GRAD_TOL
+
+
+@pytest.mark.gpu
+def test_gradient3d_order4_engine_matches_oracle(G, O):
+    from geophyinv_jl_b200.host import gallery
+    kw, true = gallery.fwi3d(n=22, nt=150, nr=8, nss=1)
+    pt = O.OraclePFdtd(G.FdtdAcoustic(), **{**kw, "medium": true}, order=4)
+    pt.update()
+    dobs = [d.copy() for d in pt.c.data[0]]
+    pg = G.PFdtd(G.FdtdAcoustic("forward_save"), **kw, order=4)
+    po = O.OraclePFdtd(G.FdtdAcoustic("forward_save"), **kw, order=4)
+    m = pg.get_modelvector()
+    gg, go = np.zeros_like(m), np.zeros_like(m)
+    G.gradient(gg, m, dobs, pg); G.gradient(go, m, dobs, po)
+    half = m.size // 2
+    eK, eR = rel_l2(gg[:half], go[:half]), rel_l2(gg[half:], go[half:])
+    print(f"3-D FWI gradient order 4: invK rel-L2 {eK:.3e}, rho rel-L2 {eR:.3e}")
+    assert eK <= GRAD_TOL and eR <= GRAD_TOL
