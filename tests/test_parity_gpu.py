@@ -256,6 +256,49 @@ def test_fwi_gradient_acoustic2d(G, O):
         assert rel_l2(pg.engine.get_gradient(name), po.engine.get_gradient(name)) <= GRAD_TOL
 
 
+@pytest.mark.parametrize("case", ["acou2d", "elastic3d"])
+def test_simultaneous_and_coincident_sources(G, O, case):
+    """Supersources of several simultaneous sources (the reference's `ns` columns of the spray matrix, fdtd.jl:469-493) with
+    different wavelets: two sources at the same point and one within a cell of it (rows of S hit by several columns -- the
+    per-cell summation order of `mul!(buf, S, w)` matters), one source on the first interior node of the medium (its taps reach
+    the PML side), receivers that coincide, and two source fields injected in the same step."""
+    from geophyinv_jl_b200.host import gallery
+    from geophyinv_jl_b200.host.data import AGeomss, make_srcwav
+    rng = np.random.default_rng(3)
+    if case == "acou2d":
+        kw = gallery.c2_acou2d_layered(nz=70, nx=100, nt=300, nss=2, nr=8, fq=15.0, sfield="p", rfields=("p", "vz"))
+        attrib, fields, sfields = G.FdtdAcoustic, ["p", "vx", "vz"], ["p", "vz"]
+    else:
+        kw = gallery.c3_elastic3d(n=30, nt=110, nr=6, fq=25.0, rfields=("vz", "vx"))
+        attrib, fields, sfields = G.FdtdElastic, ["tauxx", "tauzz", "tauxz", "vx", "vy", "vz"], ["vz", "tauxx"]
+    grid, tgrid = kw["medium"].grid, kw["tgrid"]
+    names = ["z", "x"] if len(grid) == 2 else ["z", "y", "x"]
+    ageom = []
+    for a in kw["ageom"]:
+        s0 = [float(a.s[d][0]) for d in names]
+        pts = [s0, s0, [c + 0.4 * g.step for c, g in zip(s0, grid)], [g.first + 0.25 * g.step for g in grid]]
+        src = {d: np.array([p[i] for p in pts]) for i, d in enumerate(names)}
+        rec = {d: np.concatenate([a.r[d], a.r[d][:2]]) for d in names}            # the first two receivers twice
+        ageom.append(AGeomss(src, rec))
+    srcwav = make_srcwav(tgrid, ageom, sfields)
+    base = kw["srcwav"][0].d[list(kw["srcwav"][0].d)[0]][:, 0]
+    for s in srcwav:
+        for f in sfields:
+            amp = (1e6 if f.startswith("v") else 1.0) / (1e6 if list(kw["srcwav"][0].d)[0].startswith("v") else 1.0)
+            s.d[f][...] = (base[:, None] * amp * rng.uniform(0.5, 1.5, (1, s.n))).astype(np.float32)
+    kw = {**kw, "ageom": ageom, "srcwav": srcwav}
+    pg, po = both(G, O, attrib, kw)
+    pg.update(); po.update()
+    err, exact = compare_records(pg, po)
+    print(f"{case}: 4 simultaneous sources x 2 fields, coincident taps: rel-L2 {err:.3e}, bit-exact {exact}")
+    assert err <= REC_TOL
+    assert compare_fields(pg, po, fields) <= REC_TOL
+    # the duplicated receivers record the same samples
+    for f in pg.c.rfields:
+        d = pg.c.data[0][0].d[f]
+        assert np.array_equal(d[:, 0], d[:, -2]) and np.array_equal(d[:, 1], d[:, -1])
+
+
 @pytest.mark.parametrize("case", ["acou2d_batched", "elastic2d", "acou3d"])
 def test_boundary_save_and_force_match_oracle(G, O, case):
     """:forward_save stores 3+3 planes per axis per stored field (p | tauxx, tauxz, tauzz) and the final state;
