@@ -168,7 +168,7 @@ struct gpi_handle {
     int sample_every = 16;
     // tuning
     dim3 blk3{64, 2, 2}, blk2{128, 2, 1};
-    bool tma3 = true;  int num_sms = 148;  int tma3_ctas = 0;
+    bool tma3 = true;  int num_sms = 148;  int tma3_ctas = 0;  bool tma3_force = false;   // GPI_TMA3=2: TMA kernels whatever the tile utilisation
     struct TmaSet { const float* key = nullptr; t3::Maps* d[2] = {nullptr, nullptr}; } tmaps[2];   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
     void* encode_tiled = nullptr;                                            // cuTensorMapEncodeTiled (driver entry point)   // 3-D elastic: TMA-pipelined persistent kernels (kernels3t.cuh); GPI_TMA3=0 selects k_*3v
     bool vec2 = true;                                   // 2-D: float4-per-thread kernels (kernels2v.cuh); GPI_SCALAR2D=1 selects the scalar ones
@@ -390,7 +390,12 @@ int launch_step3t(gpi_handle* h, const StepArgs& a) {
 template <int EL>
 void launch_step_kernels3v(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
     const Geom& g = h->g;
-    if (EL && h->tma3 && nbatch == 1 && g.pzm == t3::PZM && g.nx >= 2 * g.npml + 8 && g.ny >= 2 * g.npml + 8) {
+    // The TMA tiles are 128 z cells wide: a narrow z-slab window (4 or 8 slabs of C5) would leave most lanes of its
+    // last chunk idle, while the register-staged kernels linearise (z, y) and waste nothing -- they take over below
+    // 75 % tile utilisation (C3: 339 of 384 = 0.88 -> TMA; C5 on 4 GPUs: 150 of 256 = 0.59 -> k_*3v).
+    const int zext = g.khi - g.klo + 1, zchunks = (g.pz + t3::ZC - 1) / t3::ZC;
+    const bool tiles_fill = h->tma3_force || 4 * zext >= 3 * zchunks * t3::ZC;
+    if (EL && h->tma3 && tiles_fill && nbatch == 1 && g.pzm == t3::PZM && g.nx >= 2 * g.npml + 8 && g.ny >= 2 * g.npml + 8) {
         if ((vel ? launch_step3t<0>(h, a) : launch_step3t<1>(h, a)) == 0) return;
         h->tma3 = false;                        // descriptor creation failed: fall back to the register-staged kernels
     }
@@ -757,7 +762,7 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (const char* e = getenv("GPI_BLOCK3")) { int a, b, c3; if (sscanf(e, "%d,%d,%d", &a, &b, &c3) == 3 && a * b * c3 <= 256) h->blk3 = dim3(a, b, c3); }
     if (const char* e = getenv("GPI_SCALAR3D")) h->vec3 = atoi(e) == 0;
     if (const char* e = getenv("GPI_SCALAR2D")) h->vec2 = atoi(e) == 0;
-    if (const char* e = getenv("GPI_TMA3")) h->tma3 = atoi(e) != 0;
+    if (const char* e = getenv("GPI_TMA3")) { h->tma3 = atoi(e) != 0; h->tma3_force = atoi(e) == 2; }
     if (const char* e = getenv("GPI_TMA3_CTAS")) h->tma3_ctas = atoi(e);
     if (h->nd == 3 && h->el) {
         cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);

@@ -40,7 +40,25 @@ def test_shot_sharding_and_nccl_gradient_allreduce():
 
 
 @pytest.mark.skipif(ngpus() < 2, reason="needs 2 GPUs")
-def test_zslab_decomposition_matches_single_gpu():
-    out = run_ranks("_slab_worker.py", 2)
+@pytest.mark.parametrize("tma", ["1", "2"])
+def test_zslab_decomposition_matches_single_gpu(tma):
+    """GPI_TMA3=1: kernel family chosen by tile utilisation (narrow slabs -> register-staged kernels);
+    GPI_TMA3=2: the TMA-pipelined kernels on the slab windows too."""
+    out = run_ranks("_slab_worker.py", 2, extra_env={"GPI_TMA3": tma})
     assert "SLAB_OK" in out
+    print(out.strip().splitlines()[-1])
+
+
+@pytest.mark.skipif(ngpus() < 4, reason="needs 4 GPUs")
+def test_zslab_decomposition_four_ranks():
+    """Four slabs: the two middle ranks exchange with both neighbours in both phases."""
+    out = run_ranks("_slab_worker.py", 4)
+    assert "SLAB_OK world=4" in out
+    print(out.strip().splitlines()[-1])
+
+
+@pytest.mark.skipif(ngpus() < 4, reason="needs 4 GPUs")
+def test_shot_sharding_four_ranks():
+    out = run_ranks("_nccl_worker.py", 4)
+    assert "NCCL_SHOTS_OK" in out
     print(out.strip().splitlines()[-1])

@@ -135,9 +135,12 @@ def test_elastic3d_ragged_z(G, O, n):
 
 
 @pytest.mark.parametrize("faces", [("zmax", "xmin", "ymax"), ("zmin", "ymin", "ymax"), ()])
-def test_elastic3d_partial_pml_faces(G, O, faces):
-    """CPML on a subset of faces (or none): slab logic per face, untouched faces stay untouched."""
+def test_elastic3d_partial_pml_faces(G, O, faces, monkeypatch):
+    """CPML on a subset of faces (or none): slab logic per face, untouched faces stay untouched.  GPI_TMA3=2 keeps the
+    TMA-pipelined kernels on these short z extents (by default a grid that fills < 75 % of its 128-cell z tiles runs
+    the register-staged kernels), so that two-chunk tiles with and without z slabs stay covered."""
     from geophyinv_jl_b200.host import gallery
+    monkeypatch.setenv("GPI_TMA3", "2")
     kw = gallery.c3_elastic3d(n=60, nt=230, nr=10, fq=30.0, rfields=("vz", "vy"))
     kw["pml_faces"] = list(faces)
     kw["rigid_faces"] = list(faces)
