@@ -270,7 +270,7 @@ def run_ours(args):
     peak, peak_kind = measured_peak()
     kern = {}
     # kernel names as ncu lists them: 3-D elastic runs the TMA-pipelined k_step3t<0|1> unless GPI_TMA3=0
-    if wl["ndims"] == 3 and wl["elastic"] and os.environ.get("GPI_TMA3", "1") != "0":
+    if pa.engine.kernel_family() == "tma":
         KV, KS = "k_step3t<0> (velocity)", "k_step3t<1> (stress)"
     else:
         KV, KS = ("k_vel3v", "k_stress3v") if wl["ndims"] == 3 else ("k_vel2v", "k_stress2v")
@@ -392,8 +392,8 @@ def run_c5(args):
     bv, bs = algorithmic_bytes_per_step(3, True, exn, [2, 2, 2])
     peak, peak_kind = measured_peak()
     kv, ks = allmax(vel_ms / max(vel_n, 1)), allmax(str_ms / max(str_n, 1))
-    tma = os.environ.get("GPI_TMA3", "1") != "0"      # the slab windows run the TMA-pipelined kernels too
-    KV, KS = ("k_step3t<0> (velocity)", "k_step3t<1> (stress)") if tma else ("k_vel3v", "k_stress3v")
+    fam = ex.engine.kernel_family()                      # 'tma' or 'vec4': narrow slabs run the register-staged kernels
+    KV, KS = ("k_step3t<0> (velocity)", "k_step3t<1> (stress)") if fam == "tma" else ("k_vel3v", "k_stress3v")
     roof = {"bound": "hbm", "kernel": KS, "achieved": bs / world / (ks * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": bs / world / (ks * 1e-3) / 1e9 / peak, "peak_source": peak_kind, "traffic": None, "avg_launch_ms": ks,
             "other": {KV: {"avg_launch_ms": kv, "frac": bv / world / (kv * 1e-3) / 1e9 / peak}},

@@ -387,15 +387,19 @@ int launch_step3t(gpi_handle* h, const StepArgs& a) {
     h->timers.launches += 1;
     return 0;
 }
+bool tma3_eligible(const gpi_handle* h) {
+    const Geom& g = h->g;
+    const int zext = g.khi - g.klo + 1, zchunks = (g.pz + t3::ZC - 1) / t3::ZC;
+    const bool tiles_fill = h->tma3_force || 4 * zext >= 3 * zchunks * t3::ZC;
+    return h->nd == 3 && h->el && h->c.order == 2 && h->vec3 && h->tma3 && tiles_fill && g.pzm == t3::PZM && g.nx >= 2 * g.npml + 8 && g.ny >= 2 * g.npml + 8;
+}
 template <int EL>
 void launch_step_kernels3v(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
     const Geom& g = h->g;
     // The TMA tiles are 128 z cells wide: a narrow z-slab window (4 or 8 slabs of C5) would leave most lanes of its
     // last chunk idle, while the register-staged kernels linearise (z, y) and waste nothing -- they take over below
     // 75 % tile utilisation (C3: 339 of 384 = 0.88 -> TMA; C5 on 4 GPUs: 150 of 256 = 0.59 -> k_*3v).
-    const int zext = g.khi - g.klo + 1, zchunks = (g.pz + t3::ZC - 1) / t3::ZC;
-    const bool tiles_fill = h->tma3_force || 4 * zext >= 3 * zchunks * t3::ZC;
-    if (EL && h->tma3 && tiles_fill && nbatch == 1 && g.pzm == t3::PZM && g.nx >= 2 * g.npml + 8 && g.ny >= 2 * g.npml + 8) {
+    if (EL && nbatch == 1 && tma3_eligible(h)) {
         if ((vel ? launch_step3t<0>(h, a) : launch_step3t<1>(h, a)) == 0) return;
         h->tma3 = false;                        // descriptor creation failed: fall back to the register-staged kernels
     }
@@ -1411,6 +1415,12 @@ extern "C" int gpi_set_field(gpi_handle* h, int ipw, int ib, int f, const float*
     return upload_field(h, f, in, p);
 }
 extern "C" int gpi_get_timers(gpi_handle* h, gpi_timers* out) { if (!h || !out) return 1; *out = h->timers; return 0; }
+extern "C" int gpi_kernel_family(gpi_handle* h) {
+    if (!h) return -1;
+    if (h->c.order == 4) return GPI_KERNELS_ORDER4;
+    if (h->nd == 3) return !h->vec3 ? GPI_KERNELS_SCALAR : (h->B == 1 && tma3_eligible(h)) ? GPI_KERNELS_TMA : GPI_KERNELS_VEC4;
+    return h->vec2 ? GPI_KERNELS_VEC4 : GPI_KERNELS_SCALAR;
+}
 
 // =================================================================================================
 // NCCL (loaded lazily so the library also loads where libnccl is absent)

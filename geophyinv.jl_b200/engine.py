@@ -66,7 +66,7 @@ EXPORTS = [
     "gpi_update_dmod", "gpi_set_medium_pert", "gpi_update_born", "gpi_set_pml", "gpi_set_sparse", "gpi_set_wavelets", "gpi_run", "gpi_get_records",
     "gpi_get_gradient", "gpi_get_snap", "gpi_set_snap_steps", "gpi_get_field", "gpi_set_field", "gpi_reset",
     "gpi_nccl_unique_id", "gpi_nccl_init", "gpi_allreduce_gradients", "gpi_records_device_ptr",
-    "gpi_gradient_device_ptr", "gpi_set_stream", "gpi_synchronize", "gpi_get_timers", "gpi_field_shape", "gpi_field_shape_order",
+    "gpi_gradient_device_ptr", "gpi_set_stream", "gpi_synchronize", "gpi_get_timers", "gpi_kernel_family", "gpi_field_shape", "gpi_field_shape_order",
 ]
 
 _lib = None
@@ -118,6 +118,7 @@ def load_library(path: str = LIB_PATH):
         "gpi_get_timers": ([vp, C.POINTER(GpiTimers)], C.c_int),
         "gpi_field_shape": ([C.c_int, C.c_int, C.c_int, ip, ip], C.c_int),
         "gpi_field_shape_order": ([C.c_int, C.c_int, C.c_int, C.c_int, ip, ip], C.c_int),
+        "gpi_kernel_family": ([vp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)
@@ -280,6 +281,10 @@ class Engine:
 
     def reset(self, what: int):
         self._ck(self.lib.gpi_reset(self.h, what))
+
+    def kernel_family(self) -> str:
+        """Which stencil kernels `run` launches: 'scalar', 'vec4' (k_*2v / k_*3v), 'tma' (t3::k_step3t) or 'order4'."""
+        return {0: "scalar", 1: "vec4", 2: "tma", 4: "order4"}[self.lib.gpi_kernel_family(self.h)]
 
     def timers(self) -> dict:
         t = GpiTimers()
