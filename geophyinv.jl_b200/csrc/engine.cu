@@ -275,7 +275,9 @@ dim3 grid_for(const gpi_handle* h, dim3 blk, int nbatch) {
     return dim3((g.khi + 1 + blk.x - 1) / blk.x, (g.nx1 + blk.y - 1) / blk.y, nbatch);
 }
 
-void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch) {
+// `merged`: both wavefields of every resident shot in ONE launch.  The wavefield sets are laid out [b][pw][slot] and the
+// CPML memory [b][pw][term], so slot b' = b * npw + ipw of a launch with the per-pw strides is wavefield ipw of shot b.
+void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch, bool merged = false) {
     memset(&a, 0, sizeof a);
     for (int s = 0; s < 6; s++) a.tau[s] = h->slot_tau[s] >= 0 ? h->W + (long long)ipw * h->pwstride + (long long)h->slot_tau[s] * h->g.vol : nullptr;
     for (int s = 0; s < 3; s++) a.v[s] = h->slot_v[s] >= 0 ? h->W + (long long)ipw * h->pwstride + (long long)h->slot_v[s] * h->g.vol : nullptr;
@@ -293,11 +295,11 @@ void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch) {
             p.b = h->pmlcoef + ((size_t)t.dfield * 3 + 1) * np2;
             p.kI = h->pmlcoef + ((size_t)t.dfield * 3 + 2) * np2;
         }
-        p.bstride = (long long)h->npw * h->mem_per_pw;
+        p.bstride = merged ? h->mem_per_pw : (long long)h->npw * h->mem_per_pw;
         (t.vel ? a.pv : a.ps)[t.idx] = p;
     }
-    a.wstride = h->bstride;
-    a.nbatch = nbatch;
+    a.wstride = merged ? h->pwstride : h->bstride;
+    a.nbatch = merged ? nbatch * h->npw : nbatch;
 }
 
 // TMA descriptors of the operand boxes of kernels3t.cuh.  Every field / coefficient array is a rank-3 tensor
@@ -581,9 +583,24 @@ static int create_impl(gpi_handle* h) {
     g.koff = 0; g.klo = 0; g.khi = g.nz + 2 * g.h;
     h->ka = 0; h->kb = g.nz + 1;
     if (h->slab) {
-        const long long nodes = g.nz + 1;
-        h->ka = (int)(nodes * h->srank / h->snranks);
-        h->kb = (int)(nodes * (h->srank + 1) / h->snranks);
+        // Planes inside the z-CPML slabs move three extra memory variables per kernel (48 B on top of 140 B per cell and
+        // step in 3-D elastic, 16 on top of 64 in 3-D acoustic), so the end ranks get proportionally fewer planes:
+        // boundaries at equal cumulated weight, weight = 1 + alpha inside a z slab.
+        const int nodes = g.nz + 1;
+        const double alpha = h->el ? 48.0 / 140.0 : 16.0 / 64.0;
+        std::vector<double> cum(nodes + 1, 0.0);
+        for (int k = 0; k < nodes; k++) {
+            const bool inslab = ((c.pml_faces & ZMIN) && k < c.npml) || ((c.pml_faces & ZMAX) && k >= nodes - 1 - c.npml);
+            cum[k + 1] = cum[k] + 1.0 + (inslab ? alpha : 0.0);
+        }
+        auto cut = [&](int r) {
+            if (r <= 0) return 0;
+            if (r >= h->snranks) return nodes;
+            const double target = cum[nodes] * r / h->snranks;
+            return (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+        };
+        h->ka = cut(h->srank);
+        h->kb = cut(h->srank + 1);
         if (h->kb - h->ka < 4) FAIL(h, "z-slab of rank %d has only %d planes", h->srank, h->kb - h->ka);
         g.koff = h->srank == 0 ? 0 : ((h->ka - 1) / 4) * 4;
         g.klo = h->ka - g.koff;
@@ -1259,6 +1276,10 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
         const bool inj_s = any_post(h->h_post_s, nb, false), rec_s = any_post(h->h_post_s, nb, true);
         StepArgs args[2];
         for (int ipw = 0; ipw < h->npw; ipw++) fill_args(h, args[ipw], ipw, nb);
+        // adjoint / two-wavefield runs without the FD-Born write-out: pw 1 and pw 2 of all resident shots share each launch
+        const bool merge_pw = h->npw == 2 && (activepw & 3) == 3 && !born && h->c.order == 2 && h->nd == 2;
+        StepArgs margs;
+        if (merge_pw) fill_args(h, margs, 0, nb, true);
         if (born) { args[0].dout[0] = h->born_d; args[0].dout[1] = h->born_d + g.vol; args[0].dstride = 2 * g.vol; }
         // record!(1, ..., [:p]) at the start of step 1 (zero unless the fields were loaded from snapshots)
         if (rec_s) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, 1, 1, nt, (float)h->c.dt, 2); h->timers.launches += 1; }
@@ -1271,7 +1292,8 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                 if (launch_boundary(h, false, nb, nt - it)) return 1;
             }
             const bool sample = h->sample_every > 0 && (it % h->sample_every) == 0;
-            for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], true, nb, sample && ipw == 0);
+            if (merge_pw) launch_step(h, margs, true, margs.nbatch, sample);
+            else for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], true, nb, sample && ipw == 0);
             if (born) {        // add_born_sources_velocity! (propagate.jl:205)
                 dim3 blk = h->blk2, grd = grid_for(h, blk, nb);
                 k_born_add<0><<<grd, blk, 0, h->stream>>>(g, args[1].v[V_X], args[1].v[V_Z], h->born_d, h->born_d + g.vol, h->born_c[1], h->born_c[2], h->bstride, 2 * g.vol);
@@ -1279,7 +1301,8 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             }
             if (do_post_v) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_v, it, it, nt, (float)h->c.dt, 3); h->timers.launches += 1; }
             if (exchange_halos(h, 1)) return 1;
-            for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], false, nb, sample && ipw == 0);
+            if (merge_pw) launch_step(h, margs, false, margs.nbatch, sample);
+            else for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], false, nb, sample && ipw == 0);
             if (born) {        // add_born_sources_stress! (propagate.jl:226)
                 dim3 blk = h->blk2, grd = grid_for(h, blk, nb);
                 k_born_add<1><<<grd, blk, 0, h->stream>>>(g, args[1].tau[T_XX], nullptr, h->born_d, h->born_d + g.vol, h->born_c[0], nullptr, h->bstride, 2 * g.vol);
