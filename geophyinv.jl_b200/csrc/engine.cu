@@ -155,7 +155,7 @@ struct gpi_handle {
     // FD-Born (2-D acoustic): medium perturbation, scattering coefficients (d dtK, d bx, d bz), derivative scratch [B][2][vol]
     float* modp[GPI_NPARAM] = {};  float* born_c[3] = {};  float* born_d = nullptr;  bool born_ready = false;
     // gradients (acoustic 2-D): total + per batch slot
-    float* gtot[GPI_NPARAM] = {};  float* gshot = nullptr;   // gshot[b][2][vol]
+    float* gtot[GPI_NPARAM] = {};  float* gshot = nullptr;  int ngrad = 0;  int gparam[3] = {};   // gshot[b][ngrad][vol]; gparam: parameter of each slot
     std::vector<ShotData> shots[2];
     std::vector<int32_t> itsnaps;
     PostDesc *post_v = nullptr, *post_s = nullptr, *h_post_v = nullptr, *h_post_s = nullptr;
@@ -707,11 +707,14 @@ static int create_impl(gpi_handle* h) {
     CU(h, cudaMalloc((void**)&h->dmod_table, C_N * sizeof(float*)));
     CU(h, cudaMemcpy(h->dmod_table, h->dmod, C_N * sizeof(float*), cudaMemcpyHostToDevice));
 
-    // gradients exist upstream for acoustic media (fdtd.jl:164-170); imaging only in 2-D (gradient.jl:31)
-    if (!h->el && h->npw == 2) {
-        if (alloc_vol(&h->gtot[GPI_INVK]) || alloc_vol(&h->gtot[GPI_RHO])) return 1;
-        CU(h, cudaMalloc((void**)&h->gshot, (size_t)B * 2 * vb));
-        CU(h, cudaMemset(h->gshot, 0, (size_t)B * 2 * vb));
+    // gradients exist upstream for acoustic media (fdtd.jl:164-170; imaging 2-D only, gradient.jl:31); here also 3-D acoustic
+    // and 2-D elastic (kernels.cuh k_grad3d, k_grad2d_el)
+    if (h->npw == 2 && (!h->el || h->nd == 2)) {
+        if (!h->el) { h->ngrad = 2; h->gparam[0] = GPI_INVK; h->gparam[1] = GPI_RHO; }
+        else        { h->ngrad = 3; h->gparam[0] = GPI_INVLAMBDA; h->gparam[1] = GPI_INVMU; h->gparam[2] = GPI_RHO; }
+        for (int q = 0; q < h->ngrad; q++) if (alloc_vol(&h->gtot[h->gparam[q]])) return 1;
+        CU(h, cudaMalloc((void**)&h->gshot, (size_t)B * h->ngrad * vb));
+        CU(h, cudaMemset(h->gshot, 0, (size_t)B * h->ngrad * vb));
     }
 
     // per-shot state
@@ -1089,7 +1092,7 @@ extern "C" int gpi_reset(gpi_handle* h, int what) {
     }
     if (what & GPI_RESET_GRADIENTS) {
         for (auto& p : h->gtot) if (p) CU(h, cudaMemsetAsync(p, 0, vb, h->stream));
-        if (h->gshot) CU(h, cudaMemsetAsync(h->gshot, 0, (size_t)h->B * 2 * vb, h->stream));
+        if (h->gshot) CU(h, cudaMemsetAsync(h->gshot, 0, (size_t)h->B * h->ngrad * vb, h->stream));
     }
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
@@ -1245,7 +1248,8 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     if (mode == GPI_MODE_FORWARD_SAVE && !h->c.store_boundary) FAIL(h, "forward_save needs store_boundary=1 at construction (fdtd.jl:445-455)");
     if (mode == GPI_MODE_ADJOINT && !h->c.store_boundary) FAIL(h, "adjoint needs the boundary store of a forward_save run");
     const bool grad = mode == GPI_MODE_ADJOINT && (activepw & 2) && h->npw == 2;
-    if (grad && h->el) FAIL(h, "gradient imaging exists for acoustic media only (gradient.jl:17-46; 3-D: kernels.cuh k_grad3d)");
+    if (grad && !h->gshot) FAIL(h, "no gradient imaging for 3-D elastic media (no boundary store upstream, boundary.jl:215-264)");
+    if (unshifted && h->el) FAIL(h, "the exact-transpose rho imaging is defined for acoustic media");
     if (mode == GPI_MODE_ADJOINT && h->el && h->nd == 3) FAIL(h, "3-D elastic has no boundary_save! upstream (boundary.jl:215-264)");
     const Geom& g = h->g;
     const int nt = h->c.nt;
@@ -1262,7 +1266,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
         CU(h, cudaMemsetAsync(h->W, 0, (size_t)nb * h->bstride * sizeof(float), h->stream));
         if (h->TP) CU(h, cudaMemsetAsync(h->TP, 0, (size_t)nb * h->bstride * sizeof(float), h->stream));
         CU(h, cudaMemsetAsync(h->MEM, 0, (size_t)nb * h->npw * h->mem_per_pw * sizeof(float), h->stream));
-        if (grad) CU(h, cudaMemsetAsync(h->gshot, 0, (size_t)nb * 2 * vb, h->stream));
+        if (grad) CU(h, cudaMemsetAsync(h->gshot, 0, (size_t)nb * h->ngrad * vb, h->stream));
         if (mode == GPI_MODE_ADJOINT) {       // boundary_force_snap_tau!/v! (boundary.jl:173-212)
             for (int b = 0; b < nb; b++) {
                 ShotData& s = h->shots[0][shot0 + b];
@@ -1315,7 +1319,20 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             }
             if (exchange_halos(h, 0)) return 1;
             if (mode == GPI_MODE_FORWARD_SAVE && launch_boundary(h, true, nb, it - 1)) return 1;
-            if (grad && h->nd == 3) {
+            if (grad && h->el) {
+                GradE2Args ga;
+                ga.xx1 = wf_ptr(h, h->W, 0, 0, GPI_TAUXX); ga.zz1 = wf_ptr(h, h->W, 0, 0, GPI_TAUZZ); ga.xz1 = wf_ptr(h, h->W, 0, 0, GPI_TAUXZ);
+                ga.xx1tp = wf_ptr(h, h->TP, 0, 0, GPI_TAUXX); ga.zz1tp = wf_ptr(h, h->TP, 0, 0, GPI_TAUZZ); ga.xz1tp = wf_ptr(h, h->TP, 0, 0, GPI_TAUXZ);
+                ga.xx2tp = wf_ptr(h, h->TP, 0, 1, GPI_TAUXX); ga.zz2tp = wf_ptr(h, h->TP, 0, 1, GPI_TAUZZ); ga.xz2tp = wf_ptr(h, h->TP, 0, 1, GPI_TAUXZ);
+                ga.vx1 = wf_ptr(h, h->W, 0, 0, GPI_VX); ga.vx1tp = wf_ptr(h, h->TP, 0, 0, GPI_VX); ga.vx2tp = wf_ptr(h, h->TP, 0, 1, GPI_VX);
+                ga.vz1 = wf_ptr(h, h->W, 0, 0, GPI_VZ); ga.vz1tp = wf_ptr(h, h->TP, 0, 0, GPI_VZ); ga.vz2tp = wf_ptr(h, h->TP, 0, 1, GPI_VZ);
+                ga.il = h->mod[GPI_INVLAMBDA]; ga.im = h->mod[GPI_INVMU];
+                ga.gL = h->gshot; ga.gM = h->gshot + g.vol; ga.gR = h->gshot + 2 * g.vol;
+                ga.wstride = h->bstride; ga.gstride = 3 * g.vol;
+                dim3 blk = h->blk2, grd = grid_for(h, blk, nb);
+                k_grad2d_el<<<grd, blk, 0, h->stream>>>(g, ga, (float)h->c.dtI);
+                h->timers.launches += 1;
+            } else if (grad && h->nd == 3) {
                 for (int b = 0; b < nb; b++) {
                     Grad3Args ga;
                     ga.p1 = wf_ptr(h, h->W, b, 0, GPI_P); ga.p1tp = wf_ptr(h, h->TP, b, 0, GPI_P); ga.p2tp = wf_ptr(h, h->TP, b, 1, GPI_P);
@@ -1352,9 +1369,9 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                 CU(h, cudaMemcpyAsync(h->shots[0][shot0 + b].snap[vf[i]], wf_ptr(h, h->W, b, 0, vf[i]), vb, cudaMemcpyDeviceToDevice, h->stream));
         // sum_grads! (gradient.jl:2-11): stack in shot order
         if (grad) for (int b = 0; b < nb; b++) {
-            k_axpy1<<<(unsigned)((g.vol + 255) / 256), 256, 0, h->stream>>>(h->gtot[GPI_INVK], h->gshot + (size_t)b * 2 * g.vol, g.vol);
-            k_axpy1<<<(unsigned)((g.vol + 255) / 256), 256, 0, h->stream>>>(h->gtot[GPI_RHO], h->gshot + (size_t)b * 2 * g.vol + g.vol, g.vol);
-            h->timers.launches += 2;
+            for (int q = 0; q < h->ngrad; q++)
+                k_axpy1<<<(unsigned)((g.vol + 255) / 256), 256, 0, h->stream>>>(h->gtot[h->gparam[q]], h->gshot + ((size_t)b * h->ngrad + q) * g.vol, g.vol);
+            h->timers.launches += h->ngrad;
         }
         // z-slabs: every rank holds the partial sums of the taps it owns; one sum all-reduce per record block
         if (h->slab) for (int b = 0; b < nb; b++) for (int f = 0; f < GPI_NWAVEFIELD; f++) {
@@ -1410,7 +1427,7 @@ extern "C" int gpi_records_device_ptr(gpi_handle* h, int ipw, int issp, int f, v
 extern "C" int gpi_get_gradient(gpi_handle* h, int p, float* out) {
     GUARD(h);
     if (p < 0 || p >= GPI_NPARAM || !h->gtot[p]) FAIL(h, "no gradient for parameter %d (gradients exist for acoustic npw=2 experiments)", p);
-    return download_field(h, GPI_P, h->gtot[p], out);
+    return download_field(h, h->el ? GPI_TAUXX : GPI_P, h->gtot[p], out);
 }
 extern "C" int gpi_gradient_device_ptr(gpi_handle* h, int p, void** dptr, int64_t* nfloats) {
     GUARD(h);

@@ -625,6 +625,61 @@ __global__ void k_grad2d(const Geom g, const float* __restrict__ p1, const float
 }
 
 // ------------------------------------------------------------------------------------------------
+// gradient imaging, 2-D elastic (nothing upstream -- gradient.jl has acoustic methods only).  The
+// adjoint-state construction of gradlame!/gradrho! written for the compliance form of the stress update:
+//   e = (txx2 + tzz2)_tp * ((txx1 + tzz1)_tp - (txx1 + tzz1)) * dtI     isotropic part,  dS = dc/4, c = 1/(lambda + mu)
+//   d = (txx2 - tzz2)_tp * ((txx1 - tzz1)_tp - (txx1 - tzz1)) * dtI     deviatoric part, dS = d(invmu)/4
+//   s = txz2_tp * (txz1_tp - txz1) * dtI  on the shear nodes, a quarter of it to each cell of the node's @av(invmu)
+//   g_invlambda += e/4 * dc/d(invlambda);  g_invmu += e/4 * dc/d(invmu) + d/4 + sum s/4;  g_rho as in k_grad2d
+// with c = invlambda * invmu / (invlambda + invmu).  Operation order = oracle/fdtd_oracle.c::compute_gradient_el2d.
+// ------------------------------------------------------------------------------------------------
+struct GradE2Args {
+    const float *xx1, *zz1, *xz1, *xx1tp, *zz1tp, *xz1tp, *xx2tp, *zz2tp, *xz2tp;
+    const float *vx1, *vx1tp, *vx2tp, *vz1, *vz1tp, *vz2tp;
+    const float *il, *im;                 // invlambda, invmu (shared by all shots)
+    float *gL, *gM, *gR;                  // batch slot 0
+    long long wstride, gstride;
+};
+__global__ void k_grad2d_el(const Geom g, const GradE2Args a, float dtI) {
+    int k, j, i, b;
+    if (!cell<2>(g, 1, k, j, i, b)) return;
+    if (k > g.nz - 1 || i > g.nx - 1) return;            // (k, i): tauii node
+    const long long w = (long long)b * a.wstride, gw = (long long)b * a.gstride;
+    const long long c = uidx(g, k + g.h, 0, i + g.h), sx = g.pz;
+    const long long q = c + w;
+    const float e = __fmul_rn(__fmul_rn(__fadd_rn(a.xx2tp[q], a.zz2tp[q]), __fsub_rn(__fadd_rn(a.xx1tp[q], a.zz1tp[q]), __fadd_rn(a.xx1[q], a.zz1[q]))), dtI);
+    const float d = __fmul_rn(__fmul_rn(__fsub_rn(a.xx2tp[q], a.zz2tp[q]), __fsub_rn(__fsub_rn(a.xx1tp[q], a.zz1tp[q]), __fsub_rn(a.xx1[q], a.zz1[q]))), dtI);
+    const float la = a.il[c], mb = a.im[c], ab = __fadd_rn(la, mb);
+    const float ab2 = __fmul_rn(ab, ab);
+    const float dca = __fdiv_rn(__fmul_rn(mb, mb), ab2), dcb = __fdiv_rn(__fmul_rn(la, la), ab2);
+    const float qe = __fmul_rn(0.25f, e);
+    a.gL[gw + c] = __fadd_rn(a.gL[gw + c], __fmul_rn(qe, dca));
+    float gm = __fadd_rn(__fadd_rn(a.gM[gw + c], __fmul_rn(qe, dcb)), __fmul_rn(0.25f, d));
+    // shear nodes whose @av(invmu) contains this cell: array indices (iz - dz, ix - dx), dz, dx in {0, 1}, i.e. unified
+    // (k + 1 + h - dz, i + 1 + h - dx); the tauxz array covers unified [1 + h, n - 1 - h]
+    float acc = 0.f;
+#pragma unroll
+    for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+        for (int dz = 0; dz < 2; dz++) {
+            const int ku = k + 1 + g.h - dz, iu = i + 1 + g.h - dx;
+            if (ku < 1 + g.h || ku > g.nz - 1 - g.h || iu < 1 + g.h || iu > g.nx - 1 - g.h) continue;
+            const long long s = uidx(g, ku + g.h, 0, iu + g.h) + w;
+            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(a.xz2tp[s], __fsub_rn(a.xz1tp[s], a.xz1[s])), dtI));
+        }
+    a.gM[gw + c] = __fadd_rn(gm, __fmul_rn(0.25f, acc));
+    const int o = 1 + 2 * g.h;
+    if (k >= o && k <= g.nz - 1 - o && i >= o && i <= g.nx - 1 - o) {
+        auto bufx = [&](long long x) { return __fmul_rn(__fmul_rn(a.vx2tp[w + x], __fsub_rn(a.vx1[w + x], a.vx1tp[w + x])), dtI); };
+        auto bufz = [&](long long x) { return __fmul_rn(__fmul_rn(a.vz2tp[w + x], __fsub_rn(a.vz1[w + x], a.vz1tp[w + x])), dtI); };
+        const long long q1 = 3 * g.h + 1, q0 = 3 * g.h;
+        const float ax = __fadd_rn(bufx(c - q1 * sx), bufx(c - q0 * sx));
+        const float az = __fadd_rn(bufz(c - q1), bufz(c - q0));
+        a.gR[gw + c] = (float)((double)a.gR[gw + c] - (double)ax * 0.5 - (double)az * 0.5);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // gradient imaging, 3-D acoustic.  gradlame! (gradient.jl:17-29) is dimension-free; gradrho! exists
 // upstream for 2-D only (gradient.jl:31,58-61).  Same construction with the y term between x and z:
 //   g_rho_inn -= av_xi(bx) + av_yi(by) + av_zi(bz),   b? = v?2_tp * (v?1 - v?1_tp) * dtI

@@ -254,7 +254,7 @@ class Engine:
         return out.reshape((self.cfg.nt, nr), order="F")
 
     def get_gradient(self, name: str):
-        shp = self.field_shape("p")
+        shp = self.field_shape("p" if self.cfg.physics == ACOUSTIC else "tauxx")
         out = np.empty(int(np.prod(shp)), np.float32)
         self._ck(self.lib.gpi_get_gradient(self.h, PARAM[name], _fp(out)))
         return out.reshape(shp, order="F")

@@ -409,11 +409,12 @@ class PFdtd:
             else:
                 self.engine.run(mode, upa["activepw"], upa["src_flags"])
         # sum_grads! (propagate.jl:110-117, gradient.jl:2-11)
-        if mode == "adjoint" and c.ic["npw"] == 2 and c.attrib_mod.physics == "acoustic":
+        has_grad = c.attrib_mod.physics == "acoustic" or c.medium.ndims == 2      # 3-D elastic has no boundary store, hence no adjoint
+        if mode == "adjoint" and c.ic["npw"] == 2 and 2 in upa["activepw"] and has_grad:
             if self._nccl:
                 self.engine.allreduce_gradients()
             self._grad_dirty = True
-            for name in ("invK", "rho"):
+            for name in c.mparams:
                 c.gradients[name][...] = self.engine.get_gradient(name)
         # update_datamat! + update_data! (propagate.jl:119-133, receiver.jl:17-46)
         for ipw in upa["activepw"]:

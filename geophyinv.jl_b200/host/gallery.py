@@ -174,3 +174,30 @@ def fwi3d(n=24, nt=220, nr=12, nss=2, dt=1e-3, fq=18.0, d=10.0, box=0.05, seed=1
     true.vp[a:b, a:b, a:b] *= F32(1 + box)
     true.rho[a:b, a:b, a:b] *= F32(1 + box)
     return kw, true
+
+
+def fwi2d_elastic(nz=44, nx=56, nt=420, nr=16, nss=2, dt=1e-3, fq=12.0, d=10.0, box=0.05, seed=13):
+    """2-D elastic FWI gradient case: smooth random model, 'observed' data from the same medium with a
+    +5 % box in vp, vs and rho.  Sources :vz, records :vz and :vx (adjoint injection exists only for velocity fields)."""
+    from scipy.ndimage import gaussian_filter
+    grid = [StepRange(0.0, d, nz), StepRange(0.0, d, nx)]
+    rng = np.random.default_rng(seed)
+    sm = lambda: gaussian_filter(rng.standard_normal((nz, nx)), 3.0) / 0.08
+    vp = (3000.0 * (1 + 0.015 * sm())).astype(F32)
+    vs = (1600.0 * (1 + 0.015 * sm())).astype(F32)
+    rho = (2300.0 * (1 + 0.015 * sm())).astype(F32)
+    medium = Medium(grid, vp, rho, vs)
+    tgrid = StepRange(0.0, dt, nt)
+    Lz, Lx = grid[0].last, grid[1].last
+    ageom = []
+    for iss in range(nss):
+        sx = (0.25 + 0.5 * iss / max(nss - 1, 1)) * Lx + 0.37 * d
+        ageom.append(AGeomss({"z": [0.15 * Lz + 0.21 * d], "x": [sx]}, {"z": np.full(nr, 0.85 * Lz + 0.6 * d), "x": np.linspace(0.05 * Lx, 0.95 * Lx, nr)}))
+    wav = _ricker(fq, tgrid, 1.5 / fq + 0.005) * 1e6
+    srcwav = make_srcwav(tgrid, ageom, ["vz"], wav)
+    kw = dict(medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=["vz", "vx"], pml_faces=["zmin", "zmax", "xmin", "xmax"])
+    true = medium.copy()
+    z0, z1, x0, x1 = int(0.4 * nz), int(0.6 * nz), int(0.4 * nx), int(0.6 * nx)
+    for a in (true.vp, true.vs, true.rho):
+        a[z0:z1, x0:x1] *= F32(1 + box)
+    return kw, true

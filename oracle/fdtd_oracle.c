@@ -784,7 +784,61 @@ static void compute_gradient_3d(orc_handle* h, int issp, int unshifted) {
             - (double)(REAL)(A3(by, iz + O, iy, ix + O) + A3(by, iz + O, iy + 1, ix + O)) * 0.5
             - (double)(REAL)(A3(bz, iz, iy + O, ix + O) + A3(bz, iz + 1, iy + O, ix + O)) * 0.5);
 }
+/* 2-D elastic imaging (nothing upstream: gradient.jl has acoustic methods only).  Same adjoint-state
+ * construction as gradlame!/gradrho! -- "adjoint field at the previous step times the change of the forward field over the
+ * step, times dtI" -- written for the compliance form of the stress update, S dtau/dt = -eps(v):
+ *     e   = (txx2 + tzz2)_tp * ((txx1 + tzz1)_tp - (txx1 + tzz1)) * dtI        (isotropic part,  dS = dc/4,  c = 1/(lambda+mu))
+ *     d   = (txx2 - tzz2)_tp * ((txx1 - tzz1)_tp - (txx1 - tzz1)) * dtI        (deviatoric part, dS = dinvmu/4)
+ *     s   =  txz2_tp * (txz1_tp - txz1) * dtI   on the shear grid, spread back to the four cells its @av(invmu) averages
+ *     g_invlambda += e/4 * dc/dinvlambda,   g_invmu += e/4 * dc/dinvmu + d/4 + sum_4 s/4
+ * with c = invlambda*invmu/(invlambda+invmu).  g_rho is gradrho! unchanged (it only involves the velocities).
+ * Checked against finite differences of the loss in tests/test_adjoint3d.py. */
+static void compute_gradient_el2d(orc_handle* h, int issp) {
+    pw_t *p1 = &h->pw[0], *p2 = &h->pw[1]; shot_t* s = &p1->ss[issp];
+    arr gl = s->grad[GPI_INVLAMBDA], gm = s->grad[GPI_INVMU], gr = s->grad[GPI_RHO];
+    arr il = h->mod[GPI_INVLAMBDA], im = h->mod[GPI_INVMU];
+    arr xx1 = p1->w[GPI_TAUXX], zz1 = p1->w[GPI_TAUZZ], xz1 = p1->w[GPI_TAUXZ];
+    arr xx1p = p1->wtp[GPI_TAUXX], zz1p = p1->wtp[GPI_TAUZZ], xz1p = p1->wtp[GPI_TAUXZ];
+    arr xx2p = p2->wtp[GPI_TAUXX], zz2p = p2->wtp[GPI_TAUZZ], xz2p = p2->wtp[GPI_TAUXZ];
+    REAL dtI = h->dtI;
+    const int O = g_O;
+    OMP_FOR
+    for (int ix = 1; ix <= gl.n[2]; ix++) for (int iz = 1; iz <= gl.n[0]; iz++) {
+        const REAL e = (A2(xx2p, iz, ix) + A2(zz2p, iz, ix)) * ((A2(xx1p, iz, ix) + A2(zz1p, iz, ix)) - (A2(xx1, iz, ix) + A2(zz1, iz, ix))) * dtI;
+        const REAL d = (A2(xx2p, iz, ix) - A2(zz2p, iz, ix)) * ((A2(xx1p, iz, ix) - A2(zz1p, iz, ix)) - (A2(xx1, iz, ix) - A2(zz1, iz, ix))) * dtI;
+        const REAL a = A2(il, iz, ix), b = A2(im, iz, ix), ab = a + b;
+        const REAL dca = (b * b) / (ab * ab), dcb = (a * a) / (ab * ab);
+        A2(gl, iz, ix) = A2(gl, iz, ix) + (REAL)0.25 * e * dca;
+        A2(gm, iz, ix) = A2(gm, iz, ix) + (REAL)0.25 * e * dcb + (REAL)0.25 * d;
+    }
+    /* shear part: tauxz[jz, jx] uses @av(invmu) of the cells (jz, jx), (jz+1, jx), (jz, jx+1), (jz+1, jx+1) in array indices, whatever
+     * the order (diff2D.jl:222-225): every cell collects a quarter of the (up to) four shear nodes whose average contains it */
+    const int hh = 0;
+    OMP_FOR
+    for (int ix = 1; ix <= gm.n[2]; ix++) for (int iz = 1; iz <= gm.n[0]; iz++) {
+        REAL acc = 0;
+        for (int dx = 0; dx < 2; dx++) for (int dz = 0; dz < 2; dz++) {
+            const int jz = iz - dz - hh, jx = ix - dx - hh;          /* shear node whose average contains cell (iz, ix) */
+            if (jz < 1 || jz > xz1.n[0] || jx < 1 || jx > xz1.n[2]) continue;
+            acc = acc + A2(xz2p, jz, jx) * (A2(xz1p, jz, jx) - A2(xz1, jz, jx)) * dtI;
+        }
+        A2(gm, iz, ix) = A2(gm, iz, ix) + (REAL)0.25 * acc;
+    }
+    const int vf[2] = {GPI_VX, GPI_VZ};
+    for (int k = 0; k < 2; k++) {
+        arr b = p1->vbuf[vf[k]], v = p1->w[vf[k]], vp = p1->wtp[vf[k]], va = p2->wtp[vf[k]];
+        OMP_FOR
+        for (size_t i = 0; i < b.len; i++) b.d[i] = va.d[i] * (v.d[i] - vp.d[i]) * dtI;
+    }
+    arr bx = p1->vbuf[GPI_VX], bz = p1->vbuf[GPI_VZ];
+    OMP_FOR
+    for (int ix = 1; ix <= gr.n[2] - 2 * O; ix++) for (int iz = 1; iz <= gr.n[0] - 2 * O; iz++)
+        A2(gr, iz + O, ix + O) = (REAL)((double)A2(gr, iz + O, ix + O)
+            - (double)(REAL)(A2(bx, iz + O, ix) + A2(bx, iz + O, ix + 1)) * 0.5
+            - (double)(REAL)(A2(bz, iz, ix + O) + A2(bz, iz + 1, ix + O)) * 0.5);
+}
 static void compute_gradient(orc_handle* h, int issp, int unshifted) {
+    if (h->c.physics == GPI_ELASTIC) { compute_gradient_el2d(h, issp); return; }
     if (h->nd == 3) { compute_gradient_3d(h, issp, unshifted); return; }
     pw_t *p1 = &h->pw[0], *p2 = &h->pw[1]; shot_t* s = &p1->ss[issp];
     arr g = s->grad[GPI_INVK], pf = p1->w[GPI_P], pfp = p1->wtp[GPI_P], pap = p2->wtp[GPI_P];
@@ -881,6 +935,7 @@ int orc_run(orc_handle* h, int mode, int activepw, int src_flags) {
     const int born = (mode & GPI_RUN_BORN) != 0, unshifted = (mode & GPI_RUN_UNSHIFTED_RHO) != 0;
     mode &= ~(GPI_RUN_BORN | GPI_RUN_UNSHIFTED_RHO);
     g_O = h->c.order - 1;
+    if (unshifted && h->c.physics == GPI_ELASTIC) { snprintf(h->err, sizeof h->err, "the exact-transpose rho imaging is defined for acoustic media"); return 1; }
     if ((born || unshifted) && h->c.order != 2) { snprintf(h->err, sizeof h->err, "FD-Born and its exact-transpose imaging are defined for order 2 only"); return 1; }
     if (born && (h->nd != 2 || h->c.physics != GPI_ACOUSTIC || h->c.npw != 2 || (activepw & 3) != 3 || mode == GPI_MODE_ADJOINT || !h->born_ready)) {
         snprintf(h->err, sizeof h->err, "FD-Born needs a 2-D acoustic experiment, both wavefields active, a forward mode and orc_update_born"); return 1;
@@ -890,8 +945,8 @@ int orc_run(orc_handle* h, int mode, int activepw, int src_flags) {
     if (mode == GPI_MODE_FORWARD_SAVE && !h->c.store_boundary) {
         snprintf(h->err, sizeof h->err, "forward_save needs store_boundary=1 at construction (fdtd.jl:445-455)"); return 1;
     }
-    if (mode == GPI_MODE_ADJOINT && h->c.physics != GPI_ACOUSTIC && h->c.npw == 2 && (activepw & 2)) {
-        snprintf(h->err, sizeof h->err, "gradient imaging exists for acoustic media only (gradient.jl:17-46)"); return 1;
+    if (mode == GPI_MODE_ADJOINT && h->c.physics != GPI_ACOUSTIC && h->nd == 3 && h->c.npw == 2 && (activepw & 2)) {
+        snprintf(h->err, sizeof h->err, "3-D elastic has no boundary store upstream (boundary.jl:215-264), hence no adjoint run"); return 1;
     }
     for (int issp = 0; issp < h->c.nshots; issp++) {
         reset_w2(h);
@@ -1016,6 +1071,7 @@ int orc_create(const gpi_config* cfg, orc_handle** out) {
         if (h->nd == 3) { field_shape(3, GPI_DVXDY, n, sh); arr_alloc(&h->dmod[DM_MUXY], sh); field_shape(3, GPI_DVYDZ, n, sh); arr_alloc(&h->dmod[DM_MUYZ], sh); }
     }
     if (ac) { arr_alloc(&h->gradients[GPI_INVK], n); arr_alloc(&h->gradients[GPI_RHO], n); }
+    else if (h->nd == 2) { arr_alloc(&h->gradients[GPI_INVLAMBDA], n); arr_alloc(&h->gradients[GPI_INVMU], n); arr_alloc(&h->gradients[GPI_RHO], n); }
     for (int f = GPI_NWAVEFIELD; f < GPI_NFIELD; f++) if (field_exists(h->nd, cfg->physics, f)) {
         h->pa[f] = (REAL*)calloc(2 * cfg->npml, sizeof(REAL)); h->pb[f] = (REAL*)calloc(2 * cfg->npml, sizeof(REAL));
         h->pk[f] = (REAL*)malloc(2 * cfg->npml * sizeof(REAL)); for (int i = 0; i < 2 * cfg->npml; i++) h->pk[f][i] = 1;   /* cpml.jl:114 */
@@ -1032,6 +1088,7 @@ int orc_create(const gpi_config* cfg, orc_handle** out) {
         for (int is = 0; is < cfg->nshots; is++) {
             shot_t* s = &pw->ss[is];
             if (ac) { arr_alloc(&s->grad[GPI_INVK], n); arr_alloc(&s->grad[GPI_RHO], n); }
+            else if (h->nd == 2) { arr_alloc(&s->grad[GPI_INVLAMBDA], n); arr_alloc(&s->grad[GPI_INVMU], n); arr_alloc(&s->grad[GPI_RHO], n); }
             if (ipw == 0) for (int k = 0; k < GPI_NWAVEFIELD; k++) {
                 int f = WAVEF[k]; if (!pw->w[f].d) continue;
                 s->snap[f] = (REAL*)calloc(pw->w[f].len, sizeof(REAL));

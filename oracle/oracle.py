@@ -145,7 +145,7 @@ class OracleEngine:
         return out.reshape((self.cfg.nt, nr), order="F")
 
     def get_gradient(self, name):
-        shp = self.field_shape("p")
+        shp = self.field_shape("p" if self.cfg.physics == E.ACOUSTIC else "tauxx")
         out = np.empty(int(np.prod(shp)), self.dtype)
         self._ck(self.lib.orc_get_gradient(self.h, E.PARAM[name], self._p(out)))
         return out.reshape(shp, order="F")

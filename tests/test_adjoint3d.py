@@ -76,3 +76,53 @@ def test_gradient3d_order4_engine_matches_oracle(G, O):
     eK, eR = rel_l2(gg[:half], go[:half]), rel_l2(gg[half:], go[half:])
     print(f"3-D FWI gradient order 4: invK rel-L2 {eK:.3e}, rho rel-L2 {eR:.3e}")
     assert eK <= GRAD_TOL and eR <= GRAD_TOL
+
+
+# --------------------------------------------------------------------------------------------------
+# 2-D elastic gradient (invlambda, invmu, rho): nothing upstream; finite differences are the check
+# --------------------------------------------------------------------------------------------------
+def test_elastic2d_gradient_vs_finite_differences(G, O):
+    from geophyinv_jl_b200.host import gallery
+    from scipy.ndimage import gaussian_filter
+    kw, true = gallery.fwi2d_elastic()
+    pt = O.OraclePFdtd64(G.FdtdElastic(), **{**kw, "medium": true})
+    pt.update()
+    dobs = [d.copy() for d in pt.c.data[0]]
+    pa = O.OraclePFdtd64(G.FdtdElastic("forward_save"), **kw)
+    assert pa.c.mparams == ["invlambda", "invmu", "rho"]
+    m = pa.get_modelvector().astype(np.float64)
+    g = np.zeros_like(m)
+    G.gradient(g, m, dobs, pa)
+    rng = np.random.default_rng(5)
+    n3 = m.size // 3
+    for k, name in enumerate(pa.c.mparams):
+        dm = np.zeros_like(m)
+        dm[k * n3:(k + 1) * n3] = gaussian_filter(rng.standard_normal((44, 56)), 4.0).ravel(order="F")
+        dm /= np.abs(dm).max()
+        eps = 2e-3
+        fd = (G.lossvalue(m + eps * dm, dobs, pa) - G.lossvalue(m - eps * dm, dobs, pa)) / (2 * eps)
+        ratio = float(np.dot(g, dm)) / fd
+        print(f"2-D elastic: d loss / d {name} adjoint / finite-difference = {ratio:.4f}")
+        assert abs(ratio - 1) < 0.06
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [2, 4])
+def test_elastic2d_gradient_engine_matches_oracle(G, O, order):
+    from geophyinv_jl_b200.host import gallery
+    kw, true = gallery.fwi2d_elastic(nz=52, nx=66, nt=380, nss=3)
+    pt = O.OraclePFdtd(G.FdtdElastic(), **{**kw, "medium": true}, order=order)
+    pt.update()
+    dobs = [d.copy() for d in pt.c.data[0]]
+    pg = G.PFdtd(G.FdtdElastic("forward_save"), **kw, shot_batch=2, order=order)
+    po = O.OraclePFdtd(G.FdtdElastic("forward_save"), **kw, order=order)
+    m = pg.get_modelvector()
+    gg, go = np.zeros_like(m), np.zeros_like(m)
+    lg, lo = G.gradient(gg, m, dobs, pg), G.gradient(go, m, dobs, po)
+    assert abs(lg - lo) <= 1e-5 * abs(lo)
+    n3 = m.size // 3
+    for k, name in enumerate(pg.c.mparams):
+        e = rel_l2(gg[k * n3:(k + 1) * n3], go[k * n3:(k + 1) * n3])
+        print(f"2-D elastic gradient order {order}, {name}: rel-L2 {e:.3e}")
+        assert np.abs(go[k * n3:(k + 1) * n3]).max() > 0
+        assert e <= GRAD_TOL
