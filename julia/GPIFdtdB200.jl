@@ -158,4 +158,26 @@ end
 nccl_init!(e::Engine, id::Vector{UInt8}, rank, nranks) =
     check(e, ccall((:gpi_nccl_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), e.h, id, rank, nranks))
 
+# ---- staggered array shapes for the compiled-in order (src/fields.jl:92-671; `zeros(::Field, attrib_mod, n...)`) ---------
+function field_shape(pac, field::Symbol)
+    N = ndims(pac.medium)
+    n = length.(pac.exmedium.grid)
+    out = zeros(Int32, 3)
+    rc = ccall((:gpi_field_shape_order, LIB), Cint, (Cint, Cint, Cint, Cint, Ptr{Int32}, Ptr{Int32}),
+        N, pac.attrib_mod isa FdtdElastic ? 1 : 0, _fd_order, field_id(field), Int32[n[1], N == 3 ? n[2] : 1, n[end]], out)
+    rc == 0 || error("gpifdtd: field ", field, " does not exist for this physics / dimensionality")
+    return N == 3 ? Tuple(out) : (out[1], out[3])
+end
+
+# ---- FD-Born: update!(pac, medium, medium_pert)  (src/fdtd/medium.jl:103-127) ---------------------------------------
+function update_medium_pert!(e::Engine, pac)
+    for name in names(pac.δmod)[1]
+        check(e, ccall((:gpi_set_medium_pert, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}), e.h, PARAMS[name], Array{Float32}(pac.δmod[name])))
+    end
+    check(e, ccall((:gpi_update_born, LIB), Cint, (Ptr{Cvoid},), e.h))
+end
+
+# which stencil kernels the engine launches for this experiment: 0 scalar, 1 float4, 2 TMA-pipelined tiles, 4 order 4
+kernel_family(e::Engine) = ccall((:gpi_kernel_family, LIB), Cint, (Ptr{Cvoid},), e.h)
+
 end # module
