@@ -477,8 +477,13 @@ void launch_step(gpi_handle* h, const StepArgs& a, bool vel, int nbatch, bool sa
 }
 
 // boundary-stored fields (boundary.jl:113-264)
-int boundary_fields(const gpi_handle* h, int out[3]) {
+int boundary_fields(const gpi_handle* h, int out[6]) {
     if (!h->el) { out[0] = GPI_P; return 1; }
+    if (h->nd == 3) {      // no upstream method (boundary.jl:215-264): the 2-D construction applied to all six stresses
+        const int f[6] = {GPI_TAUXX, GPI_TAUYY, GPI_TAUZZ, GPI_TAUXY, GPI_TAUXZ, GPI_TAUYZ};
+        for (int q = 0; q < 6; q++) out[q] = f[q];
+        return 6;
+    }
     out[0] = GPI_TAUXX; out[1] = GPI_TAUXZ; out[2] = GPI_TAUZZ; return 3;
 }
 long long bnd_slot_floats(const gpi_handle* h, int axis) {
@@ -491,7 +496,7 @@ long long bnd_slot_floats(const gpi_handle* h, int axis) {
 int launch_boundary(gpi_handle* h, bool save, int nb, int slot /* 0-based time slot */) {
     const Geom& g = h->g;
     BndArgs a; memset(&a, 0, sizeof a);
-    int bf[3]; a.nf = boundary_fields(h, bf);
+    int bf[6]; a.nf = boundary_fields(h, bf);
     a.nbound = h->c.nbound;
     a.naxes = 0;
     for (int q = 2; q >= 0; q--) if (!(q == 1 && h->nd == 2)) a.axes[a.naxes++] = q;
@@ -527,11 +532,11 @@ int launch_boundary(gpi_handle* h, bool save, int nb, int slot /* 0-based time s
 }
 // device table of the boundary stores of the batch's shots: [b][field][axis]
 int build_bnd_table(gpi_handle* h, int shot0, int nb) {
-    int bf[3]; const int nbf = boundary_fields(h, bf);
+    int bf[6]; const int nbf = boundary_fields(h, bf);
     std::vector<float*> t((size_t)nb * nbf * 3, nullptr);
     for (int b = 0; b < nb; b++) for (int i = 0; i < nbf; i++) for (int q = 0; q < 3; q++)
         t[((size_t)b * nbf + i) * 3 + q] = h->shots[0][shot0 + b].bnd[bf[i]][q];
-    if (!h->bnd_table) CU(h, cudaMalloc((void**)&h->bnd_table, (size_t)h->B * 9 * sizeof(float*)));
+    if (!h->bnd_table) CU(h, cudaMalloc((void**)&h->bnd_table, (size_t)h->B * 18 * sizeof(float*)));
     CU(h, cudaMemcpyAsync(h->bnd_table, t.data(), t.size() * sizeof(float*), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));      // `t` is a pageable temporary
     return 0;
@@ -709,7 +714,7 @@ static int create_impl(gpi_handle* h) {
 
     // gradients exist upstream for acoustic media (fdtd.jl:164-170; imaging 2-D only, gradient.jl:31); here also 3-D acoustic
     // and 2-D elastic (kernels.cuh k_grad3d, k_grad2d_el)
-    if (h->npw == 2 && (!h->el || h->nd == 2)) {
+    if (h->npw == 2) {
         if (!h->el) { h->ngrad = 2; h->gparam[0] = GPI_INVK; h->gparam[1] = GPI_RHO; }
         else        { h->ngrad = 3; h->gparam[0] = GPI_INVLAMBDA; h->gparam[1] = GPI_INVMU; h->gparam[2] = GPI_RHO; }
         for (int q = 0; q < h->ngrad; q++) if (alloc_vol(&h->gtot[h->gparam[q]])) return 1;
@@ -719,7 +724,7 @@ static int create_impl(gpi_handle* h) {
 
     // per-shot state
     for (int ipw = 0; ipw < h->npw; ipw++) h->shots[ipw].resize(c.nshots);
-    int bf[3]; const int nbf = boundary_fields(h, bf);
+    int bf[6]; const int nbf = boundary_fields(h, bf);
     for (int is = 0; is < c.nshots; is++) {
         ShotData& s = h->shots[0][is];
         if (c.store_boundary) {
@@ -1250,11 +1255,10 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     const bool grad = mode == GPI_MODE_ADJOINT && (activepw & 2) && h->npw == 2;
     if (grad && !h->gshot) FAIL(h, "no gradient imaging for 3-D elastic media (no boundary store upstream, boundary.jl:215-264)");
     if (unshifted && h->el) FAIL(h, "the exact-transpose rho imaging is defined for acoustic media");
-    if (mode == GPI_MODE_ADJOINT && h->el && h->nd == 3) FAIL(h, "3-D elastic has no boundary_save! upstream (boundary.jl:215-264)");
     const Geom& g = h->g;
     const int nt = h->c.nt;
     const size_t vb = (size_t)g.vol * sizeof(float);
-    int bf[3]; const int nbf = boundary_fields(h, bf);
+    int bf[6]; const int nbf = boundary_fields(h, bf);
     const int vf[3] = {GPI_VX, GPI_VY, GPI_VZ};
     h->timers = gpi_timers{};
     h->evused = 0; h->evkind.clear();
@@ -1319,7 +1323,19 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             }
             if (exchange_halos(h, 0)) return 1;
             if (mode == GPI_MODE_FORWARD_SAVE && launch_boundary(h, true, nb, it - 1)) return 1;
-            if (grad && h->el) {
+            if (grad && h->el && h->nd == 3) {
+                const int tf[6] = {GPI_TAUXX, GPI_TAUYY, GPI_TAUZZ, GPI_TAUXY, GPI_TAUXZ, GPI_TAUYZ};     // T_XX .. T_YZ
+                for (int b = 0; b < nb; b++) {
+                    GradE3Args ga;
+                    for (int q = 0; q < 6; q++) { ga.t1[q] = wf_ptr(h, h->W, b, 0, tf[q]); ga.t1tp[q] = wf_ptr(h, h->TP, b, 0, tf[q]); ga.t2tp[q] = wf_ptr(h, h->TP, b, 1, tf[q]); }
+                    for (int q = 0; q < 3; q++) { ga.v1[q] = wf_ptr(h, h->W, b, 0, vf[q]); ga.v1tp[q] = wf_ptr(h, h->TP, b, 0, vf[q]); ga.v2tp[q] = wf_ptr(h, h->TP, b, 1, vf[q]); }
+                    ga.il = h->mod[GPI_INVLAMBDA]; ga.im = h->mod[GPI_INVMU];
+                    ga.gL = h->gshot + (size_t)b * 3 * g.vol; ga.gM = ga.gL + g.vol; ga.gR = ga.gL + 2 * g.vol;
+                    dim3 blk = h->blk3, grd = grid_for(h, blk, 1);
+                    k_grad3d_el<<<grd, blk, 0, h->stream>>>(g, ga, (float)h->c.dtI);
+                    h->timers.launches += 1;
+                }
+            } else if (grad && h->el) {
                 GradE2Args ga;
                 ga.xx1 = wf_ptr(h, h->W, 0, 0, GPI_TAUXX); ga.zz1 = wf_ptr(h, h->W, 0, 0, GPI_TAUZZ); ga.xz1 = wf_ptr(h, h->W, 0, 0, GPI_TAUXZ);
                 ga.xx1tp = wf_ptr(h, h->TP, 0, 0, GPI_TAUXX); ga.zz1tp = wf_ptr(h, h->TP, 0, 0, GPI_TAUZZ); ga.xz1tp = wf_ptr(h, h->TP, 0, 0, GPI_TAUXZ);

@@ -558,7 +558,7 @@ struct BndField {
 struct BndArgs {
     int nf, naxes, nbound;
     int axes[3];              // axes that exist (2-D: z, x)
-    BndField f[3];
+    BndField f[6];            // 3-D elastic stores all six stresses
     float* const* stores;     // [b][field][axis 0..2]: the shot's store of nt slots
     long long slot_off[3];    // (slot index) x (floats per slot) per axis for this time step
     long long wstride;        // floats between batch slots of the wavefield set
@@ -676,6 +676,74 @@ __global__ void k_grad2d_el(const Geom g, const GradE2Args a, float dtI) {
         const float ax = __fadd_rn(bufx(c - q1 * sx), bufx(c - q0 * sx));
         const float az = __fadd_rn(bufz(c - q1), bufz(c - q0));
         a.gR[gw + c] = (float)((double)a.gR[gw + c] - (double)ax * 0.5 - (double)az * 0.5);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gradient imaging, 3-D elastic: k_grad2d_el with the 3-D isotropic compliance
+//   eps = dev(tau) / (2 mu) + tr(tau) / (3 (3 lambda + 2 mu)) I,   c3 = invlambda invmu / (3 invmu + 2 invlambda)
+//   eT = T2_tp (T1_tp - T1) dtI, T = txx + tyy + tzz;   eD = sum_i dev2_ii_tp (dev1_ii_tp - dev1_ii) dtI, dev_ii = t_ii - T/3
+//   g_invlambda += eT/3 dc3/dinvlambda;   g_invmu += eT/3 dc3/dinvmu + eD/2 + (shear nodes of tauxz, tauxy, tauyz)/4;  g_rho as k_grad3d
+// Operation order = oracle/fdtd_oracle.c::compute_gradient_el3d.
+// ------------------------------------------------------------------------------------------------
+struct GradE3Args {
+    const float *t1[6], *t1tp[6], *t2tp[6];      // T_XX .. T_YZ slots
+    const float *v1[3], *v1tp[3], *v2tp[3];
+    const float *il, *im;
+    float *gL, *gM, *gR;
+};
+__global__ void k_grad3d_el(const Geom g, const GradE3Args a, float dtI) {
+    int k, j, i, b;
+    if (!cell<3>(g, 1, k, j, i, b)) return;
+    if (k > g.nz - 1 || j > g.ny - 1 || i > g.nx - 1) return;
+    const int h = g.h, O = 1 + 2 * g.h;
+    const long long c = uidx(g, k + h, j + h, i + h), sy = g.pz, sx = (long long)g.pz * g.ny1;
+    const int nrm[3] = {T_XX, T_YY, T_ZZ};
+    float t1 = 0.f, t1p = 0.f, t2p = 0.f;
+#pragma unroll
+    for (int q = 0; q < 3; q++) { t1 = __fadd_rn(t1, a.t1[nrm[q]][c]); t1p = __fadd_rn(t1p, a.t1tp[nrm[q]][c]); t2p = __fadd_rn(t2p, a.t2tp[nrm[q]][c]); }
+    const float third = __fdiv_rn(1.0f, 3.0f);
+    const float eT = __fmul_rn(__fmul_rn(t2p, __fsub_rn(t1p, t1)), dtI);
+    float eD = 0.f;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const float d1 = __fsub_rn(a.t1[nrm[q]][c], __fmul_rn(t1, third)), d1p = __fsub_rn(a.t1tp[nrm[q]][c], __fmul_rn(t1p, third));
+        const float d2p = __fsub_rn(a.t2tp[nrm[q]][c], __fmul_rn(t2p, third));
+        eD = __fadd_rn(eD, __fmul_rn(__fmul_rn(d2p, __fsub_rn(d1p, d1)), dtI));
+    }
+    const float la = a.il[c], mb = a.im[c];
+    const float den = __fadd_rn(__fmul_rn(3.0f, mb), __fmul_rn(2.0f, la)), den2 = __fmul_rn(den, den);
+    const float dca = __fdiv_rn(__fmul_rn(3.0f, __fmul_rn(mb, mb)), den2), dcb = __fdiv_rn(__fmul_rn(2.0f, __fmul_rn(la, la)), den2);
+    const float te = __fmul_rn(third, eT);
+    a.gL[c] = __fadd_rn(a.gL[c], __fmul_rn(te, dca));
+    float gm = __fadd_rn(__fadd_rn(a.gM[c], __fmul_rn(te, dcb)), __fmul_rn(0.5f, eD));
+    auto inH = [&](int u, int n) { return u >= 1 + h && u <= n - 1 - h; };
+    auto inJ = [&](int u, int n) { return u >= O && u <= n - 1 - O; };
+    auto term = [&](int slot, int ku, int ju, int iu) {
+        const long long s = uidx(g, ku + h, ju + h, iu + h);
+        return __fmul_rn(__fmul_rn(a.t2tp[slot][s], __fsub_rn(a.t1tp[slot][s], a.t1[slot][s])), dtI);
+    };
+    float acc = 0.f;
+    for (int d2 = 0; d2 < 2; d2++) for (int d1 = 0; d1 < 2; d1++) {          // tauxz: (z, x) averaged, y inner
+        const int ku = k + 1 - d1 + h, iu = i + 1 - d2 + h;
+        if (inH(ku, g.nz) && inJ(j, g.ny) && inH(iu, g.nx)) acc = __fadd_rn(acc, term(T_XZ, ku, j, iu));
+    }
+    for (int d2 = 0; d2 < 2; d2++) for (int d1 = 0; d1 < 2; d1++) {          // tauxy: (y, x) averaged, z inner
+        const int ju = j + 1 - d1 + h, iu = i + 1 - d2 + h;
+        if (inJ(k, g.nz) && inH(ju, g.ny) && inH(iu, g.nx)) acc = __fadd_rn(acc, term(T_XY, k, ju, iu));
+    }
+    for (int d2 = 0; d2 < 2; d2++) for (int d1 = 0; d1 < 2; d1++) {          // tauyz: (z, y) averaged, x inner
+        const int ku = k + 1 - d1 + h, ju = j + 1 - d2 + h;
+        if (inH(ku, g.nz) && inH(ju, g.ny) && inJ(i, g.nx)) acc = __fadd_rn(acc, term(T_YZ, ku, ju, i));
+    }
+    a.gM[c] = __fadd_rn(gm, __fmul_rn(0.25f, acc));
+    if (k >= O && k <= g.nz - 1 - O && j >= O && j <= g.ny - 1 - O && i >= O && i <= g.nx - 1 - O) {
+        auto buf = [&](int q, long long x) { return __fmul_rn(__fmul_rn(a.v2tp[q][x], __fsub_rn(a.v1[q][x], a.v1tp[q][x])), dtI); };
+        const long long q1 = 3 * h + 1, q0 = 3 * h;
+        const float ax = __fadd_rn(buf(V_X, c - q1 * sx), buf(V_X, c - q0 * sx));
+        const float ay = __fadd_rn(buf(V_Y, c - q1 * sy), buf(V_Y, c - q0 * sy));
+        const float az = __fadd_rn(buf(V_Z, c - q1), buf(V_Z, c - q0));
+        a.gR[c] = (float)((double)a.gR[c] - (double)ax * 0.5 - (double)ay * 0.5 - (double)az * 0.5);
     }
 }
 

@@ -409,8 +409,7 @@ class PFdtd:
             else:
                 self.engine.run(mode, upa["activepw"], upa["src_flags"])
         # sum_grads! (propagate.jl:110-117, gradient.jl:2-11)
-        has_grad = c.attrib_mod.physics == "acoustic" or c.medium.ndims == 2      # 3-D elastic has no boundary store, hence no adjoint
-        if mode == "adjoint" and c.ic["npw"] == 2 and 2 in upa["activepw"] and has_grad:
+        if mode == "adjoint" and c.ic["npw"] == 2 and 2 in upa["activepw"]:
             if self._nccl:
                 self.engine.allreduce_gradients()
             self._grad_dirty = True

@@ -201,3 +201,31 @@ def fwi2d_elastic(nz=44, nx=56, nt=420, nr=16, nss=2, dt=1e-3, fq=12.0, d=10.0, 
     for a in (true.vp, true.vs, true.rho):
         a[z0:z1, x0:x1] *= F32(1 + box)
     return kw, true
+
+
+def fwi3d_elastic(n=16, nt=150, nr=9, nss=1, dt=1e-3, fq=20.0, d=10.0, box=0.05, seed=17):
+    """3-D elastic FWI gradient case: smooth random model, 'observed' data with a +5 % box in vp, vs, rho."""
+    from scipy.ndimage import gaussian_filter
+    grid = [StepRange(0.0, d, n)] * 3
+    rng = np.random.default_rng(seed)
+    sm = lambda: gaussian_filter(rng.standard_normal((n, n, n)), 2.0) / 0.05
+    vp = (3000.0 * (1 + 0.015 * sm())).astype(F32)
+    vs = (1600.0 * (1 + 0.015 * sm())).astype(F32)
+    rho = (2300.0 * (1 + 0.015 * sm())).astype(F32)
+    medium = Medium(grid, vp, rho, vs)
+    tgrid = StepRange(0.0, dt, nt)
+    L = grid[0].last
+    ageom = []
+    for iss in range(nss):
+        sx = (0.3 + 0.4 * iss / max(nss - 1, 1)) * L + 0.13 * d
+        src = {"z": [0.2 * L + 0.3 * d], "y": [0.45 * L + 0.2 * d], "x": [sx]}
+        rec = {"z": np.full(nr, 0.8 * L + 0.4 * d), "y": np.linspace(0.2 * L, 0.8 * L, nr), "x": np.linspace(0.1 * L, 0.9 * L, nr)}
+        ageom.append(AGeomss(src, rec))
+    wav = _ricker(fq, tgrid, 1.5 / fq + 0.005) * 1e6
+    srcwav = make_srcwav(tgrid, ageom, ["vz"], wav)
+    kw = dict(medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=["vz", "vx", "vy"])
+    true = medium.copy()
+    a, b = int(0.35 * n), int(0.65 * n)
+    for arr_ in (true.vp, true.vs, true.rho):
+        arr_[a:b, a:b, a:b] *= F32(1 + box)
+    return kw, true

@@ -694,7 +694,11 @@ static void record(orc_handle* h, int it, int issp, int activepw, const int* fie
  * ---------------------------------------------------------------------------------------------- */
 static const int* boundary_fields(orc_handle* h, int* nf) {
     static const int ac[1] = {GPI_P}, el[3] = {GPI_TAUXX, GPI_TAUXZ, GPI_TAUZZ};
+    /* 3-D elastic: upstream has no boundary_save!/force! method (boundary.jl:215-264); the 2-D construction applied to all six
+     * stresses */
+    static const int el3[6] = {GPI_TAUXX, GPI_TAUYY, GPI_TAUZZ, GPI_TAUXY, GPI_TAUXZ, GPI_TAUYZ};
     if (h->c.physics == GPI_ACOUSTIC) { *nf = 1; return ac; }
+    if (h->nd == 3) { *nf = 6; return el3; }
     *nf = 3; return el;
 }
 /* boundary_half{q}!(d, b, doff, boff): d[.., doff+i, ..] = b[.., i+boff, ..] over size(b) with axis=nbound */
@@ -709,7 +713,6 @@ static void boundary_half(REAL* dst, const int dn[3], const REAL* src, const int
 }
 static void boundary_save(orc_handle* h, int it, int issp) {    /* boundary.jl:217-264 */
     int nf; const int* bf = boundary_fields(h, &nf);
-    if (h->c.physics == GPI_ELASTIC && h->nd == 3) return;      /* no 3-D elastic method upstream */
     shot_t* s = &h->pw[0].ss[issp]; int nb = h->c.nbound;
     for (int i = 0; i < nf; i++) {
         int f = bf[i]; arr d = h->pw[0].w[f];
@@ -837,8 +840,73 @@ static void compute_gradient_el2d(orc_handle* h, int issp) {
             - (double)(REAL)(A2(bx, iz + O, ix) + A2(bx, iz + O, ix + 1)) * 0.5
             - (double)(REAL)(A2(bz, iz, ix + O) + A2(bz, iz + 1, ix + O)) * 0.5);
 }
+/* 3-D elastic imaging: the construction of compute_gradient_el2d with the 3-D isotropic compliance
+ *     eps = dev(tau) / (2 mu) + tr(tau) / (3 (3 lambda + 2 mu)) I,      c3 = 1 / (3 lambda + 2 mu) = invlambda invmu / (3 invmu + 2 invlambda)
+ *     eT  = T2_tp * (T1_tp - T1) * dtI,  T = txx + tyy + tzz                      g_invlambda += eT/3 * dc3/dinvlambda
+ *     eD  = sum_i dev2_ii_tp * (dev1_ii_tp - dev1_ii) * dtI,  dev_ii = t_ii - T/3   g_invmu     += eT/3 * dc3/dinvmu + eD/2 + shear
+ *     shear: t_ij2_tp * (t_ij1_tp - t_ij1) * dtI on the three shear grids, a quarter to each cell of the node's @av_??i(invmu) */
+static void compute_gradient_el3d(orc_handle* h, int issp) {
+    pw_t *p1 = &h->pw[0], *p2 = &h->pw[1]; shot_t* s = &p1->ss[issp];
+    arr gl = s->grad[GPI_INVLAMBDA], gm = s->grad[GPI_INVMU], gr = s->grad[GPI_RHO];
+    arr il = h->mod[GPI_INVLAMBDA], im = h->mod[GPI_INVMU];
+    REAL dtI = h->dtI;
+    const int O = g_O;
+    const int nf[3] = {GPI_TAUXX, GPI_TAUYY, GPI_TAUZZ};
+    OMP_FOR
+    for (size_t i = 0; i < gl.len; i++) {
+        REAL t1 = 0, t1p = 0, t2p = 0;
+        for (int q = 0; q < 3; q++) { t1 = t1 + p1->w[nf[q]].d[i]; t1p = t1p + p1->wtp[nf[q]].d[i]; t2p = t2p + p2->wtp[nf[q]].d[i]; }
+        const REAL third = (REAL)1 / (REAL)3;
+        const REAL eT = t2p * (t1p - t1) * dtI;
+        REAL eD = 0;
+        for (int q = 0; q < 3; q++) {
+            const REAL d1 = p1->w[nf[q]].d[i] - t1 * third, d1p = p1->wtp[nf[q]].d[i] - t1p * third, d2p = p2->wtp[nf[q]].d[i] - t2p * third;
+            eD = eD + d2p * (d1p - d1) * dtI;
+        }
+        const REAL a = il.d[i], b = im.d[i], den = (REAL)3 * b + (REAL)2 * a;
+        const REAL dca = ((REAL)3 * (b * b)) / (den * den), dcb = ((REAL)2 * (a * a)) / (den * den);
+        gl.d[i] = gl.d[i] + third * eT * dca;
+        gm.d[i] = gm.d[i] + third * eT * dcb + (REAL)0.5 * eD;
+    }
+    /* shear nodes -> cells: tauxz[jz, jy, jx] averages invmu[jz..jz+1, jy+O, jx..jx+1] (@av_xzi), tauxy[..] invmu[jz+O, jy..jy+1, jx..jx+1]
+     * (@av_xyi), tauyz[..] invmu[jz..jz+1, jy..jy+1, jx+O] (@av_yzi)  (diff3D.jl:339-378) */
+    arr xz1 = p1->w[GPI_TAUXZ], xz1p = p1->wtp[GPI_TAUXZ], xz2p = p2->wtp[GPI_TAUXZ];
+    arr xy1 = p1->w[GPI_TAUXY], xy1p = p1->wtp[GPI_TAUXY], xy2p = p2->wtp[GPI_TAUXY];
+    arr yz1 = p1->w[GPI_TAUYZ], yz1p = p1->wtp[GPI_TAUYZ], yz2p = p2->wtp[GPI_TAUYZ];
+    #define INA(a, z, y, x) ((z) >= 1 && (z) <= (a).n[0] && (y) >= 1 && (y) <= (a).n[1] && (x) >= 1 && (x) <= (a).n[2])
+    OMP_FOR
+    for (int ix = 1; ix <= gm.n[2]; ix++) for (int iy = 1; iy <= gm.n[1]; iy++) for (int iz = 1; iz <= gm.n[0]; iz++) {
+        REAL acc = 0;
+        for (int d2 = 0; d2 < 2; d2++) for (int d1 = 0; d1 < 2; d1++) {      /* d1: first averaged axis, d2: second */
+            int jz = iz - d1, jy = iy - O, jx = ix - d2;                      /* tauxz: (z, x) averaged */
+            if (INA(xz1, jz, jy, jx)) acc = acc + A3(xz2p, jz, jy, jx) * (A3(xz1p, jz, jy, jx) - A3(xz1, jz, jy, jx)) * dtI;
+        }
+        for (int d2 = 0; d2 < 2; d2++) for (int d1 = 0; d1 < 2; d1++) {
+            int jz = iz - O, jy = iy - d1, jx = ix - d2;                      /* tauxy: (y, x) averaged */
+            if (INA(xy1, jz, jy, jx)) acc = acc + A3(xy2p, jz, jy, jx) * (A3(xy1p, jz, jy, jx) - A3(xy1, jz, jy, jx)) * dtI;
+        }
+        for (int d2 = 0; d2 < 2; d2++) for (int d1 = 0; d1 < 2; d1++) {
+            int jz = iz - d1, jy = iy - d2, jx = ix - O;                      /* tauyz: (z, y) averaged */
+            if (INA(yz1, jz, jy, jx)) acc = acc + A3(yz2p, jz, jy, jx) * (A3(yz1p, jz, jy, jx) - A3(yz1, jz, jy, jx)) * dtI;
+        }
+        A3(gm, iz, iy, ix) = A3(gm, iz, iy, ix) + (REAL)0.25 * acc;
+    }
+    const int vf[3] = {GPI_VX, GPI_VY, GPI_VZ};
+    for (int k = 0; k < 3; k++) {
+        arr b = p1->vbuf[vf[k]], v = p1->w[vf[k]], vp = p1->wtp[vf[k]], va = p2->wtp[vf[k]];
+        OMP_FOR
+        for (size_t i = 0; i < b.len; i++) b.d[i] = va.d[i] * (v.d[i] - vp.d[i]) * dtI;
+    }
+    arr bx = p1->vbuf[GPI_VX], by = p1->vbuf[GPI_VY], bz = p1->vbuf[GPI_VZ];
+    OMP_FOR
+    for (int ix = 1; ix <= gr.n[2] - 2 * O; ix++) for (int iy = 1; iy <= gr.n[1] - 2 * O; iy++) for (int iz = 1; iz <= gr.n[0] - 2 * O; iz++)
+        I3(gr) = (REAL)((double)I3(gr)
+            - (double)(REAL)(A3(bx, iz + O, iy + O, ix) + A3(bx, iz + O, iy + O, ix + 1)) * 0.5
+            - (double)(REAL)(A3(by, iz + O, iy, ix + O) + A3(by, iz + O, iy + 1, ix + O)) * 0.5
+            - (double)(REAL)(A3(bz, iz, iy + O, ix + O) + A3(bz, iz + 1, iy + O, ix + O)) * 0.5);
+}
 static void compute_gradient(orc_handle* h, int issp, int unshifted) {
-    if (h->c.physics == GPI_ELASTIC) { compute_gradient_el2d(h, issp); return; }
+    if (h->c.physics == GPI_ELASTIC) { if (h->nd == 3) compute_gradient_el3d(h, issp); else compute_gradient_el2d(h, issp); return; }
     if (h->nd == 3) { compute_gradient_3d(h, issp, unshifted); return; }
     pw_t *p1 = &h->pw[0], *p2 = &h->pw[1]; shot_t* s = &p1->ss[issp];
     arr g = s->grad[GPI_INVK], pf = p1->w[GPI_P], pfp = p1->wtp[GPI_P], pap = p2->wtp[GPI_P];
@@ -944,9 +1012,6 @@ int orc_run(orc_handle* h, int mode, int activepw, int src_flags) {
     const int recp[1] = {GPI_P}, recv[3] = {GPI_VX, GPI_VY, GPI_VZ};
     if (mode == GPI_MODE_FORWARD_SAVE && !h->c.store_boundary) {
         snprintf(h->err, sizeof h->err, "forward_save needs store_boundary=1 at construction (fdtd.jl:445-455)"); return 1;
-    }
-    if (mode == GPI_MODE_ADJOINT && h->c.physics != GPI_ACOUSTIC && h->nd == 3 && h->c.npw == 2 && (activepw & 2)) {
-        snprintf(h->err, sizeof h->err, "3-D elastic has no boundary store upstream (boundary.jl:215-264), hence no adjoint run"); return 1;
     }
     for (int issp = 0; issp < h->c.nshots; issp++) {
         reset_w2(h);
@@ -1071,7 +1136,7 @@ int orc_create(const gpi_config* cfg, orc_handle** out) {
         if (h->nd == 3) { field_shape(3, GPI_DVXDY, n, sh); arr_alloc(&h->dmod[DM_MUXY], sh); field_shape(3, GPI_DVYDZ, n, sh); arr_alloc(&h->dmod[DM_MUYZ], sh); }
     }
     if (ac) { arr_alloc(&h->gradients[GPI_INVK], n); arr_alloc(&h->gradients[GPI_RHO], n); }
-    else if (h->nd == 2) { arr_alloc(&h->gradients[GPI_INVLAMBDA], n); arr_alloc(&h->gradients[GPI_INVMU], n); arr_alloc(&h->gradients[GPI_RHO], n); }
+    else { arr_alloc(&h->gradients[GPI_INVLAMBDA], n); arr_alloc(&h->gradients[GPI_INVMU], n); arr_alloc(&h->gradients[GPI_RHO], n); }
     for (int f = GPI_NWAVEFIELD; f < GPI_NFIELD; f++) if (field_exists(h->nd, cfg->physics, f)) {
         h->pa[f] = (REAL*)calloc(2 * cfg->npml, sizeof(REAL)); h->pb[f] = (REAL*)calloc(2 * cfg->npml, sizeof(REAL));
         h->pk[f] = (REAL*)malloc(2 * cfg->npml * sizeof(REAL)); for (int i = 0; i < 2 * cfg->npml; i++) h->pk[f][i] = 1;   /* cpml.jl:114 */
@@ -1088,11 +1153,11 @@ int orc_create(const gpi_config* cfg, orc_handle** out) {
         for (int is = 0; is < cfg->nshots; is++) {
             shot_t* s = &pw->ss[is];
             if (ac) { arr_alloc(&s->grad[GPI_INVK], n); arr_alloc(&s->grad[GPI_RHO], n); }
-            else if (h->nd == 2) { arr_alloc(&s->grad[GPI_INVLAMBDA], n); arr_alloc(&s->grad[GPI_INVMU], n); arr_alloc(&s->grad[GPI_RHO], n); }
+            else if (cfg->npw == 2) { arr_alloc(&s->grad[GPI_INVLAMBDA], n); arr_alloc(&s->grad[GPI_INVMU], n); arr_alloc(&s->grad[GPI_RHO], n); }
             if (ipw == 0) for (int k = 0; k < GPI_NWAVEFIELD; k++) {
                 int f = WAVEF[k]; if (!pw->w[f].d) continue;
                 s->snap[f] = (REAL*)calloc(pw->w[f].len, sizeof(REAL));
-                int isb = ac ? (f == GPI_P) : (f == GPI_TAUXX || f == GPI_TAUXZ || f == GPI_TAUZZ);
+                int isb = ac ? (f == GPI_P) : (h->nd == 3 ? (f >= GPI_TAUXX && f <= GPI_TAUYZ) : (f == GPI_TAUXX || f == GPI_TAUXZ || f == GPI_TAUZZ));
                 if (!isb) continue;
                 for (int q = 0; q < 3; q++) {
                     if (q == 1 && h->nd == 2) continue;

@@ -126,3 +126,61 @@ def test_elastic2d_gradient_engine_matches_oracle(G, O, order):
         print(f"2-D elastic gradient order {order}, {name}: rel-L2 {e:.3e}")
         assert np.abs(go[k * n3:(k + 1) * n3]).max() > 0
         assert e <= GRAD_TOL
+
+
+# --------------------------------------------------------------------------------------------------
+# 3-D elastic: boundary store of all six stresses (no upstream method, boundary.jl:215-264) + gradient
+# --------------------------------------------------------------------------------------------------
+def test_elastic3d_gradient_vs_finite_differences(G, O):
+    """Perturbation = a Gaussian bump in the middle of the model, away from the source and receiver cells (the loss also depends on
+    rho at those cells through the source scaling dt/rho, source.jl:166-177, which no adjoint-state gradient -- upstream's
+    included -- accounts for).  invlambda / invmu agree with finite differences to 1e-3; rho carries the one-cell shift of
+    upstream's combine_gmodrho! construction."""
+    from geophyinv_jl_b200.host import gallery
+    n = 16
+    kw, true = gallery.fwi3d_elastic(n=n, nt=140)
+    pt = O.OraclePFdtd64(G.FdtdElastic(), **{**kw, "medium": true})
+    pt.update()
+    dobs = [d.copy() for d in pt.c.data[0]]
+    pa = O.OraclePFdtd64(G.FdtdElastic("forward_save"), **kw)
+    m = pa.get_modelvector().astype(np.float64)
+    g = np.zeros_like(m)
+    G.gradient(g, m, dobs, pa)
+    zz, yy, xx = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    c0 = 0.5 * (n - 1)
+    bump = np.exp(-((zz - c0) ** 2 + (yy - c0) ** 2 + (xx - c0) ** 2) / (2 * 2.0 ** 2)).ravel(order="F")
+    n3 = m.size // 3
+    for k, (name, tol) in enumerate(zip(pa.c.mparams, (0.01, 0.01, 0.3))):
+        dm = np.zeros_like(m)
+        dm[k * n3:(k + 1) * n3] = bump
+        eps = 2e-3
+        fd = (G.lossvalue(m + eps * dm, dobs, pa) - G.lossvalue(m - eps * dm, dobs, pa)) / (2 * eps)
+        ratio = float(np.dot(g, dm)) / fd
+        print(f"3-D elastic: d loss / d {name} adjoint / finite-difference = {ratio:.5f}")
+        assert abs(ratio - 1) < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [2, 4])
+def test_elastic3d_adjoint_engine_matches_oracle(G, O, order):
+    """forward_save (six stresses on 3+3 planes per axis) + adjoint + imaging through the TMA-pipelined / order-4 kernels."""
+    from geophyinv_jl_b200.host import gallery
+    kw, true = gallery.fwi3d_elastic(n=22, nt=160, nr=8)
+    pt = O.OraclePFdtd(G.FdtdElastic(), **{**kw, "medium": true}, order=order)
+    pt.update()
+    dobs = [d.copy() for d in pt.c.data[0]]
+    pg = G.PFdtd(G.FdtdElastic("forward_save"), **kw, order=order)
+    po = O.OraclePFdtd(G.FdtdElastic("forward_save"), **kw, order=order)
+    m = pg.get_modelvector()
+    gg, go = np.zeros_like(m), np.zeros_like(m)
+    lg, lo = G.gradient(gg, m, dobs, pg), G.gradient(go, m, dobs, po)
+    assert abs(lg - lo) <= 1e-5 * abs(lo)
+    n3 = m.size // 3
+    for k, name in enumerate(pg.c.mparams):
+        e = rel_l2(gg[k * n3:(k + 1) * n3], go[k * n3:(k + 1) * n3])
+        print(f"3-D elastic gradient order {order}, {name}: rel-L2 {e:.3e}")
+        assert np.abs(go[k * n3:(k + 1) * n3]).max() > 0
+        assert e <= GRAD_TOL
+    # the back-propagated forward field (pw 1) ends where the forward run started: compare the final fields of both engines
+    for f in ("tauxx", "tauxy", "tauyz", "vx", "vz"):
+        assert np.array_equal(pg.engine.get_field(0, f), po.engine.get_field(0, f)), f
