@@ -29,6 +29,15 @@ for r in rows[2:]:
         continue
     seen.add(name)
     print('----')
+    try:
+        def val(k):
+            i = hdr.index(k); v = float(r[i].replace(',', '')); u = units[i]
+            scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0, 'Tbyte': 1e12, 'us': 1e-6, 'ms': 1e-3, 'ns': 1e-9, 's': 1.0, 'usecond': 1e-6, 'msecond': 1e-3, 'nsecond': 1e-9, 'second': 1.0}.get(u, 1.0)
+            return v * scale
+        by = val('dram__bytes_read.sum') + val('dram__bytes_write.sum'); t = val('gpu__time_duration.sum')
+        print(f"{'ACHIEVED HBM (dram bytes / duration)':80s} {by / t / 1e9:.1f} GB/s = {by / t / 1e9 / 6650.0:.3f} of the 6650 GB/s fallback peak ({by / 1e6:.1f} MB in {t * 1e6:.1f} us)")
+    except Exception as e:
+        print('achieved HBM: n/a', e)
     for k in keys:
         if k in hdr:
             i = hdr.index(k)
