@@ -154,7 +154,7 @@ struct gpi_handle {
     float* dmod[C_N] = {};  float** dmod_table = nullptr;
     // FD-Born (2-D acoustic): medium perturbation, scattering coefficients (d dtK, d bx, d bz), derivative scratch [B][2][vol]
     float* modp[GPI_NPARAM] = {};  float* born_c[3] = {};  float* born_d = nullptr;  bool born_ready = false;
-    // gradients (acoustic 2-D): total + per batch slot
+    // gradients (every physics / dimensionality with npw = 2): total + per batch slot
     float* gtot[GPI_NPARAM] = {};  float* gshot = nullptr;  int ngrad = 0;  int gparam[3] = {};   // gshot[b][ngrad][vol]; gparam: parameter of each slot
     std::vector<ShotData> shots[2];
     std::vector<int32_t> itsnaps;
@@ -1253,7 +1253,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     if (mode == GPI_MODE_FORWARD_SAVE && !h->c.store_boundary) FAIL(h, "forward_save needs store_boundary=1 at construction (fdtd.jl:445-455)");
     if (mode == GPI_MODE_ADJOINT && !h->c.store_boundary) FAIL(h, "adjoint needs the boundary store of a forward_save run");
     const bool grad = mode == GPI_MODE_ADJOINT && (activepw & 2) && h->npw == 2;
-    if (grad && !h->gshot) FAIL(h, "no gradient imaging for 3-D elastic media (no boundary store upstream, boundary.jl:215-264)");
+    if (grad && !h->gshot) FAIL(h, "gradient imaging needs an experiment built with npw = 2");
     if (unshifted && h->el) FAIL(h, "the exact-transpose rho imaging is defined for acoustic media");
     const Geom& g = h->g;
     const int nt = h->c.nt;

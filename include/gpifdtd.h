@@ -168,6 +168,8 @@ int  gpi_run(gpi_handle* h, int mode, int activepw_mask /* bit0 = pw1, bit1 = pw
 /* ---- results: replaces update_datamat! (receiver.jl:17-34), sum_grads! (gradient.jl:2-11),
  *      snaps (getprop.jl:10-25) ---------------------------------------------------------------- */
 int  gpi_get_records(gpi_handle* h, int ipw, int issp, int field_id, float* out /* [nt,nr] */);
+/* gradients exist for every experiment built with npw = 2: invK, rho (acoustic) | invlambda, invmu, rho (elastic); upstream images
+ * 2-D acoustic media only (gradient.jl:17-61), the other methods follow the same construction */
 int  gpi_get_gradient(gpi_handle* h, int param_id, float* out /* [nz,(ny),nx], summed over local shots */);
 int  gpi_get_snap(gpi_handle* h, int ipw, int issp, int isnap, float* out /* snaps_field shape */);
 int  gpi_set_snap_steps(gpi_handle* h, int nsnaps, const int32_t* itsnaps /* 1-based steps */);
