@@ -169,6 +169,7 @@ struct gpi_handle {
     // tuning
     dim3 blk3{64, 2, 2}, blk2{128, 2, 1};
     bool tma3 = true;  int num_sms = 148;  int tma3_ctas = 0;  bool tma3_force = false;   // GPI_TMA3=2: TMA kernels whatever the tile utilisation
+    int shell_mode = 1;                                 // GPI_SHELL=0: shell kernel serialised behind the tile kernel (diagnostic)
     struct TmaSet { const float* key = nullptr; t3::Maps* d[2] = {nullptr, nullptr}; } tmaps[2];   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
     void* encode_tiled = nullptr;                                            // cuTensorMapEncodeTiled (driver entry point)   // 3-D elastic: TMA-pipelined persistent kernels (kernels3t.cuh); GPI_TMA3=0 selects k_*3v
     bool vec2 = true;                                   // 2-D: float4-per-thread kernels (kernels2v.cuh); GPI_SCALAR2D=1 selects the scalar ones
@@ -380,6 +381,12 @@ int launch_step3t(gpi_handle* h, const StepArgs& a) {
     // every CTA must become resident at once -- shell blocks that got to the SMs earlier would delay some of
     // them by the shell's whole duration.
     const int nlines = sc.nsp * g.ny1 + (sc.ihi - sc.ilo + 1) * sc.nsr;
+    if (h->shell_mode == 0) {          // GPI_SHELL=0 (diagnostic): shell after the tiles on the same stream
+        t3::k_step3t<KIND><<<nctas, t3::NTHREADS, t3::smem_bytes(KIND), h->stream>>>(g, a, sc, set->d[KIND]);
+        t3::k_shell3<KIND><<<nlines, 128, 0, h->stream>>>(g, a, sc);
+        h->timers.launches += 1;
+        return 0;
+    }
     CU(h, cudaEventRecord(h->ev_fork, h->stream));
     t3::k_step3t<KIND><<<nctas, t3::NTHREADS, t3::smem_bytes(KIND), h->stream>>>(g, a, sc, set->d[KIND]);
     CU(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
@@ -793,6 +800,7 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (const char* e = getenv("GPI_SCALAR2D")) h->vec2 = atoi(e) == 0;
     if (const char* e = getenv("GPI_TMA3")) { h->tma3 = atoi(e) != 0; h->tma3_force = atoi(e) == 2; }
     if (const char* e = getenv("GPI_TMA3_CTAS")) h->tma3_ctas = atoi(e);
+    if (const char* e = getenv("GPI_SHELL")) h->shell_mode = atoi(e);
     if (h->nd == 3 && h->el) {
         cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
         cudaError_t e0 = cudaFuncSetAttribute(t3::k_step3t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::smem_bytes(0));

@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(NTHREADS, T3_MINB) k_step3t(const Geom g, cons
 // plane), threads = z cells
 // ------------------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void __launch_bounds__(128, 4) k_shell3(const Geom g, const StepArgs a, const Sched sc) {
+__global__ void __launch_bounds__(128, 8) k_shell3(const Geom g, const StepArgs a, const Sched sc) {
     const int L = blockIdx.x;
     int i, j;
     if (L < sc.nsp * g.ny1) { const int q = L / g.ny1; i = sc.sp[q]; j = L - q * g.ny1; }
