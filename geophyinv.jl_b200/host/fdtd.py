@@ -224,6 +224,7 @@ class PFdtd:
         self.update_ageom(c.ageom)                                                     # fdtd.jl:522-525
         self.update_srcwav(c.srcwav, [1] * npw)                                        # fdtd.jl:274
         self.update_pml()                                                              # fdtd.jl:279
+        self.stability = check_stability(self, verbose)                                # fdtd.jl:282
 
     # the only place the backend is chosen: the CUDA library, or nothing
     def _make_engine(self, cfg):
@@ -448,6 +449,38 @@ class PFdtd:
         if what in ("medium", "exmedium", "ageom", "srcwav"):
             return getattr(c, what)
         raise KeyError(key)
+
+
+def check_stability(pa: "PFdtd", verbose: bool = True, H: Optional[int] = None, epsilon: Optional[float] = None):
+    """`check_stability(pa, verbose; H = div(20, _fd_order), epsilon = 1/sqrt(ndims))` (stability.jl:6-58): grid points per minimum
+    wavelength and the Courant criterion.  Upstream only warns; this returns what it found (and warns the same way) so that
+    callers can read it: {"ds_max", "ds_recommended", "dt", "dt_recommended", "warnings"}."""
+    import warnings
+    c = pa.c
+    H = 20 // c.order if H is None else H
+    epsilon = 1.0 / np.sqrt(c.medium.ndims) if epsilon is None else epsilon
+    ds = [g.step for g in c.medium.grid]
+    dt = float(c.fc["dt"])
+    freqmax = float(c.fc.get("freqmax", np.inf))
+    if c.attrib_mod.physics == "elastic":
+        vs = c.medium.vs[c.medium.vs != 0]
+        vmin = float(vs.min()) if vs.size else 0.0                                   # the vs condition overrides
+        vmax = float(np.sqrt(float(c.medium.bounds("vp")[1]) ** 2 + float(c.medium.bounds("vs")[1]) ** 2))   # Virieux (1986)
+    else:
+        vmin, vmax = float(c.medium.bounds("vp")[0]), float(c.medium.bounds("vp")[1])
+    out = {"ds_max": max(ds), "dt": dt, "warnings": []}
+    ds_temp = round(vmin / H / freqmax, 2) if np.isfinite(freqmax) and freqmax > 0 else np.inf
+    out["ds_recommended"] = ds_temp
+    if f"{max(ds):0.2e}" != f"{ds_temp:0.2e}" and max(ds) > ds_temp:
+        out["warnings"].append(f"decrease maximum spatial sampling ({max(ds):0.2e}) below {ds_temp:0.2e}")
+    dt_temp = epsilon * min(ds) / vmax
+    out["dt_recommended"] = dt_temp
+    if f"{dt:0.2e}" != f"{dt_temp:0.2e}" and dt > dt_temp:
+        out["warnings"].append(f"decrease time sampling ({dt:0.2e}) below {dt_temp:0.2e}")
+    if verbose:
+        for w in out["warnings"]:
+            warnings.warn(w)
+    return out
 
 
 def SeisForwExpt(attrib_mod, **kw) -> PFdtd:
