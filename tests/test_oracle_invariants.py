@@ -257,10 +257,12 @@ def test_check_stability_mirrors_the_courant_criterion(G, O):
     """`check_stability` (stability.jl:6-58): dt above epsilon * min(ds) / vmax is flagged, elastic media use
     sqrt(vp^2 + vs^2) (Virieux 1986) and the vs-based wavelength; nothing is flagged for a time step below the limit."""
     from geophyinv_jl_b200.host import gallery
-    ok = O.OraclePFdtd(G.FdtdAcoustic(), **gallery.c1_acou2d_homo(nz=41, nx=41, nt=20, nr=4, dt=2e-3)).stability
-    bad = O.OraclePFdtd(G.FdtdAcoustic(), **gallery.c1_acou2d_homo(nz=41, nx=41, nt=20, nr=4, dt=4e-3)).stability
-    assert abs(ok["dt_recommended"] - (1 / np.sqrt(2)) * 10.0 / 2750.0) < 1e-9          # bounds = max + 0.1 * mean (media.jl:24-26)
+    kw = gallery.c1_acou2d_homo(nz=41, nx=41, nt=20, nr=4, dt=2e-3)
+    ds = kw["medium"].grid[0].step
+    ok = O.OraclePFdtd(G.FdtdAcoustic(), **kw).stability
+    bad = O.OraclePFdtd(G.FdtdAcoustic(), **gallery.c1_acou2d_homo(nz=41, nx=41, nt=20, nr=4, dt=2e-2)).stability
+    assert abs(ok["dt_recommended"] - (1 / np.sqrt(2)) * ds / 2750.0) < 1e-9            # bounds = max + 0.1 * mean (media.jl:24-26)
     assert not any("time sampling" in w for w in ok["warnings"])
     assert any("time sampling" in w for w in bad["warnings"])
     el = O.OraclePFdtd(G.FdtdElastic(), **gallery.elastic2d(nz=40, nx=50, nt=10, nr=4)).stability
-    assert el["dt_recommended"] < ok["dt_recommended"] * 2750.0 / 3600.0                 # vmax includes vs
+    assert el["dt_recommended"] < (1 / np.sqrt(2)) * 10.0 / 3600.0                       # vmax = sqrt(vp^2 + vs^2) > the largest vp
