@@ -170,6 +170,7 @@ struct gpi_handle {
     dim3 blk3{64, 2, 2}, blk2{128, 2, 1};
     bool tma3 = true;  int num_sms = 148;  int tma3_ctas = 0;  bool tma3_force = false;   // GPI_TMA3=2: TMA kernels whatever the tile utilisation
     int shell_mode = 1;                                 // GPI_SHELL=0: shell kernel serialised behind the tile kernel (diagnostic)
+    bool o4vec = false;                                 // GPI_O4VEC=1: order-4 kernels with four z cells per thread (kernels4v.cuh)
     struct TmaSet { const float* key = nullptr; t3::Maps* d[2] = {nullptr, nullptr}; } tmaps[2];   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
     void* encode_tiled = nullptr;                                            // cuTensorMapEncodeTiled (driver entry point)   // 3-D elastic: TMA-pipelined persistent kernels (kernels3t.cuh); GPI_TMA3=0 selects k_*3v
     bool vec2 = true;                                   // 2-D: float4-per-thread kernels (kernels2v.cuh); GPI_SCALAR2D=1 selects the scalar ones
@@ -449,8 +450,17 @@ void launch_step_kernels4(gpi_handle* h, const StepArgs& a, bool vel, int nbatch
     const Geom& g = h->g;
     dim3 blk = ND == 3 ? h->blk3 : h->blk2;
     dim3 grd = grid_for(h, blk, nbatch);
-    if (!vel) { k_stress4<ND, EL><<<grd, blk, 0, h->stream>>>(g, a); return; }
-    k_vel4<ND, EL><<<grd, blk, 0, h->stream>>>(g, a);
+    if (h->o4vec) {        // four z cells per thread (kernels4v.cuh)
+        const int ngx = ((g.pz / 4) + 31) / 32;
+        if (ND == 3) { blk = dim3(32, 2, 2); grd = dim3(ngx, (g.ny1 + 1) / 2, ((g.nx1 + 1) / 2) * nbatch); }
+        else         { blk = dim3(32, 4, 1); grd = dim3(ngx, (g.nx1 + 3) / 4, nbatch); }
+        if (!vel) { k_stress4v<ND, EL><<<grd, blk, 0, h->stream>>>(g, a); return; }
+        k_vel4v<ND, EL><<<grd, blk, 0, h->stream>>>(g, a);
+        blk = ND == 3 ? h->blk3 : h->blk2;
+    } else {
+        if (!vel) { k_stress4<ND, EL><<<grd, blk, 0, h->stream>>>(g, a); return; }
+        k_vel4<ND, EL><<<grd, blk, 0, h->stream>>>(g, a);
+    }
     const int nn[3] = {g.nz, g.ny, g.nx};
     for (int axis = 2; axis >= 0; axis--) {
         if (axis == 1 && ND == 2) continue;
@@ -801,6 +811,7 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (const char* e = getenv("GPI_TMA3")) { h->tma3 = atoi(e) != 0; h->tma3_force = atoi(e) == 2; }
     if (const char* e = getenv("GPI_TMA3_CTAS")) h->tma3_ctas = atoi(e);
     if (const char* e = getenv("GPI_SHELL")) h->shell_mode = atoi(e);
+    if (const char* e = getenv("GPI_O4VEC")) h->o4vec = atoi(e) != 0;
     if (h->nd == 3 && h->el) {
         cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
         cudaError_t e0 = cudaFuncSetAttribute(t3::k_step3t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::smem_bytes(0));
