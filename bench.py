@@ -275,7 +275,7 @@ def run_ours(args):
     else:
         KV, KS = ("k_vel3v", "k_stress3v") if wl["ndims"] == 3 else ("k_vel2v", "k_stress2v")
         if args.order == 4:
-            KV, KS = "k_vel4 + k_dirichlet4", "k_stress4"
+            KV, KS = ("k_vel4v + k_dirichlet4", "k_stress4v") if os.environ.get("GPI_O4VEC", "1") != "0" else ("k_vel4 + k_dirichlet4", "k_stress4")
     if vel_n > 0 and str_n > 0:
         kern[KV] = {"ms": vel_ms / vel_n, "bytes": bv * B}
         kern[KS] = {"ms": str_ms / str_n, "bytes": bs * B}

@@ -170,7 +170,7 @@ struct gpi_handle {
     dim3 blk3{64, 2, 2}, blk2{128, 2, 1};
     bool tma3 = true;  int num_sms = 148;  int tma3_ctas = 0;  bool tma3_force = false;   // GPI_TMA3=2: TMA kernels whatever the tile utilisation
     int shell_mode = 1;                                 // GPI_SHELL=0: shell kernel serialised behind the tile kernel (diagnostic)
-    bool o4vec = false;                                 // GPI_O4VEC=1: order-4 kernels with four z cells per thread (kernels4v.cuh)
+    bool o4vec = true;                                  // order-4 kernels with four z cells per thread (kernels4v.cuh); GPI_O4VEC=0 selects the scalar ones
     struct TmaSet { const float* key = nullptr; t3::Maps* d[2] = {nullptr, nullptr}; } tmaps[2];   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
     void* encode_tiled = nullptr;                                            // cuTensorMapEncodeTiled (driver entry point)   // 3-D elastic: TMA-pipelined persistent kernels (kernels3t.cuh); GPI_TMA3=0 selects k_*3v
     bool vec2 = true;                                   // 2-D: float4-per-thread kernels (kernels2v.cuh); GPI_SCALAR2D=1 selects the scalar ones
