@@ -417,16 +417,10 @@ __global__ void __launch_bounds__(256) k_stress(const Geom g, const StepArgs a) 
     stress_cell<ND, EL>(g, a, k, j, i, b);
 }
 
-#ifndef GPI_HOST_EMU
 #include "kernels3d.cuh"
 #include "kernels2v.cuh"
+#ifndef GPI_HOST_EMU             // tests/emu compiles everything but the TMA kernels (mbarrier / cp.async.bulk PTX) as host C++
 #include "kernels3t.cuh"
-#else
-// tests/emu: the scalar kernels and the order-4 kernels compiled as host C++ (sequential threads), plain vector accessors
-struct F4 { float v[4]; };
-inline F4 ld4(const float* p) { F4 r; for (int e = 0; e < 4; e++) r.v[e] = p[e]; return r; }
-inline F4 ldg4(const float* p) { return ld4(p); }
-inline void st4(float* p, const F4& r) { for (int e = 0; e < 4; e++) p[e] = r.v[e]; }
 #endif
 #include "kernels4.cuh"
 #include "kernels4v.cuh"

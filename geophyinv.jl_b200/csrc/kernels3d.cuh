@@ -41,6 +41,18 @@ struct F4 { float v[VW]; };
 // the arithmetic that consumes the first loaded value.  With plain C++ loads nvcc sinks the loads whose
 // values are needed last (the velocities and buoyancies of k_vel3v) below the CPML arithmetic to save
 // registers, which costs a second, serialised DRAM round trip per thread.
+#ifdef GPI_HOST_EMU
+// tests/emu: the kernels compiled as host C++ (threads run one after the other); plain accessors, no prefetch
+inline F4 ld4(const float* p) { F4 r; for (int e = 0; e < VW; e++) r.v[e] = p[e]; return r; }
+inline F4 ldg4(const float* p) { return ld4(p); }
+inline void st4(float* p, const F4& r) { for (int e = 0; e < VW; e++) p[e] = r.v[e]; }
+inline void pf(const float*) {}
+inline void pf2(const float*) {}
+inline float ld1(const float* p) { return *p; }
+#ifndef GPI_PF_AHEAD
+#define GPI_PF_AHEAD 0
+#endif
+#else
 #if GPI_VEC_W == 4
 __device__ __forceinline__ F4 ld4(const float* p) {
     F4 r;
@@ -97,6 +109,7 @@ __device__ __forceinline__ float ld1(const float* p) {
     asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
+#endif   // GPI_HOST_EMU
 // value at z-1 of element 0 / at z+1 of element 3: one scalar load each, issued with all the other loads
 // of the thread.  They hit the 128-byte lines the neighbouring lanes fetch anyway (no extra DRAM or L2
 // traffic); warp shuffles would save the L1 request but make the first use of a loaded register precede

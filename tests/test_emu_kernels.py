@@ -1,0 +1,27 @@
+"""CPU emulation of the CUDA kernels (tests/emu/): the .cuh sources compiled as host C++ behind a thin shim (tests/emu/cuda_shim.h).
+Every kernel family except the TMA-pipelined one is free of shared memory, barriers and PTX outside four accessor helpers, so running
+its threads one after the other is exact.  The one-thread-per-cell reference-order kernels are pinned to the oracle bit for bit by the
+GPU tests; here the vectorised families must reproduce them on random fields -- CPML slabs on every face, rigid faces, a free surface,
+several resident shots, ragged z extents of the float4 groups -- without a GPU:
+
+  * order 2: k_vel2v / k_stress2v and k_vel3v / k_stress3v  vs  k_vel / k_stress        (emu_kernels2.cpp, three time steps)
+  * order 4: k_vel4v / k_stress4v                             vs  k_vel4 / k_stress4    (emu_kernels4.cpp)
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", ["emu_kernels2", "emu_kernels4"])
+def test_vectorised_kernels_match_the_reference_order_kernels(tmp_path, name):
+    exe = str(tmp_path / name)
+    src = os.path.join(ROOT, "tests", "emu", name + ".cpp")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-o", exe, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    sys.stdout.write(r.stdout)
+    assert r.returncode == 0 and "EMU_OK" in r.stdout, r.stdout[-3000:]
