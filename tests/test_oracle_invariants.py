@@ -266,3 +266,28 @@ def test_check_stability_mirrors_the_courant_criterion(G, O):
     assert any("time sampling" in w for w in bad["warnings"])
     el = O.OraclePFdtd(G.FdtdElastic(), **gallery.elastic2d(nz=40, nx=50, nt=10, nr=4)).stability
     assert el["dt_recommended"] < (1 / np.sqrt(2)) * 10.0 / 3600.0                       # vmax = sqrt(vp^2 + vs^2) > the largest vp
+
+
+def test_reciprocity_of_the_pressure_green_function(G, O):
+    """Source-receiver reciprocity: in a heterogeneous medium with CPML, a :p source at node A recorded as :p at node B equals
+    the swapped experiment.  The source term enters as wavelet * dt * K (source.jl:61-75,160-163), i.e. as a volume-injection rate
+    in (1/K) dp/dt = div v + s, whose pressure response is symmetric.  A property of the discrete operator, independent of any
+    reference data: it would break with a misplaced staggered node, a wrong averaging of rho or an asymmetric CPML term."""
+    from geophyinv_jl_b200.host import gallery
+    from geophyinv_jl_b200.host.data import AGeomss, make_srcwav
+    kw = gallery.c2_acou2d_layered(nz=70, nx=90, nt=420, nss=1, nr=4, fq=12.0)
+    med, grid, tg = kw["medium"], kw["medium"].grid, kw["tgrid"]
+    A, B = (12, 20), (55, 71)                                   # (iz, ix) nodes in different layers
+    pos = lambda n: {"z": [grid[0][n[0]]], "x": [grid[1][n[1]]]}
+    wav = kw["srcwav"][0].d["p"][:, 0]
+    recs = []
+    for s, r in ((A, B), (B, A)):
+        ag = [AGeomss(pos(s), pos(r))]
+        sw = make_srcwav(tg, ag, ["p"], wav)
+        pa = O.OraclePFdtd64(G.FdtdAcoustic(), **{**kw, "ageom": ag, "srcwav": sw, "rfields": ["p"]})
+        pa.update()
+        recs.append(pa.c.data[0][0].d["p"][:, 0].astype(np.float64))
+    assert np.abs(recs[0]).max() > 0
+    e = rel_l2(recs[0], recs[1])
+    print(f"reciprocity p_AB vs p_BA (K_A / K_B = {float(med.vp[A]) ** 2 * float(med.rho[A]) / (float(med.vp[B]) ** 2 * float(med.rho[B])):.3f}): rel-L2 {e:.3e}")
+    assert e < 1e-6
