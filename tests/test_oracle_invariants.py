@@ -322,3 +322,31 @@ def test_reciprocity_of_the_elastic_velocity_response(G, O):
     e1, e2 = rel_l2(zx_ab, zx_ba), rel_l2(zz_ab, zz_ba)
     print(f"elastic reciprocity: vz->vx vs vx->vz rel-L2 {e1:.3e}, vz->vz swapped {e2:.3e}")
     assert e1 < 1e-6 and e2 < 1e-6
+
+
+def test_reciprocity_3d_elastic(G, O):
+    """The same property for the 3-D elastic operators behind the roofline case (no analytic solution is at hand for them):
+    :vz force at A recorded as :vy at B  ==  :vy force at B recorded as :vz at A, heterogeneous medium, CPML on all faces.
+    (`upstream_3d_swap=False`: the z/x swap of the 3-D weights, SURVEY App. C.1, is host-side geometry and not under test here.)"""
+    from geophyinv_jl_b200.host import gallery
+    from geophyinv_jl_b200.host.data import AGeomss, make_srcwav
+    kw = gallery.c3_elastic3d(n=20, nt=170, nr=4, fq=25.0)
+    grid, tg = kw["medium"].grid, kw["tgrid"]
+    gvz, gvy = G.get_mgrid("vz", grid), G.get_mgrid("vy", grid)
+    wav = kw["srcwav"][0].d["vz"][:, 0]
+    A, B = (5, 6, 4), (13, 12, 15)
+    node = lambda g, n: {"z": [g[0][n[0]]], "y": [g[1][n[1]]], "x": [g[2][n[2]]]}
+
+    def run(sfield, spos, rfield, rpos):
+        ag = [AGeomss(spos, rpos)]
+        sw = make_srcwav(tg, ag, [sfield], wav)
+        pa = O.OraclePFdtd64(G.FdtdElastic(), **{**kw, "ageom": ag, "srcwav": sw, "rfields": [rfield]}, upstream_3d_swap=False)
+        pa.update()
+        return pa.c.data[0][0].d[rfield][:, 0].astype(np.float64)
+
+    ab = run("vz", node(gvz, A), "vy", node(gvy, B))
+    ba = run("vy", node(gvy, B), "vz", node(gvz, A))
+    assert np.abs(ab).max() > 0
+    e = rel_l2(ab, ba)
+    print(f"3-D elastic reciprocity vz->vy vs vy->vz: rel-L2 {e:.3e}")
+    assert e < 1e-6
