@@ -268,7 +268,8 @@ def test_check_stability_mirrors_the_courant_criterion(G, O):
     assert el["dt_recommended"] < (1 / np.sqrt(2)) * 10.0 / 3600.0                       # vmax = sqrt(vp^2 + vs^2) > the largest vp
 
 
-def test_reciprocity_of_the_pressure_green_function(G, O):
+@pytest.mark.parametrize("order", [2, 4])
+def test_reciprocity_of_the_pressure_green_function(G, O, order):
     """Source-receiver reciprocity: in a heterogeneous medium with CPML, a :p source at node A recorded as :p at node B equals
     the swapped experiment.  The source term enters as wavelet * dt * K (source.jl:61-75,160-163), i.e. as a volume-injection rate
     in (1/K) dp/dt = div v + s, whose pressure response is symmetric.  A property of the discrete operator, independent of any
@@ -284,7 +285,7 @@ def test_reciprocity_of_the_pressure_green_function(G, O):
     for s, r in ((A, B), (B, A)):
         ag = [AGeomss(pos(s), pos(r))]
         sw = make_srcwav(tg, ag, ["p"], wav)
-        pa = O.OraclePFdtd64(G.FdtdAcoustic(), **{**kw, "ageom": ag, "srcwav": sw, "rfields": ["p"]})
+        pa = O.OraclePFdtd64(G.FdtdAcoustic(), **{**kw, "ageom": ag, "srcwav": sw, "rfields": ["p"]}, order=order)
         pa.update()
         recs.append(pa.c.data[0][0].d["p"][:, 0].astype(np.float64))
     assert np.abs(recs[0]).max() > 0
