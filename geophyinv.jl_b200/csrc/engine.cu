@@ -906,7 +906,7 @@ extern "C" int gpi_set_medium_interior(gpi_handle* h, int p, const float* a, con
     const size_t nf = (size_t)mz * my * mx;
     if (h->dscratch_floats < nf) {
         cudaFree(h->dscratch);
-    for (auto& ts : h->tmaps) { cudaFree(ts.d[0]); cudaFree(ts.d[1]); } h->dscratch = nullptr; h->dscratch_floats = 0;
+        h->dscratch = nullptr; h->dscratch_floats = 0;
         CU(h, cudaMalloc((void**)&h->dscratch, nf * sizeof(float)));
         h->dscratch_floats = nf;
     }
