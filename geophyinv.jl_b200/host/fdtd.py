@@ -342,7 +342,7 @@ class PFdtd:
                     w[: len(s.grid), :] = s.d[sf][:nt, :]
                     w = get_source(w, sf, src_types[ipw])
                     self.engine.set_wavelets(ipw, issp, sf, w)
-                    if not np.all(np.isclose(w, 0.0)):
+                    if w.size and float(np.abs(w).max()) > 1e-8:                # !all(isapprox.(w, 0)) with numpy's atol, one pass
                         freqmax = min(findfreq(w, s.grid, "max"), freqmax)
                         freqmin = max(findfreq(w, s.grid, "min"), freqmin)
                         peaks.append(findfreq(w, s.grid, "peak"))
