@@ -13,13 +13,13 @@ from . import engine
 from .engine import Engine, EngineError, load_library
 from .host.data import (AGeomss, Medium, Recs, Srcs, ageom_xwell, get_source, make_recs, make_srcwav, padarray,
                         ricker)
-from .host.fdtd import (FdtdAcoustic, FdtdElastic, LinearMap, PFdtd, SeisForwExpt, adjoint_map, forward_map, gradient,
+from .host.fdtd import (FdtdAcoustic, FdtdElastic, LinearMap, PFdtd, SeisForwExpt, adjoint_map, check_stability, forward_map, gradient,
                         l2_adjoint_source, l2_lossvalue, lossvalue, sschunks, update, view_inner)
 from .host.grids import NBOUND, NPML, ORDER, StepRange, field_shape, get_mgrid
 
 __all__ = [
     "engine", "Engine", "EngineError", "load_library", "AGeomss", "Medium", "Recs", "Srcs", "ageom_xwell",
     "get_source", "make_recs", "make_srcwav", "padarray", "ricker", "FdtdAcoustic", "FdtdElastic", "PFdtd",
-    "SeisForwExpt", "LinearMap", "forward_map", "adjoint_map", "gradient", "l2_adjoint_source", "l2_lossvalue", "lossvalue", "sschunks", "update",
+    "SeisForwExpt", "LinearMap", "check_stability", "forward_map", "adjoint_map", "gradient", "l2_adjoint_source", "l2_lossvalue", "lossvalue", "sschunks", "update",
     "view_inner", "NBOUND", "NPML", "ORDER", "StepRange", "field_shape", "get_mgrid",
 ]

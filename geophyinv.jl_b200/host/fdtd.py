@@ -503,7 +503,9 @@ def update(pa: PFdtd, *args, **kw):
     if isinstance(first, Srcs):
         return pa.update_srcwav(a, *args[1:])
     if isinstance(first, AGeomss):
-        return pa.update_ageom(a)
+        what = args[1] if len(args) > 1 else "both"            # update!(pa, ageom, Srcs | Recs) (ageom.jl:58-98)
+        what = {"Srcs": "srcs", "Recs": "recs"}.get(getattr(what, "__name__", what), what)
+        return pa.update_ageom(a, what)
     raise TypeError("no method update! for these arguments")
 
 
