@@ -351,3 +351,17 @@ def test_reciprocity_3d_elastic(G, O):
     e = rel_l2(ab, ba)
     print(f"3-D elastic reciprocity vz->vy vs vy->vz: rel-L2 {e:.3e}")
     assert e < 1e-6
+
+
+def test_update_ageom_recs_round_trip_through_the_upload_cache(G, O):
+    """`update!(pa, ageom, Recs)` (ageom.jl:58-98): moved receivers change the records, restoring them restores the records bit for
+    bit -- the host keeps the uploaded interpolation matrices in a cache keyed by the points, which must notice both moves."""
+    from geophyinv_jl_b200.host import gallery
+    kw = gallery.c1_acou2d_homo(nz=41, nx=41, nt=400, nr=4)
+    pa = O.OraclePFdtd(G.FdtdAcoustic(), **kw)
+    pa.update(); d0 = pa.c.data[0][0].d["p"].copy()
+    ag = kw["ageom"]
+    moved = [G.AGeomss(ag[0].s, {k: v + 30.0 for k, v in ag[0].r.items()})]
+    G.update(pa, moved, G.Recs); pa.update(); d1 = pa.c.data[0][0].d["p"].copy()
+    G.update(pa, ag, "recs"); pa.update(); d2 = pa.c.data[0][0].d["p"].copy()
+    assert np.abs(d0).max() > 0 and not np.array_equal(d0, d1) and np.array_equal(d0, d2)
