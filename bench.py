@@ -41,13 +41,32 @@ NPML = 41
 
 
 def measured_peak():
+    """HBM peak in GB/s: the driver-written MEASURED_PEAKS.json when present (the sustained figure if it distinguishes burst and
+    sustained -- the kernels are timed inside a long step), else the fallback of B200_PROFILING.md."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
         with open(p) as f:
             d = json.load(f)
-        for k in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"):
-            if k in d:
-                return float(d[k]), "measured"
+        found = []
+
+        def walk(x, path):
+            if isinstance(x, dict):
+                for k, v in x.items():
+                    walk(v, path + [str(k).lower()])
+            elif isinstance(x, (int, float)) and not isinstance(x, bool):
+                joined = "/".join(path)
+                if "hbm" in joined or "dram" in joined or "copy" in joined:
+                    found.append((joined, float(x)))
+        walk(d, [])
+        for pref in ("sustain", "hbm_gbs", "hbm_gb_s", "hbm_copy_gbs", "hbm", ""):
+            for path, v in found:
+                if pref in path and v > 0:
+                    if v < 50:            # TB/s
+                        v *= 1000.0
+                    elif v > 1e6:         # B/s
+                        v /= 1e9
+                    if 1000.0 < v < 20000.0:
+                        return v, "measured"
     except Exception:
         pass
     return FALLBACK_HBM_GBS, "fallback"
