@@ -180,4 +180,66 @@ end
 # which stencil kernels the engine launches for this experiment: 0 scalar, 1 float4, 2 TMA-pipelined tiles, 4 order 4
 kernel_family(e::Engine) = ccall((:gpi_kernel_family, LIB), Cint, (Ptr{Cvoid},), e.h)
 
+# ---- the remaining exports of include/gpifdtd.h, one thin wrapper each -------------------------------------------------
+abi_version() = ccall((:gpi_abi_version, LIB), Cint, ())
+function field_shape_order2(ndims, elastic::Bool, field::Symbol, n::NTuple{3,Int})      # the order-2 entry point kept for old callers
+    out = zeros(Int32, 3)
+    ccall((:gpi_field_shape, LIB), Cint, (Cint, Cint, Cint, Ptr{Int32}, Ptr{Int32}), ndims, elastic ? 1 : 0, field_id(field), Int32[n...], out) == 0 ||
+        error("gpifdtd: field ", field, " does not exist for this physics / dimensionality")
+    return Tuple(out)
+end
+
+# pa[:snaps, i] needs the snapshot steps the constructor derived from `tsnaps` (src/fdtd/fdtd.jl:181-185)
+set_snap_steps!(e::Engine, itsnaps::Vector{<:Integer}) =
+    check(e, ccall((:gpi_set_snap_steps, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}), e.h, length(itsnaps), Int32.(itsnaps)))
+
+# wavefields and medium arrays in the reference's own shapes (debugging, `pap[ipw].w1[:t][field]`, `pac.mod[name]`)
+function get_field(e::Engine, pac, ipw, field::Symbol; batch = 1)
+    out = Array{Float32}(undef, field_shape(pac, field))
+    check(e, ccall((:gpi_get_field, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}), e.h, ipw - 1, batch - 1, field_id(field), out))
+    return out
+end
+set_field!(e::Engine, ipw, field::Symbol, a::Array{Float32}; batch = 1) =
+    check(e, ccall((:gpi_set_field, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}), e.h, ipw - 1, batch - 1, field_id(field), a))
+function get_medium(e::Engine, pac, name::Symbol)
+    out = Array{Float32}(undef, size(pac.mod[name]))
+    check(e, ccall((:gpi_get_medium, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}), e.h, PARAMS[name], out))
+    return out
+end
+
+# z-slab handles: the global z range this engine owns and a window of rows of a medium array (the host never needs the whole
+# 594 x 1106 x 1106 array on every worker)
+function slab_range(e::Engine)
+    ka = Ref{Int32}(0); kb = Ref{Int32}(0)
+    check(e, ccall((:gpi_slab_range, LIB), Cint, (Ptr{Cvoid}, Ref{Int32}, Ref{Int32}), e.h, ka, kb))
+    return Int(ka[]), Int(kb[])
+end
+set_medium_rows!(e::Engine, name::Symbol, rows::Array{Float32}, k_first::Integer) =
+    check(e, ccall((:gpi_set_medium_rows, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Cint, Cint), e.h, PARAMS[name], rows, k_first, size(rows, 1)))
+
+# zero-copy hand-off to CUDA.jl: wrap the engine's device buffers with `unsafe_wrap(CuArray, CuPtr{Float32}(ptr), dims)`
+function records_device_ptr(e::Engine, ipw, issp, rfield::Symbol)
+    p = Ref{Ptr{Cvoid}}(C_NULL); nb = Ref{Int64}(0)
+    check(e, ccall((:gpi_records_device_ptr, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ref{Ptr{Cvoid}}, Ref{Int64}), e.h, ipw - 1, issp - 1, field_id(rfield), p, nb))
+    return p[], Int(nb[])
+end
+function gradient_device_ptr(e::Engine, name::Symbol)
+    p = Ref{Ptr{Cvoid}}(C_NULL); nf = Ref{Int64}(0)
+    check(e, ccall((:gpi_gradient_device_ptr, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}, Ref{Int64}), e.h, PARAMS[name], p, nf))
+    return p[], Int(nf[])
+end
+set_stream!(e::Engine, stream::Ptr{Cvoid}) = check(e, ccall((:gpi_set_stream, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), e.h, stream))
+synchronize(e::Engine) = check(e, ccall((:gpi_synchronize, LIB), Cint, (Ptr{Cvoid},), e.h))
+
+# the engine-side analogue of the TimerOutputs sections of mod_x_proc! (src/fdtd/propagate.jl:176-233)
+struct GpiTimers
+    run_ms::Float64; steps::Float64; cell_updates::Float64; stencil_ms::Float64; launches::Float64
+    vel_ms::Float64; vel_n::Float64; stress_ms::Float64; stress_n::Float64
+end
+function timers(e::Engine)
+    t = Ref(GpiTimers(0, 0, 0, 0, 0, 0, 0, 0, 0))
+    check(e, ccall((:gpi_get_timers, LIB), Cint, (Ptr{Cvoid}, Ref{GpiTimers}), e.h, t))
+    return t[]
+end
+
 end # module

@@ -102,3 +102,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "liboracle" not in txt and "from oracle" not in txt, f
+
+
+def test_julia_shim_binds_every_export():
+    """julia/GPIFdtdB200.jl is the reference-side binding; Julia is not installed here, so the check is textual:
+    every function include/gpifdtd.h declares has a `ccall((:name, LIB), ...)` in the shim."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "gpifdtd.h")).read()
+    shim = open(os.path.join(root, "julia", "GPIFdtdB200.jl")).read()
+    exports = sorted(set(re.findall(r"\b(gpi_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(exports) >= 30
+    missing = [e for e in exports if f"(:{e}, LIB)" not in shim]
+    assert not missing, missing
