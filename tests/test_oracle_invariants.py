@@ -101,8 +101,9 @@ def test_analytic_acoustic2d(G, O):
     po = O.OraclePFdtd64(G.FdtdAcoustic(), **kw)
     po.update()
     d = po.c.data[0][0].d["p"].astype(np.float64)
-    # two samples of lag by construction: record!(p) samples the field at the START of step it
-    # (propagate.jl:177) and wavelet sample it reaches p at the END of step it (propagate.jl:223)
+    # alignment: half a sample by construction (record!(p) samples the field at the START of step it, propagate.jl:177, and wavelet
+    # sample it acts over the step that ends there, propagate.jl:223; see test_analytic_acoustic3d) plus the delay that the
+    # second-order numerical dispersion accumulates over the 160 cells between source and receivers: two samples in total
     a = analytic_p_record(kw, 2500.0, 2500.0)
     d_al, a_al = d[2:, :], a[:-2, :]
     err = np.sum((d_al - a_al) ** 2) / np.sum(a_al ** 2)
@@ -365,3 +366,38 @@ def test_update_ageom_recs_round_trip_through_the_upload_cache(G, O):
     G.update(pa, moved, G.Recs); pa.update(); d1 = pa.c.data[0][0].d["p"].copy()
     G.update(pa, ag, "recs"); pa.update(); d2 = pa.c.data[0][0].d["p"].copy()
     assert np.abs(d0).max() > 0 and not np.array_equal(d0, d1) and np.array_equal(d0, d2)
+
+
+def test_analytic_acoustic3d(G, O):
+    """3-D homogeneous Green's function: a :p source (wavelet * dt * K added to one cell of volume dV per step, source.jl:61-75) is a
+    volume-injection rate q(t) dV, so  p(r, t) = rho * dV * q'(t - r/c) / (4 pi r).  Amplitude and timing with NO free parameter:
+    the only shift is the half sample of the leapfrog (sample `it` of the wavelet acts over the step that ends at record `it`).
+    Receivers 6 to 32 cells away, so numerical dispersion is small and the gate can be ten times tighter than the reference's
+    2-D accuracy test (1e-2, test/fdtd/accuracy2D.jl:39): measured 1.5e-4.  Pins the 3-D derivative operators, dt*K and dt/rho
+    scaling, the CPML (nothing comes back) and the record weights."""
+    from geophyinv_jl_b200.host.data import AGeomss, Medium, make_srcwav, ricker
+    n, d, dt, nt, fq, c0, rho0 = 56, 10.0, 1e-3, 400, 8.0, 2500.0, 2000.0
+    grid = [G.StepRange(0.0, d, n)] * 3
+    medium = Medium(grid, np.full((n, n, n), c0, np.float32), np.full((n, n, n), rho0, np.float32))
+    tgrid = G.StepRange(0.0, dt, nt)
+    s = [grid[0][20], grid[1][22], grid[2][21]]                                    # on a node of the p grid
+    nr = 6
+    rec = {"z": np.array([grid[0][20 + 3 * k] for k in range(1, nr + 1)]), "y": np.array([grid[1][22 + 2 * k] for k in range(1, nr + 1)]),
+           "x": np.array([grid[2][21 + 4 * k] for k in range(1, nr + 1)])}
+    ageom = [AGeomss({"z": [s[0]], "y": [s[1]], "x": [s[2]]}, rec)]
+    wav = ricker(fq, tgrid, tpeak=1.5 / fq + 0.01)
+    srcwav = make_srcwav(tgrid, ageom, ["p"], wav)
+    po = O.OraclePFdtd64(G.FdtdAcoustic(), medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=["p"], upstream_3d_swap=False)
+    po.update()
+    dat = po.c.data[0][0].d["p"].astype(np.float64)
+    np2 = int(2 ** np.ceil(np.log2(2 * nt)))
+    W = np.fft.rfft(np.asarray(wav, np.float64), np2)
+    f = np.fft.rfftfreq(np2, dt)
+    ana = np.zeros_like(dat)
+    for ir in range(nr):
+        r = np.sqrt((rec["z"][ir] - s[0]) ** 2 + (rec["y"][ir] - s[1]) ** 2 + (rec["x"][ir] - s[2]) ** 2)
+        spec = W * (2j * np.pi * f) * np.exp(-2j * np.pi * f * (r / c0 + 0.5 * dt)) * rho0 * d ** 3 / (4 * np.pi * r)
+        ana[:, ir] = np.fft.irfft(spec, np2)[:nt]
+    err = np.sum((dat - ana) ** 2) / np.sum(ana ** 2)
+    print(f"analytic 3-D acoustic: normalised squared misfit {err:.3e}")
+    assert err < 1e-3
