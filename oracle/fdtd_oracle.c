@@ -7,7 +7,8 @@
  * the reference cannot be run here, and the reference ships no golden vectors for this path
  *  => PARITY UNPINNED against upstream artefacts; it is pinned instead by the
  * reference's own test invariants (analytic homogeneous solution, time reversal, gradient vs
- * finite differences, dot test), see tests/test_oracle_invariants.py.
+ * finite differences, dot test) and by closed-form solutions with no free parameter (3-D acoustic
+ * Green's function, 3-D elastic Stokes solution, reciprocity), see tests/test_oracle_invariants.py.
  *
  * Structure follows the reference literally (all citations relative to /root/reference):
  *   - same arrays with the same shapes as src/fields.jl:92-671 (column-major, [z,(y),x]);

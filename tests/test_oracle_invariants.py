@@ -401,3 +401,49 @@ def test_analytic_acoustic3d(G, O):
     err = np.sum((dat - ana) ** 2) / np.sum(ana ** 2)
     print(f"analytic 3-D acoustic: normalised squared misfit {err:.3e}")
     assert err < 1e-3
+
+
+def test_analytic_elastic3d_stokes(G, O):
+    """3-D elastic full space, point force along z: the Stokes solution (Aki & Richards eq. 4.23 -- near-field term between the P
+    and S arrivals, far-field P and S), no free parameter.  The velocity source adds wavelet * dt / rho to one vz node
+    (source.jl:166-177), i.e. a force F(t) = wavelet * dV; records are velocities, v = du/dt, taken after the velocity update of
+    step `it`, half a sample BEFORE the wavelet's time axis (leapfrog).  Receivers on nodes of their own staggered grids, 9-20 cells
+    away in all three directions, :vz and :vx.  Pins amplitude, timing and radiation pattern of the 3-D elastic operators behind the
+    roofline case (lambda + 2 mu, lambda, the three shear-modulus averages, dt / rho) against something that is not this code."""
+    from geophyinv_jl_b200.host.data import AGeomss, Medium, make_srcwav, ricker
+    n, d, dt, nt, fq = 46, 10.0, 1.5e-3, 380, 6.0
+    al, be, rho = 3000.0, 1700.0, 2300.0
+    grid = [G.StepRange(0.0, d, n)] * 3
+    medium = Medium(grid, np.full((n, n, n), al, np.float32), np.full((n, n, n), rho, np.float32), np.full((n, n, n), be, np.float32))
+    tgrid = G.StepRange(0.0, dt, nt)
+    gvz, gvx = G.get_mgrid("vz", grid), G.get_mgrid("vx", grid)
+    S = (16, 18, 17)
+    spos = [gvz[0][S[0]], gvz[1][S[1]], gvz[2][S[2]]]
+    offs = [(6, 4, 8), (10, 9, 5), (14, 6, 12), (3, 12, 10)]
+    wav = ricker(fq, tgrid, tpeak=1.5 / fq + 0.01) * 1e6
+    np2 = int(2 ** np.ceil(np.log2(2 * nt)))
+    F = np.fft.rfft(np.asarray(wav, np.float64), np2) * d ** 3                    # point force = wavelet * dV
+    w = 2 * np.pi * np.fft.rfftfreq(np2, dt)
+
+    def stokes_velocity(ri, comp):
+        r = np.linalg.norm(ri); gam = ri / r
+        gi, gj, dij = gam[comp], gam[0], 1.0 if comp == 0 else 0.0               # force along z = axis 0 of (z, y, x)
+        ww = w[1:]
+        anti = lambda t: np.exp(-1j * ww * t) * (1j * t / ww + 1.0 / ww ** 2)     # antiderivative of tau * exp(-i w tau)
+        Gw = np.zeros(w.size, complex)
+        Gw[1:] = ((3 * gi * gj - dij) / r ** 3 * (anti(r / be) - anti(r / al)) + gi * gj * np.exp(-1j * ww * r / al) / (al ** 2 * r)
+                  - (gi * gj - dij) * np.exp(-1j * ww * r / be) / (be ** 2 * r)) / (4 * np.pi * rho)
+        return np.fft.irfft(1j * w * Gw * F * np.exp(1j * w * 0.5 * dt), np2)[:nt]
+
+    for rf, g, comp in (("vz", gvz, 0), ("vx", gvx, 2)):
+        rec = {k: np.array([g[q][S[q] + o[q]] for o in offs]) for q, k in enumerate(("z", "y", "x"))}
+        ageom = [AGeomss({"z": [spos[0]], "y": [spos[1]], "x": [spos[2]]}, rec)]
+        srcwav = make_srcwav(tgrid, ageom, ["vz"], wav)
+        po = O.OraclePFdtd64(G.FdtdElastic(), medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=[rf], upstream_3d_swap=False)
+        po.update()
+        dat = po.c.data[0][0].d[rf].astype(np.float64)
+        ana = np.stack([stokes_velocity(np.array([rec["z"][ir] - spos[0], rec["y"][ir] - spos[1], rec["x"][ir] - spos[2]]), comp)
+                        for ir in range(len(offs))], axis=1)
+        err = np.sum((dat - ana) ** 2) / np.sum(ana ** 2)
+        print(f"Stokes solution, :vz force recorded as :{rf}: normalised squared misfit {err:.3e}")
+        assert err < 1e-3
