@@ -447,3 +447,51 @@ def test_analytic_elastic3d_stokes(G, O):
         err = np.sum((dat - ana) ** 2) / np.sum(ana ** 2)
         print(f"Stokes solution, :vz force recorded as :{rf}: normalised squared misfit {err:.3e}")
         assert err < 1e-3
+
+
+def test_analytic_elastic2d_line_force(G, O):
+    """2-D elastic (plane strain) full space, line force along z:  G_ij = g_s delta_ij / (rho beta^2) + d_i d_j (g_s - g_p) / (rho w^2)
+    with the 2-D Helmholtz Green's functions g_c = (-i/4) H0^(2)(w r / c).  No free parameter; same conventions as the Stokes test
+    (force = wavelet * dA, velocities half a sample ahead).  Pins the 2-D elastic operators (tauxz on the (H, H) grid, @av(invmu))."""
+    from scipy.special import hankel2
+    from geophyinv_jl_b200.host.data import AGeomss, Medium, make_srcwav, ricker
+    nz, nx, d, dt, nt, fq = 90, 100, 10.0, 1.5e-3, 520, 6.0
+    al, be, rho = 3000.0, 1700.0, 2300.0
+    grid = [G.StepRange(0.0, d, nz), G.StepRange(0.0, d, nx)]
+    medium = Medium(grid, np.full((nz, nx), al, np.float32), np.full((nz, nx), rho, np.float32), np.full((nz, nx), be, np.float32))
+    tgrid = G.StepRange(0.0, dt, nt)
+    gvz, gvx = G.get_mgrid("vz", grid), G.get_mgrid("vx", grid)
+    S = (30, 32)
+    spos = [gvz[0][S[0]], gvz[1][S[1]]]
+    offs = [(12, 9), (20, 14), (7, 25), (28, 30)]
+    wav = ricker(fq, tgrid, tpeak=1.5 / fq + 0.01) * 1e6
+    np2 = int(2 ** np.ceil(np.log2(2 * nt)))
+    F = np.fft.rfft(np.asarray(wav, np.float64), np2) * d ** 2
+    w = 2 * np.pi * np.fft.rfftfreq(np2, dt)
+
+    def velocity(ri, comp):
+        r = np.linalg.norm(ri); gam = ri / r
+        gi, gj, dij = gam[comp], gam[0], 1.0 if comp == 0 else 0.0
+        ww = w[1:]
+
+        def hess(c):            # d_i d_j of g_c(r) = (-i/4) H0^(2)(k r):  g'' gi gj + g' (dij - gi gj) / r
+            k = ww / c
+            h0, h1 = hankel2(0, k * r), hankel2(1, k * r)
+            g1 = (-0.25j) * (-k * h1)
+            g2 = (-0.25j) * (-k * k) * (h0 - h1 / (k * r))
+            return g2 * gi * gj + g1 * (dij - gi * gj) / r
+        Gw = np.zeros(w.size, complex)
+        Gw[1:] = (-0.25j) * hankel2(0, ww / be * r) * dij / (rho * be ** 2) + (hess(be) - hess(al)) / (rho * ww ** 2)
+        return np.fft.irfft(1j * w * Gw * F * np.exp(1j * w * 0.5 * dt), np2)[:nt]
+
+    for rf, g, comp in (("vz", gvz, 0), ("vx", gvx, 1)):
+        rec = {k: np.array([g[q][S[q] + o[q]] for o in offs]) for q, k in enumerate(("z", "x"))}
+        ageom = [AGeomss({"z": [spos[0]], "x": [spos[1]]}, rec)]
+        srcwav = make_srcwav(tgrid, ageom, ["vz"], wav)
+        po = O.OraclePFdtd64(G.FdtdElastic(), medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=[rf])
+        po.update()
+        dat = po.c.data[0][0].d[rf].astype(np.float64)
+        ana = np.stack([velocity(np.array([rec["z"][ir] - spos[0], rec["x"][ir] - spos[1]]), comp) for ir in range(len(offs))], axis=1)
+        err = np.sum((dat - ana) ** 2) / np.sum(ana ** 2)
+        print(f"2-D elastic line force, :vz force recorded as :{rf}: normalised squared misfit {err:.3e}")
+        assert err < 2e-3
