@@ -368,7 +368,8 @@ def test_update_ageom_recs_round_trip_through_the_upload_cache(G, O):
     assert np.abs(d0).max() > 0 and not np.array_equal(d0, d1) and np.array_equal(d0, d2)
 
 
-def test_analytic_acoustic3d(G, O):
+@pytest.mark.parametrize("order", [2, 4])
+def test_analytic_acoustic3d(G, O, order):
     """3-D homogeneous Green's function: a :p source (wavelet * dt * K added to one cell of volume dV per step, source.jl:61-75) is a
     volume-injection rate q(t) dV, so  p(r, t) = rho * dV * q'(t - r/c) / (4 pi r).  Amplitude and timing with NO free parameter:
     the only shift is the half sample of the leapfrog (sample `it` of the wavelet acts over the step that ends at record `it`).
@@ -387,7 +388,7 @@ def test_analytic_acoustic3d(G, O):
     ageom = [AGeomss({"z": [s[0]], "y": [s[1]], "x": [s[2]]}, rec)]
     wav = ricker(fq, tgrid, tpeak=1.5 / fq + 0.01)
     srcwav = make_srcwav(tgrid, ageom, ["p"], wav)
-    po = O.OraclePFdtd64(G.FdtdAcoustic(), medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=["p"], upstream_3d_swap=False)
+    po = O.OraclePFdtd64(G.FdtdAcoustic(), medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=["p"], upstream_3d_swap=False, order=order)
     po.update()
     dat = po.c.data[0][0].d["p"].astype(np.float64)
     np2 = int(2 ** np.ceil(np.log2(2 * nt)))
@@ -399,7 +400,7 @@ def test_analytic_acoustic3d(G, O):
         spec = W * (2j * np.pi * f) * np.exp(-2j * np.pi * f * (r / c0 + 0.5 * dt)) * rho0 * d ** 3 / (4 * np.pi * r)
         ana[:, ir] = np.fft.irfft(spec, np2)[:nt]
     err = np.sum((dat - ana) ** 2) / np.sum(ana ** 2)
-    print(f"analytic 3-D acoustic: normalised squared misfit {err:.3e}")
+    print(f"analytic 3-D acoustic, order {order}: normalised squared misfit {err:.3e}")
     assert err < 1e-3
 
 
@@ -449,7 +450,8 @@ def test_analytic_elastic3d_stokes(G, O):
         assert err < 1e-3
 
 
-def test_analytic_elastic2d_line_force(G, O):
+@pytest.mark.parametrize("order", [2, 4])
+def test_analytic_elastic2d_line_force(G, O, order):
     """2-D elastic (plane strain) full space, line force along z:  G_ij = g_s delta_ij / (rho beta^2) + d_i d_j (g_s - g_p) / (rho w^2)
     with the 2-D Helmholtz Green's functions g_c = (-i/4) H0^(2)(w r / c).  No free parameter; same conventions as the Stokes test
     (force = wavelet * dA, velocities half a sample ahead).  Pins the 2-D elastic operators (tauxz on the (H, H) grid, @av(invmu))."""
@@ -488,10 +490,10 @@ def test_analytic_elastic2d_line_force(G, O):
         rec = {k: np.array([g[q][S[q] + o[q]] for o in offs]) for q, k in enumerate(("z", "x"))}
         ageom = [AGeomss({"z": [spos[0]], "x": [spos[1]]}, rec)]
         srcwav = make_srcwav(tgrid, ageom, ["vz"], wav)
-        po = O.OraclePFdtd64(G.FdtdElastic(), medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=[rf])
+        po = O.OraclePFdtd64(G.FdtdElastic(), medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=[rf], order=order)
         po.update()
         dat = po.c.data[0][0].d[rf].astype(np.float64)
         ana = np.stack([velocity(np.array([rec["z"][ir] - spos[0], rec["x"][ir] - spos[1]]), comp) for ir in range(len(offs))], axis=1)
         err = np.sum((dat - ana) ** 2) / np.sum(ana ** 2)
-        print(f"2-D elastic line force, :vz force recorded as :{rf}: normalised squared misfit {err:.3e}")
+        print(f"2-D elastic line force, order {order}, :vz force recorded as :{rf}: normalised squared misfit {err:.3e}")
         assert err < 2e-3
