@@ -13,8 +13,8 @@ GRAD_TOL = 1e-4
 def test_gradient3d_vs_finite_differences(G, O):
     from geophyinv_jl_b200.host import gallery
     from scipy.ndimage import gaussian_filter
-    n = 20
-    kw, true = gallery.fwi3d(n=n, nt=170, nr=10)
+    n = 16
+    kw, true = gallery.fwi3d(n=n, nt=150, nr=10)
     pt = O.OraclePFdtd64(G.FdtdAcoustic(), **{**kw, "medium": true})
     pt.update()
     dobs = [d.copy() for d in pt.c.data[0]]
@@ -137,8 +137,8 @@ def test_elastic3d_gradient_vs_finite_differences(G, O):
     included -- accounts for).  invlambda / invmu agree with finite differences to 1e-3; rho carries the one-cell shift of
     upstream's combine_gmodrho! construction."""
     from geophyinv_jl_b200.host import gallery
-    n = 16
-    kw, true = gallery.fwi3d_elastic(n=n, nt=140)
+    n = 14
+    kw, true = gallery.fwi3d_elastic(n=n, nt=125)
     pt = O.OraclePFdtd64(G.FdtdElastic(), **{**kw, "medium": true})
     pt.update()
     dobs = [d.copy() for d in pt.c.data[0]]
