@@ -105,11 +105,14 @@ class PFdtd:
                  pml_faces: Sequence[str] = tuple(ALL_FACES), rigid_faces=None, rfields: Sequence[str] = ("vz",),
                  stressfree_faces: Sequence[str] = ("dummy",), tsnaps=None, snaps_field: Optional[str] = None,
                  verbose: bool = False, nworker: Optional[int] = None, rank: int = 0, device: int = -1,
-                 shot_batch: int = 0, upstream_3d_swap: bool = True, zslab=None, order: int = ORDER):
+                 shot_batch: int = 0, upstream_3d_swap: bool = True, zslab=None, order: int = ORDER,
+                 jobname: str = "forward_propagation", backprop_flag=None, illum_flag: bool = False):
         """`zslab=(rank, nranks)`: z-slab domain decomposition of ONE experiment over `nranks` GPUs (new
         capability): every rank builds the same experiment, owns one slab of the extended grid and
         exchanges halo planes over NVLink inside `update!`; call `init_nccl` (or `dist.attach_nccl`) first.
-        `order` = `_fd_order` (2 or 4), a compile-time preference upstream (src/GeoPhyInv.jl:85-92)."""
+        `order` = `_fd_order` (2 or 4), a compile-time preference upstream (src/GeoPhyInv.jl:85-92).
+        `jobname`, `backprop_flag`, `illum_flag` are accepted for call compatibility (fdtd.jl:61-78): upstream stores the first, no
+        longer reads the second (the mode of `attrib_mod` replaced it) and allocates a dummy for the third (fdtd.jl:504-506)."""
         N = medium.ndims
         npml = npml_of(order)
         if order != 2 and (attrib_mod.born or zslab is not None):
