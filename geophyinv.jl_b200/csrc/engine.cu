@@ -183,7 +183,7 @@ struct gpi_handle {
     float* halo_send[2] = {nullptr, nullptr};  float* halo_recv[2] = {nullptr, nullptr};   // [0] towards rank-1, [1] towards rank+1
 };
 
-static std::string g_create_err;
+static thread_local std::string g_create_err;      // per host thread: handles may be created from different threads
 
 #define FAIL(h, ...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); (h)->err = _b; return 1; } while (0)
 #define CU(h, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { char _b[512]; \
