@@ -530,7 +530,9 @@ __global__ void k_post(const Geom g, const PostDesc* __restrict__ descs, int it 
                 const long long off = op.axis == 0 ? 1 : (op.axis == 1 ? sy : sx);
                 const float s = __fadd_rn(op.coef[c - (g.h + 1) * off], op.coef[c - g.h * off]);     // @av_?i: integer nodes u-1-h, u-h
                 float* t = op.target[0];
-                t[c] = (float)((double)t[c] + ((double)buf / ((double)s * 0.5) * (double)dt));
+                // Float64 as in the reference, every operation rounded on its own (nvcc would otherwise be free to contract the
+                // product and the sum into one fma, which the CPU path does not do)
+                t[c] = (float)__dadd_rn((double)t[c], __dmul_rn(__ddiv_rn((double)buf, __dmul_rn((double)s, 0.5)), (double)dt));
             }
         }
     }

@@ -23,6 +23,7 @@ static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; retu
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline void __syncthreads() {}      // never reached by the kernels the emulation runs (k_post is compiled, not run)
 static inline int min(int a, int b) { return a < b ? a : b; }
