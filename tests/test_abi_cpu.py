@@ -115,3 +115,24 @@ def test_julia_shim_binds_every_export():
     assert len(exports) >= 30
     missing = [e for e in exports if f"(:{e}, LIB)" not in shim]
     assert not missing, missing
+
+
+def test_no_fma_contraction_in_the_ptx(tmp_path):
+    """Bit-identity with the reference's Base.Threads path rests on evaluating every product and sum separately (Julia does not
+    contract a*b+c outside @fastmath).  The kernels use __fmul_rn / __fadd_rn / __dmul_rn / ... for that; this compiles the
+    library to PTX and checks that nothing was contracted behind their back: no fma.rn.f32 at all, and the only fma.rn.f64 are the
+    four `x + 2.0 * y` of update_dmod! (medium.jl:165), whose product is exact."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ptx = str(tmp_path / "engine.ptx")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=compute_100a", "-O3", "-std=c++17", "-ptx", "-o", ptx,
+                        os.path.join(root, "geophyinv.jl_b200", "csrc", "engine.cu")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    text = open(ptx).read()
+    assert text.count("fma.rn.f32") == 0
+    f64 = [l for l in text.splitlines() if "fma.rn.f64" in l]
+    assert len(f64) <= 4 and all("0d4000000000000000" in l for l in f64), f64[:6]
