@@ -48,7 +48,7 @@ template <int ND, int EL> static int run_case(int nz, int ny, int nx, int npml, 
             for (int q = 0; q < 18; q++) {
                 PmlTerm t; t.mem = s.MEM.data() + (size_t)q * msz; t.a = coef.data() + (size_t)(q * 3 + 0) * 2 * npml;
                 t.b = coef.data() + (size_t)(q * 3 + 1) * 2 * npml; t.kI = coef.data() + (size_t)(q * 3 + 2) * 2 * npml; t.bstride = 18 * msz;
-                (q < 9 ? a.pv : a.ps)[q % 9] = t;
+                if (q < 9) a.pv[q] = t; else a.ps[q - 9] = t;
             }
             a.wstride = 9 * vol; a.nbatch = nbatch;
             return a;

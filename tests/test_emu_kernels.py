@@ -2,7 +2,8 @@
 Every kernel family except the TMA-pipelined one is free of shared memory, barriers and PTX outside four accessor helpers, so running
 its threads one after the other is exact.  The one-thread-per-cell reference-order kernels are pinned to the oracle bit for bit by the
 GPU tests; here the vectorised families must reproduce them on random fields -- CPML slabs on every face, rigid faces, a free surface,
-several resident shots, ragged z extents of the float4 groups -- without a GPU:
+several resident shots, ragged z extents of the float4 groups -- without a GPU, and under AddressSanitizer / UBSan (no access outside
+an operand array):
 
   * order 2: k_vel2v / k_stress2v and k_vel3v / k_stress3v  vs  k_vel / k_stress        (emu_kernels2.cpp, three time steps)
   * order 4: k_vel4v / k_stress4v                             vs  k_vel4 / k_stress4    (emu_kernels4.cpp)
@@ -20,7 +21,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_vectorised_kernels_match_the_reference_order_kernels(tmp_path, name):
     exe = str(tmp_path / name)
     src = os.path.join(ROOT, "tests", "emu", name + ".cpp")
-    r = subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-o", exe, src], capture_output=True, text=True)
+    # AddressSanitizer + UBSan: the operands live in exactly-sized host vectors, so any read or write outside a field, a coefficient
+    # array or a CPML memory block (a halo load at the edge of the box, a float4 straddling a row) aborts the run
+    flags = ["-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w"]
+    san = ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"]
+    r = subprocess.run(["g++"] + flags + san + ["-o", exe, src], capture_output=True, text=True)
+    if r.returncode != 0:                       # toolchain without the sanitizer runtimes: plain build
+        r = subprocess.run(["g++"] + flags + ["-o", exe, src], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     sys.stdout.write(r.stdout)
