@@ -7,6 +7,8 @@ an operand array):
 
   * order 2: k_vel2v / k_stress2v and k_vel3v / k_stress3v  vs  k_vel / k_stress        (emu_kernels2.cpp, three time steps)
   * order 4: k_vel4v / k_stress4v                             vs  k_vel4 / k_stress4    (emu_kernels4.cpp)
+  * bounds + round trip: k_grad2d_el, k_grad3d_el, k_grad3d (orders 2 and 4), k_boundary save -> wipe -> force with three / six
+    fields and a shot batch                                                              (emu_kernels_misc.cpp)
 """
 import os
 import subprocess
@@ -17,7 +19,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("name", ["emu_kernels2", "emu_kernels4"])
+@pytest.mark.parametrize("name", ["emu_kernels2", "emu_kernels4", "emu_kernels_misc"])
 def test_vectorised_kernels_match_the_reference_order_kernels(tmp_path, name):
     exe = str(tmp_path / name)
     src = os.path.join(ROOT, "tests", "emu", name + ".cpp")
