@@ -113,8 +113,63 @@ static int boundary_case(int nd, int h, unsigned seed) {
     return restored == 0 || wrong != 0;
 }
 
+// medium coefficients, rigid faces of the order-4 path, FD-Born coefficient / add kernels, z-plane halo pack / unpack: bounds only
+static int small_kernels_case(int nd, int h, unsigned seed) {
+    const int faces = ZMIN | ZMAX | XMIN | XMAX | (nd == 3 ? YMIN | YMAX : 0);
+    const Geom g = geom(nd, 22, 15, 18, h, 3, faces);
+    const size_t vol = (size_t)g.vol;
+    std::mt19937 rng(seed); std::uniform_real_distribution<float> U(0.5f, 1.5f);
+    auto rnd = [&](size_t n) { std::vector<float> v(n); for (auto& x : v) x = U(rng); return v; };
+    std::vector<float> m0 = rnd(vol), rho = rnd(vol), imu = rnd(vol);
+    std::vector<std::vector<float>> dm(C_N, std::vector<float>(vol, 0.f));
+    float* table[C_N]; for (int q = 0; q < C_N; q++) table[q] = dm[q].data();
+    const emu_dim3 blk = nd == 3 ? d3(16, 2, 2) : d3(16, 2, 1);
+    const emu_dim3 grd = nd == 3 ? d3((g.khi + 16) / 16, (g.ny1 + 1) / 2, (g.nx1 + 1) / 2) : d3((g.khi + 16) / 16, (g.nx1 + 1) / 2, 1);
+    size_t written = 0;
+    for (int el = 0; el < 2; el++) {
+        for (auto& v : dm) std::fill(v.begin(), v.end(), 0.f);
+        float* const* tp = table;
+        if (h == 0) { if (nd == 2) { if (el) launch(k_dmod<2, 1>, grd, blk, g, (const float*)m0.data(), (const float*)rho.data(), (const float*)imu.data(), tp, 1e-3f); else launch(k_dmod<2, 0>, grd, blk, g, (const float*)m0.data(), (const float*)rho.data(), (const float*)nullptr, tp, 1e-3f); }
+                      else         { if (el) launch(k_dmod<3, 1>, grd, blk, g, (const float*)m0.data(), (const float*)rho.data(), (const float*)imu.data(), tp, 1e-3f); else launch(k_dmod<3, 0>, grd, blk, g, (const float*)m0.data(), (const float*)rho.data(), (const float*)nullptr, tp, 1e-3f); } }
+        else        { if (nd == 2) { if (el) launch(k_dmod4<2, 1>, grd, blk, g, (const float*)m0.data(), (const float*)rho.data(), (const float*)imu.data(), tp, 1e-3f); else launch(k_dmod4<2, 0>, grd, blk, g, (const float*)m0.data(), (const float*)rho.data(), (const float*)nullptr, tp, 1e-3f); }
+                      else         { if (el) launch(k_dmod4<3, 1>, grd, blk, g, (const float*)m0.data(), (const float*)rho.data(), (const float*)imu.data(), tp, 1e-3f); else launch(k_dmod4<3, 0>, grd, blk, g, (const float*)m0.data(), (const float*)rho.data(), (const float*)nullptr, tp, 1e-3f); } }
+        for (auto& v : dm) for (float x : v) written += x != 0.f;
+    }
+    if (h == 1) {                                    // rigid faces, two ghost nodes per face
+        std::vector<float> W = rnd(9 * vol);
+        StepArgs a; memset(&a, 0, sizeof a);
+        for (int q = 0; q < 3; q++) a.v[q] = W.data() + (size_t)(6 + q) * vol;
+        a.wstride = 9 * vol; a.nbatch = 1;
+        const int nn[3] = {g.nz, g.ny, g.nx};
+        for (int axis = 2; axis >= 0; axis--) {
+            if (axis == 1 && nd == 2) continue;
+            const int o1 = axis == 0 ? (nd == 3 ? 1 : 2) : 0, o2 = axis == 0 ? (nd == 3 ? 2 : -1) : (axis == 1 ? 2 : (nd == 3 ? 1 : -1));
+            const emu_dim3 fg = d3((nn[o1] + 127) / 128, o2 >= 0 ? nn[o2] : 1, 1);
+            if (nd == 3) launch(k_dirichlet4<3>, fg, d3(128, 1, 1), g, a, axis); else launch(k_dirichlet4<2>, fg, d3(128, 1, 1), g, a, axis);
+        }
+    }
+    if (nd == 2 && h == 0) {                         // FD-Born kernels
+        std::vector<float> dK = rnd(vol), dr = rnd(vol), c0(vol), c1(vol), c2(vol), f0 = rnd(2 * vol), f1 = rnd(2 * vol), dd = rnd(4 * vol);
+        launch(k_born_coef, grd, blk, g, (const float*)m0.data(), (const float*)rho.data(), (const float*)dK.data(), (const float*)dr.data(), c0.data(), c1.data(), c2.data(), 1e-3f);
+        launch(k_born_add<0>, d3(grd.x, grd.y, 2), blk, g, f0.data(), f1.data(), (const float*)dd.data(), (const float*)(dd.data() + vol), (const float*)c1.data(), (const float*)c2.data(), (long long)vol, (long long)(2 * vol));
+        launch(k_born_add<1>, d3(grd.x, grd.y, 2), blk, g, f0.data(), (float*)nullptr, (const float*)dd.data(), (const float*)(dd.data() + vol), (const float*)c0.data(), (const float*)nullptr, (long long)vol, (long long)(2 * vol));
+    }
+    if (nd == 3 && h == 0) {                         // z-plane halo pack / unpack of three fields
+        std::vector<float> W = rnd(3 * vol), buf(3 * (size_t)g.ny1 * g.nx1, 0.f);
+        HaloArgs ha; ha.n = 3; for (int q = 0; q < 3; q++) { ha.field[q] = W.data() + (size_t)q * vol; ha.k[q] = g.khi; }
+        launch(k_halo<1>, d3((g.ny1 + 127) / 128, g.nx1, 1), d3(128, 1, 1), g, ha, buf.data());
+        for (int q = 0; q < 3; q++) ha.k[q] = 0;
+        launch(k_halo<0>, d3((g.ny1 + 127) / 128, g.nx1, 1), d3(128, 1, 1), g, ha, buf.data());
+        for (int q = 0; q < 3; q++) for (int i = 0; i < g.nx1; i++) for (int j = 0; j < g.ny1; j++)
+            if (W[q * vol + 0 + (size_t)g.pz * (j + (size_t)g.ny1 * i)] != W[q * vol + g.khi + (size_t)g.pz * (j + (size_t)g.ny1 * i)]) return 1;
+    }
+    printf("  medium coefficients / rigid faces / Born / halo kernels %d-D, order %d: %zu coefficients written\n", nd, 2 + 2 * h, written);
+    return written == 0;
+}
+
 int main() {
     int bad = 0;
+    for (int h = 0; h < 2; h++) { bad += small_kernels_case(2, h, 11 + h); bad += small_kernels_case(3, h, 13 + h); }
     for (int h = 0; h < 2; h++) { bad += grad_case(2, h, 1 + h); bad += grad_case(3, h, 3 + h); }
     for (int h = 0; h < 2; h++) { bad += boundary_case(2, h, 5 + h); bad += boundary_case(3, h, 7 + h); }
     printf(bad ? "EMU_MISMATCH\n" : "EMU_OK\n");
