@@ -160,6 +160,9 @@ struct gpi_handle {
     std::vector<int32_t> itsnaps;
     PostDesc *post_v = nullptr, *post_s = nullptr, *h_post_v = nullptr, *h_post_s = nullptr;
     float** bnd_table = nullptr;        // boundary stores of the resident batch, [b][field][axis]
+    // GPI_PINGPONG=1 (2-D, order 2, adjoint runs): W and TP alternate as the time levels instead of save_tp!'s copy; the forced
+    // boundary planes of the level that stays behind get their pre-force values back from `stash` ([b][field][axis], one slot)
+    bool pingpong = false;  float* stash = nullptr;  float** stash_table = nullptr;
     float* stage = nullptr;  size_t stage_floats = 0;       // pinned host staging
     float* dscratch = nullptr;  size_t dscratch_floats = 0; // device scratch (raw interior medium before padding)
     gpi_timers timers{};
@@ -279,10 +282,11 @@ dim3 grid_for(const gpi_handle* h, dim3 blk, int nbatch) {
 
 // `merged`: both wavefields of every resident shot in ONE launch.  The wavefield sets are laid out [b][pw][slot] and the
 // CPML memory [b][pw][term], so slot b' = b * npw + ipw of a launch with the per-pw strides is wavefield ipw of shot b.
-void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch, bool merged = false) {
+void fill_args(gpi_handle* h, StepArgs& a, int ipw, int nbatch, bool merged = false, float* base = nullptr) {
     memset(&a, 0, sizeof a);
-    for (int s = 0; s < 6; s++) a.tau[s] = h->slot_tau[s] >= 0 ? h->W + (long long)ipw * h->pwstride + (long long)h->slot_tau[s] * h->g.vol : nullptr;
-    for (int s = 0; s < 3; s++) a.v[s] = h->slot_v[s] >= 0 ? h->W + (long long)ipw * h->pwstride + (long long)h->slot_v[s] * h->g.vol : nullptr;
+    if (!base) base = h->W;
+    for (int s = 0; s < 6; s++) a.tau[s] = h->slot_tau[s] >= 0 ? base + (long long)ipw * h->pwstride + (long long)h->slot_tau[s] * h->g.vol : nullptr;
+    for (int s = 0; s < 3; s++) a.v[s] = h->slot_v[s] >= 0 ? base + (long long)ipw * h->pwstride + (long long)h->slot_v[s] * h->g.vol : nullptr;
     for (int s = 0; s < C_N; s++) a.c[s] = h->dmod[s];
     const int np2 = 2 * h->c.npml;
     for (const auto& t : h->terms) {
@@ -424,6 +428,11 @@ void launch_step_kernels(gpi_handle* h, const StepArgs& a, bool vel, int nbatch)
     if (ND == 2 && h->vec2 && !a.dout[0]) {        // the derivative write-out of FD-Born lives in the scalar kernels
         const int nthreads = (h->g.pz / VW) * h->g.nx1;
         dim3 blk(128), grd((nthreads + 127) / 128, nbatch);
+        if (vel ? a.v_o[V_X] != nullptr : a.tau_o[T_XX] != nullptr) {      // out of place (ping-pong adjoint runs)
+            if (vel) k_vel2v<EL, 1><<<grd, blk, 0, h->stream>>>(h->g, a);
+            else     k_stress2v<EL, 1><<<grd, blk, 0, h->stream>>>(h->g, a);
+            return;
+        }
         if (vel) k_vel2v<EL><<<grd, blk, 0, h->stream>>>(h->g, a);
         else     k_stress2v<EL><<<grd, blk, 0, h->stream>>>(h->g, a);
         return;
@@ -510,7 +519,8 @@ long long bnd_slot_floats(const gpi_handle* h, int axis) {
     return (long long)g.nx1 * g.ny1 * nb2;
 }
 // one launch for the whole batch: every stored field, axis and plane (k_boundary)
-int launch_boundary(gpi_handle* h, bool save, int nb, int slot /* 0-based time slot */) {
+int launch_boundary(gpi_handle* h, int save /* 0 force, 1 save (negated), 2 copy out */, int nb, int slot /* 0-based time slot */,
+                    float* base = nullptr, float* const* table = nullptr) {
     const Geom& g = h->g;
     BndArgs a; memset(&a, 0, sizeof a);
     int bf[6]; a.nf = boundary_fields(h, bf);
@@ -522,7 +532,7 @@ int launch_boundary(gpi_handle* h, bool save, int nb, int slot /* 0-based time s
         int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
         field_shape(h->nd, bf[i], n, sh, off, h->c.order);
         BndField& F = a.f[i];
-        F.f0 = wf_ptr(h, h->W, 0, 0, bf[i]);
+        F.f0 = wf_ptr(h, base ? base : h->W, 0, 0, bf[i]);
         for (int ia = 0; ia < a.naxes; ia++) {
             const int axis = a.axes[ia];
             const int minbit = axis == 0 ? ZMIN : axis == 1 ? YMIN : XMIN;
@@ -539,11 +549,12 @@ int launch_boundary(gpi_handle* h, bool save, int nb, int slot /* 0-based time s
         vmax = std::max(vmax, axis == 1 ? g.nx1 : g.ny1);
         a.slot_off[axis] = (long long)slot * bnd_slot_floats(h, axis);
     }
-    a.stores = h->bnd_table;
+    a.stores = table ? table : h->bnd_table;
     a.wstride = h->bstride;
     dim3 blk(128), grd((umax + 127) / 128, vmax, 2 * a.nbound * a.naxes * a.nf * nb);
-    if (save) k_boundary<1><<<grd, blk, 0, h->stream>>>(g, a);
-    else      k_boundary<0><<<grd, blk, 0, h->stream>>>(g, a);
+    if (save == 2)  k_boundary<2><<<grd, blk, 0, h->stream>>>(g, a);
+    else if (save)  k_boundary<1><<<grd, blk, 0, h->stream>>>(g, a);
+    else            k_boundary<0><<<grd, blk, 0, h->stream>>>(g, a);
     h->timers.launches += 1;
     return 0;
 }
@@ -556,6 +567,24 @@ int build_bnd_table(gpi_handle* h, int shot0, int nb) {
     if (!h->bnd_table) CU(h, cudaMalloc((void**)&h->bnd_table, (size_t)h->B * 18 * sizeof(float*)));
     CU(h, cudaMemcpyAsync(h->bnd_table, t.data(), t.size() * sizeof(float*), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));      // `t` is a pageable temporary
+    return 0;
+}
+
+// ping-pong adjoint runs: one store slot per (batch slot, stored field, axis) for the pre-force values of the forced planes
+int ensure_stash(gpi_handle* h) {
+    if (h->stash_table) return 0;
+    int bf[6]; const int nbf = boundary_fields(h, bf);
+    long long per_field = 0, off[3] = {0, 0, 0};
+    for (int q = 0; q < 3; q++) { if (q == 1 && h->nd == 2) continue; off[q] = per_field; per_field += (bnd_slot_floats(h, q) + 31) / 32 * 32; }
+    CU(h, cudaMalloc((void**)&h->stash, (size_t)h->B * nbf * per_field * sizeof(float)));
+    CU(h, cudaMemset(h->stash, 0, (size_t)h->B * nbf * per_field * sizeof(float)));
+    std::vector<float*> t((size_t)h->B * nbf * 3, nullptr);
+    for (int b = 0; b < h->B; b++) for (int i = 0; i < nbf; i++) for (int q = 0; q < 3; q++) {
+        if (q == 1 && h->nd == 2) continue;
+        t[((size_t)b * nbf + i) * 3 + q] = h->stash + ((size_t)b * nbf + i) * per_field + off[q];
+    }
+    CU(h, cudaMalloc((void**)&h->stash_table, t.size() * sizeof(float*)));
+    CU(h, cudaMemcpy(h->stash_table, t.data(), t.size() * sizeof(float*), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -812,6 +841,7 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (const char* e = getenv("GPI_TMA3_CTAS")) h->tma3_ctas = atoi(e);
     if (const char* e = getenv("GPI_SHELL")) h->shell_mode = atoi(e);
     if (const char* e = getenv("GPI_O4VEC")) h->o4vec = atoi(e) != 0;
+    if (const char* e = getenv("GPI_PINGPONG")) h->pingpong = atoi(e) != 0;
     if (h->nd == 3 && h->el) {
         cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
         cudaError_t e0 = cudaFuncSetAttribute(t3::k_step3t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3::smem_bytes(0));
@@ -848,7 +878,7 @@ extern "C" int gpi_destroy(gpi_handle* h) {
         }
         for (auto p : s.usnaps) cudaFree(p);
     }
-    cudaFree(h->post_v); cudaFree(h->post_s); cudaFree(h->bnd_table);
+    cudaFree(h->post_v); cudaFree(h->post_s); cudaFree(h->bnd_table); cudaFree(h->stash); cudaFree(h->stash_table);
     if (h->h_post_v) cudaFreeHost(h->h_post_v);
     if (h->h_post_s) cudaFreeHost(h->h_post_s);
     if (h->stage) cudaFreeHost(h->stage);
@@ -1272,6 +1302,9 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     if (mode == GPI_MODE_FORWARD_SAVE && !h->c.store_boundary) FAIL(h, "forward_save needs store_boundary=1 at construction (fdtd.jl:445-455)");
     if (mode == GPI_MODE_ADJOINT && !h->c.store_boundary) FAIL(h, "adjoint needs the boundary store of a forward_save run");
     const bool grad = mode == GPI_MODE_ADJOINT && (activepw & 2) && h->npw == 2;
+    // GPI_PINGPONG=1: the two wavefield sets alternate as "this step" / "previous step" (what save_tp! copies, save_tp.jl:5-12)
+    const bool pp = h->pingpong && mode == GPI_MODE_ADJOINT && h->TP && h->nd == 2 && h->c.order == 2 && h->vec2 && !born && !h->slab;
+    if (pp && ensure_stash(h)) return 1;
     if (grad && !h->gshot) FAIL(h, "gradient imaging needs an experiment built with npw = 2");
     if (unshifted && h->el) FAIL(h, "the exact-transpose rho imaging is defined for acoustic media");
     const Geom& g = h->g;
@@ -1309,27 +1342,44 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
         if (merge_pw) fill_args(h, margs, 0, nb, true);
         if (born) { args[0].dout[0] = h->born_d; args[0].dout[1] = h->born_d + g.vol; args[0].dstride = 2 * g.vol; }
         // record!(1, ..., [:p]) at the start of step 1 (zero unless the fields were loaded from snapshots)
-        if (rec_s) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, 1, 1, nt, (float)h->c.dt, 2); h->timers.launches += 1; }
+        if (rec_s) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, 1, 1, nt, (float)h->c.dt, 2, 0LL); h->timers.launches += 1; }
+        // time levels: `cur` holds the fields of this step, `prev` those of the step before (adjoint runs; always W / TP without ping-pong)
+        float* cur = h->W; float* prev = h->TP;
+        float* const W0 = h->W;            // the descriptors and StepArgs above were built on this base
+        long long woff = 0;                // cur - W0
+        auto rebase = [&](const StepArgs& src, float* A, float* B, bool vel) {     // out-of-place step A -> B
+            StepArgs a = src;
+            for (int q = 0; q < 6; q++) if (src.tau[q]) { a.tau[q] = A + (src.tau[q] - W0); if (!vel) a.tau_o[q] = B + (src.tau[q] - W0); }
+            for (int q = 0; q < 3; q++) if (src.v[q]) { a.v[q] = (vel ? A : B) + (src.v[q] - W0); if (vel) a.v_o[q] = B + (src.v[q] - W0); }
+            return a;
+        };
 
         for (int it = 1; it <= nt; it++) {
-            if (mode == GPI_MODE_ADJOINT) {
+            float* A = cur; float* Bn = prev;      // ping-pong: this step reads level A and writes level Bn
+            if (pp) {
+                // the planes boundary_force! overwrites keep their values aside: A stays behind as the previous level, which
+                // save_tp! copies BEFORE the force (propagate.jl:186-188)
+                if (launch_boundary(h, 2, nb, 0, A, h->stash_table)) return 1;
+                if (launch_boundary(h, 0, nb, nt - it, A)) return 1;
+                woff = Bn - W0;
+            } else if (mode == GPI_MODE_ADJOINT) {
                 // save_tp! (save_tp.jl:5-12): one device copy of every wavefield of the batch
                 CU(h, cudaMemcpyAsync(h->TP, h->W, (size_t)nb * h->bstride * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
                 // boundary_force!(nt - it + 1) on pw 1 (propagate.jl:188), x then (y) then z
                 if (launch_boundary(h, false, nb, nt - it)) return 1;
             }
             const bool sample = h->sample_every > 0 && (it % h->sample_every) == 0;
-            if (merge_pw) launch_step(h, margs, true, margs.nbatch, sample);
-            else for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], true, nb, sample && ipw == 0);
+            if (merge_pw) launch_step(h, pp ? rebase(margs, A, Bn, true) : margs, true, margs.nbatch, sample);
+            else for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, pp ? rebase(args[ipw], A, Bn, true) : args[ipw], true, nb, sample && ipw == 0);
             if (born) {        // add_born_sources_velocity! (propagate.jl:205)
                 dim3 blk = h->blk2, grd = grid_for(h, blk, nb);
                 k_born_add<0><<<grd, blk, 0, h->stream>>>(g, args[1].v[V_X], args[1].v[V_Z], h->born_d, h->born_d + g.vol, h->born_c[1], h->born_c[2], h->bstride, 2 * g.vol);
                 h->timers.launches += 1;
             }
-            if (do_post_v) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_v, it, it, nt, (float)h->c.dt, 3); h->timers.launches += 1; }
+            if (do_post_v) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_v, it, it, nt, (float)h->c.dt, 3, woff); h->timers.launches += 1; }
             if (exchange_halos(h, 1)) return 1;
-            if (merge_pw) launch_step(h, margs, false, margs.nbatch, sample);
-            else for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, args[ipw], false, nb, sample && ipw == 0);
+            if (merge_pw) launch_step(h, pp ? rebase(margs, A, Bn, false) : margs, false, margs.nbatch, sample);
+            else for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, pp ? rebase(args[ipw], A, Bn, false) : args[ipw], false, nb, sample && ipw == 0);
             if (born) {        // add_born_sources_stress! (propagate.jl:226)
                 dim3 blk = h->blk2, grd = grid_for(h, blk, nb);
                 k_born_add<1><<<grd, blk, 0, h->stream>>>(g, args[1].tau[T_XX], nullptr, h->born_d, h->born_d + g.vol, h->born_c[0], nullptr, h->bstride, 2 * g.vol);
@@ -1337,8 +1387,12 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             }
             // stress sources at step it, then the pressure record of step it+1 (record! runs at the start of a step)
             if (inj_s || (rec_s && it < nt)) {
-                k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, it, it + 1, nt, (float)h->c.dt, 3);
+                k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, it, it + 1, nt, (float)h->c.dt, 3, woff);
                 h->timers.launches += 1;
+            }
+            if (pp) {
+                if (launch_boundary(h, 0, nb, 0, A, h->stash_table)) return 1;      // the previous level as save_tp! would have left it
+                cur = Bn; prev = A;
             }
             if (exchange_halos(h, 0)) return 1;
             if (mode == GPI_MODE_FORWARD_SAVE && launch_boundary(h, true, nb, it - 1)) return 1;
@@ -1346,8 +1400,8 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                 const int tf[6] = {GPI_TAUXX, GPI_TAUYY, GPI_TAUZZ, GPI_TAUXY, GPI_TAUXZ, GPI_TAUYZ};     // T_XX .. T_YZ
                 for (int b = 0; b < nb; b++) {
                     GradE3Args ga;
-                    for (int q = 0; q < 6; q++) { ga.t1[q] = wf_ptr(h, h->W, b, 0, tf[q]); ga.t1tp[q] = wf_ptr(h, h->TP, b, 0, tf[q]); ga.t2tp[q] = wf_ptr(h, h->TP, b, 1, tf[q]); }
-                    for (int q = 0; q < 3; q++) { ga.v1[q] = wf_ptr(h, h->W, b, 0, vf[q]); ga.v1tp[q] = wf_ptr(h, h->TP, b, 0, vf[q]); ga.v2tp[q] = wf_ptr(h, h->TP, b, 1, vf[q]); }
+                    for (int q = 0; q < 6; q++) { ga.t1[q] = wf_ptr(h, cur, b, 0, tf[q]); ga.t1tp[q] = wf_ptr(h, prev, b, 0, tf[q]); ga.t2tp[q] = wf_ptr(h, prev, b, 1, tf[q]); }
+                    for (int q = 0; q < 3; q++) { ga.v1[q] = wf_ptr(h, cur, b, 0, vf[q]); ga.v1tp[q] = wf_ptr(h, prev, b, 0, vf[q]); ga.v2tp[q] = wf_ptr(h, prev, b, 1, vf[q]); }
                     ga.il = h->mod[GPI_INVLAMBDA]; ga.im = h->mod[GPI_INVMU];
                     ga.gL = h->gshot + (size_t)b * 3 * g.vol; ga.gM = ga.gL + g.vol; ga.gR = ga.gL + 2 * g.vol;
                     dim3 blk = h->blk3, grd = grid_for(h, blk, 1);
@@ -1356,11 +1410,11 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                 }
             } else if (grad && h->el) {
                 GradE2Args ga;
-                ga.xx1 = wf_ptr(h, h->W, 0, 0, GPI_TAUXX); ga.zz1 = wf_ptr(h, h->W, 0, 0, GPI_TAUZZ); ga.xz1 = wf_ptr(h, h->W, 0, 0, GPI_TAUXZ);
-                ga.xx1tp = wf_ptr(h, h->TP, 0, 0, GPI_TAUXX); ga.zz1tp = wf_ptr(h, h->TP, 0, 0, GPI_TAUZZ); ga.xz1tp = wf_ptr(h, h->TP, 0, 0, GPI_TAUXZ);
-                ga.xx2tp = wf_ptr(h, h->TP, 0, 1, GPI_TAUXX); ga.zz2tp = wf_ptr(h, h->TP, 0, 1, GPI_TAUZZ); ga.xz2tp = wf_ptr(h, h->TP, 0, 1, GPI_TAUXZ);
-                ga.vx1 = wf_ptr(h, h->W, 0, 0, GPI_VX); ga.vx1tp = wf_ptr(h, h->TP, 0, 0, GPI_VX); ga.vx2tp = wf_ptr(h, h->TP, 0, 1, GPI_VX);
-                ga.vz1 = wf_ptr(h, h->W, 0, 0, GPI_VZ); ga.vz1tp = wf_ptr(h, h->TP, 0, 0, GPI_VZ); ga.vz2tp = wf_ptr(h, h->TP, 0, 1, GPI_VZ);
+                ga.xx1 = wf_ptr(h, cur, 0, 0, GPI_TAUXX); ga.zz1 = wf_ptr(h, cur, 0, 0, GPI_TAUZZ); ga.xz1 = wf_ptr(h, cur, 0, 0, GPI_TAUXZ);
+                ga.xx1tp = wf_ptr(h, prev, 0, 0, GPI_TAUXX); ga.zz1tp = wf_ptr(h, prev, 0, 0, GPI_TAUZZ); ga.xz1tp = wf_ptr(h, prev, 0, 0, GPI_TAUXZ);
+                ga.xx2tp = wf_ptr(h, prev, 0, 1, GPI_TAUXX); ga.zz2tp = wf_ptr(h, prev, 0, 1, GPI_TAUZZ); ga.xz2tp = wf_ptr(h, prev, 0, 1, GPI_TAUXZ);
+                ga.vx1 = wf_ptr(h, cur, 0, 0, GPI_VX); ga.vx1tp = wf_ptr(h, prev, 0, 0, GPI_VX); ga.vx2tp = wf_ptr(h, prev, 0, 1, GPI_VX);
+                ga.vz1 = wf_ptr(h, cur, 0, 0, GPI_VZ); ga.vz1tp = wf_ptr(h, prev, 0, 0, GPI_VZ); ga.vz2tp = wf_ptr(h, prev, 0, 1, GPI_VZ);
                 ga.il = h->mod[GPI_INVLAMBDA]; ga.im = h->mod[GPI_INVMU];
                 ga.gL = h->gshot; ga.gM = h->gshot + g.vol; ga.gR = h->gshot + 2 * g.vol;
                 ga.wstride = h->bstride; ga.gstride = 3 * g.vol;
@@ -1370,9 +1424,9 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             } else if (grad && h->nd == 3) {
                 for (int b = 0; b < nb; b++) {
                     Grad3Args ga;
-                    ga.p1 = wf_ptr(h, h->W, b, 0, GPI_P); ga.p1tp = wf_ptr(h, h->TP, b, 0, GPI_P); ga.p2tp = wf_ptr(h, h->TP, b, 1, GPI_P);
+                    ga.p1 = wf_ptr(h, cur, b, 0, GPI_P); ga.p1tp = wf_ptr(h, prev, b, 0, GPI_P); ga.p2tp = wf_ptr(h, prev, b, 1, GPI_P);
                     for (int q = 0; q < 3; q++) {
-                        ga.v1[q] = wf_ptr(h, h->W, b, 0, vf[q]); ga.v1tp[q] = wf_ptr(h, h->TP, b, 0, vf[q]); ga.v2tp[q] = wf_ptr(h, h->TP, b, 1, vf[q]);
+                        ga.v1[q] = wf_ptr(h, cur, b, 0, vf[q]); ga.v1tp[q] = wf_ptr(h, prev, b, 0, vf[q]); ga.v2tp[q] = wf_ptr(h, prev, b, 1, vf[q]);
                     }
                     ga.gK = h->gshot + (size_t)b * 2 * g.vol; ga.gR = ga.gK + g.vol;
                     dim3 blk = h->blk3, grd = grid_for(h, blk, 1);
@@ -1382,15 +1436,15 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             } else if (grad) {
                 dim3 blk = h->blk2, grd = grid_for(h, blk, nb);
                 k_grad2d<<<grd, blk, 0, h->stream>>>(g,
-                    wf_ptr(h, h->W, 0, 0, GPI_P), wf_ptr(h, h->TP, 0, 0, GPI_P), wf_ptr(h, h->TP, 0, 1, GPI_P),
-                    wf_ptr(h, h->W, 0, 0, GPI_VX), wf_ptr(h, h->TP, 0, 0, GPI_VX), wf_ptr(h, h->TP, 0, 1, GPI_VX),
-                    wf_ptr(h, h->W, 0, 0, GPI_VZ), wf_ptr(h, h->TP, 0, 0, GPI_VZ), wf_ptr(h, h->TP, 0, 1, GPI_VZ),
+                    wf_ptr(h, cur, 0, 0, GPI_P), wf_ptr(h, prev, 0, 0, GPI_P), wf_ptr(h, prev, 0, 1, GPI_P),
+                    wf_ptr(h, cur, 0, 0, GPI_VX), wf_ptr(h, prev, 0, 0, GPI_VX), wf_ptr(h, prev, 0, 1, GPI_VX),
+                    wf_ptr(h, cur, 0, 0, GPI_VZ), wf_ptr(h, prev, 0, 0, GPI_VZ), wf_ptr(h, prev, 0, 1, GPI_VZ),
                     h->gshot, h->gshot + g.vol, (float)h->c.dtI, h->bstride, 2 * g.vol, unshifted);
                 h->timers.launches += 1;
             }
             if (!h->itsnaps.empty()) for (int ks = 0; ks < (int)h->itsnaps.size(); ks++) if (h->itsnaps[ks] == it)
                 for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) for (int b = 0; b < nb; b++)
-                    CU(h, cudaMemcpyAsync(h->shots[ipw][shot0 + b].usnaps[ks], wf_ptr(h, h->W, b, ipw, h->c.snaps_field), vb, cudaMemcpyDeviceToDevice, h->stream));
+                    CU(h, cudaMemcpyAsync(h->shots[ipw][shot0 + b].usnaps[ks], wf_ptr(h, cur, b, ipw, h->c.snaps_field), vb, cudaMemcpyDeviceToDevice, h->stream));
         }
         // final state for the initial-value problem of the time reversal (propagate.jl:251-258)
         if (mode == GPI_MODE_FORWARD_SAVE)
@@ -1398,7 +1452,11 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                 k_negate_copy<<<(unsigned)((g.vol + 255) / 256), 256, 0, h->stream>>>(h->shots[0][shot0 + b].snap[bf[i]], wf_ptr(h, h->W, b, 0, bf[i]), g.vol);
                 h->timers.launches += 1;
             }
-        launch_step(h, args[0], true, nb);
+        if (cur != W0) {       // ping-pong run that ended on the other set: from here on it is the wavefield set
+            StepArgs fin; fill_args(h, fin, 0, nb, false, cur);
+            launch_step(h, fin, true, nb);
+            std::swap(h->W, h->TP);
+        } else launch_step(h, args[0], true, nb);
         if (mode == GPI_MODE_FORWARD_SAVE)
             for (int b = 0; b < nb; b++) for (int i = 0; i < 3; i++) if (h->shots[0][shot0 + b].snap[vf[i]])
                 CU(h, cudaMemcpyAsync(h->shots[0][shot0 + b].snap[vf[i]], wf_ptr(h, h->W, b, 0, vf[i]), vb, cudaMemcpyDeviceToDevice, h->stream));

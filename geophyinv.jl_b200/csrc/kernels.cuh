@@ -79,6 +79,11 @@ struct StepArgs {
     // wavefield (dpdx, dpdz in the velocity kernel; dvxdx, dvzdz in the stress kernel), the scattering sources
     float* dout[2];
     long long dstride;       // floats between batch slots of dout
+    // out-of-place stepping (the OOP instantiations only; adjoint runs with GPI_PINGPONG=1): the velocity kernel reads v and
+    // writes v_o, the stress kernel reads tau and writes tau_o -- the set just read stays behind as the previous time level,
+    // which is what save_tp! (save_tp.jl:5-12) otherwise copies
+    float* tau_o[6];
+    float* v_o[3];
 };
 
 __device__ __forceinline__ long long uidx(const Geom& g, int k, int j, int i) {
@@ -155,7 +160,7 @@ __device__ __forceinline__ bool cell(const Geom& g, int nbatch, int& k, int& j, 
 //   acoustic : 0 dpdx, 1 dpdy, 2 dpdz
 //   elastic  : 0 dtauxxdx 1 dtauxydy 2 dtauxzdz | 3 dtauxydx 4 dtauyydy 5 dtauyzdz | 6 dtauxzdx 7 dtauyzdy 8 dtauzzdz
 // ------------------------------------------------------------------------------------------------
-template <int ND, int EL>
+template <int ND, int EL, int OOP = 0>
 __device__ __forceinline__ void vel_cell(const Geom& g, const StepArgs& a, int kl, int j, int i, int b) {
     const long long w = (long long)b * a.wstride;
     const long long c = uidx(g, kl, j, i);
@@ -175,11 +180,14 @@ __device__ __forceinline__ void vel_cell(const Geom& g, const StepArgs& a, int k
     const bool vzown = i <= nx - 1 && (ND == 2 || j <= ny - 1);            // k <= nz always
     const bool vyown = (ND == 3) && k <= nz - 1 && i <= nx - 1;            // j <= ny always
 
-    float* vx = a.v[V_X] + w; float* vz = a.v[V_Z] + w; float* vy = (ND == 3) ? a.v[V_Y] + w : nullptr;
+    float* vx = (OOP ? a.v_o[V_X] : a.v[V_X]) + w; float* vz = (OOP ? a.v_o[V_Z] : a.v[V_Z]) + w;        // written
+    float* vy = (ND == 3) ? (OOP ? a.v_o[V_Y] : a.v[V_Y]) + w : nullptr;
     float nvx = 0.f, nvy = 0.f, nvz = 0.f;
-    if (vxown) nvx = vx[c];
-    if (vzown) nvz = vz[c];
-    if (ND == 3 && vyown) nvy = vy[c];
+    const float* vxi = OOP ? a.v[V_X] + w : vx; const float* vzi = OOP ? a.v[V_Z] + w : vz;                  // read
+    const float* vyi = (ND == 3) ? (OOP ? a.v[V_Y] + w : vy) : nullptr;
+    if (vxown) nvx = vxi[c];
+    if (vzown) nvz = vzi[c];
+    if (ND == 3 && vyown) nvy = vyi[c];
 
     if (!EL) {
         const float* p = a.tau[T_XX] + w;
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(256) k_vel(const Geom g, const StepArgs a) {
 // CPML term order in a.ps:
 //   0 dvxdx 1 dvydy 2 dvzdz | 3 dvxdy 4 dvydx (tauxy) | 5 dvxdz 6 dvzdx (tauxz) | 7 dvydz 8 dvzdy (tauyz)
 // ------------------------------------------------------------------------------------------------
-template <int ND, int EL>
+template <int ND, int EL, int OOP = 0>
 __device__ __forceinline__ void stress_cell(const Geom& g, const StepArgs& a, int kl, int j, int i, int b) {
     const long long w = (long long)b * a.wstride;
     const long long c = uidx(g, kl, j, i);
@@ -347,9 +355,10 @@ __device__ __forceinline__ void stress_cell(const Geom& g, const StepArgs& a, in
     if (!EL) {
         if (ND == 2 && nin && a.dout[0]) { a.dout[0][c + (long long)b * a.dstride] = dxx; a.dout[1][c + (long long)b * a.dstride] = dzz; }
         if (nin) {
-            float* p = a.tau[T_XX] + w;
+            const float* p = a.tau[T_XX] + w;
+            float* po = (OOP ? a.tau_o[T_XX] : a.tau[T_XX]) + w;
             const float s = (ND == 3) ? __fadd_rn(__fadd_rn(dxx, dzz), dyy) : __fadd_rn(dxx, dzz);
-            p[c] = __fadd_rn(p[c], __fmul_rn(s, __ldg(a.c[C_K] + c)));
+            po[c] = __fadd_rn(p[c], __fmul_rn(s, __ldg(a.c[C_K] + c)));
         }
         return;
     }
@@ -357,55 +366,60 @@ __device__ __forceinline__ void stress_cell(const Geom& g, const StepArgs& a, in
     const bool fs = (g.freesurf & ZMIN) != 0;
     if (nin) {
         const float M = __ldg(a.c[C_K] + c), L = __ldg(a.c[C_L] + c);
-        float* txx = a.tau[T_XX] + w; float* tzz = a.tau[T_ZZ] + w;
+        const float* txx = a.tau[T_XX] + w; const float* tzz = a.tau[T_ZZ] + w;
+        float* oxx = (OOP ? a.tau_o[T_XX] : a.tau[T_XX]) + w; float* ozz = (OOP ? a.tau_o[T_ZZ] : a.tau[T_ZZ]) + w;
         float nzz;
         if (ND == 3) {
-            float* tyy = a.tau[T_YY] + w;
-            txx[c] = __fsub_rn(__fsub_rn(txx[c], __fmul_rn(M, dxx)), __fmul_rn(L, __fadd_rn(dyy, dzz)));
-            tyy[c] = __fsub_rn(__fsub_rn(tyy[c], __fmul_rn(M, dyy)), __fmul_rn(L, __fadd_rn(dxx, dzz)));
+            const float* tyy = a.tau[T_YY] + w;
+            float* oyy = (OOP ? a.tau_o[T_YY] : a.tau[T_YY]) + w;
+            oxx[c] = __fsub_rn(__fsub_rn(txx[c], __fmul_rn(M, dxx)), __fmul_rn(L, __fadd_rn(dyy, dzz)));
+            oyy[c] = __fsub_rn(__fsub_rn(tyy[c], __fmul_rn(M, dyy)), __fmul_rn(L, __fadd_rn(dxx, dzz)));
             nzz    = __fsub_rn(__fsub_rn(tzz[c], __fmul_rn(M, dzz)), __fmul_rn(L, __fadd_rn(dyy, dxx)));
         } else {
-            txx[c] = __fsub_rn(__fsub_rn(txx[c], __fmul_rn(M, dxx)), __fmul_rn(L, dzz));
+            oxx[c] = __fsub_rn(__fsub_rn(txx[c], __fmul_rn(M, dxx)), __fmul_rn(L, dzz));
             nzz    = __fsub_rn(__fsub_rn(tzz[c], __fmul_rn(M, dzz)), __fmul_rn(L, dxx));
         }
         // free surface (advance_elastic.jl:215-230): tauzz[1] = -tauzz[2], written by the owner of node 2
-        if (!(fs && k == 0)) tzz[c] = nzz;
-        if (fs && k == 1) tzz[c - 1] = -nzz;
+        if (!(fs && k == 0)) ozz[c] = nzz;
+        if (fs && k == 1) ozz[c - 1] = -nzz;
     }
     // shear stresses on their own (half) grids
     const bool jh = (ND == 2) || (j >= 1 && j <= ny - 1);     // half nodes along y
     const bool jj = (ND == 2) || (j >= 1 && j <= ny - 2);     // inner nodes along y
     // tauxz: z half, y inner, x half
     if (k >= 1 && k <= nz - 1 && jj && i >= 1 && i <= nx - 1) {
-        float* txz = a.tau[T_XZ] + w;
+        const float* txz = a.tau[T_XZ] + w;
+        float* oxz = (OOP ? a.tau_o[T_XZ] : a.tau[T_XZ]) + w;
         float dxz = __fmul_rn(__fsub_rn(cvx, vx[c - 1]), g.dzI);               // @d_zi(vx)
         dxz = cpml<0>(g, a.ps[5], dxz, k, j, i, 1, nz - 1, b);
         float dzx = __fmul_rn(__fsub_rn(cvz, vz[c - sx]), g.dxI);              // @d_xi(vz)
         dzx = cpml<2>(g, a.ps[6], dzx, k, j, i, 1, nx - 1, b);
         float n = __fsub_rn(txz[c], __fmul_rn(__ldg(a.c[C_MUXZ] + c), __fadd_rn(dxz, dzx)));
         if (fs && k == 1) n = 0.f;                                             // free_surface!(tauxz)
-        txz[c] = n;
+        oxz[c] = n;
     }
     if (ND == 3) {
         // tauxy: z inner, y half, x half
         if (k >= 1 && k <= nz - 2 && jh && i >= 1 && i <= nx - 1) {
-            float* txy = a.tau[T_XY] + w;
+            const float* txy = a.tau[T_XY] + w;
+            float* oxy = (OOP ? a.tau_o[T_XY] : a.tau[T_XY]) + w;
             float dxy = __fmul_rn(__fsub_rn(cvx, vx[c - sy]), g.dyI);          // @d_yi(vx)
             dxy = cpml<1>(g, a.ps[3], dxy, k, j, i, 1, ny - 1, b);
             float dyx = __fmul_rn(__fsub_rn(cvy, vy[c - sx]), g.dxI);          // @d_xi(vy)
             dyx = cpml<2>(g, a.ps[4], dyx, k, j, i, 1, nx - 1, b);
-            txy[c] = __fsub_rn(txy[c], __fmul_rn(__ldg(a.c[C_MUXY] + c), __fadd_rn(dxy, dyx)));
+            oxy[c] = __fsub_rn(txy[c], __fmul_rn(__ldg(a.c[C_MUXY] + c), __fadd_rn(dxy, dyx)));
         }
         // tauyz: z half, y half, x inner
         if (k >= 1 && k <= nz - 1 && jh && i >= 1 && i <= nx - 2) {
-            float* tyz = a.tau[T_YZ] + w;
+            const float* tyz = a.tau[T_YZ] + w;
+            float* oyz = (OOP ? a.tau_o[T_YZ] : a.tau[T_YZ]) + w;
             float dyz = __fmul_rn(__fsub_rn(cvy, vy[c - 1]), g.dzI);           // @d_zi(vy)
             dyz = cpml<0>(g, a.ps[7], dyz, k, j, i, 1, nz - 1, b);
             float dzy = __fmul_rn(__fsub_rn(cvz, vz[c - sy]), g.dyI);          // @d_yi(vz)
             dzy = cpml<1>(g, a.ps[8], dzy, k, j, i, 1, ny - 1, b);
             float n = __fsub_rn(tyz[c], __fmul_rn(__ldg(a.c[C_MUYZ] + c), __fadd_rn(dyz, dzy)));
             if (fs && k == 1) n = 0.f;                                         // free_surface!(tauyz)
-            tyz[c] = n;
+            oyz[c] = n;
         }
     }
 }
@@ -510,8 +524,9 @@ struct RecOp {
 enum { MAX_OPS = 8 };
 struct PostDesc { int ninj, nrec; InjOp inj[MAX_OPS]; RecOp rec[MAX_OPS]; };
 
+// woff: floats added to every wavefield pointer of the descriptors (0, or the distance to the other time-level set in ping-pong runs)
 __global__ void k_post(const Geom g, const PostDesc* __restrict__ descs, int it /*1-based*/, int rec_it /*1-based row to write*/,
-                       int nt, float dt, int flags /* bit0 inject, bit1 record */) {
+                       int nt, float dt, int flags /* bit0 inject, bit1 record */, long long woff) {
     const PostDesc& d = descs[blockIdx.x];
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
     const int ninj = (flags & 1) ? d.ninj : 0;
@@ -525,11 +540,11 @@ __global__ void k_post(const Geom g, const PostDesc* __restrict__ descs, int it 
             const long long c = op.row_cell[r];
             if (op.kind == 1) {
                 const float add = __fmul_rn(buf, op.coef[c]);        // pw = pw + (pv * dtK)
-                for (int t = 0; t < op.ntarget; t++) op.target[t][c] = __fadd_rn(op.target[t][c], add);
+                for (int t = 0; t < op.ntarget; t++) op.target[t][c + woff] = __fadd_rn(op.target[t][c + woff], add);
             } else {                                                 // pw = pw + (pv / av(rho) * dt), Float64 as in the reference
                 const long long off = op.axis == 0 ? 1 : (op.axis == 1 ? sy : sx);
                 const float s = __fadd_rn(op.coef[c - (g.h + 1) * off], op.coef[c - g.h * off]);     // @av_?i: integer nodes u-1-h, u-h
-                float* t = op.target[0];
+                float* t = op.target[0] + woff;
                 // Float64 as in the reference, every operation rounded on its own (nvcc would otherwise be free to contract the
                 // product and the sum into one fma, which the CPU path does not do)
                 t[c] = (float)__dadd_rn((double)t[c], __dmul_rn(__ddiv_rn((double)buf, __dmul_rn((double)s, 0.5)), (double)dt));
@@ -542,7 +557,7 @@ __global__ void k_post(const Geom g, const PostDesc* __restrict__ descs, int it 
         for (int ir = threadIdx.x; ir < op.nr; ir += blockDim.x) {
             float tmp = 0.f;                                         // mul!(rec, transpose(R), field)
             for (int e = op.colptr[ir]; e < op.colptr[ir + 1]; e++)
-                tmp = __fadd_rn(tmp, __fmul_rn(op.tap_val[e], op.field[op.tap_cell[e]]));
+                tmp = __fadd_rn(tmp, __fmul_rn(op.tap_val[e], op.field[op.tap_cell[e] + woff]));
             op.rec[(size_t)(rec_it - 1) + (size_t)nt * ir] = tmp;
         }
     }
@@ -588,8 +603,9 @@ __global__ void k_boundary(const Geom g, const BndArgs a) {
     if (k < F.k0 || k >= F.nk || j < F.j0 || j >= F.nj || i < F.i0 || i >= F.ni) return;
     float* field = F.f0 + (long long)b * a.wstride + uidx(g, k, j, i);
     float* store = a.stores[(b * a.nf + fi) * 3 + axis] + a.slot_off[axis] + si;
-    if (SAVE) *store = __fmul_rn(*field, -1.0f);     // rmul!(b, -1)
-    else      *field = *store;
+    if (SAVE == 2)  *store = *field;                       // plain copy: the pre-force values kept aside in ping-pong adjoint runs
+    else if (SAVE)  *store = __fmul_rn(*field, -1.0f);     // rmul!(b, -1)
+    else            *field = *store;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ __device__ __forceinline__ Vec2Idx vec2_index(const Geom& g) {
 // ------------------------------------------------------------------------------------------------
 // velocity kernel, 2-D
 // ------------------------------------------------------------------------------------------------
-template <int EL>
+template <int EL, int OOP = 0>      // OOP: out of place, reads a.v and writes a.v_o (StepArgs)
 __global__ void __launch_bounds__(128) k_vel2v(const Geom g, const StepArgs a) {
     const Vec2Idx q = vec2_index(g);
     if (!q.valid) return;
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128) k_vel2v(const Geom g, const StepArgs a) {
     const int nz = g.nz, nx = g.nx;
     if (!(i >= 2 && i <= nx - 2)) {
 #pragma unroll 1
-        for (int e = 0; e < VW; e++) if (k0 + e >= g.klo && k0 + e <= g.khi) vel_cell<2, EL>(g, a, k0 + e, 0, i, b);
+        for (int e = 0; e < VW; e++) if (k0 + e >= g.klo && k0 + e <= g.khi) vel_cell<2, EL, OOP>(g, a, k0 + e, 0, i, b);
         return;
     }
     const int kg0 = k0 + g.koff;
@@ -40,8 +40,8 @@ __global__ void __launch_bounds__(128) k_vel2v(const Geom g, const StepArgs a) {
     const bool more = k0 + VW < g.pz;
     const bool hxmin = g.pml & XMIN, hxmax = g.pml & XMAX;
 
-    float* vx = a.v[V_X] + c; float* vz = a.v[V_Z] + c;
-    F4 nvx = ld4(vx), nvz = ld4(vz);
+    float* vx = (OOP ? a.v_o[V_X] : a.v[V_X]) + c; float* vz = (OOP ? a.v_o[V_Z] : a.v[V_Z]) + c;       // written
+    F4 nvx = ld4(a.v[V_X] + c), nvz = ld4(a.v[V_Z] + c);
     const F4 bx = ldg4(a.c[C_BX] + c - w), bz = ldg4(a.c[C_BZ] + c - w);
     if (!EL) {
         const float* p = a.tau[T_XX] + c;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128) k_vel2v(const Geom g, const StepArgs a) {
 // ------------------------------------------------------------------------------------------------
 // stress kernel, 2-D
 // ------------------------------------------------------------------------------------------------
-template <int EL>
+template <int EL, int OOP = 0>      // OOP: out of place, reads a.tau and writes a.tau_o
 __global__ void __launch_bounds__(128) k_stress2v(const Geom g, const StepArgs a) {
     const Vec2Idx q = vec2_index(g);
     if (!q.valid) return;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) k_stress2v(const Geom g, const StepArgs a
     const int nz = g.nz, nx = g.nx;
     if (!(i >= 1 && i <= nx - 2)) {
 #pragma unroll 1
-        for (int e = 0; e < VW; e++) if (k0 + e >= g.klo && k0 + e <= g.khi) stress_cell<2, EL>(g, a, k0 + e, 0, i, b);
+        for (int e = 0; e < VW; e++) if (k0 + e >= g.klo && k0 + e <= g.khi) stress_cell<2, EL, OOP>(g, a, k0 + e, 0, i, b);
         return;
     }
     const int kg0 = k0 + g.koff;
@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(128) k_stress2v(const Geom g, const StepArgs a
     pml_open_z(m2, g, a.ps[2], 0, nz, k0, 0, i, b);
     const float vznext = z_next(vz, more);
     if (!EL) {
-        float* p = a.tau[T_XX] + c;
-        F4 pc = ld4(p);
+        float* p = (OOP ? a.tau_o[T_XX] : a.tau[T_XX]) + c;          // written
+        F4 pc = ld4(a.tau[T_XX] + c);
         const F4 K = ldg4(a.c[C_K] + c - w);
         F4 dxx = diff4(vxpx, cvx, g.dxI);           pml_apply(m0, a.ps[0], dxx);       // @d_xa(vx)
         F4 dzz = diff4_zp(cvz, vznext, g.dzI);      pml_apply_z(m2, a.ps[2], dzz);     // @d_za(vz)
@@ -142,8 +142,9 @@ __global__ void __launch_bounds__(128) k_stress2v(const Geom g, const StepArgs a
         return;
     }
     const bool fs = (g.freesurf & ZMIN) != 0;
-    float* txx = a.tau[T_XX] + c; float* tzz = a.tau[T_ZZ] + c; float* txz = a.tau[T_XZ] + c;
-    F4 xx = ld4(txx), zz = ld4(tzz), xz = ld4(txz);
+    float* txx = (OOP ? a.tau_o[T_XX] : a.tau[T_XX]) + c; float* tzz = (OOP ? a.tau_o[T_ZZ] : a.tau[T_ZZ]) + c;      // written
+    float* txz = (OOP ? a.tau_o[T_XZ] : a.tau[T_XZ]) + c;
+    F4 xx = ld4(a.tau[T_XX] + c), zz = ld4(a.tau[T_ZZ] + c), xz = ld4(a.tau[T_XZ] + c);
     const F4 M = ldg4(a.c[C_K] + c - w), L = ldg4(a.c[C_L] + c - w), mu = ldg4(a.c[C_MUXZ] + c - w);
     const F4 vzmx = ld4(vz - sx);
     Pml4 m5, m6;

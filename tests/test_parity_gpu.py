@@ -406,3 +406,45 @@ def test_engine_matches_the_stokes_solution(G, monkeypatch, tma):
     for rf, err in stokes_misfits(G, G.SeisForwExpt).items():
         print(f"engine vs Stokes solution (GPI_TMA3={tma}), :vz force recorded as :{rf}: normalised squared misfit {err:.3e}")
         assert err < 1e-3
+
+
+# --------------------------------------------------------------------------------------------------
+# GPI_PINGPONG=1: adjoint runs without save_tp!'s copy (the two wavefield sets alternate as time levels, out-of-place kernels)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("physics", ["acoustic", "elastic"])
+def test_pingpong_adjoint_equals_the_copy_path(G, O, monkeypatch, physics):
+    """The FWI gradient (forward_save + adjoint + imaging, 2-D, order 2) with the time levels ping-ponged between W and TP must be
+    bit-identical to the run that copies W -> TP every step (save_tp.jl:5-12) and to the oracle; nt is odd so that the run ends on
+    the other set (the handle swaps them), and the experiment is run twice to cover the swapped start.  The launch count proves the
+    ping-pong path ran: it replaces the copy by two more boundary launches per step and batch."""
+    from geophyinv_jl_b200.host import gallery
+    if physics == "acoustic":
+        kw, true = gallery.c4_fwi2d(nz=60, nx=90, nt=301, nss=3, nr=16, fq=10.0)
+        attrib = G.FdtdAcoustic
+    else:
+        kw, true = gallery.fwi2d_elastic(nt=301)
+        attrib = G.FdtdElastic
+    pt = O.OraclePFdtd(attrib(), **{**kw, "medium": true})
+    pt.update()
+    dobs = [d.copy() for d in pt.c.data[0]]
+    po = O.OraclePFdtd(attrib("forward_save"), **kw)
+    m = po.get_modelvector()
+    go = np.zeros_like(m)
+    G.gradient(go, m, dobs, po)
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("GPI_PINGPONG", flag)            # read by gpi_create
+        pg = G.PFdtd(attrib("forward_save"), **kw, shot_batch=2)
+        for rep in range(2):
+            g = np.zeros_like(m)
+            loss = G.gradient(g, m, dobs, pg)
+            res[flag, rep] = (g, loss, pg.last_launches)
+    nbatch = -(-len(kw["ageom"]) // 2)
+    nt = len(kw["tgrid"])
+    for rep in range(2):
+        g0, l0, n0 = res["0", rep]; g1, l1, n1 = res["1", rep]
+        assert np.array_equal(g0, g1) and l0 == l1, f"ping-pong differs from the copy path (run {rep})"
+        assert n1 - n0 == 2 * nt * nbatch, (n0, n1)
+        assert rel_l2(g1, go) <= GRAD_TOL
+    print(f"ping-pong adjoint ({physics}): gradient bit-identical to the copy path, rel-L2 vs oracle {rel_l2(res['1', 0][0], go):.1e}, "
+          f"launches {res['0', 0][2]:.0f} -> {res['1', 0][2]:.0f}")
