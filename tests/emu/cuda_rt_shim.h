@@ -104,16 +104,46 @@ template <typename F> static void launch(dim3 grid, dim3 block, F&& body) {
         }
     }
 }
-// kernels with __syncthreads: the threads of a block are host threads around a barrier, blocks one after the other
+// kernels with __syncthreads: the threads of a block are host threads around a barrier, blocks one after the other.  The host
+// threads live in a pool that is created once (a launch per time step would otherwise spawn 128 threads every time).
+struct Pool {
+    std::vector<std::thread> th;
+    pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    pthread_cond_t go = PTHREAD_COND_INITIALIZER, done = PTHREAD_COND_INITIALIZER;
+    unsigned long long gen = 0;  unsigned active = 0, pending = 0;
+    std::function<void(unsigned)> job;
+    void worker(unsigned id) {
+        unsigned long long seen = 0;
+        for (;;) {
+            pthread_mutex_lock(&mu);
+            while (gen == seen) pthread_cond_wait(&go, &mu);
+            seen = gen;
+            const bool mine = id < active;
+            pthread_mutex_unlock(&mu);
+            if (!mine) continue;
+            job(id);
+            pthread_mutex_lock(&mu);
+            if (--pending == 0) pthread_cond_signal(&done);
+            pthread_mutex_unlock(&mu);
+        }
+    }
+    void run(unsigned n, std::function<void(unsigned)> f) {
+        while (th.size() < n) { const unsigned id = (unsigned)th.size(); th.emplace_back([this, id] { worker(id); }); th.back().detach(); }
+        pthread_mutex_lock(&mu);
+        job = std::move(f); active = n; pending = n; gen++;
+        pthread_cond_broadcast(&go);
+        while (pending) pthread_cond_wait(&done, &mu);
+        pthread_mutex_unlock(&mu);
+    }
+};
+static Pool pool;
 template <typename F> static void launch_mt(dim3 grid, dim3 block, F&& body) {
     launches++;
     const unsigned nthreads = block.x * block.y * block.z;
     for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
         pthread_barrier_t bar;
         pthread_barrier_init(&bar, nullptr, nthreads);
-        std::vector<std::thread> pool;
-        pool.reserve(nthreads);
-        for (unsigned t = 0; t < nthreads; t++) pool.emplace_back([&, t] {
+        pool.run(nthreads, [&](unsigned t) {
             gridDim = grid; blockDim = block;
             blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
             threadIdx.x = t % block.x; threadIdx.y = (t / block.x) % block.y; threadIdx.z = t / (block.x * block.y);
@@ -121,7 +151,6 @@ template <typename F> static void launch_mt(dim3 grid, dim3 block, F&& body) {
             body();
             block_barrier = nullptr;
         });
-        for (auto& th : pool) th.join();
         pthread_barrier_destroy(&bar);
     }
 }
