@@ -124,6 +124,35 @@ __host__ __device__ inline size_t smem_bytes(int kind) {
 }
 
 // ---- PTX: mbarrier + TMA ---------------------------------------------------------------------------------------------
+#ifdef GPI_HOST_EMU
+// tests/emu (cuda_rt_shim.h): host forms of the primitives, so that the tile decomposition, the producer's box list and byte
+// accounting, the tile header and the consumers' shared-memory indexing run on the CPU.  A CTA is emulated serially (tile by
+// tile: producer, then the 128 consumer lanes), so the barriers have nothing to order; the 64-bit barrier word counts the
+// bytes still expected instead, and a consumer that finds it non-zero has caught a wrong expect_tx (a hang on the GPU).
+typedef uintptr_t sptr_t;
+struct EmuTensorMap { const float* base; unsigned long long dim[3]; unsigned box[3]; };       // what the emulated encoder stores in a CUtensorMap
+inline sptr_t s32(const void* p) { return (sptr_t)p; }
+inline void mbar_init(sptr_t bar, uint32_t) { *(long long*)bar = 0; }
+inline void mbar_expect_tx(sptr_t bar, uint32_t bytes) { *(long long*)bar += bytes; }
+inline void mbar_arrive(sptr_t) {}
+inline void mbar_wait(sptr_t, uint32_t) {}
+inline void mbar_check_complete(sptr_t bar) { if (*(long long*)bar != 0) { fprintf(stderr, "t3 emulation: %lld bytes of a stage never arrived / were never expected\n", *(long long*)bar); abort(); } }
+inline void tma_box(sptr_t dst, const void* tmap, int c0, int c1, int c2, sptr_t bar) {
+    const EmuTensorMap& m = *reinterpret_cast<const EmuTensorMap*>(tmap);
+    float* d = reinterpret_cast<float*>(dst);
+    for (unsigned z = 0; z < m.box[2]; z++) for (unsigned y = 0; y < m.box[1]; y++) for (unsigned x = 0; x < m.box[0]; x++) {
+        const long long k = (long long)c0 + x, j = (long long)c1 + y, i = (long long)c2 + z;
+        const bool in = k >= 0 && j >= 0 && i >= 0 && k < (long long)m.dim[0] && j < (long long)m.dim[1] && i < (long long)m.dim[2];
+        *d++ = in ? m.base[k + (long long)m.dim[0] * (j + (long long)m.dim[1] * i)] : 0.f;      // out-of-range coordinates read zeros
+    }
+    *(long long*)bar -= (long long)m.box[0] * m.box[1] * m.box[2] * 4;                            // complete_tx counts the whole box
+}
+inline F4 lds4(const float* p) { return *reinterpret_cast<const F4*>(p); }
+// z neighbours: the value the shuffle fetches from the adjacent lane is the staged float next to this lane's group
+inline float z_prev_s(unsigned, const F4&, const float* p, int, bool has) { return has ? p[-1] : 0.f; }
+inline float z_next_s(unsigned, const F4&, const float* p, int, bool has) { return has ? p[VW] : 0.f; }
+#else
+typedef uint32_t sptr_t;             // shared-window address
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
@@ -162,13 +191,21 @@ __device__ __forceinline__ float z_next_s(unsigned mask, const F4& c, const floa
     if (lane == 31) v = p[VW];
     return has ? v : 0.f;
 }
+#endif   // GPI_HOST_EMU
 
 // ------------------------------------------------------------------------------------------------
 // producer: one thread per CTA
 // ------------------------------------------------------------------------------------------------
+// The tile sequence of a CTA: t = blockIdx.x, blockIdx.x + gridDim.x, ... < ntiles, n = how many tiles came before (stage and
+// phase bookkeeping).  The CPU emulation calls producer / consumer once per tile and passes the range (t_first, t_step, t_end, n0).
+#ifdef GPI_HOST_EMU
+#define T3_TILE_LOOP(t, n) int n = n0; for (int t = t_first; t < t_end; t += t_step, n++)
+#else
+#define T3_TILE_LOOP(t, n) int n = 0; for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x, n++)
+#endif
 template <int KIND>
 __device__ __forceinline__ void producer(const Geom& g, const Sched& sc, const Maps* tm, float* stage0,
-                                         uint32_t full0, uint32_t empty0) {
+                                         sptr_t full0, sptr_t empty0, int t_first, int t_step, int t_end, int n0) {
     constexpr int NBOX = K<KIND>::NBOX, MAIN = K<KIND>::MAIN, SFLOATS = K<KIND>::SFLOATS;
     int main_bytes = 0;
 #pragma unroll
@@ -180,8 +217,7 @@ __device__ __forceinline__ void producer(const Geom& g, const Sched& sc, const M
 #pragma unroll
     for (int q = 0; q < 3; q++) { term_extent(g, KIND, 2, q, xs0[q], xlen[q]); term_extent(g, KIND, 1, q, ys0[q], ylen[q]); term_extent(g, KIND, 0, q, zs0[q], zlen[q]); }
     const int per_plane = sc.njb * sc.nzc;
-    int n = 0;
-    for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x, n++) {
+    T3_TILE_LOOP(t, n) {
         const int s = n % STAGES;
         const uint32_t use = n / STAGES;
         const int ip = t / per_plane, rem = t - ip * per_plane;
@@ -218,15 +254,15 @@ __device__ __forceinline__ void producer(const Geom& g, const Sched& sc, const M
         hdr[H_I] = i; hdr[H_J0] = j0; hdr[H_KC0] = kc0; hdr[H_ZLOAD] = zload ? 1 : 0;
 #pragma unroll
         for (int q = 0; q < 3; q++) { hdr[H_SX + q] = sx[q]; hdr[H_SY0 + q] = sy0[q]; hdr[H_YMASK + q] = ymask[q]; }
-        const uint32_t bar = full0 + 8 * s;
+        const sptr_t bar = full0 + 8 * s;
         mbar_expect_tx(bar, bytes);                 // release: the header is visible to whoever observes the phase
-        const uint32_t dst0 = s32(S);
+        const sptr_t dst0 = s32(S);
 #pragma unroll
         for (int b = 0; b < NBOX; b++) {
             const BoxSpec bs = box_spec(KIND, b);
             tma_box(dst0 + bs.off * 4, tm->m[b], kc0 - (bs.halo ? 4 : 0), j0 + bs.dj, i + bs.di, bar);
         }
-        const uint32_t dstp = dst0 + MAIN * 4;
+        const sptr_t dstp = dst0 + MAIN * 4;
 #pragma unroll
         for (int q = 0; q < 3; q++) {
             if (sx[q] >= 0) tma_box(dstp + (P_X + q * B4) * 4, tm->m[NBOX + q], kc0, j0, sx[q], bar);          // [k, j, s]
@@ -473,19 +509,11 @@ __device__ __forceinline__ void stress_tile(const Geom& g, const StepArgs& a, co
     st4(txz, xz); st4(txy, xy); st4(tyz, yz);
 }
 
+// z-CPML coefficient tables, re-indexed like the memory rows: zi < PZM/2 is the min slab (zi = k), the upper half
+// is the max slab from its 4-aligned start; identity (a = b = 0, kI = 1) where the k-indexed table has no entry
 template <int KIND>
-__global__ void __launch_bounds__(NTHREADS, T3_MINB) k_step3t(const Geom g, const StepArgs a, const Sched sc, const Maps* __restrict__ tm) {
-    constexpr int SFLOATS = K<KIND>::SFLOATS;
-    extern __shared__ __align__(128) unsigned char smem_dyn[];
-    unsigned char* smem_raw = smem_dyn + ((128 - (s32(smem_dyn) & 127)) & 127);      // boxes need 128-byte alignment
-    float* stage0 = reinterpret_cast<float*>(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * SFLOATS * 4);
-    const uint32_t full0 = s32(bars), empty0 = s32(bars + STAGES);
-    float* ZT = reinterpret_cast<float*>(bars + 2 * STAGES);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // z-CPML coefficient tables, re-indexed like the memory rows: zi < PZM/2 is the min slab (zi = k), the upper half
-    // is the max slab from its 4-aligned start; identity (a = b = 0, kI = 1) where the k-indexed table has no entry
-    for (int idx = threadIdx.x; idx < 9 * PZM; idx += NTHREADS) {
+__device__ __forceinline__ void fill_zt(const Geom& g, const StepArgs& a, float* ZT, int first, int step) {
+    for (int idx = first; idx < 9 * PZM; idx += step) {
         const int Q = idx / (3 * PZM), cc = (idx / PZM) % 3, zi = idx % PZM;
         int s0, len;
         term_extent(g, KIND, 0, Q, s0, len);
@@ -494,22 +522,20 @@ __global__ void __launch_bounds__(NTHREADS, T3_MINB) k_step3t(const Geom g, cons
         const float* tab = cc == 0 ? t.a : cc == 1 ? t.b : t.kI;
         ZT[idx] = (k >= 0 && k <= g.nz && tab) ? __ldg(tab + k) : (cc == 2 ? 1.f : 0.f);
     }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NCW); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (warp == NCW) {
-        if (lane == 0) producer<KIND>(g, sc, tm, stage0, full0, empty0);
-        return;
-    }
-    int n = 0;
-    for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x, n++) {
+}
+// one consumer lane: the same tile sequence as the producer (see there for the range arguments)
+template <int KIND>
+__device__ __forceinline__ void consumer(const Geom& g, const StepArgs& a, const Sched& sc, const float* stage0, const float* ZT,
+                                         sptr_t full0, sptr_t empty0, int warp, int lane, int t_first, int t_step, int t_end, int n0) {
+    constexpr int SFLOATS = K<KIND>::SFLOATS;
+    T3_TILE_LOOP(t, n) {
         const int s = n % STAGES;
         const uint32_t use = n / STAGES;
         const float* S = stage0 + (size_t)s * SFLOATS;
         mbar_wait(full0 + 8 * s, use & 1);
+#ifdef GPI_HOST_EMU
+        mbar_check_complete(full0 + 8 * s);
+#endif
         TileCtx q;
         q.ZT = ZT;
         open_tile<KIND>(q, g, a, S, warp, lane);
@@ -522,6 +548,56 @@ __global__ void __launch_bounds__(NTHREADS, T3_MINB) k_step3t(const Geom g, cons
         if (lane == 0) mbar_arrive(empty0 + 8 * s);
     }
 }
+
+#ifdef GPI_HOST_EMU
+// CPU emulation of one CTA (run by the launch's "thread 0" of each block; the other 159 return): shared memory is a heap block,
+// the tiles of the CTA are taken one after the other -- producer, then the 4 x 32 consumer lanes.
+template <int KIND>
+void k_step3t(const Geom g, const StepArgs a, const Sched sc, const Maps* tm) {
+    if (threadIdx.x != 0) return;
+    constexpr int SFLOATS = K<KIND>::SFLOATS;
+    const size_t nbytes = smem_bytes(KIND);
+    unsigned char* smem_raw = static_cast<unsigned char*>(aligned_alloc(128, (nbytes + 127) / 128 * 128));
+    memset(smem_raw, 0xff, nbytes);                       // shared memory starts as garbage (NaN patterns), not zeros
+    float* stage0 = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * SFLOATS * 4);
+    const sptr_t full0 = s32(bars), empty0 = s32(bars + STAGES);
+    float* ZT = reinterpret_cast<float*>(bars + 2 * STAGES);
+    fill_zt<KIND>(g, a, ZT, 0, 1);
+    for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NCW); }
+    int n = 0;
+    for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x, n++) {
+        producer<KIND>(g, sc, tm, stage0, full0, empty0, t, 1, t + 1, n);
+        for (int warp = 0; warp < NCW; warp++) for (int lane = 0; lane < 32; lane++)
+            consumer<KIND>(g, a, sc, stage0, ZT, full0, empty0, warp, lane, t, 1, t + 1, n);
+    }
+    free(smem_raw);
+}
+#else
+template <int KIND>
+__global__ void __launch_bounds__(NTHREADS, T3_MINB) k_step3t(const Geom g, const StepArgs a, const Sched sc, const Maps* __restrict__ tm) {
+    constexpr int SFLOATS = K<KIND>::SFLOATS;
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    unsigned char* smem_raw = smem_dyn + ((128 - (s32(smem_dyn) & 127)) & 127);      // boxes need 128-byte alignment
+    float* stage0 = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * SFLOATS * 4);
+    const sptr_t full0 = s32(bars), empty0 = s32(bars + STAGES);
+    float* ZT = reinterpret_cast<float*>(bars + 2 * STAGES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    fill_zt<KIND>(g, a, ZT, threadIdx.x, NTHREADS);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        if (lane == 0) producer<KIND>(g, sc, tm, stage0, full0, empty0, 0, 0, 0, 0);
+        return;
+    }
+    consumer<KIND>(g, a, sc, stage0, ZT, full0, empty0, warp, lane, 0, 0, 0, 0);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // shell: the rows / planes outside the fast region, scalar reference-order code.  grid.x = line (a row of one

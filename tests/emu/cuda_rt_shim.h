@@ -11,12 +11,15 @@
 //     emu::launch(grid, block, [&] { k(args); })  -- blocks in parallel over OpenMP threads (blocks of a launch are independent on the
 //     GPU as well), the threads of a block one after the other; kernels that use __syncthreads (k_post) run the threads of a block as
 //     real host threads around a barrier (emu::launch_mt);
-//   * the TMA-pipelined kernels (kernels3t.cuh: mbarrier / cp.async.bulk.tensor PTX) have no host form; cudaGetDriverEntryPoint
-//     fails here, the engine drops to its register-staged float4 kernels exactly as it does on a driver without tensor maps, and the
-//     t3 names engine.cu mentions are declared below as inert stand-ins.
+//   * the TMA-pipelined kernels (kernels3t.cuh) run through the host forms of their PTX primitives defined there under GPI_HOST_EMU:
+//     cudaGetDriverEntryPoint hands the engine an emulated cuTensorMapEncodeTiled (same argument checks as the driver's), a tensor
+//     copy is a box copy with zero fill, a CTA is a serial loop over its tiles (producer, then the 128 consumer lanes), and the
+//     barrier words count expected bytes so that a wrong expect_tx is caught.  What this leaves out is exactly what only the
+//     hardware can show: the asynchrony of the pipeline and the warp shuffles.
 #pragma once
 #define EMU_TLS thread_local
 #define EMU_HAVE_SYNCTHREADS 1
+#define GPI_EMU_T3 1
 #include <pthread.h>
 #include <cstdio>
 #include <cstdlib>
@@ -61,9 +64,8 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA runtime error"; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 148; return cudaSuccess; }
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
-static inline cudaError_t cudaGetDriverEntryPoint(const char*, void** fn, int, cudaDriverEntryPointQueryResult* q) {
-    *fn = nullptr; if (q) *q = cudaDriverEntryPointSymbolNotFound; return cudaErrorEmu;      // no tensor maps: the engine takes k_*3v
-}
+static inline unsigned __ballot_sync(unsigned, bool) { return 0xffffffffu; }      // only feeds shuffle masks, which the host forms ignore
+static inline void __syncwarp() {}
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = malloc(1); return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
@@ -74,7 +76,7 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cuda
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 
-// ---- driver API names of the tensor-map encoder (declared, never called) ---------------------------------------------------------
+// ---- driver API: the tensor-map encoder ------------------------------------------------------------------------------------------
 typedef unsigned long long cuuint64_t;
 typedef unsigned int cuuint32_t;
 typedef int CUresult;
@@ -85,6 +87,28 @@ enum CUtensorMapInterleave { CU_TENSOR_MAP_INTERLEAVE_NONE = 0 };
 enum CUtensorMapSwizzle { CU_TENSOR_MAP_SWIZZLE_NONE = 0 };
 enum CUtensorMapL2promotion { CU_TENSOR_MAP_L2_PROMOTION_L2_128B = 2 };
 enum CUtensorMapFloatOOBfill { CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = 0 };
+// what kernels3t.cuh's host tma_box reads back (gpi::t3::EmuTensorMap has the same layout)
+struct EmuTensorMapRaw { const float* base; unsigned long long dim[3]; unsigned box[3]; };
+static CUresult emu_cuTensorMapEncodeTiled(CUtensorMap* out, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* dims,
+                                           const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave,
+                                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+    // the driver's own requirements (CUDA driver API, cuTensorMapEncodeTiled): 16-byte aligned base, strides multiples of 16 bytes,
+    // box extents 1..256, inner box extent a multiple of 16 bytes, unit element strides here
+    if (!out || dt != CU_TENSOR_MAP_DATA_TYPE_FLOAT32 || rank != 3 || ((uintptr_t)base & 15)) return 1;
+    for (int q = 0; q < 3; q++) if (dims[q] == 0 || box[q] == 0 || box[q] > 256 || estr[q] != 1) return 1;
+    if ((box[0] * 4) % 16) return 1;
+    if (strides[0] % 16 || strides[1] % 16 || strides[0] != dims[0] * 4 || strides[1] != dims[0] * dims[1] * 4) return 1;
+    EmuTensorMapRaw m; m.base = (const float*)base;
+    for (int q = 0; q < 3; q++) { m.dim[q] = dims[q]; m.box[q] = box[q]; }
+    memset(out, 0, sizeof *out); memcpy(out, &m, sizeof m);
+    return CUDA_SUCCESS;
+}
+static inline cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, int, cudaDriverEntryPointQueryResult* q) {
+    const bool ok = strcmp(name, "cuTensorMapEncodeTiled") == 0;
+    *fn = ok ? (void*)&emu_cuTensorMapEncodeTiled : nullptr;
+    if (q) *q = ok ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
+    return ok ? cudaSuccess : cudaErrorEmu;
+}
 
 // ---- launches -------------------------------------------------------------------------------------------------------------------
 namespace emu {

@@ -6,9 +6,12 @@ GPI_LIB pointing at the emulated library.  Every one of them must hold bit for b
 
 What this covers that tests/test_emu_kernels.py does not: the host side of the engine (batching, descriptor tables, source / receiver
 row lists, boundary store slots, two-wavefield merged launches, the ping-pong time levels of GPI_PINGPONG=1, gradient stacking) and
-the kernels in their real launch geometry.  What it cannot cover: the TMA-pipelined kernels (PTX; the emulated runtime has no tensor
-maps, so the engine takes its register-staged kernels), NCCL, and anything about timing.  All 58 single-GPU parity tests pass under
-the emulation (37 min on 8 cores); the no-GPU suite runs the subset below.
+the kernels in their real launch geometry -- including the TMA-pipelined 3-D elastic kernels (kernels3t.cuh) through the host forms
+of their PTX primitives: the tile decomposition and the shell, the descriptors (an emulated cuTensorMapEncodeTiled with the driver's
+argument checks), the producer's box list and expect_tx byte accounting (a mismatch aborts instead of hanging), the tile header,
+the consumers' shared-memory indexing.  What it cannot cover: the asynchrony of that pipeline and its warp shuffles, NCCL, and
+anything about timing.  All 58 single-GPU parity tests pass under the emulation (37 min on 8 cores); the no-GPU suite runs the
+subset below.
 
 TEST INFRASTRUCTURE: the emulated library is built into a temporary directory, is never installed next to the package, and
 `engine.py` cannot pick it up by itself (it loads libgpifdtd.so or fails); `test_product_library_is_not_the_emulation` checks that.
@@ -29,6 +32,7 @@ SELECTION = [
     PARITY + "test_elastic2d_records[True]",
     PARITY + "test_elastic2d_stress_source",
     PARITY + "test_c3_elastic3d_reduced[True]",
+    PARITY + "test_elastic3d_partial_pml_faces[faces1]",        # TMA tiles forced (GPI_TMA3=2), CPML boxes on three faces
     PARITY + "test_elastic3d_partial_pml_faces[faces2]",
     PARITY + "test_dmod_matches_oracle",
     PARITY + "test_medium_padded_on_device",
