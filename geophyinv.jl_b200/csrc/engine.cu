@@ -599,6 +599,29 @@ __global__ void k_pad_replicate(const Geom g, const float* __restrict__ src, flo
     dst[uidx(g, kl + g.h, g.ny1 > 1 ? j + g.h : j, i + g.h)] = src[(long long)sz + (long long)mz * ((long long)sy + (long long)my * sx)];
 }
 
+// The same padding fused with the derived-parameter broadcasts of media.jl:103-130 (invK!, invlambda!, invmu!, rho!: one scalar
+// function per cell, Float32): the host hands over vp, (vs,) rho as they are and the independent parameters of the physics
+// (medium.jl:81-95) come out on the extended grid.  inv(x) is one(x) / x; 2 * abs2(vs) is a Float32 product.
+template <int EL>
+__global__ void k_pad_derive(const Geom g, const float* __restrict__ vp, const float* __restrict__ vs, const float* __restrict__ rho,
+                             float* __restrict__ m0 /* invK | invlambda */, float* __restrict__ m1 /* invmu */, float* __restrict__ mrho,
+                             int mz, int my, int mx, int lz, int ly, int lx) {
+    const int kl = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, i = blockIdx.z;
+    const int k = kl + g.koff;
+    if (kl >= g.pz || k >= g.nz) return;
+    const int sz = min(max(k - lz, 0), mz - 1), sy = min(max(j - ly, 0), my - 1), sx = min(max(i - lx, 0), mx - 1);
+    const long long s = (long long)sz + (long long)mz * ((long long)sy + (long long)my * sx);
+    const long long d = uidx(g, kl + g.h, g.ny1 > 1 ? j + g.h : j, i + g.h);
+    const float a = vp[s], r = rho[s];
+    if (!EL) m0[d] = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(a, a), r));                                  // inv(abs2(vp) * rho)
+    else {
+        const float b2 = __fmul_rn(vs[s], vs[s]);
+        m0[d] = __fdiv_rn(1.0f, __fmul_rn(__fsub_rn(__fmul_rn(a, a), __fmul_rn(b2, 2.0f)), r));       // inv((abs2(vp) - 2 * abs2(vs)) * rho)
+        m1[d] = __fdiv_rn(1.0f, __fmul_rn(b2, r));                                                    // inv(abs2(vs) * rho)
+    }
+    mrho[d] = r;
+}
+
 __global__ void k_negate_copy(float* __restrict__ dst, const float* __restrict__ src, long long n) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) dst[t] = __fmul_rn(src[t], -1.0f);
@@ -945,6 +968,34 @@ extern "C" int gpi_set_medium_interior(gpi_handle* h, int p, const float* a, con
     k_pad_replicate<<<grd, blk, 0, h->stream>>>(g, h->dscratch, h->mod[p], mz, my, mx, lz, ly, lx);
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(h->stream));     // `a` is borrowed for the duration of the call only
+    return 0;
+}
+// update!(pa, medium) in one call: vp, (vs,) rho of the UN-extended medium -> every independent parameter on the extended grid
+// (k_pad_derive).  Replaces one Medium getter + gpi_set_medium_interior per parameter; same H2D bytes, no host-side arithmetic.
+extern "C" int gpi_set_medium_fields(gpi_handle* h, const float* vp, const float* vs, const float* rho, const int32_t n_in[3], const int32_t lo[3]) {
+    GUARD(h);
+    if (!vp || !rho || !n_in || !lo || (h->el && !vs)) FAIL(h, "null medium array (an elastic medium needs vp, vs and rho)");
+    const Geom& g = h->g;
+    const int mz = n_in[0], my = h->nd == 3 ? n_in[1] : 1, mx = n_in[2];
+    const int lz = lo[0], ly = h->nd == 3 ? lo[1] : 0, lx = lo[2];
+    if (mz < 1 || my < 1 || mx < 1 || lz < 0 || ly < 0 || lx < 0 || mz + lz > g.nz || my + ly > g.ny || mx + lx > g.nx)
+        FAIL(h, "interior medium [%d,%d,%d] + padding [%d,%d,%d] does not fit the extended grid [%d,%d,%d]", mz, my, mx, lz, ly, lx, g.nz, g.ny, g.nx);
+    const size_t nf = (size_t)mz * my * mx, need = 3 * nf;
+    if (h->dscratch_floats < need) {
+        cudaFree(h->dscratch);
+        h->dscratch = nullptr; h->dscratch_floats = 0;
+        CU(h, cudaMalloc((void**)&h->dscratch, need * sizeof(float)));
+        h->dscratch_floats = need;
+    }
+    float* dvp = h->dscratch; float* dvs = h->dscratch + nf; float* drho = h->dscratch + 2 * nf;
+    CU(h, cudaMemcpyAsync(dvp, vp, nf * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (h->el) CU(h, cudaMemcpyAsync(dvs, vs, nf * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(drho, rho, nf * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    dim3 blk(128), grd((g.pz + 127) / 128, g.ny, g.nx);
+    if (h->el) k_pad_derive<1><<<grd, blk, 0, h->stream>>>(g, dvp, dvs, drho, h->mod[GPI_INVLAMBDA], h->mod[GPI_INVMU], h->mod[GPI_RHO], mz, my, mx, lz, ly, lx);
+    else       k_pad_derive<0><<<grd, blk, 0, h->stream>>>(g, dvp, nullptr, drho, h->mod[GPI_INVK], nullptr, h->mod[GPI_RHO], mz, my, mx, lz, ly, lx);
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));     // the host arrays are borrowed for the duration of the call only
     return 0;
 }
 extern "C" int gpi_slab_range(gpi_handle* h, int32_t* k_begin, int32_t* k_end) {

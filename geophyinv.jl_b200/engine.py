@@ -62,7 +62,7 @@ def face_mask(faces) -> int:
 
 
 EXPORTS = [
-    "gpi_create", "gpi_destroy", "gpi_last_error", "gpi_abi_version", "gpi_set_medium", "gpi_set_medium_rows", "gpi_set_medium_interior", "gpi_get_medium", "gpi_slab_range",
+    "gpi_create", "gpi_destroy", "gpi_last_error", "gpi_abi_version", "gpi_set_medium", "gpi_set_medium_rows", "gpi_set_medium_interior", "gpi_set_medium_fields", "gpi_get_medium", "gpi_slab_range",
     "gpi_update_dmod", "gpi_set_medium_pert", "gpi_update_born", "gpi_set_pml", "gpi_set_sparse", "gpi_set_wavelets", "gpi_run", "gpi_get_records",
     "gpi_get_gradient", "gpi_get_snap", "gpi_set_snap_steps", "gpi_get_field", "gpi_set_field", "gpi_reset",
     "gpi_nccl_unique_id", "gpi_nccl_init", "gpi_allreduce_gradients", "gpi_records_device_ptr",
@@ -93,6 +93,7 @@ def load_library(path: str = LIB_PATH):
         "gpi_get_medium": ([vp, C.c_int, fp], C.c_int),
         "gpi_set_medium_rows": ([vp, C.c_int, fp, C.c_int, C.c_int], C.c_int),
         "gpi_set_medium_interior": ([vp, C.c_int, fp, ip, ip], C.c_int),
+        "gpi_set_medium_fields": ([vp, fp, fp, fp, ip, ip], C.c_int),
         "gpi_slab_range": ([vp, ip, ip], C.c_int),
         "gpi_update_dmod": ([vp], C.c_int),
         "gpi_set_medium_pert": ([vp, C.c_int, fp], C.c_int),
@@ -192,6 +193,16 @@ class Engine:
         lo3 = tuple(lo) if len(lo) == 3 else (lo[0], 0, lo[1])
         flat = a.reshape(-1, order="F") if (a.dtype == np.float32 and a.flags.f_contiguous) else _f32(a)
         self._ck(self.lib.gpi_set_medium_interior(self.h, PARAM[name], _fp(flat), (C.c_int32 * 3)(*shp), (C.c_int32 * 3)(*lo3)))
+
+    def set_medium_fields(self, vp, vs, rho, lo):
+        """`update!(pa, medium)` in one call: the un-extended vp, vs (None for acoustic media), rho; the derived-parameter
+        broadcasts (media.jl:103-130) and the replicate padding run on the device."""
+        flat = lambda a: None if a is None else (a.reshape(-1, order="F") if (a.dtype == np.float32 and a.flags.f_contiguous) else _f32(a))
+        vp = np.asarray(vp)
+        shp = vp.shape if vp.ndim == 3 else (vp.shape[0], 1, vp.shape[1])
+        lo3 = tuple(lo) if len(lo) == 3 else (lo[0], 0, lo[1])
+        a, b, r = flat(vp), flat(None if vs is None else np.asarray(vs)), flat(np.asarray(rho))
+        self._ck(self.lib.gpi_set_medium_fields(self.h, _fp(a), None if b is None else _fp(b), _fp(r), (C.c_int32 * 3)(*shp), (C.c_int32 * 3)(*lo3)))
 
     def set_medium_rows(self, name: str, rows, k_first: int):
         """rows: [nk, (ny,) nx] = global rows k_first .. k_first+nk-1 of the extended medium array."""

@@ -90,24 +90,6 @@ class Medium:
             np.copyto(self.vs, other.vs)
         return self
 
-    def derived_into(self, name: str, out: np.ndarray, tmp: np.ndarray) -> np.ndarray:
-        """`self[name]` for the engine's independent parameters, evaluated into preallocated Float32 buffers
-        with exactly the operations (and order) of `__getitem__`, so the values are bit-identical."""
-        vp, rho, vs = self.vp, self.rho, self.vs
-        if name == "rho":
-            return rho
-        if name == "invK" and not self.elastic or name == "invlambda" and not self.elastic:
-            np.multiply(vp, vp, out=out); np.multiply(out, rho, out=out)                       # K = vp*vp*rho
-        elif name == "invmu":
-            np.multiply(vs, vs, out=out); np.multiply(out, rho, out=out)                       # mu = vs*vs*rho
-        elif name == "invlambda":
-            np.multiply(vp, vp, out=out); np.multiply(vs, vs, out=tmp); np.multiply(tmp, F32(2), out=tmp)
-            np.subtract(out, tmp, out=out); np.multiply(out, rho, out=out)                     # (vp*vp - 2*(vs*vs))*rho
-        else:
-            raise KeyError(name)
-        np.divide(F32(1), out, out=out)
-        return out
-
 
 def _face_flags(faces, ndims):
     names = dim_names(ndims)

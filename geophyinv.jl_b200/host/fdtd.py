@@ -242,10 +242,8 @@ class PFdtd:
             c.medium.copy_from(medium)                                                 # copyto!(pac.medium, medium)
         c._exmedium = c._mod = None                                                    # padarray! happens on the device
         lo, _ = pad_widths(c.medium.ndims, c.npml, c.pml_faces)
-        if getattr(self, "_dbuf", None) is None or self._dbuf[0].shape != c.medium.vp.shape:
-            self._dbuf = [np.empty(c.medium.vp.shape, F32, order="F") for _ in range(2)]
-        for name in c.mparams:                                                         # copyto!(mod[name], exmedium, name)
-            self.engine.set_medium_interior(name, c.medium.derived_into(name, self._dbuf[0], self._dbuf[1]), lo)
+        # copyto!(mod[name], exmedium, name) for every name: the getters (media.jl:103-130) are per-cell broadcasts, run on the device
+        self.engine.set_medium_fields(c.medium.vp, c.medium.vs, c.medium.rho, lo)
         self.engine.update_dmod()
 
     # ---------------------------------------------------------------------------------------------

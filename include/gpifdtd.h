@@ -141,6 +141,10 @@ int  gpi_set_medium_rows(gpi_handle* h, int param_id, const float* rows, int k_f
  * replicate padding of padarray! (media.jl:260-275) runs on the device; lo[q] = cells of padding on the
  * min face of axis q (npml on PML faces, else 0), n_in = (mz, my, mx) (my ignored in 2-D) */
 int  gpi_set_medium_interior(gpi_handle* h, int param_id, const float* a, const int32_t n_in[3], const int32_t lo[3]);
+/* update!(pa, medium) in one call: vp, vs (NULL for acoustic media), rho of the UN-extended medium, each [mz,(my),mx]; the derived-
+ * parameter broadcasts of media.jl:103-130 (invK | invlambda, invmu, rho: Float32, inv(x) = 1/x) and the replicate padding run on the
+ * device and fill every independent parameter of the physics (medium.jl:81-95).  Same n_in / lo as gpi_set_medium_interior. */
+int  gpi_set_medium_fields(gpi_handle* h, const float* vp, const float* vs, const float* rho, const int32_t n_in[3], const int32_t lo[3]);
 int  gpi_get_medium(gpi_handle* h, int param_id, float* out);
 int  gpi_update_dmod(gpi_handle* h);
 /* FD-Born (2-D acoustic): replaces copyto!(pac.δmod[name], exmedium_pert) followed by δmod .-= mod of update!(pac, medium, medium_pert)

@@ -75,10 +75,18 @@ function update_medium!(e::Engine, pac)
         lo3[slot] = Symbol(d, :min) in pac.pml_faces ? _fd_npextend : 0
         n3[slot] = length(pac.medium.grid[q])
     end
-    for name in names(pac.mod)[1]
-        a = Array{Float32}(pac.medium[name])                         # [mz,(my),mx], no padding
-        check(e, ccall((:gpi_set_medium_interior, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Ptr{Int32}, Ptr{Int32}),
-            e.h, PARAMS[name], a, n3, lo3))
+    if Set(names(pac.mod)[1]) in (Set([:invK, :rho]), Set([:invlambda, :invmu, :rho]))
+        # the stock parameterisations: vp, (vs,) rho as they are; the getters of media.jl:103-130 are broadcast on the device
+        m = pac.medium
+        vs = hasproperty(m, :vs) ? Array{Float32}(m.vs.m) : Ptr{Float32}(C_NULL)
+        check(e, ccall((:gpi_set_medium_fields, LIB), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}, Ptr{Int32}),
+            e.h, Array{Float32}(m.vp.m), vs, Array{Float32}(m.rho.m), n3, lo3))
+    else
+        for name in names(pac.mod)[1]
+            a = Array{Float32}(pac.medium[name])                         # [mz,(my),mx], no padding
+            check(e, ccall((:gpi_set_medium_interior, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Ptr{Int32}, Ptr{Int32}),
+                e.h, PARAMS[name], a, n3, lo3))
+        end
     end
     check(e, ccall((:gpi_update_dmod, LIB), Cint, (Ptr{Cvoid},), e.h))   # update_dmod! + store_invav*! (medium.jl:143-221)
 end

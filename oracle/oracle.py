@@ -99,6 +99,19 @@ class OracleEngine:
         idx = [np.clip(np.arange(-l, nn - l), 0, m - 1) for l, nn, m in zip(lo, n, a.shape)]
         self.set_medium(name, a[np.ix_(*idx)])
 
+    def set_medium_fields(self, vp, vs, rho, lo):
+        """Host-side restatement of the derived-parameter broadcasts (media.jl:103-130: invK / invlambda / invmu, Float32,
+        inv(x) = 1/x) -- the independent check of the engine's device-side k_pad_derive."""
+        f = np.float32
+        vp, rho = np.asarray(vp, f), np.asarray(rho, f)
+        if vs is None:
+            self.set_medium_interior("invK", f(1) / (vp * vp * rho), lo)
+        else:
+            vs = np.asarray(vs, f)
+            self.set_medium_interior("invlambda", f(1) / ((vp * vp - f(2) * (vs * vs)) * rho), lo)
+            self.set_medium_interior("invmu", f(1) / (vs * vs * rho), lo)
+        self.set_medium_interior("rho", rho, lo)
+
     def get_medium(self, name):
         shp = self.field_shape("p" if self.cfg.physics == E.ACOUSTIC else "tauxx")
         out = np.empty(int(np.prod(shp)), self.dtype)

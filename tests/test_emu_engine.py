@@ -1,6 +1,6 @@
 """The whole C-ABI library on the CPU: engine.cu -- handle life cycle, uploads and layout conversion, the time loop of gpi_run, every
 kernel launch -- compiled as host C++ behind a stand-in for the CUDA runtime (tests/emu/cuda_rt_shim.h, tests/emu/make_emu_engine.py:
-three textual substitutions, launches become loops over blocks and threads) and driven through the SAME ctypes binding and the SAME
+two textual substitutions, launches become loops over blocks and threads) and driven through the SAME ctypes binding and the SAME
 parity tests the B200 runs (`-m gpu` tests of tests/test_parity_gpu.py, tests/test_order4.py, ...), in a child pytest with
 GPI_LIB pointing at the emulated library.  Every one of them must hold bit for bit against the oracle without a GPU.
 
@@ -54,7 +54,7 @@ def emu_lib(tmp_path_factory):
 
 
 def test_launch_rewriting_covers_every_launch():
-    """Every `<<<...>>>` of engine.cu becomes an emu::launch; nothing else of the file changes but the three include lines."""
+    """Every `<<<...>>>` of engine.cu becomes an emu::launch; nothing else of the file changes but the include lines."""
     import make_emu_engine
     with open(os.path.join(ROOT, "geophyinv.jl_b200", "csrc", "engine.cu")) as f:
         src = f.read()
