@@ -273,23 +273,28 @@ def get_source(w: np.ndarray, field: str, src_type: int) -> np.ndarray:
     raise TypeError(f"no method get_source for src_type {src_type}")
 
 
-def findfreq(x: np.ndarray, tgrid: StepRange, attrib: str = "peak", threshold: float = -50.0) -> float:
-    """src/Utils/freq.jl:28-57"""
+def findfreq_all(x: np.ndarray, tgrid: StepRange, threshold: float = -50.0):
+    """(min, max, peak) of src/Utils/freq.jl:28-57 from ONE spectrum (the reference transforms the wavelets once per attribute)."""
     x = np.asarray(x, np.float64)
     cx = np.fft.rfft(x, axis=0)
     fgrid = np.fft.rfftfreq(len(tgrid), tgrid.step)
     ax = np.abs(cx) ** 2
     if ax.max() == 0.0:
-        return 0.0
+        return 0.0, 0.0, 0.0
     ax = 10.0 * np.log10(np.maximum(ax / ax.max(), 1e-300))
-    if attrib == "peak":
-        ii = np.unravel_index(np.argmax(ax.T), ax.T.shape)[::-1][0] if ax.ndim == 2 else int(np.argmax(ax))
-        return float(fgrid[ii])
-    rows = np.nonzero((ax >= threshold).any(axis=1))[0] if ax.ndim == 2 else np.nonzero(ax >= threshold)[0]
-    if attrib == "max":   # findlast in column-major order
+    if ax.ndim == 2:
+        ipeak = np.unravel_index(np.argmax(ax.T), ax.T.shape)[::-1][0]
         cols = np.nonzero(ax >= threshold)
-        order = np.lexsort((cols[0], cols[1])) if ax.ndim == 2 else None
-        return float(fgrid[cols[0][order[-1]]]) if ax.ndim == 2 else float(fgrid[rows[-1]])
-    cols = np.nonzero(ax >= threshold)
-    order = np.lexsort((cols[0], cols[1])) if ax.ndim == 2 else None
-    return float(fgrid[cols[0][order[0]]]) if ax.ndim == 2 else float(fgrid[rows[0]])
+        order = np.lexsort((cols[0], cols[1]))          # findfirst / findlast run in column-major order
+        ifirst, ilast = cols[0][order[0]], cols[0][order[-1]]
+    else:
+        ipeak = int(np.argmax(ax))
+        rows = np.nonzero(ax >= threshold)[0]
+        ifirst, ilast = rows[0], rows[-1]
+    return float(fgrid[ifirst]), float(fgrid[ilast]), float(fgrid[ipeak])
+
+
+def findfreq(x: np.ndarray, tgrid: StepRange, attrib: str = "peak", threshold: float = -50.0) -> float:
+    """src/Utils/freq.jl:28-57"""
+    fmin, fmax, fpeak = findfreq_all(x, tgrid, threshold)
+    return {"min": fmin, "max": fmax, "peak": fpeak}[attrib]

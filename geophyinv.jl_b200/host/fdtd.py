@@ -21,7 +21,7 @@ import numpy as np
 
 from .. import engine as E
 from .cpml import pml_coefficients
-from .data import (AGeomss, Medium, Recs, Srcs, findfreq, get_adjoint_ageom, get_source, make_recs,
+from .data import (AGeomss, Medium, Recs, Srcs, findfreq, findfreq_all, get_adjoint_ageom, get_source, make_recs,
                    pad_widths, padarray, padmgrid)
 from .grids import NBOUND, NPML, ORDER, StepRange, dfields_of, dim_names, field_shape, npml_of, wavefields_of
 from .proj import get_proj_matrix
@@ -343,10 +343,14 @@ class PFdtd:
                     w[: len(s.grid), :] = s.d[sf][:nt, :]
                     w = get_source(w, sf, src_types[ipw])
                     self.engine.set_wavelets(ipw, issp, sf, w)
-                    if w.size and float(np.abs(w).max()) > 1e-8:                # !all(isapprox.(w, 0)) with numpy's atol, one pass
-                        freqmax = min(findfreq(w, s.grid, "max"), freqmax)
-                        freqmin = max(findfreq(w, s.grid, "min"), freqmin)
-                        peaks.append(findfreq(w, s.grid, "peak"))
+                    # frequency bounds (source.jl:204-216): the reference evaluates them for every pw but keeps those of pw 1 only
+                    # (source.jl:229), so the spectra of the other wavefields' wavelets (the adjoint sources: nt x nr per
+                    # supersource and gradient) are not computed here; one spectrum serves min, max and peak
+                    if ipw == 0 and w.size and float(np.abs(w).max()) > 1e-8:   # !all(isapprox.(w, 0)) with numpy's atol, one pass
+                        fmin, fmax, fpeak = findfreq_all(w, s.grid)
+                        freqmax = min(fmax, freqmax)
+                        freqmin = max(fmin, freqmin)
+                        peaks.append(fpeak)
                 if peaks:
                     freqpeaks.append(float(np.mean(peaks)))
             # source fields may have changed => rebuild the spray matrices (source.jl:225)
@@ -518,7 +522,8 @@ def l2_lossvalue(dobs, data) -> float:
     tot = 0.0
     for a, b in zip(dobs, data):
         for f in a.fields:
-            tot += float(np.sum((a.d[f].astype(np.float64) - b.d[f].astype(np.float64)) ** 2))
+            d = np.subtract(a.d[f], b.d[f], dtype=np.float64)           # exact in Float64; no Float64 copies of the records
+            tot += float(np.sum(np.square(d, out=d)))
     return tot
 
 
