@@ -269,7 +269,8 @@ def run_ours(args):
     # ---- end to end through the host API with host buffers ----------------------------------------
     medium = kw["medium"]
     nmod = len(c.mparams)
-    h2d = int(nmod * np.prod(n_ex) * 4)
+    # update!(pa, medium) copies the UN-extended vp, (vs,) rho (gpi_set_medium_fields: derived parameters and padding on the device)
+    h2d = int(nmod * np.prod(medium.vp.shape) * 4)
     d2h = int(sum(nt * c.ageom[0][iss].nr * 4 * len(c.rfields) for iss in pa.local))
     for _ in range(1):
         pa.update_medium(medium); pa.update()

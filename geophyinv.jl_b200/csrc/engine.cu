@@ -160,7 +160,7 @@ struct gpi_handle {
     std::vector<int32_t> itsnaps;
     PostDesc *post_v = nullptr, *post_s = nullptr, *h_post_v = nullptr, *h_post_s = nullptr;
     float** bnd_table = nullptr;        // boundary stores of the resident batch, [b][field][axis]
-    // GPI_PINGPONG=1 (2-D, order 2, adjoint runs): W and TP alternate as the time levels instead of save_tp!'s copy; the forced
+    // GPI_PINGPONG=1 (order 2, adjoint runs; float4 kernel families): W and TP alternate as the time levels instead of save_tp!'s copy; the forced
     // boundary planes of the level that stays behind get their pre-force values back from `stash` ([b][field][axis], one slot)
     bool pingpong = false;  float* stash = nullptr;  float** stash_table = nullptr;
     float* stage = nullptr;  size_t stage_floats = 0;       // pinned host staging
@@ -174,7 +174,7 @@ struct gpi_handle {
     bool tma3 = true;  int num_sms = 148;  int tma3_ctas = 0;  bool tma3_force = false;   // GPI_TMA3=2: TMA kernels whatever the tile utilisation
     int shell_mode = 1;                                 // GPI_SHELL=0: shell kernel serialised behind the tile kernel (diagnostic)
     bool o4vec = true;                                  // order-4 kernels with four z cells per thread (kernels4v.cuh); GPI_O4VEC=0 selects the scalar ones
-    struct TmaSet { const float* key = nullptr; t3::Maps* d[2] = {nullptr, nullptr}; } tmaps[2];   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
+    struct TmaSet { const float* key = nullptr; t3::Maps* d[2] = {nullptr, nullptr}; } tmaps[2];  int tmap_victim = 0;   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
     void* encode_tiled = nullptr;                                            // cuTensorMapEncodeTiled (driver entry point)   // 3-D elastic: TMA-pipelined persistent kernels (kernels3t.cuh); GPI_TMA3=0 selects k_*3v
     bool vec2 = true;                                   // 2-D: float4-per-thread kernels (kernels2v.cuh); GPI_SCALAR2D=1 selects the scalar ones
     int blkv = GPI_VEC_THREADS;  bool vec3 = true;      // 3-D: float4-per-thread kernels (kernels3d.cuh); GPI_SCALAR3D=1 selects the scalar ones
@@ -362,7 +362,7 @@ int launch_step3t(gpi_handle* h, const StepArgs& a) {
     gpi_handle::TmaSet* set = nullptr;
     for (auto& ts : h->tmaps) if (ts.key == a.v[0]) set = &ts;
     if (!set) {
-        set = h->tmaps[0].key ? &h->tmaps[1] : &h->tmaps[0];
+        set = &h->tmaps[h->tmap_victim]; h->tmap_victim ^= 1;      // two sets (pw 1, pw 2), replaced in turn
         if (build_tmaps(h, a, 0, &set->d[0]) || build_tmaps(h, a, 1, &set->d[1])) return 1;
         set->key = a.v[0];
     }
@@ -413,12 +413,18 @@ void launch_step_kernels3v(gpi_handle* h, const StepArgs& a, bool vel, int nbatc
     // The TMA tiles are 128 z cells wide: a narrow z-slab window (4 or 8 slabs of C5) would leave most lanes of its
     // last chunk idle, while the register-staged kernels linearise (z, y) and waste nothing -- they take over below
     // 75 % tile utilisation (C3: 339 of 384 = 0.88 -> TMA; C5 on 4 GPUs: 150 of 256 = 0.59 -> k_*3v).
-    if (EL && nbatch == 1 && tma3_eligible(h)) {
+    const bool oop = vel ? a.v_o[V_X] != nullptr : a.tau_o[T_XX] != nullptr;       // ping-pong adjoint runs: the register-staged kernels
+    if (EL && nbatch == 1 && !oop && tma3_eligible(h)) {
         if ((vel ? launch_step3t<0>(h, a) : launch_step3t<1>(h, a)) == 0) return;
         h->tma3 = false;                        // descriptor creation failed: fall back to the register-staged kernels
     }
     const int ngroups = vec3_threads(g.pz, g.ny1);
     dim3 blk(h->blkv), grd((ngroups + h->blkv - 1) / h->blkv, g.nx1, nbatch);
+    if (oop) {
+        if (vel) k_vel3v<EL, 1><<<grd, blk, 0, h->stream>>>(g, a);
+        else     k_stress3v<EL, 1><<<grd, blk, 0, h->stream>>>(g, a);
+        return;
+    }
     if (vel) k_vel3v<EL><<<grd, blk, 0, h->stream>>>(g, a);
     else     k_stress3v<EL><<<grd, blk, 0, h->stream>>>(g, a);
 }
@@ -1354,7 +1360,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     if (mode == GPI_MODE_ADJOINT && !h->c.store_boundary) FAIL(h, "adjoint needs the boundary store of a forward_save run");
     const bool grad = mode == GPI_MODE_ADJOINT && (activepw & 2) && h->npw == 2;
     // GPI_PINGPONG=1: the two wavefield sets alternate as "this step" / "previous step" (what save_tp! copies, save_tp.jl:5-12)
-    const bool pp = h->pingpong && mode == GPI_MODE_ADJOINT && h->TP && h->nd == 2 && h->c.order == 2 && h->vec2 && !born && !h->slab;
+    const bool pp = h->pingpong && mode == GPI_MODE_ADJOINT && h->TP && h->c.order == 2 && (h->nd == 2 ? h->vec2 : h->vec3) && !born && !h->slab;
     if (pp && ensure_stash(h)) return 1;
     if (grad && !h->gshot) FAIL(h, "gradient imaging needs an experiment built with npw = 2");
     if (unshifted && h->el) FAIL(h, "the exact-transpose rho imaging is defined for acoustic media");

@@ -271,7 +271,7 @@ __device__ __forceinline__ Vec3Idx vec3_index(const Geom& g) {
 // ------------------------------------------------------------------------------------------------
 // velocity kernel, 3-D (see vel_cell for the reference citations and the CPML term order)
 // ------------------------------------------------------------------------------------------------
-template <int EL>
+template <int EL, int OOP = 0>      // OOP: out of place, reads a.v and writes a.v_o (ping-pong adjoint runs)
 __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(const Geom g, const StepArgs a) {
     const Vec3Idx q = vec3_index(g);
     const int k0 = q.k0, j = q.j, i = q.i, b = q.b;
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
     if (!q.valid) return;
     if (!fast) {
 #pragma unroll 1
-        for (int e = 0; e < VW; e++) if (k0 + e >= g.klo && k0 + e <= g.khi) vel_cell<3, EL>(g, a, k0 + e, j, i, b);
+        for (int e = 0; e < VW; e++) if (k0 + e >= g.klo && k0 + e <= g.khi) vel_cell<3, EL, OOP>(g, a, k0 + e, j, i, b);
         return;
     }
     const int kg0 = k0 + g.koff;                 // global z index of element 0
@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
     const bool hxmin = g.pml & XMIN, hxmax = g.pml & XMAX, hymin = g.pml & YMIN, hymax = g.pml & YMAX;
 
     float* vx = a.v[V_X] + c; float* vy = a.v[V_Y] + c; float* vz = a.v[V_Z] + c;
+    float* ovx = OOP ? a.v_o[V_X] + c : vx; float* ovy = OOP ? a.v_o[V_Y] + c : vy; float* ovz = OOP ? a.v_o[V_Z] + c : vz;     // written
     pf(vx); pf(vy); pf(vz); pf(a.c[C_BX] + c - w); pf(a.c[C_BY] + c - w); pf(a.c[C_BZ] + c - w);
     if (GPI_PF_AHEAD > 0 && i + GPI_PF_AHEAD <= nx - 2) {
         const long long o = GPI_PF_AHEAD * sx;
@@ -375,17 +376,17 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
     const bool head = kg0 == 0, tail = kg0 + VW - 1 >= nz - 1;
     if (head && (R & ZMIN)) { nvx.v[0] = 0.f; nvy.v[0] = 0.f; nvz.v[0] = -nvz.v[1]; }
     if (!tail) {
-        st4(vx, nvx); st4(vy, nvy); st4(vz, nvz);
+        st4(ovx, nvx); st4(ovy, nvy); st4(ovz, nvz);
     } else {
 #pragma unroll
         for (int e = 0; e < VW; e++) {
             const int k = kg0 + e; const bool own = (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo);
             if (own && k <= nz - 1) {
                 const bool zero = (R & ZMAX) && k == nz - 1;
-                vx[e] = zero ? 0.f : nvx.v[e];
-                vy[e] = zero ? 0.f : nvy.v[e];
-                vz[e] = nvz.v[e];
-                if ((R & ZMAX) && k == nz - 1) vz[e + 1] = -nvz.v[e];       // vz[nz+1] = -vz[nz]
+                ovx[e] = zero ? 0.f : nvx.v[e];
+                ovy[e] = zero ? 0.f : nvy.v[e];
+                ovz[e] = nvz.v[e];
+                if ((R & ZMAX) && k == nz - 1) ovz[e + 1] = -nvz.v[e];      // vz[nz+1] = -vz[nz]
             }
         }
     }
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_vel3v(co
 // ------------------------------------------------------------------------------------------------
 // stress kernel, 3-D (see stress_cell for the reference citations and the CPML term order)
 // ------------------------------------------------------------------------------------------------
-template <int EL>
+template <int EL, int OOP = 0>      // OOP: out of place, reads a.tau and writes a.tau_o
 __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v(const Geom g, const StepArgs a) {
     const Vec3Idx q = vec3_index(g);
     const int k0 = q.k0, j = q.j, i = q.i, b = q.b;
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
     if (!q.valid) return;
     if (!fast) {
 #pragma unroll 1
-        for (int e = 0; e < VW; e++) if (k0 + e >= g.klo && k0 + e <= g.khi) stress_cell<3, EL>(g, a, k0 + e, j, i, b);
+        for (int e = 0; e < VW; e++) if (k0 + e >= g.klo && k0 + e <= g.khi) stress_cell<3, EL, OOP>(g, a, k0 + e, j, i, b);
         return;
     }
     const int kg0 = k0 + g.koff;                 // global z index of element 0
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
 #pragma unroll
         for (int e = 0; e < VW; e++) if (kg0 + e <= nz - 1 && (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo))
             pc.v[e] = __fadd_rn(pc.v[e], __fmul_rn(__fadd_rn(__fadd_rn(dxx.v[e], dzz.v[e]), dyy.v[e]), K.v[e]));
-        st4(p, pc);
+        st4(OOP ? a.tau_o[T_XX] + c : p, pc);
         pml_close(m0); pml_close(m1); pml_close(m2);
         return;
     }
@@ -502,6 +503,11 @@ __global__ void __launch_bounds__(GPI_VEC_THREADS, GPI_VEC_MINBLOCKS) k_stress3v
     }
 
     // ---- phase 3: stores -----------------------------------------------------------------------------
-    st4(txx, xx); st4(tyy, yy); st4(tzz, zz); st4(txz, xz); st4(txy, xy); st4(tyz, yz);
+    if (OOP) {
+        st4(a.tau_o[T_XX] + c, xx); st4(a.tau_o[T_YY] + c, yy); st4(a.tau_o[T_ZZ] + c, zz);
+        st4(a.tau_o[T_XZ] + c, xz); st4(a.tau_o[T_XY] + c, xy); st4(a.tau_o[T_YZ] + c, yz);
+    } else {
+        st4(txx, xx); st4(tyy, yy); st4(tzz, zz); st4(txz, xz); st4(txy, xy); st4(tyz, yz);
+    }
     pml_close(m0); pml_close(m1); pml_close(m2); pml_close(m3); pml_close(m4); pml_close(m5); pml_close(m6); pml_close(m7); pml_close(m8);
 }

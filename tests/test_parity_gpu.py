@@ -411,19 +411,27 @@ def test_engine_matches_the_stokes_solution(G, monkeypatch, tma):
 # --------------------------------------------------------------------------------------------------
 # GPI_PINGPONG=1: adjoint runs without save_tp!'s copy (the two wavefield sets alternate as time levels, out-of-place kernels)
 # --------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("physics", ["acoustic", "elastic"])
+@pytest.mark.parametrize("physics", ["acoustic", "elastic", "acoustic3d", "elastic3d"])
 def test_pingpong_adjoint_equals_the_copy_path(G, O, monkeypatch, physics):
-    """The FWI gradient (forward_save + adjoint + imaging, 2-D, order 2) with the time levels ping-ponged between W and TP must be
+    """The FWI gradient (forward_save + adjoint + imaging, order 2) with the time levels ping-ponged between W and TP must be
     bit-identical to the run that copies W -> TP every step (save_tp.jl:5-12) and to the oracle; nt is odd so that the run ends on
     the other set (the handle swaps them), and the experiment is run twice to cover the swapped start.  The launch count proves the
-    ping-pong path ran: it replaces the copy by two more boundary launches per step and batch."""
+    ping-pong path ran: it replaces the copy by two more boundary launches per step and batch.  In 3-D the out-of-place kernels are
+    the register-staged float4 ones (for elastic media the copy path runs the TMA tiles, so the two families are compared as well)."""
     from geophyinv_jl_b200.host import gallery
+    extra = {"shot_batch": 2}
     if physics == "acoustic":
         kw, true = gallery.c4_fwi2d(nz=60, nx=90, nt=301, nss=3, nr=16, fq=10.0)
         attrib = G.FdtdAcoustic
-    else:
+    elif physics == "elastic":
         kw, true = gallery.fwi2d_elastic(nt=301)
         attrib = G.FdtdElastic
+    elif physics == "acoustic3d":
+        kw, true = gallery.fwi3d(nt=151)
+        attrib, extra = G.FdtdAcoustic, {}
+    else:
+        kw, true = gallery.fwi3d_elastic(nt=101)
+        attrib, extra = G.FdtdElastic, {}
     pt = O.OraclePFdtd(attrib(), **{**kw, "medium": true})
     pt.update()
     dobs = [d.copy() for d in pt.c.data[0]]
@@ -434,17 +442,20 @@ def test_pingpong_adjoint_equals_the_copy_path(G, O, monkeypatch, physics):
     res = {}
     for flag in ("0", "1"):
         monkeypatch.setenv("GPI_PINGPONG", flag)            # read by gpi_create
-        pg = G.PFdtd(attrib("forward_save"), **kw, shot_batch=2)
+        pg = G.PFdtd(attrib("forward_save"), **kw, **extra)
         for rep in range(2):
             g = np.zeros_like(m)
             loss = G.gradient(g, m, dobs, pg)
             res[flag, rep] = (g, loss, pg.last_launches)
-    nbatch = -(-len(kw["ageom"]) // 2)
+    nss = len(kw["ageom"])
+    nbatch = -(-nss // extra["shot_batch"]) if extra else nss
     nt = len(kw["tgrid"])
     for rep in range(2):
         g0, l0, n0 = res["0", rep]; g1, l1, n1 = res["1", rep]
         assert np.array_equal(g0, g1) and l0 == l1, f"ping-pong differs from the copy path (run {rep})"
-        assert n1 - n0 == 2 * nt * nbatch, (n0, n1)
+        # + two boundary launches per step; where the copy path runs the TMA tiles its four shell launches per step (two kernels x
+        # two wavefields) are gone as well
+        assert n1 - n0 == (2 - (4 if pg.engine.kernel_family() == "tma" else 0)) * nt * nbatch, (n0, n1)
         assert rel_l2(g1, go) <= GRAD_TOL
     print(f"ping-pong adjoint ({physics}): gradient bit-identical to the copy path, rel-L2 vs oracle {rel_l2(res['1', 0][0], go):.1e}, "
           f"launches {res['0', 0][2]:.0f} -> {res['1', 0][2]:.0f}")
