@@ -47,6 +47,10 @@ def pml_profile(exmgrid: StepRange, mgrid: StepRange, flags, dt: float, velavg: 
         b[ix] = np.exp(-(d[ix] / k[ix] + alpha[ix]) * dt)
         if abs(d[ix]) > 1.0e-6:
             a[ix] = d[ix] * (b[ix] - 1.0) / (k[ix] * (d[ix] + k[ix] * alpha[ix]))
+    if nx < npml:
+        # the reference slices the first and last npml entries of every axis whether or not it has a CPML face (cpml.jl:100-105):
+        # a BoundsError there, a message here
+        raise ValueError(f"an extended grid axis has {nx} nodes, fewer than npml = {npml}: update_pml! (cpml.jl:100-105) cannot take its slabs")
     pkI = np.concatenate([1.0 / k[:npml], 1.0 / k[nx - npml:]])
     pa = np.concatenate([a[:npml], a[nx - npml:]])
     pb = np.concatenate([b[:npml], b[nx - npml:]])

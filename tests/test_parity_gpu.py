@@ -409,6 +409,51 @@ def test_engine_matches_the_stokes_solution(G, monkeypatch, tma):
 
 
 # --------------------------------------------------------------------------------------------------
+# degenerate sizes and placements
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["nt1", "nt2", "nr1", "corners", "rigid_box_no_cpml", "three_shots_batch2"])
+def test_small_and_degenerate_cases(G, O, case):
+    """One and two time steps (the pressure record of step it+1 is written by step it: the last row must not be), a single
+    receiver, source and receivers on the corner nodes of the medium (taps next to the CPML interface), a rigid box without any
+    CPML face (no slab anywhere; every axis still >= npml nodes, which update_pml! needs, cpml.jl:100-105), three shots in batches
+    of two.  Records bit-identical to the oracle."""
+    from geophyinv_jl_b200.host import gallery
+    from geophyinv_jl_b200.host.data import AGeomss, make_srcwav
+    attrib, extra = G.FdtdAcoustic, {}
+    if case in ("nt1", "nt2"):
+        kw = gallery.c1_acou2d_homo(nz=30, nx=34, nt=int(case[2:]), nr=5)
+    elif case == "nr1":
+        kw = gallery.c1_acou2d_homo(nz=30, nx=34, nt=60, nr=1)
+    elif case == "corners":
+        kw = gallery.c1_acou2d_homo(nz=30, nx=34, nt=60, nr=1)
+        g = kw["medium"].grid
+        kw["ageom"] = [AGeomss({"z": [g[0][0]], "x": [g[1][0]]}, {"z": [g[0][0], g[0][len(g[0]) - 1]], "x": [g[1][0], g[1][len(g[1]) - 1]]})]
+        kw["srcwav"] = make_srcwav(kw["tgrid"], kw["ageom"], ["p"], kw["srcwav"][0].d["p"][:, 0])
+    elif case == "rigid_box_no_cpml":
+        kw = gallery.c1_acou2d_homo(nz=44, nx=47, nt=120, nr=3)
+        kw["pml_faces"] = []; kw["rigid_faces"] = ["zmin", "zmax", "xmin", "xmax"]
+    else:
+        kw = gallery.elastic2d(nz=24, nx=28, nt=50, nr=4, nss=3)
+        attrib, extra = G.FdtdElastic, {"shot_batch": 2}
+    pg, po = both(G, O, attrib, kw, **extra)
+    pg.update(); po.update()
+    for iss in range(len(pg.c.data[0])):
+        for f in pg.c.rfields:
+            a, b = pg.c.data[0][iss].d[f], po.c.data[0][iss].d[f]
+            assert a.shape == b.shape and np.array_equal(a, b), (case, iss, f)
+    if case not in ("nt1", "nt2"):
+        assert max(np.abs(po.c.data[0][0].d[f]).max() for f in po.c.rfields) > 0
+
+
+def test_axis_shorter_than_npml_is_rejected_with_a_message(G):
+    from geophyinv_jl_b200.host import gallery
+    kw = gallery.c1_acou2d_homo(nz=8, nx=9, nt=4, nr=2)
+    kw["pml_faces"] = []
+    with pytest.raises(ValueError, match="fewer than npml"):
+        G.SeisForwExpt(G.FdtdAcoustic(), **kw)
+
+
+# --------------------------------------------------------------------------------------------------
 # GPI_PINGPONG=1: adjoint runs without save_tp!'s copy (the two wavefield sets alternate as time levels, out-of-place kernels)
 # --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("physics", ["acoustic", "elastic", "acoustic3d", "elastic3d"])
