@@ -10,7 +10,7 @@ the kernels in their real launch geometry -- including the TMA-pipelined 3-D ela
 of their PTX primitives: the tile decomposition and the shell, the descriptors (an emulated cuTensorMapEncodeTiled with the driver's
 argument checks), the producer's box list and expect_tx byte accounting (a mismatch aborts instead of hanging), the tile header,
 the consumers' shared-memory indexing.  What it cannot cover: the asynchrony of that pipeline and its warp shuffles, NCCL, and
-anything about timing.  All 58 single-GPU parity tests pass under the emulation (37 min on 8 cores); the no-GPU suite runs the
+anything about timing.  All 69 single-GPU parity tests pass under the emulation (24 min on 8 cores, profiles/r01/emu_parity_final.log); the no-GPU suite runs the
 subset below.
 
 TEST INFRASTRUCTURE: the emulated library is built into a temporary directory, is never installed next to the package, and
