@@ -500,7 +500,8 @@ def run_c4(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C4: 2-D acoustic FWI gradient, {n_ex} extended cells, {nt} steps, {nss_per} supersources per GPU, NCCL gradient all-reduce",
                        "extended_grid": n_ex, "time_steps_per_step": nt, "supersources_per_gpu": nss_per, "parallelism": f"shots sharded x{world}",
-                       "l2": "16 resident shots x 3 wavefields exceed the 126 MB L2"},
+                       "l2": "16 resident shots x 3 wavefields exceed the 126 MB L2",
+                       "adjoint_time_levels": "ping-pong (GPI_PINGPONG=1)" if os.environ.get("GPI_PINGPONG", "0") not in ("", "0") else "save_tp copy"},
             "e2e": {"value": cells * args.steps / e2e_s / 1e9, "unit": "Gcell-updates/s", "h2d_bytes_per_step": int(m.nbytes), "d2h_bytes_per_step": int(g.nbytes),
                     "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": int(launches),
