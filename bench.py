@@ -19,7 +19,17 @@ cpu_baseline = the reference-structured CPU restatement (oracle/, all host threa
             sample (same grid, a few time steps).
 
 `--impl reference` times that CPU restatement alone (Julia is not installed here or on the GPU box,
-so the reference's own Base.Threads path cannot run).
+so the reference's own Base.Threads path cannot run).  It uses every host core it is allowed
+to (the affinity mask, NOT the OMP_NUM_THREADS=1 that torchrun exports) and prints the same `config`.
+
+extra     = after the headline leg, the two paths that COMMUNICATE run in the same process group and land
+            in the same JSON line (skip with --no-extra):
+            extra.c4: BASELINE config 4, 32 supersources in total sharded over the N ranks (strong scaling),
+                      one NCCL sum all-reduce of the gradient per `gradient!`, `parity_ok` = the N-rank gradient of
+                      a reduced grid against rank 0 running the same shots alone;
+            extra.c5: BASELINE config 5, one 3-D elastic shot over N z-slabs (strong scaling), halo planes over
+                      NVLink every half step, `slab_parity_ok` = records and owned wavefield rows of a reduced grid
+                      against the single-GPU run, `exchange_share` = sampled exchange time / step time.
 """
 from __future__ import annotations
 
@@ -154,6 +164,54 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def host_threads():
+    """Host cores this process may use: the affinity mask (torchrun exports OMP_NUM_THREADS=1, which says nothing about the box)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+_DIST = None
+
+
+def get_dist():
+    """One torch.distributed process group (NCCL) for every leg of the run; None for a single process."""
+    global _DIST
+    import torch
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    if world > 1 and _DIST is None:
+        from geophyinv_jl_b200.host import dist as D
+        _DIST = D.init_process_group("nccl")
+    return _DIST
+
+
+def barrier():
+    import torch
+    torch.cuda.synchronize()
+    if _DIST is not None:
+        _DIST.barrier()
+    torch.cuda.synchronize()
+
+
+def allmax(x):
+    import torch
+    if _DIST is None:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    _DIST.all_reduce(t, op=_DIST.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bench_config(wl, order, B, n_ex, nt, nss, world):
+    """`config` of the headline leg -- the SAME dict for our arm and for the reference arm (the CPU arm times a bounded sample of it:
+    that is said in its cpu_baseline.sample, not here)."""
+    return {"workload": wl["label"], "fd_order": order, "shot_batch": int(B), "extended_grid": [int(x) for x in n_ex], "time_steps_per_step": int(nt),
+            "supersources_per_gpu": int(nss), "parallelism": f"one supersource stream per GPU x{world}",
+            "l2": "working set (3.3 GB at C3) far exceeds the 126 MB L2; no flush needed"}
+
+
 # ====================================================================================================
 def run_reference(args):
     """CPU arm: the reference-structured restatement (oracle/) with all host threads, bounded sample."""
@@ -166,6 +224,7 @@ def run_reference(args):
     O.build()
     nt_s = args.cpu_steps
     wl = workload(args.workload, nt_override=nt_s)
+    O.OraclePFdtd.oracle_threads = host_threads()            # explicit: torchrun exports OMP_NUM_THREADS=1
     po = O.OraclePFdtd(wl["attrib"](), **wl["kw"])
     n_ex = [len(g) for g in po.c.exgrid]
     nss = len(po.local)
@@ -179,15 +238,20 @@ def run_reference(args):
     sec = float(np.sum(ts))
     val = cells * args.steps / sec / 1e9
     cores = int(po.engine.threads)
-    sample = f"{nt_s} time steps of the same extended grid {n_ex} per step ({args.steps} steps timed, {args.warmup} warm-up)"
+    nt_full = args.nt or {"c3": 2000, "c3small": 200, "c2": 4000}.get(args.workload, nt_s)
+    B = args.shot_batch or (16 if wl["ndims"] == 2 else 1)
+    sample = (f"{nt_s} of the {nt_full} time steps of the same extended grid {n_ex} per bench step ({args.steps} steps timed, {args.warmup} warm-up); "
+              f"the metric is per cell update, so the sample length does not enter it; {cores} OpenMP threads")
+    print(f"bench.py --impl reference: {cores} host threads (affinity mask; OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS')})", file=sys.stderr, flush=True)
     out = {
         "impl": "reference", "metric": "Gcell-updates/s", "value": val, "unit": "Gcell-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["label"], "time_steps_per_step": nt_s, "note": "CPU restatement of src/fdtd (Julia absent); unfused reference sweep structure, OpenMP static"},
-        "cpu_baseline": {"value": val, "unit": "Gcell-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": bench_config(wl, args.order, max(1, min(nss, B)), n_ex, nt_full, nss, max(1, world)),
+        "cpu_baseline": {"value": val, "unit": "Gcell-updates/s", "cores": cores, "kind": "port", "sample": sample, "sample_time_steps": nt_s},
         "e2e": {"value": val, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "CPU restatement of src/fdtd (Julia absent); unfused reference sweep structure, OpenMP static; rank 0 only",
     }
     print(json.dumps(out), flush=True)
 
@@ -197,6 +261,7 @@ def cpu_baseline_sample(wl_name, nt_s=8):
     import oracle as O
     O.build()
     wl = workload(wl_name, nt_override=nt_s)
+    O.OraclePFdtd.oracle_threads = host_threads()
     po = O.OraclePFdtd(wl["attrib"](), **wl["kw"])
     n_ex = [len(g) for g in po.c.exgrid]
     po.update()                                        # warm-up (page faults, thread pool)
@@ -216,11 +281,7 @@ def run_ours(args):
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dist = get_dist()
     import geophyinv_jl_b200 as G
     wl = workload(args.workload, nt_override=args.nt, nss=args.nss)
     kw = wl["kw"]
@@ -232,18 +293,7 @@ def run_ours(args):
     nt, nss = c.ic["nt"], len(pa.local)
     cells_per_step = float(np.prod(n_ex)) * nt * nss
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = allmax
 
     # ---- device-resident throughput ------------------------------------------------------------
     for _ in range(args.warmup):
@@ -324,40 +374,82 @@ def run_ours(args):
         except Exception as e:      # the baseline is reported, never required
             cpu = {"value": None, "unit": "Gcell-updates/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
+    out = None
     if rank == 0:
         out = {
             "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["label"], "fd_order": args.order, "shot_batch": int(B), "extended_grid": n_ex, "time_steps_per_step": nt, "supersources_per_gpu": nss,
-                       "parallelism": f"one supersource stream per GPU x{world}", "l2": "working set (3.3 GB at C3) far exceeds the 126 MB L2; no flush needed",
-                       "interior_equivalent_value": value * float(np.prod([len(g) for g in c.medium.grid])) / float(np.prod(n_ex))},
+            "config": bench_config(wl, args.order, B, n_ex, nt, nss, world),
+            "interior_equivalent_value": value * float(np.prod([len(g) for g in c.medium.grid])) / float(np.prod(n_ex)),
             "e2e": {"value": e2e_val, "unit": "Gcell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "wall_s_timed_region": wall, "build_s": t_build,
             "shots_per_hour": 3600.0 * nss * world * args.steps / (dev_ms * 1e-3),
         }
-        print(json.dumps(out), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    del pa
+    return out
 
 
-def run_c5(args):
+def slab_parity(dist, rank, local_rank, world):
+    """A reduced 3-D elastic grid over `world` z-slabs against rank 0 propagating the same shot alone: every wavefield's owned rows
+    and the records, bit for bit (tests/_slab_worker.py is the pytest form).  Returns a dict on rank 0."""
+    import torch
+    import geophyinv_jl_b200 as G
+    from geophyinv_jl_b200.host import dist as D, gallery
+    if world == 1:
+        return {"slab_parity_ok": None, "note": "one rank: the slab run IS the single-GPU run"}
+    n = max(38, 12 * world + 8)
+    kw = gallery.c3_elastic3d(n=n, nt=120, nr=12, fq=30.0, rfields=("vz", "vx"))
+    L = kw["medium"].grid[0].last
+    a = kw["ageom"][0]
+    a.r["z"][...] = np.linspace(0.1 * L, 0.9 * L, a.nr)          # receivers on a vertical line: taps straddle the cuts
+    ps = G.SeisForwExpt(G.FdtdElastic(), **kw, device=local_rank, zslab=(rank, world))
+    D.attach_nccl(ps, dist)
+    ps.update()
+    ref = None
+    if rank == 0:
+        ref = G.SeisForwExpt(G.FdtdElastic(), **kw, device=local_rank)
+        ref.update()
+    fields_equal, worst = True, 0.0
+    for f in ("tauxx", "tauyy", "tauzz", "tauxy", "tauxz", "tauyz", "vx", "vy", "vz"):
+        t = torch.from_numpy(np.ascontiguousarray(ps.engine.get_field(0, f))).cuda()
+        dist.all_reduce(t)                                          # slabs are disjoint: the sum is the whole field
+        if rank == 0:
+            want = ref.engine.get_field(0, f)
+            fields_equal = fields_equal and bool(np.abs(want).max() > 0) and bool(np.array_equal(t.cpu().numpy(), want))
+    rec_equal = True
+    if rank == 0:
+        for f in ps.c.rfields:
+            x, y = ps.c.data[0][0].d[f], ref.c.data[0][0].d[f]
+            rec_equal = rec_equal and bool(np.array_equal(x, y))
+            worst = max(worst, float(np.linalg.norm(x.astype(np.float64) - y) / np.linalg.norm(y)))
+    del ps, ref
+    if rank != 0:
+        return None
+    return {"slab_parity_ok": bool(fields_equal and worst <= 1e-6), "wavefields_bit_identical": bool(fields_equal), "records_bit_identical": bool(rec_equal),
+            "records_rel_l2": worst, "grid": f"3-D elastic {n}^3 + CPML, 120 steps, 12 receivers on a vertical line, {world} z-slabs vs 1 GPU",
+            "note": "a receiver whose taps straddle a cut is summed over two ranks (different association): records gate 1e-6, wavefields bit for bit"}
+
+
+def run_c5(args, steps=None, warmup=None):
     """BASELINE config 5: ONE 3-D elastic shot over z-slabs (strong scaling: the grid is fixed, each GPU owns
     1/N of its z planes and exchanges halo planes over NVLink every half step).  `c5` = [512, 1024, 1024]
     interior cells (594 x 1106 x 1106 extended); `c5small` = 96 x 128 x 128 for debugging."""
     import torch
     rank, local_rank, world = dist_env()
-    torch.cuda.set_device(local_rank)
-    from geophyinv_jl_b200.host import dist as D, slab
+    dist = get_dist()
+    from geophyinv_jl_b200.host import slab
     from geophyinv_jl_b200.host.data import AGeomss, ricker
     from geophyinv_jl_b200.host.grids import StepRange
-    dist = D.init_process_group("nccl")
-    ni = (512, 1024, 1024) if args.workload == "c5" else (96, 128, 128)
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
+    small = args.workload == "c5small" or args.c5_small
+    ni = (96, 128, 128) if small else (512, 1024, 1024)
     d = 10.0
     grid = [StepRange(0.0, d, m) for m in ni]
-    nt = args.nt or 200
+    nt = (args.nt if args.workload in ("c5", "c5small") else None) or 200
     tgrid = StepRange(0.0, 1e-3, nt)
     exn = [m + 82 for m in ni]
     L = [g.last for g in grid]
@@ -373,37 +465,25 @@ def run_c5(args):
     t_build = time.time() - t0
     N_ex = float(np.prod(exn))
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def allmax(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         ex.update()
     sampler = ClockSampler(local_rank)
     barrier(); sampler.start()
     w0 = time.perf_counter()
-    dev_ms = launches = vel_ms = vel_n = str_ms = str_n = 0.0
-    for _ in range(args.steps):
+    dev_ms = launches = vel_ms = vel_n = str_ms = str_n = exch_ms = exch_n = 0.0
+    for _ in range(steps):
         t = ex.update()
         dev_ms += t["run_ms"]; launches += t["launches"]
         vel_ms += t["vel_ms"]; vel_n += t["vel_n"]; str_ms += t["stress_ms"]; str_n += t["stress_n"]
+        exch_ms += t.get("exch_ms", 0.0); exch_n += t.get("exch_n", 0.0)
     barrier()
     wall = time.perf_counter() - w0
     clocks = sampler.stop()
     dev_ms = allmax(dev_ms)
-    value = N_ex * nt * args.steps / (dev_ms * 1e-3) / 1e9
+    value = N_ex * nt * steps / (dev_ms * 1e-3) / 1e9
     # end to end: the public call with the records brought to the host
     barrier(); e0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         ex.update(); rec_h = ex.records("vz")
     barrier()
     e2e_s = allmax(time.perf_counter() - e0)
@@ -412,43 +492,86 @@ def run_c5(args):
     bv, bs = algorithmic_bytes_per_step(3, True, exn, [2, 2, 2])
     peak, peak_kind = measured_peak()
     kv, ks = allmax(vel_ms / max(vel_n, 1)), allmax(str_ms / max(str_n, 1))
+    # two exchanges per time step; exch_* are sampled on the same steps as the kernels
+    exch_per_step = allmax(2.0 * exch_ms / max(exch_n, 1)) if world > 1 else 0.0
     fam = ex.engine.kernel_family()                      # 'tma' or 'vec4': narrow slabs run the register-staged kernels
     KV, KS = ("k_step3t<0> (velocity)", "k_step3t<1> (stress)") if fam == "tma" else ("k_vel3v", "k_stress3v")
     roof = {"bound": "hbm", "kernel": KS, "achieved": bs / world / (ks * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": bs / world / (ks * 1e-3) / 1e9 / peak, "peak_source": peak_kind, "traffic": None, "avg_launch_ms": ks,
             "other": {KV: {"avg_launch_ms": kv, "frac": bv / world / (kv * 1e-3) / 1e9 / peak}},
             "both_kernels_frac": (bv + bs) / world / ((kv + ks) * 1e-3) / 1e9 / peak,
-            "stencil_share_of_step": (kv + ks) * nt * args.steps / max(dev_ms, 1e-9),
+            "stencil_share_of_step": (kv + ks) * nt * steps / max(dev_ms, 1e-9),
+            "whole_step_frac": (bv + bs) / world * nt * steps / (dev_ms * 1e-3) / 1e9 / peak,
             "note": "per-GPU figures (max over ranks of the kernel times, 1/N of the whole-grid algorithmic bytes)"}
-    if rank == 0:
-        print(json.dumps({
-            "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C5: 3-D elastic {list(ni)} + CPML(41) = {exn}, z-slabs over {world} GPU(s), NCCL halo exchange over NVLink",
-                       "extended_grid": exn, "time_steps_per_step": nt, "parallelism": f"zslab{world}", "owned_fraction_rank0": own,
-                       "l2": "working set exceeds L2 by orders of magnitude; no flush needed"},
-            "e2e": {"value": N_ex * nt * args.steps / e2e_s / 1e9, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": int(rec_h.nbytes), "note": "inputs of a repeated shot stay resident; records D2H per step"},
-            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": None, "clocks": clocks,
-            "wall_s_timed_region": wall, "build_s": t_build, "ms_per_time_step": dev_ms / args.steps / nt}), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    del ex
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {
+        "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C5: 3-D elastic {list(ni)} + CPML(41) = {exn}, z-slabs over {world} GPU(s), halo planes over NVLink",
+                   "extended_grid": exn, "time_steps_per_step": nt, "parallelism": f"zslab{world}", "owned_fraction_rank0": own,
+                   "l2": "working set exceeds L2 by orders of magnitude; no flush needed"},
+        "e2e": {"value": N_ex * nt * steps / e2e_s / 1e9, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": int(rec_h.nbytes), "note": "inputs of a repeated shot stay resident; records D2H per step"},
+        "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": None, "clocks": clocks,
+        "exchange_ms_per_time_step": exch_per_step, "exchange_share": exch_per_step * nt * steps / max(dev_ms, 1e-9),
+        "wall_s_timed_region": wall, "build_s": t_build, "ms_per_time_step": dev_ms / steps / nt}
 
 
-def run_c4(args):
-    """BASELINE config 4: 2-D acoustic FWI gradient (forward_save + adjoint + imaging) over the supersources of
-    every rank (32 in total at N = 1; `--nss` per GPU otherwise), one NCCL sum all-reduce of the gradient over NVLink.
-    A bench step = one `gradient!` call (func_grad.jl:11-49) through the host API: model vector in, gradient out."""
-    import torch
-    rank, local_rank, world = dist_env()
-    torch.cuda.set_device(local_rank)
+def c4_parity(dist, rank, local_rank, world):
+    """The FWI gradient of a reduced grid, 8 supersources sharded over `world` ranks + NCCL all-reduce, against rank 0 running all 8 alone.
+    Per-rank partial sums are stacked in shot order and NCCL sums the partials in its own order, so the association differs from the
+    one-rank stack: the gate is the north-star's 1e-4 (measured ~1e-7); `bit_identical` is reported as found."""
     import geophyinv_jl_b200 as G
     from geophyinv_jl_b200.host import dist as D, gallery
-    dist = D.init_process_group("nccl")
-    nss_per = args.nss or 32
-    nt = args.nt or 3000
-    kw, true = gallery.c4_fwi2d(nt=nt, nss=nss_per * world)
+    if world == 1:
+        return {"parity_ok": None, "note": "one rank: no all-reduce"}
+    kwg, true = gallery.c4_fwi2d(nz=60, nx=90, nt=300, nss=8, nr=12, fq=12.0)
+    pg = G.PFdtd(G.FdtdAcoustic("forward_save"), **kwg, nworker=world, rank=rank, device=local_rank)
+    D.attach_nccl(pg, dist)
+    box = [None]
+    p1 = None
+    if rank == 0:
+        pt = G.SeisForwExpt(G.FdtdAcoustic(), **{**kwg, "medium": true}, device=local_rank)
+        pt.update()
+        box[0] = [d.copy() for d in pt.c.data[0]]
+        del pt
+    dist.broadcast_object_list(box, src=0)
+    dobs = box[0]
+    m = pg.get_modelvector()
+    g = np.zeros_like(m)
+    G.gradient(g, m, dobs, pg)                    # every rank ends with the all-reduced gradient
+    out = None
+    if rank == 0:
+        p1 = G.PFdtd(G.FdtdAcoustic("forward_save"), **kwg, device=local_rank)
+        g1 = np.zeros_like(m)
+        G.gradient(g1, m, dobs, p1)
+        err = float(np.linalg.norm(g.astype(np.float64) - g1) / np.linalg.norm(g1))
+        out = {"parity_ok": bool(np.isfinite(err) and np.abs(g1).max() > 0 and err <= 1e-4), "gradient_rel_l2": err, "bit_identical": bool(np.array_equal(g, g1)),
+               "grid": f"2-D acoustic 60x90 + CPML, 300 steps, 8 supersources over {world} ranks vs 1 GPU, parameters invK and rho"}
+        del p1
+    del pg
+    return out
+
+
+def run_c4(args, steps=None, warmup=None, nss_total=None):
+    """BASELINE config 4: 2-D acoustic FWI gradient (forward_save + adjoint + imaging), one NCCL sum all-reduce of the gradient over NVLink.
+    A bench step = one `gradient!` call (func_grad.jl:11-49) through the host API: model vector in, gradient out.
+    `nss_total` supersources in total sharded over the ranks (strong scaling, the extra leg); else `--nss` per GPU (weak, default 32)."""
+    import torch
+    rank, local_rank, world = dist_env()
+    dist = get_dist()
+    import geophyinv_jl_b200 as G
+    from geophyinv_jl_b200.host import dist as D, gallery
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
+    strong = nss_total is not None
+    nss_all = nss_total if strong else (args.nss or 32) * world
+    nt = (args.nt if args.workload == "c4" else None) or 3000
+    kw, true = gallery.c4_fwi2d(nt=nt, nss=nss_all)
     t0 = time.time()
     pa = G.SeisForwExpt(G.FdtdAcoustic("forward_save"), **kw, nworker=world, rank=rank, device=local_rank)
     D.attach_nccl(pa, dist)
@@ -462,56 +585,68 @@ def run_c4(args):
     m = pa.get_modelvector()
     g = np.zeros_like(m)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def allmax(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         G.gradient(g, m, dobs, pa)
     sampler = ClockSampler(local_rank)
     barrier(); sampler.start()
     e0 = time.perf_counter()
-    dev_ms = launches = 0.0
-    for _ in range(args.steps):
+    dev_ms = launches = ar_ms = 0.0
+    for _ in range(steps):
         G.gradient(g, m, dobs, pa)
-        # device time of the two passes of this call (forward_save, adjoint), from the engine's CUDA events
-        dev_ms += pa.last_run_ms
+        # device time of the two passes of this call (forward_save, adjoint) plus the all-reduce, from the engine's CUDA events
+        ar = pa.engine.timers().get("allreduce_ms", 0.0) if world > 1 else 0.0
+        dev_ms += pa.last_run_ms + ar
+        ar_ms += ar
         launches += pa.last_launches
     barrier()
     e2e_s = allmax(time.perf_counter() - e0)
     clocks = sampler.stop()
     dev_ms = allmax(dev_ms)
-    cells = float(np.prod(n_ex)) * nt * nss_per * world * 3          # forward_save: 1 wavefield; adjoint: 2
-    if rank == 0:
-        peak, peak_kind = measured_peak()
-        gb = cells / 3 * (48 + 112) / 1e9                             # 48 B forward, 112 B adjoint step per cell
-        print(json.dumps({
-            "metric": "Gcell-updates/s", "value": cells * args.steps / (dev_ms * 1e-3) / 1e9, "unit": "Gcell-updates/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C4: 2-D acoustic FWI gradient, {n_ex} extended cells, {nt} steps, {nss_per} supersources per GPU, NCCL gradient all-reduce",
-                       "extended_grid": n_ex, "time_steps_per_step": nt, "supersources_per_gpu": nss_per, "parallelism": f"shots sharded x{world}",
-                       "l2": "16 resident shots x 3 wavefields exceed the 126 MB L2",
-                       "adjoint_time_levels": "ping-pong (GPI_PINGPONG=1)" if os.environ.get("GPI_PINGPONG", "0") not in ("", "0") else "save_tp copy"},
-            "e2e": {"value": cells * args.steps / e2e_s / 1e9, "unit": "Gcell-updates/s", "h2d_bytes_per_step": int(m.nbytes), "d2h_bytes_per_step": int(g.nbytes),
-                    "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "forward_save + adjoint passes (k_vel2v, k_stress2v, k_grad2d, boundary, tp copy)",
-                         "achieved": gb * args.steps / (dev_ms * 1e-3), "peak": peak, "unit": "GB/s", "frac": gb * args.steps / (dev_ms * 1e-3) / peak / world,
-                         "peak_source": peak_kind, "traffic": None, "note": "whole-pass figure: algorithmic bytes of SURVEY 8d (48 + 112 B per cell-step) / device time, per GPU"},
-            "cpu_baseline": None, "clocks": clocks, "build_s": t_build,
-            "gradients_per_hour": 3600.0 * args.steps / e2e_s, "shots_per_hour": 3600.0 * nss_per * world * args.steps / e2e_s}), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    ar_ms = allmax(ar_ms)
+    cells = float(np.prod(n_ex)) * nt * nss_all * 3          # forward_save: 1 wavefield; adjoint: 2
+    nss_local = len(pa.local)
+    B = int(pa.engine.cfg.shot_batch or min(16, max(nss_local, 1)))
+    pp = os.environ.get("GPI_PINGPONG", "1") not in ("", "0")
+    del pa
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peak, peak_kind = measured_peak()
+    gb = cells / 3 * (48 + 112) / 1e9                             # 48 B forward, 112 B adjoint step per cell
+    return {
+        "metric": "Gcell-updates/s", "value": cells * steps / (dev_ms * 1e-3) / 1e9, "unit": "Gcell-updates/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C4: 2-D acoustic FWI gradient, {n_ex} extended cells, {nt} steps, {nss_all} supersources in total ({nss_local} on rank 0), NCCL gradient all-reduce",
+                   "extended_grid": n_ex, "time_steps_per_step": nt, "supersources_total": nss_all, "supersources_rank0": nss_local, "shot_batch": B,
+                   "parallelism": f"shots sharded x{world}", "l2": "the resident shots x 3 wavefields exceed the 126 MB L2 from 6 shots on",
+                   "adjoint_time_levels": "ping-pong (default)" if pp else "save_tp copy (GPI_PINGPONG=0)"},
+        "e2e": {"value": cells * steps / e2e_s / 1e9, "unit": "Gcell-updates/s", "h2d_bytes_per_step": int(m.nbytes), "d2h_bytes_per_step": int(g.nbytes),
+                "ms_per_step": e2e_s / steps * 1e3},
+        "gpu_launches": int(launches), "allreduce_ms_per_gradient": ar_ms / steps,
+        "roofline": {"bound": "hbm", "kernel": "forward_save + adjoint passes (k_vel2v, k_stress2v, imaging, boundary)",
+                     "achieved": gb * steps / (dev_ms * 1e-3) / world, "peak": peak, "unit": "GB/s", "frac": gb * steps / (dev_ms * 1e-3) / peak / world,
+                     "peak_source": peak_kind, "traffic": None, "note": "whole-pass figure: algorithmic bytes of SURVEY 8d (48 + 112 B per cell-step) / device time, per GPU"},
+        "cpu_baseline": None, "clocks": clocks, "build_s": t_build,
+        "gradients_per_hour": 3600.0 * steps / e2e_s, "shots_per_hour": 3600.0 * nss_all * steps / e2e_s}
+
+
+def extra_legs(args):
+    """The two communicating paths (BASELINE configs 4 and 5) in the same process group, after the headline leg."""
+    rank, local_rank, world = dist_env()
+    dist = get_dist()
+    extra = {}
+    for name, fn in (("c4", lambda: {**(run_c4(args, steps=2, warmup=1, nss_total=32) or {}), **(c4_parity(dist, rank, local_rank, world) or {})}),
+                     ("c5", lambda: {**(run_c5(args, steps=2, warmup=1) or {}), **(slab_parity(dist, rank, local_rank, world) or {})})):
+        t0 = time.time()
+        try:
+            leg = fn()
+        except Exception as e:                     # an extra leg must not take the headline line with it; the failure is reported
+            leg = {"failed": f"{type(e).__name__}: {e}"}
+        if rank == 0:
+            leg["leg_wall_s"] = time.time() - t0
+            extra[name] = leg
+    return extra if rank == 0 else None
 
 
 def main():
@@ -527,15 +662,27 @@ def main():
     ap.add_argument("--nss", type=int, default=None, help="supersources per GPU (c2, c4)")
     ap.add_argument("--shot-batch", type=int, default=0, help="supersources resident per launch (0 = engine default: 16 in 2-D, 1 in 3-D)")
     ap.add_argument("--order", type=int, default=2, help="_fd_order: 2 (default, the reference's default) or 4")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C5 legs that follow the headline C3 leg")
+    ap.add_argument("--c5-small", action="store_true", help="extra C5 leg on the 96 x 128 x 128 debug grid")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload in ("c5", "c5small"):
-        run_c5(args)
+        return
+    if args.workload in ("c5", "c5small"):
+        out = run_c5(args)
     elif args.workload == "c4":
-        run_c4(args)
+        out = run_c4(args)
     else:
-        run_ours(args)
+        out = run_ours(args)
+        if args.workload == "c3" and not args.no_extra:
+            extra = extra_legs(args)
+            if out is not None:
+                out["extra"] = extra
+    if out is not None:
+        print(json.dumps(out), flush=True)
+    if _DIST is not None:
+        barrier()
+        _DIST.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -160,14 +160,14 @@ struct gpi_handle {
     std::vector<int32_t> itsnaps;
     PostDesc *post_v = nullptr, *post_s = nullptr, *h_post_v = nullptr, *h_post_s = nullptr;
     float** bnd_table = nullptr;        // boundary stores of the resident batch, [b][field][axis]
-    // GPI_PINGPONG=1 (order 2, adjoint runs; float4 kernel families): W and TP alternate as the time levels instead of save_tp!'s copy; the forced
+    // adjoint runs (order 2; float4 kernel families; default, GPI_PINGPONG=0 restores the copy): W and TP alternate as the time levels instead of save_tp!'s copy; the forced
     // boundary planes of the level that stays behind get their pre-force values back from `stash` ([b][field][axis], one slot)
-    bool pingpong = false;  float* stash = nullptr;  float** stash_table = nullptr;
+    bool pingpong = true;  float* stash = nullptr;  float** stash_table = nullptr;
     float* stage = nullptr;  size_t stage_floats = 0;       // pinned host staging
     float* dscratch = nullptr;  size_t dscratch_floats = 0; // device scratch (raw interior medium before padding)
     gpi_timers timers{};
     std::vector<cudaEvent_t> evpool;  size_t evused = 0;   // sampled per-kernel timing (pairs)
-    std::vector<int> evkind;                                // 0 = velocity kernel, 1 = stress kernel
+    std::vector<int> evkind;                                // 0 = velocity kernel, 1 = stress kernel, 2 = z-slab halo exchange
     int sample_every = 16;
     // tuning
     dim3 blk3{64, 2, 2}, blk2{128, 2, 1};
@@ -358,7 +358,7 @@ int build_tmaps(gpi_handle* h, const StepArgs& a, int kind, t3::Maps** dout) {
 template <int KIND>
 int launch_step3t(gpi_handle* h, const StepArgs& a) {
     const Geom& g = h->g;
-    // descriptors are cached per wavefield set (the pointers of a pw never change after gpi_create)
+    // descriptors are cached per wavefield set, keyed by the set's first pointer (ping-pong runs swap W and TP: a new key rebuilds them)
     gpi_handle::TmaSet* set = nullptr;
     for (auto& ts : h->tmaps) if (ts.key == a.v[0]) set = &ts;
     if (!set) {
@@ -1300,9 +1300,13 @@ int build_post(gpi_handle* h, int shot0, int nb, int activepw, int src_flags) {
 // neighbour's khi+1).  phase 1 (before the stress kernel): vx, vy travel up, vz travels down.
 // One pack kernel per direction, one grouped NCCL send/recv over NVLink, one unpack kernel per direction,
 // all on the engine's stream.
-int exchange_halos(gpi_handle* h, int phase) {
+int exchange_halos(gpi_handle* h, int phase, bool sample = false) {
     if (!h->slab) return 0;
     if (!h->comm) FAIL(h, "z-slab handles need gpi_nccl_init before gpi_run");
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (sample) { e0 = sample_event(h); e1 = sample_event(h); }
+    if (e0 && e1) { cudaEventRecord(e0, h->stream); h->evkind.push_back(2); }
+    struct Closer { gpi_handle* h; cudaEvent_t e; ~Closer() { if (e) cudaEventRecord(e, h->stream); } } closer{h, (e0 && e1) ? e1 : nullptr};
     const Geom& g = h->g;
     const size_t plane = (size_t)g.ny1 * g.nx1;
     int up[3], dn[3], nup = 0, ndn = 0;
@@ -1359,7 +1363,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     if (mode == GPI_MODE_FORWARD_SAVE && !h->c.store_boundary) FAIL(h, "forward_save needs store_boundary=1 at construction (fdtd.jl:445-455)");
     if (mode == GPI_MODE_ADJOINT && !h->c.store_boundary) FAIL(h, "adjoint needs the boundary store of a forward_save run");
     const bool grad = mode == GPI_MODE_ADJOINT && (activepw & 2) && h->npw == 2;
-    // GPI_PINGPONG=1: the two wavefield sets alternate as "this step" / "previous step" (what save_tp! copies, save_tp.jl:5-12)
+    // default (GPI_PINGPONG=0 opts out; measured r02: C4 65.0 -> 76.4 Gcell-updates/s): the two wavefield sets alternate as "this step" / "previous step" (what save_tp! copies, save_tp.jl:5-12)
     const bool pp = h->pingpong && mode == GPI_MODE_ADJOINT && h->TP && h->c.order == 2 && (h->nd == 2 ? h->vec2 : h->vec3) && !born && !h->slab;
     if (pp && ensure_stash(h)) return 1;
     if (grad && !h->gshot) FAIL(h, "gradient imaging needs an experiment built with npw = 2");
@@ -1434,7 +1438,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                 h->timers.launches += 1;
             }
             if (do_post_v) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_v, it, it, nt, (float)h->c.dt, 3, woff); h->timers.launches += 1; }
-            if (exchange_halos(h, 1)) return 1;
+            if (exchange_halos(h, 1, sample)) return 1;
             if (merge_pw) launch_step(h, pp ? rebase(margs, A, Bn, false) : margs, false, margs.nbatch, sample);
             else for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, pp ? rebase(args[ipw], A, Bn, false) : args[ipw], false, nb, sample && ipw == 0);
             if (born) {        // add_born_sources_stress! (propagate.jl:226)
@@ -1451,7 +1455,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                 if (launch_boundary(h, 0, nb, 0, A, h->stash_table)) return 1;      // the previous level as save_tp! would have left it
                 cur = Bn; prev = A;
             }
-            if (exchange_halos(h, 0)) return 1;
+            if (exchange_halos(h, 0, sample)) return 1;
             if (mode == GPI_MODE_FORWARD_SAVE && launch_boundary(h, true, nb, it - 1)) return 1;
             if (grad && h->el && h->nd == 3) {
                 const int tf[6] = {GPI_TAUXX, GPI_TAUYY, GPI_TAUZZ, GPI_TAUXY, GPI_TAUXZ, GPI_TAUYZ};     // T_XX .. T_YZ
@@ -1543,8 +1547,9 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     for (size_t q = 0; q < h->evkind.size(); q++) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, h->evpool[2 * q], h->evpool[2 * q + 1]) != cudaSuccess) continue;
-        if (h->evkind[q] == 0) { h->timers.vel_ms += t; h->timers.vel_n += 1; }
-        else                   { h->timers.stress_ms += t; h->timers.stress_n += 1; }
+        if (h->evkind[q] == 0)      { h->timers.vel_ms += t; h->timers.vel_n += 1; }
+        else if (h->evkind[q] == 1) { h->timers.stress_ms += t; h->timers.stress_n += 1; }
+        else                        { h->timers.exch_ms += t; h->timers.exch_n += 1; }
     }
     h->timers.stencil_ms = h->timers.vel_ms + h->timers.stress_ms;
     const int npw_active = ((activepw & 1) ? 1 : 0) + ((activepw & 2) ? 1 : 0);
@@ -1630,7 +1635,9 @@ int load_nccl(gpi_handle* h, NcclApi& n) {
     n.GroupEnd = (int (*)())dlsym(n.lib, "ncclGroupEnd");
     n.CommDestroy = (int (*)(void*))dlsym(n.lib, "ncclCommDestroy");
     n.GetErrorString = (const char* (*)(int))dlsym(n.lib, "ncclGetErrorString");
-    if (!n.GetUniqueId || !n.CommInitRank || !n.AllReduce || !n.CommDestroy) { if (h) h->err = "libnccl is missing symbols"; return 1; }
+    if (!n.GetUniqueId || !n.CommInitRank || !n.AllReduce || !n.CommDestroy || !n.Send || !n.Recv || !n.GroupStart || !n.GroupEnd) {
+        if (h) h->err = "libnccl is missing symbols (need ncclSend / ncclRecv / ncclGroupStart / ncclGroupEnd: NCCL >= 2.7)"; return 1;
+    }
     return 0;
 }
 NcclApi g_nccl;
@@ -1653,10 +1660,15 @@ extern "C" int gpi_nccl_init(gpi_handle* h, const void* id128, int rank, int nra
 extern "C" int gpi_allreduce_gradients(gpi_handle* h) {
     GUARD(h);
     if (!h->comm) { if (h->nranks == 1) return 0; FAIL(h, "gpi_nccl_init has not been called"); }
+    CU(h, cudaEventRecord(h->ev0, h->stream));
     for (int p = 0; p < GPI_NPARAM; p++) if (h->gtot[p]) {
         int r = h->nccl.AllReduce(h->gtot[p], h->gtot[p], (size_t)h->g.vol, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->comm, h->stream);
         if (r != 0) FAIL(h, "ncclAllReduce failed: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(r) : "?");
     }
+    CU(h, cudaEventRecord(h->ev1, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->timers.allreduce_ms = ms;
     return 0;
 }

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GPI_LIB") or os.path.join(_HERE, "libgpifdtd.so")   # GPI_LIB: a tuning variant of the same library
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 ACOUSTIC, ELASTIC = 0, 1
 MODE = {"forward": 0, "forward_save": 1, "adjoint": 2}
 RUN_BORN = 0x100                     # OR into the mode: FD-Born scattering sources from pw 1 into pw 2
@@ -49,7 +49,8 @@ class GpiConfig(C.Structure):
 class GpiTimers(C.Structure):
     _fields_ = [("run_ms", C.c_double), ("steps", C.c_double), ("cell_updates", C.c_double),
                 ("stencil_ms", C.c_double), ("launches", C.c_double),
-                ("vel_ms", C.c_double), ("vel_n", C.c_double), ("stress_ms", C.c_double), ("stress_n", C.c_double)]
+                ("vel_ms", C.c_double), ("vel_n", C.c_double), ("stress_ms", C.c_double), ("stress_n", C.c_double),
+                ("exch_ms", C.c_double), ("exch_n", C.c_double), ("allreduce_ms", C.c_double)]
 
 
 def face_mask(faces) -> int:
@@ -82,6 +83,10 @@ def load_library(path: str = LIB_PATH):
             f"{path} is missing: build it with geophyinv.jl_b200/csrc/build.sh (or __graft_entry__.build()). "
             "The engine has no CPU fallback.")
     lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    # "CUDA or an error": GPI_LIB may name a tuning variant of this library, never the CPU emulation tests/emu builds
+    # (it exports gpi_emu_marker); the emulation tests opt in with GPI_TESTS_ALLOW_EMU=1.
+    if hasattr(lib, "gpi_emu_marker") and os.environ.get("GPI_TESTS_ALLOW_EMU") != "1":
+        raise RuntimeError(f"{path} is the CPU emulation of the engine (test infrastructure); the product loads the CUDA library only")
     fp, ip, i64p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
     vp = C.c_void_p
     sig = {

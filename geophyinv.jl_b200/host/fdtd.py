@@ -346,7 +346,7 @@ class PFdtd:
                     # frequency bounds (source.jl:204-216): the reference evaluates them for every pw but keeps those of pw 1 only
                     # (source.jl:229), so the spectra of the other wavefields' wavelets (the adjoint sources: nt x nr per
                     # supersource and gradient) are not computed here; one spectrum serves min, max and peak
-                    if ipw == 0 and w.size and float(np.abs(w).max()) > 1e-8:   # !all(isapprox.(w, 0)) with numpy's atol, one pass
+                    if ipw == 0 and w.size and w.any():   # !all(isapprox.(w, 0.0)) (source.jl:45): Julia's default atol is 0, so only exactly-zero wavelets are empty
                         fmin, fmax, fpeak = findfreq_all(w, s.grid)
                         freqmax = min(fmax, freqmax)
                         freqmin = max(fmin, freqmin)
@@ -418,6 +418,10 @@ class PFdtd:
         if mode == "adjoint" and c.ic["npw"] == 2 and 2 in upa["activepw"]:
             if self._nccl:
                 self.engine.allreduce_gradients()
+            elif getattr(self, "nworker", 1) > 1 and not getattr(self, "partial_gradients_ok", False):
+                # the reference's sum_grads! always stacks over ALL workers (gradient.jl:2-11, propagate.jl:110-117)
+                raise RuntimeError("sharded adjoint run (nworker > 1) without a communicator: call init_nccl / dist.attach_nccl first, "
+                                   "or set pa.partial_gradients_ok = True to read this rank's partial gradient on purpose")
             self._grad_dirty = True
             for name in c.mparams:
                 c.gradients[name][...] = self.engine.get_gradient(name)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GPI_ABI_VERSION 1
+#define GPI_ABI_VERSION 2
 
 /* ---- enumerations -------------------------------------------------------------------------- */
 
@@ -122,6 +122,10 @@ typedef struct gpi_timers {
      * default 16; pw 1 launches only): summed duration and number of sampled launches */
     double vel_ms, vel_n;     /* fused velocity kernel  (update_dstress! + update_v!)  */
     double stress_ms, stress_n; /* fused stress kernel  (update_dv! + update_stress!)  */
+    /* ABI 2: multi-GPU phases.  exch_*: z-slab halo exchanges sampled like the kernels (time the compute stream waits
+     * for / spends in the exchange of one half step); allreduce_ms: device time of the last gpi_allreduce_gradients */
+    double exch_ms, exch_n;
+    double allreduce_ms;
 } gpi_timers;
 
 typedef struct gpi_handle gpi_handle;

@@ -8,13 +8,18 @@
 #
 # Conventions: Julia arrays are column-major [z,(y),x] Float32 -- exactly what the ABI takes; sparse matrices
 # are `SparseMatrixCSC{Float32,Int64}` whose `colptr/rowval/nzval` are passed as they are (1-based).
+#
+# Loading: `include("GPIFdtdB200.jl")` from inside `module GeoPhyInv` (after src/fdtd/fdtd.jl, so that the names below exist).  A
+# submodule does not see its parent's bindings, so everything it uses from GeoPhyInv is imported explicitly:
+#   FdtdElastic (src/physics_types.jl:17-49), _fd_order / _fd_npml / _fd_nbound / _fd_npextend (src/GeoPhyInv.jl:85-92).
 module GPIFdtdB200
 
 using SparseArrays
+using ..GeoPhyInv: FdtdElastic, _fd_order, _fd_npml, _fd_nbound, _fd_npextend
 
 const LIB = get(ENV, "GPI_LIB", joinpath(@__DIR__, "..", "geophyinv.jl_b200", "libgpifdtd.so"))
 
-const ABI_VERSION = Int32(1)
+const ABI_VERSION = Int32(2)
 const FIELDS = [:p, :vx, :vy, :vz, :tauxx, :tauyy, :tauzz, :tauxy, :tauxz, :tauyz,
     :dpdx, :dpdy, :dpdz, :dvxdx, :dvydy, :dvzdz, :dvxdy, :dvxdz, :dvydx, :dvydz, :dvzdx, :dvzdy,
     :dtauxxdx, :dtauyydy, :dtauzzdz, :dtauxydx, :dtauxydy, :dtauxzdx, :dtauxzdz, :dtauyzdy, :dtauyzdz]
@@ -23,6 +28,10 @@ const PARAMS = Dict(:invK => 0, :rho => 1, :invlambda => 2, :invmu => 3)
 const FACES = Dict(:zmin => 1, :zmax => 2, :ymin => 4, :ymax => 8, :xmin => 16, :xmax => 32)
 face_mask(faces) = Int32(mapreduce(f -> get(FACES, f, 0), |, faces; init = 0))
 const MODES = Dict(:forward => 0, :forward_save => 1, :adjoint => 2)
+# OR-ed into the mode of gpi_run (include/gpifdtd.h): FD-Born scattering sources pw 1 -> pw 2 (FdtdAcoustic{Born}, born.jl:1-12);
+# exact-transpose rho imaging for LinearMap's adjoint (combine_gmodrho! without the one-cell shift, gradient.jl:53-56)
+const GPI_RUN_BORN = Int32(0x100)
+const GPI_RUN_UNSHIFTED_RHO = Int32(0x200)
 
 # mirrors `gpi_config` (include/gpifdtd.h); isbits, passed by reference
 struct GpiConfig
@@ -127,11 +136,17 @@ reset!(e::Engine, what) = check(e, ccall((:gpi_reset, LIB), Cint, (Ptr{Cvoid}, C
 
 # ---- mod_x_proc!(pac, pap, activepw, src_flags)  (src/fdtd/propagate.jl:138-261) ---------------------------------
 # the whole shot loop x time loop of this worker; blocking like the reference's remotecall_wait
-function mod_x_proc!(e::Engine, pac, activepw, src_flags)
+# `mode_flags`: GPI_RUN_BORN for `FdtdAcoustic{Born}` forward runs (propagate.jl:53-60 selects activepw = [1, 2]),
+# GPI_RUN_UNSHIFTED_RHO for the adjoint of `LinearMap(pa)` (func_grad.jl:106-120); by default Born runs are recognised from the
+# attribute's type parameter the way the reference dispatches add_born_sources_*! (born.jl:1-12).
+function mod_x_proc!(e::Engine, pac, activepw, src_flags; mode_flags::Integer = default_mode_flags(pac))
     am = mapreduce(p -> 1 << (p - 1), |, activepw; init = 0)
     sm = mapreduce(i -> src_flags[i] ? 1 << (i - 1) : 0, |, eachindex(src_flags); init = 0)
-    check(e, ccall((:gpi_run, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint), e.h, MODES[pac.attrib_mod.mode], am, sm))
+    mode = Int32(MODES[pac.attrib_mod.mode]) | Int32(mode_flags)
+    check(e, ccall((:gpi_run, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint), e.h, mode, am, sm))
 end
+default_mode_flags(pac) =
+    (occursin("Born", string(typeof(pac.attrib_mod))) && pac.attrib_mod.mode != :adjoint) ? GPI_RUN_BORN : Int32(0)
 
 # ---- update_datamat!(rfield, ipw, pac, pap)  (src/fdtd/receiver.jl:17-34): ONE copy per (shot, field) -------------
 function update_datamat!(e::Engine, datamat, rfield::Symbol, ipw, issp, iss, nr)
@@ -243,9 +258,10 @@ synchronize(e::Engine) = check(e, ccall((:gpi_synchronize, LIB), Cint, (Ptr{Cvoi
 struct GpiTimers
     run_ms::Float64; steps::Float64; cell_updates::Float64; stencil_ms::Float64; launches::Float64
     vel_ms::Float64; vel_n::Float64; stress_ms::Float64; stress_n::Float64
+    exch_ms::Float64; exch_n::Float64; allreduce_ms::Float64
 end
 function timers(e::Engine)
-    t = Ref(GpiTimers(0, 0, 0, 0, 0, 0, 0, 0, 0))
+    t = Ref(GpiTimers(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0))
     check(e, ccall((:gpi_get_timers, LIB), Cint, (Ptr{Cvoid}, Ref{GpiTimers}), e.h, t))
     return t[]
 end

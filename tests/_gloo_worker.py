@@ -41,6 +41,12 @@ def main():
     pg = O.OraclePFdtd(G.FdtdAcoustic("forward_save"), **kwg, nworker=world, rank=rank)
     m = pg.get_modelvector()
     g = np.zeros_like(m)
+    try:                                  # a sharded adjoint run without a communicator must not hand out a partial gradient silently
+        G.gradient(g.copy(), m, dobs, pg)
+        raise AssertionError("expected the partial-gradient guard to fire")
+    except RuntimeError as e:
+        assert "partial" in str(e)
+    pg.partial_gradients_ok = True        # the CPU test sums the partial gradients itself (control-plane all-reduce)
     G.gradient(g, m, dobs, pg)
     gsum = D.allreduce_host([g], dist)[0]
 
@@ -52,6 +58,7 @@ def main():
     pge = O.OraclePFdtd(G.FdtdElastic("forward_save"), **kwe, nworker=world, rank=rank, order=4)
     me = pge.get_modelvector()
     ge = np.zeros_like(me)
+    pge.partial_gradients_ok = True
     G.gradient(ge, me, dobse, pge)
     gesum = D.allreduce_host([ge], dist)[0]
 

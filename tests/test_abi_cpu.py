@@ -34,9 +34,9 @@ def test_every_declared_symbol_is_exported(G, lib):
 
 
 def test_struct_layouts_match_header(G):
-    # gpi_config: 22 int32 (n[3] counted thrice) + 8 doubles; gpi_timers: 9 doubles
+    # gpi_config: 22 int32 (n[3] counted thrice) + 8 doubles; gpi_timers: 12 doubles (ABI 2)
     assert C.sizeof(G.engine.GpiConfig) == 4 * 22 + 8 * 8
-    assert C.sizeof(G.engine.GpiTimers) == 8 * 9
+    assert C.sizeof(G.engine.GpiTimers) == 8 * 12
     assert G.engine.GpiConfig.dt.offset == 88
 
 
@@ -70,7 +70,7 @@ def test_no_gpu_means_error_not_fallback(G, lib):
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
     cfg = G.engine.GpiConfig()
-    cfg.abi_version, cfg.ndims, cfg.physics, cfg.order = 1, 2, 0, 2
+    cfg.abi_version, cfg.ndims, cfg.physics, cfg.order = 2, 2, 0, 2
     cfg.n[0], cfg.n[1], cfg.n[2] = 100, 1, 100
     cfg.nt, cfg.npml, cfg.nbound, cfg.npw, cfg.nshots = 10, 41, 3, 1, 1
     h = C.c_void_p()
@@ -88,7 +88,7 @@ def test_bad_config_rejected(G, lib):
     cfg.abi_version = 99
     assert lib.gpi_create(C.byref(cfg), C.byref(h)) != 0
     assert "ABI" in lib.gpi_last_error(None).decode()
-    cfg.abi_version, cfg.order, cfg.ndims = 1, 8, 2
+    cfg.abi_version, cfg.order, cfg.ndims = 2, 8, 2
     assert lib.gpi_create(C.byref(cfg), C.byref(h)) != 0
     assert "order" in lib.gpi_last_error(None).decode()
     assert lib.gpi_create(None, C.byref(h)) != 0
@@ -166,3 +166,83 @@ def test_machine_code_of_the_measured_kernels_is_unchanged():
     assert len(want) >= 50
     changed = [k for k in want if now.get(k) != want[k]]
     assert not changed, "SASS changed for: " + "; ".join(changed)
+
+
+def _julia_struct(shim, name):
+    """(field, type) list of `struct name ... end` in the Julia shim."""
+    import re
+    body = re.search(r"struct\s+" + name + r"\s*\n(.*?)\nend", shim, re.S).group(1)
+    out = []
+    for stmt in re.split(r"[;\n]", body):
+        stmt = stmt.split("#")[0].strip()
+        if stmt:
+            f, t = stmt.split("::")
+            out.append((f.strip(), t.strip()))
+    return out
+
+
+def _c_struct(hdr, name):
+    """(field, ctype, count) list of `typedef struct name { ... } name;` in include/gpifdtd.h."""
+    import re
+    body = re.search(r"typedef struct " + name + r"\s*\{(.*?)\}\s*" + name + ";", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for stmt in body.split(";"):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        ctype, rest = stmt.split(None, 1)
+        for decl in rest.split(","):
+            m = re.match(r"\s*(\w+)\s*(?:\[(\d+)\])?\s*$", decl)
+            out.append((m.group(1), ctype, int(m.group(2) or 1)))
+    return out
+
+
+def test_struct_layouts_agree_across_header_ctypes_and_julia(G):
+    """Struct drift is the silent failure of a ccall binding: `gpi_config` and `gpi_timers` must have the same fields, in the same order,
+    at the same byte offsets in include/gpifdtd.h, in the ctypes mirror (engine.py) and in julia/GPIFdtdB200.jl (isbits structs follow
+    the C layout rules), and the three must agree on the ABI version."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "gpifdtd.h")).read()
+    shim = open(os.path.join(ROOT, "julia", "GPIFdtdB200.jl")).read()
+    csize = {"int32_t": 4, "double": 8}
+    jsize = {"Int32": (4, 4), "Float64": (8, 8), "NTuple{3,Int32}": (12, 4), "NTuple{3,Float64}": (24, 8)}
+    for cname, jname, ct in (("gpi_config", "GpiConfig", G.engine.GpiConfig), ("gpi_timers", "GpiTimers", G.engine.GpiTimers)):
+        # header -> offsets (natural alignment)
+        off, want = 0, []
+        for f, t, n in _c_struct(hdr, cname):
+            a = csize[t]
+            off = (off + a - 1) // a * a
+            want.append((f, off, a * n))
+            off += a * n
+        got = [(f, getattr(ct, f).offset, getattr(ct, f).size) for f, _ in ct._fields_]
+        assert got == want, (cname, got, want)
+        off, jl = 0, []
+        for f, t in _julia_struct(shim, jname):
+            size, a = jsize[t]
+            off = (off + a - 1) // a * a
+            jl.append((f, off, size))
+            off += size
+        assert jl == want, (jname, jl, want)
+    abi_h = int(re.search(r"#define GPI_ABI_VERSION (\d+)", hdr).group(1))
+    abi_j = int(re.search(r"const ABI_VERSION = Int32\((\d+)\)", shim).group(1))
+    assert abi_h == abi_j == G.engine.ABI_VERSION
+
+
+def test_julia_shim_is_loadable_as_a_submodule():
+    """Textual checks of what made the round-1 shim unloadable: a submodule does not see its parent's bindings, so every GeoPhyInv
+    name the shim uses must be imported with `using ..GeoPhyInv: ...`; Born / unshifted runs must be reachable through mod_x_proc!."""
+    import re
+    shim = open(os.path.join(ROOT, "julia", "GPIFdtdB200.jl")).read()
+    code = "\n".join(l.split("#")[0] for l in shim.splitlines())
+    imported = re.search(r"using \.\.GeoPhyInv:\s*([^\n]+)", code).group(1).replace(" ", "").split(",")
+    for name in ("FdtdElastic", "_fd_order", "_fd_npml", "_fd_nbound", "_fd_npextend"):
+        assert (re.search(r"\b" + name + r"\b", code.replace("using ..GeoPhyInv:", "")) is None) or name in imported, name
+    used = set(re.findall(r"\b(_fd_\w+|Fdtd\w+)\b", code))
+    assert used <= set(imported), used - set(imported)
+    assert "mode_flags" in code and "GPI_RUN_BORN" in code and "GPI_RUN_UNSHIFTED_RHO" in code
+    hdr = open(os.path.join(ROOT, "include", "gpifdtd.h")).read()
+    for name in ("GPI_RUN_BORN", "GPI_RUN_UNSHIFTED_RHO"):
+        hv = int(re.search(r"#define " + name + r" (0x[0-9a-fA-F]+)", hdr).group(1), 16)
+        jv = int(re.search(r"const " + name + r" = Int32\((0x[0-9a-fA-F]+)\)", shim).group(1), 16)
+        assert hv == jv

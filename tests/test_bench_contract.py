@@ -34,8 +34,10 @@ def test_measured_peak_falls_back(tmp_path):
 def test_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the CPU restatement with all host threads on a bounded sample): one JSON line with the base
     contract's keys, `impl: reference`, a `cpu_baseline` describing the run and a zero-copy `e2e`."""
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm must use the host's cores all the same (round-1 defect)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c3small", "--steps", "1",
-                        "--warmup", "0", "--cpu-steps", "2"], capture_output=True, text=True, timeout=600)
+                        "--warmup", "0", "--cpu-steps", "2"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)
@@ -46,3 +48,8 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["cpu_baseline"]["cores"] == bench.host_threads()
+    # the same `config` keys as our arm prints (the driver compares the two arms' configs)
+    wl = {"label": "x"}
+    assert set(d["config"]) == set(bench.bench_config(wl, 2, 1, [1, 1, 1], 1, 1, 1))
+    assert d["config"]["time_steps_per_step"] == 200 and d["cpu_baseline"]["sample_time_steps"] == 2

@@ -80,7 +80,7 @@ def test_product_library_is_not_the_emulation(emu_lib):
 
 
 def test_engine_host_code_and_kernels_match_the_oracle_on_the_cpu(emu_lib):
-    env = dict(os.environ, GPI_LIB=emu_lib, OMP_WAIT_POLICY="passive")
+    env = dict(os.environ, GPI_LIB=emu_lib, GPI_TESTS_ALLOW_EMU="1", OMP_WAIT_POLICY="passive")
     env.pop("GPI_PINGPONG", None)
     r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-s", "-p", "no:cacheprovider"] + SELECTION,
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
