@@ -34,6 +34,30 @@
 
 namespace gpi {
 
+// ---- float literals of the reference's @parallel kernels ------------------------------------------------------------
+// The @av_* macros carry `* 0.5` / `* 0.25` and the order-4 differences `* 27.0` (diff2D.jl, diff3D.jl).  ParallelStencil's
+// @parallel retypes the float literals of a kernel to the number type the package was initialised with
+// (@init_parallel_stencil(Threads, Float32, N), src/GeoPhyInv.jl:95-100), so in the reference's Float32 build these
+// expressions are pure Float32: wide_t = float (default).  -DGPI_LITERALS_F64 evaluates them in Float64 with one rounding at
+// the store (plain Julia promotion of a Float64 literal; what round 1 shipped).  tests/test_reference_pinned.py holds the
+// engine to fixtures evaluated from the reference's own kernel text in the default typing, bit for bit.  The `2.0` of
+// update_dmod!'s dtM broadcast (medium.jl:164-166) is outside any @parallel kernel and stays Float64 in both.
+#ifdef GPI_LITERALS_F64
+typedef double wide_t;
+__device__ __forceinline__ wide_t wmul(wide_t a, wide_t b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ wide_t wadd(wide_t a, wide_t b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ wide_t wsub(wide_t a, wide_t b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ wide_t wdiv(wide_t a, wide_t b) { return __ddiv_rn(a, b); }
+#else
+typedef float wide_t;
+__device__ __forceinline__ wide_t wmul(wide_t a, wide_t b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ wide_t wadd(wide_t a, wide_t b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ wide_t wsub(wide_t a, wide_t b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ wide_t wdiv(wide_t a, wide_t b) { return __fdiv_rn(a, b); }
+#endif
+// dt / (s * lit): store_invav*! (medium.jl:191-221) with s the Float32 sum of the macro
+__device__ __forceinline__ float inv_av(float dt, float s, float lit) { return (float)wdiv((wide_t)dt, wmul((wide_t)s, (wide_t)lit)); }
+
 enum { ZMIN = 1, ZMAX = 2, YMIN = 4, YMAX = 8, XMIN = 16, XMAX = 32 };
 
 // tau slots inside a wavefield set
@@ -444,6 +468,7 @@ __global__ void __launch_bounds__(256) k_stress(const Geom g, const StepArgs a) 
 // `inv(a) + 2.0*inv(b)` carry Float64 literals, so those are evaluated in double and rounded once.
 // mod slots: 0 invK|invlambda, 1 rho, 2 invmu
 // ------------------------------------------------------------------------------------------------
+
 template <int ND, int EL>
 __global__ void k_dmod(const Geom g, const float* __restrict__ m0, const float* __restrict__ rho,
                        const float* __restrict__ imu, float* const* __restrict__ out, float dt) {
@@ -453,15 +478,14 @@ __global__ void k_dmod(const Geom g, const float* __restrict__ m0, const float* 
     k += g.koff;                                // global z index for the range predicates
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
     const int nz = g.nz, ny = g.ny, nx = g.nx;
-    const double ddt = (double)dt;
     const bool iny = (ND == 2) || (j >= 1 && j <= ny - 2);
     const bool inyh = (ND == 2) || (j >= 1 && j <= ny - 1);
     if (k >= 1 && k <= nz - 2 && iny && i >= 1 && i <= nx - 1)         // @av_xi(rho) on the vx interior
-        out[C_BX][c] = (float)(ddt / ((double)__fadd_rn(rho[c - sx], rho[c]) * 0.5));
+        out[C_BX][c] = inv_av(dt, __fadd_rn(rho[c - sx], rho[c]), 0.5f);
     if (k >= 1 && k <= nz - 1 && iny && i >= 1 && i <= nx - 2)         // @av_zi(rho)
-        out[C_BZ][c] = (float)(ddt / ((double)__fadd_rn(rho[c - 1], rho[c]) * 0.5));
+        out[C_BZ][c] = inv_av(dt, __fadd_rn(rho[c - 1], rho[c]), 0.5f);
     if (ND == 3 && k >= 1 && k <= nz - 2 && inyh && i >= 1 && i <= nx - 2)   // @av_yi(rho)
-        out[C_BY][c] = (float)(ddt / ((double)__fadd_rn(rho[c - sy], rho[c]) * 0.5));
+        out[C_BY][c] = inv_av(dt, __fadd_rn(rho[c - sy], rho[c]), 0.5f);
     const bool nin = k <= nz - 1 && (ND == 2 || j <= ny - 1) && i <= nx - 1;
     if (nin) {
         if (!EL) out[C_K][c] = __fmul_rn(__fdiv_rn(1.0f, m0[c]), dt);                                  // dtK
@@ -475,20 +499,20 @@ __global__ void k_dmod(const Geom g, const float* __restrict__ m0, const float* 
         if (ND == 2) {
             if (k >= 1 && k <= nz - 1 && i >= 1 && i <= nx - 1) {      // @av(invmu) (diff2D.jl:222-225)
                 const float s = __fadd_rn(__fadd_rn(__fadd_rn(imu[c - 1 - sx], imu[c - sx]), imu[c - 1]), imu[c]);
-                out[C_MUXZ][c] = (float)(ddt / ((double)s * 0.25));
+                out[C_MUXZ][c] = inv_av(dt, s, 0.25f);
             }
         } else {
             if (k >= 1 && k <= nz - 1 && j >= 1 && j <= ny - 2 && i >= 1 && i <= nx - 1) {   // @av_xzi
                 const float s = __fadd_rn(__fadd_rn(__fadd_rn(imu[c - 1 - sx], imu[c - sx]), imu[c - 1]), imu[c]);
-                out[C_MUXZ][c] = (float)(ddt / ((double)s * 0.25));
+                out[C_MUXZ][c] = inv_av(dt, s, 0.25f);
             }
             if (k >= 1 && k <= nz - 2 && j >= 1 && j <= ny - 1 && i >= 1 && i <= nx - 1) {   // @av_xyi
                 const float s = __fadd_rn(__fadd_rn(__fadd_rn(imu[c - sy - sx], imu[c - sx]), imu[c - sy]), imu[c]);
-                out[C_MUXY][c] = (float)(ddt / ((double)s * 0.25));
+                out[C_MUXY][c] = inv_av(dt, s, 0.25f);
             }
             if (k >= 1 && k <= nz - 1 && j >= 1 && j <= ny - 1 && i >= 1 && i <= nx - 2) {   // @av_yzi
                 const float s = __fadd_rn(__fadd_rn(__fadd_rn(imu[c - 1 - sy], imu[c - sy]), imu[c - 1]), imu[c]);
-                out[C_MUYZ][c] = (float)(ddt / ((double)s * 0.25));
+                out[C_MUYZ][c] = inv_av(dt, s, 0.25f);
             }
         }
     }
@@ -541,13 +565,13 @@ __global__ void k_post(const Geom g, const PostDesc* __restrict__ descs, int it 
             if (op.kind == 1) {
                 const float add = __fmul_rn(buf, op.coef[c]);        // pw = pw + (pv * dtK)
                 for (int t = 0; t < op.ntarget; t++) op.target[t][c + woff] = __fadd_rn(op.target[t][c + woff], add);
-            } else {                                                 // pw = pw + (pv / av(rho) * dt), Float64 as in the reference
+            } else {                                                 // pw = pw + (pv / av(rho) * dt), literal typing as in the reference (wide_t)
                 const long long off = op.axis == 0 ? 1 : (op.axis == 1 ? sy : sx);
                 const float s = __fadd_rn(op.coef[c - (g.h + 1) * off], op.coef[c - g.h * off]);     // @av_?i: integer nodes u-1-h, u-h
                 float* t = op.target[0] + woff;
-                // Float64 as in the reference, every operation rounded on its own (nvcc would otherwise be free to contract the
-                // product and the sum into one fma, which the CPU path does not do)
-                t[c] = (float)__dadd_rn((double)t[c], __dmul_rn(__ddiv_rn((double)buf, __dmul_rn((double)s, 0.5)), (double)dt));
+                // every operation rounded on its own (nvcc would otherwise be free to contract the product and the sum into one fma,
+                // which the CPU path does not do)
+                t[c] = (float)wadd((wide_t)t[c], wmul(wdiv((wide_t)buf, wmul((wide_t)s, (wide_t)0.5f)), (wide_t)dt));
             }
         }
     }
@@ -632,7 +656,7 @@ __global__ void k_grad2d(const Geom g, const float* __restrict__ p1, const float
         auto bufz = [&](int kk, int ii) { const long long q = w + uidx(g, kk, 0, ii);
             return (kk >= 1 && kk <= g.nz - 1 && ii >= 1 && ii <= g.nx - 2) ? __fmul_rn(__fmul_rn(vz2tp[q], __fsub_rn(vz1[q], vz1tp[q])), dtI) : 0.f; };
         const float ax = __fadd_rn(bufx(k, i), bufx(k, i + 1)), az = __fadd_rn(bufz(k, i), bufz(k + 1, i));
-        gR[gw + c] = (float)((double)gR[gw + c] - (double)ax * 0.5 - (double)az * 0.5);
+        gR[gw + c] = (float)wsub(wsub((wide_t)gR[gw + c], wmul((wide_t)ax, (wide_t)0.5f)), wmul((wide_t)az, (wide_t)0.5f));
         return;
     }
     const int o = 1 + 2 * g.h;                           // @inn(g): tauii nodes [O, n-1-O]
@@ -643,7 +667,7 @@ __global__ void k_grad2d(const Geom g, const float* __restrict__ p1, const float
         const long long q1 = 3 * g.h + 1, q0 = 3 * g.h;
         const float ax = __fadd_rn(bufx(c - q1 * sx), bufx(c - q0 * sx));
         const float az = __fadd_rn(bufz(c - q1), bufz(c - q0));      // @av_zi(vzbuffer)
-        gR[gw + c] = (float)((double)gR[gw + c] - (double)ax * 0.5 - (double)az * 0.5);
+        gR[gw + c] = (float)wsub(wsub((wide_t)gR[gw + c], wmul((wide_t)ax, (wide_t)0.5f)), wmul((wide_t)az, (wide_t)0.5f));
     }
 }
 
@@ -698,7 +722,7 @@ __global__ void k_grad2d_el(const Geom g, const GradE2Args a, float dtI) {
         const long long q1 = 3 * g.h + 1, q0 = 3 * g.h;
         const float ax = __fadd_rn(bufx(c - q1 * sx), bufx(c - q0 * sx));
         const float az = __fadd_rn(bufz(c - q1), bufz(c - q0));
-        a.gR[gw + c] = (float)((double)a.gR[gw + c] - (double)ax * 0.5 - (double)az * 0.5);
+        a.gR[gw + c] = (float)wsub(wsub((wide_t)a.gR[gw + c], wmul((wide_t)ax, (wide_t)0.5f)), wmul((wide_t)az, (wide_t)0.5f));
     }
 }
 
@@ -766,7 +790,7 @@ __global__ void k_grad3d_el(const Geom g, const GradE3Args a, float dtI) {
         const float ax = __fadd_rn(buf(V_X, c - q1 * sx), buf(V_X, c - q0 * sx));
         const float ay = __fadd_rn(buf(V_Y, c - q1 * sy), buf(V_Y, c - q0 * sy));
         const float az = __fadd_rn(buf(V_Z, c - q1), buf(V_Z, c - q0));
-        a.gR[c] = (float)((double)a.gR[c] - (double)ax * 0.5 - (double)ay * 0.5 - (double)az * 0.5);
+        a.gR[c] = (float)wsub(wsub(wsub((wide_t)a.gR[c], wmul((wide_t)ax, (wide_t)0.5f)), wmul((wide_t)ay, (wide_t)0.5f)), wmul((wide_t)az, (wide_t)0.5f));
     }
 }
 
@@ -795,7 +819,7 @@ __global__ void k_grad3d(const Geom g, const Grad3Args a, float dtI, int unshift
         auto by = [&](int jj) { return (k >= 1 && k <= g.nz - 2 && jj >= 1 && jj <= g.ny - 1 && i >= 1 && i <= g.nx - 2) ? buf(V_Y, uidx(g, k, jj, i)) : 0.f; };
         auto bz = [&](int kk) { return (kk >= 1 && kk <= g.nz - 1 && j >= 1 && j <= g.ny - 2 && i >= 1 && i <= g.nx - 2) ? buf(V_Z, uidx(g, kk, j, i)) : 0.f; };
         const float ax = __fadd_rn(bx(i), bx(i + 1)), ay = __fadd_rn(by(j), by(j + 1)), az = __fadd_rn(bz(k), bz(k + 1));
-        a.gR[c] = (float)((double)a.gR[c] - (double)ax * 0.5 - (double)ay * 0.5 - (double)az * 0.5);
+        a.gR[c] = (float)wsub(wsub(wsub((wide_t)a.gR[c], wmul((wide_t)ax, (wide_t)0.5f)), wmul((wide_t)ay, (wide_t)0.5f)), wmul((wide_t)az, (wide_t)0.5f));
         return;
     }
     const int o = 1 + 2 * g.h;
@@ -804,7 +828,7 @@ __global__ void k_grad3d(const Geom g, const Grad3Args a, float dtI, int unshift
         const float ax = __fadd_rn(buf(V_X, c - q1 * sx), buf(V_X, c - q0 * sx));
         const float ay = __fadd_rn(buf(V_Y, c - q1 * sy), buf(V_Y, c - q0 * sy));
         const float az = __fadd_rn(buf(V_Z, c - q1), buf(V_Z, c - q0));
-        a.gR[c] = (float)((double)a.gR[c] - (double)ax * 0.5 - (double)ay * 0.5 - (double)az * 0.5);
+        a.gR[c] = (float)wsub(wsub(wsub((wide_t)a.gR[c], wmul((wide_t)ax, (wide_t)0.5f)), wmul((wide_t)ay, (wide_t)0.5f)), wmul((wide_t)az, (wide_t)0.5f));
     }
 }
 

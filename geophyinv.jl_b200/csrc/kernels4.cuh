@@ -14,9 +14,9 @@
 //         J  inner nodes                      -> u = ix-1+O      range [O,   n-1-O]
 //   * a difference onto a half node u from integer-type neighbours is  27 f(u) - 27 f(u-1) + f(u-2) - f(u+1),
 //     onto an integer node u from half-type neighbours  27 f(u+1) - 27 f(u) + f(u-1) - f(u+2)  (the 1/24 is in
-//     d?I, fdtd.jl:318-319).  The reference's `27.0` literals promote the expression to Float64 and the store
-//     rounds once; d4() does exactly that with __dmul_rn/__dadd_rn (no contraction), so the results match the CPU
-//     restatement bit for bit;
+//     d?I, fdtd.jl:318-319).  The `27.0` literals take the kernel number type under ParallelStencil's @parallel (wide_t in
+//     kernels.cuh: Float32 by default, Float64 with -DGPI_LITERALS_F64); d4() evaluates the macro's operations one by one in that
+//     type (no contraction), so the results match the reference's kernel text bit for bit (tests/test_reference_pinned.py);
 //   * `@av_?i` averages are NOT centred at order 4 (their `+ 1` neighbour does not scale with the order):
 //     node u of a half-type axis averages the integer nodes u-1-h and u-h.  Reproduced as upstream has it;
 //   * one thread per cell, derivatives in registers, CPML in the same pass (slab-indexed coefficients for all three
@@ -30,9 +30,9 @@
 constexpr int O4 = 3, H4 = 1;
 
 __device__ __forceinline__ float d4(float hi1, float lo1, float lo2, float hi2, float sI) {
-    const double a = __dsub_rn(__dmul_rn((double)hi1, 27.0), __dmul_rn((double)lo1, 27.0));
-    const double b = __dsub_rn(__dadd_rn(a, (double)lo2), (double)hi2);
-    return (float)__dmul_rn(b, (double)sI);
+    const wide_t a = wsub(wmul((wide_t)hi1, (wide_t)27.0f), wmul((wide_t)lo1, (wide_t)27.0f));
+    const wide_t b = wsub(wadd(a, (wide_t)lo2), (wide_t)hi2);
+    return (float)wmul(b, (wide_t)sI);
 }
 // onto a half-type node from integer-type neighbours (`@d_?i` of tauii/p/v along a non-staggered axis)
 __device__ __forceinline__ float dH(const float* __restrict__ f, long long c, long long s, float sI) {
@@ -314,15 +314,14 @@ __global__ void k_dmod4(const Geom g, const float* __restrict__ m0, const float*
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
     const int nz = g.nz, ny = g.ny, nx = g.nx;
     const int k = ks - H4, j = ND == 3 ? js - H4 : 0, i = is - H4;
-    const double ddt = (double)dt;
     const bool jJ = ND == 2 || inJ(j, ny), jH = ND == 2 || inH(j, ny);
     const long long lo = -(H4 + 1), hi = -H4;            // the two averaged integer nodes, in node steps
     if (inJ(k, nz) && jJ && inH(i, nx))                  // @av_xi(rho) on the vx interior
-        out[C_BX][c] = (float)(ddt / ((double)__fadd_rn(rho[c + lo * sx], rho[c + hi * sx]) * 0.5));
+        out[C_BX][c] = inv_av(dt, __fadd_rn(rho[c + lo * sx], rho[c + hi * sx]), 0.5f);
     if (inH(k, nz) && jJ && inJ(i, nx))                  // @av_zi(rho)
-        out[C_BZ][c] = (float)(ddt / ((double)__fadd_rn(rho[c + lo], rho[c + hi]) * 0.5));
+        out[C_BZ][c] = inv_av(dt, __fadd_rn(rho[c + lo], rho[c + hi]), 0.5f);
     if (ND == 3 && inJ(k, nz) && jH && inJ(i, nx))       // @av_yi(rho)
-        out[C_BY][c] = (float)(ddt / ((double)__fadd_rn(rho[c + lo * sy], rho[c + hi * sy]) * 0.5));
+        out[C_BY][c] = inv_av(dt, __fadd_rn(rho[c + lo * sy], rho[c + hi * sy]), 0.5f);
     const bool nin = inI(k, nz) && (ND == 2 || inI(j, ny)) && inI(i, nx);
     if (nin) {
         if (!EL) out[C_K][c] = __fmul_rn(__fdiv_rn(1.0f, m0[c]), dt);
@@ -335,7 +334,7 @@ __global__ void k_dmod4(const Geom g, const float* __restrict__ m0, const float*
     if (EL) {
         auto av4 = [&](long long sa, long long sb) {     // A[a,b] + A[a+1,b] + A[a,b+1] + A[a+1,b+1], a = first listed axis
             const float s = __fadd_rn(__fadd_rn(__fadd_rn(imu[c + lo * sa + lo * sb], imu[c + hi * sa + lo * sb]), imu[c + lo * sa + hi * sb]), imu[c + hi * sa + hi * sb]);
-            return (float)(ddt / ((double)s * 0.25));
+            return inv_av(dt, s, 0.25f);
         };
         if (inH(k, nz) && jJ && inH(i, nx)) out[C_MUXZ][c] = av4(1, sx);                       // @av / @av_xzi: (z, x)
         if (ND == 3) {

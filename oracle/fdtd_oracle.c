@@ -15,12 +15,17 @@
  *   - one loop nest per ParallelStencil `@parallel` kernel, each assignment guarded like
  *     `@within` (src/fdtd/diff2D.jl:17-28, diff3D.jl:17-34): unfused derivative sweep ->
  *     CPML sweeps -> update sweep, in the order of src/fdtd/propagate.jl:170-247;
- *   - Float32 arithmetic without FMA contraction (compile with -ffp-contract=off), with the
- *     Float64 promotions the reference's Float64 literals cause (diff2D.jl:222-233 `* 0.5`,
- *     medium.jl:165 `2.0 *`) restated explicitly;
+ *   - Float32 arithmetic without FMA contraction (compile with -ffp-contract=off); float literals inside @parallel
+ *     kernels typed as ParallelStencil types them (see WIDE below), the Float64 promotion of the one literal outside
+ *     a kernel (medium.jl:165 `2.0 *`) restated explicitly;
  *   - OpenMP static schedule over the outermost index = what ParallelStencil's Threads backend does.
  *
- * Build: see oracle/Makefile (REAL=float -> liboracle_f32.so, REAL=double -> liboracle_f64.so).
+ * Build: see oracle/Makefile (REAL=float -> liboracle_f32.so, REAL=double -> liboracle_f64.so,
+ *        REAL=float -DORC_LITERALS_F64 -> liboracle_f32_lit64.so).
+ * Parity status: PINNED to the reference's source text -- tests/golden/from_reference.py evaluates the @parallel bodies,
+ * macros, templated kernels and call sequences parsed out of /root/reference/src with numpy, and
+ * tests/test_reference_pinned.py checks that this file reproduces those fixtures bit for bit (orders 2 and 4, 2-D / 3-D,
+ * acoustic / elastic, forward and forward_save + adjoint + imaging).
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -34,6 +39,20 @@
 
 #ifndef REAL
 #define REAL float
+#endif
+/* Float literals inside `@parallel` kernels (the 0.5 / 0.25 of the @av_* macros, the 27.0 of the order-4 differences).
+ * ParallelStencil's @parallel retypes untyped float literals of a kernel to the number type the package was initialised
+ * with (`literaltypes(numbertype, kernel)`; GeoPhyInv: @init_parallel_stencil(Threads, Float32, N), src/GeoPhyInv.jl:95-100),
+ * so under the shipped Float32 preference these expressions are pure Float32 -- the DEFAULT here (WIDE = REAL).
+ * -DORC_LITERALS_F64 keeps them Float64 (plain Julia promotion: expression in Float64, one rounding at the store), the
+ * reading round 1 took.  Both typings are pinned bit for bit against the reference's source text evaluated in the same
+ * typing (tests/test_reference_pinned.py); they differ by <= 1 ulp per operation (1e-7 relative).
+ * NOT affected: `inv(invl) + 2.0 * inv(invmu)` of update_dmod! (medium.jl:164-166) is a plain Julia broadcast, outside any
+ * @parallel kernel: its 2.0 stays Float64 in both typings. */
+#ifdef ORC_LITERALS_F64
+typedef double WIDE;
+#else
+typedef REAL WIDE;
 #endif
 
 /* ------------------------------------------------------------------------------------------------
@@ -181,7 +200,7 @@ static int imax3(int a, int b, int c) { return imax2(a, imax2(b, c)); }
  * The order is per handle; the entry points copy it into the file-scope g_O before any sweep runs. */
 static inline REAL fd(const REAL* p, size_t s, REAL sI) {
     if (g_O == 1) return (p[s] - p[0]) * sI;
-    return (REAL)(((double)p[2 * s] * 27.0 - (double)p[s] * 27.0 + (double)p[0] - (double)p[3 * s]) * (double)sI);
+    return (REAL)(((WIDE)p[2 * s] * (WIDE)27.0 - (WIDE)p[s] * (WIDE)27.0 + (WIDE)p[0] - (WIDE)p[3 * s]) * (WIDE)sI);
 }
 #define DZ2(a, iz, ix, sI)     fd(&A2(a, iz, ix), 1, sI)
 #define DX2(a, iz, ix, sI)     fd(&A2(a, iz, ix), (size_t)(a).n[0], sI)
@@ -559,23 +578,23 @@ static void update_stress(orc_handle* h, pw_t* pw) {
  * quotient is evaluated in Float64 and rounded on store.
  * ---------------------------------------------------------------------------------------------- */
 static void update_dmod(orc_handle* h) {
-    double dt = (double)h->dt;
+    WIDE dt = (WIDE)h->dt;
     const int O = g_O;                      /* izi = iz + O (diff2D.jl:5-13); the `+ 1` neighbours of the @av macros do not scale with the order */
     arr rho = h->mod[GPI_RHO];
     if (h->nd == 2) {
         arr bx = h->dmod[DM_BX], bz = h->dmod[DM_BZ];
         for (int ix = 1; ix <= bx.n[2]; ix++) for (int iz = 1; iz <= bx.n[0]; iz++)     /* store_invavxi!: @av_xi */
-            A2(bx, iz, ix) = (REAL)(dt / ((double)(REAL)(A2(rho, iz + O, ix) + A2(rho, iz + O, ix + 1)) * 0.5));
+            A2(bx, iz, ix) = (REAL)(dt / ((WIDE)(REAL)(A2(rho, iz + O, ix) + A2(rho, iz + O, ix + 1)) * (WIDE)0.5));
         for (int ix = 1; ix <= bz.n[2]; ix++) for (int iz = 1; iz <= bz.n[0]; iz++)     /* store_invavzi!: @av_zi */
-            A2(bz, iz, ix) = (REAL)(dt / ((double)(REAL)(A2(rho, iz, ix + O) + A2(rho, iz + 1, ix + O)) * 0.5));
+            A2(bz, iz, ix) = (REAL)(dt / ((WIDE)(REAL)(A2(rho, iz, ix + O) + A2(rho, iz + 1, ix + O)) * (WIDE)0.5));
     } else {
         arr bx = h->dmod[DM_BX], by = h->dmod[DM_BY], bz = h->dmod[DM_BZ];
         for (int ix = 1; ix <= bx.n[2]; ix++) for (int iy = 1; iy <= bx.n[1]; iy++) for (int iz = 1; iz <= bx.n[0]; iz++)
-            A3(bx, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(rho, iz + O, iy + O, ix) + A3(rho, iz + O, iy + O, ix + 1)) * 0.5));
+            A3(bx, iz, iy, ix) = (REAL)(dt / ((WIDE)(REAL)(A3(rho, iz + O, iy + O, ix) + A3(rho, iz + O, iy + O, ix + 1)) * (WIDE)0.5));
         for (int ix = 1; ix <= by.n[2]; ix++) for (int iy = 1; iy <= by.n[1]; iy++) for (int iz = 1; iz <= by.n[0]; iz++)
-            A3(by, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(rho, iz + O, iy, ix + O) + A3(rho, iz + O, iy + 1, ix + O)) * 0.5));
+            A3(by, iz, iy, ix) = (REAL)(dt / ((WIDE)(REAL)(A3(rho, iz + O, iy, ix + O) + A3(rho, iz + O, iy + 1, ix + O)) * (WIDE)0.5));
         for (int ix = 1; ix <= bz.n[2]; ix++) for (int iy = 1; iy <= bz.n[1]; iy++) for (int iz = 1; iz <= bz.n[0]; iz++)
-            A3(bz, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(rho, iz, iy + O, ix + O) + A3(rho, iz + 1, iy + O, ix + O)) * 0.5));
+            A3(bz, iz, iy, ix) = (REAL)(dt / ((WIDE)(REAL)(A3(rho, iz, iy + O, ix + O) + A3(rho, iz + 1, iy + O, ix + O)) * (WIDE)0.5));
     }
     if (h->c.physics == GPI_ACOUSTIC) {
         arr K = h->dmod[DM_DTK], iK = h->mod[GPI_INVK];    /* broadcast!(inv, dtK, invK); rmul!(dtK, dt) */
@@ -586,18 +605,18 @@ static void update_dmod(orc_handle* h) {
     for (size_t i = 0; i < L.len; i++) L.d[i] = ((REAL)1 / il.d[i]) * h->dt;
     for (size_t i = 0; i < M.len; i++)   /* inv(invl) + 2.0 * inv(invmu): Float64 sum, rounded on store; then rmul!(dt) */
         M.d[i] = (REAL)((double)((REAL)1 / il.d[i]) + 2.0 * (double)((REAL)1 / im.d[i])) * h->dt;
-    if (h->nd == 2) {          /* store_invav!: @av = 4-point mean * 0.25 (diff2D.jl:222-225) */
+    if (h->nd == 2) {          /* store_invav!: @av = 4-point mean * (WIDE)0.25 (diff2D.jl:222-225) */
         arr mu = h->dmod[DM_MUXZ];
         for (int ix = 1; ix <= mu.n[2]; ix++) for (int iz = 1; iz <= mu.n[0]; iz++)
-            A2(mu, iz, ix) = (REAL)(dt / ((double)(REAL)(A2(im, iz, ix) + A2(im, iz + 1, ix) + A2(im, iz, ix + 1) + A2(im, iz + 1, ix + 1)) * 0.25));
+            A2(mu, iz, ix) = (REAL)(dt / ((WIDE)(REAL)(A2(im, iz, ix) + A2(im, iz + 1, ix) + A2(im, iz, ix + 1) + A2(im, iz + 1, ix + 1)) * (WIDE)0.25));
     } else {                   /* @av_xzi / @av_xyi / @av_yzi (diff3D.jl:339-378) */
         arr m1 = h->dmod[DM_MUXZ], m2 = h->dmod[DM_MUXY], m3 = h->dmod[DM_MUYZ];
         for (int ix = 1; ix <= m1.n[2]; ix++) for (int iy = 1; iy <= m1.n[1]; iy++) for (int iz = 1; iz <= m1.n[0]; iz++)
-            A3(m1, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(im, iz, iy + O, ix) + A3(im, iz + 1, iy + O, ix) + A3(im, iz, iy + O, ix + 1) + A3(im, iz + 1, iy + O, ix + 1)) * 0.25));
+            A3(m1, iz, iy, ix) = (REAL)(dt / ((WIDE)(REAL)(A3(im, iz, iy + O, ix) + A3(im, iz + 1, iy + O, ix) + A3(im, iz, iy + O, ix + 1) + A3(im, iz + 1, iy + O, ix + 1)) * (WIDE)0.25));
         for (int ix = 1; ix <= m2.n[2]; ix++) for (int iy = 1; iy <= m2.n[1]; iy++) for (int iz = 1; iz <= m2.n[0]; iz++)
-            A3(m2, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(im, iz + O, iy, ix) + A3(im, iz + O, iy + 1, ix) + A3(im, iz + O, iy, ix + 1) + A3(im, iz + O, iy + 1, ix + 1)) * 0.25));
+            A3(m2, iz, iy, ix) = (REAL)(dt / ((WIDE)(REAL)(A3(im, iz + O, iy, ix) + A3(im, iz + O, iy + 1, ix) + A3(im, iz + O, iy, ix + 1) + A3(im, iz + O, iy + 1, ix + 1)) * (WIDE)0.25));
         for (int ix = 1; ix <= m3.n[2]; ix++) for (int iy = 1; iy <= m3.n[1]; iy++) for (int iz = 1; iz <= m3.n[0]; iz++)
-            A3(m3, iz, iy, ix) = (REAL)(dt / ((double)(REAL)(A3(im, iz, iy, ix + O) + A3(im, iz + 1, iy, ix + O) + A3(im, iz, iy + 1, ix + O) + A3(im, iz + 1, iy + 1, ix + O)) * 0.25));
+            A3(m3, iz, iy, ix) = (REAL)(dt / ((WIDE)(REAL)(A3(im, iz, iy, ix + O) + A3(im, iz + 1, iy, ix + O) + A3(im, iz, iy + 1, ix + O) + A3(im, iz + 1, iy + 1, ix + O)) * (WIDE)0.25));
     }
 }
 
@@ -616,13 +635,13 @@ static void spmv(arr buf, const csc* S, const REAL* w, int nt, int it) {
 /* muladd_with_density_v{x,y,z}! (source.jl:166-177): @inn(pw) += @inn(pv) / @av_?i(rho) * dt,
  * evaluated in Float64 because @av_?i carries a Float64 literal. */
 static void muladd_with_density(orc_handle* h, arr pw, arr pv, int vfield) {
-    arr rho = h->mod[GPI_RHO]; double dt = (double)h->dt;
+    arr rho = h->mod[GPI_RHO]; WIDE dt = (WIDE)h->dt;
     const int O = g_O;
     if (h->nd == 2) {
         OMP_FOR
         for (int ix = 1; ix <= pw.n[2] - 2 * O; ix++) for (int iz = 1; iz <= pw.n[0] - 2 * O; iz++) {
             REAL s = vfield == GPI_VX ? (REAL)(A2(rho, iz + O, ix) + A2(rho, iz + O, ix + 1)) : (REAL)(A2(rho, iz, ix + O) + A2(rho, iz + 1, ix + O));
-            A2(pw, iz + O, ix + O) = (REAL)((double)A2(pw, iz + O, ix + O) + ((double)A2(pv, iz + O, ix + O) / ((double)s * 0.5) * dt));
+            A2(pw, iz + O, ix + O) = (REAL)((WIDE)A2(pw, iz + O, ix + O) + ((WIDE)A2(pv, iz + O, ix + O) / ((WIDE)s * (WIDE)0.5) * dt));
         }
     } else {
         OMP_FOR
@@ -630,7 +649,7 @@ static void muladd_with_density(orc_handle* h, arr pw, arr pv, int vfield) {
             REAL s = vfield == GPI_VX ? (REAL)(A3(rho, iz + O, iy + O, ix) + A3(rho, iz + O, iy + O, ix + 1))
                    : vfield == GPI_VY ? (REAL)(A3(rho, iz + O, iy, ix + O) + A3(rho, iz + O, iy + 1, ix + O))
                                       : (REAL)(A3(rho, iz, iy + O, ix + O) + A3(rho, iz + 1, iy + O, ix + O));
-            I3(pw) = (REAL)((double)I3(pw) + ((double)I3(pv) / ((double)s * 0.5) * dt));
+            I3(pw) = (REAL)((WIDE)I3(pw) + ((WIDE)I3(pv) / ((WIDE)s * (WIDE)0.5) * dt));
         }
     }
 }
@@ -775,18 +794,18 @@ static void compute_gradient_3d(orc_handle* h, int issp, int unshifted) {
         #define INT3(b, z, y, x) (((z) >= 2 && (z) <= (b).n[0] - 1 && (y) >= 2 && (y) <= (b).n[1] - 1 && (x) >= 2 && (x) <= (b).n[2] - 1) ? A3(b, z, y, x) : (REAL)0)
         OMP_FOR
         for (int ix = 1; ix <= gr.n[2]; ix++) for (int iy = 1; iy <= gr.n[1]; iy++) for (int iz = 1; iz <= gr.n[0]; iz++)
-            A3(gr, iz, iy, ix) = (REAL)((double)A3(gr, iz, iy, ix)
-                - (double)(REAL)(INT3(bx, iz, iy, ix) + INT3(bx, iz, iy, ix + 1)) * 0.5
-                - (double)(REAL)(INT3(by, iz, iy, ix) + INT3(by, iz, iy + 1, ix)) * 0.5
-                - (double)(REAL)(INT3(bz, iz, iy, ix) + INT3(bz, iz + 1, iy, ix)) * 0.5);
+            A3(gr, iz, iy, ix) = (REAL)((WIDE)A3(gr, iz, iy, ix)
+                - (WIDE)(REAL)(INT3(bx, iz, iy, ix) + INT3(bx, iz, iy, ix + 1)) * (WIDE)0.5
+                - (WIDE)(REAL)(INT3(by, iz, iy, ix) + INT3(by, iz, iy + 1, ix)) * (WIDE)0.5
+                - (WIDE)(REAL)(INT3(bz, iz, iy, ix) + INT3(bz, iz + 1, iy, ix)) * (WIDE)0.5);
         return;
     }
     OMP_FOR
     for (int ix = 1; ix <= gr.n[2] - 2 * O; ix++) for (int iy = 1; iy <= gr.n[1] - 2 * O; iy++) for (int iz = 1; iz <= gr.n[0] - 2 * O; iz++)
-        I3(gr) = (REAL)((double)I3(gr)
-            - (double)(REAL)(A3(bx, iz + O, iy + O, ix) + A3(bx, iz + O, iy + O, ix + 1)) * 0.5
-            - (double)(REAL)(A3(by, iz + O, iy, ix + O) + A3(by, iz + O, iy + 1, ix + O)) * 0.5
-            - (double)(REAL)(A3(bz, iz, iy + O, ix + O) + A3(bz, iz + 1, iy + O, ix + O)) * 0.5);
+        I3(gr) = (REAL)((WIDE)I3(gr)
+            - (WIDE)(REAL)(A3(bx, iz + O, iy + O, ix) + A3(bx, iz + O, iy + O, ix + 1)) * (WIDE)0.5
+            - (WIDE)(REAL)(A3(by, iz + O, iy, ix + O) + A3(by, iz + O, iy + 1, ix + O)) * (WIDE)0.5
+            - (WIDE)(REAL)(A3(bz, iz, iy + O, ix + O) + A3(bz, iz + 1, iy + O, ix + O)) * (WIDE)0.5);
 }
 /* 2-D elastic imaging (nothing upstream: gradient.jl has acoustic methods only).  Same adjoint-state
  * construction as gradlame!/gradrho! -- "adjoint field at the previous step times the change of the forward field over the
@@ -837,9 +856,9 @@ static void compute_gradient_el2d(orc_handle* h, int issp) {
     arr bx = p1->vbuf[GPI_VX], bz = p1->vbuf[GPI_VZ];
     OMP_FOR
     for (int ix = 1; ix <= gr.n[2] - 2 * O; ix++) for (int iz = 1; iz <= gr.n[0] - 2 * O; iz++)
-        A2(gr, iz + O, ix + O) = (REAL)((double)A2(gr, iz + O, ix + O)
-            - (double)(REAL)(A2(bx, iz + O, ix) + A2(bx, iz + O, ix + 1)) * 0.5
-            - (double)(REAL)(A2(bz, iz, ix + O) + A2(bz, iz + 1, ix + O)) * 0.5);
+        A2(gr, iz + O, ix + O) = (REAL)((WIDE)A2(gr, iz + O, ix + O)
+            - (WIDE)(REAL)(A2(bx, iz + O, ix) + A2(bx, iz + O, ix + 1)) * (WIDE)0.5
+            - (WIDE)(REAL)(A2(bz, iz, ix + O) + A2(bz, iz + 1, ix + O)) * (WIDE)0.5);
 }
 /* 3-D elastic imaging: the construction of compute_gradient_el2d with the 3-D isotropic compliance
  *     eps = dev(tau) / (2 mu) + tr(tau) / (3 (3 lambda + 2 mu)) I,      c3 = 1 / (3 lambda + 2 mu) = invlambda invmu / (3 invmu + 2 invlambda)
@@ -901,10 +920,10 @@ static void compute_gradient_el3d(orc_handle* h, int issp) {
     arr bx = p1->vbuf[GPI_VX], by = p1->vbuf[GPI_VY], bz = p1->vbuf[GPI_VZ];
     OMP_FOR
     for (int ix = 1; ix <= gr.n[2] - 2 * O; ix++) for (int iy = 1; iy <= gr.n[1] - 2 * O; iy++) for (int iz = 1; iz <= gr.n[0] - 2 * O; iz++)
-        I3(gr) = (REAL)((double)I3(gr)
-            - (double)(REAL)(A3(bx, iz + O, iy + O, ix) + A3(bx, iz + O, iy + O, ix + 1)) * 0.5
-            - (double)(REAL)(A3(by, iz + O, iy, ix + O) + A3(by, iz + O, iy + 1, ix + O)) * 0.5
-            - (double)(REAL)(A3(bz, iz, iy + O, ix + O) + A3(bz, iz + 1, iy + O, ix + O)) * 0.5);
+        I3(gr) = (REAL)((WIDE)I3(gr)
+            - (WIDE)(REAL)(A3(bx, iz + O, iy + O, ix) + A3(bx, iz + O, iy + O, ix + 1)) * (WIDE)0.5
+            - (WIDE)(REAL)(A3(by, iz + O, iy, ix + O) + A3(by, iz + O, iy + 1, ix + O)) * (WIDE)0.5
+            - (WIDE)(REAL)(A3(bz, iz, iy + O, ix + O) + A3(bz, iz + 1, iy + O, ix + O)) * (WIDE)0.5);
 }
 static void compute_gradient(orc_handle* h, int issp, int unshifted) {
     if (h->c.physics == GPI_ELASTIC) { if (h->nd == 3) compute_gradient_el3d(h, issp); else compute_gradient_el2d(h, issp); return; }
@@ -926,17 +945,17 @@ static void compute_gradient(orc_handle* h, int issp, int unshifted) {
         for (int ix = 1; ix <= gr.n[2]; ix++) for (int iz = 1; iz <= gr.n[0]; iz++) {
             #define BXI(z, x) (((z) >= 2 && (z) <= bx.n[0] - 1 && (x) >= 2 && (x) <= bx.n[2] - 1) ? A2(bx, z, x) : (REAL)0)
             #define BZI(z, x) (((z) >= 2 && (z) <= bz.n[0] - 1 && (x) >= 2 && (x) <= bz.n[2] - 1) ? A2(bz, z, x) : (REAL)0)
-            A2(gr, iz, ix) = (REAL)((double)A2(gr, iz, ix) - (double)(REAL)(BXI(iz, ix) + BXI(iz, ix + 1)) * 0.5
-                                                             - (double)(REAL)(BZI(iz, ix) + BZI(iz + 1, ix)) * 0.5);
+            A2(gr, iz, ix) = (REAL)((WIDE)A2(gr, iz, ix) - (WIDE)(REAL)(BXI(iz, ix) + BXI(iz, ix + 1)) * (WIDE)0.5
+                                                             - (WIDE)(REAL)(BZI(iz, ix) + BZI(iz + 1, ix)) * (WIDE)0.5);
         }
         return;
     }
     const int O = g_O;
     OMP_FOR
     for (int ix = 1; ix <= gr.n[2] - 2 * O; ix++) for (int iz = 1; iz <= gr.n[0] - 2 * O; iz++)             /* combine_gmodrho!: Float64 via 0.5 literals */
-        A2(gr, iz + O, ix + O) = (REAL)((double)A2(gr, iz + O, ix + O)
-            - (double)(REAL)(A2(bx, iz + O, ix) + A2(bx, iz + O, ix + 1)) * 0.5
-            - (double)(REAL)(A2(bz, iz, ix + O) + A2(bz, iz + 1, ix + O)) * 0.5);
+        A2(gr, iz + O, ix + O) = (REAL)((WIDE)A2(gr, iz + O, ix + O)
+            - (WIDE)(REAL)(A2(bx, iz + O, ix) + A2(bx, iz + O, ix + 1)) * (WIDE)0.5
+            - (WIDE)(REAL)(A2(bz, iz, ix + O) + A2(bz, iz + 1, ix + O)) * (WIDE)0.5);
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -6,9 +6,10 @@
 bench.py's cpu_baseline / --impl reference legs may import this module; the product package never
 does, and has no code path that could reach it.
 
-Parity status: UNPINNED against upstream artefacts (the reference ships no golden vectors for this
-path and Julia is not installed here); pinned by the reference's own test invariants instead
-(tests/test_oracle_invariants.py).
+Parity status: PINNED to the reference's source text (the reference ships no golden vectors for this path and
+Julia is not installed here, so its kernel text is parsed and evaluated with numpy: tests/golden/from_reference.py;
+tests/test_reference_pinned.py holds the oracle to those fixtures bit for bit) and to the reference's own test
+invariants (tests/test_oracle_invariants.py).
 """
 from __future__ import annotations
 
@@ -31,15 +32,18 @@ def build():
     subprocess.check_call(["make", "-C", _HERE, "-s"])
 
 
-def load(dtype=np.float32):
-    key = np.dtype(dtype).itemsize
+def load(dtype=np.float32, literals="f32"):
+    """`literals`: typing of the float literals inside @parallel kernels -- "f32" (ParallelStencil retypes them to the kernel number
+    type: the reference's behaviour under its Float32 preference, default) or "f64" (plain Julia promotion); Float64 builds: moot."""
+    size = np.dtype(dtype).itemsize
+    key = (size, literals if size == 4 else "f64")
     if key in _libs:
         return _libs[key]
-    path = os.path.join(_HERE, "liboracle_f32.so" if key == 4 else "liboracle_f64.so")
-    if not os.path.exists(path):
+    path = os.path.join(_HERE, "liboracle_f64.so" if size == 8 else "liboracle_f32.so" if literals == "f32" else "liboracle_f32_lit64.so")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "fdtd_oracle.c")):
         build()
     lib = C.CDLL(path)
-    assert lib.orc_real_size() == key
+    assert lib.orc_real_size() == size
     lib.orc_last_error.restype = C.c_char_p
     lib.orc_last_error.argtypes = [C.c_void_p]
     lib.orc_last_run_seconds.restype = C.c_double
@@ -49,9 +53,9 @@ def load(dtype=np.float32):
 
 
 class OracleEngine:
-    def __init__(self, cfg: E.GpiConfig, dtype=np.float32, threads: int | None = None):
+    def __init__(self, cfg: E.GpiConfig, dtype=np.float32, threads: int | None = None, literals: str = "f32"):
         self.dtype = np.dtype(dtype)
-        self.lib = load(dtype)
+        self.lib = load(dtype, literals)
         self.cfg = cfg
         self.h = C.c_void_p()
         if threads:

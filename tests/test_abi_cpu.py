@@ -139,17 +139,17 @@ def test_no_fma_contraction_in_the_ptx(tmp_path):
 
 
 def test_machine_code_of_the_measured_kernels_is_unchanged():
-    """The numbers under profiles/r01 were measured with exactly this machine code: the SASS of every kernel that existed at the last
-    GPU run (tests/golden/sass_r01.txt: cuobjdump -sass hashed per kernel by scripts/sass_hashes.py, kernel-parameter offsets masked;
-    k_post as rebuilt afterwards) must come out of the current sources unchanged.  Template parameters added since (out-of-place
-    stepping), the split of k_step3t into producer / consumer functions and the host forms for the CPU emulation leave it identical.
-    A deliberate kernel change updates the fixture in the same commit -- and its numbers need re-measuring."""
+    """The numbers under profiles/r02 were measured with exactly this machine code: the SASS of every kernel at the round's last GPU run
+    (tests/golden/sass_r02.txt: cuobjdump -sass hashed per kernel by scripts/sass_hashes.py, kernel-parameter offsets masked; written by
+    scripts/pin_sass.py) must come out of the current sources unchanged.  A deliberate kernel change re-pins the fixture in the same
+    commit -- and its numbers need re-measuring."""
     import shutil
     import subprocess
     import sys
     lib = os.path.join(ROOT, "geophyinv.jl_b200", "libgpifdtd.so")
-    if not (os.path.exists(lib) and shutil.which("cuobjdump") and shutil.which("c++filt")):
-        pytest.skip("needs the built library and cuobjdump")
+    pin = os.path.join(ROOT, "tests", "golden", "sass_r02.txt")
+    if not (os.path.exists(lib) and os.path.exists(pin) and shutil.which("cuobjdump") and shutil.which("c++filt")):
+        pytest.skip("needs the built library, the pinned hashes and cuobjdump")
     src_newer = max(os.path.getmtime(os.path.join(ROOT, "geophyinv.jl_b200", "csrc", f))
                     for f in os.listdir(os.path.join(ROOT, "geophyinv.jl_b200", "csrc")) if f.endswith((".cu", ".cuh")))
     if src_newer > os.path.getmtime(lib):
@@ -158,11 +158,11 @@ def test_machine_code_of_the_measured_kernels_is_unchanged():
     now = {}
     for line in out.splitlines():
         h, _, name = line.split(" ", 2)
-        now[name.replace(", 0>(", ">(").strip()] = h
+        now[name.strip()] = h
     want = {}
-    for line in open(os.path.join(ROOT, "tests", "golden", "sass_r01.txt")):
+    for line in open(pin):
         h, name = line.rstrip("\n").split("  ", 1)
-        want[name.replace(", 0>(", ">(").strip()] = h
+        want[name.strip()] = h
     assert len(want) >= 50
     changed = [k for k in want if now.get(k) != want[k]]
     assert not changed, "SASS changed for: " + "; ".join(changed)
