@@ -174,6 +174,7 @@ struct gpi_handle {
     bool tma3 = true;  int num_sms = 148;  int tma3_ctas = 0;  bool tma3_force = false;   // GPI_TMA3=2: TMA kernels whatever the tile utilisation
     int shell_mode = 1;                                 // GPI_SHELL=0: shell kernel serialised behind the tile kernel (diagnostic)
     bool o4vec = true;                                  // order-4 kernels with four z cells per thread (kernels4v.cuh); GPI_O4VEC=0 selects the scalar ones
+    t3::TileRec* t3_tiles[2] = {nullptr, nullptr};      // tile tables of the two tile kernels (geometry only: built once per handle)
     struct TmaSet { const float* key = nullptr; t3::Maps* d[2] = {nullptr, nullptr}; } tmaps[2];  int tmap_victim = 0;   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
     void* encode_tiled = nullptr;                                            // cuTensorMapEncodeTiled (driver entry point)   // 3-D elastic: TMA-pipelined persistent kernels (kernels3t.cuh); GPI_TMA3=0 selects k_*3v
     bool vec2 = true;                                   // 2-D: float4-per-thread kernels (kernels2v.cuh); GPI_SCALAR2D=1 selects the scalar ones
@@ -379,6 +380,13 @@ int launch_step3t(gpi_handle* h, const StepArgs& a) {
     sc.njb = (sc.jhi - sc.jlo + 1 + t3::R - 1) / t3::R;
     sc.nzc = (g.pz + t3::ZC - 1) / t3::ZC;
     sc.ntiles = (sc.ihi - sc.ilo + 1) * sc.njb * sc.nzc;
+    if (!h->t3_tiles[KIND]) {
+        std::vector<t3::TileRec> tab((size_t)sc.ntiles);
+        t3::fill_tile_table(g, sc, KIND, tab.data());
+        CU(h, cudaMalloc((void**)&h->t3_tiles[KIND], tab.size() * sizeof(t3::TileRec)));
+        CU(h, cudaMemcpy(h->t3_tiles[KIND], tab.data(), tab.size() * sizeof(t3::TileRec), cudaMemcpyHostToDevice));
+    }
+    sc.tiles = h->t3_tiles[KIND];
     const int nctas = std::max(1, std::min(sc.ntiles, h->tma3_ctas > 0 ? h->tma3_ctas : T3_MINB * h->num_sms));
     // The shell touches cells no tile touches and reads only fields this half step does not write, so it runs
     // beside the persistent tile kernel on a side stream (it needs no shared memory and fits next to the two
@@ -386,14 +394,18 @@ int launch_step3t(gpi_handle* h, const StepArgs& a) {
     // every CTA must become resident at once -- shell blocks that got to the SMs earlier would delay some of
     // them by the shell's whole duration.
     const int nlines = sc.nsp * g.ny1 + (sc.ihi - sc.ilo + 1) * sc.nsr;
+    if (t3::L<KIND>::INKERNEL_SHELL || h->shell_mode == 2) {      // the shell lines are walked by warps of the tile kernel itself (GPI_SHELL=2 with a NSHELL = 0 build: no shell at all, timing only)
+        t3::k_step3t<KIND><<<nctas, t3::L<KIND>::NTHREADS, t3::smem_bytes(KIND), h->stream>>>(g, a, sc, set->d[KIND]);
+        return 0;
+    }
     if (h->shell_mode == 0) {          // GPI_SHELL=0 (diagnostic): shell after the tiles on the same stream
-        t3::k_step3t<KIND><<<nctas, t3::NTHREADS, t3::smem_bytes(KIND), h->stream>>>(g, a, sc, set->d[KIND]);
+        t3::k_step3t<KIND><<<nctas, t3::L<KIND>::NTHREADS, t3::smem_bytes(KIND), h->stream>>>(g, a, sc, set->d[KIND]);
         t3::k_shell3<KIND><<<nlines, 128, 0, h->stream>>>(g, a, sc);
         h->timers.launches += 1;
         return 0;
     }
     CU(h, cudaEventRecord(h->ev_fork, h->stream));
-    t3::k_step3t<KIND><<<nctas, t3::NTHREADS, t3::smem_bytes(KIND), h->stream>>>(g, a, sc, set->d[KIND]);
+    t3::k_step3t<KIND><<<nctas, t3::L<KIND>::NTHREADS, t3::smem_bytes(KIND), h->stream>>>(g, a, sc, set->d[KIND]);
     CU(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     t3::k_shell3<KIND><<<nlines, 128, 0, h->side>>>(g, a, sc);
     CU(h, cudaEventRecord(h->ev_join, h->side));
@@ -916,6 +928,7 @@ extern "C" int gpi_destroy(gpi_handle* h) {
     for (auto& p : h->born_c) cudaFree(p);
     cudaFree(h->born_d);
     for (auto& ts : h->tmaps) { cudaFree(ts.d[0]); cudaFree(ts.d[1]); }
+    cudaFree(h->t3_tiles[0]); cudaFree(h->t3_tiles[1]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);

@@ -8,23 +8,25 @@
 // SM (168 registers), so only 4-5 warps per SM have loads in flight at any time.  Here the loads are decoupled
 // from the warps that compute:
 //
-//   * persistent CTAs (2 per SM), each = 4 consumer warps + 1 producer warp, walk a static round-robin list of
-//     tiles; a tile = R = 4 rows (y) x ZC = 128 cells (z) of one x plane, ordered z-chunk, row block, plane so
-//     that the tiles in flight at any moment cover ~1.2 consecutive planes (+-1-plane operands are L2 hits);
-//   * one elected producer thread moves every operand of a tile with TMA tensor copies (cp.async.bulk.tensor.3d
-//     global -> shared through one CUtensorMap per box, completion on an mbarrier) into a 2-stage shared-memory
-//     ring: 15 (velocity) or 17 (stress) boxes of 4 or 5 rows -- the 15 / 20 arrays at the tile's own rows with
-//     their y +-1 halo row, the x +-1 plane rows, a 16-byte z halo where a z neighbour is needed -- plus, only in
-//     the CPML slabs, up to 9 boxes of memory variables.  Out-of-range coordinates read zeros.  (Per-row
+//   * persistent CTAs (2 per SM), each = consumer warps + producer warps + shell warps (layout per kernel: struct L below), walk a
+//     static round-robin list of tiles; a tile = R = 4 rows (y) x ZC = 128 cells (z) of one x plane, ordered z-chunk, row block, plane
+//     so that the tiles in flight at any moment cover ~1.2 consecutive planes (+-1-plane operands are L2 hits);
+//   * one elected thread per producer warp moves its share of the operands of a tile with TMA tensor copies
+//     (cp.async.bulk.tensor.3d global -> shared through one CUtensorMap per box, completion on an mbarrier that counts one arrival
+//     per producer plus the announced bytes) into a 2-stage shared-memory ring: 15 (velocity) or 17 (stress) boxes of 4 or 5 rows --
+//     the 15 / 20 arrays at the tile's own rows with their y +-1 halo row, the x +-1 plane rows, a 16-byte z halo where a z neighbour
+//     is needed -- plus, only in the CPML slabs, up to 9 boxes of memory variables.  Out-of-range coordinates read zeros.  (Per-row
 //     cp.async.bulk copies were tried first: ptxas serialises them lane by lane, ~85 cycles per row.)
-//   * the producer also writes a small tile header (plane, first row, slab indices, row masks) into the stage, so
-//     the consumers do no tile decoding, no slab tests and no operand address arithmetic at all: they read
-//     operands from shared memory (conflict-free 16-byte reads; z +-1 neighbours by warp shuffle), do
-//     the reference-order arithmetic and write results (fields and CPML memory) with coalesced 16-byte global
-//     stores; a full / empty mbarrier pair per stage is the only synchronisation;
-//   * the outer shell of the box (rigid faces, ghost cells, ragged x / y ranges; 2.4 % of the rows) is a separate
-//     small launch of the scalar reference-order code (k_shell3) on a side stream, beside the tile kernel: it
-//     touches cells no tile touches and needs no shared memory.
+//   * everything about a tile that does not depend on the fields (plane, first row, slab indices, row masks) comes from a tile table
+//     built once per handle on the host (fill_tile_table); producer 0 copies the record into the stage as the tile header, so neither
+//     the producers nor the consumers decode tiles, test slabs or compute operand addresses: the consumers read operands from shared
+//     memory (conflict-free 16-byte reads; z +-1 neighbours by warp shuffle), do the reference-order arithmetic and write results
+//     (fields and CPML memory) with coalesced 16-byte global stores; a full / empty mbarrier pair per stage is the only synchronisation.
+//     (r01 decoded tiles in the single producer thread: ~700 dependent instructions per tile, as long as the tile period itself.)
+//   * the outer shell of the box (rigid faces, ghost cells, ragged x / y ranges; 2.4 % of the rows) is the scalar reference-order
+//     code, walked by the shell warps of every CTA beside the tile pipeline (shell_lines): it touches cells no tile touches and needs
+//     no shared memory.  A dependent load costs ~3 us while the tiles saturate HBM, so the shell must never sit on the pipeline's
+//     critical path (a separate launch ran as a 40 - 80 us tail; shell cells between two tiles of a consumer warp cost 60 %).
 //
 // The z-slab window (Geom.koff / klo / khi) is honoured exactly as in kernels3d.cuh, so the slab decomposition
 // uses the same kernels.
@@ -41,8 +43,50 @@ constexpr int R = 4;                 // rows per tile
 constexpr int ZC = 128;              // z cells per tile
 constexpr int PH = ZC + 8;           // floats per staged row of a box with a 16-byte z halo on both sides
 constexpr int STAGES = T3_STAGES;
-constexpr int NCW = R;               // consumer warps (one per row)
-constexpr int NTHREADS = 32 * (NCW + 1);
+// Warp layout of a CTA, per kernel (measured on B200, profiles/r02/tuning.md):
+//   NCOMP  consumer warps per row: 3 = one per output group (velocity: vx | vy | vz; stress: normal | xz, yz | xy), 1 = one warp takes
+//          the three groups in turn;
+//   NPROD  producer warps (one elected thread each); operand box b belongs to producer b % NPROD;
+//   NSHELL warps that walk the shell lines beside the tile pipeline; SHELLC = 1: the consumer warps take one 32-cell shell unit every
+//          16th tile instead (their slack between two tiles is longer than a shell cell's dependent-load chain).
+// velocity: 12 + 1 warps, shell units between tiles (72 registers); stress: 4 + 2 + 2 warps (128 registers).
+#ifndef T3_V_NCOMP
+#define T3_V_NCOMP 1
+#endif
+#ifndef T3_V_NPROD
+#define T3_V_NPROD 2
+#endif
+#ifndef T3_V_NSHELL
+#define T3_V_NSHELL 2
+#endif
+#ifndef T3_V_SHELLC
+#define T3_V_SHELLC 0
+#endif
+#ifndef T3_S_NCOMP
+#define T3_S_NCOMP 1
+#endif
+#ifndef T3_S_NPROD
+#define T3_S_NPROD 2
+#endif
+#ifndef T3_S_NSHELL
+#define T3_S_NSHELL 2
+#endif
+#ifndef T3_S_SHELLC
+#define T3_S_SHELLC 0
+#endif
+template <int KIND> struct L {
+    static constexpr int NCOMP = KIND == 0 ? T3_V_NCOMP : T3_S_NCOMP;
+    static constexpr int NPROD = KIND == 0 ? T3_V_NPROD : T3_S_NPROD;
+    static constexpr int NSHELL = KIND == 0 ? T3_V_NSHELL : T3_S_NSHELL;
+    static constexpr int SHELLC = KIND == 0 ? T3_V_SHELLC : T3_S_SHELLC;
+    static constexpr int NCW = R * NCOMP;                 // consumer warps
+    static constexpr int NTHREADS = 32 * (NCW + NPROD + NSHELL);
+    static constexpr bool INKERNEL_SHELL = NSHELL > 0 || SHELLC;       // false: the shell is the separate launch k_shell3
+    static_assert(NCOMP == 1 || NCOMP == 3, "NCOMP: 1 or 3");
+    static_assert(NPROD >= 1 && NPROD <= 4, "NPROD: 1..4");
+    static_assert(!SHELLC || NCW <= 16, "SHELLC: the consumer warps take turns modulo 16 tiles");
+};
+constexpr int SHELL_EVERY = 16;
 constexpr int PZM = 96;              // floats per z-CPML memory row (Geom.pzm must equal this)
 
 // Operand boxes of a stage.  Every box is rows x pitch floats, dense, and starts on a 128-byte boundary.
@@ -60,8 +104,13 @@ enum { S_VX0 = 0 /*5 rows j-1..j+3, halo*/, S_VXP = S_VX0 + H5, S_VY0 = S_VXP + 
 // after the main boxes: CPML memory boxes (x terms, y terms: 4 x 128; z terms: 4 x 96), then the tile header
 constexpr int P_X = 0, P_Y = 3 * B4, P_Z = 6 * B4, P_HDR = 6 * B4 + 3 * 4 * PZM, P_FLOATS = P_HDR + 32;
 constexpr int MAXBOX = S_NBOX + 9;
-// tile header (ints)
-enum { H_I = 0, H_J0, H_KC0, H_SX /*3*/, H_SY0 = H_SX + 3 /*3*/, H_YMASK = H_SY0 + 3 /*3*/, H_ZLOAD = H_YMASK + 3, H_N };
+// tile header (ints) = one record of the tile table
+enum { H_I = 0, H_J0, H_KC0, H_SX /*3*/, H_SY0 = H_SX + 3 /*3*/, H_YMASK = H_SY0 + 3 /*3*/, H_ZLOAD = H_YMASK + 3, H_N, H_REC = 16 };
+// The tile table: everything about tile t that does not depend on the fields -- plane, first row, z chunk, the slab index of the plane
+// for the three x terms, first slab index and row mask for the three y terms, whether the z-memory rows are staged.  Computed once per
+// (handle, kernel) on the host (fill_tile_table) so that the producers do no tile decoding: a single thread running ~350 dependent integer
+// instructions per tile was what bounded the r01 kernels (profiles/r02/tuning.md).
+struct alignas(16) TileRec { int v[H_REC]; };
 
 // one operand box: which array, plane / first-row offset relative to (i, j0), rows, z halo, offset inside the stage
 struct BoxSpec { int arr; int di, dj, rows, halo, off; };      // arr: 0-5 tau, 6-8 v, 9.. coefficient slot + 9
@@ -112,6 +161,7 @@ struct Sched {
     int ntiles;
     int sp[4], nsp;                  // shell planes (all rows)
     int sr[4], nsr;                  // shell rows of the fast planes
+    const TileRec* tiles;            // [ntiles] (device)
 };
 
 template <int KIND> struct K {
@@ -127,7 +177,7 @@ __host__ __device__ inline size_t smem_bytes(int kind) {
 #ifdef GPI_HOST_EMU
 // tests/emu (cuda_rt_shim.h): host forms of the primitives, so that the tile decomposition, the producer's box list and byte
 // accounting, the tile header and the consumers' shared-memory indexing run on the CPU.  A CTA is emulated serially (tile by
-// tile: producer, then the 128 consumer lanes), so the barriers have nothing to order; the 64-bit barrier word counts the
+// tile: producer, then the NCW x 32 consumer lanes), so the barriers have nothing to order; the 64-bit barrier word counts the
 // bytes still expected instead, and a consumer that finds it non-zero has caught a wrong expect_tx (a hang on the GPU).
 typedef uintptr_t sptr_t;
 struct EmuTensorMap { const float* base; unsigned long long dim[3]; unsigned box[3]; };       // what the emulated encoder stores in a CUtensorMap
@@ -194,82 +244,128 @@ __device__ __forceinline__ float z_next_s(unsigned mask, const F4& c, const floa
 #endif   // GPI_HOST_EMU
 
 // ------------------------------------------------------------------------------------------------
-// producer: one thread per CTA
+// tile table (host) and producers: one elected thread per producer warp
 // ------------------------------------------------------------------------------------------------
+inline int slab_index_h(int u, int s0, int len, int npml, bool hmin, bool hmax) {
+    const int r = u - s0;
+    if (hmin && r >= 0 && r < npml) return r;
+    const int rm = r - (len - npml);
+    if (hmax && rm >= 0 && rm < npml) return npml + rm;
+    return -1;
+}
+inline void fill_tile_table(const Geom& g, const Sched& sc, int kind, TileRec* out) {
+    const int npml = g.npml;
+    const bool hxmin = g.pml & XMIN, hxmax = g.pml & XMAX, hymin = g.pml & YMIN, hymax = g.pml & YMAX;
+    int xs0[3], xlen[3], ys0[3], ylen[3], zs0[3], zlen[3];
+    for (int q = 0; q < 3; q++) { term_extent(g, kind, 2, q, xs0[q], xlen[q]); term_extent(g, kind, 1, q, ys0[q], ylen[q]); term_extent(g, kind, 0, q, zs0[q], zlen[q]); }
+    const int per_plane = sc.njb * sc.nzc;
+    for (int t = 0; t < sc.ntiles; t++) {
+        int* h = out[t].v;
+        for (int q = 0; q < H_REC; q++) h[q] = 0;
+        const int ip = t / per_plane, rem = t - ip * per_plane;
+        const int jb = rem / sc.nzc, zc = rem - jb * sc.nzc;
+        const int i = sc.ilo + ip, j0 = sc.jlo + jb * R, kc0 = zc * ZC;
+        h[H_I] = i; h[H_J0] = j0; h[H_KC0] = kc0;
+        for (int q = 0; q < 3; q++) {
+            h[H_SX + q] = slab_index_h(i, xs0[q], xlen[q], npml, hxmin, hxmax);
+            for (int r = R - 1; r >= 0; r--) {
+                const int sr = slab_index_h(j0 + r, ys0[q], ylen[q], npml, hymin, hymax);
+                if (sr >= 0) { h[H_YMASK + q] |= 1 << r; h[H_SY0 + q] = sr - r; }
+            }
+        }
+        const int kg0 = kc0 + g.koff, kg1 = kg0 + (ZC < g.pz - kc0 ? ZC : g.pz - kc0);       // global z range of the chunk
+        bool zload = false;
+        for (int q = 0; q < 3; q++) {
+            zload |= (g.pml & ZMIN) && kg0 < zs0[q] + npml;
+            zload |= (g.pml & ZMAX) && kg1 > ((zs0[q] + zlen[q] - npml) >> 2 << 2);
+        }
+        h[H_ZLOAD] = zload ? 1 : 0;
+    }
+}
+
 // The tile sequence of a CTA: t = blockIdx.x, blockIdx.x + gridDim.x, ... < ntiles, n = how many tiles came before (stage and
 // phase bookkeeping).  The CPU emulation calls producer / consumer once per tile and passes the range (t_first, t_step, t_end, n0).
 #ifdef GPI_HOST_EMU
 #define T3_TILE_LOOP(t, n) int n = n0; for (int t = t_first; t < t_end; t += t_step, n++)
+#define T3_NEXT_TILE(t) ((t) + t_step)
+struct I4 { int x, y, z, w; };
+inline I4 ldrec(const TileRec* r, int q) { return I4{r->v[4 * q], r->v[4 * q + 1], r->v[4 * q + 2], r->v[4 * q + 3]}; }
+inline void sts_i4(int* p, const I4& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
 #else
 #define T3_TILE_LOOP(t, n) int n = 0; for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x, n++)
+#define T3_NEXT_TILE(t) ((t) + (int)gridDim.x)
+typedef int4 I4;
+__device__ __forceinline__ I4 ldrec(const TileRec* r, int q) { return __ldg(reinterpret_cast<const int4*>(r->v) + q); }
+__device__ __forceinline__ void sts_i4(int* p, const I4& v) { *reinterpret_cast<int4*>(p) = v; }
 #endif
-template <int KIND>
+// producer P of NPROD: waits for the stage, (P == 0: writes the tile header,) announces the bytes of ITS boxes and issues them.
+// The full barrier of a stage counts NPROD arrivals plus every announced byte.
+template <int KIND, int P>
 __device__ __forceinline__ void producer(const Geom& g, const Sched& sc, const Maps* tm, float* stage0,
                                          sptr_t full0, sptr_t empty0, int t_first, int t_step, int t_end, int n0) {
-    constexpr int NBOX = K<KIND>::NBOX, MAIN = K<KIND>::MAIN, SFLOATS = K<KIND>::SFLOATS;
+    constexpr int NBOX = K<KIND>::NBOX, MAIN = K<KIND>::MAIN, SFLOATS = K<KIND>::SFLOATS, NPROD = L<KIND>::NPROD;
     int main_bytes = 0;
 #pragma unroll
-    for (int b = 0; b < NBOX; b++) { const BoxSpec bs = box_spec(KIND, b); main_bytes += bs.rows * (bs.halo ? PH : ZC) * 4; }
-    const int npml = g.npml;
-    const bool hxmin = g.pml & XMIN, hxmax = g.pml & XMAX, hymin = g.pml & YMIN, hymax = g.pml & YMAX;
-    // term extents (loop invariant)
-    int xs0[3], xlen[3], ys0[3], ylen[3], zs0[3], zlen[3];
-#pragma unroll
-    for (int q = 0; q < 3; q++) { term_extent(g, KIND, 2, q, xs0[q], xlen[q]); term_extent(g, KIND, 1, q, ys0[q], ylen[q]); term_extent(g, KIND, 0, q, zs0[q], zlen[q]); }
-    const int per_plane = sc.njb * sc.nzc;
+    for (int b = 0; b < NBOX; b++) if (b % NPROD == P) { const BoxSpec bs = box_spec(KIND, b); main_bytes += bs.rows * (bs.halo ? PH : ZC) * 4; }
+    I4 r0, r1, r2, r3;             // record of the tile about to be issued (loaded one tile ahead)
+    {
+#ifdef GPI_HOST_EMU
+        const int tf = t_first;
+#else
+        const int tf = blockIdx.x;
+#endif
+        if (tf < sc.ntiles) { r0 = ldrec(sc.tiles + tf, 0); r1 = ldrec(sc.tiles + tf, 1); r2 = ldrec(sc.tiles + tf, 2); r3 = ldrec(sc.tiles + tf, 3); }
+    }
     T3_TILE_LOOP(t, n) {
         const int s = n % STAGES;
         const uint32_t use = n / STAGES;
-        const int ip = t / per_plane, rem = t - ip * per_plane;
-        const int jb = rem / sc.nzc, zc = rem - jb * sc.nzc;
-        const int i = sc.ilo + ip, j0 = sc.jlo + jb * R, kc0 = zc * ZC;
-        // CPML boxes of this tile
-        int sx[3], sy0[3], ymask[3], bytes = main_bytes;
+        const I4 c0 = r0, c1 = r1, c2 = r2, c3 = r3;
+        {
+            const int tn = T3_NEXT_TILE(t);
+            if (tn < sc.ntiles) { r0 = ldrec(sc.tiles + tn, 0); r1 = ldrec(sc.tiles + tn, 1); r2 = ldrec(sc.tiles + tn, 2); r3 = ldrec(sc.tiles + tn, 3); }
+        }
+        // record layout: H_I H_J0 H_KC0 sx0 | sx1 sx2 sy0 sy1 | sy2 ym0 ym1 ym2 | zload
+        const int i = c0.x, j0 = c0.y, kc0 = c0.z;
+        const int sx[3] = {c0.w, c1.x, c1.y}, sy0[3] = {c1.z, c1.w, c2.x}, ymask[3] = {c2.y, c2.z, c2.w};
+        const bool zload = c3.x != 0;
+        int bytes = main_bytes;
 #pragma unroll
         for (int q = 0; q < 3; q++) {
-            sx[q] = slab_index(i, xs0[q], xlen[q], npml, hxmin, hxmax);
-            if (sx[q] >= 0) bytes += R * ZC * 4;
-            ymask[q] = 0; sy0[q] = 0;
-#pragma unroll
-            for (int r = R - 1; r >= 0; r--) {
-                const int sr = slab_index(j0 + r, ys0[q], ylen[q], npml, hymin, hymax);
-                if (sr >= 0) { ymask[q] |= 1 << r; sy0[q] = sr - r; }
-            }
-            if (ymask[q]) bytes += R * ZC * 4;
+            if ((NBOX + q) % NPROD == P && sx[q] >= 0) bytes += R * ZC * 4;
+            if ((NBOX + 3 + q) % NPROD == P && ymask[q]) bytes += R * ZC * 4;
+            if ((NBOX + 6 + q) % NPROD == P && zload) bytes += R * PZM * 4;
         }
-        bool zload = false;
-        {
-            const int kg0 = kc0 + g.koff, kg1 = kg0 + min(ZC, g.pz - kc0);       // global z range of the chunk
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-                zload |= (g.pml & ZMIN) && kg0 < zs0[q] + npml;
-                zload |= (g.pml & ZMAX) && kg1 > zslab_base(zs0[q], zlen[q], npml);
-            }
-        }
-        if (zload) bytes += 3 * R * PZM * 4;
-
         mbar_wait(empty0 + 8 * s, (use & 1) ^ 1);
         float* S = stage0 + (size_t)s * SFLOATS;
-        int* hdr = reinterpret_cast<int*>(S + MAIN + P_HDR);
-        hdr[H_I] = i; hdr[H_J0] = j0; hdr[H_KC0] = kc0; hdr[H_ZLOAD] = zload ? 1 : 0;
-#pragma unroll
-        for (int q = 0; q < 3; q++) { hdr[H_SX + q] = sx[q]; hdr[H_SY0 + q] = sy0[q]; hdr[H_YMASK + q] = ymask[q]; }
+        if (P == 0) {
+            int* hdr = reinterpret_cast<int*>(S + MAIN + P_HDR);
+            sts_i4(hdr, c0); sts_i4(hdr + 4, c1); sts_i4(hdr + 8, c2); sts_i4(hdr + 12, c3);
+        }
         const sptr_t bar = full0 + 8 * s;
         mbar_expect_tx(bar, bytes);                 // release: the header is visible to whoever observes the phase
         const sptr_t dst0 = s32(S);
 #pragma unroll
-        for (int b = 0; b < NBOX; b++) {
+        for (int b = 0; b < NBOX; b++) if (b % NPROD == P) {
             const BoxSpec bs = box_spec(KIND, b);
             tma_box(dst0 + bs.off * 4, tm->m[b], kc0 - (bs.halo ? 4 : 0), j0 + bs.dj, i + bs.di, bar);
         }
         const sptr_t dstp = dst0 + MAIN * 4;
 #pragma unroll
         for (int q = 0; q < 3; q++) {
-            if (sx[q] >= 0) tma_box(dstp + (P_X + q * B4) * 4, tm->m[NBOX + q], kc0, j0, sx[q], bar);          // [k, j, s]
-            if (ymask[q])   tma_box(dstp + (P_Y + q * B4) * 4, tm->m[NBOX + 3 + q], kc0, sy0[q], i, bar);      // [k, s, i]
-            if (zload)      tma_box(dstp + (P_Z + q * 4 * PZM) * 4, tm->m[NBOX + 6 + q], 0, j0, i, bar);       // [zi, j, i]
+            if ((NBOX + q) % NPROD == P && sx[q] >= 0)  tma_box(dstp + (P_X + q * B4) * 4, tm->m[NBOX + q], kc0, j0, sx[q], bar);          // [k, j, s]
+            if ((NBOX + 3 + q) % NPROD == P && ymask[q]) tma_box(dstp + (P_Y + q * B4) * 4, tm->m[NBOX + 3 + q], kc0, sy0[q], i, bar);      // [k, s, i]
+            if ((NBOX + 6 + q) % NPROD == P && zload)    tma_box(dstp + (P_Z + q * 4 * PZM) * 4, tm->m[NBOX + 6 + q], 0, j0, i, bar);       // [zi, j, i]
         }
     }
+}
+template <int KIND>
+__device__ __forceinline__ void producer_any(int p, const Geom& g, const Sched& sc, const Maps* tm, float* stage0,
+                                             sptr_t full0, sptr_t empty0, int t_first, int t_step, int t_end, int n0) {
+    constexpr int NPROD = L<KIND>::NPROD;
+    if (p == 0) producer<KIND, 0>(g, sc, tm, stage0, full0, empty0, t_first, t_step, t_end, n0);
+    else if (NPROD > 1 && p == 1) producer<KIND, 1 % NPROD>(g, sc, tm, stage0, full0, empty0, t_first, t_step, t_end, n0);
+    else if (NPROD > 2 && p == 2) producer<KIND, 2 % NPROD>(g, sc, tm, stage0, full0, empty0, t_first, t_step, t_end, n0);
+    else if (NPROD > 3 && p == 3) producer<KIND, 3 % NPROD>(g, sc, tm, stage0, full0, empty0, t_first, t_step, t_end, n0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -323,25 +419,41 @@ struct TileCtx {
     long long c;           // unified index of the first cell
 };
 
-template <int KIND>
+// which CPML terms an output group touches (AXIS: 0 z, 1 y, 2 x; Q: position in the axis' term list, see term_index)
+//   velocity: group C = component C, whose x, y and z derivative are term C of every axis
+//   stress:   group 0 = tauxx, tauyy, tauzz (the three normal derivatives, Q = 0 on every axis);
+//             group 1 = tauxz, tauyz (d_zi vx, d_xi vz | d_zi vy, d_yi vz);  group 2 = tauxy (d_yi vx, d_xi vy)
+__host__ __device__ constexpr bool group_uses(int kind, int comp, int axis, int q) {
+    return comp == 3 ? true
+         : kind == 0 ? q == comp
+         : comp == 0 ? q == 0
+         : comp == 1 ? (axis == 2 ? q == 2 : axis == 1 ? q == 2 : q >= 1)
+         :             (axis != 0 && q == 1);
+}
+template <int KIND, int COMP>
 __device__ __forceinline__ void open_tile(TileCtx& q, const Geom& g, const StepArgs& a, const float* S, int r, int lane) {
     const int* hdr = reinterpret_cast<const int*>(S + K<KIND>::MAIN + P_HDR);
     q.S = S; q.P = S + K<KIND>::MAIN; q.r = r; q.lane = lane;
     q.i = hdr[H_I]; q.j = hdr[H_J0] + r; q.k0 = hdr[H_KC0] + 4 * lane; q.kg0 = q.k0 + g.koff;
 #pragma unroll
     for (int t = 0; t < 3; t++) {
-        q.sx[t] = hdr[H_SX + t];
-        q.sy[t] = ((hdr[H_YMASK + t] >> r) & 1) ? hdr[H_SY0 + t] + r : -1;
+        if (group_uses(KIND, COMP, 2, t)) q.sx[t] = hdr[H_SX + t];
+        if (group_uses(KIND, COMP, 1, t)) q.sy[t] = ((hdr[H_YMASK + t] >> r) & 1) ? hdr[H_SY0 + t] + r : -1;
     }
     q.zload = hdr[H_ZLOAD] != 0;
     q.c = uidx(g, q.k0, q.j, q.i);
 #pragma unroll
     for (int t = 0; t < 3; t++) {
-        const PmlTerm& tx = (KIND == 0 ? a.pv : a.ps)[term_index(KIND, 2, t)];
-        const PmlTerm& ty = (KIND == 0 ? a.pv : a.ps)[term_index(KIND, 1, t)];
-        const int s = q.sx[t], u = q.sy[t];
-        if (s >= 0) { q.cx[t][0] = ld1(tx.a + s); q.cx[t][1] = ld1(tx.b + s); q.cx[t][2] = ld1(tx.kI + s); }
-        if (u >= 0) { q.cy[t][0] = ld1(ty.a + u); q.cy[t][1] = ld1(ty.b + u); q.cy[t][2] = ld1(ty.kI + u); }
+        if (group_uses(KIND, COMP, 2, t)) {
+            const PmlTerm& tx = (KIND == 0 ? a.pv : a.ps)[term_index(KIND, 2, t)];
+            const int s = q.sx[t];
+            if (s >= 0) { q.cx[t][0] = ld1(tx.a + s); q.cx[t][1] = ld1(tx.b + s); q.cx[t][2] = ld1(tx.kI + s); }
+        }
+        if (group_uses(KIND, COMP, 1, t)) {
+            const PmlTerm& ty = (KIND == 0 ? a.pv : a.ps)[term_index(KIND, 1, t)];
+            const int u = q.sy[t];
+            if (u >= 0) { q.cy[t][0] = ld1(ty.a + u); q.cy[t][1] = ld1(ty.b + u); q.cy[t][2] = ld1(ty.kI + u); }
+        }
     }
 }
 // apply the CPML term (axis, q) of kernel KIND to d
@@ -371,142 +483,142 @@ __device__ __forceinline__ void pml_t(const TileCtx& q, const Geom& g, const Ste
 }
 
 // ------------------------------------------------------------------------------------------------
-// velocity kernel (term order and citations: vel_cell in kernels.cuh)
+// velocity kernel (term order and citations: vel_cell in kernels.cuh); one warp = one component of one row
 // ------------------------------------------------------------------------------------------------
+template <int C>
 __device__ __forceinline__ void vel_tile(const Geom& g, const StepArgs& a, const TileCtx& q) {
     const int nz = g.nz, k0 = q.k0, kg0 = q.kg0, r = q.r;
     const bool more = k0 + VW < g.pz;
     const float* B = q.S + 4 * q.lane;                    // plain boxes
     const float* H = q.S + 4 * q.lane + 4;                // boxes with a z halo
-    const F4 xx = lds4(B + V_XX0 + r * ZC), xxm = lds4(B + V_XXM + r * ZC);
-    const F4 yy = lds4(B + V_YY + (r + 1) * ZC), yym = lds4(B + V_YY + r * ZC);
-    const F4 zz = lds4(H + V_ZZ + r * PH);
-    const F4 xy = lds4(B + V_XY0 + r * ZC), xypy = lds4(B + V_XY0 + (r + 1) * ZC), xypx = lds4(B + V_XYP + r * ZC);
-    const F4 xz = lds4(H + V_XZ0 + r * PH), xzpx = lds4(B + V_XZP + r * ZC);
-    const F4 yz = lds4(H + V_YZ + r * PH), yzpy = lds4(H + V_YZ + (r + 1) * PH);
-    const float zzprev = z_prev_s(q.mask, zz, H + V_ZZ + r * PH, q.lane, k0 > 0);
-    const float xznext = z_next_s(q.mask, xz, H + V_XZ0 + r * PH, q.lane, more);
-    const float yznext = z_next_s(q.mask, yz, H + V_YZ + r * PH, q.lane, more);
-
-    // vx: dtauxxdx + dtauxydy + dtauxzdz
-    F4 dxx = diff4(xx, xxm, g.dxI);            pml_t<0, 2, 0>(q, g, a, dxx);
-    F4 dxy = diff4(xypy, xy, g.dyI);           pml_t<0, 1, 0>(q, g, a, dxy);
-    F4 dxz = diff4_zp(xz, xznext, g.dzI);      pml_t<0, 0, 0>(q, g, a, dxz);
-    // vy: dtauxydx + dtauyydy + dtauyzdz
-    F4 dyx = diff4(xypx, xy, g.dxI);           pml_t<0, 2, 1>(q, g, a, dyx);
-    F4 dyy = diff4(yy, yym, g.dyI);            pml_t<0, 1, 1>(q, g, a, dyy);
-    F4 dyz = diff4_zp(yz, yznext, g.dzI);      pml_t<0, 0, 1>(q, g, a, dyz);
-    // vz: dtauxzdx + dtauyzdy + dtauzzdz
-    F4 dzx = diff4(xzpx, xz, g.dxI);           pml_t<0, 2, 2>(q, g, a, dzx);
-    F4 dzy = diff4(yzpy, yz, g.dyI);           pml_t<0, 1, 2>(q, g, a, dzy);
-    F4 dzz = diff4_zm(zz, zzprev, g.dzI);      pml_t<0, 0, 2>(q, g, a, dzz);
-
-    F4 nvx = lds4(B + V_VX + r * ZC), nvy = lds4(B + V_VY + r * ZC), nvz = lds4(B + V_VZ + r * ZC);
-    const F4 bx = lds4(B + V_BX + r * ZC), by = lds4(B + V_BY + r * ZC), bz = lds4(B + V_BZ + r * ZC);
-    float* vx = a.v[V_X] + q.c; float* vy = a.v[V_Y] + q.c; float* vz = a.v[V_Z] + q.c;
+    F4 dx, dy, dz;                                        // the component's x, y, z derivative; v -= b * ((dx + dy) + dz)
+    if (C == 0) {          // vx: dtauxxdx + dtauxydy + dtauxzdz
+        const F4 xx = lds4(B + V_XX0 + r * ZC), xxm = lds4(B + V_XXM + r * ZC);
+        const F4 xy = lds4(B + V_XY0 + r * ZC), xypy = lds4(B + V_XY0 + (r + 1) * ZC);
+        const F4 xz = lds4(H + V_XZ0 + r * PH);
+        const float xznext = z_next_s(q.mask, xz, H + V_XZ0 + r * PH, q.lane, more);
+        dx = diff4(xx, xxm, g.dxI);            pml_t<0, 2, 0>(q, g, a, dx);
+        dy = diff4(xypy, xy, g.dyI);           pml_t<0, 1, 0>(q, g, a, dy);
+        dz = diff4_zp(xz, xznext, g.dzI);      pml_t<0, 0, 0>(q, g, a, dz);
+    } else if (C == 1) {   // vy: dtauxydx + dtauyydy + dtauyzdz
+        const F4 xy = lds4(B + V_XY0 + r * ZC), xypx = lds4(B + V_XYP + r * ZC);
+        const F4 yy = lds4(B + V_YY + (r + 1) * ZC), yym = lds4(B + V_YY + r * ZC);
+        const F4 yz = lds4(H + V_YZ + r * PH);
+        const float yznext = z_next_s(q.mask, yz, H + V_YZ + r * PH, q.lane, more);
+        dx = diff4(xypx, xy, g.dxI);           pml_t<0, 2, 1>(q, g, a, dx);
+        dy = diff4(yy, yym, g.dyI);            pml_t<0, 1, 1>(q, g, a, dy);
+        dz = diff4_zp(yz, yznext, g.dzI);      pml_t<0, 0, 1>(q, g, a, dz);
+    } else {               // vz: dtauxzdx + dtauyzdy + dtauzzdz
+        const F4 xz = lds4(H + V_XZ0 + r * PH), xzpx = lds4(B + V_XZP + r * ZC);
+        const F4 yz = lds4(H + V_YZ + r * PH), yzpy = lds4(H + V_YZ + (r + 1) * PH);
+        const F4 zz = lds4(H + V_ZZ + r * PH);
+        const float zzprev = z_prev_s(q.mask, zz, H + V_ZZ + r * PH, q.lane, k0 > 0);
+        dx = diff4(xzpx, xz, g.dxI);           pml_t<0, 2, 2>(q, g, a, dx);
+        dy = diff4(yzpy, yz, g.dyI);           pml_t<0, 1, 2>(q, g, a, dy);
+        dz = diff4_zm(zz, zzprev, g.dzI);      pml_t<0, 0, 2>(q, g, a, dz);
+    }
+    F4 nv = lds4(B + V_VX + C * B4 + r * ZC);
+    const F4 b = lds4(B + V_BX + C * B4 + r * ZC);
+    float* v = a.v[C == 0 ? V_X : C == 1 ? V_Y : V_Z] + q.c;
     const int Rg = g.rigid;
     const bool head = kg0 == 0, tail = kg0 + VW - 1 >= nz - 1;
     const bool allown = k0 >= g.klo && k0 + VW - 1 <= g.khi;
     if (!head && !tail && allown) {
         // every cell of the group is an interior node of vx, vy and vz: no predicates
 #pragma unroll
-        for (int e = 0; e < VW; e++) {
-            nvx.v[e] = __fsub_rn(nvx.v[e], __fmul_rn(bx.v[e], __fadd_rn(__fadd_rn(dxx.v[e], dxy.v[e]), dxz.v[e])));
-            nvy.v[e] = __fsub_rn(nvy.v[e], __fmul_rn(by.v[e], __fadd_rn(__fadd_rn(dyx.v[e], dyy.v[e]), dyz.v[e])));
-            nvz.v[e] = __fsub_rn(nvz.v[e], __fmul_rn(bz.v[e], __fadd_rn(__fadd_rn(dzx.v[e], dzy.v[e]), dzz.v[e])));
-        }
-        st4(vx, nvx); st4(vy, nvy); st4(vz, nvz);
+        for (int e = 0; e < VW; e++) nv.v[e] = __fsub_rn(nv.v[e], __fmul_rn(b.v[e], __fadd_rn(__fadd_rn(dx.v[e], dy.v[e]), dz.v[e])));
+        st4(v, nv);
         return;
     }
+    const int klast = C == 2 ? nz - 1 : nz - 2;           // last updated node: vx, vy inner in z; vz half
 #pragma unroll
     for (int e = 0; e < VW; e++) {
         const int k = kg0 + e; const bool own = (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo);
-        if (own && k >= 1 && k <= nz - 2) {
-            nvx.v[e] = __fsub_rn(nvx.v[e], __fmul_rn(bx.v[e], __fadd_rn(__fadd_rn(dxx.v[e], dxy.v[e]), dxz.v[e])));
-            nvy.v[e] = __fsub_rn(nvy.v[e], __fmul_rn(by.v[e], __fadd_rn(__fadd_rn(dyx.v[e], dyy.v[e]), dyz.v[e])));
-        }
-        if (own && k >= 1 && k <= nz - 1)
-            nvz.v[e] = __fsub_rn(nvz.v[e], __fmul_rn(bz.v[e], __fadd_rn(__fadd_rn(dzx.v[e], dzy.v[e]), dzz.v[e])));
+        if (own && k >= 1 && k <= klast) nv.v[e] = __fsub_rn(nv.v[e], __fmul_rn(b.v[e], __fadd_rn(__fadd_rn(dx.v[e], dy.v[e]), dz.v[e])));
     }
     // rigid z faces (dirichlet.jl:35-74); the x / y faces only touch shell rows (scalar path)
-    if (head && (Rg & ZMIN)) { nvx.v[0] = 0.f; nvy.v[0] = 0.f; nvz.v[0] = -nvz.v[1]; }
-    if (!tail && allown) {
-        st4(vx, nvx); st4(vy, nvy); st4(vz, nvz);
-    } else {
+    if (head && (Rg & ZMIN)) nv.v[0] = C == 2 ? -nv.v[1] : 0.f;
+    if (!tail && allown) { st4(v, nv); return; }
 #pragma unroll
-        for (int e = 0; e < VW; e++) {
-            const int k = kg0 + e; const bool own = (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo);
-            if (own && k <= nz - 1) {
-                const bool zero = (Rg & ZMAX) && k == nz - 1;
-                vx[e] = zero ? 0.f : nvx.v[e];
-                vy[e] = zero ? 0.f : nvy.v[e];
-                vz[e] = nvz.v[e];
-                if ((Rg & ZMAX) && k == nz - 1) vz[e + 1] = -nvz.v[e];       // vz[nz+1] = -vz[nz]
-            }
+    for (int e = 0; e < VW; e++) {
+        const int k = kg0 + e; const bool own = (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo);
+        if (own && k <= nz - 1) {
+            const bool face = (Rg & ZMAX) && k == nz - 1;
+            if (C == 2) { v[e] = nv.v[e]; if (face) v[e + 1] = -nv.v[e]; }       // vz[nz+1] = -vz[nz]
+            else v[e] = face ? 0.f : nv.v[e];
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// stress kernel (term order and citations: stress_cell in kernels.cuh)
+// stress kernel (term order and citations: stress_cell in kernels.cuh); one warp = one output group of one row
 // ------------------------------------------------------------------------------------------------
+template <int C>
 __device__ __forceinline__ void stress_tile(const Geom& g, const StepArgs& a, const TileCtx& q) {
     const int nz = g.nz, k0 = q.k0, kg0 = q.kg0, r = q.r;
     const bool more = k0 + VW < g.pz;
     const float* B = q.S + 4 * q.lane;
     const float* H = q.S + 4 * q.lane + 4;
-    const F4 cvx = lds4(H + S_VX0 + (r + 1) * PH), cvy = lds4(H + S_VY0 + r * PH), cvz = lds4(H + S_VZ0 + (r + 1) * PH);
-    const F4 vxpx = lds4(B + S_VXP + r * ZC), vypy = lds4(H + S_VY0 + (r + 1) * PH);
-    const F4 vxmy = lds4(H + S_VX0 + r * PH), vymx = lds4(B + S_VYM + r * ZC), vzmx = lds4(B + S_VZM + r * ZC), vzmy = lds4(H + S_VZ0 + r * PH);
-    const float vznext = z_next_s(q.mask, cvz, H + S_VZ0 + (r + 1) * PH, q.lane, more);
-    const float vxprev = z_prev_s(q.mask, cvx, H + S_VX0 + (r + 1) * PH, q.lane, k0 > 0);
-    const float vyprev = z_prev_s(q.mask, cvy, H + S_VY0 + r * PH, q.lane, k0 > 0);
     const bool fs = (g.freesurf & ZMIN) != 0;
     const bool head = kg0 == 0, tail = kg0 + VW - 1 >= nz - 1;
     const bool allown = k0 >= g.klo && k0 + VW - 1 <= g.khi;
     const bool plain = !head && !tail && allown;        // every cell is an interior node of all six stresses (k >= 4: no free-surface row)
-
-    F4 dxx = diff4(vxpx, cvx, g.dxI);           pml_t<1, 2, 0>(q, g, a, dxx);      // @d_xa(vx)
-    F4 dyy = diff4(vypy, cvy, g.dyI);           pml_t<1, 1, 0>(q, g, a, dyy);      // @d_ya(vy)
-    F4 dzz = diff4_zp(cvz, vznext, g.dzI);      pml_t<1, 0, 0>(q, g, a, dzz);      // @d_za(vz)
-    F4 xx = lds4(B + S_XX + r * ZC), yy = lds4(B + S_YY + r * ZC), zz = lds4(B + S_ZZ + r * ZC);
-    const F4 M = lds4(B + S_K + r * ZC), L = lds4(B + S_L + r * ZC);
+    if (C == 0) {          // tauxx, tauyy, tauzz
+        const F4 cvx = lds4(H + S_VX0 + (r + 1) * PH), vxpx = lds4(B + S_VXP + r * ZC);
+        const F4 cvy = lds4(H + S_VY0 + r * PH), vypy = lds4(H + S_VY0 + (r + 1) * PH);
+        const F4 cvz = lds4(H + S_VZ0 + (r + 1) * PH);
+        const float vznext = z_next_s(q.mask, cvz, H + S_VZ0 + (r + 1) * PH, q.lane, more);
+        F4 dxx = diff4(vxpx, cvx, g.dxI);           pml_t<1, 2, 0>(q, g, a, dxx);      // @d_xa(vx)
+        F4 dyy = diff4(vypy, cvy, g.dyI);           pml_t<1, 1, 0>(q, g, a, dyy);      // @d_ya(vy)
+        F4 dzz = diff4_zp(cvz, vznext, g.dzI);      pml_t<1, 0, 0>(q, g, a, dzz);      // @d_za(vz)
+        F4 xx = lds4(B + S_XX + r * ZC), yy = lds4(B + S_YY + r * ZC), zz = lds4(B + S_ZZ + r * ZC);
+        const F4 M = lds4(B + S_K + r * ZC), L = lds4(B + S_L + r * ZC);
 #pragma unroll
-    for (int e = 0; e < VW; e++) if (plain || (kg0 + e <= nz - 1 && (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo))) {
-        xx.v[e] = __fsub_rn(__fsub_rn(xx.v[e], __fmul_rn(M.v[e], dxx.v[e])), __fmul_rn(L.v[e], __fadd_rn(dyy.v[e], dzz.v[e])));
-        yy.v[e] = __fsub_rn(__fsub_rn(yy.v[e], __fmul_rn(M.v[e], dyy.v[e])), __fmul_rn(L.v[e], __fadd_rn(dxx.v[e], dzz.v[e])));
-        zz.v[e] = __fsub_rn(__fsub_rn(zz.v[e], __fmul_rn(M.v[e], dzz.v[e])), __fmul_rn(L.v[e], __fadd_rn(dyy.v[e], dxx.v[e])));
-    }
-    if (fs && kg0 == 0) zz.v[0] = -zz.v[1];                     // free_surface_mirror!: tauzz[1] = -tauzz[2]
-    float* txx = a.tau[T_XX] + q.c; float* tyy = a.tau[T_YY] + q.c; float* tzz = a.tau[T_ZZ] + q.c;
-    st4(txx, xx); st4(tyy, yy); st4(tzz, zz);
-
-    // tauxz: z half, y inner, x half
-    F4 dxz = diff4_zm(cvx, vxprev, g.dzI);      pml_t<1, 0, 1>(q, g, a, dxz);      // @d_zi(vx)
-    F4 dzx = diff4(cvz, vzmx, g.dxI);           pml_t<1, 2, 2>(q, g, a, dzx);      // @d_xi(vz)
-    // tauxy: z inner, y half, x half
-    F4 dxy = diff4(cvx, vxmy, g.dyI);           pml_t<1, 1, 1>(q, g, a, dxy);      // @d_yi(vx)
-    F4 dyx = diff4(cvy, vymx, g.dxI);           pml_t<1, 2, 1>(q, g, a, dyx);      // @d_xi(vy)
-    // tauyz: z half, y half, x inner
-    F4 dyz = diff4_zm(cvy, vyprev, g.dzI);      pml_t<1, 0, 2>(q, g, a, dyz);      // @d_zi(vy)
-    F4 dzy = diff4(cvz, vzmy, g.dyI);           pml_t<1, 1, 2>(q, g, a, dzy);      // @d_yi(vz)
-    F4 xy = lds4(B + S_XY + r * ZC), xz = lds4(B + S_XZ + r * ZC), yz = lds4(B + S_YZ + r * ZC);
-    const F4 muxz = lds4(B + S_MUXZ + r * ZC), muxy = lds4(B + S_MUXY + r * ZC), muyz = lds4(B + S_MUYZ + r * ZC);
-#pragma unroll
-    for (int e = 0; e < VW; e++) {
-        const int k = kg0 + e; const bool own = plain || (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo);
-        if (plain || (own && k >= 1 && k <= nz - 1)) {
-            float n = __fsub_rn(xz.v[e], __fmul_rn(muxz.v[e], __fadd_rn(dxz.v[e], dzx.v[e])));
-            if (!plain && fs && k == 1) n = 0.f;                   // free_surface!(tauxz)
-            xz.v[e] = n;
-            n = __fsub_rn(yz.v[e], __fmul_rn(muyz.v[e], __fadd_rn(dyz.v[e], dzy.v[e])));
-            if (!plain && fs && k == 1) n = 0.f;                   // free_surface!(tauyz)
-            yz.v[e] = n;
+        for (int e = 0; e < VW; e++) if (plain || (kg0 + e <= nz - 1 && (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo))) {
+            xx.v[e] = __fsub_rn(__fsub_rn(xx.v[e], __fmul_rn(M.v[e], dxx.v[e])), __fmul_rn(L.v[e], __fadd_rn(dyy.v[e], dzz.v[e])));
+            yy.v[e] = __fsub_rn(__fsub_rn(yy.v[e], __fmul_rn(M.v[e], dyy.v[e])), __fmul_rn(L.v[e], __fadd_rn(dxx.v[e], dzz.v[e])));
+            zz.v[e] = __fsub_rn(__fsub_rn(zz.v[e], __fmul_rn(M.v[e], dzz.v[e])), __fmul_rn(L.v[e], __fadd_rn(dyy.v[e], dxx.v[e])));
         }
-        if (plain || (own && k >= 1 && k <= nz - 2)) xy.v[e] = __fsub_rn(xy.v[e], __fmul_rn(muxy.v[e], __fadd_rn(dxy.v[e], dyx.v[e])));
+        if (fs && kg0 == 0) zz.v[0] = -zz.v[1];                     // free_surface_mirror!: tauzz[1] = -tauzz[2]
+        st4(a.tau[T_XX] + q.c, xx); st4(a.tau[T_YY] + q.c, yy); st4(a.tau[T_ZZ] + q.c, zz);
+    } else if (C == 1) {   // tauxz: z half, y inner, x half;  tauyz: z half, y half, x inner
+        const F4 cvx = lds4(H + S_VX0 + (r + 1) * PH), cvy = lds4(H + S_VY0 + r * PH), cvz = lds4(H + S_VZ0 + (r + 1) * PH);
+        const F4 vzmx = lds4(B + S_VZM + r * ZC), vzmy = lds4(H + S_VZ0 + r * PH);
+        const float vxprev = z_prev_s(q.mask, cvx, H + S_VX0 + (r + 1) * PH, q.lane, k0 > 0);
+        const float vyprev = z_prev_s(q.mask, cvy, H + S_VY0 + r * PH, q.lane, k0 > 0);
+        F4 dxz = diff4_zm(cvx, vxprev, g.dzI);      pml_t<1, 0, 1>(q, g, a, dxz);      // @d_zi(vx)
+        F4 dzx = diff4(cvz, vzmx, g.dxI);           pml_t<1, 2, 2>(q, g, a, dzx);      // @d_xi(vz)
+        F4 dyz = diff4_zm(cvy, vyprev, g.dzI);      pml_t<1, 0, 2>(q, g, a, dyz);      // @d_zi(vy)
+        F4 dzy = diff4(cvz, vzmy, g.dyI);           pml_t<1, 1, 2>(q, g, a, dzy);      // @d_yi(vz)
+        F4 xz = lds4(B + S_XZ + r * ZC), yz = lds4(B + S_YZ + r * ZC);
+        const F4 muxz = lds4(B + S_MUXZ + r * ZC), muyz = lds4(B + S_MUYZ + r * ZC);
+#pragma unroll
+        for (int e = 0; e < VW; e++) {
+            const int k = kg0 + e; const bool own = plain || (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo);
+            if (plain || (own && k >= 1 && k <= nz - 1)) {
+                float n = __fsub_rn(xz.v[e], __fmul_rn(muxz.v[e], __fadd_rn(dxz.v[e], dzx.v[e])));
+                if (!plain && fs && k == 1) n = 0.f;                   // free_surface!(tauxz)
+                xz.v[e] = n;
+                n = __fsub_rn(yz.v[e], __fmul_rn(muyz.v[e], __fadd_rn(dyz.v[e], dzy.v[e])));
+                if (!plain && fs && k == 1) n = 0.f;                   // free_surface!(tauyz)
+                yz.v[e] = n;
+            }
+        }
+        st4(a.tau[T_XZ] + q.c, xz); st4(a.tau[T_YZ] + q.c, yz);
+    } else {               // tauxy: z inner, y half, x half
+        const F4 cvx = lds4(H + S_VX0 + (r + 1) * PH), vxmy = lds4(H + S_VX0 + r * PH);
+        const F4 cvy = lds4(H + S_VY0 + r * PH), vymx = lds4(B + S_VYM + r * ZC);
+        F4 dxy = diff4(cvx, vxmy, g.dyI);           pml_t<1, 1, 1>(q, g, a, dxy);      // @d_yi(vx)
+        F4 dyx = diff4(cvy, vymx, g.dxI);           pml_t<1, 2, 1>(q, g, a, dyx);      // @d_xi(vy)
+        F4 xy = lds4(B + S_XY + r * ZC);
+        const F4 muxy = lds4(B + S_MUXY + r * ZC);
+#pragma unroll
+        for (int e = 0; e < VW; e++) {
+            const int k = kg0 + e; const bool own = plain || (unsigned)(k0 + e - g.klo) <= (unsigned)(g.khi - g.klo);
+            if (plain || (own && k >= 1 && k <= nz - 2)) xy.v[e] = __fsub_rn(xy.v[e], __fmul_rn(muxy.v[e], __fadd_rn(dxy.v[e], dyx.v[e])));
+        }
+        st4(a.tau[T_XY] + q.c, xy);
     }
-    float* txy = a.tau[T_XY] + q.c; float* txz = a.tau[T_XZ] + q.c; float* tyz = a.tau[T_YZ] + q.c;
-    st4(txz, xz); st4(txy, xy); st4(tyz, yz);
 }
 
 // z-CPML coefficient tables, re-indexed like the memory rows: zi < PZM/2 is the min slab (zi = k), the upper half
@@ -523,11 +635,58 @@ __device__ __forceinline__ void fill_zt(const Geom& g, const StepArgs& a, float*
         ZT[idx] = (k >= 0 && k <= g.nz && tab) ? __ldg(tab + k) : (cc == 2 ? 1.f : 0.f);
     }
 }
-// one consumer lane: the same tile sequence as the producer (see there for the range arguments)
+// The outer shell of the box (rigid faces, ghost cells, ragged x / y ranges: every row of the planes sc.sp[], the rows sc.sr[] of the
+// fast planes; 2.4 % of the cells at C3) is the scalar reference-order code.  It touches cells no tile touches and reads only fields
+// this half step does not write, so it needs no ordering against the tiles: NSHELL warps of every CTA walk the shell lines beside the
+// tile pipeline, in issue slots the consumers leave idle (as a separate launch it could not become resident next to two tile CTAs that
+// fill the register file, and ran as a 40 - 80 us tail).  line -> (plane, row): as k_shell3.
+__device__ __forceinline__ void shell_line_ji(const Geom& g, const Sched& sc, int L, int& i, int& j) {
+    if (L < sc.nsp * g.ny1) { const int q = L / g.ny1; i = sc.sp[q]; j = L - q * g.ny1; }
+    else { const int L2 = L - sc.nsp * g.ny1; const int q = L2 / sc.nsr; i = sc.ilo + q; j = sc.sr[L2 - q * sc.nsr]; }
+}
 template <int KIND>
-__device__ __forceinline__ void consumer(const Geom& g, const StepArgs& a, const Sched& sc, const float* stage0, const float* ZT,
-                                         sptr_t full0, sptr_t empty0, int warp, int lane, int t_first, int t_step, int t_end, int n0) {
+__device__ __forceinline__ void shell_lines(const Geom& g, const StepArgs& a, const Sched& sc, int first, int step, int lane) {
+    const int nlines = sc.nsp * g.ny1 + (sc.ihi - sc.ilo + 1) * sc.nsr;
+    for (int L = first; L < nlines; L += step) {
+        int i, j;
+        shell_line_ji(g, sc, L, i, j);
+        for (int k = lane; k < g.pz; k += 32) if (k >= g.klo && k <= g.khi) {
+            if (KIND == 0) vel_cell<3, 1>(g, a, k, j, i, 0);
+            else           stress_cell<3, 1>(g, a, k, j, i, 0);
+        }
+    }
+}
+// shell unit u = 32 consecutive z cells of a shell line (SHELLC: one unit per consumer warp every SHELL_EVERY tiles, the rest after the last tile)
+__device__ __forceinline__ int shell_units(const Geom& g, const Sched& sc) { return (sc.nsp * g.ny1 + (sc.ihi - sc.ilo + 1) * sc.nsr) * (g.pz >> 5); }
+template <int KIND>
+__device__ __forceinline__ void shell_unit(const Geom& g, const StepArgs& a, const Sched& sc, int u, int lane) {
+    const int nzq = g.pz >> 5;                            // pz is a multiple of 32
+    const int L = u / nzq, k = (u - L * nzq) * 32 + lane;
+    int i, j;
+    shell_line_ji(g, sc, L, i, j);
+    if (k >= g.klo && k <= g.khi) {
+        if (KIND == 0) vel_cell<3, 1>(g, a, k, j, i, 0);
+        else           stress_cell<3, 1>(g, a, k, j, i, 0);
+    }
+}
+// consumer warp `warp` of CTA `cta` (of nctas): its q-th unit
+template <int KIND>
+__device__ __forceinline__ int shell_unit_of(int cta, int nctas, int warp, int q) { return cta * L<KIND>::NCW + warp + q * nctas * L<KIND>::NCW; }
+// units left after a CTA's ntl tiles (ntl tiles gave warp w a turn at n % SHELL_EVERY == w)
+template <int KIND>
+__device__ __forceinline__ void shell_tail(const Geom& g, const StepArgs& a, const Sched& sc, int cta, int nctas, int ntl, int warp, int lane) {
+    const int nu = shell_units(g, sc);
+    int q = ntl > warp ? (ntl - warp + SHELL_EVERY - 1) / SHELL_EVERY : 0;
+    for (int u = shell_unit_of<KIND>(cta, nctas, warp, q); u < nu; u = shell_unit_of<KIND>(cta, nctas, warp, ++q)) shell_unit<KIND>(g, a, sc, u, lane);
+}
+
+// one consumer lane of output group COMP, row r: the same tile sequence as the producer (see there for the range arguments)
+template <int KIND, int COMP>
+__device__ __forceinline__ void consumer_group(const Geom& g, const StepArgs& a, const Sched& sc, const float* stage0, const float* ZT,
+                                               sptr_t full0, sptr_t empty0, int warp, int r, int lane, int t_first, int t_step, int t_end, int n0) {
     constexpr int SFLOATS = K<KIND>::SFLOATS;
+    const int cta = blockIdx.x, nctas = gridDim.x;
+    const int nu = L<KIND>::SHELLC ? shell_units(g, sc) : 0;
     T3_TILE_LOOP(t, n) {
         const int s = n % STAGES;
         const uint32_t use = n / STAGES;
@@ -538,24 +697,45 @@ __device__ __forceinline__ void consumer(const Geom& g, const StepArgs& a, const
 #endif
         TileCtx q;
         q.ZT = ZT;
-        open_tile<KIND>(q, g, a, S, warp, lane);
+        open_tile<KIND, COMP>(q, g, a, S, r, lane);
         const bool active = q.j <= sc.jhi && q.k0 < g.pz;
         q.mask = __ballot_sync(0xffffffffu, active);
         if (active) {
-            if (KIND == 0) vel_tile(g, a, q); else stress_tile(g, a, q);
+            if (COMP == 3) {         // one warp, the three output groups in turn
+                if (KIND == 0) { vel_tile<0>(g, a, q); vel_tile<1>(g, a, q); vel_tile<2>(g, a, q); }
+                else { stress_tile<0>(g, a, q); stress_tile<1>(g, a, q); stress_tile<2>(g, a, q); }
+            } else if (KIND == 0) vel_tile<COMP>(g, a, q); else stress_tile<COMP>(g, a, q);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * s);
+        if (L<KIND>::SHELLC && n % SHELL_EVERY == warp) {          // this warp's turn: one shell unit in the slack before the next tile lands
+            const int u = shell_unit_of<KIND>(cta, nctas, warp, n / SHELL_EVERY);
+            if (u < nu) shell_unit<KIND>(g, a, sc, u, lane);
+        }
     }
+#ifndef GPI_HOST_EMU
+    if (L<KIND>::SHELLC) shell_tail<KIND>(g, a, sc, cta, nctas, n, warp, lane);     // n = tiles this CTA had
+#endif
+}
+// consumer warp w: row w / NCOMP, output group w % NCOMP (the four warps an SM sub-partition gets hold all three groups)
+template <int KIND>
+__device__ __forceinline__ void consumer(const Geom& g, const StepArgs& a, const Sched& sc, const float* stage0, const float* ZT,
+                                         sptr_t full0, sptr_t empty0, int warp, int lane, int t_first, int t_step, int t_end, int n0) {
+    constexpr int NCOMP = L<KIND>::NCOMP;
+    const int r = warp / NCOMP, comp = warp - r * NCOMP;
+    if (NCOMP == 1)     consumer_group<KIND, 3>(g, a, sc, stage0, ZT, full0, empty0, warp, r, lane, t_first, t_step, t_end, n0);
+    else if (comp == 0) consumer_group<KIND, 0>(g, a, sc, stage0, ZT, full0, empty0, warp, r, lane, t_first, t_step, t_end, n0);
+    else if (comp == 1) consumer_group<KIND, 1>(g, a, sc, stage0, ZT, full0, empty0, warp, r, lane, t_first, t_step, t_end, n0);
+    else                consumer_group<KIND, 2>(g, a, sc, stage0, ZT, full0, empty0, warp, r, lane, t_first, t_step, t_end, n0);
 }
 
 #ifdef GPI_HOST_EMU
 // CPU emulation of one CTA (run by the launch's "thread 0" of each block; the other 159 return): shared memory is a heap block,
-// the tiles of the CTA are taken one after the other -- producer, then the 4 x 32 consumer lanes.
+// the tiles of the CTA are taken one after the other -- producer, then the NCW x 32 consumer lanes.
 template <int KIND>
 void k_step3t(const Geom g, const StepArgs a, const Sched sc, const Maps* tm) {
     if (threadIdx.x != 0) return;
-    constexpr int SFLOATS = K<KIND>::SFLOATS;
+    constexpr int SFLOATS = K<KIND>::SFLOATS, NPROD = L<KIND>::NPROD, NCW = L<KIND>::NCW, NSHELL = L<KIND>::NSHELL;
     const size_t nbytes = smem_bytes(KIND);
     unsigned char* smem_raw = static_cast<unsigned char*>(aligned_alloc(128, (nbytes + 127) / 128 * 128));
     memset(smem_raw, 0xff, nbytes);                       // shared memory starts as garbage (NaN patterns), not zeros
@@ -564,19 +744,23 @@ void k_step3t(const Geom g, const StepArgs a, const Sched sc, const Maps* tm) {
     const sptr_t full0 = s32(bars), empty0 = s32(bars + STAGES);
     float* ZT = reinterpret_cast<float*>(bars + 2 * STAGES);
     fill_zt<KIND>(g, a, ZT, 0, 1);
-    for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NCW); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, NPROD); mbar_init(empty0 + 8 * s, NCW); }
     int n = 0;
     for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x, n++) {
-        producer<KIND>(g, sc, tm, stage0, full0, empty0, t, 1, t + 1, n);
+        for (int p = 0; p < NPROD; p++) producer_any<KIND>(p, g, sc, tm, stage0, full0, empty0, t, 1, t + 1, n);
         for (int warp = 0; warp < NCW; warp++) for (int lane = 0; lane < 32; lane++)
             consumer<KIND>(g, a, sc, stage0, ZT, full0, empty0, warp, lane, t, 1, t + 1, n);
     }
+    for (int w = 0; w < NSHELL; w++) for (int lane = 0; lane < 32; lane++)
+        shell_lines<KIND>(g, a, sc, blockIdx.x * NSHELL + w, gridDim.x * NSHELL, lane);
+    if (L<KIND>::SHELLC) for (int warp = 0; warp < NCW; warp++) for (int lane = 0; lane < 32; lane++)
+        shell_tail<KIND>(g, a, sc, blockIdx.x, gridDim.x, n, warp, lane);
     free(smem_raw);
 }
 #else
 template <int KIND>
-__global__ void __launch_bounds__(NTHREADS, T3_MINB) k_step3t(const Geom g, const StepArgs a, const Sched sc, const Maps* __restrict__ tm) {
-    constexpr int SFLOATS = K<KIND>::SFLOATS;
+__global__ void __launch_bounds__(L<KIND>::NTHREADS, T3_MINB) k_step3t(const Geom g, const StepArgs a, const Sched sc, const Maps* __restrict__ tm) {
+    constexpr int SFLOATS = K<KIND>::SFLOATS, NPROD = L<KIND>::NPROD, NCW = L<KIND>::NCW, NSHELL = L<KIND>::NSHELL, NTHREADS = L<KIND>::NTHREADS;
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     unsigned char* smem_raw = smem_dyn + ((128 - (s32(smem_dyn) & 127)) & 127);      // boxes need 128-byte alignment
     float* stage0 = reinterpret_cast<float*>(smem_raw);
@@ -586,13 +770,14 @@ __global__ void __launch_bounds__(NTHREADS, T3_MINB) k_step3t(const Geom g, cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     fill_zt<KIND>(g, a, ZT, threadIdx.x, NTHREADS);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NCW); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, NPROD); mbar_init(empty0 + 8 * s, NCW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == NCW) {
-        if (lane == 0) producer<KIND>(g, sc, tm, stage0, full0, empty0, 0, 0, 0, 0);
+    if (warp >= NCW + NPROD) { shell_lines<KIND>(g, a, sc, blockIdx.x * NSHELL + (warp - NCW - NPROD), gridDim.x * NSHELL, lane); return; }
+    if (warp >= NCW) {
+        if (lane == 0) producer_any<KIND>(warp - NCW, g, sc, tm, stage0, full0, empty0, 0, 0, 0, 0);
         return;
     }
     consumer<KIND>(g, a, sc, stage0, ZT, full0, empty0, warp, lane, 0, 0, 0, 0);
