@@ -174,6 +174,7 @@ struct gpi_handle {
     bool tma3 = true;  int num_sms = 148;  int tma3_ctas = 0;  bool tma3_force = false;   // GPI_TMA3=2: TMA kernels whatever the tile utilisation
     int shell_mode = 1;                                 // GPI_SHELL=0: shell kernel serialised behind the tile kernel (diagnostic)
     bool o4vec = true;                                  // order-4 kernels with four z cells per thread (kernels4v.cuh); GPI_O4VEC=0 selects the scalar ones
+    bool fuse2a = true;      // fused 2-D acoustic adjoint (kernels2a.cuh); GPI_FUSE2A=0 opts out
     t3::TileRec* t3_tiles[2] = {nullptr, nullptr};      // tile tables of the two tile kernels (geometry only: built once per handle)
     struct TmaSet { const float* key = nullptr; t3::Maps* d[2] = {nullptr, nullptr}; } tmaps[2];  int tmap_victim = 0;   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
     void* encode_tiled = nullptr;                                            // cuTensorMapEncodeTiled (driver entry point)   // 3-D elastic: TMA-pipelined persistent kernels (kernels3t.cuh); GPI_TMA3=0 selects k_*3v
@@ -881,6 +882,7 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (const char* e = getenv("GPI_TMA3")) { h->tma3 = atoi(e) != 0; h->tma3_force = atoi(e) == 2; }
     if (const char* e = getenv("GPI_TMA3_CTAS")) h->tma3_ctas = atoi(e);
     if (const char* e = getenv("GPI_SHELL")) h->shell_mode = atoi(e);
+    if (const char* e = getenv("GPI_FUSE2A")) h->fuse2a = atoi(e) != 0;
     if (const char* e = getenv("GPI_O4VEC")) h->o4vec = atoi(e) != 0;
     if (const char* e = getenv("GPI_PINGPONG")) h->pingpong = atoi(e) != 0;
     if (h->nd == 3 && h->el) {
@@ -1414,6 +1416,21 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
         const bool merge_pw = h->npw == 2 && (activepw & 3) == 3 && !born && h->c.order == 2 && h->nd == 2;
         StepArgs margs;
         if (merge_pw) fill_args(h, margs, 0, nb, true);
+        // 2-D acoustic adjoint with ping-pong levels: stress update of both wavefields and the imaging in one pass (kernels2a.cuh)
+        int n_stress_ops = 0;
+        for (int b = 0; b < nb; b++) n_stress_ops = std::max(n_stress_ops, h->h_post_s[b].ninj);
+        const bool fuse2a = h->fuse2a && pp && grad && merge_pw && !h->el && !unshifted && n_stress_ops == 0;      // stress sources act between update and imaging
+        Grad2aArgs ga2{};
+        if (fuse2a) {
+            int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
+            field_shape(h->nd, GPI_P, n, sh, off, h->c.order);
+            ga2.gK = h->gshot; ga2.gR = h->gshot + g.vol; ga2.gstride = 2 * g.vol;
+            ga2.dtI = (float)h->c.dtI; ga2.stash = h->stash_table; ga2.nb = h->c.nbound;
+            const int npx = (h->c.pml_faces & XMIN) ? h->c.npml : 0, npz = (h->c.pml_faces & ZMIN) ? h->c.npml : 0;     // as launch_boundary
+            ga2.xlo = npx + off[2]; ga2.xhi = sh[2] - npx - h->c.nbound + off[2];
+            ga2.zlo = npz + off[0]; ga2.zhi = sh[0] - npz - h->c.nbound + off[0];
+            ga2.k0 = off[0]; ga2.nk = off[0] + sh[0]; ga2.i0 = off[2]; ga2.ni = off[2] + sh[2];
+        }
         if (born) { args[0].dout[0] = h->born_d; args[0].dout[1] = h->born_d + g.vol; args[0].dstride = 2 * g.vol; }
         // record!(1, ..., [:p]) at the start of step 1 (zero unless the fields were loaded from snapshots)
         if (rec_s) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, 1, 1, nt, (float)h->c.dt, 2, 0LL); h->timers.launches += 1; }
@@ -1452,7 +1469,18 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             }
             if (do_post_v) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_v, it, it, nt, (float)h->c.dt, 3, woff); h->timers.launches += 1; }
             if (exchange_halos(h, 1, sample)) return 1;
-            if (merge_pw) launch_step(h, pp ? rebase(margs, A, Bn, false) : margs, false, margs.nbatch, sample);
+            if (fuse2a) {
+                cudaEvent_t e0 = nullptr, e1 = nullptr;
+                if (sample) { e0 = sample_event(h); e1 = sample_event(h); }
+                if (e0 && e1) { cudaEventRecord(e0, h->stream); h->evkind.push_back(1); }
+                ga2.vxA = wf_ptr(h, A, 0, 0, GPI_VX); ga2.vzA = wf_ptr(h, A, 0, 0, GPI_VZ);
+                const int nthreads = (g.pz / VW) * g.nx1;
+                dim3 blk(128), grd((nthreads + 127) / 128, nb);
+                k_stress2a<<<grd, blk, 0, h->stream>>>(g, rebase(margs, A, Bn, false), ga2);
+                if (e0 && e1) cudaEventRecord(e1, h->stream);
+                h->timers.launches += 1;
+            }
+            else if (merge_pw) launch_step(h, pp ? rebase(margs, A, Bn, false) : margs, false, margs.nbatch, sample);
             else for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) launch_step(h, pp ? rebase(args[ipw], A, Bn, false) : args[ipw], false, nb, sample && ipw == 0);
             if (born) {        // add_born_sources_stress! (propagate.jl:226)
                 dim3 blk = h->blk2, grd = grid_for(h, blk, nb);
@@ -1465,7 +1493,9 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                 h->timers.launches += 1;
             }
             if (pp) {
-                if (launch_boundary(h, 0, nb, 0, A, h->stash_table)) return 1;      // the previous level as save_tp! would have left it
+                // the previous level as save_tp! would have left it (the fused pass has read the pre-force values from the stash already,
+                // and level A is overwritten by the next step: no restore)
+                if (!fuse2a && launch_boundary(h, 0, nb, 0, A, h->stash_table)) return 1;
                 cur = Bn; prev = A;
             }
             if (exchange_halos(h, 0, sample)) return 1;
@@ -1507,7 +1537,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                     k_grad3d<<<grd, blk, 0, h->stream>>>(g, ga, (float)h->c.dtI, unshifted);
                     h->timers.launches += 1;
                 }
-            } else if (grad) {
+            } else if (grad && !fuse2a) {
                 dim3 blk = h->blk2, grd = grid_for(h, blk, nb);
                 k_grad2d<<<grd, blk, 0, h->stream>>>(g,
                     wf_ptr(h, cur, 0, 0, GPI_P), wf_ptr(h, prev, 0, 0, GPI_P), wf_ptr(h, prev, 0, 1, GPI_P),

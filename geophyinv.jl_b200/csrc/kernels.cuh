@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(256) k_stress(const Geom g, const StepArgs a) 
 
 #include "kernels3d.cuh"
 #include "kernels2v.cuh"
+#include "kernels2a.cuh"
 #if !defined(GPI_HOST_EMU) || defined(GPI_EMU_T3)   // tests/emu: the kernel-level harnesses leave the TMA kernels out; the emulated engine (cuda_rt_shim.h) takes their host forms
 #include "kernels3t.cuh"
 #endif
