@@ -447,6 +447,8 @@ def run_c5(args, steps=None, warmup=None):
     warmup = args.warmup if warmup is None else warmup
     small = args.workload == "c5small" or args.c5_small
     ni = (96, 128, 128) if small else (512, 1024, 1024)
+    if getattr(args, "c5_ni", None):           # e.g. 68,1024,1024 on 2 GPUs: the 75-plane slab windows C5 has on 8 GPUs
+        ni = tuple(int(v) for v in args.c5_ni.split(","))
     d = 10.0
     grid = [StepRange(0.0, d, m) for m in ni]
     nt = (args.nt if args.workload in ("c5", "c5small") else None) or 200
@@ -664,6 +666,7 @@ def main():
     ap.add_argument("--order", type=int, default=2, help="_fd_order: 2 (default, the reference's default) or 4")
     ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C5 legs that follow the headline C3 leg")
     ap.add_argument("--c5-small", action="store_true", help="extra C5 leg on the 96 x 128 x 128 debug grid")
+    ap.add_argument("--c5-ni", default=None, help="interior cells nz,ny,nx of the c5 workload (debug / slab-shape studies)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

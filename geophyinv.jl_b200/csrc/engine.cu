@@ -174,9 +174,10 @@ struct gpi_handle {
     bool tma3 = true;  int num_sms = 148;  int tma3_ctas = 0;  bool tma3_force = false;   // GPI_TMA3=2: TMA kernels whatever the tile utilisation
     int shell_mode = 1;                                 // GPI_SHELL=0: shell kernel serialised behind the tile kernel (diagnostic)
     bool o4vec = true;                                  // order-4 kernels with four z cells per thread (kernels4v.cuh); GPI_O4VEC=0 selects the scalar ones
+    int pzalign = 8;                                    // GPI_PZ_ALIGN (4, 8, 16, 32 floats)
     bool fuse2a = true;      // fused 2-D acoustic adjoint (kernels2a.cuh); GPI_FUSE2A=0 opts out
-    t3::TileRec* t3_tiles[2] = {nullptr, nullptr};      // tile tables of the two tile kernels (geometry only: built once per handle)
-    struct TmaSet { const float* key = nullptr; t3::Maps* d[2] = {nullptr, nullptr}; } tmaps[2];  int tmap_victim = 0;   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
+    void* t3_tiles[2] = {nullptr, nullptr};      // tile tables of the two tile kernels (geometry only: built once per handle)
+    struct TmaSet { const float* key = nullptr; void* d[2] = {nullptr, nullptr}; } tmaps[2];  int tmap_victim = 0;   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
     void* encode_tiled = nullptr;                                            // cuTensorMapEncodeTiled (driver entry point)   // 3-D elastic: TMA-pipelined persistent kernels (kernels3t.cuh); GPI_TMA3=0 selects k_*3v
     bool vec2 = true;                                   // 2-D: float4-per-thread kernels (kernels2v.cuh); GPI_SCALAR2D=1 selects the scalar ones
     int blkv = GPI_VEC_THREADS;  bool vec3 = true;      // 3-D: float4-per-thread kernels (kernels3d.cuh); GPI_SCALAR3D=1 selects the scalar ones
@@ -327,17 +328,18 @@ int encode_map(gpi_handle* h, void* out, const float* base, const cuuint64_t dim
     if (rc != CUDA_SUCCESS) FAIL(h, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
     return 0;
 }
-int build_tmaps(gpi_handle* h, const StepArgs& a, int kind, t3::Maps** dout) {
+template <class T>
+int build_tmaps(gpi_handle* h, const StepArgs& a, int kind, void** dout) {
     const Geom& g = h->g;
-    const int nbox = kind == 0 ? (int)t3::V_NBOX : (int)t3::S_NBOX;
-    t3::Maps hm;
+    const int nbox = kind == 0 ? (int)T::V_NBOX_ : (int)T::S_NBOX_;
+    typename T::MapsT hm;
     memset(&hm, 0, sizeof hm);
     const cuuint64_t fdims[3] = {(cuuint64_t)g.pz, (cuuint64_t)g.ny1, (cuuint64_t)g.nx1};
     for (int b = 0; b < nbox; b++) {
-        const t3::BoxSpec bs = t3::box_spec(kind, b);
+        const auto bs = T::box(kind, b);
         const float* base = bs.arr < 6 ? a.tau[bs.arr] : bs.arr < 9 ? a.v[bs.arr - 6] : a.c[bs.arr - 9];
         if (!base) FAIL(h, "TMA descriptor: operand %d of kernel %d is not allocated", bs.arr, kind);
-        if (encode_map(h, hm.m[b], base, fdims, bs.halo ? t3::PH : t3::ZC, bs.rows)) return 1;
+        if (encode_map(h, hm.m[b], base, fdims, bs.halo ? T::PH_ : T::ZC_, bs.rows)) return 1;
     }
     const cuuint64_t np2 = 2 * (cuuint64_t)g.npml;
     const cuuint64_t xdims[3] = {(cuuint64_t)g.pz, (cuuint64_t)g.ny1, np2};
@@ -345,19 +347,19 @@ int build_tmaps(gpi_handle* h, const StepArgs& a, int kind, t3::Maps** dout) {
     const cuuint64_t zdims[3] = {(cuuint64_t)g.pzm, (cuuint64_t)g.ny1, (cuuint64_t)g.nx1};
     for (int q = 0; q < 3; q++) {
         const PmlTerm* terms = kind == 0 ? a.pv : a.ps;
-        const float* mx = terms[t3::term_index(kind, 2, q)].mem;
-        const float* my = terms[t3::term_index(kind, 1, q)].mem;
-        const float* mz = terms[t3::term_index(kind, 0, q)].mem;
-        if (mx && (g.pml & (XMIN | XMAX)) && encode_map(h, hm.m[nbox + q], mx, xdims, t3::ZC, t3::R)) return 1;
-        if (my && (g.pml & (YMIN | YMAX)) && encode_map(h, hm.m[nbox + 3 + q], my, ydims, t3::ZC, t3::R)) return 1;
-        if (mz && (g.pml & (ZMIN | ZMAX)) && encode_map(h, hm.m[nbox + 6 + q], mz, zdims, t3::PZM, t3::R)) return 1;
+        const float* mx = terms[T::term(kind, 2, q)].mem;
+        const float* my = terms[T::term(kind, 1, q)].mem;
+        const float* mz = terms[T::term(kind, 0, q)].mem;
+        if (mx && (g.pml & (XMIN | XMAX)) && encode_map(h, hm.m[nbox + q], mx, xdims, T::ZC_, T::R_)) return 1;
+        if (my && (g.pml & (YMIN | YMAX)) && encode_map(h, hm.m[nbox + 3 + q], my, ydims, T::ZC_, T::R_)) return 1;
+        if (mz && (g.pml & (ZMIN | ZMAX)) && encode_map(h, hm.m[nbox + 6 + q], mz, zdims, T::PZM_, T::R_)) return 1;
     }
-    if (!*dout) CU(h, cudaMalloc((void**)dout, sizeof(t3::Maps)));
+    if (!*dout) CU(h, cudaMalloc(dout, sizeof hm));
     CU(h, cudaMemcpyAsync(*dout, &hm, sizeof hm, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
-template <int KIND>
+template <class T, int KIND>
 int launch_step3t(gpi_handle* h, const StepArgs& a) {
     const Geom& g = h->g;
     // descriptors are cached per wavefield set, keyed by the set's first pointer (ping-pong runs swap W and TP: a new key rebuilds them)
@@ -365,10 +367,10 @@ int launch_step3t(gpi_handle* h, const StepArgs& a) {
     for (auto& ts : h->tmaps) if (ts.key == a.v[0]) set = &ts;
     if (!set) {
         set = &h->tmaps[h->tmap_victim]; h->tmap_victim ^= 1;      // two sets (pw 1, pw 2), replaced in turn
-        if (build_tmaps(h, a, 0, &set->d[0]) || build_tmaps(h, a, 1, &set->d[1])) return 1;
+        if (build_tmaps<T>(h, a, 0, &set->d[0]) || build_tmaps<T>(h, a, 1, &set->d[1])) return 1;
         set->key = a.v[0];
     }
-    t3::Sched sc{};
+    typename T::SchedT sc{};
     if (KIND == 0) {
         sc.ilo = 2; sc.ihi = g.nx - 2; sc.jlo = 2; sc.jhi = g.ny - 2;
         sc.nsp = 4; sc.sp[0] = 0; sc.sp[1] = 1; sc.sp[2] = g.nx - 1; sc.sp[3] = g.nx;
@@ -378,37 +380,39 @@ int launch_step3t(gpi_handle* h, const StepArgs& a) {
         sc.nsp = 3; sc.sp[0] = 0; sc.sp[1] = g.nx - 1; sc.sp[2] = g.nx;
         sc.nsr = 3; sc.sr[0] = 0; sc.sr[1] = g.ny - 1; sc.sr[2] = g.ny;
     }
-    sc.njb = (sc.jhi - sc.jlo + 1 + t3::R - 1) / t3::R;
-    sc.nzc = (g.pz + t3::ZC - 1) / t3::ZC;
+    sc.njb = (sc.jhi - sc.jlo + 1 + T::R_ - 1) / T::R_;
+    sc.nzc = (g.pz + T::ZC_ - 1) / T::ZC_;
     sc.ntiles = (sc.ihi - sc.ilo + 1) * sc.njb * sc.nzc;
     if (!h->t3_tiles[KIND]) {
-        std::vector<t3::TileRec> tab((size_t)sc.ntiles);
-        t3::fill_tile_table(g, sc, KIND, tab.data());
-        CU(h, cudaMalloc((void**)&h->t3_tiles[KIND], tab.size() * sizeof(t3::TileRec)));
-        CU(h, cudaMemcpy(h->t3_tiles[KIND], tab.data(), tab.size() * sizeof(t3::TileRec), cudaMemcpyHostToDevice));
+        std::vector<typename T::TileRecT> tab((size_t)sc.ntiles);
+        T::tiles(g, sc, KIND, tab.data());
+        CU(h, cudaMalloc(&h->t3_tiles[KIND], tab.size() * sizeof(typename T::TileRecT)));
+        CU(h, cudaMemcpy(h->t3_tiles[KIND], tab.data(), tab.size() * sizeof(typename T::TileRecT), cudaMemcpyHostToDevice));
     }
-    sc.tiles = h->t3_tiles[KIND];
-    const int nctas = std::max(1, std::min(sc.ntiles, h->tma3_ctas > 0 ? h->tma3_ctas : T3_MINB * h->num_sms));
-    // The shell touches cells no tile touches and reads only fields this half step does not write, so it runs
-    // beside the persistent tile kernel on a side stream (it needs no shared memory and fits next to the two
-    // resident tile CTAs of an SM).  The tile kernel is launched FIRST: its tiles are assigned statically, so
-    // every CTA must become resident at once -- shell blocks that got to the SMs earlier would delay some of
-    // them by the shell's whole duration.
+    sc.tiles = static_cast<const typename T::TileRecT*>(h->t3_tiles[KIND]);
+    const int nctas = std::max(1, std::min(sc.ntiles, h->tma3_ctas > 0 ? h->tma3_ctas : T::MINB_ * h->num_sms));
+    typedef typename T::template Lay<KIND> Lay;
+    const auto k_tile = T::template tile_kernel<KIND>();
+    const auto k_shell = T::template shell_kernel<KIND>();
+    const typename T::MapsT* maps = static_cast<const typename T::MapsT*>(set->d[KIND]);
     const int nlines = sc.nsp * g.ny1 + (sc.ihi - sc.ilo + 1) * sc.nsr;
-    if (t3::L<KIND>::INKERNEL_SHELL || h->shell_mode == 2) {      // the shell lines are walked by warps of the tile kernel itself (GPI_SHELL=2 with a NSHELL = 0 build: no shell at all, timing only)
-        t3::k_step3t<KIND><<<nctas, t3::L<KIND>::NTHREADS, t3::smem_bytes(KIND), h->stream>>>(g, a, sc, set->d[KIND]);
+    if (Lay::INKERNEL_SHELL || h->shell_mode == 2) {      // the shell lines are walked by warps of the tile kernel itself (GPI_SHELL=2 with a NSHELL = 0 build: no shell at all, timing only)
+        k_tile<<<nctas, Lay::NTHREADS, T::smem(KIND), h->stream>>>(g, a, sc, maps);
         return 0;
     }
+    // NSHELL = 0 builds: the shell is a launch of its own.  It touches cells no tile touches and reads only fields this half step
+    // does not write, so it runs on a side stream; the tile kernel is launched FIRST: its tiles are assigned statically, so every
+    // CTA must become resident at once.
     if (h->shell_mode == 0) {          // GPI_SHELL=0 (diagnostic): shell after the tiles on the same stream
-        t3::k_step3t<KIND><<<nctas, t3::L<KIND>::NTHREADS, t3::smem_bytes(KIND), h->stream>>>(g, a, sc, set->d[KIND]);
-        t3::k_shell3<KIND><<<nlines, 128, 0, h->stream>>>(g, a, sc);
+        k_tile<<<nctas, Lay::NTHREADS, T::smem(KIND), h->stream>>>(g, a, sc, maps);
+        k_shell<<<nlines, 128, 0, h->stream>>>(g, a, sc);
         h->timers.launches += 1;
         return 0;
     }
     CU(h, cudaEventRecord(h->ev_fork, h->stream));
-    t3::k_step3t<KIND><<<nctas, t3::L<KIND>::NTHREADS, t3::smem_bytes(KIND), h->stream>>>(g, a, sc, set->d[KIND]);
+    k_tile<<<nctas, Lay::NTHREADS, T::smem(KIND), h->stream>>>(g, a, sc, maps);
     CU(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    t3::k_shell3<KIND><<<nlines, 128, 0, h->side>>>(g, a, sc);
+    k_shell<<<nlines, 128, 0, h->side>>>(g, a, sc);
     CU(h, cudaEventRecord(h->ev_join, h->side));
     CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->timers.launches += 1;
@@ -416,8 +420,9 @@ int launch_step3t(gpi_handle* h, const StepArgs& a) {
 }
 bool tma3_eligible(const gpi_handle* h) {
     const Geom& g = h->g;
-    const int zext = g.khi - g.klo + 1, zchunks = (g.pz + t3::ZC - 1) / t3::ZC;
-    const bool tiles_fill = h->tma3_force || 4 * zext >= 3 * zchunks * t3::ZC;
+    const int zc = t3::ZC;
+    const int zext = g.khi - g.klo + 1, zchunks = (g.pz + zc - 1) / zc;
+    const bool tiles_fill = h->tma3_force || 4 * zext >= 3 * zchunks * zc;
     return h->nd == 3 && h->el && h->c.order == 2 && h->vec3 && h->tma3 && tiles_fill && g.pzm == t3::PZM && g.nx >= 2 * g.npml + 8 && g.ny >= 2 * g.npml + 8;
 }
 template <int EL>
@@ -428,7 +433,7 @@ void launch_step_kernels3v(gpi_handle* h, const StepArgs& a, bool vel, int nbatc
     // 75 % tile utilisation (C3: 339 of 384 = 0.88 -> TMA; C5 on 4 GPUs: 150 of 256 = 0.59 -> k_*3v).
     const bool oop = vel ? a.v_o[V_X] != nullptr : a.tau_o[T_XX] != nullptr;       // ping-pong adjoint runs: the register-staged kernels
     if (EL && nbatch == 1 && !oop && tma3_eligible(h)) {
-        if ((vel ? launch_step3t<0>(h, a) : launch_step3t<1>(h, a)) == 0) return;
+        if ((vel ? launch_step3t<t3::Tr, 0>(h, a) : launch_step3t<t3::Tr, 1>(h, a)) == 0) return;
         h->tma3 = false;                        // descriptor creation failed: fall back to the register-staged kernels
     }
     const int ngroups = vec3_threads(g.pz, g.ny1);
@@ -699,7 +704,14 @@ static int create_impl(gpi_handle* h) {
         g.klo = h->ka - g.koff;
         g.khi = h->kb - 1 - g.koff;
     }
-    g.pz = ((g.khi + 2 + 31) / 32) * 32;
+    {
+        // z pitch: nodes 0..khi+1 rounded up to `pzalign` floats.  Every vector access needs 16 bytes (4 floats); the default keeps
+        // whole 32-byte sectors per row (8 floats) -- rounding rows up to 128-byte lines costs 28 % of the traffic of a 75-plane
+        // z-slab window (77 -> 96 floats) and 2.3 % at C3 (339 -> 352), and buys nothing: rows are contiguous in memory anyway
+        int pzalign = h->pzalign;
+        if (pzalign != 4 && pzalign != 8 && pzalign != 16 && pzalign != 32) pzalign = 8;
+        g.pz = ((g.khi + 2 + pzalign - 1) / pzalign) * pzalign;
+    }
     h->pzt = ((g.nz + 64 + 31) / 32) * 32;
     g.ny1 = h->nd == 3 ? g.ny + 1 + 2 * g.h : 1;
     g.nx1 = g.nx + 1 + 2 * g.h;
@@ -708,6 +720,7 @@ static int create_impl(gpi_handle* h) {
     g.pml = c.pml_faces; g.rigid = c.rigid_faces; g.freesurf = c.stressfree_faces;
     g.dzI = (float)c.dI[0]; g.dyI = (float)c.dI[1]; g.dxI = (float)c.dI[2];
     g.vol = (long long)g.pz * g.ny1 * g.nx1;
+    if (const char* e = getenv("GPI_VOL_PAD")) g.vol += (atoll(e) + 31) / 32 * 32;      // tuning: floats of padding between consecutive field volumes
     if (g.vol >= (1LL << 31)) FAIL(h, "grid of %lld unified cells exceeds the 32-bit cell index of the source/receiver tables", g.vol);
     // the min and max CPML slabs of a derivative field must not overlap (the reference would apply both)
     for (int q = 0; q < 3; q++) {
@@ -883,6 +896,7 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (const char* e = getenv("GPI_TMA3_CTAS")) h->tma3_ctas = atoi(e);
     if (const char* e = getenv("GPI_SHELL")) h->shell_mode = atoi(e);
     if (const char* e = getenv("GPI_FUSE2A")) h->fuse2a = atoi(e) != 0;
+    if (const char* e = getenv("GPI_PZ_ALIGN")) h->pzalign = atoi(e);
     if (const char* e = getenv("GPI_O4VEC")) h->o4vec = atoi(e) != 0;
     if (const char* e = getenv("GPI_PINGPONG")) h->pingpong = atoi(e) != 0;
     if (h->nd == 3 && h->el) {

@@ -459,6 +459,26 @@ __global__ void __launch_bounds__(256) k_stress(const Geom g, const StepArgs a) 
 #include "kernels2v.cuh"
 #include "kernels2a.cuh"
 #if !defined(GPI_HOST_EMU) || defined(GPI_EMU_T3)   // tests/emu: the kernel-level harnesses leave the TMA kernels out; the emulated engine (cuda_rt_shim.h) takes their host forms
+// Tile geometry and warp layout of the TMA tile kernels (kernels3t.cuh): ZC z cells x R rows per tile, MINB resident CTAs per SM;
+// layouts as four decimal digits NCOMP consumer warps per row, NPROD producer warps, NSHELL shell warps, SHELLC.  Measured on B200
+// (profiles/r02/tuning.md): 4 + 2 + 2 warps at 128 registers hide the shell; more consumer or producer warps, 8-row tiles and
+// 96-cell tiles for narrow z-slab windows all run at the same ~0.95 us per tile and SM -- the rows the TMA unit moves bound the tile rate.
+#ifndef T3_V_LAYOUT
+#define T3_V_LAYOUT 1220
+#endif
+#ifndef T3_S_LAYOUT
+#define T3_S_LAYOUT 1220
+#endif
+#ifndef T3_R
+#define T3_R 4
+#endif
+#ifndef T3_MINB
+#define T3_MINB 2
+#endif
+#ifndef T3_ZC
+#define T3_ZC 128
+#endif
+#define T3_NS t3
 #include "kernels3t.cuh"
 #endif
 #include "kernels4.cuh"

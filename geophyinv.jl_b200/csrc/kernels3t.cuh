@@ -31,16 +31,15 @@
 // The z-slab window (Geom.koff / klo / khi) is honoured exactly as in kernels3d.cuh, so the slab decomposition
 // uses the same kernels.
 
-namespace t3 {
+// Tile geometry (T3_ZC, T3_R), resident CTAs per SM (T3_MINB) and warp layouts (T3_V_LAYOUT, T3_S_LAYOUT) come from the includer.
+namespace T3_NS {
 
 #ifndef T3_STAGES
 #define T3_STAGES 2
 #endif
-#ifndef T3_MINB
-#define T3_MINB 2                    // resident CTAs per SM the register budget is sized for
-#endif
-constexpr int R = 4;                 // rows per tile
-constexpr int ZC = 128;              // z cells per tile
+constexpr int R = T3_R;               // rows per tile
+constexpr int MINB = T3_MINB;        // resident CTAs per SM the register and shared-memory budgets are sized for
+constexpr int ZC = T3_ZC;            // z cells per tile (a multiple of 32)
 constexpr int PH = ZC + 8;           // floats per staged row of a box with a 16-byte z halo on both sides
 constexpr int STAGES = T3_STAGES;
 // Warp layout of a CTA, per kernel (measured on B200, profiles/r02/tuning.md):
@@ -49,36 +48,14 @@ constexpr int STAGES = T3_STAGES;
 //   NPROD  producer warps (one elected thread each); operand box b belongs to producer b % NPROD;
 //   NSHELL warps that walk the shell lines beside the tile pipeline; SHELLC = 1: the consumer warps take one 32-cell shell unit every
 //          16th tile instead (their slack between two tiles is longer than a shell cell's dependent-load chain).
-// velocity: 12 + 1 warps, shell units between tiles (72 registers); stress: 4 + 2 + 2 warps (128 registers).
-#ifndef T3_V_NCOMP
-#define T3_V_NCOMP 1
-#endif
-#ifndef T3_V_NPROD
-#define T3_V_NPROD 2
-#endif
-#ifndef T3_V_NSHELL
-#define T3_V_NSHELL 2
-#endif
-#ifndef T3_V_SHELLC
-#define T3_V_SHELLC 0
-#endif
-#ifndef T3_S_NCOMP
-#define T3_S_NCOMP 1
-#endif
-#ifndef T3_S_NPROD
-#define T3_S_NPROD 2
-#endif
-#ifndef T3_S_NSHELL
-#define T3_S_NSHELL 2
-#endif
-#ifndef T3_S_SHELLC
-#define T3_S_SHELLC 0
-#endif
+// The macros T3_V_* / T3_S_* come from the includer (kernels.cuh: one set per tile width).
+constexpr int LAYOUT_V[4] = {(T3_V_LAYOUT) / 1000, (T3_V_LAYOUT) / 100 % 10, (T3_V_LAYOUT) / 10 % 10, (T3_V_LAYOUT) % 10};      // NCOMP, NPROD, NSHELL, SHELLC
+constexpr int LAYOUT_S[4] = {(T3_S_LAYOUT) / 1000, (T3_S_LAYOUT) / 100 % 10, (T3_S_LAYOUT) / 10 % 10, (T3_S_LAYOUT) % 10};
 template <int KIND> struct L {
-    static constexpr int NCOMP = KIND == 0 ? T3_V_NCOMP : T3_S_NCOMP;
-    static constexpr int NPROD = KIND == 0 ? T3_V_NPROD : T3_S_NPROD;
-    static constexpr int NSHELL = KIND == 0 ? T3_V_NSHELL : T3_S_NSHELL;
-    static constexpr int SHELLC = KIND == 0 ? T3_V_SHELLC : T3_S_SHELLC;
+    static constexpr int NCOMP = KIND == 0 ? LAYOUT_V[0] : LAYOUT_S[0];
+    static constexpr int NPROD = KIND == 0 ? LAYOUT_V[1] : LAYOUT_S[1];
+    static constexpr int NSHELL = KIND == 0 ? LAYOUT_V[2] : LAYOUT_S[2];
+    static constexpr int SHELLC = KIND == 0 ? LAYOUT_V[3] : LAYOUT_S[3];
     static constexpr int NCW = R * NCOMP;                 // consumer warps
     static constexpr int NTHREADS = 32 * (NCW + NPROD + NSHELL);
     static constexpr bool INKERNEL_SHELL = NSHELL > 0 || SHELLC;       // false: the shell is the separate launch k_shell3
@@ -90,8 +67,9 @@ constexpr int SHELL_EVERY = 16;
 constexpr int PZM = 96;              // floats per z-CPML memory row (Geom.pzm must equal this)
 
 // Operand boxes of a stage.  Every box is rows x pitch floats, dense, and starts on a 128-byte boundary.
-// Sizes in floats: 4 x 128 = 512, 5 x 128 = 640, 4 x 136 = 544, 5 x 136 = 680 (padded to 704).
-constexpr int B4 = 512, B5 = 640, H4 = 544, H5 = 704;
+// Sizes in floats at ZC = 128: 4 x 128 = 512, 5 x 128 = 640, 4 x 136 = 544, 5 x 136 = 680 (padded to 704); every size is a multiple of 32.
+constexpr int B4 = R * ZC, B5 = (R + 1) * ZC, H4 = R * PH, H5 = ((R + 1) * PH + 31) / 32 * 32;       // B4 / H4: R rows, B5 / H5: R + 1 rows (y halo)
+static_assert(ZC % 32 == 0 && B4 % 32 == 0 && B5 % 32 == 0 && H4 % 32 == 0 && H5 % 32 == 0, "operand boxes start on 128-byte boundaries");
 // velocity kernel: box -> offset
 enum { V_XX0 = 0, V_XXM = V_XX0 + B4, V_YY = V_XXM + B4 /*5 rows j-1..j+3*/, V_ZZ = V_YY + B5 /*halo*/, V_XY0 = V_ZZ + H4 /*5 rows j..j+4*/,
        V_XYP = V_XY0 + B5, V_XZ0 = V_XYP + B4 /*halo*/, V_XZP = V_XZ0 + H4, V_YZ = V_XZP + B4 /*5 rows, halo*/, V_VX = V_YZ + H5,
@@ -102,7 +80,7 @@ enum { S_VX0 = 0 /*5 rows j-1..j+3, halo*/, S_VXP = S_VX0 + H5, S_VY0 = S_VXP + 
        S_XY = S_ZZ + B4, S_XZ = S_XY + B4, S_YZ = S_XZ + B4, S_K = S_YZ + B4, S_L = S_K + B4, S_MUXZ = S_L + B4,
        S_MUXY = S_MUXZ + B4, S_MUYZ = S_MUXY + B4, S_MAIN = S_MUYZ + B4, S_NBOX = 17 };
 // after the main boxes: CPML memory boxes (x terms, y terms: 4 x 128; z terms: 4 x 96), then the tile header
-constexpr int P_X = 0, P_Y = 3 * B4, P_Z = 6 * B4, P_HDR = 6 * B4 + 3 * 4 * PZM, P_FLOATS = P_HDR + 32;
+constexpr int P_X = 0, P_Y = 3 * B4, P_Z = 6 * B4, P_HDR = 6 * B4 + 3 * R * PZM, P_FLOATS = P_HDR + 32;
 constexpr int MAXBOX = S_NBOX + 9;
 // tile header (ints) = one record of the tile table
 enum { H_I = 0, H_J0, H_KC0, H_SX /*3*/, H_SY0 = H_SX + 3 /*3*/, H_YMASK = H_SY0 + 3 /*3*/, H_ZLOAD = H_YMASK + 3, H_N, H_REC = 16 };
@@ -117,18 +95,18 @@ struct BoxSpec { int arr; int di, dj, rows, halo, off; };      // arr: 0-5 tau, 
 __host__ __device__ inline BoxSpec box_spec(int kind, int b) {
     if (kind == 0) {
         const BoxSpec t[V_NBOX] = {
-            {T_XX, 0, 0, 4, 0, V_XX0}, {T_XX, -1, 0, 4, 0, V_XXM}, {T_YY, 0, -1, 5, 0, V_YY}, {T_ZZ, 0, 0, 4, 1, V_ZZ},
-            {T_XY, 0, 0, 5, 0, V_XY0}, {T_XY, 1, 0, 4, 0, V_XYP}, {T_XZ, 0, 0, 4, 1, V_XZ0}, {T_XZ, 1, 0, 4, 0, V_XZP},
-            {T_YZ, 0, 0, 5, 1, V_YZ}, {6 + V_X, 0, 0, 4, 0, V_VX}, {6 + V_Y, 0, 0, 4, 0, V_VY}, {6 + V_Z, 0, 0, 4, 0, V_VZ},
-            {9 + C_BX, 0, 0, 4, 0, V_BX}, {9 + C_BY, 0, 0, 4, 0, V_BY}, {9 + C_BZ, 0, 0, 4, 0, V_BZ}};
+            {T_XX, 0, 0, R, 0, V_XX0}, {T_XX, -1, 0, R, 0, V_XXM}, {T_YY, 0, -1, R + 1, 0, V_YY}, {T_ZZ, 0, 0, R, 1, V_ZZ},
+            {T_XY, 0, 0, R + 1, 0, V_XY0}, {T_XY, 1, 0, R, 0, V_XYP}, {T_XZ, 0, 0, R, 1, V_XZ0}, {T_XZ, 1, 0, R, 0, V_XZP},
+            {T_YZ, 0, 0, R + 1, 1, V_YZ}, {6 + V_X, 0, 0, R, 0, V_VX}, {6 + V_Y, 0, 0, R, 0, V_VY}, {6 + V_Z, 0, 0, R, 0, V_VZ},
+            {9 + C_BX, 0, 0, R, 0, V_BX}, {9 + C_BY, 0, 0, R, 0, V_BY}, {9 + C_BZ, 0, 0, R, 0, V_BZ}};
         return t[b];
     }
     const BoxSpec t[S_NBOX] = {
-        {6 + V_X, 0, -1, 5, 1, S_VX0}, {6 + V_X, 1, 0, 4, 0, S_VXP}, {6 + V_Y, 0, 0, 5, 1, S_VY0}, {6 + V_Y, -1, 0, 4, 0, S_VYM},
-        {6 + V_Z, 0, -1, 5, 1, S_VZ0}, {6 + V_Z, -1, 0, 4, 0, S_VZM}, {T_XX, 0, 0, 4, 0, S_XX}, {T_YY, 0, 0, 4, 0, S_YY},
-        {T_ZZ, 0, 0, 4, 0, S_ZZ}, {T_XY, 0, 0, 4, 0, S_XY}, {T_XZ, 0, 0, 4, 0, S_XZ}, {T_YZ, 0, 0, 4, 0, S_YZ},
-        {9 + C_K, 0, 0, 4, 0, S_K}, {9 + C_L, 0, 0, 4, 0, S_L}, {9 + C_MUXZ, 0, 0, 4, 0, S_MUXZ}, {9 + C_MUXY, 0, 0, 4, 0, S_MUXY},
-        {9 + C_MUYZ, 0, 0, 4, 0, S_MUYZ}};
+        {6 + V_X, 0, -1, R + 1, 1, S_VX0}, {6 + V_X, 1, 0, R, 0, S_VXP}, {6 + V_Y, 0, 0, R + 1, 1, S_VY0}, {6 + V_Y, -1, 0, R, 0, S_VYM},
+        {6 + V_Z, 0, -1, R + 1, 1, S_VZ0}, {6 + V_Z, -1, 0, R, 0, S_VZM}, {T_XX, 0, 0, R, 0, S_XX}, {T_YY, 0, 0, R, 0, S_YY},
+        {T_ZZ, 0, 0, R, 0, S_ZZ}, {T_XY, 0, 0, R, 0, S_XY}, {T_XZ, 0, 0, R, 0, S_XZ}, {T_YZ, 0, 0, R, 0, S_YZ},
+        {9 + C_K, 0, 0, R, 0, S_K}, {9 + C_L, 0, 0, R, 0, S_L}, {9 + C_MUXZ, 0, 0, R, 0, S_MUXZ}, {9 + C_MUXY, 0, 0, R, 0, S_MUXY},
+        {9 + C_MUYZ, 0, 0, R, 0, S_MUYZ}};
     return t[b];
 }
 // CPML terms of a kernel grouped by axis: index into StepArgs.pv / .ps, and (s0, len) of the derivative field
@@ -238,7 +216,7 @@ __device__ __forceinline__ float z_prev_s(unsigned mask, const F4& c, const floa
 }
 __device__ __forceinline__ float z_next_s(unsigned mask, const F4& c, const float* p, int lane, bool has) {
     float v = __shfl_down_sync(mask, c.v[0], 1);       // the lane above may be outside the mask (k0 >= pz): then has == false
-    if (lane == 31) v = p[VW];
+    if (lane == ZC / 4 - 1) v = p[VW];
     return has ? v : 0.f;
 }
 #endif   // GPI_HOST_EMU
@@ -354,7 +332,7 @@ __device__ __forceinline__ void producer(const Geom& g, const Sched& sc, const M
         for (int q = 0; q < 3; q++) {
             if ((NBOX + q) % NPROD == P && sx[q] >= 0)  tma_box(dstp + (P_X + q * B4) * 4, tm->m[NBOX + q], kc0, j0, sx[q], bar);          // [k, j, s]
             if ((NBOX + 3 + q) % NPROD == P && ymask[q]) tma_box(dstp + (P_Y + q * B4) * 4, tm->m[NBOX + 3 + q], kc0, sy0[q], i, bar);      // [k, s, i]
-            if ((NBOX + 6 + q) % NPROD == P && zload)    tma_box(dstp + (P_Z + q * 4 * PZM) * 4, tm->m[NBOX + 6 + q], 0, j0, i, bar);       // [zi, j, i]
+            if ((NBOX + 6 + q) % NPROD == P && zload)    tma_box(dstp + (P_Z + q * R * PZM) * 4, tm->m[NBOX + 6 + q], 0, j0, i, bar);       // [zi, j, i]
         }
     }
 }
@@ -477,7 +455,7 @@ __device__ __forceinline__ void pml_t(const TileCtx& q, const Geom& g, const Ste
         if (!q.zload) return;
         int s0, len;
         term_extent(g, KIND, 0, Q, s0, len);
-        pml_z(q.P + P_Z + (Q * 4 + q.r) * PZM, t.mem + (long long)g.pzm * ((long long)q.j + (long long)g.ny1 * q.i),
+        pml_z(q.P + P_Z + (Q * R + q.r) * PZM, t.mem + (long long)g.pzm * ((long long)q.j + (long long)g.ny1 * q.i),
               q.ZT + Q * 3 * PZM, z_slot(g, s0, len, q.kg0), d);
     }
 }
@@ -657,14 +635,14 @@ __device__ __forceinline__ void shell_lines(const Geom& g, const StepArgs& a, co
     }
 }
 // shell unit u = 32 consecutive z cells of a shell line (SHELLC: one unit per consumer warp every SHELL_EVERY tiles, the rest after the last tile)
-__device__ __forceinline__ int shell_units(const Geom& g, const Sched& sc) { return (sc.nsp * g.ny1 + (sc.ihi - sc.ilo + 1) * sc.nsr) * (g.pz >> 5); }
+__device__ __forceinline__ int shell_units(const Geom& g, const Sched& sc) { return (sc.nsp * g.ny1 + (sc.ihi - sc.ilo + 1) * sc.nsr) * ((g.pz + 31) >> 5); }
 template <int KIND>
 __device__ __forceinline__ void shell_unit(const Geom& g, const StepArgs& a, const Sched& sc, int u, int lane) {
-    const int nzq = g.pz >> 5;                            // pz is a multiple of 32
+    const int nzq = (g.pz + 31) >> 5;
     const int L = u / nzq, k = (u - L * nzq) * 32 + lane;
     int i, j;
     shell_line_ji(g, sc, L, i, j);
-    if (k >= g.klo && k <= g.khi) {
+    if (k < g.pz && k >= g.klo && k <= g.khi) {
         if (KIND == 0) vel_cell<3, 1>(g, a, k, j, i, 0);
         else           stress_cell<3, 1>(g, a, k, j, i, 0);
     }
@@ -698,7 +676,7 @@ __device__ __forceinline__ void consumer_group(const Geom& g, const StepArgs& a,
         TileCtx q;
         q.ZT = ZT;
         open_tile<KIND, COMP>(q, g, a, S, r, lane);
-        const bool active = q.j <= sc.jhi && q.k0 < g.pz;
+        const bool active = q.j <= sc.jhi && q.k0 < g.pz && 4 * lane < ZC;
         q.mask = __ballot_sync(0xffffffffu, active);
         if (active) {
             if (COMP == 3) {         // one warp, the three output groups in turn
@@ -759,7 +737,7 @@ void k_step3t(const Geom g, const StepArgs a, const Sched sc, const Maps* tm) {
 }
 #else
 template <int KIND>
-__global__ void __launch_bounds__(L<KIND>::NTHREADS, T3_MINB) k_step3t(const Geom g, const StepArgs a, const Sched sc, const Maps* __restrict__ tm) {
+__global__ void __launch_bounds__(L<KIND>::NTHREADS, MINB) k_step3t(const Geom g, const StepArgs a, const Sched sc, const Maps* __restrict__ tm) {
     constexpr int SFLOATS = K<KIND>::SFLOATS, NPROD = L<KIND>::NPROD, NCW = L<KIND>::NCW, NSHELL = L<KIND>::NSHELL, NTHREADS = L<KIND>::NTHREADS;
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     unsigned char* smem_raw = smem_dyn + ((128 - (s32(smem_dyn) & 127)) & 127);      // boxes need 128-byte alignment
@@ -800,4 +778,19 @@ __global__ void __launch_bounds__(128, 8) k_shell3(const Geom g, const StepArgs 
     }
 }
 
-}  // namespace t3
+// what engine.cu needs of one variant
+struct Tr {
+    typedef Maps MapsT; typedef Sched SchedT; typedef TileRec TileRecT;
+    static constexpr int ZC_ = ZC, PH_ = PH, R_ = R, MINB_ = MINB, PZM_ = PZM, V_NBOX_ = V_NBOX, S_NBOX_ = S_NBOX;
+    static BoxSpec box(int kind, int b) { return box_spec(kind, b); }
+    static int term(int kind, int axis, int q) { return term_index(kind, axis, q); }
+    static size_t smem(int kind) { return smem_bytes(kind); }
+    static void tiles(const Geom& g, const Sched& sc, int kind, TileRec* out) { fill_tile_table(g, sc, kind, out); }
+    template <int KIND> struct Lay : L<KIND> {};
+    typedef void (*TileFn)(const Geom, const StepArgs, const Sched, const Maps*);
+    typedef void (*ShellFn)(const Geom, const StepArgs, const Sched);
+    template <int KIND> static TileFn tile_kernel() { return k_step3t<KIND>; }
+    template <int KIND> static ShellFn shell_kernel() { return k_shell3<KIND>; }
+};
+
+}  // namespace T3_NS

@@ -202,6 +202,25 @@ def test_tma_and_register_staged_kernels_agree_at_full_c3_size(G, monkeypatch):
     assert (np.abs(out["1"][4]) > 1e-20).sum() > 50000       # 79155 on B200: the sphere the wave has reached after 60 steps
 
 
+def test_tiles_on_a_ragged_z_pitch_match_the_oracle(G, O, monkeypatch):
+    """The z pitch of the unified box is a multiple of 8 floats (32-byte sectors), not of whole 128-byte lines: rows of a 12 + 2 x 41 =
+    94-node grid are 96 floats apart, those of the 10 + 82 = 92-node one 96 too, 13 + 82 -> 104.  The TMA tiles (forced: GPI_TMA3=2)
+    take one ragged 128-cell chunk per row; the last active lane takes its z + 1 neighbour from the staged halo, out-of-range box
+    columns read zeros.  Records and final fields bit-identical to the oracle."""
+    from geophyinv_jl_b200.host import gallery
+    monkeypatch.setenv("GPI_TMA3", "2")
+    for n in (12, 13):
+        kw = gallery.c3_elastic3d(n=n, nt=90, nr=8, fq=60.0, rfields=("vz", "vx"))
+        pg, po = both(G, O, G.FdtdElastic, kw)
+        pg.update(); po.update()
+        assert pg.engine.kernel_family() == "tma"
+        for f in pg.c.rfields:
+            a, b = pg.c.data[0][0].d[f], po.c.data[0][0].d[f]
+            assert np.abs(b).max() > 0 and np.array_equal(a, b), f
+        for f in ("vx", "vy", "vz", "tauxx", "tauzz", "tauxy", "tauxz", "tauyz"):
+            assert np.array_equal(pg.engine.get_field(0, f), po.engine.get_field(0, f)), f
+
+
 def test_dmod_matches_oracle(G, O):
     """update_dmod! (medium.jl:143-221): coefficient arrays agree bit for bit (checked through the
     wavefield after one step with unit fields is overkill; compare the medium round trip instead)."""
