@@ -174,6 +174,7 @@ struct gpi_handle {
     bool tma3 = true;  int num_sms = 148;  int tma3_ctas = 0;  bool tma3_force = false;   // GPI_TMA3=2: TMA kernels whatever the tile utilisation
     int shell_mode = 1;                                 // GPI_SHELL=0: shell kernel serialised behind the tile kernel (diagnostic)
     bool o4vec = true;                                  // order-4 kernels with four z cells per thread (kernels4v.cuh); GPI_O4VEC=0 selects the scalar ones
+    int o4by = 4;                                       // GPI_O4_BY: rows per block of the order-4 3-D kernels (1, 2, 4; planes = 4 / rows)
     int pzalign = 8;                                    // GPI_PZ_ALIGN (4, 8, 16, 32 floats)
     bool fuse2a = true;      // fused 2-D acoustic adjoint (kernels2a.cuh); GPI_FUSE2A=0 opts out
     void* t3_tiles[2] = {nullptr, nullptr};      // tile tables of the two tile kernels (geometry only: built once per handle)
@@ -485,7 +486,7 @@ void launch_step_kernels4(gpi_handle* h, const StepArgs& a, bool vel, int nbatch
     dim3 grd = grid_for(h, blk, nbatch);
     if (h->o4vec) {        // four z cells per thread (kernels4v.cuh)
         const int ngx = ((g.pz / 4) + 31) / 32;
-        if (ND == 3) { blk = dim3(32, 2, 2); grd = dim3(ngx, (g.ny1 + 1) / 2, ((g.nx1 + 1) / 2) * nbatch); }
+        if (ND == 3) { const int by = h->o4by, bx = 4 / by; blk = dim3(32, by, bx); grd = dim3(ngx, (g.ny1 + by - 1) / by, ((g.nx1 + bx - 1) / bx) * nbatch); }
         else         { blk = dim3(32, 4, 1); grd = dim3(ngx, (g.nx1 + 3) / 4, nbatch); }
         if (!vel) { k_stress4v<ND, EL><<<grd, blk, 0, h->stream>>>(g, a); return; }
         k_vel4v<ND, EL><<<grd, blk, 0, h->stream>>>(g, a);
@@ -897,6 +898,7 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (const char* e = getenv("GPI_SHELL")) h->shell_mode = atoi(e);
     if (const char* e = getenv("GPI_FUSE2A")) h->fuse2a = atoi(e) != 0;
     if (const char* e = getenv("GPI_PZ_ALIGN")) h->pzalign = atoi(e);
+    if (const char* e = getenv("GPI_O4_BY")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) h->o4by = v; }
     if (const char* e = getenv("GPI_O4VEC")) h->o4vec = atoi(e) != 0;
     if (const char* e = getenv("GPI_PINGPONG")) h->pingpong = atoi(e) != 0;
     if (h->nd == 3 && h->el) {

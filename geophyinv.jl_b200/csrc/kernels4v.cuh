@@ -82,6 +82,34 @@ __device__ __forceinline__ bool cell4v(const Geom& g, int& ks0, int& js, int& is
     return ks0 < g.pz && js < g.ny1 && is < g.nx1;
 }
 
+// The arithmetic below takes its operands derivative by derivative, and every CPML term stores its memory variables before the next
+// derivative's loads can issue (possible aliasing): a thread pays one DRAM round trip (2 - 3 us under load) per derivative, nine times in
+// the 3-D elastic kernels.  Requesting the thread's own lines of every array it will touch into L2 first -- and, for the differentiated
+// fields, the lines one and two planes ahead, which no earlier block has touched yet -- turns those round trips into L2 hits.
+// (Requesting the CPML memory variables as well made it slower again: 22.9 -> 21.6 Gcell-updates/s on the C3 grid.)
+// GPI_O4_PREFETCH=0 (compile time) leaves it out.
+#ifndef GPI_O4_PREFETCH
+#define GPI_O4_PREFETCH 1
+#endif
+template <int ND, int EL>
+__device__ __forceinline__ void prefetch4v(const Geom& g, const StepArgs& a, long long w, long long c, bool vel) {
+#if GPI_O4_PREFETCH
+    const long long sx = (long long)g.pz * g.ny1;
+    float* const* diff = vel ? a.tau : a.v;        // differentiated fields: 6 stresses | 3 velocities
+    float* const* upd = vel ? a.v : a.tau;         // updated fields
+    const int nd = vel ? 6 : 3, nu = vel ? 3 : 6;
+#pragma unroll
+    for (int q = 0; q < nd; q++) if (diff[q]) { pf2(diff[q] + w + c); pf2(diff[q] + w + c + sx); pf2(diff[q] + w + c + 2 * sx); }
+#pragma unroll
+    for (int q = 0; q < nu; q++) if (upd[q]) pf2(upd[q] + w + c);
+    if (vel) { pf2(a.c[C_BX] + c); pf2(a.c[C_BZ] + c); if (ND == 3) pf2(a.c[C_BY] + c); }
+    else {
+        pf2(a.c[C_K] + c);
+        if (EL) { pf2(a.c[C_L] + c); pf2(a.c[C_MUXZ] + c); if (ND == 3) { pf2(a.c[C_MUXY] + c); pf2(a.c[C_MUYZ] + c); } }
+    }
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_vel4v
 // ------------------------------------------------------------------------------------------------
@@ -103,6 +131,7 @@ __global__ void __launch_bounds__(128) k_vel4v(const Geom g, const StepArgs a) {
     const bool doy = ND == 3 && anyJ && jH && inJ(i, nx);  // vy: (J, H, J)
     const bool doz = anyH && jJ && inJ(i, nx);             // vz: (H, J, J)
     if (!(dox || doy || doz)) return;
+    prefetch4v<ND, EL>(g, a, w, c, true);
 
     if (!EL) {
         const float* p = a.tau[T_XX] + w;
@@ -245,6 +274,7 @@ __global__ void __launch_bounds__(128) k_stress4v(const Geom g, const StepArgs a
     const float* vx = a.v[V_X] + w; const float* vz = a.v[V_Z] + w; const float* vy = (ND == 3) ? a.v[V_Y] + w : nullptr;
     const bool don = anyI && jI && inI(i, nx);
     const bool fs = EL && (g.freesurf & ZMIN) != 0;
+    prefetch4v<ND, EL>(g, a, w, c, false);
 
     if (don) {
         F4 dxx = dI4(vx, c, sx, g.dxI);                                          // @d_xa(vx)
