@@ -73,6 +73,7 @@ struct Geom {
     // updates the nodes kl in [klo, khi]; kl = klo-1 and khi+1 are halo planes filled by the exchange.
     int koff, klo, khi;
     int h;                   // order 4: storage index = unified coordinate + h on every axis (kernels4.cuh); 0 at order 2
+    int ioff;                // first x plane of this launch (k_*3v: plane = blockIdx.y + ioff; pipelined z-slab runs launch the grid in two x halves)
     int pz;                  // z pitch in floats (multiple of 32)
     int ny1;                 // rows per x-plane: ny+1 (3-D) or 1 (2-D)
     int nx1;                 // nx+1
@@ -571,7 +572,7 @@ struct PostDesc { int ninj, nrec; InjOp inj[MAX_OPS]; RecOp rec[MAX_OPS]; };
 
 // woff: floats added to every wavefield pointer of the descriptors (0, or the distance to the other time-level set in ping-pong runs)
 __global__ void k_post(const Geom g, const PostDesc* __restrict__ descs, int it /*1-based*/, int rec_it /*1-based row to write*/,
-                       int nt, float dt, int flags /* bit0 inject, bit1 record */, long long woff) {
+                       int nt, float dt, int flags /* bit0 inject, bit1 record */, long long woff, int i_lo = 0, int i_hi = 0x7fffffff /* inject into x planes [i_lo, i_hi) only */) {
     const PostDesc& d = descs[blockIdx.x];
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
     const int ninj = (flags & 1) ? d.ninj : 0;
@@ -583,6 +584,7 @@ __global__ void k_post(const Geom g, const PostDesc* __restrict__ descs, int it 
             for (int e = op.row_ptr[r]; e < op.row_ptr[r + 1]; e++)
                 buf = __fadd_rn(buf, __fmul_rn(op.ent_val[e], op.wav[(size_t)(it - 1) + (size_t)nt * op.ent_col[e]]));
             const long long c = op.row_cell[r];
+            { const int ip = (int)(c / sx); if (ip < i_lo || ip >= i_hi) continue; }
             if (op.kind == 1) {
                 const float add = __fmul_rn(buf, op.coef[c]);        // pw = pw + (pv * dtK)
                 for (int t = 0; t < op.ntarget; t++) op.target[t][c + woff] = __fadd_rn(op.target[t][c + woff], add);
@@ -906,14 +908,14 @@ __global__ void k_born_add(const Geom g, float* __restrict__ f0, float* __restri
 // fast axis, so a z = const plane is strided in memory: pack gathers up to three planes into one
 // contiguous buffer [field][i][j] that travels over NVLink; unpack scatters it into the halo plane.
 // ------------------------------------------------------------------------------------------------
-struct HaloArgs { int n; float* field[3]; int k[3]; };
+struct HaloArgs { int n; float* field[3]; int k[3]; int i0, ni; };      // x planes [i0, i0 + ni) of the z plane; buffer [field][i - i0][j]
 template <int PACK>
 __global__ void k_halo(const Geom g, const HaloArgs a, float* __restrict__ buf) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
+    const int i = blockIdx.y + a.i0;
     if (j >= g.ny1) return;
-    const long long plane = (long long)g.ny1 * g.nx1;
-    const long long q = (long long)j + (long long)g.ny1 * i;
+    const long long plane = (long long)g.ny1 * a.ni;
+    const long long q = (long long)j + (long long)g.ny1 * blockIdx.y;
     for (int f = 0; f < a.n; f++) {
         float* p = a.field[f] + uidx(g, a.k[f], j, i);
         if (PACK) buf[f * plane + q] = *p;

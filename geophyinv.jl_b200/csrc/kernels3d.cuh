@@ -264,7 +264,7 @@ __device__ __forceinline__ Vec3Idx vec3_index(const Geom& g) {
         q.k0 = (zc * LPR + (l % LPR)) * VW;
         q.valid = q.j < g.ny1;
     }
-    q.i = blockIdx.y; q.b = blockIdx.z;
+    q.i = blockIdx.y + g.ioff; q.b = blockIdx.z;
     return q;
 }
 
