@@ -571,40 +571,82 @@ enum { MAX_OPS = 8 };
 struct PostDesc { int ninj, nrec; InjOp inj[MAX_OPS]; RecOp rec[MAX_OPS]; };
 
 // woff: floats added to every wavefield pointer of the descriptors (0, or the distance to the other time-level set in ping-pong runs)
+//
+// The kernel is a chain of dependent loads (descriptor -> row / column pointers -> entries -> wavelet / field -> store), 10 - 13 us per
+// launch when written naively and 17 % of a 16-shot 2-D time step.  Everything but the wavefields and the wavelet sample is the same at
+// every step, so each thread first requests the static tables of BOTH phases (its injection row: pointers, cell, averaging operands; its
+// receiver: column pointers, tap cells and weights, up to PRE_TAPS of them for the first PRE_OPS record operators) and only then walks
+// the injection chain; after the barrier a receiver costs one round trip (the field values).  Summation orders are unchanged.
+enum { PRE_OPS = 3, PRE_TAPS = 8 };
 __global__ void k_post(const Geom g, const PostDesc* __restrict__ descs, int it /*1-based*/, int rec_it /*1-based row to write*/,
                        int nt, float dt, int flags /* bit0 inject, bit1 record */, long long woff, int i_lo = 0, int i_hi = 0x7fffffff /* inject into x planes [i_lo, i_hi) only */) {
     const PostDesc& d = descs[blockIdx.x];
     const long long sy = g.pz, sx = (long long)g.pz * g.ny1;
     const int ninj = (flags & 1) ? d.ninj : 0;
     const int nrec = ((flags & 2) && rec_it >= 1 && rec_it <= nt) ? d.nrec : 0;
+    // ---- static tables of this thread's first receiver of the first record operators
+    int pe0[PRE_OPS], pn[PRE_OPS], pcell[PRE_OPS][PRE_TAPS];
+    float pval[PRE_OPS][PRE_TAPS];
+#pragma unroll
+    for (int o = 0; o < PRE_OPS; o++) {
+        pn[o] = -1; pe0[o] = 0;
+        if (o < nrec && (int)threadIdx.x < d.rec[o].nr) {
+            const RecOp& op = d.rec[o];
+            const int e0 = op.colptr[threadIdx.x], n = op.colptr[threadIdx.x + 1] - e0;
+            pe0[o] = e0;
+            if (n <= PRE_TAPS) {
+                pn[o] = n;
+#pragma unroll
+                for (int q = 0; q < PRE_TAPS; q++) if (q < n) { pcell[o][q] = op.tap_cell[e0 + q]; pval[o][q] = op.tap_val[e0 + q]; }
+            }
+        }
+    }
+    // ---- sources
     for (int o = 0; o < ninj; o++) {
         const InjOp& op = d.inj[o];
         for (int r = threadIdx.x; r < op.nrows; r += blockDim.x) {
-            float buf = 0.f;                                         // mul!(buf, S, w): buf[row] += nzval * w[col]
-            for (int e = op.row_ptr[r]; e < op.row_ptr[r + 1]; e++)
-                buf = __fadd_rn(buf, __fmul_rn(op.ent_val[e], op.wav[(size_t)(it - 1) + (size_t)nt * op.ent_col[e]]));
+            const int e0 = op.row_ptr[r], e1 = op.row_ptr[r + 1];
             const long long c = op.row_cell[r];
             { const int ip = (int)(c / sx); if (ip < i_lo || ip >= i_hi) continue; }
+            const long long off = op.axis == 0 ? 1 : (op.axis == 1 ? sy : sx);
+            // operands that do not depend on the wavelet travel while the row is summed
+            const float c0 = op.kind == 1 ? op.coef[c] : op.coef[c - (g.h + 1) * off];
+            const float c1 = op.kind == 1 ? 0.f : op.coef[c - g.h * off];
+            float old[3];
+            for (int t = 0; t < op.ntarget; t++) old[t] = op.target[t][c + woff];
+            float buf = 0.f;                                         // mul!(buf, S, w): buf[row] += nzval * w[col]
+            for (int e = e0; e < e1; e++)
+                buf = __fadd_rn(buf, __fmul_rn(op.ent_val[e], op.wav[(size_t)(it - 1) + (size_t)nt * op.ent_col[e]]));
             if (op.kind == 1) {
-                const float add = __fmul_rn(buf, op.coef[c]);        // pw = pw + (pv * dtK)
-                for (int t = 0; t < op.ntarget; t++) op.target[t][c + woff] = __fadd_rn(op.target[t][c + woff], add);
+                const float add = __fmul_rn(buf, c0);                // pw = pw + (pv * dtK)
+                for (int t = 0; t < op.ntarget; t++) op.target[t][c + woff] = __fadd_rn(old[t], add);
             } else {                                                 // pw = pw + (pv / av(rho) * dt), literal typing as in the reference (wide_t)
-                const long long off = op.axis == 0 ? 1 : (op.axis == 1 ? sy : sx);
-                const float s = __fadd_rn(op.coef[c - (g.h + 1) * off], op.coef[c - g.h * off]);     // @av_?i: integer nodes u-1-h, u-h
-                float* t = op.target[0] + woff;
+                const float s = __fadd_rn(c0, c1);                   // @av_?i: integer nodes u-1-h, u-h
                 // every operation rounded on its own (nvcc would otherwise be free to contract the product and the sum into one fma,
                 // which the CPU path does not do)
-                t[c] = (float)wadd((wide_t)t[c], wmul(wdiv((wide_t)buf, wmul((wide_t)s, (wide_t)0.5f)), (wide_t)dt));
+                op.target[0][c + woff] = (float)wadd((wide_t)old[0], wmul(wdiv((wide_t)buf, wmul((wide_t)s, (wide_t)0.5f)), (wide_t)dt));
             }
         }
     }
     __syncthreads();
+    // ---- receivers
     for (int o = 0; o < nrec; o++) {
         const RecOp& op = d.rec[o];
         for (int ir = threadIdx.x; ir < op.nr; ir += blockDim.x) {
             float tmp = 0.f;                                         // mul!(rec, transpose(R), field)
-            for (int e = op.colptr[ir]; e < op.colptr[ir + 1]; e++)
-                tmp = __fadd_rn(tmp, __fmul_rn(op.tap_val[e], op.field[op.tap_cell[e] + woff]));
+            bool done = false;
+#pragma unroll
+            for (int po = 0; po < PRE_OPS; po++) if (po == o && ir == (int)threadIdx.x && pn[po] >= 0) {
+                float fv[PRE_TAPS];
+#pragma unroll
+                for (int q = 0; q < PRE_TAPS; q++) if (q < pn[po]) fv[q] = op.field[pcell[po][q] + woff];
+#pragma unroll
+                for (int q = 0; q < PRE_TAPS; q++) if (q < pn[po]) tmp = __fadd_rn(tmp, __fmul_rn(pval[po][q], fv[q]));
+                done = true;
+            }
+            if (!done)
+                for (int e = op.colptr[ir]; e < op.colptr[ir + 1]; e++)
+                    tmp = __fadd_rn(tmp, __fmul_rn(op.tap_val[e], op.field[op.tap_cell[e] + woff]));
             op.rec[(size_t)(rec_it - 1) + (size_t)nt * ir] = tmp;
         }
     }
