@@ -5,10 +5,10 @@
  * product: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load it.  It is a restatement, not the Julia code: Julia is not installed in this image, so
  * the reference cannot be run here, and the reference ships no golden vectors for this path
- *  => PARITY UNPINNED against upstream artefacts; it is pinned instead by the
- * reference's own test invariants (analytic homogeneous solution, time reversal, gradient vs
- * finite differences, dot test) and by closed-form solutions with no free parameter (3-D acoustic
- * Green's function, 3-D elastic Stokes solution, reciprocity), see tests/test_oracle_invariants.py.
+ * (SURVEY.md section 8c).  What pins it: (1) fixtures evaluated from the reference's own kernel text
+ * (see "Parity status" below), (2) the reference's test invariants (analytic homogeneous solution, time
+ * reversal, gradient vs finite differences, dot test) and closed-form solutions with no free parameter
+ * (3-D acoustic Green's function, 3-D elastic Stokes solution, reciprocity), tests/test_oracle_invariants.py.
  *
  * Structure follows the reference literally (all citations relative to /root/reference):
  *   - same arrays with the same shapes as src/fields.jl:92-671 (column-major, [z,(y),x]);
