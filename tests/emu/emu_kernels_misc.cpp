@@ -156,7 +156,7 @@ static int small_kernels_case(int nd, int h, unsigned seed) {
     }
     if (nd == 3 && h == 0) {                         // z-plane halo pack / unpack of three fields
         std::vector<float> W = rnd(3 * vol), buf(3 * (size_t)g.ny1 * g.nx1, 0.f);
-        HaloArgs ha; ha.n = 3; for (int q = 0; q < 3; q++) { ha.field[q] = W.data() + (size_t)q * vol; ha.k[q] = g.khi; }
+        HaloArgs ha; ha.n = 3; ha.i0 = 0; ha.ni = g.nx1; for (int q = 0; q < 3; q++) { ha.field[q] = W.data() + (size_t)q * vol; ha.k[q] = g.khi; }
         launch(k_halo<1>, d3((g.ny1 + 127) / 128, g.nx1, 1), d3(128, 1, 1), g, ha, buf.data());
         for (int q = 0; q < 3; q++) ha.k[q] = 0;
         launch(k_halo<0>, d3((g.ny1 + 127) / 128, g.nx1, 1), d3(128, 1, 1), g, ha, buf.data());
