@@ -1747,7 +1747,7 @@ extern "C" int gpi_get_timers(gpi_handle* h, gpi_timers* out) { if (!h || !out) 
 extern "C" int gpi_kernel_family(gpi_handle* h) {
     if (!h) return -1;
     if (h->c.order == 4) return GPI_KERNELS_ORDER4;
-    if (h->nd == 3) return !h->vec3 ? GPI_KERNELS_SCALAR : (h->B == 1 && tma3_eligible(h)) ? GPI_KERNELS_TMA : GPI_KERNELS_VEC4;
+    if (h->nd == 3) return !h->vec3 ? GPI_KERNELS_SCALAR : (h->B == 1 && tma3_eligible(h)) ? GPI_KERNELS_TMA : slab_pipelined(h) ? GPI_KERNELS_VEC4_PIPELINED : GPI_KERNELS_VEC4;
     return h->vec2 ? GPI_KERNELS_VEC4 : GPI_KERNELS_SCALAR;
 }
 

@@ -299,8 +299,9 @@ class Engine:
         self._ck(self.lib.gpi_reset(self.h, what))
 
     def kernel_family(self) -> str:
-        """Which stencil kernels `run` launches: 'scalar', 'vec4' (k_*2v / k_*3v), 'tma' (t3::k_step3t) or 'order4'."""
-        return {0: "scalar", 1: "vec4", 2: "tma", 4: "order4"}[self.lib.gpi_kernel_family(self.h)]
+        """Which stencil kernels `run` launches: 'scalar', 'vec4' (k_*2v / k_*3v), 'tma' (t3::k_step3t), 'order4', or 'vec4-pipelined'
+        (z-slab handle: x-split launches of k_*3v with the halo exchange on a side stream)."""
+        return {0: "scalar", 1: "vec4", 2: "tma", 3: "vec4-pipelined", 4: "order4"}[self.lib.gpi_kernel_family(self.h)]
 
     def timers(self) -> dict:
         t = GpiTimers()

@@ -207,8 +207,9 @@ int  gpi_synchronize(gpi_handle* h);
 /* ---- instrumentation ------------------------------------------------------------------------- */
 int  gpi_get_timers(gpi_handle* h, gpi_timers* out);
 /* which stencil kernels gpi_run launches for this handle (for the bench's labels and the tests' coverage checks):
- * scalar one-thread-per-cell, float4-per-thread (k_*2v / k_*3v), TMA-pipelined 3-D elastic tiles (t3::k_step3t), order 4 */
-enum { GPI_KERNELS_SCALAR = 0, GPI_KERNELS_VEC4 = 1, GPI_KERNELS_TMA = 2, GPI_KERNELS_ORDER4 = 4 };
+ * scalar one-thread-per-cell, float4-per-thread (k_*2v / k_*3v), TMA-pipelined 3-D elastic tiles (t3::k_step3t), order 4;
+ * VEC4_PIPELINED: a z-slab handle whose launches are split into two x halves with the halo exchange on a side stream */
+enum { GPI_KERNELS_SCALAR = 0, GPI_KERNELS_VEC4 = 1, GPI_KERNELS_TMA = 2, GPI_KERNELS_VEC4_PIPELINED = 3, GPI_KERNELS_ORDER4 = 4 };
 int  gpi_kernel_family(gpi_handle* h);
 int  gpi_field_shape(int ndims, int physics, int field_id, const int32_t n[3], int32_t out[3]);      /* order 2 */
 /* shape of a field's own staggered array (fields.jl:92-671) for _fd_order = 2 | 4: velocity axes n + (order-1),
