@@ -585,15 +585,14 @@ __global__ void k_post(const Geom g, const PostDesc* __restrict__ descs, int it 
     const int ninj = (flags & 1) ? d.ninj : 0;
     const int nrec = ((flags & 2) && rec_it >= 1 && rec_it <= nt) ? d.nrec : 0;
     // ---- static tables of this thread's first receiver of the first record operators
-    int pe0[PRE_OPS], pn[PRE_OPS], pcell[PRE_OPS][PRE_TAPS];
+    int pn[PRE_OPS], pcell[PRE_OPS][PRE_TAPS];
     float pval[PRE_OPS][PRE_TAPS];
 #pragma unroll
     for (int o = 0; o < PRE_OPS; o++) {
-        pn[o] = -1; pe0[o] = 0;
+        pn[o] = -1;
         if (o < nrec && (int)threadIdx.x < d.rec[o].nr) {
             const RecOp& op = d.rec[o];
             const int e0 = op.colptr[threadIdx.x], n = op.colptr[threadIdx.x + 1] - e0;
-            pe0[o] = e0;
             if (n <= PRE_TAPS) {
                 pn[o] = n;
 #pragma unroll

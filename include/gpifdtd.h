@@ -119,7 +119,8 @@ typedef struct gpi_timers {
     double stencil_ms;        /* device time inside the two stencil kernels */
     double launches;          /* kernels launched by the last gpi_run       */
     /* per-kernel CUDA-event samples taken inside the last gpi_run (every GPI_SAMPLE_EVERY-th step,
-     * default 16; pw 1 launches only): summed duration and number of sampled launches */
+     * default 16; pw 1 launches only): summed duration and number of sampled launches.  Runs replayed from a CUDA graph
+     * (2-D forward, INTEGRATION.md: GPI_GRAPH) take no samples and report those of the last launch-by-launch run */
     double vel_ms, vel_n;     /* fused velocity kernel  (update_dstress! + update_v!)  */
     double stress_ms, stress_n; /* fused stress kernel  (update_dv! + update_stress!)  */
     /* ABI 2: multi-GPU phases.  exch_*: z-slab halo exchanges sampled like the kernels (time the compute stream waits
