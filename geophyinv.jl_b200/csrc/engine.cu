@@ -174,12 +174,12 @@ struct gpi_handle {
     bool tma3 = true;  int num_sms = 148;  int tma3_ctas = 0;  bool tma3_force = false;   // GPI_TMA3=2: TMA kernels whatever the tile utilisation
     int shell_mode = 1;                                 // GPI_SHELL=0: shell kernel serialised behind the tile kernel (diagnostic)
     bool o4vec = true;                                  // order-4 kernels with four z cells per thread (kernels4v.cuh); GPI_O4VEC=0 selects the scalar ones
-    // CUDA graphs for 2-D forward runs (no slabs): the launches of a batch's time loop are captured once per run configuration and
+    // CUDA graphs for 2-D runs (forward, forward_save, adjoint; no slabs): the launches of a batch's time loop are captured once per run configuration and
     // replayed by later runs -- one graph launch instead of 3 - 4 host launches per time step, which is what bounds small 2-D grids
     // (C2, one resident shot: 30.5 -> 43.3 Gcell-updates/s; 8 shots: 91.6 -> 99.8).  GPI_GRAPH = 1 (default): the first run of a
     // configuration goes launch by launch (nothing to amortise yet; its kernel samples stay the timers' kernel figures), the second is
     // captured, later ones replay; 2: capture at the first run; 0: off.
-    struct GraphEntry { unsigned long long key; void* exec; double launches; };
+    struct GraphEntry { unsigned long long key; void* exec; double launches; bool swapped; };      // swapped: the run ends on the other time-level set (ping-pong adjoint, odd nt)
     std::vector<GraphEntry> graphs;  int graph_mode = 1;  bool capturing = false;
     double kept_samples[4] = {0, 0, 0, 0};      // vel_ms, vel_n, stress_ms, stress_n of the last launch-by-launch run
     int o4by = 4;                                       // GPI_O4_BY: rows per block of the order-4 3-D kernels (1, 2, 4; planes = 4 / rows)
@@ -1505,18 +1505,18 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
         bool graphing = false;
         gpi_handle::GraphEntry* ge = nullptr;
 #ifndef GPI_HOST_EMU
-        if (h->graph_mode > 0 && mode == GPI_MODE_FORWARD && !h->slab && h->nd == 2 && !h->TP) {
+        if (h->graph_mode > 0 && !h->slab && h->nd == 2) {
             // what decides the sequence besides the handle's own fixed state
             unsigned long long key = 1469598103934665603ULL;
             auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ULL; };
             mix(mode); mix(activepw); mix(src_flags); mix(shot0); mix(nb); mix(do_post_v); mix(inj_s); mix(rec_s); mix(born); mix(nt);
-            mix((unsigned long long)(uintptr_t)h->stream); mix(h->itsnaps.size());
+            mix((unsigned long long)(uintptr_t)h->stream); mix((unsigned long long)(uintptr_t)h->W); mix(pp); mix(unshifted); mix(h->itsnaps.size());
             for (int v : h->itsnaps) mix(v);
             for (int b = 0; b < nb; b++) for (int ipw = 0; ipw < h->npw; ipw++) for (auto p : h->shots[ipw][shot0 + b].usnaps) mix((unsigned long long)(uintptr_t)p);
             for (auto& e : h->graphs) if (e.key == key) ge = &e;
             if (ge) graphing = true;                       // seen before: capture now (if not done yet) and replay
             else {
-                h->graphs.push_back({key, nullptr, 0.0});
+                h->graphs.push_back({key, nullptr, 0.0, false});
                 if (h->graph_mode >= 2) { ge = &h->graphs.back(); graphing = true; }
             }
         }
@@ -1703,8 +1703,11 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                 cudaGraph_t graph = nullptr;
                 CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
                 h->capturing = true;
+                float* const w_before = h->W;
                 const int rc = steps();
                 h->capturing = false;
+                ge->swapped = h->W != w_before;
+                if (ge->swapped) std::swap(h->W, h->TP);          // undone here, applied after the launch below like in every replay
                 const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
                 if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
                 if (ce != cudaSuccess || !graph) FAIL(h, "stream capture of the time loop failed: %s", cudaGetErrorString(ce));
@@ -1716,6 +1719,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                 h->timers.launches = l0;
             }
             CU(h, cudaGraphLaunch((cudaGraphExec_t)ge->exec, h->stream));
+            if (ge->swapped) std::swap(h->W, h->TP);
             h->timers.launches += ge->launches;
             graph_batches++;
         }

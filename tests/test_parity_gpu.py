@@ -544,14 +544,14 @@ def test_pingpong_adjoint_equals_the_copy_path(G, O, monkeypatch, physics):
     for flag in ("0", "1"):
         monkeypatch.setenv("GPI_PINGPONG", flag)            # read by gpi_create
         pg = G.PFdtd(attrib("forward_save"), **kw, **extra)
-        for rep in range(2):
+        for rep in range(4):                    # 2-D: launch by launch, captured into CUDA graphs, replayed twice (odd nt: the levels swap per run)
             g = np.zeros_like(m)
             loss = G.gradient(g, m, dobs, pg)
             res[flag, rep] = (g, loss, pg.last_launches)
     nss = len(kw["ageom"])
     nbatch = -(-nss // extra["shot_batch"]) if extra else nss
     nt = len(kw["tgrid"])
-    for rep in range(2):
+    for rep in range(4):
         g0, l0, n0 = res["0", rep]; g1, l1, n1 = res["1", rep]
         assert np.array_equal(g0, g1) and l0 == l1, f"ping-pong differs from the copy path (run {rep})"
         # + two boundary launches per step (the shell of the TMA tiles is walked by warps of the tile kernel itself: no launch of its own);
