@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Summarise an ncu --set full report (raw page CSV) into the handful of metrics DESIGN.md / profiles/ quote."""
-import csv, sys, subprocess, io
+import csv, sys, subprocess, io, json, os
+_pk = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "MEASURED_PEAKS.json")
+PEAK, PEAK_SRC = (json.load(open(_pk))["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if os.path.exists(_pk) else (6650.0, "fallback")
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -35,7 +37,7 @@ for r in rows[2:]:
             scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0, 'Tbyte': 1e12, 'us': 1e-6, 'ms': 1e-3, 'ns': 1e-9, 's': 1.0, 'usecond': 1e-6, 'msecond': 1e-3, 'nsecond': 1e-9, 'second': 1.0}.get(u, 1.0)
             return v * scale
         by = val('dram__bytes_read.sum') + val('dram__bytes_write.sum'); t = val('gpu__time_duration.sum')
-        print(f"{'ACHIEVED HBM (dram bytes / duration)':80s} {by / t / 1e9:.1f} GB/s = {by / t / 1e9 / 6650.0:.3f} of the 6650 GB/s fallback peak ({by / 1e6:.1f} MB in {t * 1e6:.1f} us)")
+        print(f"{'ACHIEVED HBM (dram bytes / duration)':80s} {by / t / 1e9:.1f} GB/s = {by / t / 1e9 / PEAK:.3f} of the {PEAK:.1f} GB/s {PEAK_SRC} peak ({by / 1e6:.1f} MB in {t * 1e6:.1f} us)")
     except Exception as e:
         print('achieved HBM: n/a', e)
     for k in keys:
