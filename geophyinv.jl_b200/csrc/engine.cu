@@ -185,6 +185,8 @@ struct gpi_handle {
     int o4by = 4;                                       // GPI_O4_BY: rows per block of the order-4 3-D kernels (1, 2, 4; planes = 4 / rows)
     int pzalign = 8;                                    // GPI_PZ_ALIGN (4, 8, 16, 32 floats)
     bool fuse2a = true;      // fused 2-D acoustic adjoint (kernels2a.cuh); GPI_FUSE2A=0 opts out
+    bool pdl = false;        // GPI_PDL=1: the launches of the 2-D chain (k_vel2v, k_stress2v, k_stress2a, k_post, k_boundary) carry the programmatic-
+                             // stream-serialization attribute (kernels.cuh: pdl_release / pdl_wait); captured into the time-loop graphs as programmatic edges
     void* t3_tiles[2] = {nullptr, nullptr};      // tile tables of the two tile kernels (geometry only: built once per handle)
     struct TmaSet { const float* key = nullptr; void* d[2] = {nullptr, nullptr}; } tmaps[2];  int tmap_victim = 0;   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
     void* encode_tiled = nullptr;                                            // cuTensorMapEncodeTiled (driver entry point)   // 3-D elastic: TMA-pipelined persistent kernels (kernels3t.cuh); GPI_TMA3=0 selects k_*3v
@@ -476,6 +478,22 @@ void launch_step_kernels3v(gpi_handle* h, const StepArgs& a, bool vel, int nbatc
     if (vel) k_vel3v<EL><<<grd, blk, 0, h->stream>>>(g, a);
     else     k_stress3v<EL><<<grd, blk, 0, h->stream>>>(g, a);
 }
+// launch with the programmatic-stream-serialization attribute (gpi_handle::pdl; the emulated engine never sets it)
+#ifndef GPI_HOST_EMU
+template <typename... P, typename... A>
+static inline void launch_pdl(gpi_handle* h, void (*kern)(P...), dim3 grd, dim3 blk, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grd; cfg.blockDim = blk; cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);      // errors surface at the cudaGetLastError() that closes the batch
+}
+#define GPI_PDL(h, kern, grd, blk, ...) launch_pdl(h, kern, grd, blk, __VA_ARGS__)
+#else
+#define GPI_PDL(h, kern, grd, blk, ...) ((void)0)
+#endif
 template <int ND, int EL>
 void launch_step_kernels(gpi_handle* h, const StepArgs& a, bool vel, int nbatch) {
     if (ND == 3 && h->vec3) { launch_step_kernels3v<EL>(h, a, vel, nbatch); return; }
@@ -483,10 +501,12 @@ void launch_step_kernels(gpi_handle* h, const StepArgs& a, bool vel, int nbatch)
         const int nthreads = (h->g.pz / VW) * h->g.nx1;
         dim3 blk(128), grd((nthreads + 127) / 128, nbatch);
         if (vel ? a.v_o[V_X] != nullptr : a.tau_o[T_XX] != nullptr) {      // out of place (ping-pong adjoint runs)
+            if (h->pdl) { if (vel) GPI_PDL(h, (k_vel2v<EL, 1>), grd, blk, h->g, a); else GPI_PDL(h, (k_stress2v<EL, 1>), grd, blk, h->g, a); return; }
             if (vel) k_vel2v<EL, 1><<<grd, blk, 0, h->stream>>>(h->g, a);
             else     k_stress2v<EL, 1><<<grd, blk, 0, h->stream>>>(h->g, a);
             return;
         }
+        if (h->pdl) { if (vel) GPI_PDL(h, (k_vel2v<EL, 0>), grd, blk, h->g, a); else GPI_PDL(h, (k_stress2v<EL, 0>), grd, blk, h->g, a); return; }
         if (vel) k_vel2v<EL><<<grd, blk, 0, h->stream>>>(h->g, a);
         else     k_stress2v<EL><<<grd, blk, 0, h->stream>>>(h->g, a);
         return;
@@ -606,7 +626,12 @@ int launch_boundary(gpi_handle* h, int save /* 0 force, 1 save (negated), 2 copy
     a.stores = table ? table : h->bnd_table;
     a.wstride = h->bstride;
     dim3 blk(128), grd((umax + 127) / 128, vmax, 2 * a.nbound * a.naxes * a.nf * nb);
-    if (save == 2)  k_boundary<2><<<grd, blk, 0, h->stream>>>(g, a);
+    if (h->pdl && h->nd == 2) {
+        if (save == 2)  GPI_PDL(h, k_boundary<2>, grd, blk, g, a);
+        else if (save)  GPI_PDL(h, k_boundary<1>, grd, blk, g, a);
+        else            GPI_PDL(h, k_boundary<0>, grd, blk, g, a);
+    }
+    else if (save == 2)  k_boundary<2><<<grd, blk, 0, h->stream>>>(g, a);
     else if (save)  k_boundary<1><<<grd, blk, 0, h->stream>>>(g, a);
     else            k_boundary<0><<<grd, blk, 0, h->stream>>>(g, a);
     h->timers.launches += 1;
@@ -938,6 +963,9 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (const char* e = getenv("GPI_TMA3_CTAS")) h->tma3_ctas = atoi(e);
     if (const char* e = getenv("GPI_SHELL")) h->shell_mode = atoi(e);
     if (const char* e = getenv("GPI_FUSE2A")) h->fuse2a = atoi(e) != 0;
+#ifndef GPI_HOST_EMU
+    if (const char* e = getenv("GPI_PDL")) h->pdl = atoi(e) != 0;
+#endif
     if (const char* e = getenv("GPI_PZ_ALIGN")) h->pzalign = atoi(e);
     if (const char* e = getenv("GPI_SLAB_PIPE")) h->slab_pipe = atoi(e) != 0;
     if (const char* e = getenv("GPI_GRAPH")) h->graph_mode = atoi(e);
@@ -1523,7 +1551,12 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
 #endif
         auto steps = [&]() -> int {
             // record!(1, ..., [:p]) at the start of step 1 (zero unless the fields were loaded from snapshots)
-            if (rec_s) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, 1, 1, nt, (float)h->c.dt, 2, 0LL); h->timers.launches += 1; }
+            const bool pdl2 = h->pdl && h->nd == 2;
+            if (rec_s) {
+                if (pdl2) GPI_PDL(h, k_post, dim3(nb), dim3(128), g, h->post_s, 1, 1, nt, (float)h->c.dt, 2, 0LL, 0, 0x7fffffff);
+                else k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, 1, 1, nt, (float)h->c.dt, 2, 0LL);
+                h->timers.launches += 1;
+            }
             // time levels: `cur` holds the fields of this step, `prev` those of the step before (adjoint runs; always W / TP without ping-pong)
             float* cur = h->W; float* prev = h->TP;
             float* const W0 = h->W;            // the descriptors and StepArgs above were built on this base
@@ -1588,7 +1621,11 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                         k_born_add<0><<<grd, blk, 0, h->stream>>>(g, args[1].v[V_X], args[1].v[V_Z], h->born_d, h->born_d + g.vol, h->born_c[1], h->born_c[2], h->bstride, 2 * g.vol);
                         h->timers.launches += 1;
                     }
-                    if (do_post_v) { k_post<<<nb, 128, 0, h->stream>>>(g, h->post_v, it, it, nt, (float)h->c.dt, 3, woff); h->timers.launches += 1; }
+                    if (do_post_v) {
+                        if (pdl2) GPI_PDL(h, k_post, dim3(nb), dim3(128), g, h->post_v, it, it, nt, (float)h->c.dt, 3, woff, 0, 0x7fffffff);
+                        else k_post<<<nb, 128, 0, h->stream>>>(g, h->post_v, it, it, nt, (float)h->c.dt, 3, woff);
+                        h->timers.launches += 1;
+                    }
                     if (exchange_halos(h, 1, sample)) return 1;
                     if (fuse2a) {
                         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1597,7 +1634,8 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                         ga2.vxA = wf_ptr(h, A, 0, 0, GPI_VX); ga2.vzA = wf_ptr(h, A, 0, 0, GPI_VZ);
                         const int nthreads = (g.pz / VW) * g.nx1;
                         dim3 blk(128), grd((nthreads + 127) / 128, nb);
-                        k_stress2a<<<grd, blk, 0, h->stream>>>(g, rebase(margs, A, Bn, false), ga2);
+                        if (pdl2) GPI_PDL(h, k_stress2a, grd, blk, g, rebase(margs, A, Bn, false), ga2);
+                        else k_stress2a<<<grd, blk, 0, h->stream>>>(g, rebase(margs, A, Bn, false), ga2);
                         if (e0 && e1) cudaEventRecord(e1, h->stream);
                         h->timers.launches += 1;
                     }
@@ -1610,7 +1648,8 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                     }
                     // stress sources at step it, then the pressure record of step it+1 (record! runs at the start of a step)
                     if (inj_s || (rec_s && it < nt)) {
-                        k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, it, it + 1, nt, (float)h->c.dt, 3, woff);
+                        if (pdl2) GPI_PDL(h, k_post, dim3(nb), dim3(128), g, h->post_s, it, it + 1, nt, (float)h->c.dt, 3, woff, 0, 0x7fffffff);
+                        else k_post<<<nb, 128, 0, h->stream>>>(g, h->post_s, it, it + 1, nt, (float)h->c.dt, 3, woff);
                         h->timers.launches += 1;
                     }
                     if (pp) {

@@ -55,6 +55,23 @@ __device__ __forceinline__ wide_t wadd(wide_t a, wide_t b) { return __fadd_rn(a,
 __device__ __forceinline__ wide_t wsub(wide_t a, wide_t b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ wide_t wdiv(wide_t a, wide_t b) { return __fdiv_rn(a, b); }
 #endif
+// ---- programmatic dependent launch (2-D time loops, gpi_handle::pdl) ---------------------------------------------------
+// A 2-D one-shot kernel lasts ~3 us of memory time but costs ~6 us as a stream / graph node: the rest is the launch of the next grid behind
+// the drained one.  The kernels of the 2-D chain therefore (1) touch nothing an earlier kernel writes before pdl_wait returns (the whole
+// preceding grid has completed and its stores are visible) -- k_post reads its static tables ahead of it -- and (2) then release their
+// dependents (pdl_release): once every CTA of the grid has got that far, the next grid's CTAs are scheduled into the slots that free up
+// and run their index preamble.  Release after wait: at most two grids overlap, and every kernel of the chain waits, so completion is
+// transitive along the stream.  Both are no-ops for a launch without the attribute (and on the host).
+__device__ __forceinline__ void pdl_release() {
+#ifndef GPI_HOST_EMU
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#ifndef GPI_HOST_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 // dt / (s * lit): store_invav*! (medium.jl:191-221) with s the Float32 sum of the macro
 __device__ __forceinline__ float inv_av(float dt, float s, float lit) { return (float)wdiv((wide_t)dt, wmul((wide_t)s, (wide_t)lit)); }
 
@@ -600,6 +617,8 @@ __global__ void k_post(const Geom g, const PostDesc* __restrict__ descs, int it 
             }
         }
     }
+    // the tables above are written before the run only; the wavefields and records below by the kernels ahead in the stream
+    pdl_wait(); pdl_release();
     // ---- sources
     for (int o = 0; o < ninj; o++) {
         const InjOp& op = d.inj[o];
@@ -675,6 +694,7 @@ struct BndArgs {
 };
 template <int SAVE>
 __global__ void k_boundary(const Geom g, const BndArgs a) {
+    pdl_wait(); pdl_release();
     int z = blockIdx.z;
     const int p = z % (2 * a.nbound); z /= 2 * a.nbound;      // plane 0..2*nbound-1
     const int ia = z % a.naxes; z /= a.naxes;

@@ -47,6 +47,7 @@ __device__ __forceinline__ bool near_forced(const Grad2aArgs& ga, int k0, int i)
 #define GPI_S2A_MINB 5
 #endif
 __global__ void __launch_bounds__(128, GPI_S2A_MINB) k_stress2a(const Geom g, const StepArgs a, const Grad2aArgs ga) {
+    pdl_wait(); pdl_release();
     const Vec2Idx q = vec2_index(g);
     if (!q.valid) return;
     const int k0 = q.k0, i = q.i, b = q.b;

@@ -24,6 +24,7 @@ __device__ __forceinline__ Vec2Idx vec2_index(const Geom& g) {
 // ------------------------------------------------------------------------------------------------
 template <int EL, int OOP = 0>      // OOP: out of place, reads a.v and writes a.v_o (StepArgs)
 __global__ void __launch_bounds__(128) k_vel2v(const Geom g, const StepArgs a) {
+    pdl_wait(); pdl_release();
     const Vec2Idx q = vec2_index(g);
     if (!q.valid) return;
     const int k0 = q.k0, i = q.i, b = q.b;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(128) k_vel2v(const Geom g, const StepArgs a) {
 // ------------------------------------------------------------------------------------------------
 template <int EL, int OOP = 0>      // OOP: out of place, reads a.tau and writes a.tau_o
 __global__ void __launch_bounds__(128) k_stress2v(const Geom g, const StepArgs a) {
+    pdl_wait(); pdl_release();
     const Vec2Idx q = vec2_index(g);
     if (!q.valid) return;
     const int k0 = q.k0, i = q.i, b = q.b;
