@@ -185,8 +185,11 @@ struct gpi_handle {
     int o4by = 4;                                       // GPI_O4_BY: rows per block of the order-4 3-D kernels (1, 2, 4; planes = 4 / rows)
     int pzalign = 8;                                    // GPI_PZ_ALIGN (4, 8, 16, 32 floats)
     bool fuse2a = true;      // fused 2-D acoustic adjoint (kernels2a.cuh); GPI_FUSE2A=0 opts out
-    bool pdl = false;        // GPI_PDL=1: the launches of the 2-D chain (k_vel2v, k_stress2v, k_stress2a, k_post, k_boundary) carry the programmatic-
-                             // stream-serialization attribute (kernels.cuh: pdl_release / pdl_wait); captured into the time-loop graphs as programmatic edges
+    // Programmatic dependent launch for the 2-D chain (k_vel2v, k_stress2v, k_stress2a, k_post, k_boundary; kernels.cuh: pdl_wait / pdl_release):
+    // the launches carry the programmatic-stream-serialization attribute, so the next grid's CTAs are scheduled while the last wave of the
+    // current one drains; captured into the time-loop graphs as programmatic edges.  C2 with 1 / 8 resident shots 42.9 -> 45.2 / 100.8 -> 105.1,
+    // C4 87.7 -> 89.2 Gcell-updates/s, bit-identical (profiles/r02/ab_pdl.txt, tests/test_pdl_gpu.py).  GPI_PDL=0 opts out.
+    bool pdl = true;
     void* t3_tiles[2] = {nullptr, nullptr};      // tile tables of the two tile kernels (geometry only: built once per handle)
     struct TmaSet { const float* key = nullptr; void* d[2] = {nullptr, nullptr}; } tmaps[2];  int tmap_victim = 0;   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
     void* encode_tiled = nullptr;                                            // cuTensorMapEncodeTiled (driver entry point)   // 3-D elastic: TMA-pipelined persistent kernels (kernels3t.cuh); GPI_TMA3=0 selects k_*3v
@@ -478,7 +481,7 @@ void launch_step_kernels3v(gpi_handle* h, const StepArgs& a, bool vel, int nbatc
     if (vel) k_vel3v<EL><<<grd, blk, 0, h->stream>>>(g, a);
     else     k_stress3v<EL><<<grd, blk, 0, h->stream>>>(g, a);
 }
-// launch with the programmatic-stream-serialization attribute (gpi_handle::pdl; the emulated engine never sets it)
+// launch with the programmatic-stream-serialization attribute (gpi_handle::pdl; always off in the emulated engine)
 #ifndef GPI_HOST_EMU
 template <typename... P, typename... A>
 static inline void launch_pdl(gpi_handle* h, void (*kern)(P...), dim3 grd, dim3 blk, A&&... args) {
@@ -963,7 +966,9 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (const char* e = getenv("GPI_TMA3_CTAS")) h->tma3_ctas = atoi(e);
     if (const char* e = getenv("GPI_SHELL")) h->shell_mode = atoi(e);
     if (const char* e = getenv("GPI_FUSE2A")) h->fuse2a = atoi(e) != 0;
-#ifndef GPI_HOST_EMU
+#ifdef GPI_HOST_EMU
+    h->pdl = false;          // the emulation runs one grid after the other through plain launches
+#else
     if (const char* e = getenv("GPI_PDL")) h->pdl = atoi(e) != 0;
 #endif
     if (const char* e = getenv("GPI_PZ_ALIGN")) h->pzalign = atoi(e);
