@@ -7,6 +7,7 @@
 // half step.  There is no CPU fallback: every entry point needs a CUDA device.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <dlfcn.h>
 #include <algorithm>
 #include <cstdarg>
@@ -190,6 +191,7 @@ struct gpi_handle {
     // current one drains; captured into the time-loop graphs as programmatic edges.  C2 with 1 / 8 resident shots 42.9 -> 45.2 / 100.8 -> 105.1,
     // C4 87.7 -> 89.2 Gcell-updates/s, bit-identical (profiles/r02/ab_pdl.txt, tests/test_pdl_gpu.py).  GPI_PDL=0 opts out.
     bool pdl = true;
+    bool nvtx = false;       // GPI_NVTX=1: NVTX ranges around the phases of the entry points (a run, each resident batch, medium update, all-reduce) for nsys / ncu --nvtx
     void* t3_tiles[2] = {nullptr, nullptr};      // tile tables of the two tile kernels (geometry only: built once per handle)
     struct TmaSet { const float* key = nullptr; void* d[2] = {nullptr, nullptr}; } tmaps[2];  int tmap_victim = 0;   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
     void* encode_tiled = nullptr;                                            // cuTensorMapEncodeTiled (driver entry point)   // 3-D elastic: TMA-pipelined persistent kernels (kernels3t.cuh); GPI_TMA3=0 selects k_*3v
@@ -481,6 +483,17 @@ void launch_step_kernels3v(gpi_handle* h, const StepArgs& a, bool vel, int nbatc
     if (vel) k_vel3v<EL><<<grd, blk, 0, h->stream>>>(g, a);
     else     k_stress3v<EL><<<grd, blk, 0, h->stream>>>(g, a);
 }
+// NVTX range for the lifetime of the object (gpi_handle::nvtx); the profiler sees the phases the per-phase timers of gpi_get_timers count
+struct Range {
+    bool on;
+    Range(const gpi_handle* h, const char* fmt, ...) : on(h && h->nvtx) {
+        if (!on) return;
+        char buf[160]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        nvtxRangePushA(buf);
+    }
+    ~Range() { if (on) nvtxRangePop(); }
+    Range(const Range&) = delete;
+};
 // launch with the programmatic-stream-serialization attribute (gpi_handle::pdl; always off in the emulated engine)
 #ifndef GPI_HOST_EMU
 template <typename... P, typename... A>
@@ -966,6 +979,7 @@ extern "C" int gpi_create(const gpi_config* cfg, gpi_handle** out) {
     if (const char* e = getenv("GPI_TMA3_CTAS")) h->tma3_ctas = atoi(e);
     if (const char* e = getenv("GPI_SHELL")) h->shell_mode = atoi(e);
     if (const char* e = getenv("GPI_FUSE2A")) h->fuse2a = atoi(e) != 0;
+    if (const char* e = getenv("GPI_NVTX")) h->nvtx = atoi(e) != 0;
 #ifdef GPI_HOST_EMU
     h->pdl = false;          // the emulation runs one grid after the other through plain launches
 #else
@@ -1091,6 +1105,7 @@ extern "C" int gpi_set_medium_interior(gpi_handle* h, int p, const float* a, con
 // (k_pad_derive).  Replaces one Medium getter + gpi_set_medium_interior per parameter; same H2D bytes, no host-side arithmetic.
 extern "C" int gpi_set_medium_fields(gpi_handle* h, const float* vp, const float* vs, const float* rho, const int32_t n_in[3], const int32_t lo[3]) {
     GUARD(h);
+    Range range(h, "%s", "gpi_set_medium_fields (update!(pa, medium))");
     if (!vp || !rho || !n_in || !lo || (h->el && !vs)) FAIL(h, "null medium array (an elastic medium needs vp, vs and rho)");
     const Geom& g = h->g;
     const int mz = n_in[0], my = h->nd == 3 ? n_in[1] : 1, mx = n_in[2];
@@ -1127,6 +1142,7 @@ extern "C" int gpi_get_medium(gpi_handle* h, int p, float* out) {
 }
 extern "C" int gpi_update_dmod(gpi_handle* h) {
     GUARD(h);
+    Range range(h, "%s", "gpi_update_dmod");
     dim3 blk = h->nd == 3 ? h->blk3 : h->blk2, grd = grid_for(h, blk, 1);
     const float dt = (float)h->c.dt;
     const float* m0 = h->el ? h->mod[GPI_INVLAMBDA] : h->mod[GPI_INVK];
@@ -1488,6 +1504,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     const size_t vb = (size_t)g.vol * sizeof(float);
     int bf[6]; const int nbf = boundary_fields(h, bf);
     const int vf[3] = {GPI_VX, GPI_VY, GPI_VZ};
+    Range run_range(h, "gpi_run %s%s pw %d", mode == GPI_MODE_FORWARD ? "forward" : mode == GPI_MODE_FORWARD_SAVE ? "forward_save" : "adjoint", born ? " born" : "", activepw);
     h->timers = gpi_timers{};
     h->evused = 0; h->evkind.clear();
     CU(h, cudaEventRecord(h->ev0, h->stream));
@@ -1495,6 +1512,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     int graph_batches = 0;
     for (int shot0 = 0; shot0 < h->c.nshots; shot0 += h->B) {
         const int nb = std::min(h->B, h->c.nshots - shot0);
+        Range batch_range(h, "shots %d..%d (%d time steps)", shot0, shot0 + nb - 1, nt);
         // reset_w2! (types.jl:100-113)
         CU(h, cudaMemsetAsync(h->W, 0, (size_t)nb * h->bstride * sizeof(float), h->stream));
         if (h->TP) CU(h, cudaMemsetAsync(h->TP, 0, (size_t)nb * h->bstride * sizeof(float), h->stream));
@@ -1908,6 +1926,7 @@ extern "C" int gpi_nccl_init(gpi_handle* h, const void* id128, int rank, int nra
 // the cross-worker half of sum_grads! (gradient.jl:2-11): one sum all-reduce per parameter over NVLink
 extern "C" int gpi_allreduce_gradients(gpi_handle* h) {
     GUARD(h);
+    Range range(h, "%s", "gpi_allreduce_gradients (sum_grads! across ranks)");
     if (!h->comm) { if (h->nranks == 1) return 0; FAIL(h, "gpi_nccl_init has not been called"); }
     CU(h, cudaEventRecord(h->ev0, h->stream));
     for (int p = 0; p < GPI_NPARAM; p++) if (h->gtot[p]) {

@@ -76,6 +76,8 @@ static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = malloc(1); retu
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = malloc(1); return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline int nvtxRangePushA(const char*) { return 0; }      // NVTX (engine.cu: struct Range)
+static inline int nvtxRangePop() { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 
 // ---- driver API: the tensor-map encoder ------------------------------------------------------------------------------------------

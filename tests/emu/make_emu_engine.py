@@ -1,7 +1,7 @@
 """Rewrites geophyinv.jl_b200/csrc/engine.cu into a host C++ translation unit (test infrastructure; see tests/emu/cuda_rt_shim.h).
 
 Only two textual changes are made, so what the no-GPU suite runs IS the engine's host code and kernels:
-  1. <cuda.h> / <cuda_runtime.h>  ->  "cuda_rt_shim.h"  (host stand-in for the runtime API);
+  1. <cuda.h> / <cuda_runtime.h> / <nvtx3/nvToolsExt.h>  ->  "cuda_rt_shim.h"  (host stand-in for the runtime API);
   2. every launch  k<<<grid, block, smem, stream>>>(args);  ->  emu::launch(grid, block, [&] { k(args); });
      (emu::launch_mt for the kernels that use __syncthreads).
 build(out_dir) compiles the result to libgpifdtd_emu.so and returns its path.
@@ -71,6 +71,7 @@ def rewrite_launches(src: str):
 
 def transform(src: str):
     src = src.replace("#include <cuda.h>\n", "").replace("#include <cuda_runtime.h>", '#include "cuda_rt_shim.h"')
+    src = src.replace("#include <nvtx3/nvToolsExt.h>\n", "")          # nvtxRangePushA / nvtxRangePop: no-op stand-ins in the shim
     src = src.replace('#include "../../include/gpifdtd.h"', f'#include "{os.path.join(ROOT, "include", "gpifdtd.h")}"')
     src, n = rewrite_launches(src)
     assert "<<<" not in src
