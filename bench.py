@@ -642,8 +642,8 @@ def extra_legs(args):
     rank, local_rank, world = dist_env()
     dist = get_dist()
     extra = {}
-    for name, fn in (("c4", lambda: {**(run_c4(args, steps=2, warmup=2, nss_total=32) or {}), **(c4_parity(dist, rank, local_rank, world) or {})}),
-                     ("c5", lambda: {**(run_c5(args, steps=2, warmup=1) or {}), **(slab_parity(dist, rank, local_rank, world) or {})})):
+    for name, fn in (("c4", lambda: {**(run_c4(args, steps=2, warmup=3, nss_total=32) or {}), **(c4_parity(dist, rank, local_rank, world) or {})}),
+                     ("c5", lambda: {**(run_c5(args, steps=2, warmup=3) or {}), **(slab_parity(dist, rank, local_rank, world) or {})})):
         t0 = time.time()
         try:
             leg = fn()

@@ -14,7 +14,7 @@ def test_gradient3d_vs_finite_differences(G, O):
     from geophyinv_jl_b200.host import gallery
     from scipy.ndimage import gaussian_filter
     n = 16
-    kw, true = gallery.fwi3d(n=n, nt=150, nr=10)
+    kw, true = gallery.fwi3d(n=n, nt=150, nr=10, nss=1)        # one supersource: eleven passes over the (16 + 2 x 41)^3 grid in Float64
     pt = O.OraclePFdtd64(G.FdtdAcoustic(), **{**kw, "medium": true})
     pt.update()
     dobs = [d.copy() for d in pt.c.data[0]]
@@ -138,7 +138,7 @@ def test_elastic3d_gradient_vs_finite_differences(G, O):
     upstream's combine_gmodrho! construction."""
     from geophyinv_jl_b200.host import gallery
     n = 14
-    kw, true = gallery.fwi3d_elastic(n=n, nt=125)
+    kw, true = gallery.fwi3d_elastic(n=n, nt=100)
     pt = O.OraclePFdtd64(G.FdtdElastic(), **{**kw, "medium": true})
     pt.update()
     dobs = [d.copy() for d in pt.c.data[0]]

@@ -31,7 +31,6 @@ SELECTION = [
     PARITY + "test_acoustic2d_multishot_batches",
     PARITY + "test_elastic2d_records[True]",
     PARITY + "test_elastic2d_stress_source",
-    PARITY + "test_c3_elastic3d_reduced[True]",
     PARITY + "test_elastic3d_partial_pml_faces[faces1]",        # TMA tiles forced (GPI_TMA3=2), CPML boxes on three faces
     PARITY + "test_elastic3d_partial_pml_faces[faces2]",
     PARITY + "test_dmod_matches_oracle",
@@ -41,9 +40,8 @@ SELECTION = [
     PARITY + "test_boundary_save_and_force_match_oracle[elastic2d]",
     PARITY + "test_small_and_degenerate_cases",
     PARITY + "test_axis_shorter_than_npml_is_rejected_with_a_message",
-    PARITY + "test_fwi_gradient_acoustic2d",
+    PARITY + "test_fwi_gradient_acoustic2d",                    # default path: ping-pong time levels + the fused pass of kernels2a.cuh
     PARITY + "test_born_records_match_oracle[p-rfields0]",
-    PARITY + "test_pingpong_adjoint_equals_the_copy_path[acoustic]",
     PARITY + "test_pingpong_adjoint_equals_the_copy_path[elastic]",
     "tests/test_order4.py::test_order4_elastic2d[False-vz]",
     # the engine against fixtures evaluated from the REFERENCE'S OWN KERNEL TEXT (no oracle in the loop): every physics / order / dimension

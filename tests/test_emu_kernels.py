@@ -19,9 +19,11 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("name", ["emu_kernels2", "emu_kernels4", "emu_kernels_misc"])
-def test_vectorised_kernels_match_the_reference_order_kernels(tmp_path, name):
-    exe = str(tmp_path / name)
+NAMES = ["emu_kernels2", "emu_kernels4", "emu_kernels_misc"]
+
+
+def _build_and_run(name, out_dir):
+    exe = os.path.join(out_dir, name)
     src = os.path.join(ROOT, "tests", "emu", name + ".cpp")
     # AddressSanitizer + UBSan: the operands live in exactly-sized host vectors, so any read or write outside a field, a coefficient
     # array or a CPML memory block (a halo load at the edge of the box, a float4 straddling a row) aborts the run
@@ -30,7 +32,25 @@ def test_vectorised_kernels_match_the_reference_order_kernels(tmp_path, name):
     r = subprocess.run(["g++"] + flags + san + ["-o", exe, src], capture_output=True, text=True)
     if r.returncode != 0:                       # toolchain without the sanitizer runtimes: plain build
         r = subprocess.run(["g++"] + flags + ["-o", exe, src], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-3000:]
+    if r.returncode != 0:
+        return r.returncode, "compile failed:\n" + r.stderr[-3000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
-    sys.stdout.write(r.stdout)
-    assert r.returncode == 0 and "EMU_OK" in r.stdout, r.stdout[-3000:]
+    return r.returncode, r.stdout
+
+
+@pytest.fixture(scope="module")
+def harness_runs(tmp_path_factory):
+    """The three harnesses are single-threaded compile-and-run jobs: started together, collected one by one."""
+    from concurrent.futures import ThreadPoolExecutor
+    out_dir = str(tmp_path_factory.mktemp("emu_kernels"))
+    pool = ThreadPoolExecutor(max_workers=len(NAMES))
+    futures = {name: pool.submit(_build_and_run, name, out_dir) for name in NAMES}
+    yield futures
+    pool.shutdown(wait=True)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_vectorised_kernels_match_the_reference_order_kernels(harness_runs, name):
+    rc, out = harness_runs[name].result(timeout=1200)
+    sys.stdout.write(out)
+    assert rc == 0 and "EMU_OK" in out, out[-3000:]

@@ -436,15 +436,19 @@ def stokes_misfits(G, make):
                   - (gi * gj - dij) * np.exp(-1j * ww * r / be) / (be ** 2 * r)) / (4 * np.pi * rho)
         return np.fft.irfft(1j * w * Gw * F * np.exp(1j * w * 0.5 * dt), np2)[:nt]
 
+    # one run records both fields at the union of the two receiver sets (nodes of the :vz grid, then nodes of the :vx grid); each field is
+    # compared at its own nodes only, where the interpolation weights are a single 1
+    sets = {rf: {k: np.array([g[q][S[q] + o[q]] for o in offs]) for q, k in enumerate(("z", "y", "x"))} for rf, g in (("vz", gvz), ("vx", gvx))}
+    rec = {k: np.concatenate([sets["vz"][k], sets["vx"][k]]) for k in ("z", "y", "x")}
+    ageom = [AGeomss({"z": [spos[0]], "y": [spos[1]], "x": [spos[2]]}, rec)]
+    srcwav = make_srcwav(tgrid, ageom, ["vz"], wav)
+    po = make(G.FdtdElastic(), medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=["vz", "vx"], upstream_3d_swap=False)
+    po.update()
     out = {}
-    for rf, g, comp in (("vz", gvz, 0), ("vx", gvx, 2)):
-        rec = {k: np.array([g[q][S[q] + o[q]] for o in offs]) for q, k in enumerate(("z", "y", "x"))}
-        ageom = [AGeomss({"z": [spos[0]], "y": [spos[1]], "x": [spos[2]]}, rec)]
-        srcwav = make_srcwav(tgrid, ageom, ["vz"], wav)
-        po = make(G.FdtdElastic(), medium=medium, tgrid=tgrid, ageom=ageom, srcwav=srcwav, rfields=[rf], upstream_3d_swap=False)
-        po.update()
-        dat = po.c.data[0][0].d[rf].astype(np.float64)
-        ana = np.stack([stokes_velocity(np.array([rec["z"][ir] - spos[0], rec["y"][ir] - spos[1], rec["x"][ir] - spos[2]]), comp)
+    for rf, comp, first in (("vz", 0, 0), ("vx", 2, len(offs))):
+        dat = po.c.data[0][0].d[rf].astype(np.float64)[:, first:first + len(offs)]
+        r = sets[rf]
+        ana = np.stack([stokes_velocity(np.array([r["z"][ir] - spos[0], r["y"][ir] - spos[1], r["x"][ir] - spos[2]]), comp)
                         for ir in range(len(offs))], axis=1)
         out[rf] = float(np.sum((dat - ana) ** 2) / np.sum(ana ** 2))
     return out
