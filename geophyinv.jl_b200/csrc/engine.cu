@@ -191,6 +191,7 @@ struct gpi_handle {
     // current one drains; captured into the time-loop graphs as programmatic edges.  C2 with 1 / 8 resident shots 42.9 -> 45.2 / 100.8 -> 105.1,
     // C4 87.7 -> 89.2 Gcell-updates/s, bit-identical (profiles/r02/ab_pdl.txt, tests/test_pdl_gpu.py).  GPI_PDL=0 opts out.
     bool pdl = true;
+    bool illum_on = false;  double* illum_acc = nullptr;  double* illum_stack = nullptr;   // gpi_set_illum: [B][vol] per resident shot, [vol] stacked over the shots
     bool nvtx = false;       // GPI_NVTX=1: NVTX ranges around the phases of the entry points (a run, each resident batch, medium update, all-reduce) for nsys / ncu --nvtx
     void* t3_tiles[2] = {nullptr, nullptr};      // tile tables of the two tile kernels (geometry only: built once per handle)
     struct TmaSet { const float* key = nullptr; void* d[2] = {nullptr, nullptr}; } tmaps[2];  int tmap_victim = 0;   // TMA descriptors (device copies) per pw: [0] velocity, [1] stress kernel
@@ -262,20 +263,21 @@ int upload_field(gpi_handle* h, int f, const float* src, float* dvol, int k_firs
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
-int download_field(gpi_handle* h, int f, const float* dvol, float* dst) {
+template <typename T>
+int download_field(gpi_handle* h, int f, const T* dvol, T* dst) {
     const Geom& g = h->g;
     int n[3] = {g.nz, g.ny, g.nx}, sh[3], off[3];
     if (field_shape(h->nd, f, n, sh, off, h->c.order)) FAIL(h, "field %d has no shape in %d-D", f, h->nd);
-    if (ensure_stage(h, (size_t)g.vol)) return 1;
-    CU(h, cudaMemcpyAsync(h->stage, dvol, (size_t)g.vol * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (ensure_stage(h, (size_t)g.vol * (sizeof(T) / sizeof(float)))) return 1;
+    CU(h, cudaMemcpyAsync(h->stage, dvol, (size_t)g.vol * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     const int iz_lo = std::max(0, g.koff + g.klo - off[0]);
     const int iz_hi = std::min(sh[0], g.koff + g.khi + 1 - off[0]);                          // exclusive
-    if (h->slab) memset(dst, 0, (size_t)sh[0] * sh[1] * sh[2] * sizeof(float));
+    if (h->slab) memset(dst, 0, (size_t)sh[0] * sh[1] * sh[2] * sizeof(T));
     if (iz_hi > iz_lo) for (int ix = 0; ix < sh[2]; ix++) for (int iy = 0; iy < sh[1]; iy++) {
-        float* d = dst + (size_t)sh[0] * ((size_t)iy + (size_t)sh[1] * ix) + iz_lo;
-        const float* sp = h->stage + (iz_lo + off[0] - g.koff) + (size_t)g.pz * ((size_t)(iy + off[1]) + (size_t)g.ny1 * (ix + off[2]));
-        memcpy(d, sp, (size_t)(iz_hi - iz_lo) * sizeof(float));
+        T* d = dst + (size_t)sh[0] * ((size_t)iy + (size_t)sh[1] * ix) + iz_lo;
+        const T* sp = (const T*)h->stage + (iz_lo + off[0] - g.koff) + (size_t)g.pz * ((size_t)(iy + off[1]) + (size_t)g.ny1 * (ix + off[2]));
+        memcpy(d, sp, (size_t)(iz_hi - iz_lo) * sizeof(T));
     }
     return 0;
 }
@@ -1019,6 +1021,7 @@ extern "C" int gpi_destroy(gpi_handle* h) {
     cudaFree(h->dmod_table);
     for (auto& p : h->gtot) cudaFree(p);
     cudaFree(h->gshot);
+    cudaFree(h->illum_acc); cudaFree(h->illum_stack);
     for (int ipw = 0; ipw < 2; ipw++) for (auto& s : h->shots[ipw]) {
         for (int f = 0; f < GPI_NWAVEFIELD; f++) {
             free_sparse(s.spray[f]); free_sparse(s.interp[f]);
@@ -1509,6 +1512,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
     h->evused = 0; h->evkind.clear();
     CU(h, cudaEventRecord(h->ev0, h->stream));
 
+    if (h->illum_on) CU(h, cudaMemsetAsync(h->illum_stack, 0, (size_t)g.vol * sizeof(double), h->stream));      // initialize!(pac): fill!(illum_stack, 0.0) (types.jl:171)
     int graph_batches = 0;
     for (int shot0 = 0; shot0 < h->c.nshots; shot0 += h->B) {
         const int nb = std::min(h->B, h->c.nshots - shot0);
@@ -1518,6 +1522,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
         if (h->TP) CU(h, cudaMemsetAsync(h->TP, 0, (size_t)nb * h->bstride * sizeof(float), h->stream));
         CU(h, cudaMemsetAsync(h->MEM, 0, (size_t)nb * h->npw * h->mem_per_pw * sizeof(float), h->stream));
         if (grad) CU(h, cudaMemsetAsync(h->gshot, 0, (size_t)nb * h->ngrad * vb, h->stream));
+        if (h->illum_on) CU(h, cudaMemsetAsync(h->illum_acc, 0, (size_t)nb * g.vol * sizeof(double), h->stream));
         if (mode == GPI_MODE_ADJOINT) {       // boundary_force_snap_tau!/v! (boundary.jl:173-212)
             for (int b = 0; b < nb; b++) {
                 ShotData& s = h->shots[0][shot0 + b];
@@ -1561,7 +1566,7 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             unsigned long long key = 1469598103934665603ULL;
             auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ULL; };
             mix(mode); mix(activepw); mix(src_flags); mix(shot0); mix(nb); mix(do_post_v); mix(inj_s); mix(rec_s); mix(born); mix(nt);
-            mix((unsigned long long)(uintptr_t)h->stream); mix((unsigned long long)(uintptr_t)h->W); mix(pp); mix(unshifted); mix(h->itsnaps.size());
+            mix((unsigned long long)(uintptr_t)h->stream); mix((unsigned long long)(uintptr_t)h->W); mix(pp); mix(unshifted); mix(h->illum_on); mix(h->itsnaps.size());
             for (int v : h->itsnaps) mix(v);
             for (int b = 0; b < nb; b++) for (int ipw = 0; ipw < h->npw; ipw++) for (auto p : h->shots[ipw][shot0 + b].usnaps) mix((unsigned long long)(uintptr_t)p);
             for (auto& e : h->graphs) if (e.key == key) ge = &e;
@@ -1730,6 +1735,10 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
                         h->gshot, h->gshot + g.vol, (float)h->c.dtI, h->bstride, 2 * g.vol, unshifted);
                     h->timers.launches += 1;
                 }
+                if (h->illum_on) {      // compute_illum! (fdtd.jl:570-581; its place in the loop: propagate.jl:236): pressure of pw 1 after the stress update and sources of this step
+                    k_illum<<<dim3((unsigned)((g.vol + 255) / 256), nb), 256, 0, h->stream>>>(h->illum_acc, wf_ptr(h, cur, 0, 0, GPI_P), g.vol, h->bstride);
+                    h->timers.launches += 1;
+                }
                 if (!h->itsnaps.empty()) for (int ks = 0; ks < (int)h->itsnaps.size(); ks++) if (h->itsnaps[ks] == it)
                     for (int ipw = 0; ipw < h->npw; ipw++) if (activepw & (1 << ipw)) for (int b = 0; b < nb; b++)
                         CU(h, cudaMemcpyAsync(h->shots[ipw][shot0 + b].usnaps[ks], wf_ptr(h, cur, b, ipw, h->c.snaps_field), vb, cudaMemcpyDeviceToDevice, h->stream));
@@ -1749,6 +1758,11 @@ extern "C" int gpi_run(gpi_handle* h, int mode, int activepw, int src_flags) {
             if (mode == GPI_MODE_FORWARD_SAVE)
                 for (int b = 0; b < nb; b++) for (int i = 0; i < 3; i++) if (h->shots[0][shot0 + b].snap[vf[i]])
                     CU(h, cudaMemcpyAsync(h->shots[0][shot0 + b].snap[vf[i]], wf_ptr(h, h->W, b, 0, vf[i]), vb, cudaMemcpyDeviceToDevice, h->stream));
+            // stack_illums! (fdtd.jl:556-565): shot order
+            if (h->illum_on) for (int b = 0; b < nb; b++) {
+                k_axpy1d<<<(unsigned)((g.vol + 255) / 256), 256, 0, h->stream>>>(h->illum_stack, h->illum_acc + (size_t)b * g.vol, g.vol);
+                h->timers.launches += 1;
+            }
             // sum_grads! (gradient.jl:2-11): stack in shot order
             if (grad) for (int b = 0; b < nb; b++) {
                 for (int q = 0; q < h->ngrad; q++)
@@ -1861,6 +1875,24 @@ extern "C" int gpi_get_snap(gpi_handle* h, int ipw, int issp, int isnap, float* 
     GUARD(h);
     if (ipw < 0 || ipw >= h->npw || issp < 0 || issp >= h->c.nshots || isnap < 0 || isnap >= h->c.nsnaps) FAIL(h, "bad snapshot index");
     return download_field(h, h->c.snaps_field, h->shots[ipw][issp].usnaps[isnap], out);
+}
+// source illumination (gpifdtd.h): accumulators are allocated at the first gpi_set_illum(h, 1)
+extern "C" int gpi_set_illum(gpi_handle* h, int on) {
+    GUARD(h);
+    if (on && h->el) FAIL(h, "the illumination is defined on the pressure field: acoustic experiments only (fdtd.jl:570-581)");
+    if (on && h->slab) FAIL(h, "z-slab handles do not accumulate the illumination");
+    if (on && !h->illum_acc) {
+        CU(h, cudaMalloc((void**)&h->illum_acc, (size_t)h->B * h->g.vol * sizeof(double)));
+        CU(h, cudaMalloc((void**)&h->illum_stack, (size_t)h->g.vol * sizeof(double)));
+        CU(h, cudaMemset(h->illum_stack, 0, (size_t)h->g.vol * sizeof(double)));
+    }
+    h->illum_on = on != 0;
+    return 0;
+}
+extern "C" int gpi_get_illum(gpi_handle* h, double* out) {
+    GUARD(h);
+    if (!h->illum_stack) FAIL(h, "no illumination: call gpi_set_illum(h, 1) before gpi_run");
+    return download_field(h, GPI_P, h->illum_stack, out);
 }
 extern "C" int gpi_get_field(gpi_handle* h, int ipw, int ib, int f, float* out) {
     GUARD(h);

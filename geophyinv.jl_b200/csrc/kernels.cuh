@@ -990,4 +990,22 @@ __global__ void k_axpy1(float* __restrict__ y, const float* __restrict__ x, long
     if (t < n) y[t] = __fadd_rn(y[t], x[t]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// source illumination (compute_illum!, fdtd.jl:570-581: illum[i] += abs2(p[i]) at every time step, Float32 square added
+// into a Float64 array; stack_illums!, fdtd.jl:556-565: summed over the supersources in shot order).  Upstream has the
+// two calls commented out (propagate.jl:114,236) and allocates a dummy; `illum_flag` (fdtd.jl:59,73) documents the intent:
+// the wavefield energy of pw 1 as a preconditioner.  One accumulator per resident shot (blockIdx.y).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_illum(double* __restrict__ acc, const float* __restrict__ p, long long n, long long wstride) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float v = p[(long long)blockIdx.y * wstride + t];
+    double* a = acc + (long long)blockIdx.y * n + t;
+    *a = __dadd_rn(*a, (double)__fmul_rn(v, v));
+}
+__global__ void k_axpy1d(double* __restrict__ y, const double* __restrict__ x, long long n) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) y[t] = __dadd_rn(y[t], x[t]);
+}
+
 }  // namespace gpi

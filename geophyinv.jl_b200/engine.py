@@ -67,7 +67,7 @@ EXPORTS = [
     "gpi_update_dmod", "gpi_set_medium_pert", "gpi_update_born", "gpi_set_pml", "gpi_set_sparse", "gpi_set_wavelets", "gpi_run", "gpi_get_records",
     "gpi_get_gradient", "gpi_get_snap", "gpi_set_snap_steps", "gpi_get_field", "gpi_set_field", "gpi_reset",
     "gpi_nccl_unique_id", "gpi_nccl_init", "gpi_allreduce_gradients", "gpi_records_device_ptr",
-    "gpi_gradient_device_ptr", "gpi_set_stream", "gpi_synchronize", "gpi_get_timers", "gpi_kernel_family", "gpi_field_shape", "gpi_field_shape_order",
+    "gpi_gradient_device_ptr", "gpi_set_illum", "gpi_get_illum", "gpi_set_stream", "gpi_synchronize", "gpi_get_timers", "gpi_kernel_family", "gpi_field_shape", "gpi_field_shape_order",
 ]
 
 _lib = None
@@ -111,6 +111,8 @@ def load_library(path: str = LIB_PATH):
         "gpi_get_gradient": ([vp, C.c_int, fp], C.c_int),
         "gpi_get_snap": ([vp, C.c_int, C.c_int, C.c_int, fp], C.c_int),
         "gpi_set_snap_steps": ([vp, C.c_int, ip], C.c_int),
+        "gpi_set_illum": ([vp, C.c_int], C.c_int),
+        "gpi_get_illum": ([vp, C.POINTER(C.c_double)], C.c_int),
         "gpi_get_field": ([vp, C.c_int, C.c_int, C.c_int, fp], C.c_int),
         "gpi_set_field": ([vp, C.c_int, C.c_int, C.c_int, fp], C.c_int),
         "gpi_reset": ([vp, C.c_int], C.c_int),
@@ -293,6 +295,16 @@ class Engine:
         shp = self.field_shape(FIELDS[self.cfg.snaps_field])
         out = np.empty(int(np.prod(shp)), np.float32)
         self._ck(self.lib.gpi_get_snap(self.h, ipw, issp, isnap, _fp(out)))
+        return out.reshape(shp, order="F")
+
+    def set_illum(self, on: bool):
+        self._ck(self.lib.gpi_set_illum(self.h, 1 if on else 0))
+
+    def get_illum(self):
+        """Float64, extended grid of :p (fdtd.jl:556-581)."""
+        shp = self.field_shape("p")
+        out = np.empty(int(np.prod(shp)), np.float64)
+        self._ck(self.lib.gpi_get_illum(self.h, out.ctypes.data_as(C.POINTER(C.c_double))))
         return out.reshape(shp, order="F")
 
     def reset(self, what: int):

@@ -88,3 +88,21 @@ def allreduce_host(arrays, dist=None):
         dist.all_reduce(t)
         out.append(t.numpy().reshape(a.shape))
     return out
+
+
+def stack_illum(pa, dist=None):
+    """`stack_illums!` across workers (fdtd.jl:556-565, propagate.jl:110-117: upstream adds every worker's shots into one SharedArray):
+    after `update!`, `pa.c.illum_stack` holds this rank's supersources; one sum over the ranks completes it on every rank.  A
+    preconditioner read once per inversion (Float64, medium grid): control plane, not the data path."""
+    if dist is None or getattr(pa.c, "illum_stack", None) is None:
+        return getattr(pa.c, "illum_stack", None)
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(pa.c.illum_stack))
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+        dist.all_reduce(t)
+        pa.c.illum_stack[...] = t.cpu().numpy()
+    else:
+        dist.all_reduce(t)
+        pa.c.illum_stack[...] = t.numpy()
+    return pa.c.illum_stack

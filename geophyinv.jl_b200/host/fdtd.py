@@ -111,8 +111,12 @@ class PFdtd:
         capability): every rank builds the same experiment, owns one slab of the extended grid and
         exchanges halo planes over NVLink inside `update!`; call `init_nccl` (or `dist.attach_nccl`) first.
         `order` = `_fd_order` (2 or 4), a compile-time preference upstream (src/GeoPhyInv.jl:85-92).
-        `jobname`, `backprop_flag`, `illum_flag` are accepted for call compatibility (fdtd.jl:61-78): upstream stores the first, no
-        longer reads the second (the mode of `attrib_mod` replaced it) and allocates a dummy for the third (fdtd.jl:504-506)."""
+        `jobname`, `backprop_flag` are accepted for call compatibility (fdtd.jl:61-78): upstream stores the first and no longer reads
+        the second (the mode of `attrib_mod` replaced it).  `illum_flag` ("flag to output wavefield energy or source illumination; it can
+        be used as preconditioner during inversion", fdtd.jl:59): upstream keeps `compute_illum!` / `stack_illums!` (fdtd.jl:556-581) but
+        has their calls commented out (propagate.jl:114,236) and allocates a dummy; here the flag does what those functions say --
+        `pa.c.illum_stack` (Float64, medium grid) = sum over supersources and time steps of abs2(p) of pw 1, refreshed by every `update!`
+        (acoustic experiments)."""
         N = medium.ndims
         npml = npml_of(order)
         if order != 2 and (attrib_mod.born or zslab is not None):
@@ -219,6 +223,12 @@ class PFdtd:
         self.engine = self._make_engine(cfg)
         if c.itsnaps:
             self.engine.set_snap_steps(c.itsnaps)
+        c.illum_flag = bool(illum_flag)
+        c.illum_stack = np.zeros([len(g) for g in medium.grid], np.float64) if illum_flag else None     # fdtd.jl:177
+        if illum_flag:
+            if attrib_mod.physics != "acoustic":
+                raise NotImplementedError("illum_flag: the illumination is the energy of the pressure field (fdtd.jl:570-581), acoustic experiments only")
+            self.engine.set_illum(True)
 
         self.update_medium(medium)                                                     # fdtd.jl:240
         if attrib_mod.born:                                                            # fdtd.jl:242-244: no perturbation yet
@@ -425,6 +435,9 @@ class PFdtd:
             self._grad_dirty = True
             for name in c.mparams:
                 c.gradients[name][...] = self.engine.get_gradient(name)
+        # stack_illums! (fdtd.jl:556-565; propagate.jl:114): interior view of the stacked energy
+        if getattr(c, "illum_flag", False):
+            c.illum_stack[...] = view_inner(self.engine.get_illum(), c.npml, c.pml_faces) if len(self.local) else 0.0
         # update_datamat! + update_data! (propagate.jl:119-133, receiver.jl:17-46)
         for ipw in upa["activepw"]:
             if upa["rec_flags"][ipw - 1]:
@@ -455,6 +468,8 @@ class PFdtd:
             return c.data[ipw - 1]
         if what == "snaps":
             return [[self.engine.get_snap(ipw - 1, issp, k) for k in range(len(c.itsnaps))] for issp, _ in enumerate(self.local)]
+        if what == "illum":
+            return c.illum_stack
         if what in ("medium", "exmedium", "ageom", "srcwav"):
             return getattr(c, what)
         raise KeyError(key)

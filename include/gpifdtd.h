@@ -182,6 +182,13 @@ int  gpi_get_records(gpi_handle* h, int ipw, int issp, int field_id, float* out 
 int  gpi_get_gradient(gpi_handle* h, int param_id, float* out /* [nz,(ny),nx], summed over local shots */);
 int  gpi_get_snap(gpi_handle* h, int ipw, int issp, int isnap, float* out /* snaps_field shape */);
 int  gpi_set_snap_steps(gpi_handle* h, int nsnaps, const int32_t* itsnaps /* 1-based steps */);
+/* Source illumination, `illum_flag` of SeisForwExpt (fdtd.jl:59,73): the energy of pw 1's pressure field, illum += abs2(p) at every time
+ * step (compute_illum!, fdtd.jl:570-581; Float64 accumulation of the Float32 square) stacked over the supersources in shot order
+ * (stack_illums!, fdtd.jl:556-565).  Upstream has both calls commented out (propagate.jl:114,236) and allocates a dummy (fdtd.jl:504-506);
+ * this is the documented intent.  Acoustic experiments; zeroed at the start of every gpi_run like initialize!(pac) does (types.jl:171).
+ * gpi_get_illum returns the extended grid ([nz,(ny),nx] of :p); the host takes the interior view as stack_illums! does. */
+int  gpi_set_illum(gpi_handle* h, int on);
+int  gpi_get_illum(gpi_handle* h, double* out /* [nz,(ny),nx] */);
 int  gpi_get_field(gpi_handle* h, int ipw, int ibatch, int field_id, float* out /* field's own shape */);
 int  gpi_set_field(gpi_handle* h, int ipw, int ibatch, int field_id, const float* in);
 int  gpi_reset(gpi_handle* h, int what);

@@ -172,6 +172,16 @@ function get_snap(e::Engine, shape, ipw, issp, isnap)
     return out
 end
 
+# ---- illum_flag (src/fdtd/fdtd.jl:59,73): compute_illum! / stack_illums! (fdtd.jl:556-581; their calls are commented out upstream,
+#      propagate.jl:114,236).  set_illum! once after the constructor when pac.illum_flag; stack_illums! after mod_x_proc! -------------
+set_illum!(e::Engine, on::Bool = true) = check(e, ccall((:gpi_set_illum, LIB), Cint, (Ptr{Cvoid}, Cint), e.h, on ? 1 : 0))
+function stack_illums!(e::Engine, pac)
+    ex = Array{Float64}(undef, field_shape(pac, :p))
+    check(e, ccall((:gpi_get_illum, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), e.h, ex))
+    inner = ntuple(d -> (_fd_npml+1):(size(ex, d)-_fd_npml), ndims(ex))          # the view stack_illums! takes (fdtd.jl:562)
+    pac.illum_stack .+= view(ex, inner...)
+end
+
 # ---- one process per GPU: the ncclUniqueId travels over Julia Distributed (remotecall_fetch) -----------------------
 function nccl_unique_id()
     id = zeros(UInt8, 128)

@@ -180,6 +180,7 @@ typedef struct orc_handle {
     int32_t* itsnaps;
     char err[256];
     double last_run_s; double last_steps;
+    int illum_on; double* illum_shot; double* illum_stack;     /* compute_illum!, stack_illums! (fdtd.jl:556-581) */
 } orc_handle;
 
 static char g_err[256];
@@ -1033,9 +1034,12 @@ int orc_run(orc_handle* h, int mode, int activepw, int src_flags) {
     if (mode == GPI_MODE_FORWARD_SAVE && !h->c.store_boundary) {
         snprintf(h->err, sizeof h->err, "forward_save needs store_boundary=1 at construction (fdtd.jl:445-455)"); return 1;
     }
+    const size_t nill = h->illum_on ? h->pw[0].w[GPI_P].len : 0;
+    if (nill) memset(h->illum_stack, 0, nill * sizeof(double));           /* initialize!(pac): fill!(illum_stack, 0.0) (types.jl:171) */
     for (int issp = 0; issp < h->c.nshots; issp++) {
         reset_w2(h);
         shot_t* s1 = &h->pw[0].ss[issp];
+        if (nill) memset(h->illum_shot, 0, nill * sizeof(double));
         if (mode == GPI_MODE_ADJOINT) {      /* boundary_force_snap_tau!/v! (boundary.jl:173-212) */
             int nf; const int* bf = boundary_fields(h, &nf);
             for (int i = 0; i < nf; i++) memcpy(h->pw[0].w[bf[i]].d, s1->snap[bf[i]], h->pw[0].w[bf[i]].len * sizeof(REAL));
@@ -1060,6 +1064,11 @@ int orc_run(orc_handle* h, int mode, int activepw, int src_flags) {
             if (born) born_stress(h);
             if (mode == GPI_MODE_FORWARD_SAVE) boundary_save(h, it, issp);
             if (mode == GPI_MODE_ADJOINT && h->c.npw == 2 && (activepw & 2)) compute_gradient(h, issp, unshifted);
+            if (nill) {      /* compute_illum! (fdtd.jl:570-581; commented out at propagate.jl:236): illum[i] += abs2(p[i]), Float32 square, Float64 sum */
+                const REAL* p = h->pw[0].w[GPI_P].d;
+                OMP_FOR
+                for (long long i = 0; i < (long long)nill; i++) { const REAL sq = p[i] * p[i]; h->illum_shot[i] += (double)sq; }
+            }
             if (h->c.nsnaps > 0 && h->itsnaps)
                 for (int k = 0; k < h->c.nsnaps; k++) if (h->itsnaps[k] == it)
                     for (int ipw = 0; ipw < h->c.npw; ipw++) if ((activepw & (1 << ipw)) && h->pw[ipw].ss[issp].usnaps)
@@ -1069,6 +1078,7 @@ int orc_run(orc_handle* h, int mode, int activepw, int src_flags) {
             int nf; const int* bf = boundary_fields(h, &nf);
             for (int i = 0; i < nf; i++) { arr a = h->pw[0].w[bf[i]]; for (size_t k = 0; k < a.len; k++) s1->snap[bf[i]][k] = a.d[k] * (REAL)-1; }
         }
+        if (nill) for (size_t i = 0; i < nill; i++) h->illum_stack[i] += h->illum_shot[i];      /* stack_illums! (fdtd.jl:556-565): shot order */
         update_dstress(h, &h->pw[0]);
         update_v(h, &h->pw[0]);
         if (mode == GPI_MODE_FORWARD_SAVE)
@@ -1222,6 +1232,7 @@ int orc_destroy(orc_handle* h) {
         free(pw->ss);
     }
     free(h->itsnaps);
+    free(h->illum_shot); free(h->illum_stack);
     free(h);
     return 0;
 }
@@ -1338,6 +1349,20 @@ int orc_reset(orc_handle* h, int what) {
         if ((what & GPI_RESET_SNAPS) && s->usnaps) for (int k = 0; k < h->c.nsnaps; k++) memset(s->usnaps[k], 0, h->pw[ipw].w[h->c.snaps_field].len * sizeof(REAL));
     }
     if (what & GPI_RESET_GRADIENTS) for (int p = 0; p < GPI_NPARAM; p++) arr_zero(&h->gradients[p]);
+    return 0;
+}
+int orc_set_illum(orc_handle* h, int on) {
+    if (on && h->c.physics != GPI_ACOUSTIC) { snprintf(h->err, sizeof h->err, "the illumination is defined on the pressure field: acoustic experiments only"); return 1; }
+    if (on && !h->illum_shot) {
+        h->illum_shot = (double*)calloc(h->pw[0].w[GPI_P].len, sizeof(double));
+        h->illum_stack = (double*)calloc(h->pw[0].w[GPI_P].len, sizeof(double));
+    }
+    h->illum_on = on != 0;
+    return 0;
+}
+int orc_get_illum(orc_handle* h, double* out) {
+    if (!h->illum_stack) { snprintf(h->err, sizeof h->err, "no illumination: call orc_set_illum(h, 1) before orc_run"); return 1; }
+    memcpy(out, h->illum_stack, h->pw[0].w[GPI_P].len * sizeof(double));
     return 0;
 }
 double orc_last_run_seconds(orc_handle* h) { return h->last_run_s; }

@@ -194,6 +194,16 @@ class OracleEngine:
         self._ck(self.lib.orc_get_snap(self.h, ipw, issp, isnap, self._p(out)))
         return out.reshape(shp, order="F")
 
+    def set_illum(self, on):
+        self._ck(self.lib.orc_set_illum(self.h, 1 if on else 0))
+
+    def get_illum(self):
+        shp = self.field_shape("p")
+        out = np.empty(int(np.prod(shp)), np.float64)
+        self.lib.orc_get_illum.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self._ck(self.lib.orc_get_illum(self.h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out.reshape(shp, order="F")
+
     def reset(self, what):
         self._ck(self.lib.orc_reset(self.h, what))
 

@@ -23,11 +23,12 @@ def main():
 
     # --- forward modelling, 5 supersources over 2 ranks (chunks 0:2 and 2:5, fdtd.jl:251-255)
     kw = gallery.c2_acou2d_layered(nz=60, nx=90, nt=220, nss=5, nr=12, fq=15.0)
-    pa = O.OraclePFdtd(G.FdtdAcoustic(), **kw, nworker=world, rank=rank)
+    pa = O.OraclePFdtd(G.FdtdAcoustic(), **kw, nworker=world, rank=rank, illum_flag=True)
     assert [list(c) for c in pa.sschunks] == [[0, 1], [2, 3, 4]]
     assert list(pa.local) == [[0, 1], [2, 3, 4]][rank]
     pa.update()
     D.gather_records(pa, dist, dst=0)
+    D.stack_illum(pa, dist)              # stack_illums! over the workers (fdtd.jl:556-565)
 
     # --- the 128-byte id travels from rank 0 to everyone
     uid = D.share_unique_id(lambda: bytes(range(128)), dist)
@@ -68,8 +69,9 @@ def main():
         G.gradient(gre, me, dobse, pre)
         erre = np.linalg.norm(gesum - gre) / np.linalg.norm(gre)
         assert np.abs(gre).max() > 0 and erre < 1e-5, erre
-        ref = O.OraclePFdtd(G.FdtdAcoustic(), **kw)
+        ref = O.OraclePFdtd(G.FdtdAcoustic(), **kw, illum_flag=True)
         ref.update()
+        assert ref.c.illum_stack.max() > 0 and np.allclose(pa.c.illum_stack, ref.c.illum_stack, rtol=1e-13, atol=0), "illumination stacked over the ranks differs"
         for iss in range(5):
             a, b = pa.c.data[0][iss].d["p"], ref.c.data[0][iss].d["p"]
             assert np.abs(b).max() > 0 and np.array_equal(a, b), f"records of supersource {iss} differ"

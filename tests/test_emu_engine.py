@@ -42,6 +42,8 @@ SELECTION = [
     PARITY + "test_axis_shorter_than_npml_is_rejected_with_a_message",
     PARITY + "test_fwi_gradient_acoustic2d",                    # default path: ping-pong time levels + the fused pass of kernels2a.cuh
     PARITY + "test_born_records_match_oracle[p-rfields0]",
+    PARITY + "test_illumination_matches_oracle[acou2d]",
+    PARITY + "test_illumination_matches_oracle[fwi2d]",
     PARITY + "test_pingpong_adjoint_equals_the_copy_path[elastic]",
     "tests/test_order4.py::test_order4_elastic2d[False-vz]",
     # the engine against fixtures evaluated from the REFERENCE'S OWN KERNEL TEXT (no oracle in the loop): every physics / order / dimension

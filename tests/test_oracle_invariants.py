@@ -509,3 +509,29 @@ def test_analytic_elastic2d_line_force(G, O, order):
         err = np.sum((dat - ana) ** 2) / np.sum(ana ** 2)
         print(f"2-D elastic line force, order {order}, :vz force recorded as :{rf}: normalised squared misfit {err:.3e}")
         assert err < 2e-3
+
+
+def test_illumination_is_the_stacked_energy_of_the_pressure_snapshots(G, O):
+    """`illum_flag` (fdtd.jl:59,73): compute_illum! adds abs2(p) of pw 1 at every time step into a Float64 array, stack_illums! sums the
+    interior views over the supersources (fdtd.jl:556-581; the calls are commented out upstream, propagate.jl:114,236).  Checked against
+    the same sum formed from a snapshot of :p at EVERY step of the same run (Float32 square, Float64 sum, shot order), bit for bit;
+    a second update! starts from zero again (types.jl:171)."""
+    from geophyinv_jl_b200.host import gallery
+    from geophyinv_jl_b200.host.fdtd import view_inner
+    kw = gallery.c2_acou2d_layered(nz=40, nx=56, nt=120, nss=2, nr=6, fq=20.0)
+    tg = kw["tgrid"]
+    pa = O.OraclePFdtd(G.FdtdAcoustic(), **kw, illum_flag=True, snaps_field="p", tsnaps=list(tg.values))
+    assert pa.c.itsnaps == list(range(1, 121))
+    for rep in range(2):
+        pa.update()
+        want = np.zeros(pa.c.illum_stack.shape, np.float64)
+        for shot in pa["snaps", 1]:
+            e = np.zeros_like(want)
+            for snap in shot:
+                inner = view_inner(snap, pa.c.npml, pa.c.pml_faces)
+                e += (inner * inner).astype(np.float64)               # Float32 square, Float64 sum
+            want += e
+        assert want.max() > 0 and pa.c.illum_stack.shape == tuple(len(g) for g in kw["medium"].grid)
+        assert np.array_equal(pa["illum"], want), f"update {rep}"
+    with pytest.raises(Exception):
+        O.OraclePFdtd(G.FdtdElastic(), **gallery.elastic2d(nt=5), illum_flag=True)

@@ -462,6 +462,46 @@ def test_engine_matches_the_stokes_solution(G, monkeypatch, tma):
 
 
 # --------------------------------------------------------------------------------------------------
+# illum_flag: source illumination (compute_illum! / stack_illums!, fdtd.jl:556-581)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["acou2d", "acou3d", "fwi2d"])
+def test_illumination_matches_oracle(G, O, case):
+    """Sum over time steps and supersources of abs2(p) of pw 1 (Float32 square, Float64 accumulation in shot order): the engine's k_illum /
+    k_axpy1d against the oracle bit for bit -- three supersources in batches of two (2-D; launch by launch, captured, replayed), 3-D, and
+    inside gradient! where every update! (forward_save, then adjoint with the ping-pong levels) refreshes it."""
+    from geophyinv_jl_b200.host import gallery
+    if case == "fwi2d":
+        kw, true = gallery.c4_fwi2d(nz=44, nx=60, nt=151, nss=3, nr=10, fq=12.0)
+        pt = O.OraclePFdtd(G.FdtdAcoustic(), **{**kw, "medium": true})
+        pt.update()
+        dobs = [d.copy() for d in pt.c.data[0]]
+        pg = G.PFdtd(G.FdtdAcoustic("forward_save"), **kw, shot_batch=2, illum_flag=True)
+        po = O.OraclePFdtd(G.FdtdAcoustic("forward_save"), **kw, illum_flag=True)
+        m = pg.get_modelvector()
+        for rep in range(3):
+            gg, go = np.zeros_like(m), np.zeros_like(m)
+            G.gradient(gg, m, dobs, pg); G.gradient(go, m, dobs, po)
+            assert np.array_equal(gg, go)
+            assert po.c.illum_stack.max() > 0 and np.array_equal(pg.c.illum_stack, po.c.illum_stack), f"run {rep}"
+        return
+    if case == "acou2d":
+        kw, extra = gallery.c2_acou2d_layered(nz=60, nx=80, nt=200, nss=3, nr=8, fq=15.0), {"shot_batch": 2}
+    else:
+        kw, extra = gallery.acou3d(n=20, nt=90, nr=6), {}
+    pg = G.SeisForwExpt(G.FdtdAcoustic(), **kw, **extra, illum_flag=True)
+    po = O.OraclePFdtd(G.FdtdAcoustic(), **kw, illum_flag=True)
+    po.update()
+    assert po.c.illum_stack.max() > 0 and po.c.illum_stack.dtype == np.float64
+    for rep in range(3):
+        pg.update()
+        assert np.array_equal(pg["illum"], po["illum"]), f"run {rep}"
+    worst, exact = compare_records(pg, po)
+    assert exact
+    with pytest.raises(Exception):
+        G.SeisForwExpt(G.FdtdElastic(), **gallery.elastic2d(nt=5), illum_flag=True)
+
+
+# --------------------------------------------------------------------------------------------------
 # degenerate sizes and placements
 # --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("case", ["nt1", "nt2", "nr1", "corners", "rigid_box_no_cpml", "three_shots_batch2"])
