@@ -42,6 +42,10 @@ if want("elastic3d"):
     os.environ["GPI_SCALAR3D"] = "1"
     run("3-D elastic scalar kernels", G.SeisForwExpt(G.FdtdElastic(), **gallery.c3_elastic3d(n=18, nt=8, nr=4, fq=40.0)))
     del os.environ["GPI_TMA3"], os.environ["GPI_SCALAR3D"]
+if want("illum"):      # illum_flag: k_illum per step (Float64 accumulators per resident shot), k_axpy1d stack; 2-D launches carry the programmatic-launch attribute
+    pa = G.SeisForwExpt(G.FdtdAcoustic(), **gallery.c2_acou2d_layered(nz=60, nx=75, nt=40, nss=3, nr=8, fq=20.0), shot_batch=2, illum_flag=True)
+    run("2-D acoustic with illumination", pa)
+    assert np.isfinite(pa["illum"]).all() and pa["illum"].max() > 0
 if want("gradient"):
     for order in (2, 4):
         kw, true = gallery.c4_fwi2d(nz=40, nx=50, nt=60, nss=3, nr=8, fq=15.0)
