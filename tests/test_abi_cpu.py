@@ -246,3 +246,16 @@ def test_julia_shim_is_loadable_as_a_submodule():
         hv = int(re.search(r"#define " + name + r" (0x[0-9a-fA-F]+)", hdr).group(1), 16)
         jv = int(re.search(r"const " + name + r" = Int32\((0x[0-9a-fA-F]+)\)", shim).group(1), 16)
         assert hv == jv
+
+
+def test_every_environment_switch_is_documented():
+    """Every GPI_* variable the library or the binding reads appears in INTEGRATION.md's switch table."""
+    import re
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    names = set()
+    for rel in ("geophyinv.jl_b200/csrc/engine.cu", "geophyinv.jl_b200/engine.py", "geophyinv.jl_b200/host/fdtd.py"):
+        txt = open(os.path.join(ROOT, rel)).read()
+        names |= set(re.findall(r'getenv\("(GPI_[A-Z0-9_]+)"\)', txt)) | set(re.findall(r'environ(?:\.get)?[\[(]"(GPI_[A-Z0-9_]+)"', txt))
+    assert len(names) >= 15
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, missing
